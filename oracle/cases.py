@@ -1,0 +1,129 @@
+"""Deterministic synthetic inputs shared by the golden generator, the tests, smoke() and bench.py.
+
+TEST / BENCH INFRASTRUCTURE.  Nothing here touches /root/reference; everything is a pure function of
+a seed so the GPU box can regenerate the same tensors the golden vectors were produced from
+(coords in [-1,1]^d, latent grid = meshgrid(linspace(-1,1,H),..., indexing='ij')
+as reference src/datasets/data_processor.py:289-307, features ~ N(0,1))."""
+from __future__ import annotations
+
+import math
+from typing import Dict, List
+
+import torch
+
+
+def latent_grid(size) -> torch.Tensor:
+    axes = [torch.linspace(-1.0, 1.0, s, dtype=torch.float32) for s in size]
+    return torch.stack(torch.meshgrid(*axes, indexing="ij"), dim=-1).reshape(-1, len(size)).contiguous()
+
+
+def uniform_points(n: int, d: int, seed: int) -> torch.Tensor:
+    g = torch.Generator().manual_seed(seed)
+    return (torch.rand(n, d, generator=g, dtype=torch.float32) * 2.0 - 1.0).contiguous()
+
+
+def clustered_points(n: int, d: int, seed: int, sigma: float = 0.15) -> torch.Tensor:
+    """Airfoil-like density: half uniform, half N(0, sigma^2) around the origin, clipped to the box."""
+    g = torch.Generator().manual_seed(seed)
+    a = torch.rand(n // 2, d, generator=g, dtype=torch.float32) * 2.0 - 1.0
+    b = (torch.randn(n - n // 2, d, generator=g, dtype=torch.float32) * sigma).clamp_(-1.0, 1.0)
+    return torch.cat([a, b], dim=0).contiguous()
+
+
+def normal(shape, seed: int) -> torch.Tensor:
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g, dtype=torch.float32)
+
+
+def synth_params(shapes: Dict[str, List[int]], seed: int) -> Dict[str, torch.Tensor]:
+    """Deterministic parameter values for a given {state_dict key: shape} table (key order matters):
+    matrices U(-1,1)/sqrt(fan_in), biases U(-1,1)*0.1, norm gains 1 + 0.1*U(-1,1)."""
+    g = torch.Generator().manual_seed(seed)
+    out = {}
+    for k, shp in shapes.items():
+        u = torch.rand(*shp, generator=g, dtype=torch.float32) * 2.0 - 1.0
+        if k.endswith("norm.weight"):
+            out[k] = 1.0 + 0.1 * u
+        elif k.endswith(".bias"):
+            out[k] = 0.1 * u
+        else:
+            fan_in = int(math.prod(shp[1:])) if len(shp) > 1 else shp[0]
+            out[k] = u / math.sqrt(max(fan_in, 1))
+    return out
+
+
+# ---- model cases (hyper-parameters only; tensors come from the generators above) ----------------
+CASES = {
+    # tiny 2-D fx model: head_dim 32, Dp == Dh (Identity in/out proj)
+    "tiny2d": dict(latent=(8, 8), n=300, d=2, B=2, cin=2, cout=3, seed=1,
+                   magno=dict(coord_dim=2, radius=0.35, hidden_size=16, mlp_layers=3, lifting_channels=16,
+                              neighbor_search_method="native"),
+                   transformer=dict(patch_size=2, hidden_size=64, num_layers=3, ffn_multiplier=2),
+                   attn=dict(num_heads=2, num_kv_heads=2)),
+    # tiny 3-D fx, two scales with learned scale weights, Dp=48 != Dh=64 (input/output proj), 5 layers
+    "tiny3d": dict(latent=(4, 4, 4), n=400, d=3, B=2, cin=3, cout=1, seed=2,
+                   magno=dict(coord_dim=3, radius=0.6, hidden_size=16, mlp_layers=2, lifting_channels=6,
+                              scales=[1.0, 1.5], use_scale_weights=True, neighbor_search_method="native"),
+                   transformer=dict(patch_size=2, hidden_size=64, num_layers=5, ffn_multiplier=2),
+                   attn=dict(num_heads=2, num_kv_heads=2)),
+    # vx: per-sample meshes and precomputed per-sample graphs
+    "vx2d": dict(latent=(8, 8), n=250, d=2, B=3, cin=3, cout=1, seed=3, vx=True,
+                 magno=dict(coord_dim=2, radius=0.4, hidden_size=16, mlp_layers=3, lifting_channels=16,
+                            precompute_edges=True, neighbor_search_method="native"),
+                 transformer=dict(patch_size=2, hidden_size=64, num_layers=2, ffn_multiplier=2),
+                 attn=dict(num_heads=2, num_kv_heads=2)),
+    # no attention (mean reduce), no geo-embedding
+    "plain2d": dict(latent=(8, 8), n=300, d=2, B=2, cin=1, cout=1, seed=4,
+                    magno=dict(coord_dim=2, radius=0.35, hidden_size=16, mlp_layers=3, lifting_channels=16,
+                               use_attention=False, use_geoembed=False, neighbor_search_method="native"),
+                    transformer=dict(patch_size=2, hidden_size=64, num_layers=1, ffn_multiplier=2),
+                    attn=dict(num_heads=2, num_kv_heads=2)),
+    # BASELINE cfg-2 geometry (Poisson-Gauss hyper-parameters, config/examples/time_indep/poisson_gauss.json)
+    "cfg2": dict(latent=(64, 64), n=9216, d=2, B=2, cin=1, cout=1, seed=0, summary_only=True,
+                 magno=dict(coord_dim=2, radius=0.033, hidden_size=64, mlp_layers=3, lifting_channels=64,
+                            neighbor_search_method="native"),
+                 transformer=dict(patch_size=2, hidden_size=256, num_layers=3, ffn_multiplier=4),
+                 attn=dict(num_heads=8, num_kv_heads=8)),
+}
+
+
+def case_inputs(name: str):
+    c = CASES[name]
+    lat = latent_grid(c["latent"])
+    if c.get("vx"):
+        x = torch.stack([clustered_points(c["n"], c["d"], 100 + c["seed"] * 10 + b) for b in range(c["B"])])
+    else:
+        x = uniform_points(c["n"], c["d"], c["seed"])
+    pn = normal((c["B"], c["n"], c["cin"]), 1000 + c["seed"])
+    tgt = normal((c["B"], c["n"], c["cout"]), 2000 + c["seed"])
+    return lat, x, pn, tgt
+
+
+# ---- neighbour-search cases ---------------------------------------------------------------------
+def nbr_case(name: str):
+    """(data, queries, radius).  'lattice*' cases sit on dyadic coordinates so that distances equal to
+    the radius are exact in fp32 (ties well defined in every back-end); they also contain duplicate
+    points and queries with no neighbour."""
+    if name == "rand2d":
+        return uniform_points(2000, 2, 11), latent_grid((16, 16)), 0.11
+    if name == "rand3d":
+        return uniform_points(3000, 3, 12), latent_grid((6, 6, 6)), 0.3
+    if name == "dec2d":
+        return latent_grid((16, 16)), uniform_points(1500, 2, 13), 0.15
+    if name == "lattice2d":
+        ax = torch.arange(-8, 9, dtype=torch.float32) * 0.125
+        pts = torch.stack(torch.meshgrid(ax, ax, indexing="ij"), -1).reshape(-1, 2)
+        pts = torch.cat([pts, pts[::7]], dim=0)                     # duplicates
+        q = torch.cat([pts[::3] * 1.0, torch.tensor([[5.0, 5.0], [-3.0, 0.0]])], dim=0)  # + empty rows
+        return pts.contiguous(), q.contiguous(), 0.25
+    if name == "lattice3d":
+        ax = torch.arange(-3, 4, dtype=torch.float32) * 0.25
+        pts = torch.stack(torch.meshgrid(ax, ax, ax, indexing="ij"), -1).reshape(-1, 3)
+        q = torch.cat([pts[::5], torch.tensor([[4.0, 4.0, 4.0]])], dim=0)
+        return pts.contiguous(), q.contiguous(), 0.5
+    if name == "empty":
+        return uniform_points(50, 2, 14), uniform_points(20, 2, 15) + 10.0, 0.1
+    raise KeyError(name)
+
+
+NBR_CASES = ["rand2d", "rand3d", "dec2d", "lattice2d", "lattice3d", "empty"]
