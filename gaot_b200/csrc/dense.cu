@@ -1,0 +1,502 @@
+// fp32 dense kernels of the parity path: tiled FFMA GEMM with fused bias / broadcast-add /
+// activation epilogue and split-K, column sums, activation backward, RMSNorm, SwiGLU gate,
+// patchify permutations, MSE and AdamW.
+// Reference: src/model/layers/mlp.py:283-337, src/model/layers/attn.py:133-172, src/model/gaot.py:182-231,
+//            src/core/base_trainer.py:71, src/utils/optimizers.py:196,252-255.
+#include "common.cuh"
+#include "../../include/gaot_b200.h"
+
+namespace {
+
+constexpr int GEMM_THREADS = 256;
+constexpr int BK = 16;
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+    if (act == GAOT_ACT_GELU) return gelu_erf(v);
+    if (act == GAOT_ACT_RELU) return fmaxf(v, 0.f);
+    return v;
+}
+
+// Stage a [ROWS x BK] operand tile into smem as tile[k][row].
+//   kcontig = true : src[row*ld + k]   (row-major [rows, K], e.g. activations or nn.Linear weights)
+//   kcontig = false: src[k*ld + row]   ([K, rows])
+template <int ROWS>
+struct TileLoader {
+    static constexpr int VECS = ROWS * BK / 4;                 // float4 slots per tile
+    static constexpr int ITERS = (VECS + GEMM_THREADS - 1) / GEMM_THREADS;
+    float4 reg[ITERS];
+
+    __device__ __forceinline__ void fetch(const float* __restrict__ src, int64_t ld, bool kcontig, bool vec_ok,
+                                          int64_t row0, int64_t nrows, int64_t k0, int64_t kend) {
+#pragma unroll
+        for (int it = 0; it < ITERS; ++it) {
+            const int s = threadIdx.x + it * GEMM_THREADS;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (s >= VECS) { reg[it] = v; continue; }
+            if (kcontig) {
+                const int r = s / (BK / 4), k4 = (s % (BK / 4)) * 4;
+                const int64_t row = row0 + r, k = k0 + k4;
+                if (row < nrows) {
+                    const float* p = src + row * ld + k;
+                    if (vec_ok && k + 3 < kend) v = __ldg(reinterpret_cast<const float4*>(p));
+                    else {
+                        if (k < kend) v.x = __ldg(p);
+                        if (k + 1 < kend) v.y = __ldg(p + 1);
+                        if (k + 2 < kend) v.z = __ldg(p + 2);
+                        if (k + 3 < kend) v.w = __ldg(p + 3);
+                    }
+                }
+            } else {
+                const int kk = s / (ROWS / 4), r4 = (s % (ROWS / 4)) * 4;
+                const int64_t row = row0 + r4, k = k0 + kk;
+                if (k < kend) {
+                    const float* p = src + k * ld + row;
+                    if (vec_ok && row + 3 < nrows) v = __ldg(reinterpret_cast<const float4*>(p));
+                    else {
+                        if (row < nrows) v.x = __ldg(p);
+                        if (row + 1 < nrows) v.y = __ldg(p + 1);
+                        if (row + 2 < nrows) v.z = __ldg(p + 2);
+                        if (row + 3 < nrows) v.w = __ldg(p + 3);
+                    }
+                }
+            }
+            reg[it] = v;
+        }
+    }
+    __device__ __forceinline__ void commit(float (*tile)[ROWS + 4], bool kcontig) const {
+#pragma unroll
+        for (int it = 0; it < ITERS; ++it) {
+            const int s = threadIdx.x + it * GEMM_THREADS;
+            if (s >= VECS) continue;
+            if (kcontig) {
+                const int r = s / (BK / 4), k4 = (s % (BK / 4)) * 4;
+                tile[k4 + 0][r] = reg[it].x; tile[k4 + 1][r] = reg[it].y;
+                tile[k4 + 2][r] = reg[it].z; tile[k4 + 3][r] = reg[it].w;
+            } else {
+                const int kk = s / (ROWS / 4), r4 = (s % (ROWS / 4)) * 4;
+                *reinterpret_cast<float4*>(&tile[kk][r4]) = reg[it];
+            }
+        }
+    }
+};
+
+struct GemmArgs {
+    const float* A; const float* B; float* C;
+    int64_t M, N, K, lda, ldb, ldc;
+    int transA, transB;
+    const float* bias; const float* add; int64_t add_rows, ldadd;
+    int act; float* pre; int accumulate; int splits;
+    int vecA, vecB;
+};
+
+template <int BM, int BN, int TM, int TN>
+__global__ void __launch_bounds__(GEMM_THREADS) gemm_f32_kernel(const GemmArgs g) {
+    static_assert((BM / TM) * (BN / TN) == GEMM_THREADS, "thread tiling");
+    static_assert(TM == 8, "row micro-tile is two groups of 4");
+    __shared__ __align__(16) float As[BK][BM + 4];
+    __shared__ __align__(16) float Bs[BK][BN + 4];
+    const int tx = threadIdx.x % (BN / TN), ty = threadIdx.x / (BN / TN);
+    const int64_t m0 = (int64_t)blockIdx.x * BM, n0 = (int64_t)blockIdx.y * BN;
+    // K range of this split
+    const int64_t ktiles = (g.K + BK - 1) / BK;
+    const int64_t per = (ktiles + g.splits - 1) / g.splits;
+    const int64_t kbeg = (int64_t)blockIdx.z * per * BK;
+    const int64_t kend = min(g.K, kbeg + per * BK);
+
+    float acc[TM][TN];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+    TileLoader<BM> la;
+    TileLoader<BN> lb;
+    const bool akc = !g.transA, bkc = g.transB != 0;
+    if (kbeg < kend) {
+        la.fetch(g.A, g.lda, akc, g.vecA, m0, g.M, kbeg, kend);
+        lb.fetch(g.B, g.ldb, bkc, g.vecB, n0, g.N, kbeg, kend);
+    }
+    for (int64_t k0 = kbeg; k0 < kend; k0 += BK) {
+        la.commit(As, akc);
+        lb.commit(Bs, bkc);
+        __syncthreads();
+        if (k0 + BK < kend) {
+            la.fetch(g.A, g.lda, akc, g.vecA, m0, g.M, k0 + BK, kend);
+            lb.fetch(g.B, g.ldb, bkc, g.vecB, n0, g.N, k0 + BK, kend);
+        }
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+            float a[TM], b[TN];
+            const float4 a0 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&As[k][BM / 2 + ty * 4]);
+            a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+            if constexpr (TN == 8) {
+                const float4 b0 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+                const float4 b1 = *reinterpret_cast<const float4*>(&Bs[k][BN / 2 + tx * 4]);
+                b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
+            } else if constexpr (TN == 4) {
+                const float4 b0 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+                b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w;
+            } else {
+#pragma unroll
+                for (int j = 0; j < TN; ++j) b[j] = Bs[k][tx * TN + j];
+            }
+#pragma unroll
+            for (int i = 0; i < TM; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+
+    const bool first = blockIdx.z == 0;
+    const bool atomic = g.splits > 1;
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+        const int64_t m = m0 + ((i < 4) ? ty * 4 + i : BM / 2 + ty * 4 + (i - 4));
+        if (m >= g.M) continue;
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+            const int64_t n = n0 + ((TN == 8) ? ((j < 4) ? tx * 4 + j : BN / 2 + tx * 4 + (j - 4)) : tx * TN + j);
+            if (n >= g.N) continue;
+            float v = acc[i][j];
+            if (first) {
+                if (g.bias) v += __ldg(g.bias + n);
+                if (g.add) v += __ldg(g.add + (m % g.add_rows) * g.ldadd + n);
+            }
+            float* cp = g.C + m * g.ldc + n;
+            if (atomic) { atomicAdd(cp, v); continue; }
+            if (g.pre) g.pre[m * g.ldc + n] = v;
+            v = apply_act(v, g.act);
+            if (g.accumulate) v += *cp;
+            *cp = v;
+        }
+    }
+}
+
+template <int BM, int BN, int TM, int TN>
+int launch_gemm(GemmArgs& g, cudaStream_t st) {
+    const int64_t gm = (g.M + BM - 1) / BM, gn = (g.N + BN - 1) / BN;
+    const int64_t tiles = gm * gn, ktiles = (g.K + BK - 1) / BK;
+    int splits = 1;
+    const bool can_split = (g.act == GAOT_ACT_NONE) && !g.pre && (g.ldc == g.N);
+    if (can_split && tiles < 148 && ktiles >= 16) {
+        splits = (int)((296 + tiles - 1) / tiles);
+        if (splits > ktiles / 8) splits = (int)(ktiles / 8);
+        if (splits < 1) splits = 1;
+        if (splits > 64) splits = 64;
+    }
+    g.splits = splits;
+    if (splits > 1 && !g.accumulate) GAOT_CHECK(cudaMemsetAsync(g.C, 0, sizeof(float) * (size_t)(g.M * g.N), st));
+    if (gn > 65535 || gm > 0x7fffffffLL) return GAOT_E_BADARG;
+    dim3 grid((unsigned)gm, (unsigned)gn, (unsigned)splits);
+    gemm_f32_kernel<BM, BN, TM, TN><<<grid, GEMM_THREADS, 0, st>>>(g);
+    GAOT_RETURN_LAST();
+}
+
+// ---- small pointwise / reduction kernels ----------------------------------------------------------
+__global__ void col_sum_kernel(const float* __restrict__ x, int64_t M, int64_t N, float* __restrict__ out, int64_t rows_per) {
+    // grid (ceil(N/32), row-slices); block 32 x 8: threadIdx.x -> column (coalesced), threadIdx.y -> row lane
+    __shared__ float red[8][33];
+    const int64_t n = (int64_t)blockIdx.x * 32 + threadIdx.x;
+    const int64_t r0 = (int64_t)blockIdx.y * rows_per, r1 = min(M, r0 + rows_per);
+    float s = 0.f;
+    if (n < N)
+        for (int64_t r = r0 + threadIdx.y; r < r1; r += 8) s += __ldg(x + r * N + n);
+    red[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0 && n < N) {
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x];
+        atomicAdd(out + n, t);
+    }
+}
+
+__global__ void act_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ pre, float* __restrict__ dx,
+                               int64_t n, int act) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float p = pre[i];
+        const float gr = (act == GAOT_ACT_GELU) ? gelu_erf_grad(p) : ((act == GAOT_ACT_RELU) ? (p > 0.f ? 1.f : 0.f) : 1.f);
+        dx[i] = dy[i] * gr;
+    }
+}
+
+constexpr int NORM_MAXE = 64;   // per-lane elements: D <= 2048
+
+__global__ void __launch_bounds__(256) rmsnorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                          float* __restrict__ y, float* __restrict__ rstd,
+                                                          int64_t rows, int D, float eps) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp; r < rows; r += nwarps) {
+        const float* xp = x + r * D;
+        float ss = 0.f;
+        for (int c = lane; c < D; c += 32) { const float v = xp[c]; ss = fmaf(v, v, ss); }
+        ss = warp_sum(ss);
+        const float rs = rsqrtf(ss / (float)D + eps);
+        if (lane == 0) rstd[r] = rs;
+        float* yp = y + r * D;
+        for (int c = lane; c < D; c += 32) yp[c] = (xp[c] * rs) * __ldg(gamma + c);
+    }
+}
+
+__global__ void __launch_bounds__(256) rmsnorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                          const float* __restrict__ gamma, const float* __restrict__ rstd,
+                                                          float* __restrict__ dx, float* __restrict__ dgamma,
+                                                          int64_t rows, int D) {
+    extern __shared__ float sdg[];                 // [D] per-CTA partial of dgamma
+    for (int c = threadIdx.x; c < D; c += blockDim.x) sdg[c] = 0.f;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    float dg[NORM_MAXE];
+#pragma unroll
+    for (int k = 0; k < NORM_MAXE; ++k) dg[k] = 0.f;
+    for (int64_t r = warp; r < rows; r += nwarps) {
+        const float* xp = x + r * D;
+        const float* gp = dy + r * D;
+        const float rs = rstd[r];
+        float dot = 0.f;
+        for (int c = lane; c < D; c += 32) dot = fmaf(gp[c] * __ldg(gamma + c), xp[c], dot);
+        dot = warp_sum(dot);
+        const float coef = dot * rs * rs * rs / (float)D;
+        float* dxp = dx + r * D;
+#pragma unroll
+        for (int k = 0; k < NORM_MAXE; ++k) {
+            const int c = lane + k * 32;
+            if (c < D) {
+                const float gy = gp[c], xv = xp[c];
+                dxp[c] = gy * __ldg(gamma + c) * rs - xv * coef;
+                dg[k] = fmaf(gy, xv * rs, dg[k]);
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < NORM_MAXE; ++k) {
+        const int c = lane + k * 32;
+        if (c < D) atomicAdd(&sdg[c], dg[k]);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < D; c += blockDim.x) atomicAdd(dgamma + c, sdg[c]);
+}
+
+__global__ void swiglu_fwd_kernel(const float* __restrict__ ab, float* __restrict__ u, int64_t rows, int64_t F) {
+    const int64_t total = rows * F;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / F, c = i - r * F;
+        const float a = ab[r * 2 * F + c], b = ab[r * 2 * F + F + c];
+        u[i] = (a / (1.f + expf(-a))) * b;
+    }
+}
+__global__ void swiglu_bwd_kernel(const float* __restrict__ du, const float* __restrict__ ab, float* __restrict__ dab,
+                                  int64_t rows, int64_t F) {
+    const int64_t total = rows * F;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / F, c = i - r * F;
+        const float a = ab[r * 2 * F + c], b = ab[r * 2 * F + F + c], gu = du[i];
+        const float sg = 1.f / (1.f + expf(-a));
+        dab[r * 2 * F + c] = gu * b * (sg + a * sg * (1.f - sg));
+        dab[r * 2 * F + F + c] = gu * a * sg;
+    }
+}
+
+__global__ void patch_permute_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t B, int dims,
+                                     int64_t H, int64_t W, int64_t D, int64_t P, int64_t C, int to_tokens) {
+    // iterate over token-layout elements; channel fastest -> both sides move contiguous C-runs
+    const int64_t nodes = H * W * (dims == 3 ? D : 1);
+    const int64_t total = B * nodes * C;
+    const int64_t pw = W / P, pd = (dims == 3) ? D / P : 1;
+    const int64_t pv = (dims == 3) ? P * P * P : P * P;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t c = i % C;
+        int64_t r = i / C;
+        const int64_t pin = r % pv; r /= pv;          // position inside the patch
+        const int64_t t = r % (nodes / pv);            // token
+        const int64_t b = r / (nodes / pv);
+        int64_t node;
+        if (dims == 2) {
+            const int64_t ti = t / pw, tj = t % pw, pi = pin / P, pj = pin % P;
+            node = (ti * P + pi) * W + (tj * P + pj);
+        } else {
+            const int64_t tk = t % pd, tj = (t / pd) % pw, ti = t / (pd * pw);
+            const int64_t pk = pin % P, pj = (pin / P) % P, pi = pin / (P * P);
+            node = ((ti * P + pi) * W + (tj * P + pj)) * D + (tk * P + pk);
+        }
+        const int64_t g = (b * nodes + node) * C + c;
+        if (to_tokens) out[i] = in[g]; else out[g] = in[i];
+    }
+}
+
+__global__ void __launch_bounds__(256) mse_kernel(const float* __restrict__ pred, const float* __restrict__ target,
+                                                  float* __restrict__ loss, float* __restrict__ dpred, int64_t n,
+                                                  float inv_n, float gcoef) {
+    __shared__ float red[8];
+    float s = 0.f;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float df = pred[i] - target[i];
+        s = fmaf(df, df, s);
+        if (dpred) dpred[i] = df * gcoef;
+    }
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float t = (threadIdx.x < 8) ? red[threadIdx.x] : 0.f;
+        t = warp_sum(t);
+        if (threadIdx.x == 0) atomicAdd(loss, t * inv_n);
+    }
+}
+
+__global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                             float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps, float wd,
+                             float inv_bc1, float inv_sqrt_bc2, float gscale) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float gr = g[i] * gscale;
+        float pv = p[i] * (1.f - lr * wd);
+        const float mv = b1 * m[i] + (1.f - b1) * gr;
+        const float vv = b2 * v[i] + (1.f - b2) * gr * gr;
+        m[i] = mv; v[i] = vv;
+        const float denom = sqrtf(vv) * inv_sqrt_bc2 + eps;
+        pv -= (lr * inv_bc1) * (mv / denom);
+        p[i] = pv;
+    }
+}
+
+__global__ void rollout_kernel(const float* __restrict__ pred, const float* __restrict__ u_in, float* __restrict__ u_next,
+                               int64_t rows, int C, float dt, int mode, const float* __restrict__ um,
+                               const float* __restrict__ us, const float* __restrict__ sm, const float* __restrict__ ss) {
+    const int64_t total = rows * C;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        if (mode == 0) { u_next[i] = pred[i]; continue; }
+        const float ucur = u_in[i] * us[c] + um[c];
+        const float inc = pred[i] * ss[c] + sm[c];
+        const float un = ucur + (mode == 2 ? dt * inc : inc);
+        u_next[i] = (un - um[c]) / us[c];
+    }
+}
+
+inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace
+
+GAOT_API int gaot_abi_version(void) { return 1; }
+
+static long long g_launches = 0;
+extern "C" __attribute__((visibility("default"))) long long gaot_launch_counter_add(long long n) {
+    return __atomic_add_fetch(&g_launches, n, __ATOMIC_RELAXED);
+}
+GAOT_API long long gaot_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
+
+GAOT_API int gaot_gemm_f32(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K, int64_t lda,
+                           int64_t ldb, int64_t ldc, int transA, int transB, const float* bias, const float* add,
+                           int64_t add_rows, int64_t ldadd, int act, float* pre, int accumulate, void* stream) {
+    if (!A || !B || !C || M < 0 || N < 0 || K < 0) return GAOT_E_BADARG;
+    if (add && (add_rows < 1 || ldadd < N)) return GAOT_E_BADARG;
+    if (act < 0 || act > 2 || ldc < N) return GAOT_E_BADARG;
+    if (M == 0 || N == 0) return 0;
+    GemmArgs g{A, B, C, M, N, K, lda, ldb, ldc, transA, transB, bias, add, add ? add_rows : 1, ldadd, act, pre,
+               accumulate, 1, 0, 0};
+    g.vecA = al16(A) && (lda % 4 == 0);
+    g.vecB = al16(B) && (ldb % 4 == 0);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (N <= 16) return launch_gemm<256, 16, 8, 2>(g, st);
+    if (N <= 64) return launch_gemm<128, 64, 8, 4>(g, st);
+    return launch_gemm<128, 128, 8, 8>(g, st);
+}
+
+GAOT_API int gaot_col_sum(const float* x, int64_t M, int64_t N, float* out, int accumulate, void* stream) {
+    if (!x || !out || M < 0 || N < 1) return GAOT_E_BADARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!accumulate) GAOT_CHECK(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)N, st));
+    if (M == 0) return 0;
+    const int64_t gx = (N + 31) / 32;
+    int64_t slices = (148 * 8 + gx - 1) / gx;
+    if (slices > (M + 63) / 64) slices = (M + 63) / 64;
+    if (slices < 1) slices = 1;
+    const int64_t rows_per = (M + slices - 1) / slices;
+    col_sum_kernel<<<dim3((unsigned)gx, (unsigned)slices), dim3(32, 8), 0, st>>>(x, M, N, out, rows_per);
+    GAOT_RETURN_LAST();
+}
+
+GAOT_API int gaot_act_bwd(const float* dy, const float* pre, float* dx, int64_t n, int act, void* stream) {
+    if (!dy || !pre || !dx || n < 0 || act < 0 || act > 2) return GAOT_E_BADARG;
+    if (n == 0) return 0;
+    act_bwd_kernel<<<gaot_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(dy, pre, dx, n, act);
+    GAOT_RETURN_LAST();
+}
+
+GAOT_API int gaot_rmsnorm_fwd(const float* x, const float* gamma, float* y, float* rstd, int64_t rows, int64_t D,
+                              float eps, void* stream) {
+    if (!x || !gamma || !y || !rstd || rows < 0 || D < 1) return GAOT_E_BADARG;
+    if (rows == 0) return 0;
+    rmsnorm_fwd_kernel<<<gaot_grid(rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(x, gamma, y, rstd, rows, (int)D, eps);
+    GAOT_RETURN_LAST();
+}
+
+GAOT_API int gaot_rmsnorm_bwd(const float* dy, const float* x, const float* gamma, const float* rstd, float* dx,
+                              float* dgamma, int64_t rows, int64_t D, void* stream) {
+    if (!dy || !x || !gamma || !rstd || !dx || !dgamma || rows < 0 || D < 1 || D > 32 * NORM_MAXE) return GAOT_E_BADARG;
+    if (rows == 0) return 0;
+    int grid = gaot_grid(rows * 32, 256, 2);
+    rmsnorm_bwd_kernel<<<grid, 256, sizeof(float) * (size_t)D, (cudaStream_t)stream>>>(dy, x, gamma, rstd, dx, dgamma,
+                                                                                       rows, (int)D);
+    GAOT_RETURN_LAST();
+}
+
+GAOT_API int gaot_swiglu_fwd(const float* ab, float* u, int64_t rows, int64_t F, void* stream) {
+    if (!ab || !u || rows < 0 || F < 1) return GAOT_E_BADARG;
+    if (rows == 0) return 0;
+    swiglu_fwd_kernel<<<gaot_grid(rows * F, 256), 256, 0, (cudaStream_t)stream>>>(ab, u, rows, F);
+    GAOT_RETURN_LAST();
+}
+GAOT_API int gaot_swiglu_bwd(const float* du, const float* ab, float* dab, int64_t rows, int64_t F, void* stream) {
+    if (!du || !ab || !dab || rows < 0 || F < 1) return GAOT_E_BADARG;
+    if (rows == 0) return 0;
+    swiglu_bwd_kernel<<<gaot_grid(rows * F, 256), 256, 0, (cudaStream_t)stream>>>(du, ab, dab, rows, F);
+    GAOT_RETURN_LAST();
+}
+
+GAOT_API int gaot_patch_permute(const float* in, float* out, int64_t B, int dims, int64_t H, int64_t W, int64_t D,
+                                int64_t P, int64_t C, int to_tokens, void* stream) {
+    if (!in || !out || B < 1 || (dims != 2 && dims != 3) || P < 1 || C < 1) return GAOT_E_BADARG;
+    if (H % P || W % P || (dims == 3 && D % P)) return GAOT_E_BADARG;
+    const int64_t total = B * H * W * (dims == 3 ? D : 1) * C;
+    patch_permute_kernel<<<gaot_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(in, out, B, dims, H, W, D, P, C, to_tokens);
+    GAOT_RETURN_LAST();
+}
+
+GAOT_API int gaot_mse_fwd_bwd(const float* pred, const float* target, float* loss, float* dpred, int64_t n, float gscale,
+                              void* stream) {
+    if (!pred || !target || !loss || n < 1) return GAOT_E_BADARG;
+    const float inv_n = (float)(1.0 / (double)n);
+    mse_kernel<<<gaot_grid(n, 256, 4), 256, 0, (cudaStream_t)stream>>>(pred, target, loss, dpred, n, inv_n,
+                                                                       (float)(2.0 / (double)n) * gscale);
+    GAOT_RETURN_LAST();
+}
+
+GAOT_API int gaot_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                             float beta1, float beta2, float eps, float weight_decay, int64_t step, float grad_scale,
+                             void* stream) {
+    if (!param || !grad || !exp_avg || !exp_avg_sq || n < 0 || step < 1) return GAOT_E_BADARG;
+    if (n == 0) return 0;
+    const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+    adamw_kernel<<<gaot_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2,
+                                                                      eps, weight_decay, (float)(1.0 / bc1),
+                                                                      (float)(1.0 / sqrt(bc2)), grad_scale);
+    GAOT_RETURN_LAST();
+}
+
+GAOT_API int gaot_rollout_update(const float* pred, const float* u_in, float* u_next, int64_t rows, int64_t C, float dt,
+                                 int mode, const float* u_mean, const float* u_std, const float* s_mean,
+                                 const float* s_std, void* stream) {
+    if (!pred || !u_next || rows < 0 || C < 1 || mode < 0 || mode > 2) return GAOT_E_BADARG;
+    if (mode != 0 && (!u_in || !u_mean || !u_std || !s_mean || !s_std)) return GAOT_E_BADARG;
+    if (rows == 0) return 0;
+    rollout_kernel<<<gaot_grid(rows * C, 256), 256, 0, (cudaStream_t)stream>>>(pred, u_in, u_next, rows, (int)C, dt, mode,
+                                                                               u_mean, u_std, s_mean, s_std);
+    GAOT_RETURN_LAST();
+}

@@ -1,0 +1,494 @@
+// MAGNO encoder/decoder kernels: edge inputs, cosine segment-softmax, the attentional
+// gather * weight -> segment-sum aggregate (forward, and both backward products), the generic
+// segment_csr drop-in and the statistical geometry features.
+// Reference: src/model/layers/agno.py:148-273, src/model/layers/gemb.py:83-171,
+//            src/model/layers/utils/segment_csr.py:14-55.
+//
+// Aggregate layout: features [B, N, C] fp32, channel-contiguous.  A group of G lanes (G*4 >= C, so
+// one 128-bit load per lane covers a feature row) owns one destination row and BC batch samples:
+// the edge weight row w[e,:] is loaded once per edge into registers and reused for the BC samples,
+// every feature row is fetched with coalesced 16-byte loads, sums stay in registers in edge order
+// (deterministic, no atomics) and one coalesced store writes the result.  Repeated reads of the
+// same source row by neighbouring destination rows are served by L2 (the whole per-sample feature
+// matrix is a few MB).
+#include "common.cuh"
+#include "../../include/gaot_b200.h"
+
+namespace {
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void fma4(float4& a, const float4& x, const float4& y) {
+    a.x = fmaf(x.x, y.x, a.x); a.y = fmaf(x.y, y.y, a.y); a.z = fmaf(x.z, y.z, a.z); a.w = fmaf(x.w, y.w, a.w);
+}
+
+// ------------------------------------------------------------------------------------------------
+// edge inputs / attention weights
+// ------------------------------------------------------------------------------------------------
+__global__ void edge_inputs_kernel(const float* __restrict__ y, int dy, const float* __restrict__ x, int dx,
+                                   const int64_t* __restrict__ index, const int64_t* __restrict__ edge_row,
+                                   int64_t E, float* __restrict__ z) {
+    const int w = dy + dx;
+    const int64_t total = E * w;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t e = i / w;
+        const int k = (int)(i - e * w);
+        z[i] = (k < dy) ? __ldg(y + index[e] * dy + k) : __ldg(x + edge_row[e] * dx + (k - dy));
+    }
+}
+
+// one thread per destination row: rows are short (mean degree 3..50) and the whole op touches E scalars
+__global__ void cosine_softmax_kernel(const float* __restrict__ y, int dy, const float* __restrict__ x, int dx, int cd,
+                                      const int64_t* __restrict__ index, const int64_t* __restrict__ rs, int64_t m,
+                                      float* __restrict__ alpha) {
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= m) return;
+    const int64_t a = rs[row], e = rs[row + 1];
+    if (a == e) return;
+    float qn = 0.f;
+    for (int k = 0; k < cd; ++k) { const float v = x[row * dx + k]; qn = fmaf(v, v, qn); }
+    const float qinv = 1.f / fmaxf(sqrtf(qn), 1e-12f);
+    float smax = -INFINITY;
+    for (int64_t i = a; i < e; ++i) {
+        const float* yp = y + index[i] * dy;
+        float kn = 0.f, dot = 0.f;
+        for (int k = 0; k < cd; ++k) {
+            const float kv = __ldg(yp + k);
+            kn = fmaf(kv, kv, kn);
+            dot = fmaf(kv, x[row * dx + k] * qinv, dot);
+        }
+        const float s = dot / fmaxf(sqrtf(kn), 1e-12f);
+        alpha[i] = s;
+        smax = fmaxf(smax, s);
+    }
+    float den = 0.f;
+    for (int64_t i = a; i < e; ++i) { const float ex = expf(alpha[i] - smax); alpha[i] = ex; den += ex; }
+    const float inv = 1.f / den;
+    for (int64_t i = a; i < e; ++i) alpha[i] *= inv;
+}
+
+__global__ void scale_rows_kernel(const float* __restrict__ in, const float* __restrict__ scale, int64_t rows, int C,
+                                  float* __restrict__ out) {
+    const int64_t total = rows * C;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = in[i] * __ldg(scale + i / C);
+}
+
+// ------------------------------------------------------------------------------------------------
+// aggregate: out[b,r,:] = sum_{e in row r} w[p(e),:] * f[b,index[e],:]
+// ------------------------------------------------------------------------------------------------
+template <int G, int VPL, int BC>
+__global__ void __launch_bounds__(256)
+agno_aggregate_kernel(const float* __restrict__ f, const float* __restrict__ w, const int64_t* __restrict__ w_perm,
+                      const int64_t* __restrict__ index, const int64_t* __restrict__ rs,
+                      float* __restrict__ out, int B, int64_t Ns, int64_t Nd, int C, int64_t n_items) {
+    const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const int gl = threadIdx.x % G;
+    if (gid >= n_items) return;
+    const int64_t row = gid % Nd;
+    const int b0 = (int)(gid / Nd) * BC;
+    const int nvec = C >> 2;
+    float4 acc[BC][VPL];
+#pragma unroll
+    for (int bb = 0; bb < BC; ++bb)
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) acc[bb][v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int64_t a = __ldg(rs + row), e = __ldg(rs + row + 1);
+    for (int64_t i = a; i < e; ++i) {
+        const int64_t j = __ldg(index + i);
+        const int64_t pe = w_perm ? __ldg(w_perm + i) : i;
+        float4 wv[VPL];
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+            const int c4 = gl + v * G;
+            wv[v] = (c4 < nvec) ? ldg4(w + pe * C + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int bb = 0; bb < BC; ++bb) {
+            if (b0 + bb < B) {
+                const float* fp = f + ((int64_t)(b0 + bb) * Ns + j) * C;
+#pragma unroll
+                for (int v = 0; v < VPL; ++v) {
+                    const int c4 = gl + v * G;
+                    if (c4 < nvec) fma4(acc[bb][v], wv[v], ldg4(fp + c4 * 4));
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int bb = 0; bb < BC; ++bb) {
+        if (b0 + bb < B) {
+            float* op = out + ((int64_t)(b0 + bb) * Nd + row) * C;
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) {
+                const int c4 = gl + v * G;
+                if (c4 < nvec) *reinterpret_cast<float4*>(op + c4 * 4) = acc[bb][v];
+            }
+        }
+    }
+}
+
+// any C (not a multiple of 4, or very wide): one thread per (b, row, c)
+__global__ void agno_aggregate_scalar_kernel(const float* __restrict__ f, const float* __restrict__ w,
+                                             const int64_t* __restrict__ w_perm, const int64_t* __restrict__ index,
+                                             const int64_t* __restrict__ rs, float* __restrict__ out,
+                                             int64_t B, int64_t Ns, int64_t Nd, int64_t C) {
+    const int64_t total = B * Nd * C;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t c = t % C, row = (t / C) % Nd, b = t / (C * Nd);
+        float acc = 0.f;
+        for (int64_t i = rs[row]; i < rs[row + 1]; ++i) {
+            const int64_t pe = w_perm ? w_perm[i] : i;
+            acc = fmaf(__ldg(w + pe * C + c), __ldg(f + (b * Ns + index[i]) * C + c), acc);
+        }
+        out[t] = acc;
+    }
+}
+
+template <int G, int VPL>
+int launch_aggregate_bc(const float* f, const float* w, const int64_t* w_perm, const int64_t* index, const int64_t* rs,
+                        float* out, int64_t B, int64_t Ns, int64_t Nd, int64_t C, cudaStream_t st) {
+    const int bc = B >= 8 ? 8 : (B >= 4 ? 4 : (B >= 2 ? 2 : 1));
+    const int64_t n_items = Nd * ((B + bc - 1) / bc);
+    const int threads = 256;
+    const int64_t blocks = (n_items * G + threads - 1) / threads;
+    if (blocks > 0x7fffffffLL) return GAOT_E_BADARG;
+#define GAOT_AGG(BC_) agno_aggregate_kernel<G, VPL, BC_><<<(unsigned)blocks, threads, 0, st>>>( \
+        f, w, w_perm, index, rs, out, (int)B, Ns, Nd, (int)C, n_items)
+    switch (bc) {
+        case 8: GAOT_AGG(8); break;
+        case 4: GAOT_AGG(4); break;
+        case 2: GAOT_AGG(2); break;
+        default: GAOT_AGG(1); break;
+    }
+#undef GAOT_AGG
+    GAOT_RETURN_LAST();
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight gradient: dw[e,:] = sum_b g[b,row(e),:] * f[b,index[e],:]
+// A group of G lanes owns one destination row and a slice of the batch; it keeps EC edge
+// accumulators in registers so g[b,row,:] is loaded once per EC edges.  With more than one batch
+// slice the partial sums are combined with 128-bit red.add.
+// ------------------------------------------------------------------------------------------------
+template <int G, int VPL, int EC>
+__global__ void __launch_bounds__(256)
+agno_weight_grad_kernel(const float* __restrict__ g, const float* __restrict__ f, const int64_t* __restrict__ index,
+                        const int64_t* __restrict__ rs, float* __restrict__ dw,
+                        int B, int64_t Ns, int64_t Nd, int C, int bsplit, int64_t n_items) {
+    const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const int gl = threadIdx.x % G;
+    if (gid >= n_items) return;
+    const int64_t row = gid % Nd;
+    const int slice = (int)(gid / Nd);
+    const int per = (B + bsplit - 1) / bsplit;
+    const int b_lo = slice * per, b_hi = min(B, b_lo + per);
+    const int nvec = C >> 2;
+    const int64_t a = __ldg(rs + row), e = __ldg(rs + row + 1);
+    for (int64_t i0 = a; i0 < e; i0 += EC) {
+        int64_t j[EC];
+#pragma unroll
+        for (int k = 0; k < EC; ++k) j[k] = (i0 + k < e) ? __ldg(index + i0 + k) : -1;
+        float4 acc[EC][VPL];
+#pragma unroll
+        for (int k = 0; k < EC; ++k)
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) acc[k][v] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int b = b_lo; b < b_hi; ++b) {
+            float4 gv[VPL];
+            const float* gp = g + ((int64_t)b * Nd + row) * C;
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) {
+                const int c4 = gl + v * G;
+                gv[v] = (c4 < nvec) ? ldg4(gp + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int k = 0; k < EC; ++k) {
+                if (j[k] >= 0) {
+                    const float* fp = f + ((int64_t)b * Ns + j[k]) * C;
+#pragma unroll
+                    for (int v = 0; v < VPL; ++v) {
+                        const int c4 = gl + v * G;
+                        if (c4 < nvec) fma4(acc[k][v], gv[v], ldg4(fp + c4 * 4));
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < EC; ++k) {
+            if (j[k] >= 0) {
+#pragma unroll
+                for (int v = 0; v < VPL; ++v) {
+                    const int c4 = gl + v * G;
+                    if (c4 < nvec) {
+                        float4* dst = reinterpret_cast<float4*>(dw + (i0 + k) * C + c4 * 4);
+                        if (bsplit > 1) atomicAdd(dst, acc[k][v]);
+                        else *dst = acc[k][v];
+                    }
+                }
+            }
+        }
+    }
+}
+
+__global__ void agno_weight_grad_scalar_kernel(const float* __restrict__ g, const float* __restrict__ f,
+                                               const int64_t* __restrict__ index, const int64_t* __restrict__ edge_rows_unused,
+                                               const int64_t* __restrict__ rs, float* __restrict__ dw,
+                                               int64_t B, int64_t Ns, int64_t Nd, int64_t C) {
+    // one thread per (row, c): walks the row's edges; tiny-C fallback only
+    const int64_t total = Nd * C;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t c = t % C, row = t / C;
+        for (int64_t i = rs[row]; i < rs[row + 1]; ++i) {
+            const int64_t jj = index[i];
+            float acc = 0.f;
+            for (int64_t b = 0; b < B; ++b)
+                acc = fmaf(__ldg(g + (b * Nd + row) * C + c), __ldg(f + (b * Ns + jj) * C + c), acc);
+            dw[i * C + c] = acc;
+        }
+    }
+}
+
+template <int G, int VPL>
+int launch_weight_grad(const float* g, const float* f, const int64_t* index, const int64_t* rs, float* dw,
+                       int64_t B, int64_t Ns, int64_t Nd, int64_t C, int64_t E, cudaStream_t st) {
+    // enough groups to fill the chip: target >= 148 SMs * 2048 threads
+    int bsplit = 1;
+    const int64_t want = 148LL * 2048;
+    while (bsplit < B && Nd * G * bsplit < want && bsplit < 8) bsplit <<= 1;
+    if (bsplit > B) bsplit = (int)B;
+    if (bsplit > 1) GAOT_CHECK(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)(E * C), st));
+    const int64_t n_items = Nd * bsplit;
+    const int threads = 256;
+    const int64_t blocks = (n_items * G + threads - 1) / threads;
+    if (blocks > 0x7fffffffLL) return GAOT_E_BADARG;
+    agno_weight_grad_kernel<G, VPL, 4><<<(unsigned)blocks, threads, 0, st>>>(g, f, index, rs, dw, (int)B, Ns, Nd,
+                                                                             (int)C, bsplit, n_items);
+    GAOT_RETURN_LAST();
+}
+
+// ------------------------------------------------------------------------------------------------
+// generic segment_csr (drop-in API; not on the fused hot path)
+// ------------------------------------------------------------------------------------------------
+__global__ void segment_csr_kernel(const float* __restrict__ src, const int64_t* __restrict__ rs, float* __restrict__ out,
+                                   int64_t B, int64_t E, int64_t m, int64_t C, int reduce) {
+    const int64_t total = B * m * C;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t c = t % C, row = (t / C) % m, b = t / (C * m);
+        const int64_t a = rs[row], e = rs[row + 1];
+        float acc = (reduce == 2) ? -INFINITY : 0.f;
+        for (int64_t i = a; i < e; ++i) {
+            const float v = __ldg(src + (b * E + i) * C + c);
+            acc = (reduce == 2) ? fmaxf(acc, v) : acc + v;
+        }
+        if (a == e) acc = 0.f;
+        else if (reduce == 1) acc /= (float)(e - a);
+        out[t] = acc;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// statistical geometry features (fp64 inside: the variance is a difference of moments)
+// ------------------------------------------------------------------------------------------------
+__device__ void eig_sym2(double a, double b, double c, double* ev) {   // [[a,b],[b,c]] -> descending
+    const double mid = 0.5 * (a + c), h = 0.5 * (a - c);
+    const double r = sqrt(h * h + b * b);
+    ev[0] = mid + r; ev[1] = mid - r;
+}
+__device__ void eig_sym3(double a00, double a01, double a02, double a11, double a12, double a22, double* ev) {
+    const double p1 = a01 * a01 + a02 * a02 + a12 * a12;
+    const double q = (a00 + a11 + a22) / 3.0;
+    const double p2 = (a00 - q) * (a00 - q) + (a11 - q) * (a11 - q) + (a22 - q) * (a22 - q) + 2.0 * p1;
+    if (p2 <= 0.0) { ev[0] = ev[1] = ev[2] = q; return; }
+    const double p = sqrt(p2 / 6.0);
+    const double ip = 1.0 / p;
+    const double b00 = (a00 - q) * ip, b11 = (a11 - q) * ip, b22 = (a22 - q) * ip;
+    const double b01 = a01 * ip, b02 = a02 * ip, b12 = a12 * ip;
+    double r = 0.5 * (b00 * (b11 * b22 - b12 * b12) - b01 * (b01 * b22 - b12 * b02) + b02 * (b01 * b12 - b11 * b02));
+    r = fmin(1.0, fmax(-1.0, r));
+    const double phi = acos(r) / 3.0;
+    const double e0 = q + 2.0 * p * cos(phi);
+    const double e2 = q + 2.0 * p * cos(phi + 2.0943951023931954923);
+    ev[0] = e0; ev[1] = 3.0 * q - e0 - e2; ev[2] = e2;
+}
+
+template <int D>
+__global__ void geo_stats_kernel(const float* __restrict__ src, const float* __restrict__ qry,
+                                 const int64_t* __restrict__ index, const int64_t* __restrict__ rs, int64_t m,
+                                 float* __restrict__ feat) {
+    constexpr int F = 3 + 2 * D;
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= m) return;
+    float* o = feat + row * F;
+    const int64_t a = rs[row], e = rs[row + 1];
+    if (a == e) {
+#pragma unroll
+        for (int k = 0; k < F; ++k) o[k] = 0.f;
+        return;
+    }
+    double q[D], sp[D], sd = 0.0, sd2 = 0.0;
+#pragma unroll
+    for (int k = 0; k < D; ++k) { q[k] = (double)qry[row * D + k]; sp[k] = 0.0; }
+    for (int64_t i = a; i < e; ++i) {
+        const float* pp = src + index[i] * D;
+        double d2 = 0.0;
+#pragma unroll
+        for (int k = 0; k < D; ++k) { const double pv = (double)__ldg(pp + k); sp[k] += pv; const double df = pv - q[k]; d2 += df * df; }
+        sd += sqrt(d2); sd2 += d2;
+    }
+    const double n = (double)(e - a), inv = 1.0 / n;
+    const double davg = sd * inv;
+    double dvar = sd2 * inv - davg * davg;
+    if (dvar < 0.0) dvar = 0.0;
+    double cen[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) cen[k] = sp[k] * inv;
+    double cov[D][D];
+#pragma unroll
+    for (int r = 0; r < D; ++r)
+#pragma unroll
+        for (int c = 0; c < D; ++c) cov[r][c] = 0.0;
+    for (int64_t i = a; i < e; ++i) {
+        const float* pp = src + index[i] * D;
+        double ct[D];
+#pragma unroll
+        for (int k = 0; k < D; ++k) ct[k] = (double)__ldg(pp + k) - cen[k];
+#pragma unroll
+        for (int r = 0; r < D; ++r)
+#pragma unroll
+            for (int c = r; c < D; ++c) cov[r][c] += ct[r] * ct[c];
+    }
+    double ev[D];
+    if (D == 2) eig_sym2(cov[0][0] * inv, cov[0][1] * inv, cov[1][1] * inv, ev);
+    else eig_sym3(cov[0][0] * inv, cov[0][1] * inv, cov[0][D - 1] * inv, cov[1][1] * inv, cov[1][D - 1] * inv,
+                  cov[D - 1][D - 1] * inv, ev);
+    o[0] = (float)n; o[1] = (float)davg; o[2] = (float)dvar;
+#pragma unroll
+    for (int k = 0; k < D; ++k) { o[3 + k] = (float)(cen[k] - q[k]); o[3 + D + k] = (float)ev[k]; }
+}
+
+// one CTA per column: mean and unbiased std in fp64, then in-place standardisation
+__global__ void __launch_bounds__(1024) col_standardize_kernel(float* __restrict__ feat, int64_t m, int F) {
+    __shared__ double red[32];
+    __shared__ double bc;
+    const int col = blockIdx.x;
+    feat += (int64_t)blockIdx.y * m * F;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    auto block_sum = [&](double v) -> double {
+        v = warp_sum_d(v);
+        __syncthreads();
+        if (lane == 0) red[warp] = v;
+        __syncthreads();
+        if (warp == 0) {
+            double t = red[lane];
+            t = warp_sum_d(t);
+            if (lane == 0) bc = t;
+        }
+        __syncthreads();
+        return bc;
+    };
+    double s = 0.0;
+    for (int64_t r = threadIdx.x; r < m; r += blockDim.x) s += (double)feat[r * F + col];
+    const double mean = block_sum(s) / (double)m;
+    double ss = 0.0;
+    for (int64_t r = threadIdx.x; r < m; r += blockDim.x) { const double dv = (double)feat[r * F + col] - mean; ss += dv * dv; }
+    double sd = sqrt(block_sum(ss) / (double)(m - 1));
+    if (sd < 1e-6) sd = 1.0;
+    const double inv = 1.0 / sd;
+    for (int64_t r = threadIdx.x; r < m; r += blockDim.x) feat[r * F + col] = (float)(((double)feat[r * F + col] - mean) * inv);
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace
+
+GAOT_API int gaot_edge_inputs(const float* y, int64_t dy, const float* x, int64_t dx, const int64_t* index,
+                              const int64_t* edge_row, int64_t E, float* z, void* stream) {
+    if (!y || !x || !index || !edge_row || !z || dy < 1 || dx < 1 || E < 0) return GAOT_E_BADARG;
+    if (E == 0) return 0;
+    edge_inputs_kernel<<<gaot_grid(E * (dy + dx), 256), 256, 0, (cudaStream_t)stream>>>(y, (int)dy, x, (int)dx, index,
+                                                                                        edge_row, E, z);
+    GAOT_RETURN_LAST();
+}
+
+GAOT_API int gaot_edge_cosine_softmax(const float* y, int64_t dy, const float* x, int64_t dx, int64_t cd,
+                                      const int64_t* index, const int64_t* row_splits, int64_t m, float* alpha,
+                                      void* stream) {
+    if (!y || !x || !index || !row_splits || !alpha || cd < 1 || cd > dy || cd > dx || m < 0) return GAOT_E_BADARG;
+    if (m == 0) return 0;
+    cosine_softmax_kernel<<<gaot_blocks(m, 128), 128, 0, (cudaStream_t)stream>>>(y, (int)dy, x, (int)dx, (int)cd, index,
+                                                                                 row_splits, m, alpha);
+    GAOT_RETURN_LAST();
+}
+
+GAOT_API int gaot_scale_rows(const float* in, const float* scale, int64_t rows, int64_t C, float* out, void* stream) {
+    if (!in || !scale || !out || rows < 0 || C < 1) return GAOT_E_BADARG;
+    if (rows == 0) return 0;
+    scale_rows_kernel<<<gaot_grid(rows * C, 256), 256, 0, (cudaStream_t)stream>>>(in, scale, rows, (int)C, out);
+    GAOT_RETURN_LAST();
+}
+
+GAOT_API int gaot_agno_aggregate(const float* f, const float* w, const int64_t* w_perm, const int64_t* index,
+                                 const int64_t* row_splits, float* out, int64_t B, int64_t Ns, int64_t Nd, int64_t C,
+                                 void* stream) {
+    if (!f || !w || !index || !row_splits || !out || B < 1 || Ns < 0 || Nd < 0 || C < 1) return GAOT_E_BADARG;
+    if (Nd == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool vec = (C % 4 == 0) && C <= 512 && aligned16(f) && aligned16(w) && aligned16(out);
+    if (!vec) {
+        agno_aggregate_scalar_kernel<<<gaot_grid(B * Nd * C, 256), 256, 0, st>>>(f, w, w_perm, index, row_splits, out, B,
+                                                                                 Ns, Nd, C);
+        GAOT_RETURN_LAST();
+    }
+    const int nvec = (int)(C / 4);
+    if (nvec <= 4) return launch_aggregate_bc<4, 1>(f, w, w_perm, index, row_splits, out, B, Ns, Nd, C, st);
+    if (nvec <= 8) return launch_aggregate_bc<8, 1>(f, w, w_perm, index, row_splits, out, B, Ns, Nd, C, st);
+    if (nvec <= 16) return launch_aggregate_bc<16, 1>(f, w, w_perm, index, row_splits, out, B, Ns, Nd, C, st);
+    if (nvec <= 32) return launch_aggregate_bc<32, 1>(f, w, w_perm, index, row_splits, out, B, Ns, Nd, C, st);
+    if (nvec <= 64) return launch_aggregate_bc<32, 2>(f, w, w_perm, index, row_splits, out, B, Ns, Nd, C, st);
+    return launch_aggregate_bc<32, 4>(f, w, w_perm, index, row_splits, out, B, Ns, Nd, C, st);
+}
+
+GAOT_API int gaot_agno_weight_grad(const float* g, const float* f, const int64_t* index, const int64_t* row_splits,
+                                   float* dw, int64_t B, int64_t Ns, int64_t Nd, int64_t E, int64_t C, void* stream) {
+    if (!g || !f || !index || !row_splits || !dw || B < 1 || Ns < 0 || Nd < 0 || E < 0 || C < 1) return GAOT_E_BADARG;
+    if (Nd == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool vec = (C % 4 == 0) && C <= 512 && aligned16(f) && aligned16(g) && aligned16(dw);
+    if (!vec) {
+        agno_weight_grad_scalar_kernel<<<gaot_grid(Nd * C, 128), 128, 0, st>>>(g, f, index, nullptr, row_splits, dw, B, Ns,
+                                                                               Nd, C);
+        GAOT_RETURN_LAST();
+    }
+    const int nvec = (int)(C / 4);
+    if (nvec <= 4) return launch_weight_grad<4, 1>(g, f, index, row_splits, dw, B, Ns, Nd, C, E, st);
+    if (nvec <= 8) return launch_weight_grad<8, 1>(g, f, index, row_splits, dw, B, Ns, Nd, C, E, st);
+    if (nvec <= 16) return launch_weight_grad<16, 1>(g, f, index, row_splits, dw, B, Ns, Nd, C, E, st);
+    if (nvec <= 32) return launch_weight_grad<32, 1>(g, f, index, row_splits, dw, B, Ns, Nd, C, E, st);
+    if (nvec <= 64) return launch_weight_grad<32, 2>(g, f, index, row_splits, dw, B, Ns, Nd, C, E, st);
+    return launch_weight_grad<32, 4>(g, f, index, row_splits, dw, B, Ns, Nd, C, E, st);
+}
+
+GAOT_API int gaot_segment_csr(const float* src, const int64_t* row_splits, float* out, int64_t B, int64_t E, int64_t m,
+                              int64_t C, int reduce, void* stream) {
+    if (!src || !row_splits || !out || B < 1 || E < 0 || m < 0 || C < 1 || reduce < 0 || reduce > 2) return GAOT_E_BADARG;
+    if (m == 0) return 0;
+    segment_csr_kernel<<<gaot_grid(B * m * C, 256), 256, 0, (cudaStream_t)stream>>>(src, row_splits, out, B, E, m, C, reduce);
+    GAOT_RETURN_LAST();
+}
+
+GAOT_API int gaot_geo_stats(const float* src, const float* queries, int64_t d, const int64_t* index,
+                            const int64_t* row_splits, int64_t m, float* feat, void* stream) {
+    if (!src || !queries || !index || !row_splits || !feat || m < 0) return GAOT_E_BADARG;
+    if (d != 2 && d != 3) return GAOT_E_BADARG;
+    if (m == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (d == 2) geo_stats_kernel<2><<<gaot_blocks(m, 128), 128, 0, st>>>(src, queries, index, row_splits, m, feat);
+    else geo_stats_kernel<3><<<gaot_blocks(m, 128), 128, 0, st>>>(src, queries, index, row_splits, m, feat);
+    GAOT_RETURN_LAST();
+}
+
+GAOT_API int gaot_col_standardize(float* feat, int64_t m, int64_t F, int64_t groups, void* stream) {
+    if (!feat || m < 1 || F < 1 || groups < 1 || groups > 65535) return GAOT_E_BADARG;
+    col_standardize_kernel<<<dim3((unsigned)F, (unsigned)groups), 1024, 0, (cudaStream_t)stream>>>(feat, m, (int)F);
+    GAOT_RETURN_LAST();
+}

@@ -1,0 +1,125 @@
+"""GAOT top level (reference src/model/gaot.py:11-476): MAGNO encoder -> patchify + U-ViT -> MAGNO decoder,
+same constructor, forward signature and state-dict keys; all arithmetic in libgaot_b200.so."""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+from torch import nn
+
+from .. import ops
+from .layers.attn import Transformer
+from .layers.magno import MAGNODecoder, MAGNOEncoder
+
+
+class GAOT(nn.Module):
+    def __init__(self, input_size: int, output_size: int, config=None):
+        super().__init__()
+        coord_dim = config.args.magno.coord_dim
+        if coord_dim not in [2, 3]:
+            raise ValueError(f"coord_dim must be 2 or 3, got {coord_dim}")
+        self.input_size, self.output_size, self.coord_dim = input_size, output_size, coord_dim
+        self.node_latent_size = config.args.magno.lifting_channels
+        self.patch_size = config.args.transformer.patch_size
+        lts = tuple(config.latent_tokens_size)
+        if len(lts) != coord_dim:
+            raise ValueError(f"For {coord_dim}D, latent_tokens_size must have {coord_dim} dimensions, got {len(lts)}")
+        self.H, self.W = lts[0], lts[1]
+        self.D = lts[2] if coord_dim == 3 else None
+        self.encoder = MAGNOEncoder(in_channels=input_size, out_channels=self.node_latent_size, config=config.args.magno)
+        pv = self.patch_size ** coord_dim
+        self.patch_linear = nn.Linear(pv * self.node_latent_size, pv * self.node_latent_size)
+        self.positional_embedding_name = config.args.transformer.positional_embedding
+        self.positions = self._get_patch_positions()
+        self.processor = Transformer(input_size=self.node_latent_size * pv, output_size=self.node_latent_size * pv,
+                                     config=config.args.transformer)
+        self.decoder = MAGNODecoder(in_channels=self.node_latent_size, out_channels=output_size, config=config.args.magno)
+        self._pos_emb = None
+
+    def _grid(self):
+        return (self.H, self.W) if self.coord_dim == 2 else (self.H, self.W, self.D)
+
+    def _get_patch_positions(self):
+        axes = [torch.arange(g // self.patch_size, dtype=torch.float32) for g in self._grid()]
+        return torch.stack(torch.meshgrid(*axes, indexing="ij"), dim=-1).reshape(-1, self.coord_dim)
+
+    def _compute_absolute_embeddings(self, positions, embed_dim):
+        """gaot.py:119-130 - a constant table, built once per device."""
+        nd = positions.size(1)
+        k = embed_dim // (2 * nd)
+        inv = 1.0 / (10000 ** (torch.arange(k, dtype=torch.float32, device=positions.device) / k))
+        ang = positions[:, :, None] * inv[None, None, :]
+        return torch.cat([torch.sin(ang), torch.cos(ang)], dim=-1).view(positions.size(0), -1)
+
+    def encode(self, x_coord, pndata, latent_tokens_coord, encoder_nbrs):
+        return self.encoder(x_coord=x_coord, pndata=pndata, latent_tokens_coord=latent_tokens_coord,
+                            encoder_nbrs=encoder_nbrs)
+
+    def process(self, rndata, condition: Optional[float] = None):
+        """gaot.py:145-233."""
+        B, n_tok, C = rndata.shape
+        grid, P = self._grid(), self.patch_size
+        n_expected = 1
+        for g in grid:
+            n_expected *= g
+            if g % P != 0:
+                raise ValueError(f"latent grid {grid} must be divisible by patch size P={P}")
+        if n_tok != n_expected:
+            raise ValueError(f"rndata has {n_tok} tokens, expected {n_expected} for latent grid {grid}")
+        x = ops.patchify(rndata, grid, P)                                 # [B,T,P^d*C]
+        T, Dp = x.shape[1], x.shape[2]
+        add = None
+        if self.positional_embedding_name == "absolute":
+            if self._pos_emb is None or self._pos_emb.device != x.device:
+                pe = self._compute_absolute_embeddings(self.positions.to(x.device), Dp)
+                if pe.shape[1] != Dp:
+                    raise ValueError(f"absolute positional embedding width {pe.shape[1]} != patch dim {Dp}")
+                self._pos_emb = pe.contiguous()
+            add = self._pos_emb
+        elif self.positional_embedding_name == "rope":
+            raise NotImplementedError("positional_embedding='rope' is not on the accelerated path")
+        x = ops.linear(x.view(B * T, Dp), self.patch_linear.weight, self.patch_linear.bias, add=add).view(B, T, Dp)
+        x = self.processor(x, condition=condition, relative_positions=None)
+        return ops.unpatchify(x, grid, P, C)
+
+    def decode(self, latent_tokens_coord, rndata, query_coord, decoder_nbrs):
+        return self.decoder(latent_tokens_coord=latent_tokens_coord, rndata=rndata, query_coord=query_coord,
+                            decoder_nbrs=decoder_nbrs)
+
+    def forward(self, latent_tokens_coord, xcoord, pndata, query_coord=None, encoder_nbrs=None, decoder_nbrs=None,
+                condition: Optional[float] = None):
+        rndata = self.encode(xcoord, pndata, latent_tokens_coord, encoder_nbrs)
+        rndata = self.process(rndata, condition=condition)
+        if query_coord is None:
+            query_coord = xcoord
+        return self.decode(latent_tokens_coord, rndata, query_coord, decoder_nbrs)
+
+    @torch.no_grad()
+    def autoregressive_predict(self, x_batch, time_indices, t_values, stats, stepper_mode="output",
+                               latent_tokens_coord=None, fixed_coord=None, encoder_nbrs=None, decoder_nbrs=None,
+                               c_batch=None):
+        """gaot.py:307-434 (fx mode): x_batch [B,N,u_dim] normalised initial state, optional conditioning
+        channels c_batch [B,N,c]; returns [B, len(time_indices)-1, N, u_dim] normalised predictions.
+        stats = {"u": {mean,std}, "res": {...}, "der": {...}, "start_time": {...}, "time_diffs": {...}} of
+        per-channel tensors / floats as the reference's sequential trainer supplies them."""
+        dev = x_batch.device
+        B, N, U = x_batch.shape
+        cur = x_batch
+        outs = []
+        mode = {"output": 0, "residual": 1, "time_der": 2}[stepper_mode]
+        t = lambda v: torch.as_tensor(v, dtype=torch.float32, device=dev).reshape(-1).expand(U).contiguous()  # noqa: E731
+        um, us = t(stats["u"]["mean"]), t(stats["u"]["std"])
+        skey = {1: "res", 2: "der"}.get(mode)
+        sm, ss = (t(stats[skey]["mean"]), t(stats[skey]["std"])) if skey else (um, us)
+        for i in range(len(time_indices) - 1):
+            t0 = float(t_values[time_indices[i]])
+            dt = float(t_values[time_indices[i + 1]]) - t0
+            t0n = (t0 - float(stats["start_time"]["mean"])) / float(stats["start_time"]["std"])
+            dtn = (dt - float(stats["time_diffs"]["mean"])) / float(stats["time_diffs"]["std"])
+            feats = [cur] + ([c_batch] if c_batch is not None else [])
+            feats += [torch.full((B, N, 1), t0n, device=dev), torch.full((B, N, 1), dtn, device=dev)]
+            pred = self.forward(latent_tokens_coord, fixed_coord, torch.cat(feats, dim=-1),
+                                encoder_nbrs=encoder_nbrs, decoder_nbrs=decoder_nbrs)
+            cur = ops.rollout_update(pred, cur, dt, mode, um, us, sm, ss)
+            outs.append(cur)
+        return torch.stack(outs, dim=1)

@@ -1,0 +1,66 @@
+"""AGNO - attentional graph neural operator (reference src/model/layers/agno.py:67-273).
+
+out[b,m,:] = sum_{e in row m} alpha_e * k(y_e, x_m)[:] * f[b, idx_e, :]      (use_attn: sum)
+out[b,m,:] = mean_{e in row m}          k(y_e, x_m)[:] * f[b, idx_e, :]      (no attention)
+The edge weight w = alpha * k is batch independent and computed once per call; the gather, the
+product and the segment reduction are one kernel (gaot_agno_aggregate) that never materialises the
+[B,E,C] tensors of agno.py:198,246,250."""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+from ... import ops
+from .mlp import LinearChannelMLP
+
+
+class AGNO(nn.Module):
+    def __init__(self, channel_mlp=None, channel_mlp_layers=None, channel_mlp_non_linearity=None,
+                 transform_type="linear", use_attn=None, attention_type="cosine", coord_dim=None, use_torch_scatter=True):
+        super().__init__()
+        self.transform_type = transform_type
+        self.use_torch_scatter = use_torch_scatter
+        self.use_attn = use_attn
+        self.attention_type = attention_type
+        if channel_mlp is None and channel_mlp_layers is None:
+            raise ValueError("Either channel_mlp or channel_mlp_layers must be provided.")
+        if transform_type not in ["linear_kernelonly", "linear", "nonlinear_kernelonly", "nonlinear"]:
+            raise ValueError(f"Invalid transform_type: {transform_type}")
+        if transform_type != "linear":
+            # nonlinear* are shape-broken in the reference itself; *_kernelonly is "next"
+            raise NotImplementedError(f"transform_type={transform_type!r} is not on the accelerated path")
+        if use_attn:
+            if coord_dim is None:
+                raise ValueError("coord_dim must be specified when use_attn is True")
+            self.coord_dim = coord_dim
+            if attention_type not in ["cosine", "dot_product"]:
+                raise ValueError(f"Invalid attention_type: {attention_type}")
+            if attention_type == "dot_product":
+                raise NotImplementedError("attention_type='dot_product' is not on the accelerated path yet")
+        self.channel_mlp = channel_mlp if channel_mlp is not None else LinearChannelMLP(layers=channel_mlp_layers)
+
+    def edge_weights(self, y, x, plan: ops.GraphPlan):
+        """w [E, C]: kernel MLP on [y_j, x_m] (agno.py:229-242) times the attention weight (agno.py:218-224, 250)
+        or 1/deg when the reduce is `mean` (agno.py:264)."""
+        kappa = self.channel_mlp(ops.edge_inputs(y, x, plan))
+        if self.use_attn:
+            alpha = ops.edge_cosine_softmax(y, x, self.coord_dim, plan)
+        else:
+            deg = (plan.splits[1:] - plan.splits[:-1]).clamp(min=1).to(torch.float32)
+            alpha = (1.0 / deg)[plan.edge_row]
+        return ops.scale_rows(kappa, alpha)
+
+    def forward(self, y, neighbors, x=None, f_y=None, weights=None):
+        if weights is not None:
+            raise NotImplementedError("integration weights are not on the accelerated path")
+        if x is None:
+            x = y
+        if f_y is None:
+            raise NotImplementedError("f_y=None (kernel-only transform) is not on the accelerated path")
+        plan = ops.graph_plan(neighbors, y.shape[0])
+        w = self.edge_weights(y, x, plan)
+        if f_y.ndim == 3:
+            return ops.agno_aggregate(f_y, w, plan)
+        if f_y.ndim == 2:
+            return ops.agno_aggregate(f_y.unsqueeze(0), w, plan).squeeze(0)
+        raise ValueError(f"f_y has unexpected ndim: {f_y.ndim}")

@@ -1,0 +1,172 @@
+"""U-ViT processor (reference src/model/layers/attn.py:19-317) on the sm_100a kernels.
+
+Block (attn.py:229-233, note the non-standard second residual):
+    h   = x + O * SDPA(Q n1(x), K n1(x), V n1(x))
+    h   = n2(h)
+    out = h + W2 (silu(W1 h) * W3 h)
+Q/K/V run as one GEMM on the concatenated weight, W1/W3 likewise; residual adds are GEMM epilogues."""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Optional
+
+import torch
+from torch import nn
+
+from ... import ops
+
+
+@dataclass
+class AttentionConfig:
+    num_heads: int = 8
+    num_kv_heads: int = 8
+    use_conditional_norm: bool = False
+    cond_norm_hidden_size: int = 4
+    atten_dropout: float = 0.0
+
+
+@dataclass
+class TransformerConfig:
+    patch_size: int = 8
+    hidden_size: int = 256
+    use_attn_norm: bool = True
+    use_ffn_norm: bool = True
+    norm_eps: float = 1e-6
+    num_layers: int = 3
+    positional_embedding: str = "absolute"
+    use_long_range_skip: bool = True
+    ffn_multiplier: int = 4
+    attn_config: AttentionConfig = field(default_factory=AttentionConfig)
+
+
+class RMSNorm(nn.Module):
+    def __init__(self, dim: int, eps: float = 1e-6):
+        super().__init__()
+        self.eps = eps
+        self.weight = nn.Parameter(torch.ones(dim))
+
+    def forward(self, x):
+        shape = x.shape
+        return ops.rmsnorm(x.reshape(-1, shape[-1]), self.weight, self.eps).view(shape)
+
+
+class GroupQueryFlashAttention(nn.Module):
+    def __init__(self, input_size: int, hidden_size: int, num_heads: int = 8, num_kv_heads: int = 8,
+                 use_conditional_norm: bool = False, cond_norm_hidden_size: int = 4, atten_dropout: float = 0.0,
+                 positional_embedding: str = "absolute"):
+        super().__init__()
+        assert hidden_size % num_heads == 0, f"hidden_size {hidden_size} must be divisible by num_heads {num_heads}"
+        assert num_heads % num_kv_heads == 0, f"num_heads {num_heads} must be divisible by num_kv_heads {num_kv_heads}"
+        if use_conditional_norm:
+            raise NotImplementedError("time-conditioned norm is not on the accelerated path yet")
+        if positional_embedding == "rope":
+            raise NotImplementedError("positional_embedding='rope' is not on the accelerated path")
+        if atten_dropout:
+            raise NotImplementedError("attention dropout is not on the accelerated path")
+        self.num_heads, self.num_kv_heads = num_heads, num_kv_heads
+        self.num_repeat = num_heads // num_kv_heads
+        self.head_dim = hidden_size // num_heads
+        kv = self.head_dim * num_kv_heads
+        self.q_proj = nn.Linear(input_size, hidden_size, bias=False)
+        self.k_proj = nn.Linear(input_size, kv, bias=False)
+        self.v_proj = nn.Linear(input_size, kv, bias=False)
+        self.o_proj = nn.Linear(hidden_size, input_size, bias=False)
+        self.correction = None
+
+    @classmethod
+    def from_config(cls, input_size, hidden_size, config: AttentionConfig, positional_embedding="absolute"):
+        return cls(input_size, hidden_size, num_heads=config.num_heads, num_kv_heads=config.num_kv_heads,
+                   use_conditional_norm=config.use_conditional_norm, cond_norm_hidden_size=config.cond_norm_hidden_size,
+                   atten_dropout=config.atten_dropout, positional_embedding=positional_embedding)
+
+    def forward(self, x, condition=None, relative_positions=None, residual=None):
+        """x [B,T,D] -> o_proj(SDPA(...)) (+ residual, fused into the o_proj GEMM)."""
+        B, T, D = x.shape
+        wqkv = torch.cat([self.q_proj.weight, self.k_proj.weight, self.v_proj.weight], dim=0)
+        qkv = ops.linear(x.reshape(B * T, D), wqkv)
+        o = ops.attention(qkv, B, T, self.num_heads, self.num_kv_heads, self.head_dim)
+        add = residual.reshape(B * T, -1) if residual is not None else None
+        return ops.linear(o, self.o_proj.weight, None, add=add).view(B, T, -1)
+
+
+class FFN(nn.Module):
+    def __init__(self, input_size: int, ffn_hidden_size: int, use_conditional_norm: bool = False, cond_norm_hidden_size: int = 4):
+        super().__init__()
+        if use_conditional_norm:
+            raise NotImplementedError("time-conditioned norm is not on the accelerated path yet")
+        self.w1 = nn.Linear(input_size, ffn_hidden_size, bias=False)
+        self.w2 = nn.Linear(ffn_hidden_size, input_size, bias=False)
+        self.w3 = nn.Linear(input_size, ffn_hidden_size, bias=False)
+        self.correction = None
+
+    def forward(self, x, condition=None, residual=None):
+        shape = x.shape
+        x2 = x.reshape(-1, shape[-1])
+        ab = ops.linear(x2, torch.cat([self.w1.weight, self.w3.weight], dim=0))
+        add = residual.reshape(-1, shape[-1]) if residual is not None else None
+        return ops.linear(ops.swiglu(ab), self.w2.weight, None, add=add).view(shape)
+
+
+class TransformerBlock(nn.Module):
+    def __init__(self, input_size: int, config: TransformerConfig, skip_connection: bool = False):
+        super().__init__()
+        hidden = config.hidden_size
+        self.attn = GroupQueryFlashAttention.from_config(input_size=input_size, hidden_size=hidden,
+                                                         config=config.attn_config,
+                                                         positional_embedding=config.positional_embedding)
+        self.ffn = FFN(input_size=input_size, ffn_hidden_size=hidden * config.ffn_multiplier,
+                       use_conditional_norm=config.attn_config.use_conditional_norm,
+                       cond_norm_hidden_size=config.attn_config.cond_norm_hidden_size)
+        self.attn_norm = RMSNorm(input_size, eps=config.norm_eps) if config.use_attn_norm else None
+        self.ffn_norm = RMSNorm(input_size, eps=config.norm_eps) if config.use_ffn_norm else None
+        self.skip_connection = skip_connection
+        if skip_connection:
+            self.skip_proj = nn.Linear(input_size * 2, input_size)
+
+    def forward(self, x, skip=None, condition=None, relative_positions=None):
+        if self.skip_connection and skip is not None:
+            B, T, D = x.shape
+            W = self.skip_proj.weight                                    # [D, 2D] acting on cat[x, skip] (attn.py:225-227)
+            t = ops.linear(skip.reshape(B * T, D), W[:, D:], None)
+            x = ops.linear(x.reshape(B * T, D), W[:, :D], self.skip_proj.bias, add=t).view(B, T, D)
+        h = self.attn_norm(x) if self.attn_norm is not None else x
+        h = self.attn(h, condition=condition, relative_positions=relative_positions, residual=x)
+        h = self.ffn_norm(h) if self.ffn_norm is not None else h
+        return self.ffn(h, condition=condition, residual=h)
+
+
+class Transformer(nn.Module):
+    def __init__(self, input_size: int, output_size: int, config: TransformerConfig = TransformerConfig()):
+        super().__init__()
+        hidden, L = config.hidden_size, config.num_layers
+        self.use_long_range_skip = config.use_long_range_skip
+        if input_size != hidden:
+            self.input_proj = nn.Linear(input_size, hidden)
+            working = hidden
+        else:
+            self.input_proj = nn.Identity()
+            working = input_size
+        self.output_proj = nn.Linear(working, output_size) if working != output_size else nn.Identity()
+        self.encoder_layers = nn.ModuleList([TransformerBlock(working, config, False) for _ in range(L // 2)])
+        self.middle_layer = TransformerBlock(working, config, False) if L % 2 == 1 else None
+        self.decoder_layers = nn.ModuleList([TransformerBlock(working, config, True) for _ in range(L // 2)])
+
+    @staticmethod
+    def _proj(layer, x):
+        if isinstance(layer, nn.Identity):
+            return x
+        B, T, D = x.shape
+        return ops.linear(x.reshape(B * T, D), layer.weight, layer.bias).view(B, T, -1)
+
+    def forward(self, x, condition=None, relative_positions=None):
+        x = self._proj(self.input_proj, x)
+        skips = []
+        for blk in self.encoder_layers:
+            x = blk(x, condition=condition, relative_positions=relative_positions)
+            skips.append(x)
+        if self.middle_layer is not None:
+            x = self.middle_layer(x, condition=condition, relative_positions=relative_positions)
+        for blk in self.decoder_layers:
+            skip = skips.pop() if self.use_long_range_skip else None
+            x = blk(x, skip=skip, condition=condition, relative_positions=relative_positions)
+        return self._proj(self.output_proj, x)

@@ -1,0 +1,52 @@
+"""Geometry embedding (reference src/model/layers/gemb.py).  'statistical' only: per-row neighbour
+statistics (gaot_geo_stats, fp64 inside) -> column standardisation -> MLP (3+2d)->64->C, ReLU, ReLU."""
+from __future__ import annotations
+
+import math
+
+import torch
+from torch import nn
+
+from ... import ops
+
+
+def node_pos_encode(x: torch.Tensor, freq: int = 4) -> torch.Tensor:
+    """gemb.py:12-34 (small, coordinate-only; plain torch)."""
+    freqs = torch.arange(1, freq + 1, device=x.device, dtype=x.dtype)
+    z = freqs[None, :, None] * (math.pi * (x + 1))[:, None, :]
+    return torch.cat([z.sin(), z.cos()], dim=2).reshape(x.shape[0], -1)
+
+
+class GeometricEmbedding(nn.Module):
+    def __init__(self, input_dim, output_dim, method="statistical", pooling="max", **kwargs):
+        super().__init__()
+        self.input_dim, self.output_dim = input_dim, output_dim
+        self.method, self.pooling, self.kwargs = method.lower(), pooling.lower(), kwargs
+        if self.pooling not in ["max", "mean"]:
+            raise ValueError(f"Unsupported pooling method: {self.pooling}. Supported methods: 'max', 'mean'.")
+        if self.method == "statistical":
+            self.mlp = nn.Sequential(nn.Linear(3 + 2 * input_dim, 64), nn.ReLU(), nn.Linear(64, output_dim), nn.ReLU())
+        elif self.method == "pointnet":
+            raise NotImplementedError("embedding_method='pointnet' is not on the accelerated path yet")
+        else:
+            raise ValueError(f"Unknown method: {self.method}")
+
+    def features(self, input_geom, latent_queries, plan: ops.GraphPlan, groups: int = 1, cache: bool = True):
+        """Parameter-free part; a pure function of (coords, graph), cached on the graph plan."""
+        key = (input_geom.data_ptr(), input_geom._version, latent_queries.data_ptr(), latent_queries._version, groups)
+        if cache and key in plan._geo:
+            return plan._geo[key]
+        with torch.no_grad():
+            feat = ops.geo_stats(input_geom, latent_queries, plan, groups)
+        if cache:
+            plan._geo.clear()
+            plan._geo[key] = feat
+        return feat
+
+    def embed(self, feat):
+        h = ops.linear(feat, self.mlp[0].weight, self.mlp[0].bias, act=ops.ACT_RELU)
+        return ops.linear(h, self.mlp[2].weight, self.mlp[2].bias, act=ops.ACT_RELU)
+
+    def forward(self, input_geom, latent_queries, spatial_nbrs):
+        plan = ops.graph_plan(spatial_nbrs, input_geom.shape[0])
+        return self.embed(self.features(input_geom, latent_queries, plan))

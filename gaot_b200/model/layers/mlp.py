@@ -1,0 +1,57 @@
+"""Parameter containers with the reference's names/shapes (src/model/layers/mlp.py:227-337); the
+arithmetic runs in libgaot_b200.so through gaot_b200.ops."""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+from ... import ops
+
+
+class LinearChannelMLP(nn.Module):
+    """Linear stack with exact-erf GELU between layers (mlp.py:307-337); keys `fcs.{i}.{weight,bias}`."""
+
+    def __init__(self, layers, non_linearity=None, dropout=0.0):
+        super().__init__()
+        self.n_layers = len(layers) - 1
+        assert self.n_layers >= 1
+        if dropout and dropout > 0.0:
+            raise NotImplementedError("dropout > 0 is not part of the accelerated path")
+        self.fcs = nn.ModuleList([nn.Linear(layers[j], layers[j + 1]) for j in range(self.n_layers)])
+
+    def forward(self, x):
+        shape = x.shape
+        x = x.reshape(-1, shape[-1])
+        for i, fc in enumerate(self.fcs):
+            x = ops.linear(x, fc.weight, fc.bias, act=ops.ACT_GELU if i < self.n_layers - 1 else ops.ACT_NONE)
+        return x.view(*shape[:-1], x.shape[-1])
+
+
+class ChannelMLP(nn.Module):
+    """Stack of 1x1 Conv1d (mlp.py:227-305); with n_layers=1 a single affine map.  Unlike the
+    reference this module takes channel-LAST input [B, rows, Cin] (the layout the reference permutes
+    from and back to around every call, magno.py:273-274) and returns [B, rows, Cout]."""
+
+    def __init__(self, in_channels, out_channels=None, hidden_channels=None, n_layers=2, n_dim=2,
+                 non_linearity=None, dropout=0.0, **kwargs):
+        super().__init__()
+        self.n_layers = n_layers
+        self.in_channels = in_channels
+        self.out_channels = in_channels if out_channels is None else out_channels
+        self.hidden_channels = in_channels if hidden_channels is None else hidden_channels
+        if dropout and dropout > 0.0:
+            raise NotImplementedError("dropout > 0 is not part of the accelerated path")
+        self.fcs = nn.ModuleList()
+        for i in range(n_layers):
+            cin = self.in_channels if i == 0 else self.hidden_channels
+            cout = self.out_channels if i == n_layers - 1 else self.hidden_channels
+            self.fcs.append(nn.Conv1d(cin, cout, 1))
+
+    def forward(self, x, add=None):
+        shape = x.shape
+        x = x.reshape(-1, shape[-1])
+        for i, fc in enumerate(self.fcs):
+            last = i == self.n_layers - 1
+            x = ops.linear(x, fc.weight[:, :, 0], fc.bias, add=add if last else None,
+                           act=ops.ACT_NONE if last else ops.ACT_GELU)
+        return x.view(*shape[:-1], x.shape[-1])

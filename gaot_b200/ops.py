@@ -1,0 +1,448 @@
+"""Host-side operators over the C ABI (include/gaot_b200.h): thin torch.autograd.Function wrappers
+whose forward AND backward are calls into libgaot_b200.so.  torch is used for device memory, the
+stream and the autograd tape only - there is no eager/CPU fallback behind any of these.
+
+Shapes are row-major contiguous fp32; CSR arrays are int64 as in the reference container
+({"neighbors_index", "neighbors_row_splits"}, reference src/model/layers/utils/neighbor_search.py:80-90).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+
+from . import _lib
+from ._lib import call, ptr
+
+ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
+
+
+def _c(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _need_cuda(t: torch.Tensor):
+    if not t.is_cuda:
+        raise _lib.GaotLibraryError("gaot_b200 runs on CUDA tensors only - there is no CPU fallback")
+
+
+# ------------------------------------------------------------------------------------------------
+# graphs
+# ------------------------------------------------------------------------------------------------
+def radius_csr(data: torch.Tensor, queries: torch.Tensor, radius: float, inclusive: bool = True,
+               max_num_neighbors: Optional[int] = None) -> Dict[str, torch.Tensor]:
+    """Fixed-radius graph in the reference's CSR container (neighbor_search.py:65-106).
+    data [n,d] (or [S,n,d]), queries [m,d] (or [S,m,d]); a batched side yields a list of S dicts."""
+    _need_cuda(data)
+    data, queries = _c(data), _c(queries)
+    db, qb = data.ndim == 3, queries.ndim == 3
+    S = data.shape[0] if db else (queries.shape[0] if qb else 1)
+    n, m, d = data.shape[-2], queries.shape[-2], data.shape[-1]
+    cap = 0 if max_num_neighbors is None else int(max_num_neighbors)
+    splits = torch.empty((S, m + 1), dtype=torch.int64, device=data.device)
+    call("gaot_radius_count", ptr(data), n, ptr(queries), m, d, float(radius), int(inclusive), cap, S, int(db), int(qb),
+         ptr(splits))
+    counts = splits[:, m].clone()
+    offs = torch.zeros(S, dtype=torch.int64, device=data.device)
+    if S > 1:
+        offs[1:] = torch.cumsum(counts, 0)[:-1]
+    counts_h = counts.cpu()                       # E is data dependent: one host read per build
+    total = int(counts_h.sum())
+    index = torch.empty(max(total, 1), dtype=torch.int64, device=data.device)[:total]
+    if total > 0:
+        call("gaot_radius_fill", ptr(data), n, ptr(queries), m, d, float(radius), int(inclusive), cap, S, int(db), int(qb),
+             ptr(splits), ptr(offs), ptr(index))
+    out, o = [], 0
+    for s in range(S):
+        e = int(counts_h[s])
+        out.append({"neighbors_index": index[o:o + e], "neighbors_row_splits": splits[s]})
+        o += e
+    return out if (db or qb) else out[0]
+
+
+class GraphPlan:
+    """Device-side companions of one CSR graph that the kernels need: the row of every edge and the
+    source-sorted (transposed) view used by the backward of the gather."""
+
+    def __init__(self, index: torch.Tensor, splits: torch.Tensor, n_src: int):
+        _need_cuda(index)
+        self.index = index.to(torch.int64).contiguous()
+        self.splits = splits.to(torch.int64).contiguous()
+        self.n_src = int(n_src)
+        self.m = int(self.splits.numel() - 1)
+        self.E = int(self.index.numel())
+        dev = self.index.device
+        self.edge_row = torch.empty(max(self.E, 1), dtype=torch.int64, device=dev)[:self.E]
+        call("gaot_csr_edge_rows", ptr(self.splits), self.m, ptr(self.edge_row))
+        self._t = None
+        self._geo: Dict = {}
+
+    def transposed(self):
+        if self._t is None:
+            dev = self.index.device
+            ts = torch.empty(self.n_src + 1, dtype=torch.int64, device=dev)
+            tr = torch.empty(max(self.E, 1), dtype=torch.int64, device=dev)[:self.E]
+            tp = torch.empty(max(self.E, 1), dtype=torch.int64, device=dev)[:self.E]
+            ws = torch.empty(max(self.n_src, 1), dtype=torch.int64, device=dev)
+            call("gaot_csr_transpose", ptr(self.index), ptr(self.splits), self.m, self.n_src, self.E, ptr(ts), ptr(tr),
+                 ptr(tp), ptr(ws))
+            self._t = (ts, tr, tp)
+        return self._t
+
+
+def graph_plan(nbrs, n_src: int) -> GraphPlan:
+    """Plan cached inside the graph dict (key '_gaot_plan') so that it lives exactly as long as the graph."""
+    if isinstance(nbrs, GraphPlan):
+        return nbrs
+    plan = nbrs.get("_gaot_plan") if isinstance(nbrs, dict) else None
+    if plan is None or plan.n_src != n_src or plan.index.data_ptr() != nbrs["neighbors_index"].data_ptr():
+        plan = GraphPlan(nbrs["neighbors_index"], nbrs["neighbors_row_splits"], n_src)
+        if isinstance(nbrs, dict):
+            nbrs["_gaot_plan"] = plan
+    return plan
+
+
+def merge_graphs(graphs: List[dict], n_src_each: int) -> GraphPlan:
+    """Block-diagonal merge of per-sample CSR graphs (vx mode): sample b's sources are offset by
+    b*n_src_each and its rows appended after sample b-1's rows.  One launch then serves the batch."""
+    idx = torch.cat([g["neighbors_index"].to(torch.int64) + b * n_src_each for b, g in enumerate(graphs)])
+    parts, off = [graphs[0]["neighbors_row_splits"][:1].to(torch.int64)], 0
+    for g in graphs:
+        rs = g["neighbors_row_splits"].to(torch.int64)
+        parts.append(rs[1:] + off)
+        off += int(g["neighbors_index"].numel())
+    return GraphPlan(idx, torch.cat(parts), n_src_each * len(graphs))
+
+
+# ------------------------------------------------------------------------------------------------
+# dense
+# ------------------------------------------------------------------------------------------------
+def gemm(A, B, M, N, K, lda, ldb, transA, transB, out=None, bias=None, add=None, add_rows=0, act=ACT_NONE, pre=None,
+         accumulate=False):
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device=A.device)
+    call("gaot_gemm_f32", ptr(A), ptr(B), ptr(out), M, N, K, lda, ldb, N, int(transA), int(transB), ptr(bias), ptr(add),
+         int(add_rows), N, int(act), ptr(pre), int(accumulate))
+    return out
+
+
+def col_sum(x2d: torch.Tensor, M: int, N: int) -> torch.Tensor:
+    out = torch.empty(N, dtype=torch.float32, device=x2d.device)
+    call("gaot_col_sum", ptr(x2d), M, N, ptr(out), 0)
+    return out
+
+
+class _Linear(torch.autograd.Function):
+    """y = act(x W^T + bias + add[row % add_rows]); x [M,K], W [N,K] (nn.Linear layout)."""
+
+    @staticmethod
+    def forward(ctx, x, W, bias, add, act):
+        _need_cuda(x)
+        x, W = _c(x), _c(W)
+        M, K = x.shape
+        N = W.shape[0]
+        bias_c = _c(bias) if bias is not None else None
+        add_c = _c(add) if add is not None else None
+        add_rows = add_c.shape[0] if add_c is not None else 0
+        if add_c is not None and (add_c.shape[1] != N or M % add_rows != 0):
+            raise ValueError(f"broadcast-add of shape {tuple(add_c.shape)} does not tile an [{M},{N}] output")
+        pre = torch.empty((M, N), dtype=torch.float32, device=x.device) if act != ACT_NONE else None
+        y = gemm(x, W, M, N, K, K, K, 0, 1, bias=bias_c, add=add_c, add_rows=add_rows, act=act, pre=pre)
+        ctx.save_for_backward(x, W, pre)
+        ctx.act, ctx.has_bias, ctx.add_rows = act, bias is not None, add_rows
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, W, pre = ctx.saved_tensors
+        dy = _c(dy)
+        M, K = x.shape
+        N = W.shape[0]
+        if ctx.act != ACT_NONE:
+            dpre = torch.empty_like(dy)
+            call("gaot_act_bwd", ptr(dy), ptr(pre), ptr(dpre), dy.numel(), ctx.act)
+        else:
+            dpre = dy
+        dx = dW = db = dadd = None
+        if ctx.needs_input_grad[0]:
+            dx = gemm(dpre, W, M, K, N, N, K, 0, 0)                  # [M,N] x [N,K]
+        if ctx.needs_input_grad[1]:
+            dW = gemm(dpre, x, N, K, M, N, K, 1, 0)                  # dpre^T [N,M] x [M,K]
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = col_sum(dpre, M, N)
+        if ctx.add_rows and ctx.needs_input_grad[3]:
+            dadd = dpre if ctx.add_rows == M else col_sum(dpre, M // ctx.add_rows, ctx.add_rows * N).view(ctx.add_rows, N)
+        return dx, dW, db, dadd, None
+
+
+def linear(x, W, bias=None, add=None, act=ACT_NONE):
+    return _Linear.apply(x, W, bias, add, act)
+
+
+class _RMSNorm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, eps):
+        x, gamma = _c(x), _c(gamma)
+        rows, D = x.shape
+        y = torch.empty_like(x)
+        rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
+        call("gaot_rmsnorm_fwd", ptr(x), ptr(gamma), ptr(y), ptr(rstd), rows, D, float(eps))
+        ctx.save_for_backward(x, gamma, rstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, gamma, rstd = ctx.saved_tensors
+        dy = _c(dy)
+        rows, D = x.shape
+        dx = torch.empty_like(x)
+        dg = torch.zeros(D, dtype=torch.float32, device=x.device)
+        call("gaot_rmsnorm_bwd", ptr(dy), ptr(x), ptr(gamma), ptr(rstd), ptr(dx), ptr(dg), rows, D)
+        return dx, dg, None
+
+
+def rmsnorm(x, gamma, eps):
+    return _RMSNorm.apply(x, gamma, eps)
+
+
+class _SwiGLU(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, ab):
+        ab = _c(ab)
+        rows, F2 = ab.shape
+        u = torch.empty((rows, F2 // 2), dtype=torch.float32, device=ab.device)
+        call("gaot_swiglu_fwd", ptr(ab), ptr(u), rows, F2 // 2)
+        ctx.save_for_backward(ab)
+        return u
+
+    @staticmethod
+    def backward(ctx, du):
+        (ab,) = ctx.saved_tensors
+        du = _c(du)
+        dab = torch.empty_like(ab)
+        call("gaot_swiglu_bwd", ptr(du), ptr(ab), ptr(dab), ab.shape[0], ab.shape[1] // 2)
+        return dab
+
+
+def swiglu(ab):
+    return _SwiGLU.apply(ab)
+
+
+class _Attention(torch.autograd.Function):
+    """qkv [B*T, (H + 2*Hkv)*hd] = [q | k | v] per token -> o [B*T, H*hd]."""
+
+    @staticmethod
+    def forward(ctx, qkv, B, T, H, Hkv, hd):
+        qkv = _c(qkv)
+        ld = qkv.shape[1]
+        o = torch.empty((B * T, H * hd), dtype=torch.float32, device=qkv.device)
+        lse = torch.empty((B, H, T), dtype=torch.float32, device=qkv.device)
+        scale = 1.0 / (hd ** 0.5)
+        base = qkv.data_ptr()
+        call("gaot_attention_fwd", base, base + 4 * H * hd, base + 4 * (H + Hkv) * hd, ptr(o), ptr(lse), B, T, H, Hkv, hd,
+             ld, ld, scale)
+        ctx.save_for_backward(qkv, o, lse)
+        ctx.dims = (B, T, H, Hkv, hd, scale)
+        return o
+
+    @staticmethod
+    def backward(ctx, do):
+        qkv, o, lse = ctx.saved_tensors
+        B, T, H, Hkv, hd, scale = ctx.dims
+        do = _c(do)
+        ld = qkv.shape[1]
+        dqkv = torch.empty_like(qkv)
+        delta = torch.empty_like(lse)
+        b, d = qkv.data_ptr(), dqkv.data_ptr()
+        ok, ov = 4 * H * hd, 4 * (H + Hkv) * hd
+        call("gaot_attention_bwd", b, b + ok, b + ov, ptr(o), ptr(lse), ptr(do), ptr(delta), d, d + ok, d + ov, B, T, H, Hkv,
+             hd, ld, ld, scale)
+        return dqkv, None, None, None, None, None
+
+
+def attention(qkv, B, T, H, Hkv, hd):
+    return _Attention.apply(qkv, B, T, H, Hkv, hd)
+
+
+class _PatchPermute(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, grid, P, C, to_tokens):
+        x = _c(x)
+        B = x.shape[0]
+        dims = len(grid)
+        H, W = grid[0], grid[1]
+        D = grid[2] if dims == 3 else 1
+        nodes, pv = H * W * D, P ** dims
+        out = torch.empty((B, nodes // pv, pv * C) if to_tokens else (B, nodes, C), dtype=torch.float32, device=x.device)
+        call("gaot_patch_permute", ptr(x), ptr(out), B, dims, H, W, D, P, C, int(to_tokens))
+        ctx.args = (grid, P, C, to_tokens)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        grid, P, C, to_tokens = ctx.args
+        return _PatchPermute.apply(g, grid, P, C, not to_tokens), None, None, None, None
+
+
+def patchify(x, grid, P):
+    return _PatchPermute.apply(x, tuple(grid), P, x.shape[-1], True)
+
+
+def unpatchify(x, grid, P, C):
+    return _PatchPermute.apply(x, tuple(grid), P, C, False)
+
+
+# ------------------------------------------------------------------------------------------------
+# AGNO
+# ------------------------------------------------------------------------------------------------
+def edge_inputs(y, x, plan: GraphPlan):
+    y, x = _c(y), _c(x)
+    z = torch.empty((plan.E, y.shape[1] + x.shape[1]), dtype=torch.float32, device=y.device)
+    call("gaot_edge_inputs", ptr(y), y.shape[1], ptr(x), x.shape[1], ptr(plan.index), ptr(plan.edge_row), plan.E, ptr(z))
+    return z
+
+
+def edge_cosine_softmax(y, x, cd, plan: GraphPlan):
+    y, x = _c(y), _c(x)
+    alpha = torch.empty(max(plan.E, 1), dtype=torch.float32, device=y.device)[:plan.E]
+    call("gaot_edge_cosine_softmax", ptr(y), y.shape[1], ptr(x), x.shape[1], int(cd), ptr(plan.index), ptr(plan.splits),
+         plan.m, ptr(alpha))
+    return alpha
+
+
+class _ScaleRows(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, k, alpha):
+        k = _c(k)
+        out = torch.empty_like(k)
+        call("gaot_scale_rows", ptr(k), ptr(alpha), k.shape[0], k.shape[1], ptr(out))
+        ctx.save_for_backward(alpha)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (alpha,) = ctx.saved_tensors
+        g = _c(g)
+        out = torch.empty_like(g)
+        call("gaot_scale_rows", ptr(g), ptr(alpha), g.shape[0], g.shape[1], ptr(out))
+        return out, None
+
+
+def scale_rows(k, alpha):
+    return _ScaleRows.apply(k, alpha)
+
+
+class _Aggregate(torch.autograd.Function):
+    """out[b,r,:] = sum_{e in row r} w[e,:] * f[b,index[e],:]  (agno.py:198,245-271)."""
+
+    @staticmethod
+    def forward(ctx, f, w, plan):
+        f, w = _c(f), _c(w)
+        B, Ns, C = f.shape
+        if Ns != plan.n_src or w.shape[0] != plan.E or w.shape[1] != C:
+            raise ValueError(f"aggregate: f {tuple(f.shape)} / w {tuple(w.shape)} do not match graph (n_src={plan.n_src}, E={plan.E})")
+        out = torch.empty((B, plan.m, C), dtype=torch.float32, device=f.device)
+        call("gaot_agno_aggregate", ptr(f), ptr(w), 0, ptr(plan.index), ptr(plan.splits), ptr(out), B, Ns, plan.m, C)
+        ctx.save_for_backward(f, w)
+        ctx.plan = plan
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        f, w = ctx.saved_tensors
+        plan = ctx.plan
+        g = _c(g)
+        B, Ns, C = f.shape
+        df = dw = None
+        if ctx.needs_input_grad[0]:
+            ts, tr, tp = plan.transposed()
+            df = torch.empty_like(f)
+            call("gaot_agno_aggregate", ptr(g), ptr(w), ptr(tp), ptr(tr), ptr(ts), ptr(df), B, plan.m, Ns, C)
+        if ctx.needs_input_grad[1]:
+            dw = torch.empty_like(w)
+            call("gaot_agno_weight_grad", ptr(g), ptr(f), ptr(plan.index), ptr(plan.splits), ptr(dw), B, Ns, plan.m, plan.E, C)
+        return df, dw, None
+
+
+def agno_aggregate(f, w, plan):
+    return _Aggregate.apply(f, w, plan)
+
+
+def segment_csr(src: torch.Tensor, indptr: torch.Tensor, reduce: str = "sum", use_scatter: bool = True) -> torch.Tensor:
+    """Drop-in for reference segment_csr (src/model/layers/utils/segment_csr.py:14-19), forward only:
+    src [E,C] / [B,E,C] / [E], indptr [m+1] (or [B,m+1] repeated rows, as agno.py:266-269 builds it)."""
+    _need_cuda(src)
+    code = {"sum": 0, "mean": 1, "max": 2}.get(reduce)
+    if code is None:
+        raise ValueError("reduce must be one of 'mean', 'sum', 'max'")
+    if indptr.ndim == 2:
+        indptr = indptr[0]
+    s = _c(src)
+    shape = s.shape
+    if s.ndim == 1:
+        s3 = s.view(1, -1, 1)
+    elif s.ndim == 2:
+        s3 = s.view(1, shape[0], shape[1])
+    else:
+        s3 = s
+    B, E, C = s3.shape
+    m = indptr.numel() - 1
+    out = torch.empty((B, m, C), dtype=torch.float32, device=s.device)
+    ip = indptr.to(torch.int64).contiguous()
+    call("gaot_segment_csr", ptr(s3), ptr(ip), ptr(out), B, E, m, C, code)
+    if src.ndim == 1:
+        return out.view(m)
+    if src.ndim == 2:
+        return out.view(m, C)
+    return out
+
+
+def geo_stats(src, queries, plan: GraphPlan, groups: int = 1):
+    """Standardised statistical features [m, 3+2d] (gemb.py:83-171); `groups` consecutive row blocks
+    are standardised separately (vx mode merged graphs)."""
+    src, queries = _c(src), _c(queries)
+    d = queries.shape[1]
+    feat = torch.empty((plan.m, 3 + 2 * d), dtype=torch.float32, device=src.device)
+    call("gaot_geo_stats", ptr(src), ptr(queries), d, ptr(plan.index), ptr(plan.splits), plan.m, ptr(feat))
+    call("gaot_col_standardize", ptr(feat), plan.m // groups, 3 + 2 * d, groups)
+    return feat
+
+
+# ------------------------------------------------------------------------------------------------
+# step
+# ------------------------------------------------------------------------------------------------
+class _MSE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, target):
+        pred, target = _c(pred), _c(target)
+        loss = torch.zeros(1, dtype=torch.float32, device=pred.device)
+        dpred = torch.empty_like(pred)
+        call("gaot_mse_fwd_bwd", ptr(pred), ptr(target), ptr(loss), ptr(dpred), pred.numel(), 1.0)
+        ctx.save_for_backward(dpred)
+        return loss.view(())
+
+    @staticmethod
+    def backward(ctx, g):
+        (dpred,) = ctx.saved_tensors
+        return dpred * g, None
+
+
+def mse_loss(pred, target):
+    return _MSE.apply(pred, target)
+
+
+def adamw_step(param, grad, exp_avg, exp_avg_sq, step, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, grad_scale=1.0):
+    call("gaot_adamw_step", ptr(param), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), param.numel(), float(lr), float(betas[0]),
+         float(betas[1]), float(eps), float(weight_decay), int(step), float(grad_scale))
+
+
+def rollout_update(pred, u_in, dt, mode, u_mean, u_std, s_mean, s_std):
+    pred = _c(pred)
+    u_in = _c(u_in) if u_in is not None else None
+    C = pred.shape[-1]
+    out = torch.empty_like(pred)
+    call("gaot_rollout_update", ptr(pred), ptr(u_in), ptr(out), pred.numel() // C, C,
+         float(dt), int(mode), ptr(u_mean), ptr(u_std), ptr(s_mean), ptr(s_std))
+    return out

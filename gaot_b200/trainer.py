@@ -1,0 +1,91 @@
+"""The training step around the hot path, restated from the reference's trainer loop
+(src/utils/optimizers.py:252-255: zero_grad -> train_step -> backward -> step;
+src/trainer/static_trainer.py:160-202: forward + MSE; src/core/base_trainer.py:71).
+
+B200-native differences: parameters, gradients and both AdamW moments live in four flat fp32
+buffers (one fused optimizer kernel, one all-reduce over the whole gradient); data parallelism is
+one process per GPU with a single NCCL all-reduce of the flat gradient per step (the reference has
+no working DP at all)."""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+
+
+class TrainStep:
+    def __init__(self, model: torch.nn.Module, lr: float = 1e-3, weight_decay: float = 1e-2, betas=(0.9, 0.999),
+                 eps: float = 1e-8, process_group: Optional[dist.ProcessGroup] = None, distributed: Optional[bool] = None):
+        self.model = model
+        self.lr, self.weight_decay, self.betas, self.eps = lr, weight_decay, betas, eps
+        self.group = process_group
+        self.distributed = dist.is_available() and dist.is_initialized() if distributed is None else distributed
+        self.world = dist.get_world_size(process_group) if self.distributed else 1
+        self.params = [p for p in model.parameters() if p.requires_grad]
+        dev = self.params[0].device
+        n = sum(p.numel() for p in self.params)
+        # 16-byte aligned segments so every parameter view stays vector-load friendly
+        offs, o = [], 0
+        for p in self.params:
+            offs.append(o)
+            o += (p.numel() + 3) // 4 * 4
+        self.flat_param = torch.zeros(o, dtype=torch.float32, device=dev)
+        self.flat_grad = torch.zeros(o, dtype=torch.float32, device=dev)
+        self.exp_avg = torch.zeros(o, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(o, dtype=torch.float32, device=dev)
+        for p, off in zip(self.params, offs):
+            view = self.flat_param[off:off + p.numel()].view_as(p)
+            view.copy_(p.data)
+            p.data = view
+            p.grad = self.flat_grad[off:off + p.numel()].view_as(p)
+        self.num_params = n
+        self.step_count = 0
+        if self.distributed and self.world > 1:
+            dist.broadcast(self.flat_param, src=0, group=self.group)     # identical replicas
+
+    # ---- the four calls of optimizers.py:252-255 ---------------------------------------------------
+    def zero_grad(self):
+        self.flat_grad.zero_()
+
+    def reduce_gradients(self):
+        if self.distributed and self.world > 1:
+            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.group)
+
+    def optimizer_step(self):
+        self.step_count += 1
+        ops.adamw_step(self.flat_param, self.flat_grad, self.exp_avg, self.exp_avg_sq, self.step_count, self.lr,
+                       self.betas, self.eps, self.weight_decay, grad_scale=1.0 / self.world)
+
+    def _finish(self, pred, y):
+        loss = ops.mse_loss(pred, y)
+        loss.backward()
+        self.reduce_gradients()
+        self.optimizer_step()
+        return loss.detach()
+
+    def fixed_coords_step(self, latent, coord, x, y, encoder_nbrs=None, decoder_nbrs=None):
+        """static_trainer.py:160-178 (+ backward + AdamW): x [B,N,Cin], y [B,N,Cout] -> scalar loss tensor."""
+        self.zero_grad()
+        pred = self.model(latent_tokens_coord=latent, xcoord=coord, pndata=x, encoder_nbrs=encoder_nbrs,
+                          decoder_nbrs=decoder_nbrs)
+        return self._finish(pred, y)
+
+    def variable_coords_step(self, latent, x, y, coords, encoder_graphs, decoder_graphs):
+        """static_trainer.py:180-202: per-sample coords [B,N,d] and per-sample graphs."""
+        self.zero_grad()
+        pred = self.model(latent_tokens_coord=latent, xcoord=coords, pndata=x, query_coord=coords,
+                          encoder_nbrs=encoder_graphs, decoder_nbrs=decoder_graphs)
+        return self._finish(pred, y)
+
+    def train_step(self, batch, latent, coord=None):
+        """Dispatch on the reference's batch tuple layouts."""
+        if len(batch) == 2:
+            x, y = batch
+            return self.fixed_coords_step(latent, coord, x, y)
+        if len(batch) == 5:
+            x, y, coords, enc, dec = batch
+            return self.variable_coords_step(latent, x, y, coords, enc, dec)
+        raise ValueError(f"unsupported batch tuple of length {len(batch)}")

@@ -1,0 +1,186 @@
+/* gaot_b200 - C ABI of the B200-native GAOT forward/backward hot path.
+ *
+ * Every entry point
+ *   - takes plain device pointers + sizes (no torch types), row-major contiguous unless a leading
+ *     dimension is passed, fp32 activations/weights, int64 CSR arrays exactly as the reference
+ *     stores them ({"neighbors_index", "neighbors_row_splits"}, src/model/layers/utils/neighbor_search.py:80-90);
+ *   - is asynchronous on `stream` (a cudaStream_t passed as void*), never synchronises, keeps no
+ *     global state, and is re-entrant per stream;
+ *   - returns 0 on success or a cudaError_t value (>0) / GAOT_E_* (<0) on failure.  The caller
+ *     allocates every output and workspace.
+ *
+ * The comment on each function names the reference interface it replaces (paths relative to the
+ * reference checkout /root/reference).  The reference has no FFI of its own (pure Python over
+ * torch / torch_scatter / torch_cluster wheels); INTEGRATION.md shows the ctypes binding a maintainer
+ * would add in those modules.
+ */
+#ifndef GAOT_B200_H
+#define GAOT_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GAOT_E_BADARG (-1)   /* unsupported size / null pointer / bad flag            */
+#define GAOT_E_ALIGN  (-2)   /* pointer or leading dimension violates an alignment rule */
+
+/* activation codes for the dense epilogues */
+#define GAOT_ACT_NONE 0
+#define GAOT_ACT_GELU 1      /* exact erf GELU (torch F.gelu default)  */
+#define GAOT_ACT_RELU 2
+
+int gaot_abi_version(void);
+/* kernels launched by this library in this process so far (diagnostics; bench.py `gpu_launches`) */
+long long gaot_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Radius graph.  Replaces NeighborSearch.forward and its back-ends
+ * (src/model/layers/utils/neighbor_search.py:65-106, :108-144 `native`, :147-180 `torch_cluster`,
+ * :275-335 `chunked`) and the per-sample loops of src/datasets/graph_builder.py:28-87.
+ * Row q lists, in ascending j, every j with sum_k (data[j,k]-queries[q,k])^2 (<=|<) r*r, all in
+ * fp32 with no fma contraction (bit-exact with the oracle).  inclusive=1,max_nbrs=0 is `native`;
+ * inclusive=0,max_nbrs=32 is torch_cluster.radius as the reference calls it.
+ * Two phases because E is data dependent: count writes the finished row_splits (exclusive scan,
+ * row_splits[m] = E); the caller reads E, allocates index[E], and calls fill.
+ * `batch` graphs are built in one launch (vx mode): data [batch, n, d] if data_batched else [n, d],
+ * queries likewise; row_splits [batch, m+1] (each starting at 0), index_offsets [batch] gives where
+ * each sample's edges start inside `index`.
+ * ---------------------------------------------------------------------------------------------- */
+int gaot_radius_count(const float* data, int64_t n, const float* queries, int64_t m, int d,
+                      float radius, int inclusive, int64_t max_nbrs,
+                      int64_t batch, int data_batched, int queries_batched,
+                      int64_t* row_splits, void* stream);
+int gaot_radius_fill(const float* data, int64_t n, const float* queries, int64_t m, int d,
+                     float radius, int inclusive, int64_t max_nbrs,
+                     int64_t batch, int data_batched, int queries_batched,
+                     const int64_t* row_splits, const int64_t* index_offsets,
+                     int64_t* index, void* stream);
+
+/* edge_row[e] = the CSR row of edge e (the reference materialises the same thing with
+ * torch.repeat_interleave, src/model/layers/agno.py:206-207). */
+int gaot_csr_edge_rows(const int64_t* row_splits, int64_t m, int64_t* edge_row, void* stream);
+
+/* Source-sorted (transposed) view of a CSR graph, needed by the backward of the gather
+ * (autograd's index_add for agno.py:198).  t_splits [n_src+1]; t_rows[k] = destination row of the
+ * k-th transposed edge; t_perm[k] = its edge id in the original CSR.  Lists ascending in edge id. */
+int gaot_csr_transpose(const int64_t* index, const int64_t* row_splits, int64_t m, int64_t n_src,
+                       int64_t E, int64_t* t_splits, int64_t* t_rows, int64_t* t_perm,
+                       int64_t* cursor_ws /* [n_src] workspace */, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * AGNO (src/model/layers/agno.py:148-273).
+ * ---------------------------------------------------------------------------------------------- */
+/* z[e,:] = [ y[index[e], :dy], x[row(e), :dx] ]   (agno.py:188, 206-207, 229) */
+int gaot_edge_inputs(const float* y, int64_t dy, const float* x, int64_t dx,
+                     const int64_t* index, const int64_t* edge_row, int64_t E, float* z, void* stream);
+
+/* alpha[e] = softmax over the row of cos(x_row, y_j) using the first `cd` coordinates
+ * (F.normalize eps 1e-12; agno.py:218-224 and _segment_softmax :112-146). */
+int gaot_edge_cosine_softmax(const float* y, int64_t dy, const float* x, int64_t dx, int64_t cd,
+                             const int64_t* index, const int64_t* row_splits, int64_t m,
+                             float* alpha, void* stream);
+
+/* out[e,c] = scale[e] * in[e,c]    (agno.py:250 forward; alpha * dW in the backward) */
+int gaot_scale_rows(const float* in, const float* scale, int64_t rows, int64_t C, float* out, void* stream);
+
+/* out[b,r,c] = sum_{e in row r} w[p(e),c] * f[b,index[e],c],  p(e) = w_perm ? w_perm[e] : e.
+ * Replaces the gather + multiply + torch_scatter.segment_csr chain
+ * (agno.py:198, 245-250, 264-271; src/model/layers/utils/segment_csr.py:48-55).
+ * With the transposed graph and w_perm = t_perm it is also the backward w.r.t. f. */
+int gaot_agno_aggregate(const float* f, const float* w, const int64_t* w_perm,
+                        const int64_t* index, const int64_t* row_splits,
+                        float* out, int64_t B, int64_t Ns, int64_t Nd, int64_t C, void* stream);
+
+/* dw[e,c] = sum_b g[b,row(e),c] * f[b,index[e],c]   (backward of agno.py:245-271 w.r.t. the edge weights) */
+int gaot_agno_weight_grad(const float* g, const float* f, const int64_t* index,
+                          const int64_t* row_splits, float* dw,
+                          int64_t B, int64_t Ns, int64_t Nd, int64_t E, int64_t C, void* stream);
+
+/* generic segment reduction of src[B,E,C] over CSR rows, reduce 0=sum 1=mean 2=max (empty -> 0);
+ * the drop-in for segment_csr(src, indptr, reduce) (segment_csr.py:14-19). */
+int gaot_segment_csr(const float* src, const int64_t* row_splits, float* out,
+                     int64_t B, int64_t E, int64_t m, int64_t C, int reduce, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Statistical geometry embedding, parameter-free part
+ * (GeometricEmbedding._compute_statistical_features, src/model/layers/gemb.py:83-171).
+ * feat [m, 3+2d] = [deg, mean dist, var dist, centroid-q (d), eig(cov) descending (d)], empty rows 0,
+ * then every column standardised over the m rows (unbiased std, std<1e-6 -> 1).  fp64 inside.
+ * ---------------------------------------------------------------------------------------------- */
+int gaot_geo_stats(const float* src, const float* queries, int64_t d,
+                   const int64_t* index, const int64_t* row_splits, int64_t m,
+                   float* feat, void* stream);
+/* standardises each of `groups` consecutive blocks of m rows separately (vx mode: one block per sample) */
+int gaot_col_standardize(float* feat, int64_t m, int64_t F, int64_t groups, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Dense layers: nn.Linear / 1x1 Conv1d of src/model/layers/mlp.py:283-337, attn.py:92-94,117,151,
+ * gaot.py:208.  C[M,N] = act( opA(A)[M,K] * opB(B)[K,N] + bias[n] + add[(m % add_rows), n] ),
+ * opA(A)[m,k] = transA ? A[k*lda+m] : A[m*lda+k];  opB(B)[k,n] = transB ? B[n*ldb+k] : B[k*ldb+n].
+ * accumulate=1 adds the result to what C already holds.  pre (nullable) receives the value before
+ * the activation.  fp32 FFMA arithmetic (the parity path).
+ * ---------------------------------------------------------------------------------------------- */
+int gaot_gemm_f32(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K,
+                  int64_t lda, int64_t ldb, int64_t ldc, int transA, int transB,
+                  const float* bias, const float* add, int64_t add_rows, int64_t ldadd,
+                  int act, float* pre, int accumulate, void* stream);
+
+/* out[n] (+)= sum_m x[m,n]  (bias gradients) */
+int gaot_col_sum(const float* x, int64_t M, int64_t N, float* out, int accumulate, void* stream);
+/* dx = dy * act'(pre) */
+int gaot_act_bwd(const float* dy, const float* pre, float* dx, int64_t n, int act, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Processor pieces (src/model/layers/attn.py).
+ * ---------------------------------------------------------------------------------------------- */
+/* RMSNorm.forward (attn.py:167-172): y = x * rsqrt(mean(x^2)+eps) * gamma; rstd[rows] saved. */
+int gaot_rmsnorm_fwd(const float* x, const float* gamma, float* y, float* rstd,
+                     int64_t rows, int64_t D, float eps, void* stream);
+int gaot_rmsnorm_bwd(const float* dy, const float* x, const float* gamma, const float* rstd,
+                     float* dx, float* dgamma /* accumulated, caller zeroes */,
+                     int64_t rows, int64_t D, void* stream);
+/* FFN gate (attn.py:150-156): u = silu(ab[:, :F]) * ab[:, F:]  with ab = x [W1;W3]^T  [rows, 2F] */
+int gaot_swiglu_fwd(const float* ab, float* u, int64_t rows, int64_t F, void* stream);
+int gaot_swiglu_bwd(const float* du, const float* ab, float* dab, int64_t rows, int64_t F, void* stream);
+
+/* Non-causal softmax(Q K^T * scale) V, GroupQueryFlashAttention.forward (attn.py:96-116).
+ * q[(b*T+t)*ldq + h*hd + i], k/v[(b*T+t)*ldk + hk*hd + i] with hk = h / (H/Hkv);
+ * o [B,T,H*hd] contiguous; lse [B,H,T].  hd in {16,32,64}. */
+int gaot_attention_fwd(const float* q, const float* k, const float* v, float* o, float* lse,
+                       int64_t B, int64_t T, int64_t H, int64_t Hkv, int64_t hd,
+                       int64_t ldq, int64_t ldk, float scale, void* stream);
+/* delta [B,H,T] is workspace.  dq/dk/dv use the same strides as q/k/v. */
+int gaot_attention_bwd(const float* q, const float* k, const float* v, const float* o,
+                       const float* lse, const float* dout, float* delta,
+                       float* dq, float* dk, float* dv,
+                       int64_t B, int64_t T, int64_t H, int64_t Hkv, int64_t hd,
+                       int64_t ldq, int64_t ldk, float scale, void* stream);
+
+/* Patchify / un-patchify permutations of GAOT.process (src/model/gaot.py:182-185, 202-205, 225-231).
+ * grid [B, H*W*(D), C] <-> tokens [B, T, P^dims * C]; dims 2 or 3; to_tokens 1 = patchify. */
+int gaot_patch_permute(const float* in, float* out, int64_t B, int dims, int64_t H, int64_t W,
+                       int64_t D, int64_t P, int64_t C, int to_tokens, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Step (src/trainer/static_trainer.py:160-178, src/core/base_trainer.py:71, src/utils/optimizers.py:252-255)
+ * ---------------------------------------------------------------------------------------------- */
+/* loss[0] += mean((pred-target)^2) (caller zeroes); dpred = 2 (pred-target) / n * gscale (nullable). */
+int gaot_mse_fwd_bwd(const float* pred, const float* target, float* loss, float* dpred,
+                     int64_t n, float gscale, void* stream);
+/* torch.optim.AdamW step on a flat parameter buffer; grad is multiplied by grad_scale first
+ * (1/world_size after a summing all-reduce). */
+int gaot_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                    float lr, float beta1, float beta2, float eps, float weight_decay,
+                    int64_t step, float grad_scale, void* stream);
+
+/* Rollout update rule of GAOT._process_autoregressive_prediction (src/model/gaot.py:436-476).
+ * mode 0 output, 1 residual, 2 time_der.  All tensors [rows, C]; stats are per channel [C]. */
+int gaot_rollout_update(const float* pred, const float* u_in, float* u_next, int64_t rows, int64_t C,
+                        float dt, int mode, const float* u_mean, const float* u_std,
+                        const float* s_mean, const float* s_std, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GAOT_B200_H */

@@ -1,5 +1,6 @@
-"""Shared test helpers: golden loading and error metrics."""
+"""Shared test helpers: golden loading, error metrics, model construction from oracle/cases.py."""
 import os
+from types import SimpleNamespace
 
 import numpy as np
 import torch
@@ -37,3 +38,20 @@ def rel_l2(a, b):
     a = torch.as_tensor(a).detach().double().cpu()
     b = torch.as_tensor(b).detach().double().cpu()
     return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def graphs_to(graphs, device):
+    if isinstance(graphs, dict):
+        return {k: v.to(device) for k, v in graphs.items()}
+    return [graphs_to(g, device) for g in graphs]
+
+
+def build_model(case: dict, device="cuda"):
+    """gaot_b200.model.GAOT for a case of oracle/cases.py (the same hyper-parameters the golden generator
+    gave the reference)."""
+    from gaot_b200.model import GAOT, AttentionConfig, MAGNOConfig, TransformerConfig
+    t = dict(case["transformer"])
+    t["attn_config"] = AttentionConfig(**case["attn"])
+    cfg = SimpleNamespace(latent_tokens_size=tuple(case["latent"]),
+                          args=SimpleNamespace(magno=MAGNOConfig(**case["magno"]), transformer=TransformerConfig(**t)))
+    return GAOT(case["cin"], case["cout"], cfg).to(device)

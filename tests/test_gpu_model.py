@@ -1,0 +1,128 @@
+"""GPU parity of the whole GAOT forward/backward (gaot_b200.model, through the C ABI) against golden
+vectors produced by the unmodified reference (tests/golden, oracle/make_golden.py).  Run with -m gpu.
+
+Tolerances: forward <= 1e-5 relative L2 (BASELINE.json north_star).  Gradients: per tensor
+max(1e-4, 10 x the fp32 noise floor of the reference arithmetic for that tensor), the floor being the
+`gerr32` array stored with each fixture (oracle fp32 vs fp64 on the same graph)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import cases, gaot_oracle as orc
+from tests.helpers import (build_model, golden_graphs, golden_params, golden_shapes, graphs_to, load_golden, rel_l2)
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+FWD_TOL = 1e-5
+
+
+def _run(name, use_golden_graphs):
+    c = cases.CASES[name]
+    g = load_golden(name)
+    model = build_model(c)
+    model.load_state_dict({k: v.to(DEV) for k, v in golden_params(g).items()})
+    model.train()
+    lat, x, pn, tgt = [t.to(DEV) for t in cases.case_inputs(name)]
+    enc = dec = None
+    if use_golden_graphs:
+        vx = bool(c.get("vx"))
+        enc, dec = graphs_to(golden_graphs(g, "enc", vx), DEV), graphs_to(golden_graphs(g, "dec", vx), DEV)
+        model.encoder.precompute_edges = model.decoder.precompute_edges = True
+    inter = {}
+    hooks = [model.encoder.register_forward_hook(lambda m, i, o: inter.__setitem__("enc_out", o.detach())),
+             model.processor.register_forward_hook(lambda m, i, o: inter.__setitem__("proc_out", o.detach()))]
+    out = model(lat, x, pn, encoder_nbrs=enc, decoder_nbrs=dec)
+    for h in hooks:
+        h.remove()
+    from gaot_b200 import ops
+    loss = ops.mse_loss(out, tgt)
+    loss.backward()
+    return c, g, model, out, loss, inter
+
+
+@pytest.mark.parametrize("name,golden_graph", [("tiny2d", False), ("tiny2d", True), ("tiny3d", False),
+                                               ("plain2d", False), ("vx2d", True)])
+def test_forward_backward_matches_reference(name, golden_graph):
+    c, g, model, out, loss, inter = _run(name, golden_graph)
+    assert rel_l2(inter["enc_out"], g["enc_out"]) < FWD_TOL
+    assert rel_l2(out, g["out"]) < FWD_TOL
+    assert abs(float(loss) - float(g["loss64"])) < 1e-5 * abs(float(g["loss64"]))
+    floors = {str(k): float(e) for k, e in zip(g["keys"], g["gerr32"])}
+    worst = 0.0
+    for k, p in model.named_parameters():
+        assert p.grad is not None, k
+        err = rel_l2(p.grad, g["grad." + k])
+        tol = max(1e-4, 10 * floors[k])
+        assert err < tol, (k, err, tol)
+        worst = max(worst, err)
+    print(f"{name}: out {rel_l2(out, g['out']):.2e} worst grad {worst:.2e}")
+
+
+def test_vx_graphs_built_on_gpu_match_reference():
+    from gaot_b200 import ops
+    c = cases.CASES["vx2d"]
+    g = load_golden("vx2d")
+    lat, x, _, _ = cases.case_inputs("vx2d")
+    r = c["magno"]["radius"]
+    enc = ops.radius_csr(x.to(DEV), lat.to(DEV), r)
+    dec = ops.radius_csr(lat.to(DEV), x.to(DEV), r)
+    for b in range(c["B"]):
+        for mine, ref in ((enc[b], golden_graphs(g, "enc", True)[b][0]), (dec[b], golden_graphs(g, "dec", True)[b][0])):
+            assert torch.equal(mine["neighbors_index"].cpu(), ref["neighbors_index"])
+            assert torch.equal(mine["neighbors_row_splits"].cpu(), ref["neighbors_row_splits"])
+
+
+def test_cfg2_matches_reference_summary():
+    """BASELINE cfg-2 geometry (N=9216, latent 64x64, r=0.033, 3.4 M parameters), B=2."""
+    c = cases.CASES["cfg2"]
+    g = load_golden("cfg2")
+    model = build_model(c)
+    params = cases.synth_params(golden_shapes(g), 7 + c["seed"])
+    model.load_state_dict({k: v.to(DEV) for k, v in params.items()})
+    lat, x, pn, tgt = [t.to(DEV) for t in cases.case_inputs("cfg2")]
+    inter = {}
+    model.encoder.register_forward_hook(lambda m, i, o: inter.__setitem__("enc", o.detach()))
+    model.processor.register_forward_hook(lambda m, i, o: inter.__setitem__("proc", o.detach()))
+    out = model(lat, x, pn)
+    assert rel_l2(inter["enc"][:, ::41, ::5], g["enc_sub"]) < FWD_TOL
+    assert rel_l2(out[:, ::37, :], g["out_sub"]) < FWD_TOL
+    assert abs(float(out.double().norm()) - float(g["out_norm"])) < 1e-5 * float(g["out_norm"])
+    from gaot_b200 import ops
+    loss = ops.mse_loss(out, tgt)
+    loss.backward()
+    assert abs(float(loss) - float(g["loss64"])) < 1e-5 * float(g["loss64"])
+    floors = {str(k): float(e) for k, e in zip(g["keys"], g["gerr32"])}
+    norms = {str(k): float(n) for k, n in zip(g["keys"], g["grad_norms"])}
+    grads = dict(model.named_parameters())
+    for k in norms:
+        got = float(grads[k].grad.double().norm())
+        assert abs(got - norms[k]) < max(1e-4, 10 * floors[k]) * norms[k], (k, got, norms[k])
+    for k in [kk[5:] for kk in g if kk.startswith("grad.")]:
+        assert rel_l2(grads[k].grad, g["grad." + k]) < max(1e-4, 10 * floors[k]), k
+
+
+def test_train_steps_match_oracle_adamw():
+    """3 optimizer steps of the restated trainer loop (optimizers.py:252-255) vs the oracle in fp64."""
+    from gaot_b200.trainer import TrainStep
+    name = "tiny2d"
+    c = cases.CASES[name]
+    g = load_golden(name)
+    model = build_model(c)
+    model.load_state_dict({k: v.to(DEV) for k, v in golden_params(g).items()})
+    lat, x, pn, tgt = cases.case_inputs(name)
+    step = TrainStep(model, lr=1e-3, weight_decay=1e-2)
+    cfg = orc.make_config(c["latent"], c["magno"], c["transformer"], c["attn"])
+    p = {k: v.double() for k, v in golden_params(g).items()}
+    m = {k: torch.zeros_like(v) for k, v in p.items()}
+    v_ = {k: torch.zeros_like(v) for k, v in p.items()}
+    enc, dec = orc.build_graphs(cfg.args.magno, x, lat), orc.build_graphs(cfg.args.magno, lat, x)
+    for it in range(1, 4):
+        loss = step.fixed_coords_step(lat.to(DEV), x.to(DEV), pn.to(DEV), tgt.to(DEV))
+        pr = {k: t.clone().requires_grad_(True) for k, t in p.items()}
+        lo = orc.train_step_loss(pr, cfg, lat.double(), x.double(), pn.double(), tgt.double(), enc, dec)
+        lo.backward()
+        p, m, v_ = orc.adamw_step({k: t.detach() for k, t in pr.items()}, {k: t.grad for k, t in pr.items()}, m, v_, it, 1e-3)
+        assert abs(float(loss) - float(lo)) < 2e-5 * abs(float(lo)), it
+    sd = model.state_dict()
+    for k in p:
+        assert rel_l2(sd[k], p[k]) < 2e-5, k

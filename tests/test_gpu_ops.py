@@ -1,0 +1,237 @@
+"""GPU parity of the individual C-ABI operators against the CPU oracle / fp64 torch (run with -m gpu).
+Integer outputs are compared bit-exact; floating point within the tolerance written in each test."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import cases, gaot_oracle as orc
+from tests.helpers import load_golden, rel_l2
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _ops():
+    from gaot_b200 import ops
+    return ops
+
+
+@pytest.mark.parametrize("name", cases.NBR_CASES)
+def test_radius_csr_bit_exact_vs_reference_golden(name):
+    ops = _ops()
+    g = load_golden("neighbors")
+    data, q, r = cases.nbr_case(name)
+    out = ops.radius_csr(data.to(DEV), q.to(DEV), r)
+    assert out["neighbors_index"].dtype == torch.int64 and out["neighbors_row_splits"].dtype == torch.int64
+    assert np.array_equal(out["neighbors_index"].cpu().numpy(), g[f"{name}.index"].astype(np.int64))
+    assert np.array_equal(out["neighbors_row_splits"].cpu().numpy(), g[f"{name}.splits"].astype(np.int64))
+
+
+@pytest.mark.parametrize("name", ["lattice2d", "rand3d"])
+def test_radius_csr_torch_cluster_semantics(name):
+    ops = _ops()
+    data, q, r = cases.nbr_case(name)
+    for incl, cap in [(False, None), (True, 3), (False, 32)]:
+        want = orc.radius_csr(data, q, r, inclusive=incl, max_num_neighbors=cap)
+        got = ops.radius_csr(data.to(DEV), q.to(DEV), r, inclusive=incl, max_num_neighbors=cap)
+        assert torch.equal(got["neighbors_index"].cpu(), want["neighbors_index"])
+        assert torch.equal(got["neighbors_row_splits"].cpu(), want["neighbors_row_splits"])
+
+
+def test_radius_csr_batched_equals_per_sample():
+    ops = _ops()
+    lat = cases.latent_grid((8, 8))
+    xs = torch.stack([cases.clustered_points(500, 2, 40 + b) for b in range(3)])
+    enc = ops.radius_csr(xs.to(DEV), lat.to(DEV), 0.3)          # data batched
+    dec = ops.radius_csr(lat.to(DEV), xs.to(DEV), 0.3)          # queries batched
+    for b in range(3):
+        for got, want in ((enc[b], orc.radius_csr(xs[b], lat, 0.3)), (dec[b], orc.radius_csr(lat, xs[b], 0.3))):
+            assert torch.equal(got["neighbors_index"].cpu(), want["neighbors_index"])
+            assert torch.equal(got["neighbors_row_splits"].cpu(), want["neighbors_row_splits"])
+
+
+def test_radius_csr_large_property():
+    """BASELINE cfg-2 size: the decoder graph is the transpose of the encoder graph, rows ascending."""
+    ops = _ops()
+    x = cases.uniform_points(9216, 2, 0).to(DEV)
+    lat = cases.latent_grid((64, 64)).to(DEV)
+    enc = ops.radius_csr(x, lat, 0.033)
+    dec = ops.radius_csr(lat, x, 0.033)
+    g = load_golden("cfg2")
+    assert int(enc["neighbors_index"].numel()) == int(g["enc_E"])
+    assert int(enc["neighbors_index"].sum()) == int(g["enc_index_sum"])
+    assert int(dec["neighbors_index"].sum()) == int(g["dec_index_sum"])
+    assert np.array_equal(enc["neighbors_row_splits"][::64].cpu().numpy(), g["enc_splits_sub"])
+    assert np.array_equal(dec["neighbors_row_splits"][::128].cpu().numpy(), g["dec_splits_sub"])
+    plan = ops.GraphPlan(enc["neighbors_index"], enc["neighbors_row_splits"], 9216)
+    ts, tr, tp = plan.transposed()
+    assert torch.equal(ts, dec["neighbors_row_splits"]) and torch.equal(tr, dec["neighbors_index"])
+
+
+def test_csr_transpose_and_edge_rows_vs_oracle():
+    ops = _ops()
+    data, q, r = cases.nbr_case("rand2d")
+    g = orc.radius_csr(data, q, r)
+    t = orc.csr_transpose(g, data.shape[0])
+    plan = ops.GraphPlan(g["neighbors_index"].to(DEV), g["neighbors_row_splits"].to(DEV), data.shape[0])
+    ts, tr, tp = plan.transposed()
+    assert torch.equal(ts.cpu(), t["neighbors_row_splits"])
+    assert torch.equal(tr.cpu(), t["neighbors_index"])
+    assert torch.equal(tp.cpu(), t["edge_perm"])
+    rs = g["neighbors_row_splits"]
+    row = torch.repeat_interleave(torch.arange(q.shape[0]), rs[1:] - rs[:-1])
+    assert torch.equal(plan.edge_row.cpu(), row)
+
+
+@pytest.mark.parametrize("M,N,K", [(300, 64, 4), (257, 130, 67), (1000, 1, 64), (64, 256, 1000), (5, 7, 3), (2048, 512, 256)])
+def test_linear_fwd_bwd_vs_fp64(M, N, K):
+    ops = _ops()
+    gen = torch.Generator().manual_seed(M * 7 + N)
+    x = torch.randn(M, K, generator=gen)
+    W = torch.randn(N, K, generator=gen) / K ** 0.5
+    b = torch.randn(N, generator=gen)
+    R = 5 if M % 5 == 0 else M
+    add = torch.randn(R, N, generator=gen)
+    for act, fact in ((ops.ACT_NONE, lambda t: t), (ops.ACT_GELU, torch.nn.functional.gelu), (ops.ACT_RELU, torch.relu)):
+        xs = [t.clone().to(DEV).requires_grad_(True) for t in (x, W, b, add)]
+        y = ops.linear(xs[0], xs[1], xs[2], add=xs[3], act=act)
+        xr = [t.clone().double().requires_grad_(True) for t in (x, W, b, add)]
+        yr = fact(xr[0] @ xr[1].T + xr[2] + xr[3].repeat(M // R, 1))
+        assert rel_l2(y, yr) < 2e-6
+        gy = torch.randn(M, N, generator=gen)
+        y.backward(gy.to(DEV))
+        yr.backward(gy.double())
+        for a, r_ in zip(xs, xr):
+            assert rel_l2(a.grad, r_.grad) < 5e-6
+
+
+def test_aggregate_fwd_bwd_vs_oracle():
+    ops = _ops()
+    data, q, r = cases.nbr_case("rand2d")
+    g = orc.radius_csr(data, q, r)
+    E = g["neighbors_index"].numel()
+    for C, B in ((64, 5), (16, 2), (48, 9), (6, 3), (128, 1)):
+        f = cases.normal((B, data.shape[0], C), 5)
+        w = cases.normal((E, C), 6)
+        fr, wr = f.double().requires_grad_(True), w.double().requires_grad_(True)
+        want = orc.segment_csr(wr.unsqueeze(0) * fr[:, g["neighbors_index"], :], g["neighbors_row_splits"], "sum")
+        fg, wg = f.to(DEV).requires_grad_(True), w.to(DEV).requires_grad_(True)
+        plan = ops.GraphPlan(g["neighbors_index"].to(DEV), g["neighbors_row_splits"].to(DEV), data.shape[0])
+        got = ops.agno_aggregate(fg, wg, plan)
+        assert rel_l2(got, want) < 1e-6
+        go = cases.normal(tuple(want.shape), 7)
+        want.backward(go.double())
+        got.backward(go.to(DEV))
+        assert rel_l2(fg.grad, fr.grad) < 1e-6
+        assert rel_l2(wg.grad, wr.grad) < 2e-6
+
+
+def test_segment_csr_dropin():
+    ops = _ops()
+    data, q, r = cases.nbr_case("lattice2d")          # has empty rows
+    g = orc.radius_csr(data, q, r)
+    E = g["neighbors_index"].numel()
+    src = cases.normal((3, E, 5), 8)
+    for red in ("sum", "mean", "max"):
+        want = orc.segment_csr(src, g["neighbors_row_splits"], red)
+        got = ops.segment_csr(src.to(DEV), g["neighbors_row_splits"].to(DEV), red)
+        assert rel_l2(got, want) < 1e-6
+    want = orc.segment_csr(src[0, :, 0], g["neighbors_row_splits"], "max")
+    got = ops.segment_csr(src[0, :, 0].contiguous().to(DEV), g["neighbors_row_splits"].to(DEV), "max")
+    assert rel_l2(got, want) < 1e-6
+
+
+@pytest.mark.parametrize("name", ["rand2d", "rand3d", "lattice2d"])
+def test_edge_softmax_and_geo_stats_vs_oracle(name):
+    ops = _ops()
+    data, q, r = cases.nbr_case(name)
+    g = orc.radius_csr(data, q, r)
+    plan = ops.GraphPlan(g["neighbors_index"].to(DEV), g["neighbors_row_splits"].to(DEV), data.shape[0])
+    seg, _ = orc._seg_ids(g["neighbors_row_splits"])
+    qd, yd = q.double()[seg], data.double()[g["neighbors_index"]]
+    s = (torch.nn.functional.normalize(qd, dim=-1) * torch.nn.functional.normalize(yd, dim=-1)).sum(-1)
+    ex = torch.exp(s - orc.segment_csr(s, g["neighbors_row_splits"], "max")[seg])
+    want = ex / orc.segment_csr(ex, g["neighbors_row_splits"], "sum")[seg]
+    got = ops.edge_cosine_softmax(data.to(DEV), q.to(DEV), data.shape[1], plan)
+    assert rel_l2(got, want) < 2e-6
+    z = ops.edge_inputs(data.to(DEV), q.to(DEV), plan)
+    assert torch.equal(z.cpu(), torch.cat([data[g["neighbors_index"]], q[seg]], dim=-1))
+    feat = ops.geo_stats(data.to(DEV), q.to(DEV), plan)
+    want = orc.geo_stat_features(data.double(), q.double(), g)
+    # the smallest covariance eigenvalue of near-degenerate neighbourhoods is the noisiest column
+    assert rel_l2(feat, want) < 5e-6
+
+
+@pytest.mark.parametrize("B,T,H,Hkv,hd", [(2, 100, 2, 2, 32), (1, 257, 4, 2, 16), (2, 64, 2, 1, 64)])
+def test_attention_fwd_bwd_vs_oracle(B, T, H, Hkv, hd):
+    ops = _ops()
+    W = (H + 2 * Hkv) * hd
+    qkv = cases.normal((B * T, W), 9)
+    go = cases.normal((B * T, H * hd), 10)
+
+    def ref(qkv64):
+        q = qkv64[:, :H * hd].view(B, T, H, hd).transpose(1, 2)
+        k = qkv64[:, H * hd:(H + Hkv) * hd].view(B, T, Hkv, hd).transpose(1, 2).repeat_interleave(H // Hkv, dim=1)
+        v = qkv64[:, (H + Hkv) * hd:].view(B, T, Hkv, hd).transpose(1, 2).repeat_interleave(H // Hkv, dim=1)
+        p = torch.softmax(q @ k.transpose(-1, -2) / hd ** 0.5, dim=-1)
+        return (p @ v).transpose(1, 2).reshape(B * T, H * hd)
+
+    a = qkv.double().requires_grad_(True)
+    want = ref(a)
+    want.backward(go.double())
+    b = qkv.to(DEV).requires_grad_(True)
+    got = ops.attention(b, B, T, H, Hkv, hd)
+    got.backward(go.to(DEV))
+    assert rel_l2(got, want) < 2e-6
+    assert rel_l2(b.grad, a.grad) < 5e-6
+
+
+def test_rmsnorm_swiglu_patch_mse_adamw():
+    ops = _ops()
+    x = cases.normal((77, 96), 11)
+    gm = 1 + 0.1 * cases.normal((96,), 12)
+    go = cases.normal((77, 96), 13)
+    a, ag = x.double().requires_grad_(True), gm.double().requires_grad_(True)
+    want = a * torch.rsqrt(a.pow(2).mean(-1, keepdim=True) + 1e-6) * ag
+    want.backward(go.double())
+    b, bg = x.to(DEV).requires_grad_(True), gm.to(DEV).requires_grad_(True)
+    got = ops.rmsnorm(b, bg, 1e-6)
+    got.backward(go.to(DEV))
+    assert rel_l2(got, want) < 1e-6 and rel_l2(b.grad, a.grad) < 2e-6 and rel_l2(bg.grad, ag.grad) < 2e-6
+    # swiglu
+    ab = cases.normal((50, 64), 14)
+    a = ab.double().requires_grad_(True)
+    want = torch.nn.functional.silu(a[:, :32]) * a[:, 32:]
+    want.backward(go[:50, :32].double())
+    b = ab.to(DEV).requires_grad_(True)
+    got = ops.swiglu(b)
+    got.backward(go[:50, :32].contiguous().to(DEV))
+    assert rel_l2(got, want) < 1e-6 and rel_l2(b.grad, a.grad) < 2e-6
+    # patchify round trip and parity, 2-D and 3-D
+    for grid, P, C in (((8, 4), 2, 3), ((4, 4, 6), 2, 5)):
+        n = int(np.prod(grid))
+        t = cases.normal((2, n, C), 15)
+        want = orc.patchify(t, grid, P)
+        got = ops.patchify(t.to(DEV), grid, P)
+        assert torch.equal(got.cpu(), want)
+        assert torch.equal(ops.unpatchify(got, grid, P, C).cpu(), t)
+    # mse
+    p, y = cases.normal((3, 50, 2), 16), cases.normal((3, 50, 2), 17)
+    a = p.double().requires_grad_(True)
+    want = torch.nn.functional.mse_loss(a, y.double())
+    want.backward()
+    b = p.to(DEV).requires_grad_(True)
+    got = ops.mse_loss(b, y.to(DEV))
+    got.backward()
+    assert abs(float(got) - float(want)) < 1e-6 * float(want) and rel_l2(b.grad, a.grad) < 1e-6
+    # adamw vs torch.optim.AdamW (the oracle's adamw_step is pinned to it in test_oracle_golden.py)
+    w = cases.normal((1000,), 18)
+    ref = torch.nn.Parameter(w.clone().double())
+    opt = torch.optim.AdamW([ref], lr=1e-3, weight_decay=1e-2)
+    pw, m, v = w.to(DEV), torch.zeros(1000, device=DEV), torch.zeros(1000, device=DEV)
+    for step in range(1, 4):
+        gr = cases.normal((1000,), 19 + step)
+        ref.grad = gr.double()
+        opt.step()
+        ops.adamw_step(pw, gr.to(DEV), m, v, step, 1e-3)
+    assert rel_l2(pw, ref.detach()) < 1e-6
