@@ -1,0 +1,325 @@
+"""bench.py - mesh-points/sec of one GAOT training step (forward + backward + AdamW) on synthetic meshes.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg2_16k|cfg4|cfg5]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...      (one rank per GPU, NCCL)
+
+One "step" = zero_grad -> GAOT.forward -> MSE -> backward -> (gradient all-reduce) -> AdamW over one
+batch of synthetic input (reference src/utils/optimizers.py:252-255).  Default workload is BASELINE.json
+configs[1]: Poisson-Gauss 2-D, N = 9216 points, latent 64x64, batch 32 PER GPU (weak scaling).
+Prints ONE JSON line (rank 0).  `value` = points/s with inputs resident in HBM; `e2e` = the same metric
+through the public API with pinned-host inputs copied H2D and the loss read back D2H every step.
+`--impl reference` times the reference algorithm's CPU port (oracle/, all host threads) on a bounded
+sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+from types import SimpleNamespace
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # BASELINE.json configs[1] (hyper-parameters: reference config/examples/time_indep/poisson_gauss.json:12-28)
+    "cfg2": dict(d=2, n=9216, latent=(64, 64), B=32, cin=1, cout=1, radius=0.033, C=64, hidden=64, mlp_layers=3,
+                 patch=2, dh=256, layers=3, heads=8, desc="Poisson-Gauss 2D fx, N=9216, latent 64x64, B=32/GPU"),
+    "cfg2_16k": dict(d=2, n=16384, latent=(64, 64), B=32, cin=1, cout=1, radius=0.033, C=64, hidden=64, mlp_layers=3,
+                     patch=2, dh=256, layers=3, heads=8, desc="Poisson-Gauss 2D fx, N=16384, latent 64x64, B=32/GPU"),
+    "cfg4": dict(d=2, n=16384, latent=(64, 64), B=16, cin=4, cout=2, radius=0.033, C=64, hidden=64, mlp_layers=3,
+                 patch=2, dh=256, layers=3, heads=8, desc="ns_gauss-like 2D fx training pair step, N=16384, B=16/GPU"),
+    "cfg5": dict(d=3, n=262144, latent=(32, 32, 32), B=1, cin=3, cout=1, radius=0.07, C=48, hidden=64, mlp_layers=3,
+                 patch=2, dh=256, layers=3, heads=8, desc="synthetic 3D fx, N=262144, latent 32^3, B=1/GPU"),
+}
+
+
+def make_config(w):
+    from gaot_b200.model import AttentionConfig, MAGNOConfig, TransformerConfig
+    mc = MAGNOConfig(coord_dim=w["d"], radius=w["radius"], hidden_size=w["hidden"], mlp_layers=w["mlp_layers"],
+                     lifting_channels=w["C"], neighbor_search_method="native")
+    tc = TransformerConfig(patch_size=w["patch"], hidden_size=w["dh"], num_layers=w["layers"],
+                           attn_config=AttentionConfig(num_heads=w["heads"], num_kv_heads=w["heads"]))
+    return SimpleNamespace(latent_tokens_size=tuple(w["latent"]), args=SimpleNamespace(magno=mc, transformer=tc))
+
+
+def synth(w, rank, B):
+    from gaot_b200 import synth as cases
+    lat = cases.latent_grid(w["latent"])
+    x = cases.uniform_points(w["n"], w["d"], 0)
+    pn = cases.normal((B, w["n"], w["cin"]), 1000 + rank)
+    tgt = cases.normal((B, w["n"], w["cout"]), 2000 + rank)
+    return lat, x, pn, tgt
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return None
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(", ") for r in open(self.f.name).read().strip().splitlines() if r.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], 0.0, set()
+        for r in rows:
+            try:
+                sm.append(float(r[0])); mx = max(mx, float(r[1]))
+            except Exception:
+                continue
+            for nm, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.strip().lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return None
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# algorithmic work per ABI call (DESIGN.md section "kernels"): (flops, bytes) from the call's own arguments
+def call_work(name, a):
+    if name == "gaot_gemm_f32":
+        M, N, K = a[3], a[4], a[5]
+        return 2.0 * M * N * K, 4.0 * (M * K + N * K + M * N)
+    if name == "gaot_agno_aggregate":
+        B, Ns, Nd, C = a[6], a[7], a[8], a[9]
+        return None, None  # E is not an argument; filled by the caller from the graph
+    if name == "gaot_attention_fwd":
+        B, T, H, hd = a[5], a[6], a[7], a[9]
+        return 4.0 * B * H * T * T * hd, 4.0 * B * T * H * hd * 4
+    if name == "gaot_attention_bwd":
+        B, T, H, hd = a[10], a[11], a[12], a[14]
+        return 10.0 * B * H * T * T * hd, 4.0 * B * T * H * hd * 8
+    return None, None
+
+
+def run_ours(args, w):
+    import torch.distributed as dist
+    from gaot_b200 import _lib
+    from gaot_b200.model import GAOT
+    from gaot_b200.trainer import TrainStep
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl ours) needs a CUDA device: the product has no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch or w["B"]
+    torch.manual_seed(42)
+    model = GAOT(w["cin"], w["cout"], make_config(w)).to(dev)
+    step = TrainStep(model, lr=1e-3, weight_decay=1e-2)
+    lat, x, pn, tgt = synth(w, rank, B)
+    lat_d, x_d = lat.to(dev), x.to(dev)
+    pn_d, tgt_d = pn.to(dev), tgt.to(dev)
+    pn_h, tgt_h = pn.pin_memory(), tgt.pin_memory()
+    pn_s, tgt_s = torch.empty_like(pn_d), torch.empty_like(tgt_d)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, K):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(K):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    def dev_step():
+        return step.fixed_coords_step(lat_d, x_d, pn_d, tgt_d)
+
+    def e2e_step():
+        pn_s.copy_(pn_h, non_blocking=True)
+        tgt_s.copy_(tgt_h, non_blocking=True)
+        return float(step.fixed_coords_step(lat_d, x_d, pn_s, tgt_s))        # .item(): D2H read of the loss
+
+    W = max(args.warmup, 3)
+    for _ in range(W):
+        dev_step()
+    sampler = ClockSampler(local) if rank == 0 else None
+    n0 = _lib.launch_count()
+    ms = timed(dev_step, args.steps)
+    launches = _lib.launch_count() - n0
+    clocks = sampler.stop() if sampler else None
+    e2e_step()
+    ms_e2e = timed(e2e_step, args.steps)
+
+    # per-kernel breakdown: one extra step with CUDA events around every ABI call (same stream)
+    rec = []
+    _lib.set_profile(rec)
+    dev_step()
+    torch.cuda.synchronize()
+    _lib.set_profile(None)
+    agg = {}
+    for name, a, e0, e1 in rec:
+        t = e0.elapsed_time(e1) * 1e-3
+        fl, by = call_work(name, a)
+        d = agg.setdefault(name, dict(calls=0, s=0.0, flops=0.0, bytes=0.0, items=[]))
+        d["calls"] += 1; d["s"] += t
+        if fl:
+            d["flops"] += fl
+        d["items"].append((t, a))
+    total_s = sum(d["s"] for d in agg.values())
+
+    peaks = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "src": "fallback"}
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        j = json.load(open(pk))
+        peaks = {"hbm_gbs": j["hbm_gbs"], "bf16_tflops": j["bf16_tflops_sustained"], "src": "measured"}
+
+    # MAGNO scatter (the metric BASELINE.json names): algorithmic bytes of SURVEY.md section 8d
+    enc_g = model.encoder.neighbor_cache["graph"][1][0]
+    E = int(enc_g["neighbors_index"].numel())
+    C, N, M = w["C"], w["n"], lat.shape[0]
+    magno = []
+    for t, a in agg.get("gaot_agno_aggregate", dict(items=[]))["items"]:
+        Bc, Ns, Nd, Cc = a[6], a[7], a[8], a[9]
+        by = 4.0 * Cc * Bc * (Ns + Nd) + 4.0 * Cc * E + 8.0 * E + 8.0 * (Nd + 1) + (8.0 * E if a[2] else 0.0)
+        magno.append(dict(Ns=Ns, Nd=Nd, bwd=bool(a[2]), us=t * 1e6, gbs=by / t / 1e9))
+    best = max(magno, key=lambda r: r["us"]) if magno else None
+    top_name = max(agg, key=lambda k: agg[k]["s"])
+    top = agg[top_name]
+    if top["flops"] > 0:
+        ach = top["flops"] / top["s"] / 1e12
+        roof = {"kernel": top_name, "bound": "tensor", "achieved": round(ach, 3), "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                "frac": round(ach / peaks["bf16_tflops"], 5), "traffic": None, "peak_src": peaks["src"],
+                "share_of_step": round(top["s"] / total_s, 3),
+                "note": "fp32 FFMA parity-path kernel measured against the bf16 tensor peak; the tcgen05 path replaces it"}
+    else:
+        ach = best["gbs"] if best else 0.0
+        roof = {"kernel": top_name, "bound": "hbm", "achieved": round(ach, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": round(ach / peaks["hbm_gbs"], 4), "traffic": None, "peak_src": peaks["src"],
+                "share_of_step": round(top["s"] / total_s, 3)}
+    roof_magno = None
+    if magno:
+        roof_magno = {"kernel": "gaot_agno_aggregate", "bound": "hbm", "unit": "GB/s", "peak": peaks["hbm_gbs"],
+                      "launches": [dict(Ns=r["Ns"], Nd=r["Nd"], bwd=r["bwd"], us=round(r["us"], 1), achieved=round(r["gbs"], 1),
+                                        frac=round(r["gbs"] / peaks["hbm_gbs"], 4)) for r in magno],
+                      "share_of_step": round(agg["gaot_agno_aggregate"]["s"] / total_s, 4), "traffic": None}
+    breakdown = {k: {"calls": d["calls"], "ms": round(d["s"] * 1e3, 3), "share": round(d["s"] / total_s, 4)}
+                 for k, d in sorted(agg.items(), key=lambda kv: -kv[1]["s"])}
+
+    pts = world * B * w["n"] * args.steps
+    out = {
+        "metric": "mesh-points/sec fwd+bwd", "value": pts / (ms * 1e-3), "unit": "points/s", "n_gpus": world,
+        "steps": args.steps, "warmup": W, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "desc": w["desc"], "batch_per_gpu": B, "points": w["n"], "latent_tokens": int(M),
+                   "edges": E, "params": step.num_params, "parallelism": f"dp{world}",
+                   "l2": "no flush: per-step working set (~3 GB of activations at B=32) exceeds the 126 MB L2"},
+        "e2e": {"value": pts / (ms_e2e * 1e-3), "unit": "points/s", "ms_per_step": ms_e2e / args.steps,
+                "h2d_bytes_per_step": int(pn.numel() * 4 + tgt.numel() * 4), "d2h_bytes_per_step": 4},
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "roofline_magno": roof_magno,
+        "kernel_breakdown": breakdown,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_reference(w, steps=2, warmup=1, sample_B=min(8, w["B"]))
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def cpu_reference(w, steps, warmup, sample_B):
+    """The reference algorithm's CPU port (oracle/gaot_oracle.py, torch-CPU, all host threads) on a bounded
+    sample (sample_B samples of the same mesh/model) - the reported baseline, not the target."""
+    from oracle import cases, gaot_oracle as orc
+    from gaot_b200.model import GAOT
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(42)
+    model = GAOT(w["cin"], w["cout"], make_config(w))       # parameter container only (CPU): same init as our arm
+    p = {k: v.detach().clone().requires_grad_(True) for k, v in model.state_dict().items()}
+    cfg = orc.make_config(w["latent"], dict(coord_dim=w["d"], radius=w["radius"], hidden_size=w["hidden"], mlp_layers=w["mlp_layers"],
+                                            lifting_channels=w["C"]),
+                          dict(patch_size=w["patch"], hidden_size=w["dh"], num_layers=w["layers"]),
+                          dict(num_heads=w["heads"], num_kv_heads=w["heads"]))
+    lat, x, pn, tgt = synth(w, 0, sample_B)
+    enc, dec = orc.build_graphs(cfg.args.magno, x, lat), orc.build_graphs(cfg.args.magno, lat, x)
+    m = {k: torch.zeros_like(v) for k, v in p.items()}
+    v_ = {k: torch.zeros_like(v) for k, v in p.items()}
+    times = []
+    for it in range(1, warmup + steps + 1):
+        t0 = time.perf_counter()
+        for t in p.values():
+            t.grad = None
+        loss = orc.train_step_loss(p, cfg, lat, x, pn, tgt, enc, dec)
+        loss.backward()
+        with torch.no_grad():
+            newp, m, v_ = orc.adamw_step({k: t.detach() for k, t in p.items()}, {k: t.grad for k, t in p.items()}, m, v_, it, 1e-3)
+        p = {k: t.requires_grad_(True) for k, t in newp.items()}
+        times.append(time.perf_counter() - t0)
+    dt = sum(times[warmup:]) / steps
+    return {"value": sample_B * w["n"] / dt, "unit": "points/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{steps} steps of batch {sample_B} (of the workload's batch) after {warmup} warm-up; graphs prebuilt; "
+                      f"{dt:.3f} s/step", "s_per_step": dt}
+
+
+def run_reference(args, w):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return
+    sample_B = min(8, w["B"])
+    base = cpu_reference(w, steps=args.steps, warmup=max(1, min(args.warmup, 2)), sample_B=sample_B)
+    out = {"impl": "reference", "metric": "mesh-points/sec fwd+bwd", "value": base["value"], "unit": "points/s",
+           "n_gpus": world, "steps": args.steps, "warmup": max(1, min(args.warmup, 2)), "ms_per_step": base["s_per_step"] * 1e3,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": args.workload, "desc": w["desc"], "batch_per_gpu": args.batch or w["B"], "points": w["n"],
+                      "parallelism": "cpu"},
+           "cpu_baseline": base,
+           "e2e": {"value": base["value"], "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch override")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, w)
+    else:
+        run_ours(args, w)
+
+
+if __name__ == "__main__":
+    main()

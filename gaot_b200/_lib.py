@@ -80,9 +80,25 @@ def stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+_profile = None   # when a list: (name, args, start_event, end_event) appended per call (bench.py kernel breakdown)
+
+
+def set_profile(records):
+    """records: a list to collect per-call CUDA-event timings into, or None to switch profiling off."""
+    global _profile
+    _profile = records
+
+
 def call(name: str, *args):
     """Invoke an entry point on the current torch CUDA stream; raise on a non-zero status."""
-    rc = getattr(lib(), name)(*args, stream())
+    if _profile is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(lib(), name)(*args, stream())
+        e1.record()
+        _profile.append((name, args, e0, e1))
+    else:
+        rc = getattr(lib(), name)(*args, stream())
     if rc != 0:
         raise GaotLibraryError(f"{name} failed with status {rc}"
                                + (" (bad argument)" if rc == -1 else " (alignment)" if rc == -2 else " (CUDA error)"))

@@ -12,27 +12,7 @@ from typing import Dict, List
 import torch
 
 
-def latent_grid(size) -> torch.Tensor:
-    axes = [torch.linspace(-1.0, 1.0, s, dtype=torch.float32) for s in size]
-    return torch.stack(torch.meshgrid(*axes, indexing="ij"), dim=-1).reshape(-1, len(size)).contiguous()
-
-
-def uniform_points(n: int, d: int, seed: int) -> torch.Tensor:
-    g = torch.Generator().manual_seed(seed)
-    return (torch.rand(n, d, generator=g, dtype=torch.float32) * 2.0 - 1.0).contiguous()
-
-
-def clustered_points(n: int, d: int, seed: int, sigma: float = 0.15) -> torch.Tensor:
-    """Airfoil-like density: half uniform, half N(0, sigma^2) around the origin, clipped to the box."""
-    g = torch.Generator().manual_seed(seed)
-    a = torch.rand(n // 2, d, generator=g, dtype=torch.float32) * 2.0 - 1.0
-    b = (torch.randn(n - n // 2, d, generator=g, dtype=torch.float32) * sigma).clamp_(-1.0, 1.0)
-    return torch.cat([a, b], dim=0).contiguous()
-
-
-def normal(shape, seed: int) -> torch.Tensor:
-    g = torch.Generator().manual_seed(seed)
-    return torch.randn(*shape, generator=g, dtype=torch.float32)
+from gaot_b200.synth import clustered_points, latent_grid, normal, uniform_points  # noqa: E402,F401
 
 
 def synth_params(shapes: Dict[str, List[int]], seed: int) -> Dict[str, torch.Tensor]:

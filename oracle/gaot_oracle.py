@@ -326,8 +326,7 @@ def attention(p, prefix, x, num_heads, num_kv_heads):
     if num_kv_heads != num_heads:
         k = k.repeat_interleave(num_heads // num_kv_heads, dim=1)
         v = v.repeat_interleave(num_heads // num_kv_heads, dim=1)
-    s = torch.matmul(q, k.transpose(-1, -2)) / math.sqrt(hd)
-    o = torch.matmul(torch.softmax(s, dim=-1), v)
+    o = F.scaled_dot_product_attention(q, k, v)           # attn.py:114 (non-causal, scale 1/sqrt(hd), dropout 0)
     o = o.transpose(1, 2).contiguous().view(b, t, -1)
     return F.linear(o, p[f"{prefix}.o_proj.weight"])
 

@@ -1,0 +1,308 @@
+"""TEST INFRASTRUCTURE ONLY: a CPU stand-in for libgaot_b200.so's entry points, used by the
+`-m "not gpu"` tests to exercise the *host logic* (argument order, shapes, autograd formulas, graph
+merging, flat-buffer optimizer, gloo data parallelism) in a container without a GPU.
+
+`install()` monkeypatches `gaot_b200._lib.call` for the duration of a test; the product never imports
+this file and has no CPU path of its own (`gaot_b200._lib.call` on CPU tensors raises).  Each emulated
+function receives exactly what the C function would: raw addresses and sizes, in the order
+include/gaot_b200.h declares them; it views host memory through ctypes/numpy and computes with
+numpy/torch in fp64 where that is cheap.
+"""
+from __future__ import annotations
+
+import contextlib
+import ctypes
+import math
+
+import numpy as np
+import torch
+
+from oracle import gaot_oracle as orc
+
+_CT = {np.float32: ctypes.c_float, np.int64: ctypes.c_int64}
+
+
+def _arr(ptr, shape, dtype=np.float32):
+    n = int(np.prod(shape)) if len(shape) else 1
+    if n == 0 or not ptr:
+        return np.zeros(shape, dtype=dtype)
+    return np.ctypeslib.as_array(ctypes.cast(int(ptr), ctypes.POINTER(_CT[dtype])), shape=(n,)).reshape(shape)
+
+
+def _t(ptr, shape, dtype=np.float32):
+    return torch.from_numpy(_arr(ptr, shape, dtype))
+
+
+def _csr(index_ptr, splits_ptr, m):
+    rs = _t(splits_ptr, (m + 1,), np.int64)
+    E = int(rs[-1])
+    return {"neighbors_index": _t(index_ptr, (E,), np.int64), "neighbors_row_splits": rs}, E
+
+
+def _act(x, act):
+    return torch.nn.functional.gelu(x) if act == 1 else (torch.relu(x) if act == 2 else x)
+
+
+# ---- graph -------------------------------------------------------------------------------------
+def gaot_radius_count(data, n, queries, m, d, radius, inclusive, cap, batch, db, qb, row_splits):
+    D = _t(data, (batch if db else 1, n, d))
+    Q = _t(queries, (batch if qb else 1, m, d))
+    rs = _arr(row_splits, (batch, m + 1), np.int64)
+    for b in range(batch):
+        g = orc.radius_csr(D[b if db else 0], Q[b if qb else 0], radius, bool(inclusive), cap if cap > 0 else None)
+        rs[b] = g["neighbors_row_splits"].numpy()
+
+
+def gaot_radius_fill(data, n, queries, m, d, radius, inclusive, cap, batch, db, qb, row_splits, offsets, index):
+    D = _t(data, (batch if db else 1, n, d))
+    Q = _t(queries, (batch if qb else 1, m, d))
+    offs = _arr(offsets, (batch,), np.int64)
+    for b in range(batch):
+        g = orc.radius_csr(D[b if db else 0], Q[b if qb else 0], radius, bool(inclusive), cap if cap > 0 else None)
+        e = g["neighbors_index"].numel()
+        _arr(index + 8 * int(offs[b]), (e,), np.int64)[:] = g["neighbors_index"].numpy()
+
+
+def gaot_csr_edge_rows(row_splits, m, edge_row):
+    rs = _arr(row_splits, (m + 1,), np.int64)
+    _arr(edge_row, (int(rs[-1]),), np.int64)[:] = np.repeat(np.arange(m, dtype=np.int64), np.diff(rs))
+
+
+def gaot_csr_transpose(index, row_splits, m, n_src, E, t_splits, t_rows, t_perm, ws):
+    g, _ = _csr(index, row_splits, m)
+    t = orc.csr_transpose(g, n_src)
+    _arr(t_splits, (n_src + 1,), np.int64)[:] = t["neighbors_row_splits"].numpy()
+    _arr(t_rows, (E,), np.int64)[:] = t["neighbors_index"].numpy()
+    _arr(t_perm, (E,), np.int64)[:] = t["edge_perm"].numpy()
+
+
+# ---- AGNO ---------------------------------------------------------------------------------------
+def gaot_edge_inputs(y, dy, x, dx, index, edge_row, E, z):
+    idx, row = _arr(index, (E,), np.int64), _arr(edge_row, (E,), np.int64)
+    n_y, n_x = (int(idx.max()) + 1 if E else 0), (int(row.max()) + 1 if E else 0)
+    _arr(z, (E, dy + dx))[:] = np.concatenate([_arr(y, (n_y, dy))[idx], _arr(x, (n_x, dx))[row]], axis=1)
+
+
+def gaot_edge_cosine_softmax(y, dy, x, dx, cd, index, row_splits, m, alpha):
+    g, E = _csr(index, row_splits, m)
+    idx = g["neighbors_index"]
+    seg, _ = orc._seg_ids(g["neighbors_row_splits"])
+    n_y = int(idx.max()) + 1 if E else 0
+    yy, xx = _t(y, (n_y, dy)).double()[:, :cd], _t(x, (m, dx)).double()[:, :cd]
+    s = (torch.nn.functional.normalize(xx[seg], dim=-1) * torch.nn.functional.normalize(yy[idx], dim=-1)).sum(-1)
+    ex = torch.exp(s - orc.segment_csr(s, g["neighbors_row_splits"], "max")[seg])
+    _arr(alpha, (E,))[:] = (ex / orc.segment_csr(ex, g["neighbors_row_splits"], "sum")[seg]).float().numpy()
+
+
+def gaot_scale_rows(inp, scale, rows, C, out):
+    _arr(out, (rows, C))[:] = _arr(inp, (rows, C)) * _arr(scale, (rows,))[:, None]
+
+
+def gaot_agno_aggregate(f, w, w_perm, index, row_splits, out, B, Ns, Nd, C):
+    g, E = _csr(index, row_splits, Nd)
+    W = _t(w, (E, C)).double()
+    if w_perm:
+        W = W[_t(w_perm, (E,), np.int64)]
+    msg = W.unsqueeze(0) * _t(f, (B, Ns, C)).double()[:, g["neighbors_index"], :]
+    _arr(out, (B, Nd, C))[:] = orc.segment_csr(msg, g["neighbors_row_splits"], "sum").float().numpy()
+
+
+def gaot_agno_weight_grad(gr, f, index, row_splits, dw, B, Ns, Nd, E, C):
+    g, E2 = _csr(index, row_splits, Nd)
+    assert E2 == E
+    seg, _ = orc._seg_ids(g["neighbors_row_splits"])
+    G, F = _t(gr, (B, Nd, C)).double(), _t(f, (B, Ns, C)).double()
+    _arr(dw, (E, C))[:] = (G[:, seg, :] * F[:, g["neighbors_index"], :]).sum(0).float().numpy()
+
+
+def gaot_segment_csr(src, row_splits, out, B, E, m, C, reduce):
+    rs = _t(row_splits, (m + 1,), np.int64)
+    _arr(out, (B, m, C))[:] = orc.segment_csr(_t(src, (B, E, C)), rs, ("sum", "mean", "max")[reduce]).numpy()
+
+
+def gaot_geo_stats(src, queries, d, index, row_splits, m, feat):
+    g, E = _csr(index, row_splits, m)
+    idx, rs = g["neighbors_index"], g["neighbors_row_splits"]
+    n_s = int(idx.max()) + 1 if E else 0
+    S, Q = _t(src, (n_s, d)).double(), _t(queries, (m, d)).double()
+    seg, deg = orc._seg_ids(rs)
+    n = deg.double()
+    nc = n.clamp(min=1)
+    pts = S[idx]
+    dist = (pts - Q[seg]).norm(dim=1)
+    davg = torch.zeros(m, dtype=torch.float64).index_add(0, seg, dist) / nc
+    ex2 = torch.zeros(m, dtype=torch.float64).index_add(0, seg, dist ** 2) / nc
+    cen = torch.zeros(m, d, dtype=torch.float64).index_add(0, seg, pts) / nc[:, None]
+    ctr = pts - cen[seg]
+    cov = torch.zeros(m, d, d, dtype=torch.float64).index_add(0, seg, ctr[:, :, None] * ctr[:, None, :]) / nc.view(-1, 1, 1)
+    ev = torch.linalg.eigvalsh(cov).flip(dims=[1])
+    out = torch.cat([n[:, None], davg[:, None], (ex2 - davg ** 2).clamp(min=0)[:, None], cen - Q, ev], dim=1)
+    out[deg == 0] = 0.0
+    _arr(feat, (m, 3 + 2 * d))[:] = out.float().numpy()
+
+
+def gaot_col_standardize(feat, m, F, groups):
+    a = _t(feat, (groups, m, F))
+    x = a.double()
+    mean, std = x.mean(dim=1, keepdim=True), x.std(dim=1, keepdim=True)
+    std[std < 1e-6] = 1.0
+    a[:] = ((x - mean) / std).float()
+
+
+# ---- dense --------------------------------------------------------------------------------------
+def _strided(ptr, rows, cols, ld):
+    return _t(ptr, (rows * ld,))[: (rows - 1) * ld + cols].as_strided((rows, cols), (ld, 1)) if rows and cols else torch.zeros(rows, cols)
+
+
+def gaot_gemm_f32(A, B, C, M, N, K, lda, ldb, ldc, transA, transB, bias, add, add_rows, ldadd, act, pre, accumulate):
+    a = (_strided(A, K, M, lda).T if transA else _strided(A, M, K, lda)).double()
+    b = (_strided(B, N, K, ldb).T if transB else _strided(B, K, N, ldb)).double()
+    v = a @ b
+    if bias:
+        v = v + _t(bias, (N,)).double()
+    if add:
+        v = v + _strided(add, add_rows, N, ldadd).double().repeat(M // add_rows, 1)
+    if pre:
+        _strided(pre, M, N, ldc)[:] = v.float()
+    v = _act(v, act)
+    c = _strided(C, M, N, ldc)
+    c[:] = (v + c.double()).float() if accumulate else v.float()
+
+
+def gaot_col_sum(x, M, N, out, accumulate):
+    o = _arr(out, (N,))
+    s = _arr(x, (M, N)).astype(np.float64).sum(0)
+    o[:] = (o + s if accumulate else s).astype(np.float32)
+
+
+def gaot_act_bwd(dy, pre, dx, n, act):
+    with torch.enable_grad():
+        p = _t(pre, (n,)).double().requires_grad_(True)
+        (gr,) = torch.autograd.grad(_act(p, act).sum(), p)
+    _arr(dx, (n,))[:] = (_t(dy, (n,)).double() * gr).float().numpy()
+
+
+def gaot_rmsnorm_fwd(x, gamma, y, rstd, rows, D, eps):
+    X = _t(x, (rows, D)).double()
+    r = torch.rsqrt(X.pow(2).mean(-1) + eps)
+    _arr(rstd, (rows,))[:] = r.float().numpy()
+    _arr(y, (rows, D))[:] = (X * r[:, None] * _t(gamma, (D,)).double()).float().numpy()
+
+
+def gaot_rmsnorm_bwd(dy, x, gamma, rstd, dx, dgamma, rows, D):
+    X, G, gm = _t(x, (rows, D)).double(), _t(dy, (rows, D)).double(), _t(gamma, (D,)).double()
+    r = _t(rstd, (rows,)).double()[:, None]
+    dot = (G * gm * X).sum(-1, keepdim=True)
+    _arr(dx, (rows, D))[:] = (G * gm * r - X * dot * r ** 3 / D).float().numpy()
+    _arr(dgamma, (D,))[:] += (G * X * r).sum(0).float().numpy()
+
+
+def gaot_swiglu_fwd(ab, u, rows, F):
+    a = _t(ab, (rows, 2 * F)).double()
+    _arr(u, (rows, F))[:] = (torch.nn.functional.silu(a[:, :F]) * a[:, F:]).float().numpy()
+
+
+def gaot_swiglu_bwd(du, ab, dab, rows, F):
+    with torch.enable_grad():
+        a = _t(ab, (rows, 2 * F)).double().requires_grad_(True)
+        (torch.nn.functional.silu(a[:, :F]) * a[:, F:]).backward(_t(du, (rows, F)).double())
+    _arr(dab, (rows, 2 * F))[:] = a.grad.float().numpy()
+
+
+def _heads(base, B, T, H, hd, ld):
+    return _t(base, (B * T * ld,))[: (B * T - 1) * ld + H * hd].as_strided((B, T, H, hd), (T * ld, ld, hd, 1))
+
+
+def _attn_ref(q, k, v, H, Hkv, scale):
+    rep = H // Hkv
+    q, k, v = q.transpose(1, 2), k.transpose(1, 2).repeat_interleave(rep, 1), v.transpose(1, 2).repeat_interleave(rep, 1)
+    s = q @ k.transpose(-1, -2) * scale
+    return (torch.softmax(s, -1) @ v).transpose(1, 2), torch.logsumexp(s, -1)
+
+
+def gaot_attention_fwd(q, k, v, o, lse, B, T, H, Hkv, hd, ldq, ldk, scale):
+    Q, K, V = _heads(q, B, T, H, hd, ldq).double(), _heads(k, B, T, Hkv, hd, ldk).double(), _heads(v, B, T, Hkv, hd, ldk).double()
+    out, l = _attn_ref(Q, K, V, H, Hkv, scale)
+    _arr(o, (B, T, H, hd))[:] = out.float().numpy()
+    _arr(lse, (B, H, T))[:] = l.float().numpy()
+
+
+def gaot_attention_bwd(q, k, v, o, lse, dout, delta, dq, dk, dv, B, T, H, Hkv, hd, ldq, ldk, scale):
+    with torch.enable_grad():
+        Q = _heads(q, B, T, H, hd, ldq).double().requires_grad_(True)
+        K = _heads(k, B, T, Hkv, hd, ldk).double().requires_grad_(True)
+        V = _heads(v, B, T, Hkv, hd, ldk).double().requires_grad_(True)
+        out, _ = _attn_ref(Q, K, V, H, Hkv, scale)
+        out.backward(_t(dout, (B, T, H, hd)).double())
+    _heads(dq, B, T, H, hd, ldq)[:] = Q.grad.float()
+    _heads(dk, B, T, Hkv, hd, ldk)[:] = K.grad.float()
+    _heads(dv, B, T, Hkv, hd, ldk)[:] = V.grad.float()
+
+
+def gaot_patch_permute(inp, out, B, dims, H, W, D, P, C, to_tokens):
+    grid = (H, W) if dims == 2 else (H, W, D)
+    nodes, pv = int(np.prod(grid)), P ** dims
+    if to_tokens:
+        _arr(out, (B, nodes // pv, pv * C))[:] = orc.patchify(_t(inp, (B, nodes, C)), grid, P).numpy()
+    else:
+        _arr(out, (B, nodes, C))[:] = orc.unpatchify(_t(inp, (B, nodes // pv, pv * C)), grid, P, C).numpy()
+
+
+# ---- step ---------------------------------------------------------------------------------------
+def gaot_mse_fwd_bwd(pred, target, loss, dpred, n, gscale):
+    d = _arr(pred, (n,)).astype(np.float64) - _arr(target, (n,)).astype(np.float64)
+    _arr(loss, (1,))[:] += np.float32((d * d).mean())
+    if dpred:
+        _arr(dpred, (n,))[:] = (2.0 * d / n * gscale).astype(np.float32)
+
+
+def gaot_adamw_step(param, grad, m, v, n, lr, b1, b2, eps, wd, step, gscale):
+    p, g = _arr(param, (n,)), _arr(grad, (n,)).astype(np.float64) * gscale
+    mm, vv = _arr(m, (n,)), _arr(v, (n,))
+    pn = p.astype(np.float64) * (1 - lr * wd)
+    m2 = b1 * mm.astype(np.float64) + (1 - b1) * g
+    v2 = b2 * vv.astype(np.float64) + (1 - b2) * g * g
+    den = np.sqrt(v2) / math.sqrt(1 - b2 ** step) + eps
+    p[:] = (pn - lr / (1 - b1 ** step) * m2 / den).astype(np.float32)
+    mm[:], vv[:] = m2.astype(np.float32), v2.astype(np.float32)
+
+
+def gaot_rollout_update(pred, u_in, u_next, rows, C, dt, mode, um, us, sm, ss):
+    P = _arr(pred, (rows, C)).astype(np.float64)
+    if mode == 0:
+        _arr(u_next, (rows, C))[:] = P.astype(np.float32)
+        return
+    ucur = _arr(u_in, (rows, C)) * _arr(us, (C,)) + _arr(um, (C,))
+    inc = P * _arr(ss, (C,)) + _arr(sm, (C,))
+    _arr(u_next, (rows, C))[:] = ((ucur + (dt * inc if mode == 2 else inc) - _arr(um, (C,))) / _arr(us, (C,))).astype(np.float32)
+
+
+_TABLE = {k: v for k, v in list(globals().items()) if k.startswith("gaot_")}
+CALLS = []
+
+
+def _call(name, *args):
+    from gaot_b200 import _lib
+    sig = _lib.parse_header()[name][1]
+    assert len(args) == len(sig) - 1, f"{name}: {len(args)} arguments for signature {sig} (+stream)"
+    for a, kind in zip(args, sig):
+        if kind == "f":
+            assert isinstance(a, float), (name, a)
+        else:
+            assert isinstance(a, int) and not isinstance(a, bool), (name, kind, a)
+    CALLS.append(name)
+    _TABLE[name](*args)
+
+
+@contextlib.contextmanager
+def install():
+    """Route gaot_b200's ABI calls to the emulator (CPU tensors) inside the `with` block."""
+    from gaot_b200 import _lib, ops
+    saved = (_lib.call, ops.call, ops._need_cuda)
+    _lib.call, ops.call = _call, _call
+    ops._need_cuda = lambda t: None
+    CALLS.clear()
+    try:
+        yield CALLS
+    finally:
+        _lib.call, ops.call, ops._need_cuda = saved
