@@ -101,9 +101,9 @@ def call_work(name, a):
     if name == "gaot_gemm_f32":
         M, N, K = a[3], a[4], a[5]
         return 2.0 * M * N * K, 4.0 * (M * K + N * K + M * N)
-    if name == "gaot_agno_aggregate":
-        B, Ns, Nd, C = a[6], a[7], a[8], a[9]
-        return None, None  # E is not an argument; filled by the caller from the graph
+    if name == "gaot_gemm_bf16":
+        M, N, K = a[3], a[4], a[5]
+        return 2.0 * M * N * K, 2.0 * (M * K + N * K) + (2.0 if a[6] else 4.0) * M * N
     if name == "gaot_attention_fwd":
         B, T, H, hd = a[5], a[6], a[7], a[9]
         return 4.0 * B * H * T * T * hd, 4.0 * B * T * H * hd * 4
@@ -129,6 +129,8 @@ def run_ours(args, w):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch or w["B"]
+    from gaot_b200 import ops as _ops
+    _ops.set_precision(args.precision)
     torch.manual_seed(42)
     model = GAOT(w["cin"], w["cout"], make_config(w)).to(dev)
     step = TrainStep(model, lr=1e-3, weight_decay=1e-2)
@@ -234,8 +236,8 @@ def run_ours(args, w):
     out = {
         "metric": "mesh-points/sec fwd+bwd", "value": pts / (ms * 1e-3), "unit": "points/s", "n_gpus": world,
         "steps": args.steps, "warmup": W, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "desc": w["desc"], "batch_per_gpu": B, "points": w["n"], "latent_tokens": int(M),
+        "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "precision": args.precision, "desc": w["desc"], "batch_per_gpu": B, "points": w["n"], "latent_tokens": int(M),
                    "edges": E, "params": step.num_params, "parallelism": f"dp{world}",
                    "l2": "no flush: per-step working set (~3 GB of activations at B=32) exceeds the 126 MB L2"},
         "e2e": {"value": pts / (ms_e2e * 1e-3), "unit": "points/s", "ms_per_step": ms_e2e / args.steps,
@@ -313,6 +315,8 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch override")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precision", default=os.environ.get("GAOT_B200_PRECISION", "fp32"), choices=["fp32", "bf16"],
+                    help="processor numerics: fp32 parity path or bf16 tensor-core path")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     if args.impl == "reference":

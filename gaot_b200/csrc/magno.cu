@@ -87,31 +87,41 @@ agno_aggregate_kernel(const float* __restrict__ f, const float* __restrict__ w, 
     const int64_t row = gid % Nd;
     const int b0 = (int)(gid / Nd) * BC;
     const int nvec = C >> 2;
+    // Branch-free inner loop: out-of-range batch slots / channel lanes read a valid (clamped) address and
+    // are dropped at the store, so the BC+1 loads of an edge issue back to back and stay in flight together.
+    int64_t boff[BC];
+#pragma unroll
+    for (int bb = 0; bb < BC; ++bb) boff[bb] = (int64_t)min(b0 + bb, B - 1) * Ns * C;
+    int coff[VPL];
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) coff[v] = min(gl + v * G, nvec - 1) * 4;
     float4 acc[BC][VPL];
 #pragma unroll
     for (int bb = 0; bb < BC; ++bb)
 #pragma unroll
         for (int v = 0; v < VPL; ++v) acc[bb][v] = make_float4(0.f, 0.f, 0.f, 0.f);
     const int64_t a = __ldg(rs + row), e = __ldg(rs + row + 1);
-    for (int64_t i = a; i < e; ++i) {
-        const int64_t j = __ldg(index + i);
-        const int64_t pe = w_perm ? __ldg(w_perm + i) : i;
-        float4 wv[VPL];
+    if (a < e) {
+        // software pipeline: the index (and permuted weight row id) of edge i+1 is fetched while edge i's
+        // feature rows are in flight
+        int64_t j = __ldg(index + a);
+        int64_t pe = w_perm ? __ldg(w_perm + a) : a;
+        for (int64_t i = a; i < e; ++i) {
+            const int64_t inext = (i + 1 < e) ? i + 1 : i;
+            const int64_t jn = __ldg(index + inext);
+            const int64_t pn = w_perm ? __ldg(w_perm + inext) : inext;
+            float4 wv[VPL], fv[BC][VPL];
 #pragma unroll
-        for (int v = 0; v < VPL; ++v) {
-            const int c4 = gl + v * G;
-            wv[v] = (c4 < nvec) ? ldg4(w + pe * C + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+            for (int v = 0; v < VPL; ++v) wv[v] = ldg4(w + pe * C + coff[v]);
 #pragma unroll
-        for (int bb = 0; bb < BC; ++bb) {
-            if (b0 + bb < B) {
-                const float* fp = f + ((int64_t)(b0 + bb) * Ns + j) * C;
+            for (int bb = 0; bb < BC; ++bb)
 #pragma unroll
-                for (int v = 0; v < VPL; ++v) {
-                    const int c4 = gl + v * G;
-                    if (c4 < nvec) fma4(acc[bb][v], wv[v], ldg4(fp + c4 * 4));
-                }
-            }
+                for (int v = 0; v < VPL; ++v) fv[bb][v] = ldg4(f + boff[bb] + j * C + coff[v]);
+#pragma unroll
+            for (int bb = 0; bb < BC; ++bb)
+#pragma unroll
+                for (int v = 0; v < VPL; ++v) fma4(acc[bb][v], wv[v], fv[bb][v]);
+            j = jn; pe = pn;
         }
     }
 #pragma unroll
@@ -183,39 +193,37 @@ agno_weight_grad_kernel(const float* __restrict__ g, const float* __restrict__ f
     const int per = (B + bsplit - 1) / bsplit;
     const int b_lo = slice * per, b_hi = min(B, b_lo + per);
     const int nvec = C >> 2;
+    int coff[VPL];
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) coff[v] = min(gl + v * G, nvec - 1) * 4;
     const int64_t a = __ldg(rs + row), e = __ldg(rs + row + 1);
     for (int64_t i0 = a; i0 < e; i0 += EC) {
-        int64_t j[EC];
+        int64_t j[EC];                      // edges past the row end alias the last valid edge (dropped at the store)
 #pragma unroll
-        for (int k = 0; k < EC; ++k) j[k] = (i0 + k < e) ? __ldg(index + i0 + k) : -1;
+        for (int k = 0; k < EC; ++k) j[k] = __ldg(index + min(i0 + k, e - 1)) * C;
         float4 acc[EC][VPL];
 #pragma unroll
         for (int k = 0; k < EC; ++k)
 #pragma unroll
             for (int v = 0; v < VPL; ++v) acc[k][v] = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int b = b_lo; b < b_hi; ++b) {
-            float4 gv[VPL];
+            float4 gv[VPL], fv[EC][VPL];
             const float* gp = g + ((int64_t)b * Nd + row) * C;
+            const float* fb = f + (int64_t)b * Ns * C;
 #pragma unroll
-            for (int v = 0; v < VPL; ++v) {
-                const int c4 = gl + v * G;
-                gv[v] = (c4 < nvec) ? ldg4(gp + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
+            for (int v = 0; v < VPL; ++v) gv[v] = ldg4(gp + coff[v]);
 #pragma unroll
-            for (int k = 0; k < EC; ++k) {
-                if (j[k] >= 0) {
-                    const float* fp = f + ((int64_t)b * Ns + j[k]) * C;
+            for (int k = 0; k < EC; ++k)
 #pragma unroll
-                    for (int v = 0; v < VPL; ++v) {
-                        const int c4 = gl + v * G;
-                        if (c4 < nvec) fma4(acc[k][v], gv[v], ldg4(fp + c4 * 4));
-                    }
-                }
-            }
+                for (int v = 0; v < VPL; ++v) fv[k][v] = ldg4(fb + j[k] + coff[v]);
+#pragma unroll
+            for (int k = 0; k < EC; ++k)
+#pragma unroll
+                for (int v = 0; v < VPL; ++v) fma4(acc[k][v], gv[v], fv[k][v]);
         }
 #pragma unroll
         for (int k = 0; k < EC; ++k) {
-            if (j[k] >= 0) {
+            if (i0 + k < e) {
 #pragma unroll
                 for (int v = 0; v < VPL; ++v) {
                     const int c4 = gl + v * G;

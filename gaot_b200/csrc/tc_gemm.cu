@@ -1,0 +1,362 @@
+// bf16 tensor-core GEMM for the processor's dense layers (the performance path):
+//     C[M,N] (fp32 or bf16) = A[M,K] (bf16, row-major) * B[N,K]^T (bf16, row-major) + bias[n] + add[(m % add_rows), n]
+// fp32 accumulation in TMEM.  Reference call sites: nn.Linear of src/model/layers/attn.py:92-94,117,151,
+// src/model/gaot.py:208 and their autograd backward.
+//
+// Blackwell design (sm_100a only):
+//   * warp 0  : TMA producer  - cp.async.bulk.tensor 2-D boxes (64 x 128 rows, SWIZZLE_128B) into a 3-stage ring,
+//               completion signalled on mbarriers (complete_tx)
+//   * warp 1  : TMEM allocator + MMA issuer - one lane issues tcgen05.mma.cta_group::1.kind::f16
+//               (M=128, N=BN, K=16) straight from the swizzled smem tiles; tcgen05.commit frees ring slots
+//               and finally publishes the accumulator
+//   * warps 2-5: epilogue - tcgen05.ld (32 lanes x 32 columns per warp), bias / broadcast-add, 16-byte stores
+//               (or 128-bit red.add for split-K)
+//   3 stages x 32 KB leave room for two CTAs per SM, so one CTA's epilogue overlaps the other's main loop.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "../../include/gaot_b200.h"
+
+namespace {
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 64;          // 64 bf16 = 128 bytes = one SWIZZLE_128B row
+constexpr int TC_STAGES = 3;
+constexpr int TC_THREADS = 192;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_c, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_c), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+// K-major operand tile, rows of 128 bytes, SWIZZLE_128B: 8-row atoms 1024 bytes apart (SBO), LBO unused (=1),
+// descriptor version 1 (sm_100), layout type 2 (cute/arch/mma_sm100_desc.hpp SmemDescriptor)
+__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+           ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,"
+        "%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]),
+          "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]),
+          "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct TcArgs {
+    void* C; int64_t M, N, K;
+    const float* bias; const float* add; int64_t add_rows, ldadd;
+    int out_bf16, splits, accumulate;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS)
+gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs g) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // carve: [stages][A 16 KB][B BN*128 B] (all 1024-aligned), then barriers
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    constexpr int A_BYTES = TC_BM * TC_BK * 2, B_BYTES = BN * TC_BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + TC_STAGES * STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + TC_STAGES;
+    uint64_t* acc_bar = empty_bar + TC_STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t m0 = (int64_t)blockIdx.x * TC_BM, n0 = (int64_t)blockIdx.y * BN;
+    const int64_t kblocks = (g.K + TC_BK - 1) / TC_BK;
+    const int64_t per = (kblocks + g.splits - 1) / g.splits;
+    const int64_t kb0 = (int64_t)blockIdx.z * per, kb1 = min(kblocks, kb0 + per);
+    const int nkb = (int)max((int64_t)0, kb1 - kb0);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(acc_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)BN));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_acc = *tmem_slot;
+
+    if (warp == 0) {
+        // ---------------- TMA producer ----------------
+        if (lane == 0) {
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % TC_STAGES;
+                const uint32_t ph = (uint32_t)(i / TC_STAGES) & 1u;
+                mbar_wait(&empty_bar[s], ph ^ 1u);
+                mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+                uint8_t* st = smem + s * STAGE_BYTES;
+                const int kc = (int)((kb0 + i) * TC_BK);
+                tma_load_2d(st, &tmA, &full_bar[s], kc, (int)m0);
+                tma_load_2d(st + A_BYTES, &tmB, &full_bar[s], kc, (int)n0);
+            }
+        }
+    } else if (warp == 1) {
+        // ---------------- MMA issuer ----------------
+        // instruction descriptor: D fp32, A/B bf16, both K-major, N = BN, M = 128 (cute/arch/mma_sm100_desc.hpp)
+        constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+        for (int i = 0; i < nkb; ++i) {
+            const int s = i % TC_STAGES;
+            const uint32_t ph = (uint32_t)(i / TC_STAGES) & 1u;
+            mbar_wait(&full_bar[s], ph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (lane == 0) {
+                const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+                const uint64_t da = make_smem_desc_sw128(sa), db = make_smem_desc_sw128(sa + A_BYTES);
+#pragma unroll
+                for (int k = 0; k < TC_BK / 16; ++k)      // +32 bytes (>>4 = 2) per K=16 step inside the 128-byte swizzle row
+                    umma_f16(tmem_acc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, (i > 0 || k > 0) ? 1u : 0u);
+                umma_commit(&empty_bar[s]);                // frees the slot once these MMAs have read it
+                if (i == nkb - 1) umma_commit(acc_bar);    // accumulator complete
+            }
+            __syncwarp();
+        }
+    } else {
+        // ---------------- epilogue (warps 2..5; warp w may touch TMEM lanes 32*(w%4) .. +31) ----------------
+        const int q = warp & 3;
+        const int64_t m = m0 + q * 32 + lane;
+        if (nkb > 0) {
+            mbar_wait(acc_bar, 0);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+        const bool first = blockIdx.z == 0;
+        const float* addrow = (g.add && first && m < g.M) ? g.add + (m % g.add_rows) * g.ldadd : nullptr;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t r[32];
+            if (nkb > 0) tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+            else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) r[j] = 0u;
+            }
+            if (m >= g.M) continue;
+            const int64_t n = n0 + c0;
+            if (n >= g.N) continue;
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+            const bool full = n + 32 <= g.N;
+            if (first && g.bias) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) if (full || n + j < g.N) v[j] += __ldg(g.bias + n + j);
+            }
+            if (addrow) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) if (full || n + j < g.N) v[j] += __ldg(addrow + n + j);
+            }
+            if (g.out_bf16) {
+                __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(g.C) + m * g.N + n;
+                if (full && (g.N % 8 == 0)) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) {
+                        uint4 pk;
+                        __nv_bfloat162 t0 = __floats2bfloat162_rn(v[j], v[j + 1]), t1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
+                        __nv_bfloat162 t2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), t3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+                        pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
+                        pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
+                        *reinterpret_cast<uint4*>(cp + j) = pk;
+                    }
+                } else {
+                    for (int j = 0; j < 32; ++j) if (n + j < g.N) cp[j] = __float2bfloat16_rn(v[j]);
+                }
+            } else {
+                float* cp = reinterpret_cast<float*>(g.C) + m * g.N + n;
+                if (g.splits > 1 || g.accumulate) {
+                    if (full && (g.N % 4 == 0)) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) atomicAdd(reinterpret_cast<float4*>(cp + j), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+                    } else {
+                        for (int j = 0; j < 32; ++j) if (n + j < g.N) atomicAdd(cp + j, v[j]);
+                    }
+                } else if (full && (g.N % 4 == 0)) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(cp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                } else {
+                    for (int j = 0; j < 32; ++j) if (n + j < g.N) cp[j] = v[j];
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"((uint32_t)BN));
+    }
+}
+
+// ---- fp32 -> bf16 casts and bf16 transposes (feed the TMA descriptors) ---------------------------------
+__global__ void cast_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int64_t n) {
+    const int64_t n4 = n >> 2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(in) + i);
+        __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+        uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&a); pk.y = *reinterpret_cast<uint32_t*>(&b);
+        reinterpret_cast<uint2*>(out)[i] = pk;
+    }
+    for (int64_t i = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = __float2bfloat16_rn(in[i]);
+}
+
+// out_t[c, r] = bf16(in[r, c]); TIn = float or bf16.  64x64 tiles through padded smem, both sides coalesced.
+template <typename TIn>
+__global__ void __launch_bounds__(256) transpose_bf16_kernel(const TIn* __restrict__ in, __nv_bfloat16* __restrict__ out_t,
+                                                             int64_t rows, int64_t cols) {
+    __shared__ __nv_bfloat16 tile[64][66];
+    const int64_t r0 = (int64_t)blockIdx.y * 64, c0 = (int64_t)blockIdx.x * 64;
+    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;          // 64 x 4
+    for (int i = ty; i < 64; i += 4) {
+        const int64_t r = r0 + i, c = c0 + tx;
+        float v = 0.f;
+        if (r < rows && c < cols) v = (float)in[r * cols + c];
+        tile[i][tx] = __float2bfloat16_rn(v);
+    }
+    __syncthreads();
+    for (int i = ty; i < 64; i += 4) {
+        const int64_t c = c0 + i, r = r0 + tx;
+        if (c < cols && r < rows) out_t[c * rows + r] = tile[tx][i];
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// [rows, K] bf16 row-major -> 2-D map with box {64 (K), box_rows}, SWIZZLE_128B, zero fill out of bounds
+int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t K, int box_rows) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return GAOT_E_BADARG;
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+    cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : GAOT_E_BADARG;
+}
+
+template <int BN>
+int launch_tc(const void* A, const void* B, TcArgs& g, cudaStream_t st) {
+    CUtensorMap ta, tb;
+    int rc = make_map(&ta, A, g.M, g.K, TC_BM);
+    if (rc) return rc;
+    rc = make_map(&tb, B, g.N, g.K, BN);
+    if (rc) return rc;
+    const int64_t gm = (g.M + TC_BM - 1) / TC_BM, gn = (g.N + BN - 1) / BN, kblocks = (g.K + TC_BK - 1) / TC_BK;
+    int splits = 1;
+    if (!g.out_bf16 && gm * gn < 148 && kblocks >= 8) {
+        splits = (int)((296 + gm * gn - 1) / (gm * gn));
+        if (splits > kblocks / 4) splits = (int)(kblocks / 4);
+        if (splits > 128) splits = 128;
+        if (splits < 1) splits = 1;
+    }
+    g.splits = splits;
+    if (splits > 1 && !g.accumulate) GAOT_CHECK(cudaMemsetAsync(g.C, 0, sizeof(float) * (size_t)(g.M * g.N), st));
+    constexpr int SMEM = TC_STAGES * (TC_BM * TC_BK * 2 + BN * TC_BK * 2) + 1024 + 256;
+    static bool attr_done = false;
+    if (!attr_done) {
+        GAOT_CHECK(cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+        attr_done = true;
+    }
+    if (gn > 65535 || splits > 65535) return GAOT_E_BADARG;
+    dim3 grid((unsigned)gm, (unsigned)gn, (unsigned)splits);
+    gemm_bf16_tc_kernel<BN><<<grid, TC_THREADS, SMEM, st>>>(ta, tb, g);
+    GAOT_RETURN_LAST();
+}
+
+}  // namespace
+
+GAOT_API int gaot_gemm_bf16(const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K, int out_bf16,
+                            const float* bias, const float* add, int64_t add_rows, int64_t ldadd, int accumulate,
+                            void* stream) {
+    if (!A || !B || !C || M < 1 || N < 1 || K < 1) return GAOT_E_BADARG;
+    if (K % 8 != 0 || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15) ||
+        (reinterpret_cast<uintptr_t>(C) & 15))
+        return GAOT_E_ALIGN;                       // TMA: 16-byte aligned base and row pitch
+    if (add && (add_rows < 1 || ldadd < N)) return GAOT_E_BADARG;
+    if (out_bf16 && accumulate) return GAOT_E_BADARG;
+    if (M > 0x7fffffffLL || N > 0x7fffffffLL || K > 0x7fffffffLL) return GAOT_E_BADARG;
+    TcArgs g{C, M, N, K, bias, add, add ? add_rows : 1, ldadd, out_bf16, 1, accumulate};
+    cudaStream_t st = (cudaStream_t)stream;
+    if (N <= 64) return launch_tc<64>(A, B, g, st);
+    return launch_tc<128>(A, B, g, st);
+}
+
+GAOT_API int gaot_cast_bf16(const float* in, void* out, int64_t rows, int64_t cols, void* out_t, void* stream) {
+    if (!in || (!out && !out_t) || rows < 0 || cols < 0) return GAOT_E_BADARG;
+    if (rows == 0 || cols == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (out) {
+        if ((reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(out) & 7)) return GAOT_E_ALIGN;
+        cast_bf16_kernel<<<gaot_grid(rows * cols / 4 + 1, 256), 256, 0, st>>>(in, reinterpret_cast<__nv_bfloat16*>(out), rows * cols);
+        if (out_t) GAOT_NOTE_LAUNCHES(1);
+    }
+    if (out_t) {
+        dim3 grid((unsigned)((cols + 63) / 64), (unsigned)((rows + 63) / 64));
+        if (grid.y > 65535) return GAOT_E_BADARG;
+        transpose_bf16_kernel<float><<<grid, 256, 0, st>>>(in, reinterpret_cast<__nv_bfloat16*>(out_t), rows, cols);
+    }
+    GAOT_RETURN_LAST();
+}
+
+GAOT_API int gaot_transpose_bf16(const void* in, void* out_t, int64_t rows, int64_t cols, void* stream) {
+    if (!in || !out_t || rows < 0 || cols < 0) return GAOT_E_BADARG;
+    if (rows == 0 || cols == 0) return 0;
+    dim3 grid((unsigned)((cols + 63) / 64), (unsigned)((rows + 63) / 64));
+    if (grid.y > 65535) return GAOT_E_BADARG;
+    transpose_bf16_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(in),
+                                                                                 reinterpret_cast<__nv_bfloat16*>(out_t), rows, cols);
+    GAOT_RETURN_LAST();
+}

@@ -78,7 +78,7 @@ class GAOT(nn.Module):
             add = self._pos_emb
         elif self.positional_embedding_name == "rope":
             raise NotImplementedError("positional_embedding='rope' is not on the accelerated path")
-        x = ops.linear(x.view(B * T, Dp), self.patch_linear.weight, self.patch_linear.bias, add=add).view(B, T, Dp)
+        x = ops.linear(x.view(B * T, Dp), self.patch_linear.weight, self.patch_linear.bias, add=add, tc=True).view(B, T, Dp)
         x = self.processor(x, condition=condition, relative_positions=None)
         return ops.unpatchify(x, grid, P, C)
 

@@ -83,10 +83,10 @@ class GroupQueryFlashAttention(nn.Module):
         """x [B,T,D] -> o_proj(SDPA(...)) (+ residual, fused into the o_proj GEMM)."""
         B, T, D = x.shape
         wqkv = torch.cat([self.q_proj.weight, self.k_proj.weight, self.v_proj.weight], dim=0)
-        qkv = ops.linear(x.reshape(B * T, D), wqkv)
+        qkv = ops.linear(x.reshape(B * T, D), wqkv, tc=True)
         o = ops.attention(qkv, B, T, self.num_heads, self.num_kv_heads, self.head_dim)
         add = residual.reshape(B * T, -1) if residual is not None else None
-        return ops.linear(o, self.o_proj.weight, None, add=add).view(B, T, -1)
+        return ops.linear(o, self.o_proj.weight, None, add=add, tc=True).view(B, T, -1)
 
 
 class FFN(nn.Module):
@@ -102,9 +102,9 @@ class FFN(nn.Module):
     def forward(self, x, condition=None, residual=None):
         shape = x.shape
         x2 = x.reshape(-1, shape[-1])
-        ab = ops.linear(x2, torch.cat([self.w1.weight, self.w3.weight], dim=0))
+        ab = ops.linear(x2, torch.cat([self.w1.weight, self.w3.weight], dim=0), tc=True)
         add = residual.reshape(-1, shape[-1]) if residual is not None else None
-        return ops.linear(ops.swiglu(ab), self.w2.weight, None, add=add).view(shape)
+        return ops.linear(ops.swiglu(ab), self.w2.weight, None, add=add, tc=True).view(shape)
 
 
 class TransformerBlock(nn.Module):
@@ -127,8 +127,8 @@ class TransformerBlock(nn.Module):
         if self.skip_connection and skip is not None:
             B, T, D = x.shape
             W = self.skip_proj.weight                                    # [D, 2D] acting on cat[x, skip] (attn.py:225-227)
-            t = ops.linear(skip.reshape(B * T, D), W[:, D:], None)
-            x = ops.linear(x.reshape(B * T, D), W[:, :D], self.skip_proj.bias, add=t).view(B, T, D)
+            t = ops.linear(skip.reshape(B * T, D), W[:, D:], None, tc=True)
+            x = ops.linear(x.reshape(B * T, D), W[:, :D], self.skip_proj.bias, add=t, tc=True).view(B, T, D)
         h = self.attn_norm(x) if self.attn_norm is not None else x
         h = self.attn(h, condition=condition, relative_positions=relative_positions, residual=x)
         h = self.ffn_norm(h) if self.ffn_norm is not None else h
@@ -156,7 +156,7 @@ class Transformer(nn.Module):
         if isinstance(layer, nn.Identity):
             return x
         B, T, D = x.shape
-        return ops.linear(x.reshape(B * T, D), layer.weight, layer.bias).view(B, T, -1)
+        return ops.linear(x.reshape(B * T, D), layer.weight, layer.bias, tc=True).view(B, T, -1)
 
     def forward(self, x, condition=None, relative_positions=None):
         x = self._proj(self.input_proj, x)

@@ -16,6 +16,22 @@ from ._lib import call, ptr
 
 ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
 
+# Numerics mode of the processor's dense layers.  "fp32": FFMA kernels, the parity path (<= 1e-5 vs the
+# reference).  "bf16": tcgen05 tensor-core kernels with bf16 operands and fp32 accumulation, the
+# performance path (tolerance stated in tests/test_gpu_tc.py).  MAGNO stays fp32 in both modes.
+_PRECISION = "fp32"
+
+
+def set_precision(mode: str):
+    global _PRECISION
+    if mode not in ("fp32", "bf16"):
+        raise ValueError("precision must be 'fp32' or 'bf16'")
+    _PRECISION = mode
+
+
+def get_precision() -> str:
+    return _PRECISION
+
 
 def _c(t: torch.Tensor) -> torch.Tensor:
     if t.dtype != torch.float32:
@@ -177,7 +193,83 @@ class _Linear(torch.autograd.Function):
         return dx, dW, db, dadd, None
 
 
-def linear(x, W, bias=None, add=None, act=ACT_NONE):
+def cast_bf16(x2d, want=True, want_t=False):
+    """bf16 copy and/or bf16 transposed copy of an fp32 [rows, cols] matrix."""
+    rows, cols = x2d.shape
+    out = torch.empty((rows, cols), dtype=torch.bfloat16, device=x2d.device) if want else None
+    out_t = torch.empty((cols, rows), dtype=torch.bfloat16, device=x2d.device) if want_t else None
+    call("gaot_cast_bf16", ptr(x2d), ptr(out), rows, cols, ptr(out_t))
+    return out, out_t
+
+
+def transpose_bf16(xb):
+    rows, cols = xb.shape
+    out = torch.empty((cols, rows), dtype=torch.bfloat16, device=xb.device)
+    call("gaot_transpose_bf16", ptr(xb), ptr(out), rows, cols)
+    return out
+
+
+def gemm_bf16(A, B, M, N, K, out_bf16=False, bias=None, add=None, add_rows=0, out=None, accumulate=False):
+    """C[M,N] = A[M,K] B[N,K]^T on the tensor cores (A, B bf16 row-major)."""
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.bfloat16 if out_bf16 else torch.float32, device=A.device)
+    call("gaot_gemm_bf16", ptr(A), ptr(B), ptr(out), M, N, K, int(out_bf16), ptr(bias), ptr(add), int(add_rows), N,
+         int(accumulate))
+    return out
+
+
+class _LinearTC(torch.autograd.Function):
+    """y = x W^T + bias + add[row % add_rows] with bf16 operands on tcgen05 (fp32 in / fp32 out)."""
+
+    @staticmethod
+    def forward(ctx, x, W, bias, add):
+        _need_cuda(x)
+        x, W = _c(x), _c(W)
+        M, K = x.shape
+        N = W.shape[0]
+        bias_c = _c(bias) if bias is not None else None
+        add_c = _c(add) if add is not None else None
+        add_rows = add_c.shape[0] if add_c is not None else 0
+        if add_c is not None and (add_c.shape[1] != N or M % add_rows != 0):
+            raise ValueError(f"broadcast-add of shape {tuple(add_c.shape)} does not tile an [{M},{N}] output")
+        xb, _ = cast_bf16(x)
+        wb, _ = cast_bf16(W)
+        y = gemm_bf16(xb, wb, M, N, K, bias=bias_c, add=add_c, add_rows=add_rows)
+        ctx.save_for_backward(xb, W)
+        ctx.has_bias, ctx.add_rows = bias is not None, add_rows
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xb, W = ctx.saved_tensors
+        dy = _c(dy)
+        M, K = xb.shape
+        N = W.shape[0]
+        dx = dW = db = dadd = None
+        need_t = ctx.needs_input_grad[1] and M % 8 == 0
+        dyb, dybT = cast_bf16(dy, want=True, want_t=need_t)
+        if ctx.needs_input_grad[0]:
+            if N % 8 == 0:
+                _, wT = cast_bf16(W, want=False, want_t=True)        # [K, N]
+                dx = gemm_bf16(dyb, wT, M, K, N)
+            else:
+                dx = gemm(dy, W, M, K, N, N, K, 0, 0)
+        if ctx.needs_input_grad[1]:
+            if need_t:
+                dW = gemm_bf16(dybT, transpose_bf16(xb), N, K, M)    # contraction over the M rows
+            else:
+                dW = gemm(dy, xb.float(), N, K, M, N, K, 1, 0)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = col_sum(dy, M, N)
+        if ctx.add_rows and ctx.needs_input_grad[3]:
+            dadd = dy if ctx.add_rows == M else col_sum(dy, M // ctx.add_rows, ctx.add_rows * N).view(ctx.add_rows, N)
+        return dx, dW, db, dadd
+
+
+def linear(x, W, bias=None, add=None, act=ACT_NONE, tc=False):
+    """tc=True marks a processor layer that may run on the tensor cores when precision is 'bf16'."""
+    if tc and _PRECISION == "bf16" and act == ACT_NONE and x.shape[-1] % 8 == 0:
+        return _LinearTC.apply(x, W, bias, add)
     return _Linear.apply(x, W, bias, add, act)
 
 

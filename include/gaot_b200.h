@@ -126,6 +126,17 @@ int gaot_gemm_f32(const float* A, const float* B, float* C, int64_t M, int64_t N
                   const float* bias, const float* add, int64_t add_rows, int64_t ldadd,
                   int act, float* pre, int accumulate, void* stream);
 
+/* Tensor-core (tcgen05, TMA, TMEM) variant for the processor: A [M,K] and B [N,K] are bf16 row-major
+ * (B in nn.Linear layout), fp32 accumulation; C [M,N] is fp32 (out_bf16=0) or bf16 (out_bf16=1).
+ * accumulate=1 (fp32 C only) adds into C.  K % 8 == 0 and 16-byte aligned bases (TMA). */
+int gaot_gemm_bf16(const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K, int out_bf16,
+                   const float* bias, const float* add, int64_t add_rows, int64_t ldadd, int accumulate,
+                   void* stream);
+/* out[r,c] = bf16(in[r,c]) (out nullable) and/or out_t[c,r] = bf16(in[r,c]) (out_t nullable) */
+int gaot_cast_bf16(const float* in, void* out, int64_t rows, int64_t cols, void* out_t, void* stream);
+/* out_t[c,r] = in[r,c], bf16 */
+int gaot_transpose_bf16(const void* in, void* out_t, int64_t rows, int64_t cols, void* stream);
+
 /* out[n] (+)= sum_m x[m,n]  (bias gradients) */
 int gaot_col_sum(const float* x, int64_t M, int64_t N, float* out, int accumulate, void* stream);
 /* dx = dy * act'(pre) */

@@ -169,6 +169,38 @@ def gaot_gemm_f32(A, B, C, M, N, K, lda, ldb, ldc, transA, transB, bias, add, ad
     c[:] = (v + c.double()).float() if accumulate else v.float()
 
 
+def _bf(ptr, shape):
+    """bf16 host array viewed as a torch.bfloat16 tensor"""
+    n = int(np.prod(shape))
+    raw = np.ctypeslib.as_array(ctypes.cast(int(ptr), ctypes.POINTER(ctypes.c_uint16)), shape=(n,))
+    return torch.from_numpy(raw.view(np.int16)).view(torch.bfloat16).view(shape)
+
+
+def gaot_gemm_bf16(A, B, C, M, N, K, out_bf16, bias, add, add_rows, ldadd, accumulate):
+    v = _bf(A, (M, K)).double() @ _bf(B, (N, K)).double().T
+    if bias:
+        v = v + _t(bias, (N,)).double()
+    if add:
+        v = v + _strided(add, add_rows, N, ldadd).double().repeat(M // add_rows, 1)
+    if out_bf16:
+        _bf(C, (M, N))[:] = v.to(torch.bfloat16)
+    else:
+        c = _t(C, (M, N))
+        c[:] = (v + c.double()).float() if accumulate else v.float()
+
+
+def gaot_cast_bf16(inp, out, rows, cols, out_t):
+    x = _t(inp, (rows, cols))
+    if out:
+        _bf(out, (rows, cols))[:] = x.to(torch.bfloat16)
+    if out_t:
+        _bf(out_t, (cols, rows))[:] = x.T.to(torch.bfloat16)
+
+
+def gaot_transpose_bf16(inp, out_t, rows, cols):
+    _bf(out_t, (cols, rows))[:] = _bf(inp, (rows, cols)).T
+
+
 def gaot_col_sum(x, M, N, out, accumulate):
     o = _arr(out, (N,))
     s = _arr(x, (M, N)).astype(np.float64).sum(0)

@@ -1,0 +1,80 @@
+"""GPU tests of the tensor-core (tcgen05 / TMA / TMEM) performance path.  Run with -m gpu.
+
+Tolerances: the GEMM itself is compared against an fp64 product of the SAME bf16-rounded operands, so
+only accumulation order differs (<= 2e-5 relative L2, K up to 32768).  The bf16 *mode* of the model
+rounds activations and weights to bf16 (8 mantissa bits) at every processor GEMM input, so it is
+checked against the fp64 reference golden vectors at 2e-2 (forward) / 6e-2 (gradients) relative L2;
+the 1e-5 parity bar applies to the fp32 mode (tests/test_gpu_model.py)."""
+import pytest
+import torch
+
+from oracle import cases
+from tests.helpers import build_model, golden_params, load_golden, rel_l2
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 64, 256), (1000, 200, 136), (4096, 768, 256), (256, 256, 32768),
+                                   (77, 24, 8), (2048, 2048, 1024)])
+def test_gemm_bf16_vs_fp64_of_rounded_operands(M, N, K):
+    from gaot_b200 import ops
+    a = cases.normal((M, K), 1).to(DEV)
+    b = (cases.normal((N, K), 2) / K ** 0.5).to(DEV)
+    bias = cases.normal((N,), 3).to(DEV)
+    R = M // 2 if M % 2 == 0 else M
+    add = cases.normal((R, N), 4).to(DEV)
+    ab, _ = ops.cast_bf16(a)
+    bb, bt = ops.cast_bf16(b, want=True, want_t=True)
+    assert torch.equal(ab, a.to(torch.bfloat16)) and torch.equal(bt, b.to(torch.bfloat16).T.contiguous())
+    assert torch.equal(ops.transpose_bf16(ab), ab.T.contiguous())
+    want = ab.double() @ bb.double().T
+    got = ops.gemm_bf16(ab, bb, M, N, K)
+    assert rel_l2(got, want) < 2e-5
+    got = ops.gemm_bf16(ab, bb, M, N, K, bias=bias, add=add, add_rows=R)
+    assert rel_l2(got, want + bias.double() + add.double().repeat(M // R, 1)) < 2e-5
+    got16 = ops.gemm_bf16(ab, bb, M, N, K, out_bf16=True)
+    assert got16.dtype == torch.bfloat16 and rel_l2(got16, want) < 4e-3
+    acc = torch.ones((M, N), device=DEV)
+    ops.gemm_bf16(ab, bb, M, N, K, out=acc, accumulate=True)
+    assert rel_l2(acc, want + 1.0) < 2e-5
+
+
+def test_linear_tc_fwd_bwd():
+    from gaot_b200 import ops
+    M, N, K = 1024, 256, 512
+    x, W, b = cases.normal((M, K), 5), cases.normal((N, K), 6) / K ** 0.5, cases.normal((N,), 7)
+    add, gy = cases.normal((M, N), 8), cases.normal((M, N), 9)
+    ops.set_precision("bf16")
+    try:
+        xs = [t.clone().to(DEV).requires_grad_(True) for t in (x, W, b, add)]
+        y = ops.linear(xs[0], xs[1], xs[2], add=xs[3], tc=True)
+        y.backward(gy.to(DEV))
+    finally:
+        ops.set_precision("fp32")
+    xr = [t.clone().double().requires_grad_(True) for t in (x, W, b, add)]
+    yr = xr[0] @ xr[1].T + xr[2] + xr[3]
+    yr.backward(gy.double())
+    assert rel_l2(y, yr) < 5e-3
+    for a, r_ in zip(xs, xr):
+        assert rel_l2(a.grad, r_.grad) < 6e-3
+
+
+@pytest.mark.parametrize("name", ["tiny2d", "tiny3d"])
+def test_model_bf16_mode_close_to_reference(name):
+    from gaot_b200 import ops
+    c = cases.CASES[name]
+    g = load_golden(name)
+    ops.set_precision("bf16")
+    try:
+        model = build_model(c)
+        model.load_state_dict({k: v.to(DEV) for k, v in golden_params(g).items()})
+        lat, x, pn, tgt = [t.to(DEV) for t in cases.case_inputs(name)]
+        out = model(lat, x, pn)
+        loss = ops.mse_loss(out, tgt)
+        loss.backward()
+    finally:
+        ops.set_precision("fp32")
+    assert rel_l2(out, g["out"]) < 2e-2
+    for k, p in model.named_parameters():
+        assert rel_l2(p.grad, g["grad." + k]) < 6e-2, k

@@ -194,3 +194,27 @@ def test_rollout_matches_oracle_update_rules():
             pred = model(lat, x, inp)
             cur = orc.rollout_update(pred, cur, dt, stats, "time_der")
             assert rel_l2(got[:, i], cur) < 1e-6
+
+
+def test_bf16_mode_wiring_close_to_reference():
+    """precision='bf16' routes the processor's Linear layers through the tensor-core ABI (emulated here);
+    bf16 operand rounding keeps the output within a few 1e-3 of the fp64 reference on the tiny model."""
+    name = "tiny2d"
+    c = cases.CASES[name]
+    g = load_golden(name)
+    with abi_emulator.install() as calls:
+        from gaot_b200 import ops
+        ops.set_precision("bf16")
+        try:
+            model = build_model(c, "cpu")
+            model.load_state_dict(golden_params(g))
+            lat, x, pn, tgt = cases.case_inputs(name)
+            out = model(lat, x, pn)
+            loss = ops.mse_loss(out, tgt)
+            loss.backward()
+        finally:
+            ops.set_precision("fp32")
+        assert "gaot_gemm_bf16" in calls and "gaot_transpose_bf16" in calls
+    assert rel_l2(out, g["out"]) < 2e-2
+    for k, p in model.named_parameters():
+        assert rel_l2(p.grad, g["grad." + k]) < 6e-2, k
