@@ -1,0 +1,661 @@
+// Tensor-core attention (performance path): non-causal softmax(Q K^T * scale) V on tcgen05 with TMA-staged
+// bf16 tiles and TMEM accumulators, forward and backward.  Reference: GroupQueryFlashAttention.forward,
+// src/model/layers/attn.py:96-116 (F.scaled_dot_product_attention) and its autograd backward.
+//
+// Layout: fused qkv [B*T, ld] bf16 (per token: H*hd query | Hkv*hd key | Hkv*hd value columns), one TMA
+// tensor map over that matrix with a {hd, 128 rows} box whose swizzle span equals the row bytes of a head.
+//
+// Forward, one CTA per (128-query tile, head, sample):
+//   warp 0   TMA producer: Q once, then K/V tiles of 128 keys through a 2-stage mbarrier ring
+//   warp 1   MMA issuer  : S = Q K^T  (tcgen05.mma M=128,N=128, operands straight from the swizzled tiles)
+//                          PV = P V   (A = P written by the softmax warps as a K-major SWIZZLE_128B tile,
+//                                      B = V used in place as an MN-major operand)
+//   warps 2-5 softmax    : one thread per query row reads its S row from TMEM (tcgen05.ld), online softmax in
+//                          base 2, writes P (bf16) to shared memory, then folds PV into its fp32 output row
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "../../include/gaot_b200.h"
+
+namespace {
+
+constexpr int AT_THREADS = 192;
+constexpr int AT_BQ = 128, AT_BKV = 128;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_c, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_c), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+// shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp): rows of ROWB bytes, swizzle span == ROWB,
+// 8-row atoms SBO bytes apart; layout code 2 = SWIZZLE_128B, 4 = SWIZZLE_64B, 6 = SWIZZLE_32B
+template <int ROWB>
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+    constexpr uint64_t layout = ROWB == 128 ? 2 : (ROWB == 64 ? 4 : 6);
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)((8 * ROWB) >> 4) << 32) | ((uint64_t)1 << 46) |
+           (layout << 61);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,"
+        "%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]),
+          "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]),
+          "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+    __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&t);
+}
+// address of the 16-byte piece `chunk` (0..7) of row r inside a K-major SWIZZLE_128B tile of 128-byte rows
+__device__ __forceinline__ uint32_t sw128_off(int r, int chunk) {
+    return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((chunk ^ (r & 7)) << 4));
+}
+
+struct AttnArgs {
+    void* o;            // bf16 [B*T, H*hd]
+    float* lse;         // [B,H,T] natural log
+    int T, H, Hkv, koff, voff;   // column offsets (elements) of the key / value blocks inside a qkv row
+    float scale_log2;
+};
+
+template <int HD>
+__global__ void __launch_bounds__(AT_THREADS)
+attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttnArgs g) {
+    constexpr int ROWB = HD * 2;                         // bytes per head row = swizzle span
+    constexpr int TILE_BYTES = 128 * ROWB;               // a 128-row Q / K / V tile
+    constexpr int P_BYTES = AT_BQ * AT_BKV * 2;          // 32 KB: two 64-column SWIZZLE_128B blocks
+    constexpr uint32_t TMEM_COLS = 256;                  // S: [0,128), PV: [128,128+HD)
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sQ = smem;
+    uint8_t* sK = sQ + TILE_BYTES;                       // [2 stages]
+    uint8_t* sV = sK + 2 * TILE_BYTES;                   // [2 stages]
+    uint8_t* sP = sV + 2 * TILE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + P_BYTES);
+    uint64_t* q_bar = bars;
+    uint64_t* kv_full = bars + 1;      // [2]
+    uint64_t* kv_empty = bars + 3;     // [2]
+    uint64_t* s_full = bars + 5;
+    uint64_t* p_full = bars + 6;
+    uint64_t* o_full = bars + 7;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int t0 = blockIdx.x * AT_BQ, h = blockIdx.y, b = blockIdx.z;
+    const int hk = h / (g.H / g.Hkv);
+    const int row_base = b * g.T;
+    const int n_tiles = (g.T + AT_BKV - 1) / AT_BKV;
+
+    if (threadIdx.x == 0) {
+        mbar_init(q_bar, 1);
+        for (int s = 0; s < 2; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+        mbar_init(s_full, 1); mbar_init(p_full, 128); mbar_init(o_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t tmem_s = tmem, tmem_pv = tmem + 128;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_expect_tx(q_bar, TILE_BYTES);
+            tma_load_2d(sQ, &tm, q_bar, h * HD, row_base + t0);
+            for (int i = 0; i < n_tiles; ++i) {
+                const int s = i & 1;
+                mbar_wait(&kv_empty[s], ((uint32_t)(i >> 1) & 1u) ^ 1u);
+                mbar_expect_tx(&kv_full[s], 2 * TILE_BYTES);
+                tma_load_2d(sK + s * TILE_BYTES, &tm, &kv_full[s], g.koff + hk * HD, row_base + i * AT_BKV);
+                tma_load_2d(sV + s * TILE_BYTES, &tm, &kv_full[s], g.voff + hk * HD, row_base + i * AT_BKV);
+            }
+        }
+    } else if (warp == 1) {
+        // S: M=128, N=128, A (Q) and B (K) K-major.  PV: M=128, N=HD, A (P) K-major, B (V) MN-major (bit 16).
+        constexpr uint32_t IDESC_S = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(AT_BKV >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        constexpr uint32_t IDESC_PV = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(HD >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        mbar_wait(q_bar, 0);
+        auto issue_s = [&](int i) {
+            const int s = i & 1;
+            mbar_wait(&kv_full[s], (uint32_t)(i >> 1) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (lane == 0) {
+                const uint64_t dq = make_desc<ROWB>(smem_u32(sQ)), dk = make_desc<ROWB>(smem_u32(sK + s * TILE_BYTES));
+#pragma unroll
+                for (int k = 0; k < HD / 16; ++k) umma_f16(tmem_s, dq + (uint64_t)(2 * k), dk + (uint64_t)(2 * k), IDESC_S, k > 0 ? 1u : 0u);
+                umma_commit(s_full);
+            }
+            __syncwarp();
+        };
+        issue_s(0);
+        for (int i = 0; i < n_tiles; ++i) {
+            const int s = i & 1;
+            mbar_wait(p_full, (uint32_t)i & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (lane == 0) {
+                const uint32_t pv = smem_u32(sV + s * TILE_BYTES), pp = smem_u32(sP);
+#pragma unroll
+                for (int k = 0; k < AT_BKV / 16; ++k) {
+                    // A: 16 keys = 32 bytes inside the 128-byte swizzle row of P's column block (k / 4)
+                    const uint64_t da = make_desc<128>(pp + (k >> 2) * (AT_BQ * 128)) + (uint64_t)(2 * (k & 3));
+                    // B: 16 keys = 16 rows of V, two 8-row swizzle atoms
+                    const uint64_t db = make_desc<ROWB>(pv + k * 16 * ROWB);
+                    umma_f16(tmem_pv, da, db, IDESC_PV, k > 0 ? 1u : 0u);
+                }
+                umma_commit(o_full);
+                umma_commit(&kv_empty[s]);
+            }
+            __syncwarp();
+            if (i + 1 < n_tiles) issue_s(i + 1);
+        }
+    } else {
+        const int q = warp & 3;
+        const int r = q * 32 + lane;                       // query row inside the tile == TMEM lane
+        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+        float o[HD];
+#pragma unroll
+        for (int d = 0; d < HD; ++d) o[d] = 0.f;
+        float mrun = -INFINITY, lrun = 0.f;
+        for (int i = 0; i < n_tiles; ++i) {
+            mbar_wait(s_full, (uint32_t)i & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int kv_left = g.T - i * AT_BKV;          // keys of this tile that exist
+            float mx = -INFINITY;
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                uint32_t v[32];
+                tmem_ld32(tmem_s + lane_addr + c * 32, v);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float sv = (c * 32 + j < kv_left) ? __uint_as_float(v[j]) * g.scale_log2 : -INFINITY;
+                    mx = fmaxf(mx, sv);
+                }
+            }
+            const float mnew = fmaxf(mrun, mx);
+            const float corr = exp2f(mrun - mnew);
+            float psum = 0.f;
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                uint32_t v[32];
+                tmem_ld32(tmem_s + lane_addr + c * 32, v);
+                uint32_t pk[16];
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                    const float p0 = (c * 32 + j < kv_left) ? exp2f(__uint_as_float(v[j]) * g.scale_log2 - mnew) : 0.f;
+                    const float p1 = (c * 32 + j + 1 < kv_left) ? exp2f(__uint_as_float(v[j + 1]) * g.scale_log2 - mnew) : 0.f;
+                    psum += p0 + p1;
+                    pk[j >> 1] = pack_bf16(p0, p1);
+                }
+                uint8_t* blk = sP + (c >> 1) * (AT_BQ * 128);
+#pragma unroll
+                for (int w = 0; w < 4; ++w)
+                    *reinterpret_cast<uint4*>(blk + sw128_off(r, (c & 1) * 4 + w)) = make_uint4(pk[4 * w], pk[4 * w + 1], pk[4 * w + 2], pk[4 * w + 3]);
+            }
+            lrun = lrun * corr + psum;
+            mrun = mnew;
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes of P -> async proxy (MMA)
+            mbar_arrive(p_full);
+            mbar_wait(o_full, (uint32_t)i & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int c = 0; c < HD / 16; ++c) {
+                uint32_t v[16];
+                tmem_ld16(tmem_pv + lane_addr + c * 16, v);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) o[c * 16 + j] = o[c * 16 + j] * corr + __uint_as_float(v[j]);
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        }
+        const int t = t0 + r;
+        if (t < g.T) {
+            const float inv = 1.f / lrun;
+            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(g.o) + ((int64_t)(row_base + t) * g.H + h) * HD;
+#pragma unroll
+            for (int d = 0; d < HD; d += 8)
+                *reinterpret_cast<uint4*>(op + d) = make_uint4(pack_bf16(o[d] * inv, o[d + 1] * inv), pack_bf16(o[d + 2] * inv, o[d + 3] * inv),
+                                                               pack_bf16(o[d + 4] * inv, o[d + 5] * inv), pack_bf16(o[d + 6] * inv, o[d + 7] * inv));
+            g.lse[((int64_t)b * g.H + h) * g.T + t] = (mrun + log2f(lrun)) * 0.69314718055994531f;
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Backward.  One CTA per (128-key tile, KV head, sample); it loops over the query heads of its group and
+// over 128-query tiles.  Rows (TMEM lanes, threads) are KEYS for S^T, dP^T, dV, dK and QUERIES for dQ:
+//   S^T  = K Q^T            dP^T = V dO^T                         (A, B K-major)
+//   P^T  = exp2(S^T*c - lse2[q]),   dS^T = P^T * (dP^T - delta[q])   (per thread = per key row)
+//   dV  += P^T dO           dK  += dS^T Q                         (A K-major from smem, B MN-major in place)
+//   dQ   = dS K                                                    (A = dS^T tile read MN-major, B = K MN-major)
+// dV / dK accumulate in TMEM over all query tiles; dQ tiles are drained per step into an fp32 buffer
+// with 128-bit red.add (different key tiles contribute to the same dQ rows).
+// ------------------------------------------------------------------------------------------------
+struct AttnBwdArgs {
+    const float* lse;      // [B,H,T] natural log
+    const float* delta;    // [B,H,T] rowsum(dO * O)
+    float* dq_acc;         // fp32 [B*T, H*hd], zero-initialised
+    void* dqkv;            // bf16 [B*T, ld]: dK and dV are written here (dQ is converted afterwards)
+    int T, H, Hkv, koff, voff, ld;
+    float scale, scale_log2;
+};
+
+template <int HD>
+__global__ void __launch_bounds__(AT_THREADS)
+attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUtensorMap tmdo, const AttnBwdArgs g) {
+    constexpr int ROWB = HD * 2;
+    constexpr int TILE_BYTES = 128 * ROWB;
+    constexpr int PT_BYTES = 128 * 128 * 2;
+    constexpr uint32_t TMEM_COLS = 512;      // S^T [0,128) dP^T [128,256) dV [256,..) dK [320,..) dQ [384,..)
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sK = smem;
+    uint8_t* sV = sK + TILE_BYTES;
+    uint8_t* sQ = sV + TILE_BYTES;           // [2 stages]
+    uint8_t* sG = sQ + 2 * TILE_BYTES;       // dO, [2 stages]
+    uint8_t* sPt = sG + 2 * TILE_BYTES;
+    uint8_t* sSt = sPt + PT_BYTES;
+    float* sLse = reinterpret_cast<float*>(sSt + PT_BYTES);   // [2][128] base-2 lse
+    float* sDel = sLse + 256;                                  // [2][128]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sDel + 256);
+    uint64_t* kv_bar = bars;
+    uint64_t* q_full = bars + 1;     // [2]
+    uint64_t* q_empty = bars + 3;    // [2]
+    uint64_t* st_full = bars + 5;
+    uint64_t* pds_full = bars + 6;   // 128 arrivals
+    uint64_t* dq_full = bars + 7;
+    uint64_t* dq_empty = bars + 8;   // 128 arrivals
+    uint64_t* fin_bar = bars + 9;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int k0 = blockIdx.x * 128, hk = blockIdx.y, b = blockIdx.z;
+    const int rep = g.H / g.Hkv;
+    const int row_base = b * g.T;
+    const int n_qt = (g.T + 127) / 128;
+    const int n_steps = rep * n_qt;
+
+    if (threadIdx.x == 0) {
+        mbar_init(kv_bar, 1);
+        for (int s = 0; s < 2; ++s) { mbar_init(&q_full[s], 1); mbar_init(&q_empty[s], 1); }
+        mbar_init(st_full, 1); mbar_init(pds_full, 128); mbar_init(dq_full, 1); mbar_init(dq_empty, 128); mbar_init(fin_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t tm_st = tmem, tm_dp = tmem + 128, tm_dv = tmem + 256, tm_dk = tmem + 320, tm_dq = tmem + 384;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_expect_tx(kv_bar, 2 * TILE_BYTES);
+            tma_load_2d(sK, &tm, kv_bar, g.koff + hk * HD, row_base + k0);
+            tma_load_2d(sV, &tm, kv_bar, g.voff + hk * HD, row_base + k0);
+            for (int i = 0; i < n_steps; ++i) {
+                const int s = i & 1, h = hk * rep + i / n_qt, q0 = (i % n_qt) * 128;
+                mbar_wait(&q_empty[s], ((uint32_t)(i >> 1) & 1u) ^ 1u);
+                mbar_expect_tx(&q_full[s], 2 * TILE_BYTES);
+                tma_load_2d(sQ + s * TILE_BYTES, &tm, &q_full[s], h * HD, row_base + q0);
+                tma_load_2d(sG + s * TILE_BYTES, &tmdo, &q_full[s], h * HD, row_base + q0);
+            }
+        }
+    } else if (warp == 1) {
+        constexpr uint32_t BASE = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 4) << 24);
+        constexpr uint32_t IDESC_ST = BASE | ((uint32_t)(128 >> 3) << 17);                           // N=128, K-major x K-major
+        constexpr uint32_t IDESC_KN = BASE | (1u << 16) | ((uint32_t)(HD >> 3) << 17);               // N=HD, B MN-major
+        constexpr uint32_t IDESC_MN = BASE | (1u << 15) | (1u << 16) | ((uint32_t)(HD >> 3) << 17);  // A and B MN-major
+        mbar_wait(kv_bar, 0);
+        auto issue_st = [&](int i) {
+            const int s = i & 1;
+            mbar_wait(&q_full[s], (uint32_t)(i >> 1) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (lane == 0) {
+                const uint64_t dk = make_desc<ROWB>(smem_u32(sK)), dv = make_desc<ROWB>(smem_u32(sV));
+                const uint64_t dq = make_desc<ROWB>(smem_u32(sQ + s * TILE_BYTES)), dg = make_desc<ROWB>(smem_u32(sG + s * TILE_BYTES));
+#pragma unroll
+                for (int k = 0; k < HD / 16; ++k) umma_f16(tm_st, dk + (uint64_t)(2 * k), dq + (uint64_t)(2 * k), IDESC_ST, k > 0 ? 1u : 0u);
+#pragma unroll
+                for (int k = 0; k < HD / 16; ++k) umma_f16(tm_dp, dv + (uint64_t)(2 * k), dg + (uint64_t)(2 * k), IDESC_ST, k > 0 ? 1u : 0u);
+                umma_commit(st_full);
+            }
+            __syncwarp();
+        };
+        issue_st(0);
+        for (int i = 0; i < n_steps; ++i) {
+            const int s = i & 1;
+            mbar_wait(pds_full, (uint32_t)i & 1u);
+            if (i > 0) mbar_wait(dq_empty, (uint32_t)(i - 1) & 1u);       // previous dQ tile drained from TMEM
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (lane == 0) {
+                const uint32_t pq = smem_u32(sQ + s * TILE_BYTES), pg = smem_u32(sG + s * TILE_BYTES);
+                const uint32_t ppt = smem_u32(sPt), pst = smem_u32(sSt), pk = smem_u32(sK);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {      // contraction over 128 queries, 16 per MMA
+                    const uint64_t a_p = make_desc<128>(ppt + (k >> 2) * (128 * 128)) + (uint64_t)(2 * (k & 3));
+                    const uint64_t a_s = make_desc<128>(pst + (k >> 2) * (128 * 128)) + (uint64_t)(2 * (k & 3));
+                    umma_f16(tm_dv, a_p, make_desc<ROWB>(pg + k * 16 * ROWB), IDESC_KN, (i > 0 || k > 0) ? 1u : 0u);
+                    umma_f16(tm_dk, a_s, make_desc<ROWB>(pq + k * 16 * ROWB), IDESC_KN, (i > 0 || k > 0) ? 1u : 0u);
+                }
+                // dQ[q, :] = sum_keys dS^T[key, q] K[key, :]: A = the dS^T tile as an MN-major operand
+                // (M = 128 queries = two 64-wide swizzle atoms LBO = 16 KB apart, 8-key groups SBO = 1 KB apart)
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {      // contraction over 128 keys, 16 per MMA = 16 rows of 128 bytes
+                    const uint64_t a_mn = (uint64_t)(((pst + k * 2048) & 0x3FFFF) >> 4) | ((uint64_t)(16384 >> 4) << 16) |
+                                          ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+                    umma_f16(tm_dq, a_mn, make_desc<ROWB>(pk + k * 16 * ROWB), IDESC_MN, k > 0 ? 1u : 0u);
+                }
+                umma_commit(dq_full);
+                umma_commit(&q_empty[s]);
+                if (i == n_steps - 1) umma_commit(fin_bar);
+            }
+            __syncwarp();
+            if (i + 1 < n_steps) issue_st(i + 1);
+        }
+    } else {
+        const int q4 = warp & 3;
+        const int r = q4 * 32 + lane;                      // key row for S^T.., query row for dQ
+        const uint32_t lane_addr = (uint32_t)(q4 * 32) << 16;
+        const bool key_ok = k0 + r < g.T;
+        const int ct = threadIdx.x - 64;                   // 0..127
+        for (int i = 0; i < n_steps; ++i) {
+            const int s = i & 1, h = hk * rep + i / n_qt, q0 = (i % n_qt) * 128;
+            // stage this step's per-query statistics (base-2 lse, delta); +inf lse switches a query column off
+            {
+                const bool ok = q0 + ct < g.T;
+                const int64_t off = ((int64_t)b * g.H + h) * g.T + q0 + ct;
+                sLse[s * 128 + ct] = ok ? g.lse[off] * 1.4426950408889634f : INFINITY;
+                sDel[s * 128 + ct] = ok ? g.delta[off] : 0.f;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            mbar_wait(st_full, (uint32_t)i & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                uint32_t sv[32], dv[32];
+                tmem_ld32(tm_st + lane_addr + c * 32, sv);
+                tmem_ld32(tm_dp + lane_addr + c * 32, dv);
+                uint32_t pp[16], ds[16];
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                    const float l0 = sLse[s * 128 + c * 32 + j], l1 = sLse[s * 128 + c * 32 + j + 1];
+                    float p0 = exp2f(__uint_as_float(sv[j]) * g.scale_log2 - l0);
+                    float p1 = exp2f(__uint_as_float(sv[j + 1]) * g.scale_log2 - l1);
+                    if (!key_ok) { p0 = 0.f; p1 = 0.f; }
+                    const float d0 = p0 * (__uint_as_float(dv[j]) - sDel[s * 128 + c * 32 + j]);
+                    const float d1 = p1 * (__uint_as_float(dv[j + 1]) - sDel[s * 128 + c * 32 + j + 1]);
+                    pp[j >> 1] = pack_bf16(p0, p1);
+                    ds[j >> 1] = pack_bf16(d0, d1);
+                }
+                uint8_t* bp = sPt + (c >> 1) * (128 * 128);
+                uint8_t* bs = sSt + (c >> 1) * (128 * 128);
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+                    const uint32_t off = sw128_off(r, (c & 1) * 4 + w);
+                    *reinterpret_cast<uint4*>(bp + off) = make_uint4(pp[4 * w], pp[4 * w + 1], pp[4 * w + 2], pp[4 * w + 3]);
+                    *reinterpret_cast<uint4*>(bs + off) = make_uint4(ds[4 * w], ds[4 * w + 1], ds[4 * w + 2], ds[4 * w + 3]);
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive(pds_full);
+            // drain dQ: here the TMEM lane is the QUERY row
+            mbar_wait(dq_full, (uint32_t)i & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            {
+                const int t = q0 + r;
+                float* dst = g.dq_acc + ((int64_t)(row_base + t) * g.H + h) * HD;
+#pragma unroll
+                for (int c = 0; c < HD / 16; ++c) {
+                    uint32_t v[16];
+                    tmem_ld16(tm_dq + lane_addr + c * 16, v);
+                    if (t < g.T) {
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4)
+                            atomicAdd(reinterpret_cast<float4*>(dst + c * 16 + j),
+                                      make_float4(__uint_as_float(v[j]) * g.scale, __uint_as_float(v[j + 1]) * g.scale,
+                                                  __uint_as_float(v[j + 2]) * g.scale, __uint_as_float(v[j + 3]) * g.scale));
+                    }
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(dq_empty);
+        }
+        // final: dV and dK rows of this key tile
+        mbar_wait(fin_bar, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        {
+            __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(g.dqkv) + (int64_t)(row_base + k0 + r) * g.ld;
+#pragma unroll
+            for (int c = 0; c < HD / 16; ++c) {
+                uint32_t vv[16], vk[16];
+                tmem_ld16(tm_dv + lane_addr + c * 16, vv);
+                tmem_ld16(tm_dk + lane_addr + c * 16, vk);
+                if (key_ok) {
+                    __nv_bfloat16* pv = base + g.voff + hk * HD + c * 16;
+                    __nv_bfloat16* pk = base + g.koff + hk * HD + c * 16;
+#pragma unroll
+                    for (int j = 0; j < 16; j += 8) {
+                        *reinterpret_cast<uint4*>(pv + j) = make_uint4(
+                            pack_bf16(__uint_as_float(vv[j]), __uint_as_float(vv[j + 1])), pack_bf16(__uint_as_float(vv[j + 2]), __uint_as_float(vv[j + 3])),
+                            pack_bf16(__uint_as_float(vv[j + 4]), __uint_as_float(vv[j + 5])), pack_bf16(__uint_as_float(vv[j + 6]), __uint_as_float(vv[j + 7])));
+                        *reinterpret_cast<uint4*>(pk + j) = make_uint4(
+                            pack_bf16(__uint_as_float(vk[j]) * g.scale, __uint_as_float(vk[j + 1]) * g.scale),
+                            pack_bf16(__uint_as_float(vk[j + 2]) * g.scale, __uint_as_float(vk[j + 3]) * g.scale),
+                            pack_bf16(__uint_as_float(vk[j + 4]) * g.scale, __uint_as_float(vk[j + 5]) * g.scale),
+                            pack_bf16(__uint_as_float(vk[j + 6]) * g.scale, __uint_as_float(vk[j + 7]) * g.scale));
+                    }
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS));
+    }
+}
+
+// delta[b,h,t] = sum_d dO[t,h,d] * O[t,h,d]   (bf16 in, fp32 out); one thread per (token, head)
+template <int HD>
+__global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dout,
+                                  float* __restrict__ delta, int64_t B, int64_t T, int H) {
+    const int64_t total = B * T * H;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int h = (int)(i % H);
+        const int64_t bt = i / H;
+        const uint4* po = reinterpret_cast<const uint4*>(o + i * HD);
+        const uint4* pg = reinterpret_cast<const uint4*>(dout + i * HD);
+        float acc = 0.f;
+#pragma unroll
+        for (int c = 0; c < HD / 8; ++c) {
+            const uint4 a = __ldg(po + c), g4 = __ldg(pg + c);
+            const __nv_bfloat162* x = reinterpret_cast<const __nv_bfloat162*>(&a);
+            const __nv_bfloat162* y = reinterpret_cast<const __nv_bfloat162*>(&g4);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float2 fx = __bfloat1622float2(x[k]), fy = __bfloat1622float2(y[k]);
+                acc = fmaf(fx.x, fy.x, acc); acc = fmaf(fx.y, fy.y, acc);
+            }
+        }
+        delta[((bt / T) * H + h) * T + (bt % T)] = acc;
+    }
+}
+
+// dqkv[row, 0:W] = bf16(dq_acc[row, 0:W])   (W = H*hd query columns of the fused gradient)
+__global__ void attn_dq_store_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dqkv, int64_t rows, int W, int ld) {
+    const int64_t total = rows * (W / 4);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = i / (W / 4);
+        const int c = (int)(i % (W / 4)) * 4;
+        const float4 v = __ldg(reinterpret_cast<const float4*>(acc + row * W + c));
+        uint2 pk;
+        pk.x = pack_bf16(v.x, v.y); pk.y = pack_bf16(v.z, v.w);
+        *reinterpret_cast<uint2*>(dqkv + row * ld + c) = pk;
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// [rows, ld] bf16 matrix, box {hd, box_rows}, swizzle span = hd*2 bytes
+int make_head_map(CUtensorMap* map, const void* base, int64_t rows, int64_t ld, int hd, int box_rows) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return GAOT_E_BADARG;
+    cuuint64_t dims[2] = {(cuuint64_t)ld, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {(cuuint32_t)hd, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    const CUtensorMapSwizzle sw = hd == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (hd == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : GAOT_E_BADARG;
+}
+
+template <int HD>
+int launch_fwd(const CUtensorMap& tm, const AttnArgs& g, int64_t B, cudaStream_t st) {
+    constexpr int SMEM = 5 * 128 * HD * 2 + AT_BQ * AT_BKV * 2 + 1024 + 256;
+    static bool done = false;
+    if (!done) {
+        GAOT_CHECK(cudaFuncSetAttribute(attn_fwd_tc_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+        done = true;
+    }
+    dim3 grid((unsigned)((g.T + AT_BQ - 1) / AT_BQ), (unsigned)g.H, (unsigned)B);
+    attn_fwd_tc_kernel<HD><<<grid, AT_THREADS, SMEM, st>>>(tm, g);
+    GAOT_RETURN_LAST();
+}
+
+}  // namespace
+
+GAOT_API int gaot_attention_fwd_bf16(const void* qkv, void* o, float* lse, int64_t B, int64_t T, int64_t H, int64_t Hkv,
+                                     int64_t hd, int64_t ld, float scale, void* stream) {
+    if (!qkv || !o || !lse || B < 1 || T < 1 || H < 1 || Hkv < 1 || H % Hkv) return GAOT_E_BADARG;
+    if (hd != 16 && hd != 32 && hd != 64) return GAOT_E_BADARG;
+    if (ld < (H + 2 * Hkv) * hd || ld % 8 || (reinterpret_cast<uintptr_t>(qkv) & 15) || (reinterpret_cast<uintptr_t>(o) & 15))
+        return GAOT_E_ALIGN;
+    if (B > 65535 || H > 65535 || B * T > 0x7fffffffLL) return GAOT_E_BADARG;
+    CUtensorMap tm;
+    int rc = make_head_map(&tm, qkv, B * T, ld, (int)hd, 128);
+    if (rc) return rc;
+    AttnArgs g{o, lse, (int)T, (int)H, (int)Hkv, (int)(H * hd), (int)((H + Hkv) * hd), scale * 1.4426950408889634f};
+    cudaStream_t st = (cudaStream_t)stream;
+    if (hd == 16) return launch_fwd<16>(tm, g, B, st);
+    if (hd == 32) return launch_fwd<32>(tm, g, B, st);
+    return launch_fwd<64>(tm, g, B, st);
+}
+
+namespace {
+template <int HD>
+int launch_bwd(const CUtensorMap& tm, const CUtensorMap& tmdo, const AttnBwdArgs& g, const void* o, const void* dout,
+               float* delta, int64_t B, cudaStream_t st) {
+    constexpr int SMEM = 6 * 128 * HD * 2 + 2 * 128 * 128 * 2 + 2048 + 1024 + 256;
+    static bool done = false;
+    if (!done) {
+        GAOT_CHECK(cudaFuncSetAttribute(attn_bwd_tc_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+        done = true;
+    }
+    const int64_t rows = B * g.T;
+    attn_delta_kernel<HD><<<gaot_grid(rows * g.H, 256), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(o),
+                                                                     reinterpret_cast<const __nv_bfloat16*>(dout), delta, B, g.T, g.H);
+    GAOT_CHECK(cudaMemsetAsync(g.dq_acc, 0, sizeof(float) * (size_t)(rows * g.H * HD), st));
+    dim3 grid((unsigned)((g.T + 127) / 128), (unsigned)g.Hkv, (unsigned)B);
+    attn_bwd_tc_kernel<HD><<<grid, AT_THREADS, SMEM, st>>>(tm, tmdo, g);
+    attn_dq_store_kernel<<<gaot_grid(rows * g.H * HD / 4, 256), 256, 0, st>>>(g.dq_acc, reinterpret_cast<__nv_bfloat16*>(g.dqkv), rows,
+                                                                            g.H * HD, g.ld);
+    GAOT_NOTE_LAUNCHES(2);
+    GAOT_RETURN_LAST();
+}
+}  // namespace
+
+GAOT_API int gaot_attention_bwd_bf16(const void* qkv, const void* o, const float* lse, const void* dout, float* delta,
+                                     float* dq_acc, void* dqkv, int64_t B, int64_t T, int64_t H, int64_t Hkv, int64_t hd,
+                                     int64_t ld, float scale, void* stream) {
+    if (!qkv || !o || !lse || !dout || !delta || !dq_acc || !dqkv || B < 1 || T < 1 || H < 1 || Hkv < 1 || H % Hkv) return GAOT_E_BADARG;
+    if (hd != 16 && hd != 32 && hd != 64) return GAOT_E_BADARG;
+    if (ld < (H + 2 * Hkv) * hd || ld % 8 || (reinterpret_cast<uintptr_t>(qkv) & 15) || (reinterpret_cast<uintptr_t>(dout) & 15) ||
+        (reinterpret_cast<uintptr_t>(dqkv) & 15) || (reinterpret_cast<uintptr_t>(dq_acc) & 15) || (reinterpret_cast<uintptr_t>(o) & 15))
+        return GAOT_E_ALIGN;
+    if (B > 65535 || Hkv > 65535 || B * T > 0x7fffffffLL) return GAOT_E_BADARG;
+    CUtensorMap tm, tmdo;
+    int rc = make_head_map(&tm, qkv, B * T, ld, (int)hd, 128);
+    if (rc) return rc;
+    rc = make_head_map(&tmdo, dout, B * T, H * hd, (int)hd, 128);
+    if (rc) return rc;
+    AttnBwdArgs g{lse, delta, dq_acc, dqkv, (int)T, (int)H, (int)Hkv, (int)(H * hd), (int)((H + Hkv) * hd), (int)ld, scale,
+                  scale * 1.4426950408889634f};
+    cudaStream_t st = (cudaStream_t)stream;
+    if (hd == 16) return launch_bwd<16>(tm, tmdo, g, o, dout, delta, B, st);
+    if (hd == 32) return launch_bwd<32>(tm, tmdo, g, o, dout, delta, B, st);
+    return launch_bwd<64>(tm, tmdo, g, o, dout, delta, B, st);
+}

@@ -152,14 +152,19 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
     } else {
         // ---------------- epilogue (warps 2..5; warp w may touch TMEM lanes 32*(w%4) .. +31) ----------------
+        // TMEM hands each thread one accumulator ROW; a per-warp 32x32 staging tile (aliasing ring stage 0,
+        // idle once the accumulator is complete) turns that into row-contiguous 128-byte global accesses:
+        // lane -> (row it*4 + lane/8, 4 columns (lane%8)*4) for bias / add loads and the C stores.
         const int q = warp & 3;
-        const int64_t m = m0 + q * 32 + lane;
         if (nkb > 0) {
             mbar_wait(acc_bar, 0);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
+        constexpr int PITCH = 36;                                  // floats; 16-byte aligned rows, conflict-free float4
+        float* stg = reinterpret_cast<float*>(smem) + q * (32 * PITCH);
         const bool first = blockIdx.z == 0;
-        const float* addrow = (g.add && first && m < g.M) ? g.add + (m % g.add_rows) * g.ldadd : nullptr;
+        const bool vec_ok = (g.N % 4 == 0) && (!g.add || (g.ldadd % 4 == 0));
+        const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
             uint32_t r[32];
@@ -168,50 +173,51 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
                 for (int j = 0; j < 32; ++j) r[j] = 0u;
             }
-            if (m >= g.M) continue;
             const int64_t n = n0 + c0;
-            if (n >= g.N) continue;
-            float v[32];
+            if (n >= g.N) continue;                                // warp-uniform
+            __syncwarp();
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-            const bool full = n + 32 <= g.N;
-            if (first && g.bias) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) if (full || n + j < g.N) v[j] += __ldg(g.bias + n + j);
-            }
-            if (addrow) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) if (full || n + j < g.N) v[j] += __ldg(addrow + n + j);
-            }
-            if (g.out_bf16) {
-                __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(g.C) + m * g.N + n;
-                if (full && (g.N % 8 == 0)) {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 8) {
-                        uint4 pk;
-                        __nv_bfloat162 t0 = __floats2bfloat162_rn(v[j], v[j + 1]), t1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
-                        __nv_bfloat162 t2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), t3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
-                        pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
-                        pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
-                        *reinterpret_cast<uint4*>(cp + j) = pk;
+            for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(stg + lane * PITCH + j) =
+                    make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+            __syncwarp();
+            const bool full = (n + 32 <= g.N) && vec_ok;
+#pragma unroll 1
+            for (int it = 0; it < 8; ++it) {
+                const int rr = it * 4 + sub_r;
+                const int64_t m = m0 + q * 32 + rr;
+                if (m >= g.M) continue;
+                float4 v = *reinterpret_cast<const float4*>(stg + rr * PITCH + sub_c);
+                const int64_t nc = n + sub_c;
+                if (full) {
+                    if (first && g.bias) {
+                        const float4 bv = __ldg(reinterpret_cast<const float4*>(g.bias + nc));
+                        v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
                     }
-                } else {
-                    for (int j = 0; j < 32; ++j) if (n + j < g.N) cp[j] = __float2bfloat16_rn(v[j]);
-                }
-            } else {
-                float* cp = reinterpret_cast<float*>(g.C) + m * g.N + n;
-                if (g.splits > 1 || g.accumulate) {
-                    if (full && (g.N % 4 == 0)) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4) atomicAdd(reinterpret_cast<float4*>(cp + j), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+                    if (first && g.add) {
+                        const float4 av = __ldg(reinterpret_cast<const float4*>(g.add + (m % g.add_rows) * g.ldadd + nc));
+                        v.x += av.x; v.y += av.y; v.z += av.z; v.w += av.w;
+                    }
+                    if (g.out_bf16) {
+                        __nv_bfloat162 t0 = __floats2bfloat162_rn(v.x, v.y), t1 = __floats2bfloat162_rn(v.z, v.w);
+                        uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
+                        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(g.C) + m * g.N + nc) = pk;
                     } else {
-                        for (int j = 0; j < 32; ++j) if (n + j < g.N) atomicAdd(cp + j, v[j]);
+                        float* cp = reinterpret_cast<float*>(g.C) + m * g.N + nc;
+                        if (g.splits > 1 || g.accumulate) atomicAdd(reinterpret_cast<float4*>(cp), v);
+                        else *reinterpret_cast<float4*>(cp) = v;
                     }
-                } else if (full && (g.N % 4 == 0)) {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(cp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
                 } else {
-                    for (int j = 0; j < 32; ++j) if (n + j < g.N) cp[j] = v[j];
+                    float vv[4] = {v.x, v.y, v.z, v.w};
+                    for (int j = 0; j < 4; ++j) {
+                        if (nc + j >= g.N) break;
+                        float x = vv[j];
+                        if (first && g.bias) x += __ldg(g.bias + nc + j);
+                        if (first && g.add) x += __ldg(g.add + (m % g.add_rows) * g.ldadd + nc + j);
+                        if (g.out_bf16) reinterpret_cast<__nv_bfloat16*>(g.C)[m * g.N + nc + j] = __float2bfloat16_rn(x);
+                        else if (g.splits > 1 || g.accumulate) atomicAdd(reinterpret_cast<float*>(g.C) + m * g.N + nc + j, x);
+                        else reinterpret_cast<float*>(g.C)[m * g.N + nc + j] = x;
+                    }
                 }
             }
         }

