@@ -181,10 +181,10 @@ int launch_gemm(GemmArgs& g, cudaStream_t st) {
     int splits = 1;
     const bool can_split = (g.act == GAOT_ACT_NONE) && !g.pre && (g.ldc == g.N);
     if (can_split && tiles < 148 && ktiles >= 16) {
-        splits = (int)((296 + tiles - 1) / tiles);
+        splits = (int)((148 * 4 + tiles - 1) / tiles);
         if (splits > ktiles / 8) splits = (int)(ktiles / 8);
         if (splits < 1) splits = 1;
-        if (splits > 64) splits = 64;
+        if (splits > 1024) splits = 1024;
     }
     g.splits = splits;
     if (splits > 1 && !g.accumulate) GAOT_CHECK(cudaMemsetAsync(g.C, 0, sizeof(float) * (size_t)(g.M * g.N), st));

@@ -81,8 +81,10 @@ def test_model_bf16_mode_close_to_reference(name):
     mine = torch.cat([p.grad.flatten().double().cpu() for _, p in model.named_parameters()])
     ref = torch.cat([torch.from_numpy(g["grad." + k]).flatten().double() for k, _ in model.named_parameters()])
     assert rel_l2(mine, ref) < 3e-2
+    gmax = max(float(torch.from_numpy(g["grad." + k]).norm()) for k, _ in model.named_parameters())
     for k, p in model.named_parameters():
-        assert rel_l2(p.grad, g["grad." + k]) < 0.15, k
+        if float(torch.from_numpy(g["grad." + k]).norm()) > 1e-3 * gmax:
+            assert rel_l2(p.grad, g["grad." + k]) < 0.1, k
 
 
 @pytest.mark.parametrize("B,T,H,Hkv,hd", [(2, 256, 2, 2, 32), (1, 1024, 8, 8, 32), (2, 200, 4, 2, 32), (1, 384, 2, 2, 64), (1, 130, 2, 1, 16)])
