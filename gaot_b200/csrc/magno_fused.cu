@@ -1,0 +1,439 @@
+// Algebraically fused MAGNO operators.  Both exploit that the layers around AGNO are affine
+// (ChannelMLP with n_layers=1, reference src/model/layers/magno.py:127-132, 457-462 and mlp.py:274-275):
+//
+// (1) lift + aggregate (encoder, magno.py:273-274 + agno.py:198,245-271):
+//       out[b,m,c] = sum_{e in m} w[e,c] * ( sum_i Wl[c,i] * pn[b, idx_e, i] + bl[c] )
+//     The lifted features f[B,N,C] (75 MB at cfg-2) are never written or gathered: the kernel gathers the
+//     Cin raw input channels (4..16 bytes per point, L2 resident) and applies the lifting on the fly.
+//     Backward: dw[e,c] = sum_b g[b,m,c] * f[b,idx_e,c] with f recomputed the same way;
+//               dWl[c,i] = sum_{b,m,e} g[b,m,c] w[e,c] pn[b,idx_e,i];  dbl[c] = sum_{b,m,e} g[b,m,c] w[e,c]
+//     (inputs carry no gradient, so no transposed graph is needed on the encoder side).
+//
+// (2) aggregate + recovery + projection (decoder, agno.py:198-271 + magno.py:684-688, 640-641):
+//       out[b,n,o] = sum_{e in n} < u[o,e,:], r[b, idx_e, :] >,    u[o,e,c] = (Wp Wa)[o,c] * w[e,c]
+//     (the batch-independent geometry/bias term is added by the caller).  The [B,N,C] decoder activations
+//     (75 MB) and the two 295k-row GEMMs disappear; the kernel gathers latent rows (1 MB per sample, L2
+//     resident) and writes Cout scalars per point.
+//     Backward: dr[b,j,c] = sum_{e: idx_e=j} sum_o u[o,e,c] g[b,row_e,o]   (transposed graph)
+//               du[o,e,c] = sum_b g[b,row_e,o] r[b,idx_e,c]
+#include "common.cuh"
+#include "../../include/gaot_b200.h"
+
+namespace {
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void fma4(float4& a, const float4& x, const float4& y) {
+    a.x = fmaf(x.x, y.x, a.x); a.y = fmaf(x.y, y.y, a.y); a.z = fmaf(x.z, y.z, a.z); a.w = fmaf(x.w, y.w, a.w);
+}
+__device__ __forceinline__ void fma4s(float4& a, const float4& x, float s) {
+    a.x = fmaf(x.x, s, a.x); a.y = fmaf(x.y, s, a.y); a.z = fmaf(x.z, s, a.z); a.w = fmaf(x.w, s, a.w);
+}
+__device__ __forceinline__ float dot4(const float4& x, const float4& y) {
+    return fmaf(x.x, y.x, fmaf(x.y, y.y, fmaf(x.z, y.z, x.w * y.w)));
+}
+
+constexpr int FB = 8;        // samples per work item
+
+// ---------------------------------------------------------------------------------------------
+// (1) forward.  G lanes x float4 = one channel row; item = (row, chunk of FB samples)
+// ---------------------------------------------------------------------------------------------
+template <int G, int CIN>
+__global__ void __launch_bounds__(256)
+lift_aggregate_fwd_kernel(const float* __restrict__ pn, const float* __restrict__ Wl, const float* __restrict__ bl,
+                          const float* __restrict__ w, const int64_t* __restrict__ index, const int64_t* __restrict__ rs,
+                          float* __restrict__ out, int B, int64_t Ns, int64_t Nd, int C, int64_t n_items) {
+    const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const int gl = threadIdx.x % G;
+    if (gid >= n_items) return;
+    const int64_t row = gid % Nd;
+    const int b0 = (int)(gid / Nd) * FB;
+    const int nvec = C >> 2;
+    const int c0 = min(gl, nvec - 1) * 4;
+    float4 wl[CIN];                                   // Wl[c0..c0+3, i]
+#pragma unroll
+    for (int i = 0; i < CIN; ++i)
+        wl[i] = make_float4(__ldg(Wl + (c0 + 0) * CIN + i), __ldg(Wl + (c0 + 1) * CIN + i), __ldg(Wl + (c0 + 2) * CIN + i),
+                            __ldg(Wl + (c0 + 3) * CIN + i));
+    const float4 blv = ldg4(bl + c0);
+    int64_t boff[FB];
+#pragma unroll
+    for (int bb = 0; bb < FB; ++bb) boff[bb] = (int64_t)min(b0 + bb, B - 1) * Ns * CIN;
+    // s[bb][i] = sum_e w[e,c] pn[b,j,i] (per lane: 4 channels), sw = sum_e w[e,c]
+    float4 s[FB][CIN];
+    float4 sw = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int bb = 0; bb < FB; ++bb)
+#pragma unroll
+        for (int i = 0; i < CIN; ++i) s[bb][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int64_t a = __ldg(rs + row), e = __ldg(rs + row + 1);
+    if (a < e) {
+        int64_t j = __ldg(index + a);
+        for (int64_t it = a; it < e; ++it) {
+            const int64_t jn = __ldg(index + ((it + 1 < e) ? it + 1 : it));
+            const float4 wv = ldg4(w + it * C + c0);
+            float p[FB][CIN];
+#pragma unroll
+            for (int bb = 0; bb < FB; ++bb)
+#pragma unroll
+                for (int i = 0; i < CIN; ++i) p[bb][i] = __ldg(pn + boff[bb] + j * CIN + i);
+            sw.x += wv.x; sw.y += wv.y; sw.z += wv.z; sw.w += wv.w;
+#pragma unroll
+            for (int bb = 0; bb < FB; ++bb)
+#pragma unroll
+                for (int i = 0; i < CIN; ++i) fma4s(s[bb][i], wv, p[bb][i]);
+            j = jn;
+        }
+    }
+    if (gl < nvec) {
+#pragma unroll
+        for (int bb = 0; bb < FB; ++bb) {
+            if (b0 + bb < B) {
+                float4 o = make_float4(blv.x * sw.x, blv.y * sw.y, blv.z * sw.z, blv.w * sw.w);
+#pragma unroll
+                for (int i = 0; i < CIN; ++i) fma4(o, wl[i], s[bb][i]);
+                *reinterpret_cast<float4*>(out + ((int64_t)(b0 + bb) * Nd + row) * C + c0) = o;
+            }
+        }
+    }
+}
+
+// (1) backward: dw (atomics over the sample chunks), dWl / dbl (CTA partial sums -> atomics)
+template <int G, int CIN>
+__global__ void __launch_bounds__(256)
+lift_aggregate_bwd_kernel(const float* __restrict__ g, const float* __restrict__ pn, const float* __restrict__ Wl,
+                          const float* __restrict__ bl, const float* __restrict__ w, const int64_t* __restrict__ index,
+                          const int64_t* __restrict__ rs, float* __restrict__ dw, float* __restrict__ dWl,
+                          float* __restrict__ dbl, int B, int64_t Ns, int64_t Nd, int C, int64_t n_items, int chunks) {
+    extern __shared__ float sred[];                   // [C * (CIN + 1)] CTA partial of dWl | dbl
+    for (int t = threadIdx.x; t < C * (CIN + 1); t += blockDim.x) sred[t] = 0.f;
+    __syncthreads();
+    const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const int gl = threadIdx.x % G;
+    const int nvec = C >> 2;
+    const int c0 = min(gl, nvec - 1) * 4;
+    float4 dl[CIN];
+    float4 db = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < CIN; ++i) dl[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (gid < n_items) {
+        const int64_t row = gid % Nd;
+        const int b0 = (int)(gid / Nd) * FB;
+        float4 wl[CIN];
+#pragma unroll
+        for (int i = 0; i < CIN; ++i)
+            wl[i] = make_float4(__ldg(Wl + (c0 + 0) * CIN + i), __ldg(Wl + (c0 + 1) * CIN + i), __ldg(Wl + (c0 + 2) * CIN + i),
+                                __ldg(Wl + (c0 + 3) * CIN + i));
+        const float4 blv = ldg4(bl + c0);
+        float4 gv[FB];
+        int64_t boff[FB];
+#pragma unroll
+        for (int bb = 0; bb < FB; ++bb) {
+            const bool ok = b0 + bb < B;
+            boff[bb] = (int64_t)min(b0 + bb, B - 1) * Ns * CIN;
+            gv[bb] = ok ? ldg4(g + ((int64_t)(b0 + bb) * Nd + row) * C + c0) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        const int64_t a = __ldg(rs + row), e = __ldg(rs + row + 1);
+        if (a < e) {
+            int64_t j = __ldg(index + a);
+            for (int64_t it = a; it < e; ++it) {
+                const int64_t jn = __ldg(index + ((it + 1 < e) ? it + 1 : it));
+                const float4 wv = ldg4(w + it * C + c0);
+                float p[FB][CIN];
+#pragma unroll
+                for (int bb = 0; bb < FB; ++bb)
+#pragma unroll
+                    for (int i = 0; i < CIN; ++i) p[bb][i] = __ldg(pn + boff[bb] + j * CIN + i);
+                float4 dwe = make_float4(0.f, 0.f, 0.f, 0.f);        // sum_b g * f
+                float4 gsum = make_float4(0.f, 0.f, 0.f, 0.f);       // sum_b g
+                float4 gp[CIN];                                       // sum_b g * pn_i
+#pragma unroll
+                for (int i = 0; i < CIN; ++i) gp[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int bb = 0; bb < FB; ++bb) {
+                    gsum.x += gv[bb].x; gsum.y += gv[bb].y; gsum.z += gv[bb].z; gsum.w += gv[bb].w;
+#pragma unroll
+                    for (int i = 0; i < CIN; ++i) fma4s(gp[i], gv[bb], p[bb][i]);
+                }
+                // f = Wl pn + bl  ->  sum_b g f = sum_i Wl_i * gp_i + bl * gsum
+                dwe = make_float4(blv.x * gsum.x, blv.y * gsum.y, blv.z * gsum.z, blv.w * gsum.w);
+#pragma unroll
+                for (int i = 0; i < CIN; ++i) {
+                    fma4(dwe, wl[i], gp[i]);
+                    fma4(dl[i], wv, gp[i]);                            // dWl += w * (sum_b g pn_i)
+                }
+                fma4(db, wv, gsum);                                    // dbl += w * sum_b g
+                if (gl < nvec) {
+                    float4* dst = reinterpret_cast<float4*>(dw + it * C + c0);
+                    if (chunks > 1) atomicAdd(dst, dwe); else *dst = dwe;
+                }
+                j = jn;
+            }
+        }
+    }
+    if (gl < nvec) {
+#pragma unroll
+        for (int i = 0; i < CIN; ++i) {
+            atomicAdd(&sred[(c0 + 0) * (CIN + 1) + i], dl[i].x); atomicAdd(&sred[(c0 + 1) * (CIN + 1) + i], dl[i].y);
+            atomicAdd(&sred[(c0 + 2) * (CIN + 1) + i], dl[i].z); atomicAdd(&sred[(c0 + 3) * (CIN + 1) + i], dl[i].w);
+        }
+        atomicAdd(&sred[(c0 + 0) * (CIN + 1) + CIN], db.x); atomicAdd(&sred[(c0 + 1) * (CIN + 1) + CIN], db.y);
+        atomicAdd(&sred[(c0 + 2) * (CIN + 1) + CIN], db.z); atomicAdd(&sred[(c0 + 3) * (CIN + 1) + CIN], db.w);
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < C * (CIN + 1); t += blockDim.x) {
+        const int c = t / (CIN + 1), i = t % (CIN + 1);
+        const float v = sred[t];
+        if (v != 0.f) {
+            if (i < CIN) atomicAdd(dWl + c * CIN + i, v); else atomicAdd(dbl + c, v);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// (2) forward: out[b,n,o] = sum_e <u[o,e,:], r[b,idx_e,:]>
+// ---------------------------------------------------------------------------------------------
+template <int G, int COUT>
+__global__ void __launch_bounds__(256)
+agno_dot_fwd_kernel(const float* __restrict__ r, const float* __restrict__ u, const int64_t* __restrict__ index,
+                    const int64_t* __restrict__ rs, float* __restrict__ out, int B, int64_t Ns, int64_t Nd, int64_t E,
+                    int C, int64_t n_items) {
+    const int64_t gid_raw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const int gl = threadIdx.x % G;
+    const bool valid = gid_raw < n_items;             // no early exit: the group shuffles below need full warps
+    const int64_t gid = valid ? gid_raw : n_items - 1;
+    const int64_t row = gid % Nd;
+    const int b0 = (int)(gid / Nd) * FB;
+    const int nvec = C >> 2;
+    const bool act = gl < nvec;
+    const int c0 = min(gl, nvec - 1) * 4;
+    int64_t boff[FB];
+#pragma unroll
+    for (int bb = 0; bb < FB; ++bb) boff[bb] = (int64_t)min(b0 + bb, B - 1) * Ns * C;
+    float acc[FB][COUT];
+#pragma unroll
+    for (int bb = 0; bb < FB; ++bb)
+#pragma unroll
+        for (int o = 0; o < COUT; ++o) acc[bb][o] = 0.f;
+    const int64_t a = __ldg(rs + row), e = __ldg(rs + row + 1);
+    if (a < e) {
+        int64_t j = __ldg(index + a);
+        for (int64_t it = a; it < e; ++it) {
+            const int64_t jn = __ldg(index + ((it + 1 < e) ? it + 1 : it));
+            float4 uv[COUT], rv[FB];
+#pragma unroll
+            for (int o = 0; o < COUT; ++o) uv[o] = ldg4(u + ((int64_t)o * E + it) * C + c0);
+#pragma unroll
+            for (int bb = 0; bb < FB; ++bb) rv[bb] = ldg4(r + boff[bb] + j * C + c0);
+            if (act) {
+#pragma unroll
+                for (int bb = 0; bb < FB; ++bb)
+#pragma unroll
+                    for (int o = 0; o < COUT; ++o) acc[bb][o] += dot4(uv[o], rv[bb]);
+            }
+            j = jn;
+        }
+    }
+    // reduce the per-lane partial dot products over the G lanes of the group
+#pragma unroll
+    for (int bb = 0; bb < FB; ++bb)
+#pragma unroll
+        for (int o = 0; o < COUT; ++o) {
+            float v = acc[bb][o];
+#pragma unroll
+            for (int off = G / 2; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off, G);
+            acc[bb][o] = v;
+        }
+    if (gl == 0 && valid) {
+#pragma unroll
+        for (int bb = 0; bb < FB; ++bb)
+            if (b0 + bb < B)
+#pragma unroll
+                for (int o = 0; o < COUT; ++o) out[((int64_t)(b0 + bb) * Nd + row) * COUT + o] = acc[bb][o];
+    }
+}
+
+// (2) dr on the transposed graph: dr[b,j,c] = sum_{k in T(j)} sum_o u[o, perm_k, c] * g[b, trow_k, o]
+template <int G, int COUT>
+__global__ void __launch_bounds__(256)
+agno_dot_bwd_r_kernel(const float* __restrict__ g, const float* __restrict__ u, const int64_t* __restrict__ t_rows,
+                      const int64_t* __restrict__ t_perm, const int64_t* __restrict__ ts, float* __restrict__ dr, int B,
+                      int64_t Ns, int64_t Nd, int64_t E, int C, int64_t n_items) {
+    const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const int gl = threadIdx.x % G;
+    if (gid >= n_items) return;
+    const int64_t src = gid % Ns;
+    const int b0 = (int)(gid / Ns) * FB;
+    const int nvec = C >> 2;
+    const int c0 = min(gl, nvec - 1) * 4;
+    float4 acc[FB];
+#pragma unroll
+    for (int bb = 0; bb < FB; ++bb) acc[bb] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int64_t a = __ldg(ts + src), e = __ldg(ts + src + 1);
+    for (int64_t k = a; k < e; ++k) {
+        const int64_t row = __ldg(t_rows + k), pe = __ldg(t_perm + k);
+        float4 uv[COUT];
+#pragma unroll
+        for (int o = 0; o < COUT; ++o) uv[o] = ldg4(u + ((int64_t)o * E + pe) * C + c0);
+#pragma unroll
+        for (int bb = 0; bb < FB; ++bb) {
+            const int64_t gb = ((int64_t)min(b0 + bb, B - 1) * Nd + row) * COUT;
+#pragma unroll
+            for (int o = 0; o < COUT; ++o) fma4s(acc[bb], uv[o], __ldg(g + gb + o));
+        }
+    }
+    if (gl < nvec) {
+#pragma unroll
+        for (int bb = 0; bb < FB; ++bb)
+            if (b0 + bb < B) *reinterpret_cast<float4*>(dr + ((int64_t)(b0 + bb) * Ns + src) * C + c0) = acc[bb];
+    }
+}
+
+// (2) du[o,e,c] = sum_b g[b,row_e,o] r[b,idx_e,c]; group owns a destination row and a slice of the batch
+template <int G, int COUT>
+__global__ void __launch_bounds__(256)
+agno_dot_bwd_u_kernel(const float* __restrict__ g, const float* __restrict__ r, const int64_t* __restrict__ index,
+                      const int64_t* __restrict__ rs, float* __restrict__ du, int B, int64_t Ns, int64_t Nd, int64_t E, int C,
+                      int bsplit, int64_t n_items) {
+    const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const int gl = threadIdx.x % G;
+    if (gid >= n_items) return;
+    const int64_t row = gid % Nd;
+    const int slice = (int)(gid / Nd);
+    const int per = (B + bsplit - 1) / bsplit;
+    const int b_lo = slice * per, b_hi = min(B, b_lo + per);
+    const int nvec = C >> 2;
+    const int c0 = min(gl, nvec - 1) * 4;
+    const int64_t a = __ldg(rs + row), e = __ldg(rs + row + 1);
+    for (int64_t it = a; it < e; ++it) {
+        const int64_t j = __ldg(index + it);
+        float4 acc[COUT];
+#pragma unroll
+        for (int o = 0; o < COUT; ++o) acc[o] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int b = b_lo; b < b_hi; b += 4) {
+            float4 rv[4];
+            float gs[4][COUT];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int bq = min(b + q, b_hi - 1);
+                rv[q] = ldg4(r + ((int64_t)bq * Ns + j) * C + c0);
+#pragma unroll
+                for (int o = 0; o < COUT; ++o) gs[q][o] = (b + q < b_hi) ? __ldg(g + ((int64_t)bq * Nd + row) * COUT + o) : 0.f;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int o = 0; o < COUT; ++o) fma4s(acc[o], rv[q], gs[q][o]);
+        }
+        if (gl < nvec) {
+#pragma unroll
+            for (int o = 0; o < COUT; ++o) {
+                float4* dst = reinterpret_cast<float4*>(du + ((int64_t)o * E + it) * C + c0);
+                if (bsplit > 1) atomicAdd(dst, acc[o]); else *dst = acc[o];
+            }
+        }
+    }
+}
+
+inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+inline int group_of(int64_t C) { const int nv = (int)(C / 4); return nv <= 4 ? 4 : (nv <= 8 ? 8 : (nv <= 16 ? 16 : 32)); }
+
+#define GAOT_DISPATCH_G(G_, ...)  \
+    switch (G_) { case 4: { constexpr int G = 4; __VA_ARGS__; break; } case 8: { constexpr int G = 8; __VA_ARGS__; break; } \
+                  case 16: { constexpr int G = 16; __VA_ARGS__; break; } default: { constexpr int G = 32; __VA_ARGS__; break; } }
+#define GAOT_DISPATCH_N(N_, NAME, ...)  \
+    switch (N_) { case 1: { constexpr int NAME = 1; __VA_ARGS__; break; } case 2: { constexpr int NAME = 2; __VA_ARGS__; break; } \
+                  case 3: { constexpr int NAME = 3; __VA_ARGS__; break; } case 4: { constexpr int NAME = 4; __VA_ARGS__; break; } \
+                  default: return GAOT_E_BADARG; }
+
+}  // namespace
+
+GAOT_API int gaot_lift_aggregate_fwd(const float* pn, const float* Wl, const float* bl, const float* w, const int64_t* index,
+                                     const int64_t* row_splits, float* out, int64_t B, int64_t Ns, int64_t Nd, int64_t C,
+                                     int64_t Cin, void* stream) {
+    if (!pn || !Wl || !bl || !w || !index || !row_splits || !out || B < 1 || Ns < 0 || Nd < 0) return GAOT_E_BADARG;
+    if (C % 4 || C > 128 || Cin < 1 || Cin > 4) return GAOT_E_BADARG;
+    if (!al16(w) || !al16(out) || !al16(bl)) return GAOT_E_ALIGN;
+    if (Nd == 0) return 0;
+    const int g_ = group_of(C);
+    const int64_t n_items = Nd * ((B + FB - 1) / FB);
+    const int64_t blocks = (n_items * g_ + 255) / 256;
+    if (blocks > 0x7fffffffLL) return GAOT_E_BADARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    GAOT_DISPATCH_G(g_, GAOT_DISPATCH_N((int)Cin, CIN, (lift_aggregate_fwd_kernel<G, CIN><<<(unsigned)blocks, 256, 0, st>>>(
+                                                          pn, Wl, bl, w, index, row_splits, out, (int)B, Ns, Nd, (int)C, n_items))));
+    GAOT_RETURN_LAST();
+}
+
+GAOT_API int gaot_lift_aggregate_bwd(const float* g, const float* pn, const float* Wl, const float* bl, const float* w,
+                                     const int64_t* index, const int64_t* row_splits, float* dw, float* dWl, float* dbl,
+                                     int64_t B, int64_t Ns, int64_t Nd, int64_t E, int64_t C, int64_t Cin, void* stream) {
+    if (!g || !pn || !Wl || !bl || !w || !index || !row_splits || !dw || !dWl || !dbl || B < 1 || E < 0) return GAOT_E_BADARG;
+    if (C % 4 || C > 128 || Cin < 1 || Cin > 4) return GAOT_E_BADARG;
+    if (!al16(w) || !al16(g) || !al16(dw) || !al16(bl)) return GAOT_E_ALIGN;
+    cudaStream_t st = (cudaStream_t)stream;
+    GAOT_CHECK(cudaMemsetAsync(dWl, 0, sizeof(float) * (size_t)(C * Cin), st));
+    GAOT_CHECK(cudaMemsetAsync(dbl, 0, sizeof(float) * (size_t)C, st));
+    if (Nd == 0 || E == 0) return 0;
+    const int chunks = (int)((B + FB - 1) / FB);
+    if (chunks > 1) GAOT_CHECK(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)(E * C), st));
+    const int g_ = group_of(C);
+    const int64_t n_items = Nd * chunks;
+    const int64_t blocks = (n_items * g_ + 255) / 256;
+    if (blocks > 0x7fffffffLL) return GAOT_E_BADARG;
+    const size_t smem = sizeof(float) * (size_t)(C * (Cin + 1));
+    GAOT_DISPATCH_G(g_, GAOT_DISPATCH_N((int)Cin, CIN, (lift_aggregate_bwd_kernel<G, CIN><<<(unsigned)blocks, 256, smem, st>>>(
+                                                          g, pn, Wl, bl, w, index, row_splits, dw, dWl, dbl, (int)B, Ns, Nd, (int)C,
+                                                          n_items, chunks))));
+    GAOT_RETURN_LAST();
+}
+
+GAOT_API int gaot_agno_dot_fwd(const float* r, const float* u, const int64_t* index, const int64_t* row_splits, float* out,
+                               int64_t B, int64_t Ns, int64_t Nd, int64_t E, int64_t C, int64_t Cout, void* stream) {
+    if (!r || !u || !index || !row_splits || !out || B < 1 || Ns < 0 || Nd < 0 || E < 0) return GAOT_E_BADARG;
+    if (C % 4 || C > 128 || Cout < 1 || Cout > 4) return GAOT_E_BADARG;
+    if (!al16(r) || !al16(u)) return GAOT_E_ALIGN;
+    if (Nd == 0) return 0;
+    const int g_ = group_of(C);
+    const int64_t n_items = Nd * ((B + FB - 1) / FB);
+    const int64_t blocks = (n_items * g_ + 255) / 256;
+    if (blocks > 0x7fffffffLL) return GAOT_E_BADARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    GAOT_DISPATCH_G(g_, GAOT_DISPATCH_N((int)Cout, COUT, (agno_dot_fwd_kernel<G, COUT><<<(unsigned)blocks, 256, 0, st>>>(
+                                                            r, u, index, row_splits, out, (int)B, Ns, Nd, E, (int)C, n_items))));
+    GAOT_RETURN_LAST();
+}
+
+GAOT_API int gaot_agno_dot_bwd(const float* g, const float* r, const float* u, const int64_t* index, const int64_t* row_splits,
+                               const int64_t* t_splits, const int64_t* t_rows, const int64_t* t_perm, float* dr, float* du,
+                               int64_t B, int64_t Ns, int64_t Nd, int64_t E, int64_t C, int64_t Cout, void* stream) {
+    if (!g || !r || !u || !index || !row_splits || B < 1 || Ns < 0 || Nd < 0 || E < 0) return GAOT_E_BADARG;
+    if (dr && (!t_splits || !t_rows || !t_perm)) return GAOT_E_BADARG;
+    if (C % 4 || C > 128 || Cout < 1 || Cout > 4) return GAOT_E_BADARG;
+    if (!al16(r) || !al16(u) || (dr && !al16(dr)) || (du && !al16(du))) return GAOT_E_ALIGN;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int g_ = group_of(C);
+    int launches = 0;
+    if (dr && Ns > 0) {
+        const int64_t n_items = Ns * ((B + FB - 1) / FB);
+        const int64_t blocks = (n_items * g_ + 255) / 256;
+        if (blocks > 0x7fffffffLL) return GAOT_E_BADARG;
+        GAOT_DISPATCH_G(g_, GAOT_DISPATCH_N((int)Cout, COUT, (agno_dot_bwd_r_kernel<G, COUT><<<(unsigned)blocks, 256, 0, st>>>(
+                                                                g, u, t_rows, t_perm, t_splits, dr, (int)B, Ns, Nd, E, (int)C, n_items))));
+        ++launches;
+    }
+    if (du && Nd > 0 && E > 0) {
+        int bsplit = 1;
+        while (bsplit < B && Nd * g_ * bsplit < 148LL * 2048 && bsplit < 8) bsplit <<= 1;
+        if (bsplit > B) bsplit = (int)B;
+        if (bsplit > 1) GAOT_CHECK(cudaMemsetAsync(du, 0, sizeof(float) * (size_t)(Cout * E * C), st));
+        const int64_t n_items = Nd * bsplit;
+        const int64_t blocks = (n_items * g_ + 255) / 256;
+        if (blocks > 0x7fffffffLL) return GAOT_E_BADARG;
+        GAOT_DISPATCH_G(g_, GAOT_DISPATCH_N((int)Cout, COUT, (agno_dot_bwd_u_kernel<G, COUT><<<(unsigned)blocks, 256, 0, st>>>(
+                                                                g, r, index, row_splits, du, (int)B, Ns, Nd, E, (int)C, bsplit, n_items))));
+        ++launches;
+    }
+    if (launches == 0) return 0;
+    if (launches == 2) GAOT_NOTE_LAUNCHES(1);
+    GAOT_RETURN_LAST();
+}

@@ -69,6 +69,7 @@ class _MAGNOBase(nn.Module):
         self.nb_search = NeighborSearch(method=config.neighbor_search_method)
         self.neighbor_cache = {}
         self._merged_cache = {}
+        self.fuse_affine = True          # fold the affine lifting / recovery+projection into the graph kernels
         self.sampling_strategy = config.sampling_strategy
         self.max_neighbors = config.max_neighbors
         self.sample_ratio = config.sample_ratio
@@ -122,12 +123,19 @@ class _MAGNOBase(nn.Module):
         return hit[0]
 
     # ---- one scale --------------------------------------------------------------------------------
-    def _one_scale(self, plan, src_coord, dst_coord, feats, groups: int):
-        """AGNO + geo-embedding + recovery on one graph (magno.py:322-350 / 660-688).
-        src/dst coords are [n_src,d] / [m,d] matching the plan; feats [Bf, n_src, C]."""
+    def _edge_weights(self, plan, src_coord, dst_coord):
         ys, xs = (node_pos_encode(src_coord), node_pos_encode(dst_coord)) if self.node_embedding else (src_coord, dst_coord)
-        w = self.agno.edge_weights(ys, xs, plan)
-        out = ops.agno_aggregate(feats, w, plan)                         # [Bf, m, C]
+        return self.agno.edge_weights(ys, xs, plan)
+
+    def _one_scale(self, plan, src_coord, dst_coord, feats, groups: int, lift=None):
+        """AGNO + geo-embedding + recovery on one graph (magno.py:322-350 / 660-688).
+        src/dst coords are [n_src,d] / [m,d] matching the plan; feats [Bf, n_src, C] - or, with
+        lift=(Wl, bl), the raw inputs [Bf, n_src, Cin] whose affine lifting is fused into the gather."""
+        w = self._edge_weights(plan, src_coord, dst_coord)
+        if lift is not None:
+            out = ops.lift_aggregate(feats, lift[0], lift[1], w, plan)   # [Bf, m, C], lifted features never materialised
+        else:
+            out = ops.agno_aggregate(feats, w, plan)                     # [Bf, m, C]
         if self.use_geoembed:
             C = out.shape[-1]
             feat = self.geoembed.features(src_coord, dst_coord, plan, groups, cache=(groups == 1))
@@ -181,18 +189,22 @@ class MAGNOEncoder(_MAGNOBase):
             encoder_nbrs = self._search(x_coord, latent_tokens_coord)
         B, N = pndata.shape[0], pndata.shape[1]
         M = latent_tokens_coord.shape[0]
-        f = self.lifting(pndata)                                          # [B,N,C]  (magno.py:273-274)
-        C = f.shape[-1]
+        Wl, bl = self.lifting.fcs[0].weight[:, :, 0], self.lifting.fcs[0].bias
+        C, Cin = Wl.shape
+        fuse = self.fuse_affine and Cin <= ops.FUSE_MAX_CIN and C % 4 == 0 and C <= ops.FUSE_MAX_C
+        lift = (Wl, bl) if fuse else None
+        f = pndata if fuse else self.lifting(pndata)                      # [B,N,C]  (magno.py:273-274)
+        Cf = f.shape[-1]
         outs = []
         for s in range(len(self.scales)):
             if not vx:
                 nb = self._drop(encoder_nbrs[s])
                 plan = ops.graph_plan(nb, N)
-                outs.append(self._one_scale(plan, x_coord, latent_tokens_coord, f, 1))
+                outs.append(self._one_scale(plan, x_coord, latent_tokens_coord, f, 1, lift))
             else:
                 plan = self._merged_plan([self._drop(encoder_nbrs[b][s]) for b in range(B)], N)
                 o = self._one_scale(plan, x_coord.reshape(B * N, -1), latent_tokens_coord.repeat(B, 1),
-                                    f.view(1, B * N, C), B)
+                                    f.reshape(1, B * N, Cf), B, lift)
                 outs.append(o.view(B, M, C))
         return self._combine(outs, latent_tokens_coord)
 
@@ -222,6 +234,10 @@ class MAGNODecoder(_MAGNOBase):
             decoder_nbrs = self._search(latent_tokens_coord, query_coord)
         B, M, C = rndata.shape
         Nq = query_coord.shape[-2]
+        Wp, bp = self.projection.fcs[0].weight[:, :, 0], self.projection.fcs[0].bias
+        if (self.fuse_affine and len(self.scales) == 1 and Wp.shape[0] <= ops.FUSE_MAX_COUT and C % 4 == 0
+                and C <= ops.FUSE_MAX_C):
+            return self._forward_fused(latent_tokens_coord, rndata, query_coord, decoder_nbrs, vx, Wp, bp)
         outs = []
         for s in range(len(self.scales)):
             if not vx:
@@ -235,3 +251,31 @@ class MAGNODecoder(_MAGNOBase):
                 outs.append(o.view(B, Nq, C))
         dec = self._combine(outs, query_coord if not vx else query_coord[0])
         return self.projection(dec)                                       # [B,Nq,Cout]  (magno.py:640-641)
+
+    def _forward_fused(self, latent, rndata, query_coord, decoder_nbrs, vx, Wp, bp):
+        """Single-scale decoder with recovery and projection (both affine, no activation between them:
+        magno.py:684-688, 640-641) folded into the aggregate:
+            out[b,n,:] = (Wp Wa) A[b,n,:] + Wp (Wg G[n,:] + b_rec) + bp,   A = AGNO output
+        so the kernel reduces <u[o,e,:], r[b,j,:]> with u = (Wp Wa)[o,:] * w[e,:] and writes Cout scalars per
+        point; the [B,N,C] decoder activations are never formed."""
+        B, M, C = rndata.shape
+        Nq = query_coord.shape[-2]
+        if not vx:
+            plan = ops.graph_plan(self._drop(decoder_nbrs[0]), M)
+            src, dst, feats, groups = latent, query_coord, rndata, 1
+        else:
+            plan = self._merged_plan([self._drop(decoder_nbrs[b][0]) for b in range(B)], M)
+            src, dst, feats, groups = latent.repeat(B, 1), query_coord.reshape(B * Nq, -1), rndata.reshape(1, B * M, C), B
+        w = self._edge_weights(plan, src, dst)                            # [E, C]
+        if self.use_geoembed:
+            Wrec = self.recovery.fcs[0].weight[:, :, 0]                   # [C, 2C]
+            feat = self.geoembed.features(src, dst, plan, groups, cache=(groups == 1))
+            g = self.geoembed.embed(feat)                                 # [rows, C]
+            gterm = ops.linear(g, Wrec[:, C:], self.recovery.fcs[0].bias)
+            const = ops.linear(gterm, Wp, bp)                             # [rows, Cout]
+            Wfold = ops.linear(Wp, Wrec[:, :C].t())                       # Wp @ Wa   [Cout, C]
+        else:
+            const, Wfold = bp.view(1, -1), Wp
+        u = Wfold.unsqueeze(1) * w.unsqueeze(0)                           # [Cout, E, C]
+        out = ops.agno_dot(feats, u, plan)                                # [Bf, rows, Cout]
+        return (out + const.unsqueeze(0)).view(B, Nq, -1)

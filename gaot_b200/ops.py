@@ -505,6 +505,78 @@ def agno_aggregate(f, w, plan):
     return _Aggregate.apply(f, w, plan)
 
 
+FUSE_MAX_CIN, FUSE_MAX_COUT, FUSE_MAX_C = 4, 4, 128
+
+
+class _LiftAggregate(torch.autograd.Function):
+    """out[b,r,:] = sum_{e in r} w[e,:] * (Wl pn[b,index[e],:] + bl): lifting fused into the gather."""
+
+    @staticmethod
+    def forward(ctx, pn, Wl, bl, w, plan):
+        pn, Wl, bl, w = _c(pn), _c(Wl), _c(bl), _c(w)
+        B, Ns, Cin = pn.shape
+        C = Wl.shape[0]
+        if Ns != plan.n_src or w.shape[0] != plan.E or w.shape[1] != C:
+            raise ValueError(f"lift_aggregate: pn {tuple(pn.shape)} / w {tuple(w.shape)} do not match graph")
+        out = torch.empty((B, plan.m, C), dtype=torch.float32, device=pn.device)
+        call("gaot_lift_aggregate_fwd", ptr(pn), ptr(Wl), ptr(bl), ptr(w), ptr(plan.index), ptr(plan.splits), ptr(out), B, Ns,
+             plan.m, C, Cin)
+        ctx.save_for_backward(pn, Wl, bl, w)
+        ctx.plan = plan
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        pn, Wl, bl, w = ctx.saved_tensors
+        plan = ctx.plan
+        g = _c(g)
+        B, Ns, Cin = pn.shape
+        C = Wl.shape[0]
+        dw, dWl, dbl = torch.empty_like(w), torch.empty_like(Wl), torch.empty_like(bl)
+        call("gaot_lift_aggregate_bwd", ptr(g), ptr(pn), ptr(Wl), ptr(bl), ptr(w), ptr(plan.index), ptr(plan.splits), ptr(dw),
+             ptr(dWl), ptr(dbl), B, Ns, plan.m, plan.E, C, Cin)
+        return None, dWl, dbl, dw, None
+
+
+def lift_aggregate(pn, Wl, bl, w, plan):
+    return _LiftAggregate.apply(pn, Wl, bl, w, plan)
+
+
+class _AgnoDot(torch.autograd.Function):
+    """out[b,r,o] = sum_{e in r} <u[o,e,:], f[b,index[e],:]>: aggregate fused with an affine read-out."""
+
+    @staticmethod
+    def forward(ctx, f, u, plan):
+        f, u = _c(f), _c(u)
+        B, Ns, C = f.shape
+        Cout = u.shape[0]
+        if Ns != plan.n_src or u.shape[1] != plan.E or u.shape[2] != C:
+            raise ValueError(f"agno_dot: f {tuple(f.shape)} / u {tuple(u.shape)} do not match graph")
+        out = torch.empty((B, plan.m, Cout), dtype=torch.float32, device=f.device)
+        call("gaot_agno_dot_fwd", ptr(f), ptr(u), ptr(plan.index), ptr(plan.splits), ptr(out), B, Ns, plan.m, plan.E, C, Cout)
+        ctx.save_for_backward(f, u)
+        ctx.plan = plan
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        f, u = ctx.saved_tensors
+        plan = ctx.plan
+        g = _c(g)
+        B, Ns, C = f.shape
+        Cout = u.shape[0]
+        df = torch.empty_like(f) if ctx.needs_input_grad[0] else None
+        du = torch.empty_like(u) if ctx.needs_input_grad[1] else None
+        ts, tr, tp = plan.transposed() if df is not None else (None, None, None)
+        call("gaot_agno_dot_bwd", ptr(g), ptr(f), ptr(u), ptr(plan.index), ptr(plan.splits), ptr(ts), ptr(tr), ptr(tp), ptr(df),
+             ptr(du), B, Ns, plan.m, plan.E, C, Cout)
+        return df, du, None
+
+
+def agno_dot(f, u, plan):
+    return _AgnoDot.apply(f, u, plan)
+
+
 def segment_csr(src: torch.Tensor, indptr: torch.Tensor, reduce: str = "sum", use_scatter: bool = True) -> torch.Tensor:
     """Drop-in for reference segment_csr (src/model/layers/utils/segment_csr.py:14-19), forward only:
     src [E,C] / [B,E,C] / [E], indptr [m+1] (or [B,m+1] repeated rows, as agno.py:266-269 builds it)."""

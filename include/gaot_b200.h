@@ -97,6 +97,29 @@ int gaot_agno_weight_grad(const float* g, const float* f, const int64_t* index,
                           const int64_t* row_splits, float* dw,
                           int64_t B, int64_t Ns, int64_t Nd, int64_t E, int64_t C, void* stream);
 
+/* Fused lifting + aggregate (encoder): out[b,r,c] = sum_{e in r} w[e,c] * (sum_i Wl[c,i] pn[b,index[e],i] + bl[c]).
+ * Replaces ChannelMLP lifting (magno.py:273-274, mlp.py:274-275: a single affine map) followed by the
+ * gather/multiply/segment_csr chain of agno.py:198,245-271 without materialising the lifted features.
+ * pn [B,Ns,Cin], Wl [C,Cin], bl [C], w [E,C]; Cin <= 4, C % 4 == 0, C <= 128. */
+int gaot_lift_aggregate_fwd(const float* pn, const float* Wl, const float* bl, const float* w, const int64_t* index,
+                            const int64_t* row_splits, float* out, int64_t B, int64_t Ns, int64_t Nd, int64_t C,
+                            int64_t Cin, void* stream);
+/* its backward: dw [E,C], dWl [C,Cin], dbl [C] (all overwritten); pn carries no gradient. */
+int gaot_lift_aggregate_bwd(const float* g, const float* pn, const float* Wl, const float* bl, const float* w,
+                            const int64_t* index, const int64_t* row_splits, float* dw, float* dWl, float* dbl,
+                            int64_t B, int64_t Ns, int64_t Nd, int64_t E, int64_t C, int64_t Cin, void* stream);
+
+/* Fused aggregate + affine read-out (decoder): out[b,r,o] = sum_{e in r} <u[o,e,:], f[b,index[e],:]>, with
+ * u[o,e,c] = (W_proj W_rec_a)[o,c] * w[e,c] folded by the caller.  Replaces agno.py:198-271 followed by the
+ * recovery and projection 1x1 convolutions (magno.py:684-688, 640-641), both affine.  f [B,Ns,C],
+ * u [Cout,E,C], out [B,Nd,Cout]; Cout <= 4, C % 4 == 0, C <= 128. */
+int gaot_agno_dot_fwd(const float* f, const float* u, const int64_t* index, const int64_t* row_splits, float* out,
+                      int64_t B, int64_t Ns, int64_t Nd, int64_t E, int64_t C, int64_t Cout, void* stream);
+/* its backward: df [B,Ns,C] through the transposed graph (nullable), du [Cout,E,C] (nullable). */
+int gaot_agno_dot_bwd(const float* g, const float* f, const float* u, const int64_t* index, const int64_t* row_splits,
+                      const int64_t* t_splits, const int64_t* t_rows, const int64_t* t_perm, float* df, float* du,
+                      int64_t B, int64_t Ns, int64_t Nd, int64_t E, int64_t C, int64_t Cout, void* stream);
+
 /* generic segment reduction of src[B,E,C] over CSR rows, reduce 0=sum 1=mean 2=max (empty -> 0);
  * the drop-in for segment_csr(src, indptr, reduce) (segment_csr.py:14-19). */
 int gaot_segment_csr(const float* src, const int64_t* row_splits, float* out,

@@ -115,6 +115,52 @@ def gaot_agno_weight_grad(gr, f, index, row_splits, dw, B, Ns, Nd, E, C):
     _arr(dw, (E, C))[:] = (G[:, seg, :] * F[:, g["neighbors_index"], :]).sum(0).float().numpy()
 
 
+def gaot_lift_aggregate_fwd(pn, Wl, bl, w, index, row_splits, out, B, Ns, Nd, C, Cin):
+    g, E = _csr(index, row_splits, Nd)
+    f = _t(pn, (B, Ns, Cin)).double() @ _t(Wl, (C, Cin)).double().T + _t(bl, (C,)).double()
+    msg = _t(w, (E, C)).double().unsqueeze(0) * f[:, g["neighbors_index"], :]
+    _arr(out, (B, Nd, C))[:] = orc.segment_csr(msg, g["neighbors_row_splits"], "sum").float().numpy()
+
+
+def gaot_lift_aggregate_bwd(gr, pn, Wl, bl, w, index, row_splits, dw, dWl, dbl, B, Ns, Nd, E, C, Cin):
+    g, _ = _csr(index, row_splits, Nd)
+    with torch.enable_grad():
+        wl = _t(Wl, (C, Cin)).double().requires_grad_(True)
+        b = _t(bl, (C,)).double().requires_grad_(True)
+        ww = _t(w, (E, C)).double().requires_grad_(True)
+        f = _t(pn, (B, Ns, Cin)).double() @ wl.T + b
+        out = orc.segment_csr(ww.unsqueeze(0) * f[:, g["neighbors_index"], :], g["neighbors_row_splits"], "sum")
+        out.backward(_t(gr, (B, Nd, C)).double())
+    _arr(dw, (E, C))[:] = ww.grad.float().numpy()
+    _arr(dWl, (C, Cin))[:] = wl.grad.float().numpy()
+    _arr(dbl, (C,))[:] = b.grad.float().numpy()
+
+
+def _dot_ref(f, u, g):
+    msg = torch.einsum("oec,bec->beo", u, f[:, g["neighbors_index"], :])
+    return orc.segment_csr(msg, g["neighbors_row_splits"], "sum")
+
+
+def gaot_agno_dot_fwd(f, u, index, row_splits, out, B, Ns, Nd, E, C, Cout):
+    g, _ = _csr(index, row_splits, Nd)
+    _arr(out, (B, Nd, Cout))[:] = _dot_ref(_t(f, (B, Ns, C)).double(), _t(u, (Cout, E, C)).double(), g).float().numpy()
+
+
+def gaot_agno_dot_bwd(gr, f, u, index, row_splits, ts, tr, tp, df, du, B, Ns, Nd, E, C, Cout):
+    g, _ = _csr(index, row_splits, Nd)
+    with torch.enable_grad():
+        F_ = _t(f, (B, Ns, C)).double().requires_grad_(True)
+        U = _t(u, (Cout, E, C)).double().requires_grad_(True)
+        _dot_ref(F_, U, g).backward(_t(gr, (B, Nd, Cout)).double())
+    if df:
+        t = orc.csr_transpose(g, Ns)                      # the kernel walks the transposed graph it is handed
+        assert np.array_equal(_arr(ts, (Ns + 1,), np.int64), t["neighbors_row_splits"].numpy())
+        assert np.array_equal(_arr(tp, (E,), np.int64), t["edge_perm"].numpy())
+        _arr(df, (B, Ns, C))[:] = F_.grad.float().numpy()
+    if du:
+        _arr(du, (Cout, E, C))[:] = U.grad.float().numpy()
+
+
 def gaot_segment_csr(src, row_splits, out, B, E, m, C, reduce):
     rs = _t(row_splits, (m + 1,), np.int64)
     _arr(out, (B, m, C))[:] = orc.segment_csr(_t(src, (B, E, C)), rs, ("sum", "mean", "max")[reduce]).numpy()

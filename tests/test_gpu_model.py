@@ -16,10 +16,11 @@ DEV = "cuda"
 FWD_TOL = 1e-5
 
 
-def _run(name, use_golden_graphs):
+def _run(name, use_golden_graphs, fuse=True):
     c = cases.CASES[name]
     g = load_golden(name)
     model = build_model(c)
+    model.encoder.fuse_affine = model.decoder.fuse_affine = fuse
     model.load_state_dict({k: v.to(DEV) for k, v in golden_params(g).items()})
     model.train()
     lat, x, pn, tgt = [t.to(DEV) for t in cases.case_inputs(name)]
@@ -40,10 +41,11 @@ def _run(name, use_golden_graphs):
     return c, g, model, out, loss, inter
 
 
+@pytest.mark.parametrize("fuse", [True, False])
 @pytest.mark.parametrize("name,golden_graph", [("tiny2d", False), ("tiny2d", True), ("tiny3d", False),
                                                ("plain2d", False), ("vx2d", True)])
-def test_forward_backward_matches_reference(name, golden_graph):
-    c, g, model, out, loss, inter = _run(name, golden_graph)
+def test_forward_backward_matches_reference(name, golden_graph, fuse):
+    c, g, model, out, loss, inter = _run(name, golden_graph, fuse)
     assert rel_l2(inter["enc_out"], g["enc_out"]) < FWD_TOL
     assert rel_l2(out, g["out"]) < FWD_TOL
     assert abs(float(loss) - float(g["loss64"])) < 1e-5 * abs(float(g["loss64"]))

@@ -235,3 +235,35 @@ def test_rmsnorm_swiglu_patch_mse_adamw():
         opt.step()
         ops.adamw_step(pw, gr.to(DEV), m, v, step, 1e-3)
     assert rel_l2(pw, ref.detach()) < 1e-6
+
+
+def test_fused_lift_aggregate_and_dot_vs_oracle():
+    ops = _ops()
+    data, q, r = cases.nbr_case("rand2d")
+    g = orc.radius_csr(data, q, r)
+    E, n, m = g["neighbors_index"].numel(), data.shape[0], q.shape[0]
+    plan = ops.GraphPlan(g["neighbors_index"].to(DEV), g["neighbors_row_splits"].to(DEV), n)
+    for C, B, Cin in ((64, 11, 1), (48, 3, 3), (16, 8, 4), (64, 1, 2)):
+        pn, Wl, bl, w = cases.normal((B, n, Cin), 31), cases.normal((C, Cin), 32), cases.normal((C,), 33), cases.normal((E, C), 34)
+        ref = [t.double().requires_grad_(True) for t in (Wl, bl, w)]
+        f = pn.double() @ ref[0].T + ref[1]
+        want = orc.segment_csr(ref[2].unsqueeze(0) * f[:, g["neighbors_index"], :], g["neighbors_row_splits"], "sum")
+        mine = [t.to(DEV).requires_grad_(True) for t in (Wl, bl, w)]
+        got = ops.lift_aggregate(pn.to(DEV), mine[0], mine[1], mine[2], plan)
+        assert rel_l2(got, want) < 2e-6
+        go = cases.normal(tuple(want.shape), 35)
+        want.backward(go.double())
+        got.backward(go.to(DEV))
+        for a, b in zip(mine, ref):
+            assert rel_l2(a.grad, b.grad) < 5e-6
+    for C, B, Cout in ((64, 11, 1), (48, 3, 3), (16, 8, 2)):
+        f, u = cases.normal((B, n, C), 36), cases.normal((Cout, E, C), 37)
+        fr, ur = f.double().requires_grad_(True), u.double().requires_grad_(True)
+        want = orc.segment_csr(torch.einsum("oec,bec->beo", ur, fr[:, g["neighbors_index"], :]), g["neighbors_row_splits"], "sum")
+        fg, ug = f.to(DEV).requires_grad_(True), u.to(DEV).requires_grad_(True)
+        got = ops.agno_dot(fg, ug, plan)
+        assert rel_l2(got, want) < 2e-6
+        go = cases.normal(tuple(want.shape), 38)
+        want.backward(go.double())
+        got.backward(go.to(DEV))
+        assert rel_l2(fg.grad, fr.grad) < 2e-6 and rel_l2(ug.grad, ur.grad) < 5e-6

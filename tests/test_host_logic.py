@@ -39,13 +39,15 @@ def test_nothing_in_the_product_imports_the_oracle():
                 assert "import oracle" not in src and "from oracle" not in src and "abi_emulator" not in src, f
 
 
+@pytest.mark.parametrize("fuse", [True, False])
 @pytest.mark.parametrize("name", ["tiny2d", "tiny3d", "plain2d", "vx2d"])
-def test_model_wiring_matches_reference_golden(name):
+def test_model_wiring_matches_reference_golden(name, fuse):
     c = cases.CASES[name]
     g = load_golden(name)
     with abi_emulator.install() as calls:
         from gaot_b200 import ops
         model = build_model(c, "cpu")
+        model.encoder.fuse_affine = model.decoder.fuse_affine = fuse
         model.load_state_dict(golden_params(g))
         lat, x, pn, tgt = cases.case_inputs(name)
         enc = dec = None
@@ -54,7 +56,13 @@ def test_model_wiring_matches_reference_golden(name):
         out = model(lat, x, pn, encoder_nbrs=enc, decoder_nbrs=dec)
         loss = ops.mse_loss(out, tgt)
         loss.backward()
-        assert "gaot_agno_aggregate" in calls and "gaot_attention_bwd" in calls
+        assert "gaot_attention_bwd" in calls
+        fusable = fuse and c["magno"]["lifting_channels"] % 4 == 0        # tiny3d has C = 6: falls back
+        assert ("gaot_lift_aggregate_bwd" in calls) == fusable
+        if not fusable:
+            assert "gaot_agno_aggregate" in calls and "gaot_agno_weight_grad" in calls
+        elif len(c["magno"].get("scales", [1.0])) == 1:
+            assert "gaot_agno_dot_bwd" in calls
     assert rel_l2(out, g["out"]) < 1e-5
     assert abs(float(loss) - float(g["loss64"])) < 1e-5 * abs(float(g["loss64"]))
     for k, p in model.named_parameters():
