@@ -225,8 +225,8 @@ __global__ void act_bwd_kernel(const float* __restrict__ dy, const float* __rest
 constexpr int NORM_MAXE = 64;   // per-lane elements: D <= 2048
 
 __global__ void __launch_bounds__(256) rmsnorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
-                                                          float* __restrict__ y, float* __restrict__ rstd,
-                                                          int64_t rows, int D, float eps) {
+                                                          float* __restrict__ y, __nv_bfloat16* __restrict__ y16,
+                                                          float* __restrict__ rstd, int64_t rows, int D, float eps) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -237,12 +237,16 @@ __global__ void __launch_bounds__(256) rmsnorm_fwd_kernel(const float* __restric
         ss = warp_sum(ss);
         const float rs = rsqrtf(ss / (float)D + eps);
         if (lane == 0) rstd[r] = rs;
-        float* yp = y + r * D;
-        for (int c = lane; c < D; c += 32) yp[c] = (xp[c] * rs) * __ldg(gamma + c);
+        for (int c = lane; c < D; c += 32) {
+            const float v = (xp[c] * rs) * __ldg(gamma + c);
+            if (y) y[r * D + c] = v;
+            if (y16) y16[r * D + c] = __float2bfloat16_rn(v);
+        }
     }
 }
 
-__global__ void __launch_bounds__(256) rmsnorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+__global__ void __launch_bounds__(256) rmsnorm_bwd_kernel(const float* __restrict__ dy, const __nv_bfloat16* __restrict__ dy16,
+                                                          const float* __restrict__ x,
                                                           const float* __restrict__ gamma, const float* __restrict__ rstd,
                                                           float* __restrict__ dx, float* __restrict__ dgamma,
                                                           int64_t rows, int D) {
@@ -257,10 +261,14 @@ __global__ void __launch_bounds__(256) rmsnorm_bwd_kernel(const float* __restric
     for (int k = 0; k < NORM_MAXE; ++k) dg[k] = 0.f;
     for (int64_t r = warp; r < rows; r += nwarps) {
         const float* xp = x + r * D;
-        const float* gp = dy + r * D;
         const float rs = rstd[r];
+        auto grad_at = [&](int c) -> float {        // the two consumers of y (fp32 residual path, bf16 GEMM path) add up
+            float v = dy ? dy[r * D + c] : 0.f;
+            if (dy16) v += __bfloat162float(dy16[r * D + c]);
+            return v;
+        };
         float dot = 0.f;
-        for (int c = lane; c < D; c += 32) dot = fmaf(gp[c] * __ldg(gamma + c), xp[c], dot);
+        for (int c = lane; c < D; c += 32) dot = fmaf(grad_at(c) * __ldg(gamma + c), xp[c], dot);
         dot = warp_sum(dot);
         const float coef = dot * rs * rs * rs / (float)D;
         float* dxp = dx + r * D;
@@ -268,7 +276,7 @@ __global__ void __launch_bounds__(256) rmsnorm_bwd_kernel(const float* __restric
         for (int k = 0; k < NORM_MAXE; ++k) {
             const int c = lane + k * 32;
             if (c < D) {
-                const float gy = gp[c], xv = xp[c];
+                const float gy = grad_at(c), xv = xp[c];
                 dxp[c] = gy * __ldg(gamma + c) * rs - xv * coef;
                 dg[k] = fmaf(gy, xv * rs, dg[k]);
             }
@@ -300,6 +308,57 @@ __global__ void swiglu_bwd_kernel(const float* __restrict__ du, const float* __r
         const float sg = 1.f / (1.f + expf(-a));
         dab[r * 2 * F + c] = gu * b * (sg + a * sg * (1.f - sg));
         dab[r * 2 * F + F + c] = gu * a * sg;
+    }
+}
+
+__device__ __forceinline__ float bf_lo(uint32_t v) { return __uint_as_float(v << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
+__device__ __forceinline__ uint32_t bf_pack(float a, float b) {
+    __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&t);
+}
+// bf16 SwiGLU: 8 elements (16 bytes) per thread; F % 8 == 0
+__global__ void swiglu_fwd_bf16_kernel(const __nv_bfloat16* __restrict__ ab, __nv_bfloat16* __restrict__ u, int64_t rows, int64_t F) {
+    const int64_t f8 = F >> 3, total = rows * f8;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / f8, c = (i - r * f8) << 3;
+        const uint4 av = __ldg(reinterpret_cast<const uint4*>(ab + r * 2 * F + c));
+        const uint4 bv = __ldg(reinterpret_cast<const uint4*>(ab + r * 2 * F + F + c));
+        const uint32_t aw[4] = {av.x, av.y, av.z, av.w}, bw[4] = {bv.x, bv.y, bv.z, bv.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float a0 = bf_lo(aw[k]), a1 = bf_hi(aw[k]);
+            o[k] = bf_pack(a0 / (1.f + __expf(-a0)) * bf_lo(bw[k]), a1 / (1.f + __expf(-a1)) * bf_hi(bw[k]));
+        }
+        *reinterpret_cast<uint4*>(u + r * F + c) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+__global__ void swiglu_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ du, const __nv_bfloat16* __restrict__ ab,
+                                       __nv_bfloat16* __restrict__ dab, int64_t rows, int64_t F) {
+    const int64_t f8 = F >> 3, total = rows * f8;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / f8, c = (i - r * f8) << 3;
+        const uint4 av = __ldg(reinterpret_cast<const uint4*>(ab + r * 2 * F + c));
+        const uint4 bv = __ldg(reinterpret_cast<const uint4*>(ab + r * 2 * F + F + c));
+        const uint4 gv = __ldg(reinterpret_cast<const uint4*>(du + r * F + c));
+        const uint32_t aw[4] = {av.x, av.y, av.z, av.w}, bw[4] = {bv.x, bv.y, bv.z, bv.w}, gw[4] = {gv.x, gv.y, gv.z, gv.w};
+        uint32_t oa[4], ob[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float da[2], db[2];
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                const float a = hh ? bf_hi(aw[k]) : bf_lo(aw[k]), b = hh ? bf_hi(bw[k]) : bf_lo(bw[k]);
+                const float gu = hh ? bf_hi(gw[k]) : bf_lo(gw[k]);
+                const float sg = 1.f / (1.f + __expf(-a));
+                da[hh] = gu * b * (sg + a * sg * (1.f - sg));
+                db[hh] = gu * a * sg;
+            }
+            oa[k] = bf_pack(da[0], da[1]); ob[k] = bf_pack(db[0], db[1]);
+        }
+        *reinterpret_cast<uint4*>(dab + r * 2 * F + c) = make_uint4(oa[0], oa[1], oa[2], oa[3]);
+        *reinterpret_cast<uint4*>(dab + r * 2 * F + F + c) = make_uint4(ob[0], ob[1], ob[2], ob[3]);
     }
 }
 
@@ -429,21 +488,22 @@ GAOT_API int gaot_act_bwd(const float* dy, const float* pre, float* dx, int64_t 
     GAOT_RETURN_LAST();
 }
 
-GAOT_API int gaot_rmsnorm_fwd(const float* x, const float* gamma, float* y, float* rstd, int64_t rows, int64_t D,
-                              float eps, void* stream) {
-    if (!x || !gamma || !y || !rstd || rows < 0 || D < 1) return GAOT_E_BADARG;
+GAOT_API int gaot_rmsnorm_fwd(const float* x, const float* gamma, float* y, void* y_bf16, float* rstd, int64_t rows,
+                              int64_t D, float eps, void* stream) {
+    if (!x || !gamma || (!y && !y_bf16) || !rstd || rows < 0 || D < 1) return GAOT_E_BADARG;
     if (rows == 0) return 0;
-    rmsnorm_fwd_kernel<<<gaot_grid(rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(x, gamma, y, rstd, rows, (int)D, eps);
+    rmsnorm_fwd_kernel<<<gaot_grid(rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+        x, gamma, y, reinterpret_cast<__nv_bfloat16*>(y_bf16), rstd, rows, (int)D, eps);
     GAOT_RETURN_LAST();
 }
 
-GAOT_API int gaot_rmsnorm_bwd(const float* dy, const float* x, const float* gamma, const float* rstd, float* dx,
-                              float* dgamma, int64_t rows, int64_t D, void* stream) {
-    if (!dy || !x || !gamma || !rstd || !dx || !dgamma || rows < 0 || D < 1 || D > 32 * NORM_MAXE) return GAOT_E_BADARG;
+GAOT_API int gaot_rmsnorm_bwd(const float* dy, const void* dy_bf16, const float* x, const float* gamma, const float* rstd,
+                              float* dx, float* dgamma, int64_t rows, int64_t D, void* stream) {
+    if ((!dy && !dy_bf16) || !x || !gamma || !rstd || !dx || !dgamma || rows < 0 || D < 1 || D > 32 * NORM_MAXE) return GAOT_E_BADARG;
     if (rows == 0) return 0;
     int grid = gaot_grid(rows * 32, 256, 2);
-    rmsnorm_bwd_kernel<<<grid, 256, sizeof(float) * (size_t)D, (cudaStream_t)stream>>>(dy, x, gamma, rstd, dx, dgamma,
-                                                                                       rows, (int)D);
+    rmsnorm_bwd_kernel<<<grid, 256, sizeof(float) * (size_t)D, (cudaStream_t)stream>>>(
+        dy, reinterpret_cast<const __nv_bfloat16*>(dy_bf16), x, gamma, rstd, dx, dgamma, rows, (int)D);
     GAOT_RETURN_LAST();
 }
 
@@ -457,6 +517,25 @@ GAOT_API int gaot_swiglu_bwd(const float* du, const float* ab, float* dab, int64
     if (!du || !ab || !dab || rows < 0 || F < 1) return GAOT_E_BADARG;
     if (rows == 0) return 0;
     swiglu_bwd_kernel<<<gaot_grid(rows * F, 256), 256, 0, (cudaStream_t)stream>>>(du, ab, dab, rows, F);
+    GAOT_RETURN_LAST();
+}
+
+GAOT_API int gaot_swiglu_fwd_bf16(const void* ab, void* u, int64_t rows, int64_t F, void* stream) {
+    if (!ab || !u || rows < 0 || F < 8 || F % 8) return GAOT_E_BADARG;
+    if ((reinterpret_cast<uintptr_t>(ab) & 15) || (reinterpret_cast<uintptr_t>(u) & 15)) return GAOT_E_ALIGN;
+    if (rows == 0) return 0;
+    swiglu_fwd_bf16_kernel<<<gaot_grid(rows * F / 8, 256), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(ab), reinterpret_cast<__nv_bfloat16*>(u), rows, F);
+    GAOT_RETURN_LAST();
+}
+GAOT_API int gaot_swiglu_bwd_bf16(const void* du, const void* ab, void* dab, int64_t rows, int64_t F, void* stream) {
+    if (!du || !ab || !dab || rows < 0 || F < 8 || F % 8) return GAOT_E_BADARG;
+    if ((reinterpret_cast<uintptr_t>(ab) & 15) || (reinterpret_cast<uintptr_t>(du) & 15) || (reinterpret_cast<uintptr_t>(dab) & 15))
+        return GAOT_E_ALIGN;
+    if (rows == 0) return 0;
+    swiglu_bwd_bf16_kernel<<<gaot_grid(rows * F / 8, 256), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(du), reinterpret_cast<const __nv_bfloat16*>(ab), reinterpret_cast<__nv_bfloat16*>(dab),
+        rows, F);
     GAOT_RETURN_LAST();
 }
 

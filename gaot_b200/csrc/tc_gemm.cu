@@ -82,7 +82,17 @@ struct TcArgs {
     int out_bf16, splits, accumulate;
 };
 
-template <int BN>
+// MN-major operand tile (TN mode): [64 contraction rows][64 elements = 128 bytes] blocks of 8 KB, one per 64 output
+// rows/columns; SWIZZLE_128B; LBO = 8 KB between the 64-wide blocks, SBO = 1 KB between 8-row groups
+__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(8192 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+           ((uint64_t)2 << 61);
+}
+
+// TN = false:  C[M,N] = A[M,K] B[N,K]^T        (A, B row-major with the contraction contiguous: K-major operands)
+// TN = true :  C[M,N] = A[R,M]^T B[R,N]        (A, B row-major [contraction rows R = g.K, outputs]: MN-major operands,
+//              used for dW = dY^T X so that neither activation has to be transposed in memory)
+template <int BN, bool TN>
 __global__ void __launch_bounds__(TC_THREADS)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs g) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -126,14 +136,22 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 mbar_expect_tx(&full_bar[s], STAGE_BYTES);
                 uint8_t* st = smem + s * STAGE_BYTES;
                 const int kc = (int)((kb0 + i) * TC_BK);
-                tma_load_2d(st, &tmA, &full_bar[s], kc, (int)m0);
-                tma_load_2d(st + A_BYTES, &tmB, &full_bar[s], kc, (int)n0);
+                if (!TN) {
+                    tma_load_2d(st, &tmA, &full_bar[s], kc, (int)m0);
+                    tma_load_2d(st + A_BYTES, &tmB, &full_bar[s], kc, (int)n0);
+                } else {                                   // boxes of 64 output columns x 64 contraction rows
+#pragma unroll
+                    for (int j = 0; j < TC_BM / 64; ++j) tma_load_2d(st + j * 8192, &tmA, &full_bar[s], (int)m0 + 64 * j, kc);
+#pragma unroll
+                    for (int j = 0; j < BN / 64; ++j) tma_load_2d(st + A_BYTES + j * 8192, &tmB, &full_bar[s], (int)n0 + 64 * j, kc);
+                }
             }
         }
     } else if (warp == 1) {
         // ---------------- MMA issuer ----------------
         // instruction descriptor: D fp32, A/B bf16, both K-major, N = BN, M = 128 (cute/arch/mma_sm100_desc.hpp)
-        constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+        constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (TN ? ((1u << 15) | (1u << 16)) : 0u) |
+                                   ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
         for (int i = 0; i < nkb; ++i) {
             const int s = i % TC_STAGES;
             const uint32_t ph = (uint32_t)(i / TC_STAGES) & 1u;
@@ -141,10 +159,17 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (lane == 0) {
                 const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
-                const uint64_t da = make_smem_desc_sw128(sa), db = make_smem_desc_sw128(sa + A_BYTES);
+                if (!TN) {
+                    const uint64_t da = make_smem_desc_sw128(sa), db = make_smem_desc_sw128(sa + A_BYTES);
 #pragma unroll
-                for (int k = 0; k < TC_BK / 16; ++k)      // +32 bytes (>>4 = 2) per K=16 step inside the 128-byte swizzle row
-                    umma_f16(tmem_acc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, (i > 0 || k > 0) ? 1u : 0u);
+                    for (int k = 0; k < TC_BK / 16; ++k)  // +32 bytes (>>4 = 2) per K=16 step inside the 128-byte swizzle row
+                        umma_f16(tmem_acc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, (i > 0 || k > 0) ? 1u : 0u);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < TC_BK / 16; ++k)  // 16 contraction rows = 2048 bytes per K=16 step
+                        umma_f16(tmem_acc, make_smem_desc_mn(sa + k * 2048), make_smem_desc_mn(sa + A_BYTES + k * 2048), IDESC,
+                                 (i > 0 || k > 0) ? 1u : 0u);
+                }
                 umma_commit(&empty_bar[s]);                // frees the slot once these MMAs have read it
                 if (i == nkb - 1) umma_commit(acc_bar);    // accumulator complete
             }
@@ -293,12 +318,26 @@ int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t K, int bo
     return r == CUDA_SUCCESS ? 0 : GAOT_E_BADARG;
 }
 
-template <int BN>
+// [R, cols] bf16 row-major -> 2-D map with box {64 columns, 64 rows}, SWIZZLE_128B (MN-major operand blocks)
+int make_map_mn(CUtensorMap* map, const void* base, int64_t R, int64_t cols) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return GAOT_E_BADARG;
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)R};
+    cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+    cuuint32_t box[2] = {64, 64};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : GAOT_E_BADARG;
+}
+
+template <int BN, bool TN>
 int launch_tc(const void* A, const void* B, TcArgs& g, cudaStream_t st) {
     CUtensorMap ta, tb;
-    int rc = make_map(&ta, A, g.M, g.K, TC_BM);
+    int rc = TN ? make_map_mn(&ta, A, g.K, g.M) : make_map(&ta, A, g.M, g.K, TC_BM);
     if (rc) return rc;
-    rc = make_map(&tb, B, g.N, g.K, BN);
+    rc = TN ? make_map_mn(&tb, B, g.K, g.N) : make_map(&tb, B, g.N, g.K, BN);
     if (rc) return rc;
     const int64_t gm = (g.M + TC_BM - 1) / TC_BM, gn = (g.N + BN - 1) / BN, kblocks = (g.K + TC_BK - 1) / TC_BK;
     int splits = 1;
@@ -313,12 +352,12 @@ int launch_tc(const void* A, const void* B, TcArgs& g, cudaStream_t st) {
     constexpr int SMEM = TC_STAGES * (TC_BM * TC_BK * 2 + BN * TC_BK * 2) + 1024 + 256;
     static bool attr_done = false;
     if (!attr_done) {
-        GAOT_CHECK(cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+        GAOT_CHECK(cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN, TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
         attr_done = true;
     }
     if (gn > 65535 || splits > 65535) return GAOT_E_BADARG;
     dim3 grid((unsigned)gm, (unsigned)gn, (unsigned)splits);
-    gemm_bf16_tc_kernel<BN><<<grid, TC_THREADS, SMEM, st>>>(ta, tb, g);
+    gemm_bf16_tc_kernel<BN, TN><<<grid, TC_THREADS, SMEM, st>>>(ta, tb, g);
     GAOT_RETURN_LAST();
 }
 
@@ -336,8 +375,21 @@ GAOT_API int gaot_gemm_bf16(const void* A, const void* B, void* C, int64_t M, in
     if (M > 0x7fffffffLL || N > 0x7fffffffLL || K > 0x7fffffffLL) return GAOT_E_BADARG;
     TcArgs g{C, M, N, K, bias, add, add ? add_rows : 1, ldadd, out_bf16, 1, accumulate};
     cudaStream_t st = (cudaStream_t)stream;
-    if (N <= 64) return launch_tc<64>(A, B, g, st);
-    return launch_tc<128>(A, B, g, st);
+    if (N <= 64) return launch_tc<64, false>(A, B, g, st);
+    return launch_tc<128, false>(A, B, g, st);
+}
+
+GAOT_API int gaot_gemm_bf16_tn(const void* A, const void* B, float* C, int64_t M, int64_t N, int64_t R, int accumulate,
+                               void* stream) {
+    if (!A || !B || !C || M < 1 || N < 1 || R < 1) return GAOT_E_BADARG;
+    if (M % 8 != 0 || N % 8 != 0 || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15) ||
+        (reinterpret_cast<uintptr_t>(C) & 15))
+        return GAOT_E_ALIGN;                       // TMA: 16-byte aligned base and row pitch
+    if (M > 0x7fffffffLL || N > 0x7fffffffLL || R > 0x7fffffffLL) return GAOT_E_BADARG;
+    TcArgs g{C, M, N, R, nullptr, nullptr, 1, 0, 0, 1, accumulate};
+    cudaStream_t st = (cudaStream_t)stream;
+    if (N <= 64) return launch_tc<64, true>(A, B, g, st);
+    return launch_tc<128, true>(A, B, g, st);
 }
 
 GAOT_API int gaot_cast_bf16(const float* in, void* out, int64_t rows, int64_t cols, void* out_t, void* stream) {

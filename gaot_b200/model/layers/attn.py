@@ -45,9 +45,13 @@ class RMSNorm(nn.Module):
         self.eps = eps
         self.weight = nn.Parameter(torch.ones(dim))
 
-    def forward(self, x):
+    def forward(self, x, mode="fp32"):
+        """mode 'bf16' / 'both' additionally (or only) emit the bf16 copy a tensor-core GEMM consumes."""
         shape = x.shape
-        return ops.rmsnorm(x.reshape(-1, shape[-1]), self.weight, self.eps).view(shape)
+        y = ops.rmsnorm(x.reshape(-1, shape[-1]), self.weight, self.eps, mode)
+        if mode == "both":
+            return y[0].view(shape), y[1].view(shape)
+        return y.view(shape)
 
 
 class GroupQueryFlashAttention(nn.Module):
@@ -103,9 +107,10 @@ class FFN(nn.Module):
     def forward(self, x, condition=None, residual=None):
         shape = x.shape
         x2 = x.reshape(-1, shape[-1])
-        ab = ops.linear(x2, torch.cat([self.w1.weight, self.w3.weight], dim=0), tc=True)
+        tc16 = ops.get_precision() == "bf16" and shape[-1] % 8 == 0 and self.w1.weight.shape[0] % 8 == 0
+        ab = ops.linear(x2, torch.cat([self.w1.weight, self.w3.weight], dim=0), tc=True, out_bf16=tc16)
         add = residual.reshape(-1, shape[-1]) if residual is not None else None
-        return ops.linear(ops.swiglu(ab), self.w2.weight, None, add=add, tc=True).view(shape)
+        return ops.linear(ops.swiglu(ab), self.w2.weight, None, add=add, tc=True).view(residual.shape if residual is not None else shape)
 
 
 class TransformerBlock(nn.Module):
@@ -130,8 +135,13 @@ class TransformerBlock(nn.Module):
             W = self.skip_proj.weight                                    # [D, 2D] acting on cat[x, skip] (attn.py:225-227)
             t = ops.linear(skip.reshape(B * T, D), W[:, D:], None, tc=True)
             x = ops.linear(x.reshape(B * T, D), W[:, :D], self.skip_proj.bias, add=t, tc=True).view(B, T, D)
-        h = self.attn_norm(x) if self.attn_norm is not None else x
+        bf = ops.get_precision() == "bf16" and x.shape[-1] % 8 == 0
+        # bf16 mode: the norms emit the bf16 GEMM operands directly (no separate cast pass)
+        h = self.attn_norm(x, "bf16" if bf else "fp32") if self.attn_norm is not None else x
         h = self.attn(h, condition=condition, relative_positions=relative_positions, residual=x)
+        if self.ffn_norm is not None and bf:
+            h, h16 = self.ffn_norm(h, "both")
+            return self.ffn(h16, condition=condition, residual=h)
         h = self.ffn_norm(h) if self.ffn_norm is not None else h
         return self.ffn(h, condition=condition, residual=h)
 

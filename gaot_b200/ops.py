@@ -218,6 +218,14 @@ def gemm_bf16(A, B, M, N, K, out_bf16=False, bias=None, add=None, add_rows=0, ou
     return out
 
 
+def gemm_bf16_tn(A, B, M, N, R, out=None, accumulate=False):
+    """C[M,N] (fp32) = A[R,M]^T B[R,N] on the tensor cores (A, B bf16 row-major, contraction over rows)."""
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device=A.device)
+    call("gaot_gemm_bf16_tn", ptr(A), ptr(B), ptr(out), M, N, R, int(accumulate))
+    return out
+
+
 class _LinearTC(torch.autograd.Function):
     """y = x W^T + bias + add[row % add_rows] with bf16 operands on tcgen05.  x may be fp32 (cast here) or
     already bf16; y is fp32, or bf16 when out_bf16 (feeding another tensor-core kernel)."""
@@ -248,12 +256,7 @@ class _LinearTC(torch.autograd.Function):
         M, K = xb.shape
         N = W.shape[0]
         dx = dW = db = dadd = None
-        need_t = ctx.needs_input_grad[1] and M % 8 == 0
-        if dy.dtype == torch.bfloat16:
-            dyb = dy
-            dybT = transpose_bf16(dyb) if need_t else None
-        else:
-            dyb, dybT = cast_bf16(dy, want=True, want_t=need_t)
+        dyb = dy if dy.dtype == torch.bfloat16 else cast_bf16(dy)[0]
         if ctx.needs_input_grad[0]:
             if N % 8 == 0:
                 _, wT = cast_bf16(W, want=False, want_t=True)        # [K, N]
@@ -262,8 +265,8 @@ class _LinearTC(torch.autograd.Function):
                 dx = gemm(dy.float(), W, M, K, N, N, K, 0, 0)
                 dx = dx.to(torch.bfloat16) if ctx.x_bf16 else dx
         if ctx.needs_input_grad[1]:
-            if need_t:
-                dW = gemm_bf16(dybT, transpose_bf16(xb), N, K, M)    # contraction over the M rows
+            if N % 8 == 0:
+                dW = gemm_bf16_tn(dyb, xb, N, K, M)                  # dY^T X, both operands read MN-major in place
             else:
                 dW = gemm(dy.float(), xb.float(), N, K, M, N, K, 1, 0)
         if (ctx.has_bias and ctx.needs_input_grad[2]) or (ctx.add_rows and ctx.needs_input_grad[3]):
@@ -286,29 +289,42 @@ def linear(x, W, bias=None, add=None, act=ACT_NONE, tc=False, out_bf16=False):
 
 
 class _RMSNorm(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, x, gamma, eps):
-        x, gamma = _c(x), _c(gamma)
-        rows, D = x.shape
-        y = torch.empty_like(x)
-        rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
-        call("gaot_rmsnorm_fwd", ptr(x), ptr(gamma), ptr(y), ptr(rstd), rows, D, float(eps))
-        ctx.save_for_backward(x, gamma, rstd)
-        return y
+    """mode 'fp32' -> y; 'bf16' -> y16 (GEMM input only); 'both' -> (y, y16) (residual + GEMM input)."""
 
     @staticmethod
-    def backward(ctx, dy):
+    def forward(ctx, x, gamma, eps, mode):
+        x, gamma = _c(x), _c(gamma)
+        rows, D = x.shape
+        y = torch.empty_like(x) if mode in ("fp32", "both") else None
+        y16 = torch.empty((rows, D), dtype=torch.bfloat16, device=x.device) if mode in ("bf16", "both") else None
+        rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
+        call("gaot_rmsnorm_fwd", ptr(x), ptr(gamma), ptr(y), ptr(y16), ptr(rstd), rows, D, float(eps))
+        ctx.save_for_backward(x, gamma, rstd)
+        ctx.mode = mode
+        return y if mode == "fp32" else (y16 if mode == "bf16" else (y, y16))
+
+    @staticmethod
+    def backward(ctx, *grads):
         x, gamma, rstd = ctx.saved_tensors
-        dy = _c(dy)
+        if ctx.mode == "fp32":
+            dy, dy16 = grads[0], None
+        elif ctx.mode == "bf16":
+            dy, dy16 = None, grads[0]
+        else:
+            dy, dy16 = grads
+        dy = _c(dy) if dy is not None else None
+        if dy16 is not None:
+            dy16 = dy16 if dy16.dtype == torch.bfloat16 else dy16.to(torch.bfloat16)
+            dy16 = dy16 if dy16.is_contiguous() else dy16.contiguous()
         rows, D = x.shape
         dx = torch.empty_like(x)
         dg = torch.zeros(D, dtype=torch.float32, device=x.device)
-        call("gaot_rmsnorm_bwd", ptr(dy), ptr(x), ptr(gamma), ptr(rstd), ptr(dx), ptr(dg), rows, D)
-        return dx, dg, None
+        call("gaot_rmsnorm_bwd", ptr(dy), ptr(dy16), ptr(x), ptr(gamma), ptr(rstd), ptr(dx), ptr(dg), rows, D)
+        return dx, dg, None, None
 
 
-def rmsnorm(x, gamma, eps):
-    return _RMSNorm.apply(x, gamma, eps)
+def rmsnorm(x, gamma, eps, mode="fp32"):
+    return _RMSNorm.apply(x, gamma, eps, mode)
 
 
 class _SwiGLU(torch.autograd.Function):
@@ -330,8 +346,30 @@ class _SwiGLU(torch.autograd.Function):
         return dab
 
 
+class _SwiGLU16(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, ab):
+        ab = ab if ab.is_contiguous() else ab.contiguous()
+        rows, F2 = ab.shape
+        u = torch.empty((rows, F2 // 2), dtype=torch.bfloat16, device=ab.device)
+        call("gaot_swiglu_fwd_bf16", ptr(ab), ptr(u), rows, F2 // 2)
+        ctx.save_for_backward(ab)
+        return u
+
+    @staticmethod
+    def backward(ctx, du):
+        (ab,) = ctx.saved_tensors
+        du = du if du.dtype == torch.bfloat16 else du.to(torch.bfloat16)
+        du = du if du.is_contiguous() else du.contiguous()
+        dab = torch.empty_like(ab)
+        call("gaot_swiglu_bwd_bf16", ptr(du), ptr(ab), ptr(dab), ab.shape[0], ab.shape[1] // 2)
+        return dab
+
+
 def swiglu(ab):
-    return _SwiGLU.apply(ab)
+    if ab.dtype == torch.bfloat16 and (ab.shape[1] // 2) % 8 == 0:
+        return _SwiGLU16.apply(ab)
+    return _SwiGLU.apply(ab.float() if ab.dtype != torch.float32 else ab)
 
 
 class _Attention(torch.autograd.Function):

@@ -155,6 +155,11 @@ int gaot_gemm_f32(const float* A, const float* B, float* C, int64_t M, int64_t N
 int gaot_gemm_bf16(const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K, int out_bf16,
                    const float* bias, const float* add, int64_t add_rows, int64_t ldadd, int accumulate,
                    void* stream);
+/* Weight-gradient form: C[M,N] (fp32) = A[R,M]^T B[R,N], A and B bf16 row-major with the contraction over
+ * their R rows (dW = dY^T X): both operands are consumed MN-major straight from their natural layout.
+ * M % 8 == 0, N % 8 == 0. */
+int gaot_gemm_bf16_tn(const void* A, const void* B, float* C, int64_t M, int64_t N, int64_t R, int accumulate,
+                      void* stream);
 /* out[r,c] = bf16(in[r,c]) (out nullable) and/or out_t[c,r] = bf16(in[r,c]) (out_t nullable) */
 int gaot_cast_bf16(const float* in, void* out, int64_t rows, int64_t cols, void* out_t, void* stream);
 /* out_t[c,r] = in[r,c], bf16 */
@@ -169,14 +174,18 @@ int gaot_act_bwd(const float* dy, const float* pre, float* dx, int64_t n, int ac
  * Processor pieces (src/model/layers/attn.py).
  * ---------------------------------------------------------------------------------------------- */
 /* RMSNorm.forward (attn.py:167-172): y = x * rsqrt(mean(x^2)+eps) * gamma; rstd[rows] saved. */
-int gaot_rmsnorm_fwd(const float* x, const float* gamma, float* y, float* rstd,
+/* y (fp32) and/or y_bf16 may be requested (either nullable, not both); the backward adds the gradients of both. */
+int gaot_rmsnorm_fwd(const float* x, const float* gamma, float* y, void* y_bf16, float* rstd,
                      int64_t rows, int64_t D, float eps, void* stream);
-int gaot_rmsnorm_bwd(const float* dy, const float* x, const float* gamma, const float* rstd,
+int gaot_rmsnorm_bwd(const float* dy, const void* dy_bf16, const float* x, const float* gamma, const float* rstd,
                      float* dx, float* dgamma /* accumulated, caller zeroes */,
                      int64_t rows, int64_t D, void* stream);
 /* FFN gate (attn.py:150-156): u = silu(ab[:, :F]) * ab[:, F:]  with ab = x [W1;W3]^T  [rows, 2F] */
 int gaot_swiglu_fwd(const float* ab, float* u, int64_t rows, int64_t F, void* stream);
 int gaot_swiglu_bwd(const float* du, const float* ab, float* dab, int64_t rows, int64_t F, void* stream);
+/* bf16 in / bf16 out variants (F % 8 == 0), used between tensor-core GEMMs */
+int gaot_swiglu_fwd_bf16(const void* ab, void* u, int64_t rows, int64_t F, void* stream);
+int gaot_swiglu_bwd_bf16(const void* du, const void* ab, void* dab, int64_t rows, int64_t F, void* stream);
 
 /* Non-causal softmax(Q K^T * scale) V, GroupQueryFlashAttention.forward (attn.py:96-116).
  * q[(b*T+t)*ldq + h*hd + i], k/v[(b*T+t)*ldk + hk*hd + i] with hk = h / (H/Hkv);

@@ -33,6 +33,13 @@ def _t(ptr, shape, dtype=np.float32):
     return torch.from_numpy(_arr(ptr, shape, dtype))
 
 
+def _bf(ptr, shape):
+    """bf16 host array viewed as a torch.bfloat16 tensor"""
+    n = int(np.prod(shape))
+    raw = np.ctypeslib.as_array(ctypes.cast(int(ptr), ctypes.POINTER(ctypes.c_uint16)), shape=(n,))
+    return torch.from_numpy(raw.view(np.int16)).view(torch.bfloat16).view(shape)
+
+
 def _csr(index_ptr, splits_ptr, m):
     rs = _t(splits_ptr, (m + 1,), np.int64)
     E = int(rs[-1])
@@ -215,13 +222,6 @@ def gaot_gemm_f32(A, B, C, M, N, K, lda, ldb, ldc, transA, transB, bias, add, ad
     c[:] = (v + c.double()).float() if accumulate else v.float()
 
 
-def _bf(ptr, shape):
-    """bf16 host array viewed as a torch.bfloat16 tensor"""
-    n = int(np.prod(shape))
-    raw = np.ctypeslib.as_array(ctypes.cast(int(ptr), ctypes.POINTER(ctypes.c_uint16)), shape=(n,))
-    return torch.from_numpy(raw.view(np.int16)).view(torch.bfloat16).view(shape)
-
-
 def gaot_gemm_bf16(A, B, C, M, N, K, out_bf16, bias, add, add_rows, ldadd, accumulate):
     v = _bf(A, (M, K)).double() @ _bf(B, (N, K)).double().T
     if bias:
@@ -260,15 +260,24 @@ def gaot_act_bwd(dy, pre, dx, n, act):
     _arr(dx, (n,))[:] = (_t(dy, (n,)).double() * gr).float().numpy()
 
 
-def gaot_rmsnorm_fwd(x, gamma, y, rstd, rows, D, eps):
+def gaot_rmsnorm_fwd(x, gamma, y, y16, rstd, rows, D, eps):
     X = _t(x, (rows, D)).double()
     r = torch.rsqrt(X.pow(2).mean(-1) + eps)
     _arr(rstd, (rows,))[:] = r.float().numpy()
-    _arr(y, (rows, D))[:] = (X * r[:, None] * _t(gamma, (D,)).double()).float().numpy()
+    v = X * r[:, None] * _t(gamma, (D,)).double()
+    if y:
+        _arr(y, (rows, D))[:] = v.float().numpy()
+    if y16:
+        _bf(y16, (rows, D))[:] = v.to(torch.bfloat16)
 
 
-def gaot_rmsnorm_bwd(dy, x, gamma, rstd, dx, dgamma, rows, D):
-    X, G, gm = _t(x, (rows, D)).double(), _t(dy, (rows, D)).double(), _t(gamma, (D,)).double()
+def gaot_rmsnorm_bwd(dy, dy16, x, gamma, rstd, dx, dgamma, rows, D):
+    X, gm = _t(x, (rows, D)).double(), _t(gamma, (D,)).double()
+    G = torch.zeros(rows, D, dtype=torch.float64)
+    if dy:
+        G = G + _t(dy, (rows, D)).double()
+    if dy16:
+        G = G + _bf(dy16, (rows, D)).double()
     r = _t(rstd, (rows,)).double()[:, None]
     dot = (G * gm * X).sum(-1, keepdim=True)
     _arr(dx, (rows, D))[:] = (G * gm * r - X * dot * r ** 3 / D).float().numpy()
@@ -285,6 +294,24 @@ def gaot_swiglu_bwd(du, ab, dab, rows, F):
         a = _t(ab, (rows, 2 * F)).double().requires_grad_(True)
         (torch.nn.functional.silu(a[:, :F]) * a[:, F:]).backward(_t(du, (rows, F)).double())
     _arr(dab, (rows, 2 * F))[:] = a.grad.float().numpy()
+
+
+def gaot_swiglu_fwd_bf16(ab, u, rows, F):
+    a = _bf(ab, (rows, 2 * F)).double()
+    _bf(u, (rows, F))[:] = (torch.nn.functional.silu(a[:, :F]) * a[:, F:]).to(torch.bfloat16)
+
+
+def gaot_swiglu_bwd_bf16(du, ab, dab, rows, F):
+    with torch.enable_grad():
+        a = _bf(ab, (rows, 2 * F)).double().requires_grad_(True)
+        (torch.nn.functional.silu(a[:, :F]) * a[:, F:]).backward(_bf(du, (rows, F)).double())
+    _bf(dab, (rows, 2 * F))[:] = a.grad.to(torch.bfloat16)
+
+
+def gaot_gemm_bf16_tn(A, B, C, M, N, R, accumulate):
+    v = _bf(A, (R, M)).double().T @ _bf(B, (R, N)).double()
+    c = _t(C, (M, N))
+    c[:] = (v + c.double()).float() if accumulate else v.float()
 
 
 def _heads(base, B, T, H, hd, ld):

@@ -197,6 +197,8 @@ def test_rmsnorm_swiglu_patch_mse_adamw():
     b, bg = x.to(DEV).requires_grad_(True), gm.to(DEV).requires_grad_(True)
     got = ops.rmsnorm(b, bg, 1e-6)
     got.backward(go.to(DEV))
+    y32, y16 = ops.rmsnorm(b.detach(), bg.detach(), 1e-6, "both")
+    assert torch.equal(y32, got.detach()) and torch.equal(y16, got.detach().to(torch.bfloat16))
     assert rel_l2(got, want) < 1e-6 and rel_l2(b.grad, a.grad) < 2e-6 and rel_l2(bg.grad, ag.grad) < 2e-6
     # swiglu
     ab = cases.normal((50, 64), 14)

@@ -128,3 +128,30 @@ def test_attention_bwd_bf16_vs_fp64(B, T, H, Hkv, hd):
     assert rel_l2(gv, rv) < 1e-2, "dV"
     assert rel_l2(gk, rk) < 2e-2, "dK"
     assert rel_l2(gq, rq) < 2e-2, "dQ"
+
+
+@pytest.mark.parametrize("M,N,R", [(256, 256, 32768), (2048, 256, 4096), (768, 256, 1000), (64, 64, 512), (200, 72, 136)])
+def test_gemm_bf16_tn_vs_fp64(M, N, R):
+    """dW form: C = A^T B with the contraction over the rows of both operands (MN-major tcgen05 operands)."""
+    from gaot_b200 import ops
+    a = cases.normal((R, M), 41).to(DEV).to(torch.bfloat16)
+    b = (cases.normal((R, N), 42) / R ** 0.5).to(DEV).to(torch.bfloat16)
+    want = a.double().T @ b.double()
+    got = ops.gemm_bf16_tn(a, b, M, N, R)
+    assert rel_l2(got, want) < 2e-5
+    acc = torch.ones((M, N), device=DEV)
+    ops.gemm_bf16_tn(a, b, M, N, R, out=acc, accumulate=True)
+    assert rel_l2(acc, want + 1.0) < 2e-5
+
+
+def test_swiglu_bf16():
+    from gaot_b200 import ops
+    ab = cases.normal((300, 128), 43).to(torch.bfloat16)
+    go = cases.normal((300, 64), 44).to(torch.bfloat16)
+    a = ab.double().requires_grad_(True)
+    want = torch.nn.functional.silu(a[:, :64]) * a[:, 64:]
+    want.backward(go.double())
+    b = ab.to(DEV).requires_grad_(True)
+    got = ops.swiglu(b)
+    got.backward(go.to(DEV))
+    assert got.dtype == torch.bfloat16 and rel_l2(got, want) < 4e-3 and rel_l2(b.grad, a.grad) < 6e-3

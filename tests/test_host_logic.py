@@ -222,7 +222,8 @@ def test_bf16_mode_wiring_close_to_reference():
             loss.backward()
         finally:
             ops.set_precision("fp32")
-        assert "gaot_gemm_bf16" in calls and "gaot_transpose_bf16" in calls and "gaot_attention_bwd_bf16" in calls
+        assert "gaot_gemm_bf16" in calls and "gaot_gemm_bf16_tn" in calls and "gaot_attention_bwd_bf16" in calls
+        assert "gaot_swiglu_bwd_bf16" in calls
     assert rel_l2(out, g["out"]) < 2e-2
     for k, p in model.named_parameters():
         assert rel_l2(p.grad, g["grad." + k]) < 6e-2, k
