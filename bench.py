@@ -164,13 +164,25 @@ def run_ours(args, w):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms)
 
-    def dev_step():
+    def eager_step():
         return step.fixed_coords_step(lat_d, x_d, pn_d, tgt_d)
+
+    if args.no_graph:
+        graphed = None
+    else:
+        for _ in range(2):
+            eager_step()
+        graphed = step.capture_fixed_coords(lat_d, x_d, pn_s, tgt_s)           # static input buffers pn_s / tgt_s
+        pn_s.copy_(pn_d); tgt_s.copy_(tgt_d)
+
+    def dev_step():
+        return graphed() if graphed is not None else eager_step()
 
     def e2e_step():
         pn_s.copy_(pn_h, non_blocking=True)
         tgt_s.copy_(tgt_h, non_blocking=True)
-        return float(step.fixed_coords_step(lat_d, x_d, pn_s, tgt_s))        # .item(): D2H read of the loss
+        loss = graphed() if graphed is not None else step.fixed_coords_step(lat_d, x_d, pn_s, tgt_s)
+        return float(loss)                                                     # .item(): D2H read of the loss
 
     W = max(args.warmup, 3)
     for _ in range(W):
@@ -186,7 +198,7 @@ def run_ours(args, w):
     # per-kernel breakdown: one extra step with CUDA events around every ABI call (same stream)
     rec = []
     _lib.set_profile(rec)
-    dev_step()
+    eager_step()
     torch.cuda.synchronize()
     _lib.set_profile(None)
     agg = {}
@@ -249,7 +261,7 @@ def run_ours(args, w):
         "steps": args.steps, "warmup": W, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
         "config": {"workload": args.workload, "precision": args.precision, "desc": w["desc"], "batch_per_gpu": B, "points": w["n"], "latent_tokens": int(M),
-                   "edges": E, "params": step.num_params, "parallelism": f"dp{world}",
+                   "edges": E, "params": step.num_params, "parallelism": f"dp{world}", "cuda_graph": graphed is not None,
                    "l2": "no flush: per-step working set (~3 GB of activations at B=32) exceeds the 126 MB L2"},
         "e2e": {"value": pts / (ms_e2e * 1e-3), "unit": "points/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": int(pn.numel() * 4 + tgt.numel() * 4), "d2h_bytes_per_step": 4},
@@ -326,6 +338,7 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch override")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
     ap.add_argument("--dump-calls", default="", help="write the per-ABI-call timing list of one step to this file")
     ap.add_argument("--precision", default=os.environ.get("GAOT_B200_PRECISION", "fp32"), choices=["fp32", "bf16"],
                     help="processor numerics: fp32 parity path or bf16 tensor-core path")

@@ -72,6 +72,11 @@ def launch_count() -> int:
     return int(lib().gaot_launch_count())
 
 
+def note_launches(n: int):
+    """Account for kernels that ran through a CUDA-graph replay (they bypass the per-call counter)."""
+    lib().gaot_launch_counter_add(int(n))
+
+
 def ptr(t):
     return 0 if t is None else t.data_ptr()
 

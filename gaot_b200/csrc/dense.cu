@@ -222,7 +222,111 @@ __global__ void act_bwd_kernel(const float* __restrict__ dy, const float* __rest
     }
 }
 
-constexpr int NORM_MAXE = 64;   // per-lane elements: D <= 2048
+constexpr int NORM_MAXE = 64;   // scalar fallback: per-lane elements, D <= 2048
+
+// Vectorised RMSNorm (D % 4 == 0, D <= 128*KMAX): a warp owns a row, lane l holds the float4 chunks
+// l, l+32, ... so every load/store is a coalesced 512-byte warp access; the row stays in registers.
+template <int KMAX>
+__global__ void __launch_bounds__(256) rmsnorm_fwd_vec_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                              float* __restrict__ y, __nv_bfloat16* __restrict__ y16,
+                                                              float* __restrict__ rstd, int64_t rows, int D, float eps) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int nv = D >> 2;
+    float4 gm[KMAX];
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) gm[k] = (lane + 32 * k < nv) ? __ldg(reinterpret_cast<const float4*>(gamma) + lane + 32 * k) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int64_t r = warp; r < rows; r += nwarps) {
+        const float4* xp = reinterpret_cast<const float4*>(x + r * D);
+        float4 xv[KMAX];
+        float ss = 0.f;
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) {
+            xv[k] = (lane + 32 * k < nv) ? __ldg(xp + lane + 32 * k) : make_float4(0.f, 0.f, 0.f, 0.f);
+            ss += xv[k].x * xv[k].x + xv[k].y * xv[k].y + xv[k].z * xv[k].z + xv[k].w * xv[k].w;
+        }
+        ss = warp_sum(ss);
+        const float rs = rsqrtf(ss / (float)D + eps);
+        if (lane == 0) rstd[r] = rs;
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) {
+            const int c4 = lane + 32 * k;
+            if (c4 < nv) {
+                const float4 o = make_float4(xv[k].x * rs * gm[k].x, xv[k].y * rs * gm[k].y, xv[k].z * rs * gm[k].z, xv[k].w * rs * gm[k].w);
+                if (y) reinterpret_cast<float4*>(y + r * D)[c4] = o;
+                if (y16) {
+                    __nv_bfloat162 t0 = __floats2bfloat162_rn(o.x, o.y), t1 = __floats2bfloat162_rn(o.z, o.w);
+                    uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
+                    reinterpret_cast<uint2*>(y16 + r * D)[c4] = pk;
+                }
+            }
+        }
+    }
+}
+
+template <int KMAX>
+__global__ void __launch_bounds__(256) rmsnorm_bwd_vec_kernel(const float* __restrict__ dy, const __nv_bfloat16* __restrict__ dy16,
+                                                              const float* __restrict__ x, const float* __restrict__ gamma,
+                                                              const float* __restrict__ rstd, float* __restrict__ dx,
+                                                              float* __restrict__ dgamma, int64_t rows, int D) {
+    extern __shared__ float sdg[];                 // [D] per-CTA partial of dgamma
+    for (int c = threadIdx.x; c < D; c += blockDim.x) sdg[c] = 0.f;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int nv = D >> 2;
+    float4 gm[KMAX], dg[KMAX];
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+        gm[k] = (lane + 32 * k < nv) ? __ldg(reinterpret_cast<const float4*>(gamma) + lane + 32 * k) : make_float4(0.f, 0.f, 0.f, 0.f);
+        dg[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (int64_t r = warp; r < rows; r += nwarps) {
+        float4 xv[KMAX], gv[KMAX];
+        float dot = 0.f;
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) {
+            const int c4 = lane + 32 * k;
+            xv[k] = gv[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (c4 < nv) {
+                xv[k] = __ldg(reinterpret_cast<const float4*>(x + r * D) + c4);
+                if (dy) gv[k] = __ldg(reinterpret_cast<const float4*>(dy + r * D) + c4);
+                if (dy16) {     // the two consumers of y (fp32 residual path, bf16 GEMM path) add up
+                    const uint2 pk = __ldg(reinterpret_cast<const uint2*>(dy16 + r * D) + c4);
+                    gv[k].x += __uint_as_float(pk.x << 16); gv[k].y += __uint_as_float(pk.x & 0xffff0000u);
+                    gv[k].z += __uint_as_float(pk.y << 16); gv[k].w += __uint_as_float(pk.y & 0xffff0000u);
+                }
+            }
+            dot += gv[k].x * gm[k].x * xv[k].x + gv[k].y * gm[k].y * xv[k].y + gv[k].z * gm[k].z * xv[k].z + gv[k].w * gm[k].w * xv[k].w;
+        }
+        dot = warp_sum(dot);
+        const float rs = __ldg(rstd + r);
+        const float coef = dot * rs * rs * rs / (float)D;
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) {
+            const int c4 = lane + 32 * k;
+            if (c4 < nv) {
+                reinterpret_cast<float4*>(dx + r * D)[c4] =
+                    make_float4(gv[k].x * gm[k].x * rs - xv[k].x * coef, gv[k].y * gm[k].y * rs - xv[k].y * coef,
+                                gv[k].z * gm[k].z * rs - xv[k].z * coef, gv[k].w * gm[k].w * rs - xv[k].w * coef);
+                dg[k].x = fmaf(gv[k].x, xv[k].x * rs, dg[k].x); dg[k].y = fmaf(gv[k].y, xv[k].y * rs, dg[k].y);
+                dg[k].z = fmaf(gv[k].z, xv[k].z * rs, dg[k].z); dg[k].w = fmaf(gv[k].w, xv[k].w * rs, dg[k].w);
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+        const int c = (lane + 32 * k) * 4;
+        if (c < D) {
+            atomicAdd(&sdg[c], dg[k].x); atomicAdd(&sdg[c + 1], dg[k].y); atomicAdd(&sdg[c + 2], dg[k].z); atomicAdd(&sdg[c + 3], dg[k].w);
+        }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < D; c += blockDim.x) atomicAdd(dgamma + c, sdg[c]);
+}
+
 
 __global__ void __launch_bounds__(256) rmsnorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                           float* __restrict__ y, __nv_bfloat16* __restrict__ y16,
@@ -492,8 +596,16 @@ GAOT_API int gaot_rmsnorm_fwd(const float* x, const float* gamma, float* y, void
                               int64_t D, float eps, void* stream) {
     if (!x || !gamma || (!y && !y_bf16) || !rstd || rows < 0 || D < 1) return GAOT_E_BADARG;
     if (rows == 0) return 0;
-    rmsnorm_fwd_kernel<<<gaot_grid(rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(
-        x, gamma, y, reinterpret_cast<__nv_bfloat16*>(y_bf16), rstd, rows, (int)D, eps);
+    cudaStream_t st = (cudaStream_t)stream;
+    __nv_bfloat16* y16 = reinterpret_cast<__nv_bfloat16*>(y_bf16);
+    const bool vec = D % 4 == 0 && D <= 1024 && !(reinterpret_cast<uintptr_t>(x) & 15) && !(reinterpret_cast<uintptr_t>(gamma) & 15) &&
+                     !(reinterpret_cast<uintptr_t>(y) & 15) && !(reinterpret_cast<uintptr_t>(y_bf16) & 7);
+    const int grid = gaot_grid(rows * 32, 256);
+    if (vec && D <= 128) rmsnorm_fwd_vec_kernel<1><<<grid, 256, 0, st>>>(x, gamma, y, y16, rstd, rows, (int)D, eps);
+    else if (vec && D <= 256) rmsnorm_fwd_vec_kernel<2><<<grid, 256, 0, st>>>(x, gamma, y, y16, rstd, rows, (int)D, eps);
+    else if (vec && D <= 512) rmsnorm_fwd_vec_kernel<4><<<grid, 256, 0, st>>>(x, gamma, y, y16, rstd, rows, (int)D, eps);
+    else if (vec) rmsnorm_fwd_vec_kernel<8><<<grid, 256, 0, st>>>(x, gamma, y, y16, rstd, rows, (int)D, eps);
+    else rmsnorm_fwd_kernel<<<grid, 256, 0, st>>>(x, gamma, y, y16, rstd, rows, (int)D, eps);
     GAOT_RETURN_LAST();
 }
 
@@ -501,9 +613,18 @@ GAOT_API int gaot_rmsnorm_bwd(const float* dy, const void* dy_bf16, const float*
                               float* dx, float* dgamma, int64_t rows, int64_t D, void* stream) {
     if ((!dy && !dy_bf16) || !x || !gamma || !rstd || !dx || !dgamma || rows < 0 || D < 1 || D > 32 * NORM_MAXE) return GAOT_E_BADARG;
     if (rows == 0) return 0;
-    int grid = gaot_grid(rows * 32, 256, 2);
-    rmsnorm_bwd_kernel<<<grid, 256, sizeof(float) * (size_t)D, (cudaStream_t)stream>>>(
-        dy, reinterpret_cast<const __nv_bfloat16*>(dy_bf16), x, gamma, rstd, dx, dgamma, rows, (int)D);
+    const int grid = gaot_grid(rows * 32, 256, 4);
+    cudaStream_t st = (cudaStream_t)stream;
+    const __nv_bfloat16* g16 = reinterpret_cast<const __nv_bfloat16*>(dy_bf16);
+    const size_t sm = sizeof(float) * (size_t)D;
+    const bool vec = D % 4 == 0 && D <= 1024 && !(reinterpret_cast<uintptr_t>(x) & 15) && !(reinterpret_cast<uintptr_t>(gamma) & 15) &&
+                     !(reinterpret_cast<uintptr_t>(dy) & 15) && !(reinterpret_cast<uintptr_t>(dy_bf16) & 7) &&
+                     !(reinterpret_cast<uintptr_t>(dx) & 15);
+    if (vec && D <= 128) rmsnorm_bwd_vec_kernel<1><<<grid, 256, sm, st>>>(dy, g16, x, gamma, rstd, dx, dgamma, rows, (int)D);
+    else if (vec && D <= 256) rmsnorm_bwd_vec_kernel<2><<<grid, 256, sm, st>>>(dy, g16, x, gamma, rstd, dx, dgamma, rows, (int)D);
+    else if (vec && D <= 512) rmsnorm_bwd_vec_kernel<4><<<grid, 256, sm, st>>>(dy, g16, x, gamma, rstd, dx, dgamma, rows, (int)D);
+    else if (vec) rmsnorm_bwd_vec_kernel<8><<<grid, 256, sm, st>>>(dy, g16, x, gamma, rstd, dx, dgamma, rows, (int)D);
+    else rmsnorm_bwd_kernel<<<grid, 256, sm, st>>>(dy, g16, x, gamma, rstd, dx, dgamma, rows, (int)D);
     GAOT_RETURN_LAST();
 }
 

@@ -33,6 +33,7 @@ extern "C" {
 int gaot_abi_version(void);
 /* kernels launched by this library in this process so far (diagnostics; bench.py `gpu_launches`) */
 long long gaot_launch_count(void);
+long long gaot_launch_counter_add(long long n);   /* host code adds launches replayed through a CUDA graph */
 
 /* ------------------------------------------------------------------------------------------------
  * Radius graph.  Replaces NeighborSearch.forward and its back-ends
