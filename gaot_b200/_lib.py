@@ -32,7 +32,7 @@ def parse_header(path: str = HEADER_PATH):
                 a = a.strip()
                 if "*" in a:
                     kinds += "p"
-                elif a.startswith("int64_t"):
+                elif a.startswith("int64_t") or a.startswith("long long"):
                     kinds += "l"
                 elif a.startswith("float"):
                     kinds += "f"
