@@ -85,6 +85,11 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
         : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ float ex2(float x) {          // single MUFU.EX2 (ex2(-inf) = 0)
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&t);
@@ -208,31 +213,44 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttnArgs g) {
             mbar_wait(s_full, (uint32_t)i & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int kv_left = g.T - i * AT_BKV;          // keys of this tile that exist
-            float mx = -INFINITY;
+            const bool full_tile = kv_left >= AT_BKV;      // warp-uniform: only the last tile can be ragged
+            float mx = -INFINITY;                          // max of the RAW scores (scale > 0)
 #pragma unroll 1
             for (int c = 0; c < 4; ++c) {
                 uint32_t v[32];
                 tmem_ld32(tmem_s + lane_addr + c * 32, v);
+                if (full_tile) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const float sv = (c * 32 + j < kv_left) ? __uint_as_float(v[j]) * g.scale_log2 : -INFINITY;
-                    mx = fmaxf(mx, sv);
+                    for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) mx = fmaxf(mx, (c * 32 + j < kv_left) ? __uint_as_float(v[j]) : -INFINITY);
                 }
             }
-            const float mnew = fmaxf(mrun, mx);
-            const float corr = exp2f(mrun - mnew);
+            const float mnew = fmaxf(mrun, mx * g.scale_log2);
+            const float corr = ex2(mrun - mnew);
             float psum = 0.f;
 #pragma unroll 1
             for (int c = 0; c < 4; ++c) {
                 uint32_t v[32];
                 tmem_ld32(tmem_s + lane_addr + c * 32, v);
                 uint32_t pk[16];
+                if (full_tile) {
 #pragma unroll
-                for (int j = 0; j < 32; j += 2) {
-                    const float p0 = (c * 32 + j < kv_left) ? exp2f(__uint_as_float(v[j]) * g.scale_log2 - mnew) : 0.f;
-                    const float p1 = (c * 32 + j + 1 < kv_left) ? exp2f(__uint_as_float(v[j + 1]) * g.scale_log2 - mnew) : 0.f;
-                    psum += p0 + p1;
-                    pk[j >> 1] = pack_bf16(p0, p1);
+                    for (int j = 0; j < 32; j += 2) {
+                        const float p0 = ex2(fmaf(__uint_as_float(v[j]), g.scale_log2, -mnew));
+                        const float p1 = ex2(fmaf(__uint_as_float(v[j + 1]), g.scale_log2, -mnew));
+                        psum += p0 + p1;
+                        pk[j >> 1] = pack_bf16(p0, p1);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 2) {
+                        const float p0 = (c * 32 + j < kv_left) ? ex2(fmaf(__uint_as_float(v[j]), g.scale_log2, -mnew)) : 0.f;
+                        const float p1 = (c * 32 + j + 1 < kv_left) ? ex2(fmaf(__uint_as_float(v[j + 1]), g.scale_log2, -mnew)) : 0.f;
+                        psum += p0 + p1;
+                        pk[j >> 1] = pack_bf16(p0, p1);
+                    }
                 }
                 uint8_t* blk = sP + (c >> 1) * (AT_BQ * 128);
 #pragma unroll
@@ -434,16 +452,20 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
                 tmem_ld32(tm_st + lane_addr + c * 32, sv);
                 tmem_ld32(tm_dp + lane_addr + c * 32, dv);
                 uint32_t pp[16], ds[16];
+                const float4* l4 = reinterpret_cast<const float4*>(sLse + s * 128 + c * 32);
+                const float4* d4 = reinterpret_cast<const float4*>(sDel + s * 128 + c * 32);
 #pragma unroll
-                for (int j = 0; j < 32; j += 2) {
-                    const float l0 = sLse[s * 128 + c * 32 + j], l1 = sLse[s * 128 + c * 32 + j + 1];
-                    float p0 = exp2f(__uint_as_float(sv[j]) * g.scale_log2 - l0);
-                    float p1 = exp2f(__uint_as_float(sv[j + 1]) * g.scale_log2 - l1);
-                    if (!key_ok) { p0 = 0.f; p1 = 0.f; }
-                    const float d0 = p0 * (__uint_as_float(dv[j]) - sDel[s * 128 + c * 32 + j]);
-                    const float d1 = p1 * (__uint_as_float(dv[j + 1]) - sDel[s * 128 + c * 32 + j + 1]);
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 lv = l4[j >> 2], dl = d4[j >> 2];      // broadcast reads: every thread, same address
+                    float p0 = ex2(fmaf(__uint_as_float(sv[j]), g.scale_log2, -lv.x));
+                    float p1 = ex2(fmaf(__uint_as_float(sv[j + 1]), g.scale_log2, -lv.y));
+                    float p2 = ex2(fmaf(__uint_as_float(sv[j + 2]), g.scale_log2, -lv.z));
+                    float p3 = ex2(fmaf(__uint_as_float(sv[j + 3]), g.scale_log2, -lv.w));
+                    if (!key_ok) { p0 = 0.f; p1 = 0.f; p2 = 0.f; p3 = 0.f; }
                     pp[j >> 1] = pack_bf16(p0, p1);
-                    ds[j >> 1] = pack_bf16(d0, d1);
+                    pp[(j >> 1) + 1] = pack_bf16(p2, p3);
+                    ds[j >> 1] = pack_bf16(p0 * (__uint_as_float(dv[j]) - dl.x), p1 * (__uint_as_float(dv[j + 1]) - dl.y));
+                    ds[(j >> 1) + 1] = pack_bf16(p2 * (__uint_as_float(dv[j + 2]) - dl.z), p3 * (__uint_as_float(dv[j + 3]) - dl.w));
                 }
                 uint8_t* bp = sPt + (c >> 1) * (128 * 128);
                 uint8_t* bs = sSt + (c >> 1) * (128 * 128);
