@@ -22,7 +22,7 @@ namespace {
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;          // 64 bf16 = 128 bytes = one SWIZZLE_128B row
-constexpr int TC_STAGES = 3;
+constexpr int TC_STAGES = 5;
 constexpr int TC_THREADS = 192;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -80,178 +80,212 @@ struct TcArgs {
     void* C; int64_t M, N, K;
     const float* bias; const float* add; int64_t add_rows, ldadd;
     int out_bf16, splits, accumulate;
+    int64_t gm, gn;                   // tile grid
 };
 
-// MN-major operand tile (TN mode): [64 contraction rows][64 elements = 128 bytes] blocks of 8 KB, one per 64 output
+// MN-major operand tile: [64 contraction rows][64 elements = 128 bytes] blocks of 8 KB, one per 64 output
 // rows/columns; SWIZZLE_128B; LBO = 8 KB between the 64-wide blocks, SBO = 1 KB between 8-row groups
 __device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t saddr) {
     return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(8192 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
            ((uint64_t)2 << 61);
 }
 
-// TN = false:  C[M,N] = A[M,K] B[N,K]^T        (A, B row-major with the contraction contiguous: K-major operands)
-// TN = true :  C[M,N] = A[R,M]^T B[R,N]        (A, B row-major [contraction rows R = g.K, outputs]: MN-major operands,
-//              used for dW = dY^T X so that neither activation has to be transposed in memory)
-template <int BN, bool TN>
-__global__ void __launch_bounds__(TC_THREADS)
+// Persistent GEMM: C[M,N] = opA * opB, one CTA per SM walking tiles (m fastest) with a static stride.
+//   AMN = false: A is [M, K] row-major (K-major operand);  AMN = true: A is [K, M] row-major (MN-major operand)
+//   BMN = false: B is [N, K] row-major (K-major operand);  BMN = true: B is [K, N] row-major (MN-major operand)
+// so forward / dX / dW of a Linear layer all read activations and weights in their natural layout.
+// Two TMEM accumulators (2*BN columns): the epilogue of tile i overlaps the main loop of tile i+1, and the TMA
+// ring keeps prefetching across tile boundaries.
+template <int BN, bool AMN, bool BMN>
+__global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs g) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    // carve: [stages][A 16 KB][B BN*128 B] (all 1024-aligned), then barriers
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     constexpr int A_BYTES = TC_BM * TC_BK * 2, B_BYTES = BN * TC_BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + TC_STAGES * STAGE_BYTES);
+    constexpr int PITCH = 36;                                      // epilogue staging: floats per row (16-byte aligned)
+    float* stg_all = reinterpret_cast<float*>(smem + TC_STAGES * STAGE_BYTES);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(stg_all + 4 * 32 * PITCH);
     uint64_t* empty_bar = full_bar + TC_STAGES;
-    uint64_t* acc_bar = empty_bar + TC_STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
+    uint64_t* acc_full = empty_bar + TC_STAGES;                    // [2]
+    uint64_t* acc_empty = acc_full + 2;                            // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t m0 = (int64_t)blockIdx.x * TC_BM, n0 = (int64_t)blockIdx.y * BN;
     const int64_t kblocks = (g.K + TC_BK - 1) / TC_BK;
     const int64_t per = (kblocks + g.splits - 1) / g.splits;
-    const int64_t kb0 = (int64_t)blockIdx.z * per, kb1 = min(kblocks, kb0 + per);
-    const int nkb = (int)max((int64_t)0, kb1 - kb0);
+    const int64_t n_tiles = g.gm * g.gn * g.splits;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        mbar_init(acc_bar, 1);
+        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)BN));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)(2 * BN)));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_acc = *tmem_slot;
+    const uint32_t tmem_base = *tmem_slot;
+
+    auto tile_coords = [&](int64_t t, int64_t& m0, int64_t& n0, int64_t& kb0, int& nkb) {
+        const int64_t mi = t % g.gm, rest = t / g.gm;
+        const int64_t ni = rest % g.gn, sp = rest / g.gn;
+        m0 = mi * TC_BM; n0 = ni * BN;
+        kb0 = sp * per;
+        nkb = (int)max((int64_t)0, min(kblocks, kb0 + per) - kb0);
+    };
 
     if (warp == 0) {
         // ---------------- TMA producer ----------------
         if (lane == 0) {
-            for (int i = 0; i < nkb; ++i) {
-                const int s = i % TC_STAGES;
-                const uint32_t ph = (uint32_t)(i / TC_STAGES) & 1u;
-                mbar_wait(&empty_bar[s], ph ^ 1u);
-                mbar_expect_tx(&full_bar[s], STAGE_BYTES);
-                uint8_t* st = smem + s * STAGE_BYTES;
-                const int kc = (int)((kb0 + i) * TC_BK);
-                if (!TN) {
-                    tma_load_2d(st, &tmA, &full_bar[s], kc, (int)m0);
-                    tma_load_2d(st + A_BYTES, &tmB, &full_bar[s], kc, (int)n0);
-                } else {                                   // boxes of 64 output columns x 64 contraction rows
+            uint32_t it = 0;
+            for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+                int64_t m0, n0, kb0; int nkb;
+                tile_coords(t, m0, n0, kb0, nkb);
+                for (int i = 0; i < nkb; ++i, ++it) {
+                    const int s = (int)(it % TC_STAGES);
+                    mbar_wait(&empty_bar[s], ((it / TC_STAGES) & 1u) ^ 1u);
+                    mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+                    uint8_t* st = smem + s * STAGE_BYTES;
+                    const int kc = (int)((kb0 + i) * TC_BK);
+                    if (!AMN) tma_load_2d(st, &tmA, &full_bar[s], kc, (int)m0);
+                    else {
 #pragma unroll
-                    for (int j = 0; j < TC_BM / 64; ++j) tma_load_2d(st + j * 8192, &tmA, &full_bar[s], (int)m0 + 64 * j, kc);
+                        for (int j = 0; j < TC_BM / 64; ++j) tma_load_2d(st + j * 8192, &tmA, &full_bar[s], (int)m0 + 64 * j, kc);
+                    }
+                    if (!BMN) tma_load_2d(st + A_BYTES, &tmB, &full_bar[s], kc, (int)n0);
+                    else {
 #pragma unroll
-                    for (int j = 0; j < BN / 64; ++j) tma_load_2d(st + A_BYTES + j * 8192, &tmB, &full_bar[s], (int)n0 + 64 * j, kc);
+                        for (int j = 0; j < BN / 64; ++j) tma_load_2d(st + A_BYTES + j * 8192, &tmB, &full_bar[s], (int)n0 + 64 * j, kc);
+                    }
                 }
             }
         }
     } else if (warp == 1) {
         // ---------------- MMA issuer ----------------
-        // instruction descriptor: D fp32, A/B bf16, both K-major, N = BN, M = 128 (cute/arch/mma_sm100_desc.hpp)
-        constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (TN ? ((1u << 15) | (1u << 16)) : 0u) |
+        // instruction descriptor: D fp32, A/B bf16, majors per template, N = BN, M = 128 (cute/arch/mma_sm100_desc.hpp)
+        constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (AMN ? (1u << 15) : 0u) | (BMN ? (1u << 16) : 0u) |
                                    ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-        for (int i = 0; i < nkb; ++i) {
-            const int s = i % TC_STAGES;
-            const uint32_t ph = (uint32_t)(i / TC_STAGES) & 1u;
-            mbar_wait(&full_bar[s], ph);
+        uint32_t it = 0, lt = 0;
+        for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++lt) {
+            int64_t m0, n0, kb0; int nkb;
+            tile_coords(t, m0, n0, kb0, nkb);
+            const uint32_t ab = lt & 1u;
+            mbar_wait(&acc_empty[ab], ((lt >> 1) & 1u) ^ 1u);       // epilogue has drained this accumulator
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (lane == 0) {
-                const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
-                if (!TN) {
-                    const uint64_t da = make_smem_desc_sw128(sa), db = make_smem_desc_sw128(sa + A_BYTES);
+            const uint32_t tmem_acc = tmem_base + ab * BN;
+            for (int i = 0; i < nkb; ++i, ++it) {
+                const int s = (int)(it % TC_STAGES);
+                mbar_wait(&full_bar[s], (it / TC_STAGES) & 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (lane == 0) {
+                    const uint32_t sa = smem_u32(smem + s * STAGE_BYTES), sb = sa + A_BYTES;
 #pragma unroll
-                    for (int k = 0; k < TC_BK / 16; ++k)  // +32 bytes (>>4 = 2) per K=16 step inside the 128-byte swizzle row
-                        umma_f16(tmem_acc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, (i > 0 || k > 0) ? 1u : 0u);
-                } else {
-#pragma unroll
-                    for (int k = 0; k < TC_BK / 16; ++k)  // 16 contraction rows = 2048 bytes per K=16 step
-                        umma_f16(tmem_acc, make_smem_desc_mn(sa + k * 2048), make_smem_desc_mn(sa + A_BYTES + k * 2048), IDESC,
-                                 (i > 0 || k > 0) ? 1u : 0u);
+                    for (int k = 0; k < TC_BK / 16; ++k) {
+                        // K-major: +32 bytes per K=16 step inside the 128-byte swizzle row; MN-major: 16 rows = 2048 bytes
+                        const uint64_t da = AMN ? make_smem_desc_mn(sa + k * 2048) : make_smem_desc_sw128(sa) + (uint64_t)(2 * k);
+                        const uint64_t db = BMN ? make_smem_desc_mn(sb + k * 2048) : make_smem_desc_sw128(sb) + (uint64_t)(2 * k);
+                        umma_f16(tmem_acc, da, db, IDESC, (i > 0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[s]);                    // frees the slot once these MMAs have read it
+                    if (i == nkb - 1) umma_commit(&acc_full[ab]);  // accumulator complete
                 }
-                umma_commit(&empty_bar[s]);                // frees the slot once these MMAs have read it
-                if (i == nkb - 1) umma_commit(acc_bar);    // accumulator complete
+                __syncwarp();
             }
-            __syncwarp();
         }
     } else {
         // ---------------- epilogue (warps 2..5; warp w may touch TMEM lanes 32*(w%4) .. +31) ----------------
-        // TMEM hands each thread one accumulator ROW; a per-warp 32x32 staging tile (aliasing ring stage 0,
-        // idle once the accumulator is complete) turns that into row-contiguous 128-byte global accesses:
-        // lane -> (row it*4 + lane/8, 4 columns (lane%8)*4) for bias / add loads and the C stores.
+        // TMEM hands each thread one accumulator ROW; a per-warp 32x32 staging tile turns that into
+        // row-contiguous 128-byte global accesses: lane -> (row it*4 + lane/8, 4 columns (lane%8)*4).
         const int q = warp & 3;
-        if (nkb > 0) {
-            mbar_wait(acc_bar, 0);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        }
-        constexpr int PITCH = 36;                                  // floats; 16-byte aligned rows, conflict-free float4
-        float* stg = reinterpret_cast<float*>(smem) + q * (32 * PITCH);
-        const bool first = blockIdx.z == 0;
+        float* stg = stg_all + q * (32 * PITCH);
         const bool vec_ok = (g.N % 4 == 0) && (!g.add || (g.ldadd % 4 == 0));
         const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-            uint32_t r[32];
-            if (nkb > 0) tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-            else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) r[j] = 0u;
+        uint32_t lt = 0;
+        for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++lt) {
+            int64_t m0, n0, kb0; int nkb;
+            tile_coords(t, m0, n0, kb0, nkb);
+            const uint32_t ab = lt & 1u;
+            if (nkb > 0) {
+                mbar_wait(&acc_full[ab], (lt >> 1) & 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             }
-            const int64_t n = n0 + c0;
-            if (n >= g.N) continue;                                // warp-uniform
-            __syncwarp();
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-                *reinterpret_cast<float4*>(stg + lane * PITCH + j) =
-                    make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
-            __syncwarp();
-            const bool full = (n + 32 <= g.N) && vec_ok;
+            const bool first = kb0 == 0;
+            const uint32_t tmem_acc = tmem_base + ab * BN + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-            for (int it = 0; it < 8; ++it) {
-                const int rr = it * 4 + sub_r;
-                const int64_t m = m0 + q * 32 + rr;
-                if (m >= g.M) continue;
-                float4 v = *reinterpret_cast<const float4*>(stg + rr * PITCH + sub_c);
-                const int64_t nc = n + sub_c;
-                if (full) {
-                    if (first && g.bias) {
-                        const float4 bv = __ldg(reinterpret_cast<const float4*>(g.bias + nc));
-                        v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
-                    }
-                    if (first && g.add) {
-                        const float4 av = __ldg(reinterpret_cast<const float4*>(g.add + (m % g.add_rows) * g.ldadd + nc));
-                        v.x += av.x; v.y += av.y; v.z += av.z; v.w += av.w;
-                    }
-                    if (g.out_bf16) {
-                        __nv_bfloat162 t0 = __floats2bfloat162_rn(v.x, v.y), t1 = __floats2bfloat162_rn(v.z, v.w);
-                        uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
-                        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(g.C) + m * g.N + nc) = pk;
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t r[32];
+                if (nkb > 0) tmem_ld32(tmem_acc + (uint32_t)c0, r);
+                else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) r[j] = 0u;
+                }
+                const int64_t n = n0 + c0;
+                if (n >= g.N) continue;                            // warp-uniform
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4*>(stg + lane * PITCH + j) =
+                        make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+                __syncwarp();
+                const bool full = (n + 32 <= g.N) && vec_ok;
+#pragma unroll 2
+                for (int it8 = 0; it8 < 8; ++it8) {
+                    const int rr = it8 * 4 + sub_r;
+                    const int64_t m = m0 + q * 32 + rr;
+                    if (m >= g.M) continue;
+                    float4 v = *reinterpret_cast<const float4*>(stg + rr * PITCH + sub_c);
+                    const int64_t nc = n + sub_c;
+                    if (full) {
+                        if (first && g.bias) {
+                            const float4 bv = __ldg(reinterpret_cast<const float4*>(g.bias + nc));
+                            v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+                        }
+                        if (first && g.add) {
+                            const float4 av = __ldg(reinterpret_cast<const float4*>(g.add + (m % g.add_rows) * g.ldadd + nc));
+                            v.x += av.x; v.y += av.y; v.z += av.z; v.w += av.w;
+                        }
+                        if (g.out_bf16) {
+                            __nv_bfloat162 t0 = __floats2bfloat162_rn(v.x, v.y), t1 = __floats2bfloat162_rn(v.z, v.w);
+                            uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
+                            *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(g.C) + m * g.N + nc) = pk;
+                        } else {
+                            float* cp = reinterpret_cast<float*>(g.C) + m * g.N + nc;
+                            if (g.splits > 1 || g.accumulate) atomicAdd(reinterpret_cast<float4*>(cp), v);
+                            else *reinterpret_cast<float4*>(cp) = v;
+                        }
                     } else {
-                        float* cp = reinterpret_cast<float*>(g.C) + m * g.N + nc;
-                        if (g.splits > 1 || g.accumulate) atomicAdd(reinterpret_cast<float4*>(cp), v);
-                        else *reinterpret_cast<float4*>(cp) = v;
-                    }
-                } else {
-                    float vv[4] = {v.x, v.y, v.z, v.w};
-                    for (int j = 0; j < 4; ++j) {
-                        if (nc + j >= g.N) break;
-                        float x = vv[j];
-                        if (first && g.bias) x += __ldg(g.bias + nc + j);
-                        if (first && g.add) x += __ldg(g.add + (m % g.add_rows) * g.ldadd + nc + j);
-                        if (g.out_bf16) reinterpret_cast<__nv_bfloat16*>(g.C)[m * g.N + nc + j] = __float2bfloat16_rn(x);
-                        else if (g.splits > 1 || g.accumulate) atomicAdd(reinterpret_cast<float*>(g.C) + m * g.N + nc + j, x);
-                        else reinterpret_cast<float*>(g.C)[m * g.N + nc + j] = x;
+                        float vv[4] = {v.x, v.y, v.z, v.w};
+                        for (int j = 0; j < 4; ++j) {
+                            if (nc + j >= g.N) break;
+                            float x = vv[j];
+                            if (first && g.bias) x += __ldg(g.bias + nc + j);
+                            if (first && g.add) x += __ldg(g.add + (m % g.add_rows) * g.ldadd + nc + j);
+                            if (g.out_bf16) reinterpret_cast<__nv_bfloat16*>(g.C)[m * g.N + nc + j] = __float2bfloat16_rn(x);
+                            else if (g.splits > 1 || g.accumulate) atomicAdd(reinterpret_cast<float*>(g.C) + m * g.N + nc + j, x);
+                            else reinterpret_cast<float*>(g.C)[m * g.N + nc + j] = x;
+                        }
                     }
                 }
             }
+            // this warp is done with the accumulator: let the MMA warp reuse it
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[ab])) : "memory");
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"((uint32_t)BN));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * BN)));
     }
 }
 
@@ -332,32 +366,49 @@ int make_map_mn(CUtensorMap* map, const void* base, int64_t R, int64_t cols) {
     return r == CUDA_SUCCESS ? 0 : GAOT_E_BADARG;
 }
 
-template <int BN, bool TN>
+int sm_count() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
+}
+
+template <int BN, bool AMN, bool BMN>
 int launch_tc(const void* A, const void* B, TcArgs& g, cudaStream_t st) {
     CUtensorMap ta, tb;
-    int rc = TN ? make_map_mn(&ta, A, g.K, g.M) : make_map(&ta, A, g.M, g.K, TC_BM);
+    int rc = AMN ? make_map_mn(&ta, A, g.K, g.M) : make_map(&ta, A, g.M, g.K, TC_BM);
     if (rc) return rc;
-    rc = TN ? make_map_mn(&tb, B, g.K, g.N) : make_map(&tb, B, g.N, g.K, BN);
+    rc = BMN ? make_map_mn(&tb, B, g.K, g.N) : make_map(&tb, B, g.N, g.K, BN);
     if (rc) return rc;
-    const int64_t gm = (g.M + TC_BM - 1) / TC_BM, gn = (g.N + BN - 1) / BN, kblocks = (g.K + TC_BK - 1) / TC_BK;
+    g.gm = (g.M + TC_BM - 1) / TC_BM;
+    g.gn = (g.N + BN - 1) / BN;
+    const int64_t kblocks = (g.K + TC_BK - 1) / TC_BK, tiles = g.gm * g.gn;
+    const int sms = sm_count();
     int splits = 1;
-    if (!g.out_bf16 && gm * gn < 148 && kblocks >= 8) {
-        splits = (int)((296 + gm * gn - 1) / (gm * gn));
+    if (!g.out_bf16 && tiles < sms && kblocks >= 8) {          // too few tiles for the chip: split the contraction
+        splits = (int)((2 * sms + tiles - 1) / tiles);
         if (splits > kblocks / 4) splits = (int)(kblocks / 4);
         if (splits > 128) splits = 128;
         if (splits < 1) splits = 1;
     }
+    if (splits > 1) {                                           // no empty splits: every tile must own >= 1 k-block
+        const int64_t per = (kblocks + splits - 1) / splits;
+        splits = (int)((kblocks + per - 1) / per);
+    }
     g.splits = splits;
     if (splits > 1 && !g.accumulate) GAOT_CHECK(cudaMemsetAsync(g.C, 0, sizeof(float) * (size_t)(g.M * g.N), st));
-    constexpr int SMEM = TC_STAGES * (TC_BM * TC_BK * 2 + BN * TC_BK * 2) + 1024 + 256;
+    constexpr int SMEM = TC_STAGES * (TC_BM * TC_BK * 2 + BN * TC_BK * 2) + 4 * 32 * 36 * 4 + 1024 + 256;
     static bool attr_done = false;
     if (!attr_done) {
-        GAOT_CHECK(cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN, TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+        GAOT_CHECK(cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN, AMN, BMN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
         attr_done = true;
     }
-    if (gn > 65535 || splits > 65535) return GAOT_E_BADARG;
-    dim3 grid((unsigned)gm, (unsigned)gn, (unsigned)splits);
-    gemm_bf16_tc_kernel<BN, TN><<<grid, TC_THREADS, SMEM, st>>>(ta, tb, g);
+    const int64_t total = tiles * splits;
+    const unsigned grid = (unsigned)(total < sms ? total : sms);   // persistent: one CTA per SM
+    gemm_bf16_tc_kernel<BN, AMN, BMN><<<grid, TC_THREADS, SMEM, st>>>(ta, tb, g);
     GAOT_RETURN_LAST();
 }
 
@@ -373,10 +424,23 @@ GAOT_API int gaot_gemm_bf16(const void* A, const void* B, void* C, int64_t M, in
     if (add && (add_rows < 1 || ldadd < N)) return GAOT_E_BADARG;
     if (out_bf16 && accumulate) return GAOT_E_BADARG;
     if (M > 0x7fffffffLL || N > 0x7fffffffLL || K > 0x7fffffffLL) return GAOT_E_BADARG;
-    TcArgs g{C, M, N, K, bias, add, add ? add_rows : 1, ldadd, out_bf16, 1, accumulate};
+    TcArgs g{C, M, N, K, bias, add, add ? add_rows : 1, ldadd, out_bf16, 1, accumulate, 0, 0};
     cudaStream_t st = (cudaStream_t)stream;
-    if (N <= 64) return launch_tc<64, false>(A, B, g, st);
-    return launch_tc<128, false>(A, B, g, st);
+    if (N <= 64) return launch_tc<64, false, false>(A, B, g, st);
+    return launch_tc<128, false, false>(A, B, g, st);
+}
+
+GAOT_API int gaot_gemm_bf16_nn(const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K, int out_bf16,
+                               void* stream) {
+    if (!A || !B || !C || M < 1 || N < 1 || K < 1) return GAOT_E_BADARG;
+    if (K % 8 != 0 || N % 8 != 0 || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15) ||
+        (reinterpret_cast<uintptr_t>(C) & 15))
+        return GAOT_E_ALIGN;
+    if (M > 0x7fffffffLL || N > 0x7fffffffLL || K > 0x7fffffffLL) return GAOT_E_BADARG;
+    TcArgs g{C, M, N, K, nullptr, nullptr, 1, 0, out_bf16, 1, 0, 0, 0};
+    cudaStream_t st = (cudaStream_t)stream;
+    if (N <= 64) return launch_tc<64, false, true>(A, B, g, st);
+    return launch_tc<128, false, true>(A, B, g, st);
 }
 
 GAOT_API int gaot_gemm_bf16_tn(const void* A, const void* B, float* C, int64_t M, int64_t N, int64_t R, int accumulate,
@@ -386,10 +450,10 @@ GAOT_API int gaot_gemm_bf16_tn(const void* A, const void* B, float* C, int64_t M
         (reinterpret_cast<uintptr_t>(C) & 15))
         return GAOT_E_ALIGN;                       // TMA: 16-byte aligned base and row pitch
     if (M > 0x7fffffffLL || N > 0x7fffffffLL || R > 0x7fffffffLL) return GAOT_E_BADARG;
-    TcArgs g{C, M, N, R, nullptr, nullptr, 1, 0, 0, 1, accumulate};
+    TcArgs g{C, M, N, R, nullptr, nullptr, 1, 0, 0, 1, accumulate, 0, 0};
     cudaStream_t st = (cudaStream_t)stream;
-    if (N <= 64) return launch_tc<64, true>(A, B, g, st);
-    return launch_tc<128, true>(A, B, g, st);
+    if (N <= 64) return launch_tc<64, true, true>(A, B, g, st);
+    return launch_tc<128, true, true>(A, B, g, st);
 }
 
 GAOT_API int gaot_cast_bf16(const float* in, void* out, int64_t rows, int64_t cols, void* out_t, void* stream) {

@@ -218,6 +218,13 @@ def gemm_bf16(A, B, M, N, K, out_bf16=False, bias=None, add=None, add_rows=0, ou
     return out
 
 
+def gemm_bf16_nn(A, B, M, N, K, out_bf16=False):
+    """C[M,N] = A[M,K] B[K,N] on the tensor cores (A, B bf16 row-major; B consumed MN-major)."""
+    out = torch.empty((M, N), dtype=torch.bfloat16 if out_bf16 else torch.float32, device=A.device)
+    call("gaot_gemm_bf16_nn", ptr(A), ptr(B), ptr(out), M, N, K, int(out_bf16))
+    return out
+
+
 def gemm_bf16_tn(A, B, M, N, R, out=None, accumulate=False):
     """C[M,N] (fp32) = A[R,M]^T B[R,N] on the tensor cores (A, B bf16 row-major, contraction over rows)."""
     if out is None:
@@ -245,24 +252,23 @@ class _LinearTC(torch.autograd.Function):
         xb = x if x.dtype == torch.bfloat16 else cast_bf16(_c(x))[0]
         wb, _ = cast_bf16(W)
         y = gemm_bf16(xb, wb, M, N, K, out_bf16=out_bf16, bias=bias_c, add=add_c, add_rows=add_rows)
-        ctx.save_for_backward(xb, W)
+        ctx.save_for_backward(xb, wb)
         ctx.has_bias, ctx.add_rows, ctx.x_bf16 = bias is not None, add_rows, x.dtype == torch.bfloat16
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        xb, W = ctx.saved_tensors
+        xb, wb = ctx.saved_tensors
         dy = dy if dy.is_contiguous() else dy.contiguous()
         M, K = xb.shape
-        N = W.shape[0]
+        N = wb.shape[0]
         dx = dW = db = dadd = None
         dyb = dy if dy.dtype == torch.bfloat16 else cast_bf16(dy)[0]
         if ctx.needs_input_grad[0]:
             if N % 8 == 0:
-                _, wT = cast_bf16(W, want=False, want_t=True)        # [K, N]
-                dx = gemm_bf16(dyb, wT, M, K, N, out_bf16=ctx.x_bf16)
+                dx = gemm_bf16_nn(dyb, wb, M, K, N, out_bf16=ctx.x_bf16)   # dY W, W read MN-major in its nn.Linear layout
             else:
-                dx = gemm(dy.float(), W, M, K, N, N, K, 0, 0)
+                dx = gemm(dy.float(), wb.float(), M, K, N, N, K, 0, 0)
                 dx = dx.to(torch.bfloat16) if ctx.x_bf16 else dx
         if ctx.needs_input_grad[1]:
             if N % 8 == 0:

@@ -156,6 +156,10 @@ int gaot_gemm_f32(const float* A, const float* B, float* C, int64_t M, int64_t N
 int gaot_gemm_bf16(const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K, int out_bf16,
                    const float* bias, const float* add, int64_t add_rows, int64_t ldadd, int accumulate,
                    void* stream);
+/* Input-gradient form: C[M,N] (fp32 or bf16) = A[M,K] B[K,N], B row-major [K,N] consumed MN-major in place
+ * (dX = dY W with W in nn.Linear layout).  K % 8 == 0, N % 8 == 0. */
+int gaot_gemm_bf16_nn(const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K, int out_bf16,
+                      void* stream);
 /* Weight-gradient form: C[M,N] (fp32) = A[R,M]^T B[R,N], A and B bf16 row-major with the contraction over
  * their R rows (dW = dY^T X): both operands are consumed MN-major straight from their natural layout.
  * M % 8 == 0, N % 8 == 0. */

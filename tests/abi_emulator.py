@@ -308,6 +308,14 @@ def gaot_swiglu_bwd_bf16(du, ab, dab, rows, F):
     _bf(dab, (rows, 2 * F))[:] = a.grad.to(torch.bfloat16)
 
 
+def gaot_gemm_bf16_nn(A, B, C, M, N, K, out_bf16):
+    v = _bf(A, (M, K)).double() @ _bf(B, (K, N)).double()
+    if out_bf16:
+        _bf(C, (M, N))[:] = v.to(torch.bfloat16)
+    else:
+        _t(C, (M, N))[:] = v.float()
+
+
 def gaot_gemm_bf16_tn(A, B, C, M, N, R, accumulate):
     v = _bf(A, (R, M)).double().T @ _bf(B, (R, N)).double()
     c = _t(C, (M, N))

@@ -155,3 +155,14 @@ def test_swiglu_bf16():
     got = ops.swiglu(b)
     got.backward(go.to(DEV))
     assert got.dtype == torch.bfloat16 and rel_l2(got, want) < 4e-3 and rel_l2(b.grad, a.grad) < 6e-3
+
+
+@pytest.mark.parametrize("M,N,K", [(32768, 256, 768), (4096, 1024, 256), (1000, 72, 136), (128, 64, 64)])
+def test_gemm_bf16_nn_vs_fp64(M, N, K):
+    """dX form: C = A B with B [K,N] row-major consumed as an MN-major tcgen05 operand."""
+    from gaot_b200 import ops
+    a = cases.normal((M, K), 51).to(DEV).to(torch.bfloat16)
+    b = (cases.normal((K, N), 52) / K ** 0.5).to(DEV).to(torch.bfloat16)
+    want = a.double() @ b.double()
+    assert rel_l2(ops.gemm_bf16_nn(a, b, M, N, K), want) < 2e-5
+    assert rel_l2(ops.gemm_bf16_nn(a, b, M, N, K, out_bf16=True), want) < 4e-3
