@@ -466,9 +466,11 @@ __global__ void swiglu_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ du, con
     }
 }
 
-__global__ void patch_permute_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t B, int dims,
+template <typename T>
+__global__ void patch_permute_kernel(const T* __restrict__ in, T* __restrict__ out, int64_t B, int dims,
                                      int64_t H, int64_t W, int64_t D, int64_t P, int64_t C, int to_tokens) {
-    // iterate over token-layout elements; channel fastest -> both sides move contiguous C-runs
+    // iterate over token-layout elements (T = float, or float4 with C counted in vectors); channel fastest ->
+    // both sides move contiguous C-runs
     const int64_t nodes = H * W * (dims == 3 ? D : 1);
     const int64_t total = B * nodes * C;
     const int64_t pw = W / P, pd = (dims == 3) ? D / P : 1;
@@ -665,7 +667,11 @@ GAOT_API int gaot_patch_permute(const float* in, float* out, int64_t B, int dims
     if (!in || !out || B < 1 || (dims != 2 && dims != 3) || P < 1 || C < 1) return GAOT_E_BADARG;
     if (H % P || W % P || (dims == 3 && D % P)) return GAOT_E_BADARG;
     const int64_t total = B * H * W * (dims == 3 ? D : 1) * C;
-    patch_permute_kernel<<<gaot_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(in, out, B, dims, H, W, D, P, C, to_tokens);
+    if (C % 4 == 0 && !(reinterpret_cast<uintptr_t>(in) & 15) && !(reinterpret_cast<uintptr_t>(out) & 15))
+        patch_permute_kernel<float4><<<gaot_grid(total / 4, 256), 256, 0, (cudaStream_t)stream>>>(
+            reinterpret_cast<const float4*>(in), reinterpret_cast<float4*>(out), B, dims, H, W, D, P, C / 4, to_tokens);
+    else
+        patch_permute_kernel<float><<<gaot_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(in, out, B, dims, H, W, D, P, C, to_tokens);
     GAOT_RETURN_LAST();
 }
 

@@ -13,6 +13,7 @@
 //               (or 128-bit red.add for split-K)
 //   3 stages x 32 KB leave room for two CTAs per SM, so one CTA's epilogue overlaps the other's main loop.
 #include <cuda.h>
+#include <cstdlib>
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -23,7 +24,7 @@ namespace {
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;          // 64 bf16 = 128 bytes = one SWIZZLE_128B row
 constexpr int TC_STAGES = 5;
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;        // TMA warp, MMA warp, 8 epilogue warps
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -81,6 +82,7 @@ struct TcArgs {
     const float* bias; const float* add; int64_t add_rows, ldadd;
     int out_bf16, splits, accumulate;
     int64_t gm, gn;                   // tile grid
+    int dbg;                          // GAOT_TC_DEBUG bit mask (performance experiments only; 0 in production)
 };
 
 // MN-major operand tile: [64 contraction rows][64 elements = 128 bytes] blocks of 8 KB, one per 64 output
@@ -104,7 +106,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     constexpr int A_BYTES = TC_BM * TC_BK * 2, B_BYTES = BN * TC_BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
     constexpr int PITCH = 36;                                      // epilogue staging: floats per row (16-byte aligned)
     float* stg_all = reinterpret_cast<float*>(smem + TC_STAGES * STAGE_BYTES);
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(stg_all + 4 * 32 * PITCH);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(stg_all + 8 * 32 * PITCH);
     uint64_t* empty_bar = full_bar + TC_STAGES;
     uint64_t* acc_full = empty_bar + TC_STAGES;                    // [2]
     uint64_t* acc_empty = acc_full + 2;                            // [2]
@@ -117,7 +119,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -152,10 +154,11 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 for (int i = 0; i < nkb; ++i, ++it) {
                     const int s = (int)(it % TC_STAGES);
                     mbar_wait(&empty_bar[s], ((it / TC_STAGES) & 1u) ^ 1u);
-                    mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+                    mbar_expect_tx(&full_bar[s], (g.dbg & 4) ? B_BYTES : STAGE_BYTES);
                     uint8_t* st = smem + s * STAGE_BYTES;
                     const int kc = (int)((kb0 + i) * TC_BK);
-                    if (!AMN) tma_load_2d(st, &tmA, &full_bar[s], kc, (int)m0);
+                    if (g.dbg & 4) {}
+                    else if (!AMN) tma_load_2d(st, &tmA, &full_bar[s], kc, (int)m0);
                     else {
 #pragma unroll
                         for (int j = 0; j < TC_BM / 64; ++j) tma_load_2d(st + j * 8192, &tmA, &full_bar[s], (int)m0 + 64 * j, kc);
@@ -188,7 +191,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 if (lane == 0) {
                     const uint32_t sa = smem_u32(smem + s * STAGE_BYTES), sb = sa + A_BYTES;
 #pragma unroll
-                    for (int k = 0; k < TC_BK / 16; ++k) {
+                    for (int k = 0; k < ((g.dbg & 2) ? 1 : TC_BK / 16); ++k) {
                         // K-major: +32 bytes per K=16 step inside the 128-byte swizzle row; MN-major: 16 rows = 2048 bytes
                         const uint64_t da = AMN ? make_smem_desc_mn(sa + k * 2048) : make_smem_desc_sw128(sa) + (uint64_t)(2 * k);
                         const uint64_t db = BMN ? make_smem_desc_mn(sb + k * 2048) : make_smem_desc_sw128(sb) + (uint64_t)(2 * k);
@@ -201,13 +204,16 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
         }
     } else {
-        // ---------------- epilogue (warps 2..5; warp w may touch TMEM lanes 32*(w%4) .. +31) ----------------
-        // TMEM hands each thread one accumulator ROW; a per-warp 32x32 staging tile turns that into
-        // row-contiguous 128-byte global accesses: lane -> (row it*4 + lane/8, 4 columns (lane%8)*4).
-        const int q = warp & 3;
-        float* stg = stg_all + q * (32 * PITCH);
+        // ---------------- epilogue (8 warps; warp w may touch TMEM lanes 32*(w%4) .. +31) ----------------
+        // TMEM hands each thread one accumulator ROW.  A per-warp 32x32 fp32 staging tile turns that into
+        // row-contiguous global accesses: lane -> (row it*4 + lane/8, 4 columns (lane%8)*4), i.e. each store
+        // instruction writes 4 rows x 128 bytes (fp32) / 64 bytes (bf16).  Two warps share a lane quadrant and
+        // split the BN columns.  Row offsets are hoisted out of the column loop; the store loops are specialised.
+        const int q = warp & 3, half = (warp - 2) >> 2;
+        float* stg = stg_all + (warp - 2) * (32 * PITCH);
         const bool vec_ok = (g.N % 4 == 0) && (!g.add || (g.ldadd % 4 == 0));
         const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
+        const bool atomic = g.splits > 1 || g.accumulate;
         uint32_t lt = 0;
         for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++lt) {
             int64_t m0, n0, kb0; int nkb;
@@ -218,9 +224,19 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             }
             const bool first = kb0 == 0;
+            const float* bias = first ? g.bias : nullptr;
+            const float* add = first ? g.add : nullptr;
             const uint32_t tmem_acc = tmem_base + ab * BN + ((uint32_t)(q * 32) << 16);
+            // per-lane row bookkeeping for the 8 store iterations (rows do not depend on the column chunk)
+            int64_t coff[8], aoff[8];
+#pragma unroll
+            for (int it8 = 0; it8 < 8; ++it8) {
+                const int64_t m = m0 + q * 32 + it8 * 4 + sub_r;
+                coff[it8] = (m < g.M) ? m * g.N : -1;
+                aoff[it8] = (add && m < g.M) ? (m % g.add_rows) * g.ldadd : 0;
+            }
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
+            for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
                 uint32_t r[32];
                 if (nkb > 0) tmem_ld32(tmem_acc + (uint32_t)c0, r);
                 else {
@@ -228,49 +244,65 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     for (int j = 0; j < 32; ++j) r[j] = 0u;
                 }
                 const int64_t n = n0 + c0;
-                if (n >= g.N) continue;                            // warp-uniform
+                if (n >= g.N || (g.dbg & 1)) continue;             // warp-uniform
                 __syncwarp();
 #pragma unroll
                 for (int j = 0; j < 32; j += 4)
                     *reinterpret_cast<float4*>(stg + lane * PITCH + j) =
                         make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
                 __syncwarp();
-                const bool full = (n + 32 <= g.N) && vec_ok;
-#pragma unroll 2
-                for (int it8 = 0; it8 < 8; ++it8) {
-                    const int rr = it8 * 4 + sub_r;
-                    const int64_t m = m0 + q * 32 + rr;
-                    if (m >= g.M) continue;
-                    float4 v = *reinterpret_cast<const float4*>(stg + rr * PITCH + sub_c);
-                    const int64_t nc = n + sub_c;
-                    if (full) {
-                        if (first && g.bias) {
-                            const float4 bv = __ldg(reinterpret_cast<const float4*>(g.bias + nc));
-                            v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
-                        }
-                        if (first && g.add) {
-                            const float4 av = __ldg(reinterpret_cast<const float4*>(g.add + (m % g.add_rows) * g.ldadd + nc));
-                            v.x += av.x; v.y += av.y; v.z += av.z; v.w += av.w;
-                        }
-                        if (g.out_bf16) {
-                            __nv_bfloat162 t0 = __floats2bfloat162_rn(v.x, v.y), t1 = __floats2bfloat162_rn(v.z, v.w);
+                const int64_t nc = n + sub_c;
+                if ((n + 32 <= g.N) && vec_ok) {
+                    float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (bias) bv = __ldg(reinterpret_cast<const float4*>(bias + nc));
+                    float4 v[8];
+#pragma unroll
+                    for (int it8 = 0; it8 < 8; ++it8) {
+                        v[it8] = *reinterpret_cast<const float4*>(stg + (it8 * 4 + sub_r) * PITCH + sub_c);
+                        v[it8].x += bv.x; v[it8].y += bv.y; v[it8].z += bv.z; v[it8].w += bv.w;
+                    }
+                    if (add) {
+                        float4 av[8];
+#pragma unroll
+                        for (int it8 = 0; it8 < 8; ++it8)
+                            av[it8] = (coff[it8] >= 0) ? __ldg(reinterpret_cast<const float4*>(add + aoff[it8] + nc)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                        for (int it8 = 0; it8 < 8; ++it8) { v[it8].x += av[it8].x; v[it8].y += av[it8].y; v[it8].z += av[it8].z; v[it8].w += av[it8].w; }
+                    }
+                    if (g.out_bf16) {
+                        __nv_bfloat16* cb = reinterpret_cast<__nv_bfloat16*>(g.C) + nc;
+#pragma unroll
+                        for (int it8 = 0; it8 < 8; ++it8) {
+                            if (coff[it8] < 0) continue;
+                            __nv_bfloat162 t0 = __floats2bfloat162_rn(v[it8].x, v[it8].y), t1 = __floats2bfloat162_rn(v[it8].z, v[it8].w);
                             uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
-                            *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(g.C) + m * g.N + nc) = pk;
-                        } else {
-                            float* cp = reinterpret_cast<float*>(g.C) + m * g.N + nc;
-                            if (g.splits > 1 || g.accumulate) atomicAdd(reinterpret_cast<float4*>(cp), v);
-                            else *reinterpret_cast<float4*>(cp) = v;
+                            *reinterpret_cast<uint2*>(cb + coff[it8]) = pk;
                         }
+                    } else if (atomic) {
+                        float* cf = reinterpret_cast<float*>(g.C) + nc;
+#pragma unroll
+                        for (int it8 = 0; it8 < 8; ++it8)
+                            if (coff[it8] >= 0) atomicAdd(reinterpret_cast<float4*>(cf + coff[it8]), v[it8]);
                     } else {
-                        float vv[4] = {v.x, v.y, v.z, v.w};
+                        float* cf = reinterpret_cast<float*>(g.C) + nc;
+#pragma unroll
+                        for (int it8 = 0; it8 < 8; ++it8)
+                            if (coff[it8] >= 0) *reinterpret_cast<float4*>(cf + coff[it8]) = v[it8];
+                    }
+                } else {                                           // ragged N / unaligned: scalar, guarded
+#pragma unroll 1
+                    for (int it8 = 0; it8 < 8; ++it8) {
+                        if (coff[it8] < 0) continue;
+                        const float4 v4 = *reinterpret_cast<const float4*>(stg + (it8 * 4 + sub_r) * PITCH + sub_c);
+                        const float vv[4] = {v4.x, v4.y, v4.z, v4.w};
                         for (int j = 0; j < 4; ++j) {
                             if (nc + j >= g.N) break;
                             float x = vv[j];
-                            if (first && g.bias) x += __ldg(g.bias + nc + j);
-                            if (first && g.add) x += __ldg(g.add + (m % g.add_rows) * g.ldadd + nc + j);
-                            if (g.out_bf16) reinterpret_cast<__nv_bfloat16*>(g.C)[m * g.N + nc + j] = __float2bfloat16_rn(x);
-                            else if (g.splits > 1 || g.accumulate) atomicAdd(reinterpret_cast<float*>(g.C) + m * g.N + nc + j, x);
-                            else reinterpret_cast<float*>(g.C)[m * g.N + nc + j] = x;
+                            if (bias) x += __ldg(bias + nc + j);
+                            if (add) x += __ldg(add + aoff[it8] + nc + j);
+                            if (g.out_bf16) reinterpret_cast<__nv_bfloat16*>(g.C)[coff[it8] + nc + j] = __float2bfloat16_rn(x);
+                            else if (atomic) atomicAdd(reinterpret_cast<float*>(g.C) + coff[it8] + nc + j, x);
+                            else reinterpret_cast<float*>(g.C)[coff[it8] + nc + j] = x;
                         }
                     }
                 }
@@ -383,6 +415,9 @@ int launch_tc(const void* A, const void* B, TcArgs& g, cudaStream_t st) {
     if (rc) return rc;
     rc = BMN ? make_map_mn(&tb, B, g.K, g.N) : make_map(&tb, B, g.N, g.K, BN);
     if (rc) return rc;
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("GAOT_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
+    g.dbg = dbg;
     g.gm = (g.M + TC_BM - 1) / TC_BM;
     g.gn = (g.N + BN - 1) / BN;
     const int64_t kblocks = (g.K + TC_BK - 1) / TC_BK, tiles = g.gm * g.gn;
@@ -400,7 +435,7 @@ int launch_tc(const void* A, const void* B, TcArgs& g, cudaStream_t st) {
     }
     g.splits = splits;
     if (splits > 1 && !g.accumulate) GAOT_CHECK(cudaMemsetAsync(g.C, 0, sizeof(float) * (size_t)(g.M * g.N), st));
-    constexpr int SMEM = TC_STAGES * (TC_BM * TC_BK * 2 + BN * TC_BK * 2) + 4 * 32 * 36 * 4 + 1024 + 256;
+    constexpr int SMEM = TC_STAGES * (TC_BM * TC_BK * 2 + BN * TC_BK * 2) + 8 * 32 * 36 * 4 + 1024 + 256;
     static bool attr_done = false;
     if (!attr_done) {
         GAOT_CHECK(cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN, AMN, BMN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
@@ -424,7 +459,7 @@ GAOT_API int gaot_gemm_bf16(const void* A, const void* B, void* C, int64_t M, in
     if (add && (add_rows < 1 || ldadd < N)) return GAOT_E_BADARG;
     if (out_bf16 && accumulate) return GAOT_E_BADARG;
     if (M > 0x7fffffffLL || N > 0x7fffffffLL || K > 0x7fffffffLL) return GAOT_E_BADARG;
-    TcArgs g{C, M, N, K, bias, add, add ? add_rows : 1, ldadd, out_bf16, 1, accumulate, 0, 0};
+    TcArgs g{C, M, N, K, bias, add, add ? add_rows : 1, ldadd, out_bf16, 1, accumulate, 0, 0, 0};
     cudaStream_t st = (cudaStream_t)stream;
     if (N <= 64) return launch_tc<64, false, false>(A, B, g, st);
     return launch_tc<128, false, false>(A, B, g, st);
@@ -437,7 +472,7 @@ GAOT_API int gaot_gemm_bf16_nn(const void* A, const void* B, void* C, int64_t M,
         (reinterpret_cast<uintptr_t>(C) & 15))
         return GAOT_E_ALIGN;
     if (M > 0x7fffffffLL || N > 0x7fffffffLL || K > 0x7fffffffLL) return GAOT_E_BADARG;
-    TcArgs g{C, M, N, K, nullptr, nullptr, 1, 0, out_bf16, 1, 0, 0, 0};
+    TcArgs g{C, M, N, K, nullptr, nullptr, 1, 0, out_bf16, 1, 0, 0, 0, 0};
     cudaStream_t st = (cudaStream_t)stream;
     if (N <= 64) return launch_tc<64, false, true>(A, B, g, st);
     return launch_tc<128, false, true>(A, B, g, st);
@@ -450,7 +485,7 @@ GAOT_API int gaot_gemm_bf16_tn(const void* A, const void* B, float* C, int64_t M
         (reinterpret_cast<uintptr_t>(C) & 15))
         return GAOT_E_ALIGN;                       // TMA: 16-byte aligned base and row pitch
     if (M > 0x7fffffffLL || N > 0x7fffffffLL || R > 0x7fffffffLL) return GAOT_E_BADARG;
-    TcArgs g{C, M, N, R, nullptr, nullptr, 1, 0, 0, 1, accumulate, 0, 0};
+    TcArgs g{C, M, N, R, nullptr, nullptr, 1, 0, 0, 1, accumulate, 0, 0, 0};
     cudaStream_t st = (cudaStream_t)stream;
     if (N <= 64) return launch_tc<64, true, true>(A, B, g, st);
     return launch_tc<128, true, true>(A, B, g, st);

@@ -142,7 +142,8 @@ class _MAGNOBase(nn.Module):
             g = self.geoembed.embed(feat)                                # [m, C], batch independent
             W = self.recovery.fcs[0].weight[:, :, 0]                     # [C, 2C]: cat[agno, geo] (magno.py:346-350)
             gterm = ops.linear(g, W[:, C:], self.recovery.fcs[0].bias)   # batch-independent half of the recovery
-            out = ops.linear(out.view(-1, C), W[:, :C], None, add=gterm).view(out.shape)
+            # [B*m, C] x [C, C]: the one big dense layer of MAGNO; tensor cores in bf16 mode, FFMA in fp32 mode
+            out = ops.linear(out.view(-1, C), W[:, :C], None, add=gterm, tc=True).view(out.shape)
         return out
 
     def _combine(self, outs, weight_coords):

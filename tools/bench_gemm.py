@@ -1,0 +1,27 @@
+"""Micro-benchmark of the tcgen05 GEMM at the processor's shapes (GPU box).  GAOT_TC_DEBUG=1|2|4 switch off the
+epilogue stores / three quarters of the MMAs / the A-operand loads to locate the bottleneck."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+from gaot_b200 import ops  # noqa: E402
+
+dev = "cuda"
+shapes = [(32768, 2048, 256, True), (32768, 768, 256, True), (32768, 256, 1024, False), (32768, 256, 256, False)]
+for M, N, K, o16 in shapes:
+    a = torch.randn(M, K, device=dev).to(torch.bfloat16)
+    b = torch.randn(N, K, device=dev).to(torch.bfloat16)
+    for _ in range(3):
+        ops.gemm_bf16(a, b, M, N, K, out_bf16=o16)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(20):
+        ops.gemm_bf16(a, b, M, N, K, out_bf16=o16)
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) / 20 * 1e3
+    print(f"dbg={os.environ.get('GAOT_TC_DEBUG', '0')} M={M} N={N} K={K} out_bf16={o16}: {us:.1f} us  {2.0 * M * N * K / us / 1e6:.0f} TFLOP/s")
