@@ -21,6 +21,7 @@
 namespace {
 
 constexpr int AT_THREADS = 192;
+constexpr int AT_BWD_THREADS = 320;      // TMA warp, MMA warp, 8 compute warps (2 per TMEM lane quadrant)
 constexpr int AT_BQ = 128, AT_BKV = 128;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -90,6 +91,12 @@ __device__ __forceinline__ float ex2(float x) {          // single MUFU.EX2 (ex2
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&t);
@@ -137,7 +144,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttnArgs g) {
     if (threadIdx.x == 0) {
         mbar_init(q_bar, 1);
         for (int s = 0; s < 2; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
-        mbar_init(s_full, 1); mbar_init(p_full, 128); mbar_init(o_full, 1);
+        mbar_init(s_full, 1); mbar_init(p_full, 4); mbar_init(o_full, 1);    // p_full: one arrival per softmax warp
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -261,7 +268,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttnArgs g) {
             mrun = mnew;
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes of P -> async proxy (MMA)
-            mbar_arrive(p_full);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(p_full);
             mbar_wait(o_full, (uint32_t)i & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
@@ -312,7 +320,7 @@ struct AttnBwdArgs {
 };
 
 template <int HD>
-__global__ void __launch_bounds__(AT_THREADS)
+__global__ void __launch_bounds__(AT_BWD_THREADS)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUtensorMap tmdo, const AttnBwdArgs g) {
     constexpr int ROWB = HD * 2;
     constexpr int TILE_BYTES = 128 * ROWB;
@@ -349,7 +357,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
     if (threadIdx.x == 0) {
         mbar_init(kv_bar, 1);
         for (int s = 0; s < 2; ++s) { mbar_init(&q_full[s], 1); mbar_init(&q_empty[s], 1); }
-        mbar_init(st_full, 1); mbar_init(pds_full, 128); mbar_init(dq_full, 1); mbar_init(dq_empty, 128); mbar_init(fin_bar, 1);
+        mbar_init(st_full, 1); mbar_init(pds_full, 8); mbar_init(dq_full, 1); mbar_init(dq_empty, 8); mbar_init(fin_bar, 1);   // pds_full / dq_empty: one arrival per compute warp
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -429,25 +437,36 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
             if (i + 1 < n_steps) issue_st(i + 1);
         }
     } else {
-        const int q4 = warp & 3;
+        // 8 compute warps: warps w and w+4 share TMEM lane quadrant w%4 (the hardware restricts a warp to the lanes
+        // 32*(w%4)..+31) and split the columns: `half` 0/1 owns query columns [64*half, 64*half+64) of S^T / dP^T
+        // (= one 64-column swizzle block of the P^T / dS^T tiles) and half of the dQ / dV / dK columns.
+        const int q4 = warp & 3, half = (warp - 2) >> 2;
         const int r = q4 * 32 + lane;                      // key row for S^T.., query row for dQ
         const uint32_t lane_addr = (uint32_t)(q4 * 32) << 16;
         const bool key_ok = k0 + r < g.T;
-        const int ct = threadIdx.x - 64;                   // 0..127
+        const int ct = threadIdx.x - 64;                   // 0..255
+        // per-query statistics (base-2 lse for threads < 128, delta for the rest) are fetched one step ahead so
+        // their global-load latency is off the step's critical path
+        auto fetch_stat = [&](int i) -> float {
+            const int h = hk * rep + i / n_qt, q0 = (i % n_qt) * 128, cq = ct & 127;
+            const bool ok = q0 + cq < g.T;
+            const int64_t off = ((int64_t)b * g.H + h) * g.T + q0 + cq;
+            if (ct < 128) return ok ? __ldg(g.lse + off) * 1.4426950408889634f : INFINITY;   // +inf switches a query column off
+            return ok ? __ldg(g.delta + off) : 0.f;
+        };
+        float stat_next = n_steps > 0 ? fetch_stat(0) : 0.f;
         for (int i = 0; i < n_steps; ++i) {
             const int s = i & 1, h = hk * rep + i / n_qt, q0 = (i % n_qt) * 128;
-            // stage this step's per-query statistics (base-2 lse, delta); +inf lse switches a query column off
             {
-                const bool ok = q0 + ct < g.T;
-                const int64_t off = ((int64_t)b * g.H + h) * g.T + q0 + ct;
-                sLse[s * 128 + ct] = ok ? g.lse[off] * 1.4426950408889634f : INFINITY;
-                sDel[s * 128 + ct] = ok ? g.delta[off] : 0.f;
+                const int cq = ct & 127;
+                if (ct < 128) sLse[s * 128 + cq] = stat_next; else sDel[s * 128 + cq] = stat_next;
+                if (i + 1 < n_steps) stat_next = fetch_stat(i + 1);
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, 256;" ::: "memory");
             mbar_wait(st_full, (uint32_t)i & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 2 * half; c < 2 * half + 2; ++c) {
                 uint32_t sv[32], dv[32];
                 tmem_ld32(tm_st + lane_addr + c * 32, sv);
                 tmem_ld32(tm_dp + lane_addr + c * 32, dv);
@@ -478,7 +497,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mbar_arrive(pds_full);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(pds_full);
             // drain dQ: here the TMEM lane is the QUERY row
             mbar_wait(dq_full, (uint32_t)i & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -486,20 +506,22 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
                 const int t = q0 + r;
                 float* dst = g.dq_acc + ((int64_t)(row_base + t) * g.H + h) * HD;
 #pragma unroll
-                for (int c = 0; c < HD / 16; ++c) {
-                    uint32_t v[16];
-                    tmem_ld16(tm_dq + lane_addr + c * 16, v);
+                for (int c = 0; c < HD / 16; ++c) {           // this warp's half of the HD columns, 8 at a time
+                    const int col = half * (HD / 2) + c * 8;
+                    uint32_t v[8];
+                    tmem_ld8(tm_dq + lane_addr + col, v);
                     if (t < g.T) {
 #pragma unroll
-                        for (int j = 0; j < 16; j += 4)
-                            atomicAdd(reinterpret_cast<float4*>(dst + c * 16 + j),
+                        for (int j = 0; j < 8; j += 4)
+                            atomicAdd(reinterpret_cast<float4*>(dst + col + j),
                                       make_float4(__uint_as_float(v[j]) * g.scale, __uint_as_float(v[j + 1]) * g.scale,
                                                   __uint_as_float(v[j + 2]) * g.scale, __uint_as_float(v[j + 3]) * g.scale));
                     }
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            mbar_arrive(dq_empty);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(dq_empty);
         }
         // final: dV and dK rows of this key tile
         mbar_wait(fin_bar, 0);
@@ -508,23 +530,19 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
             __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(g.dqkv) + (int64_t)(row_base + k0 + r) * g.ld;
 #pragma unroll
             for (int c = 0; c < HD / 16; ++c) {
-                uint32_t vv[16], vk[16];
-                tmem_ld16(tm_dv + lane_addr + c * 16, vv);
-                tmem_ld16(tm_dk + lane_addr + c * 16, vk);
+                const int col = half * (HD / 2) + c * 8;
+                uint32_t vv[8], vk[8];
+                tmem_ld8(tm_dv + lane_addr + col, vv);
+                tmem_ld8(tm_dk + lane_addr + col, vk);
                 if (key_ok) {
-                    __nv_bfloat16* pv = base + g.voff + hk * HD + c * 16;
-                    __nv_bfloat16* pk = base + g.koff + hk * HD + c * 16;
-#pragma unroll
-                    for (int j = 0; j < 16; j += 8) {
-                        *reinterpret_cast<uint4*>(pv + j) = make_uint4(
-                            pack_bf16(__uint_as_float(vv[j]), __uint_as_float(vv[j + 1])), pack_bf16(__uint_as_float(vv[j + 2]), __uint_as_float(vv[j + 3])),
-                            pack_bf16(__uint_as_float(vv[j + 4]), __uint_as_float(vv[j + 5])), pack_bf16(__uint_as_float(vv[j + 6]), __uint_as_float(vv[j + 7])));
-                        *reinterpret_cast<uint4*>(pk + j) = make_uint4(
-                            pack_bf16(__uint_as_float(vk[j]) * g.scale, __uint_as_float(vk[j + 1]) * g.scale),
-                            pack_bf16(__uint_as_float(vk[j + 2]) * g.scale, __uint_as_float(vk[j + 3]) * g.scale),
-                            pack_bf16(__uint_as_float(vk[j + 4]) * g.scale, __uint_as_float(vk[j + 5]) * g.scale),
-                            pack_bf16(__uint_as_float(vk[j + 6]) * g.scale, __uint_as_float(vk[j + 7]) * g.scale));
-                    }
+                    *reinterpret_cast<uint4*>(base + g.voff + hk * HD + col) = make_uint4(
+                        pack_bf16(__uint_as_float(vv[0]), __uint_as_float(vv[1])), pack_bf16(__uint_as_float(vv[2]), __uint_as_float(vv[3])),
+                        pack_bf16(__uint_as_float(vv[4]), __uint_as_float(vv[5])), pack_bf16(__uint_as_float(vv[6]), __uint_as_float(vv[7])));
+                    *reinterpret_cast<uint4*>(base + g.koff + hk * HD + col) = make_uint4(
+                        pack_bf16(__uint_as_float(vk[0]) * g.scale, __uint_as_float(vk[1]) * g.scale),
+                        pack_bf16(__uint_as_float(vk[2]) * g.scale, __uint_as_float(vk[3]) * g.scale),
+                        pack_bf16(__uint_as_float(vk[4]) * g.scale, __uint_as_float(vk[5]) * g.scale),
+                        pack_bf16(__uint_as_float(vk[6]) * g.scale, __uint_as_float(vk[7]) * g.scale));
                 }
             }
         }
@@ -652,7 +670,7 @@ int launch_bwd(const CUtensorMap& tm, const CUtensorMap& tmdo, const AttnBwdArgs
                                                                      reinterpret_cast<const __nv_bfloat16*>(dout), delta, B, g.T, g.H);
     GAOT_CHECK(cudaMemsetAsync(g.dq_acc, 0, sizeof(float) * (size_t)(rows * g.H * HD), st));
     dim3 grid((unsigned)((g.T + 127) / 128), (unsigned)g.Hkv, (unsigned)B);
-    attn_bwd_tc_kernel<HD><<<grid, AT_THREADS, SMEM, st>>>(tm, tmdo, g);
+    attn_bwd_tc_kernel<HD><<<grid, AT_BWD_THREADS, SMEM, st>>>(tm, tmdo, g);
     attn_dq_store_kernel<<<gaot_grid(rows * g.H * HD / 4, 256), 256, 0, st>>>(g.dq_acc, reinterpret_cast<__nv_bfloat16*>(g.dqkv), rows,
                                                                             g.H * HD, g.ld);
     GAOT_NOTE_LAUNCHES(2);
