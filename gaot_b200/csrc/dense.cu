@@ -194,6 +194,159 @@ int launch_gemm(GemmArgs& g, cudaStream_t st) {
     GAOT_RETURN_LAST();
 }
 
+// ------------------------------------------------------------------------------------------------
+// Narrow GEMMs (both small dimensions <= 64): the MAGNO kernel MLP (reference mlp.py:329-337 on E edge
+// rows, hidden 64), the geometry-embedding MLP and their backward.  A 128x64 smem-tiled GEMM is
+// latency bound at K = 64; here the 64x64 weight block lives in REGISTERS (lane l owns output columns
+// l and l+32 -> 2 x 64 weights), a warp streams rows four at a time through a 1 KB smem staging slab
+// that is read back with broadcast 128-bit loads (1 LDS per 8 FFMA), so the kernel is FFMA bound.
+//   ROWS mode:  C[r, n] = act( sum_k A[r,k] * Wt(k,n) + bias[n] + add[r % R, n] )   r over M rows
+//               (forward: Wt(k,n) = B[n*ldb+k]; input gradient: Wt(k,n) = B[k*ldb+n])
+//   RED  mode:  C[m, n] = sum_r A[r,m] * B[r,n]     (weight gradient; lane owns rows m = l, l+32 of C,
+//               64 accumulators each; warps reduce through fp32 atomics into the zeroed C)
+// ------------------------------------------------------------------------------------------------
+constexpr int NW_THREADS = 256;
+constexpr int NW_ROWS = 4;               // rows in flight per warp
+
+template <bool BT>
+__global__ void __launch_bounds__(NW_THREADS, 1) narrow_rows_kernel(const GemmArgs g) {
+    __shared__ __align__(16) float slab[NW_THREADS / 32][NW_ROWS][64];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int K = (int)g.K, N = (int)g.N;
+    const int n0 = lane, n1 = lane + 32;
+    float w0[64], w1[64];
+#pragma unroll
+    for (int k = 0; k < 64; ++k) {
+        w0[k] = (k < K && n0 < N) ? __ldg(BT ? g.B + (int64_t)n0 * g.ldb + k : g.B + (int64_t)k * g.ldb + n0) : 0.f;
+        w1[k] = (k < K && n1 < N) ? __ldg(BT ? g.B + (int64_t)n1 * g.ldb + k : g.B + (int64_t)k * g.ldb + n1) : 0.f;
+    }
+    const float b0 = (g.bias && n0 < N) ? __ldg(g.bias + n0) : 0.f, b1 = (g.bias && n1 < N) ? __ldg(g.bias + n1) : 0.f;
+    float (*my)[64] = slab[warp];
+    const int kc_n = (K + 3) >> 2;
+    const int64_t gw = (int64_t)blockIdx.x * (NW_THREADS / 32) + warp, nw = (int64_t)gridDim.x * (NW_THREADS / 32);
+    for (int64_t r0 = gw * NW_ROWS; r0 < g.M; r0 += nw * NW_ROWS) {
+        __syncwarp();
+#pragma unroll
+        for (int rr = 0; rr < NW_ROWS; ++rr) {
+            const int64_t r = min(r0 + rr, g.M - 1);
+            const float* ap = g.A + r * g.lda;
+            my[rr][lane] = (lane < K) ? __ldg(ap + lane) : 0.f;
+            my[rr][lane + 32] = (lane + 32 < K) ? __ldg(ap + lane + 32) : 0.f;
+        }
+        __syncwarp();
+        float acc0[NW_ROWS], acc1[NW_ROWS];
+#pragma unroll
+        for (int rr = 0; rr < NW_ROWS; ++rr) { acc0[rr] = b0; acc1[rr] = b1; }
+#pragma unroll
+        for (int kc = 0; kc < 16; ++kc) {
+            if (kc < kc_n) {                             // warp-uniform
+#pragma unroll
+                for (int rr = 0; rr < NW_ROWS; ++rr) {
+                    const float4 x = *reinterpret_cast<const float4*>(&my[rr][kc * 4]);
+                    acc0[rr] = fmaf(x.x, w0[kc * 4 + 0], acc0[rr]); acc1[rr] = fmaf(x.x, w1[kc * 4 + 0], acc1[rr]);
+                    acc0[rr] = fmaf(x.y, w0[kc * 4 + 1], acc0[rr]); acc1[rr] = fmaf(x.y, w1[kc * 4 + 1], acc1[rr]);
+                    acc0[rr] = fmaf(x.z, w0[kc * 4 + 2], acc0[rr]); acc1[rr] = fmaf(x.z, w1[kc * 4 + 2], acc1[rr]);
+                    acc0[rr] = fmaf(x.w, w0[kc * 4 + 3], acc0[rr]); acc1[rr] = fmaf(x.w, w1[kc * 4 + 3], acc1[rr]);
+                }
+            }
+        }
+#pragma unroll
+        for (int rr = 0; rr < NW_ROWS; ++rr) {
+            const int64_t r = r0 + rr;
+            if (r >= g.M) break;
+            float v0 = acc0[rr], v1 = acc1[rr];
+            if (g.add) {
+                const float* ar = g.add + (r % g.add_rows) * g.ldadd;
+                if (n0 < N) v0 += __ldg(ar + n0);
+                if (n1 < N) v1 += __ldg(ar + n1);
+            }
+            if (g.pre) {
+                if (n0 < N) g.pre[r * g.ldc + n0] = v0;
+                if (n1 < N) g.pre[r * g.ldc + n1] = v1;
+            }
+            v0 = apply_act(v0, g.act); v1 = apply_act(v1, g.act);
+            float* cp = g.C + r * g.ldc;
+            if (n0 < N) cp[n0] = g.accumulate ? cp[n0] + v0 : v0;
+            if (n1 < N) cp[n1] = g.accumulate ? cp[n1] + v1 : v1;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(NW_THREADS, 1) narrow_reduce_kernel(const GemmArgs g) {
+    // C[m,n] (+)= sum_r A[r*lda + m] * B[r*ldb + n],  m < M <= 64, n < N <= 64, r < K (the long dimension)
+    __shared__ __align__(16) float slab[NW_THREADS / 32][NW_ROWS][64];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int M = (int)g.M, N = (int)g.N;
+    const int m0 = lane, m1 = lane + 32;
+    float c0[64], c1[64];
+#pragma unroll
+    for (int n = 0; n < 64; ++n) { c0[n] = 0.f; c1[n] = 0.f; }
+    float (*my)[64] = slab[warp];
+    const int nc_n = (N + 3) >> 2;
+    const int64_t gw = (int64_t)blockIdx.x * (NW_THREADS / 32) + warp, nw = (int64_t)gridDim.x * (NW_THREADS / 32);
+    for (int64_t r0 = gw * NW_ROWS; r0 < g.K; r0 += nw * NW_ROWS) {
+        float a0[NW_ROWS], a1[NW_ROWS];
+        __syncwarp();
+#pragma unroll
+        for (int rr = 0; rr < NW_ROWS; ++rr) {
+            const bool ok = r0 + rr < g.K;
+            const int64_t r = ok ? r0 + rr : g.K - 1;
+            const float* bp = g.B + r * g.ldb;
+            my[rr][lane] = (ok && lane < N) ? __ldg(bp + lane) : 0.f;
+            my[rr][lane + 32] = (ok && lane + 32 < N) ? __ldg(bp + lane + 32) : 0.f;
+            a0[rr] = (ok && m0 < M) ? __ldg(g.A + r * g.lda + m0) : 0.f;
+            a1[rr] = (ok && m1 < M) ? __ldg(g.A + r * g.lda + m1) : 0.f;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int nc = 0; nc < 16; ++nc) {
+            if (nc < nc_n) {
+#pragma unroll
+                for (int rr = 0; rr < NW_ROWS; ++rr) {
+                    const float4 x = *reinterpret_cast<const float4*>(&my[rr][nc * 4]);
+                    c0[nc * 4 + 0] = fmaf(a0[rr], x.x, c0[nc * 4 + 0]); c1[nc * 4 + 0] = fmaf(a1[rr], x.x, c1[nc * 4 + 0]);
+                    c0[nc * 4 + 1] = fmaf(a0[rr], x.y, c0[nc * 4 + 1]); c1[nc * 4 + 1] = fmaf(a1[rr], x.y, c1[nc * 4 + 1]);
+                    c0[nc * 4 + 2] = fmaf(a0[rr], x.z, c0[nc * 4 + 2]); c1[nc * 4 + 2] = fmaf(a1[rr], x.z, c1[nc * 4 + 2]);
+                    c0[nc * 4 + 3] = fmaf(a0[rr], x.w, c0[nc * 4 + 3]); c1[nc * 4 + 3] = fmaf(a1[rr], x.w, c1[nc * 4 + 3]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int n = 0; n < 64; ++n) {
+        if (n < N) {
+            if (m0 < M) atomicAdd(g.C + (int64_t)m0 * g.ldc + n, c0[n]);
+            if (m1 < M) atomicAdd(g.C + (int64_t)m1 * g.ldc + n, c1[n]);
+        }
+    }
+}
+
+int launch_narrow(GemmArgs& g, cudaStream_t st) {
+    // returns 1 when the shape is not handled here
+    const bool rows_mode = !g.transA && g.N <= 64 && g.K <= 64 && g.M >= 2048;
+    const bool red_mode = g.transA && !g.transB && g.M <= 64 && g.N <= 64 && g.K >= 2048 && g.act == GAOT_ACT_NONE && !g.pre &&
+                          !g.bias && !g.add;
+    if (!rows_mode && !red_mode) return 1;
+    const int warps = NW_THREADS / 32;
+    if (rows_mode) {
+        int64_t ctas = (g.M + warps * NW_ROWS - 1) / (warps * NW_ROWS);
+        if (ctas > 148 * 4) ctas = 148 * 4;
+        if (g.transB) narrow_rows_kernel<true><<<(unsigned)ctas, NW_THREADS, 0, st>>>(g);
+        else narrow_rows_kernel<false><<<(unsigned)ctas, NW_THREADS, 0, st>>>(g);
+    } else {
+        if (!g.accumulate) {
+            if (g.ldc == g.N) GAOT_CHECK(cudaMemsetAsync(g.C, 0, sizeof(float) * (size_t)(g.M * g.N), st));
+            else GAOT_CHECK(cudaMemset2DAsync(g.C, sizeof(float) * (size_t)g.ldc, 0, sizeof(float) * (size_t)g.N, (size_t)g.M, st));
+        }
+        int64_t ctas = (g.K + warps * NW_ROWS * 8 - 1) / (warps * NW_ROWS * 8);    // >= 8 row groups per warp before the atomics
+        if (ctas > 148) ctas = 148;
+        if (ctas < 1) ctas = 1;
+        narrow_reduce_kernel<<<(unsigned)ctas, NW_THREADS, 0, st>>>(g);
+    }
+    gaot_launch_counter_add(1);
+    return (int)cudaGetLastError();
+}
+
 // ---- small pointwise / reduction kernels ----------------------------------------------------------
 __global__ void col_sum_kernel(const float* __restrict__ x, int64_t M, int64_t N, float* __restrict__ out, int64_t rows_per) {
     // grid (ceil(N/32), row-slices); block 32 x 8: threadIdx.x -> column (coalesced), threadIdx.y -> row lane
@@ -568,6 +721,10 @@ GAOT_API int gaot_gemm_f32(const float* A, const float* B, float* C, int64_t M, 
     g.vecA = al16(A) && (lda % 4 == 0);
     g.vecB = al16(B) && (ldb % 4 == 0);
     cudaStream_t st = (cudaStream_t)stream;
+    {
+        const int rc = launch_narrow(g, st);              // both small dimensions <= 64: weights-in-registers kernels
+        if (rc != 1) return rc;
+    }
     if (N <= 16) return launch_gemm<256, 16, 8, 2>(g, st);
     if (N <= 64) return launch_gemm<128, 64, 8, 4>(g, st);
     return launch_gemm<128, 128, 8, 8>(g, st);

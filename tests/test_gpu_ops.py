@@ -83,7 +83,8 @@ def test_csr_transpose_and_edge_rows_vs_oracle():
     assert torch.equal(plan.edge_row.cpu(), row)
 
 
-@pytest.mark.parametrize("M,N,K", [(300, 64, 4), (257, 130, 67), (1000, 1, 64), (64, 256, 1000), (5, 7, 3), (2048, 512, 256)])
+@pytest.mark.parametrize("M,N,K", [(300, 64, 4), (257, 130, 67), (1000, 1, 64), (64, 256, 1000), (5, 7, 3), (2048, 512, 256),
+                                   (5000, 64, 64), (4100, 48, 6), (3000, 7, 64), (31245, 64, 4)])
 def test_linear_fwd_bwd_vs_fp64(M, N, K):
     ops = _ops()
     gen = torch.Generator().manual_seed(M * 7 + N)
