@@ -206,7 +206,7 @@ int launch_gemm(GemmArgs& g, cudaStream_t st) {
 //               64 accumulators each; warps reduce through fp32 atomics into the zeroed C)
 // ------------------------------------------------------------------------------------------------
 constexpr int NW_THREADS = 256;
-constexpr int NW_ROWS = 4;               // rows in flight per warp
+constexpr int NW_ROWS = 8;               // rows in flight per warp
 
 template <bool BT>
 __global__ void __launch_bounds__(NW_THREADS, 1) narrow_rows_kernel(const GemmArgs g) {
@@ -224,16 +224,24 @@ __global__ void __launch_bounds__(NW_THREADS, 1) narrow_rows_kernel(const GemmAr
     float (*my)[64] = slab[warp];
     const int kc_n = (K + 3) >> 2;
     const int64_t gw = (int64_t)blockIdx.x * (NW_THREADS / 32) + warp, nw = (int64_t)gridDim.x * (NW_THREADS / 32);
-    for (int64_t r0 = gw * NW_ROWS; r0 < g.M; r0 += nw * NW_ROWS) {
-        __syncwarp();
+    // software pipeline: the next group's rows are fetched into registers while this group is computed
+    float pa[NW_ROWS], pb[NW_ROWS];
+    auto fetch = [&](int64_t r0) {
 #pragma unroll
         for (int rr = 0; rr < NW_ROWS; ++rr) {
             const int64_t r = min(r0 + rr, g.M - 1);
             const float* ap = g.A + r * g.lda;
-            my[rr][lane] = (lane < K) ? __ldg(ap + lane) : 0.f;
-            my[rr][lane + 32] = (lane + 32 < K) ? __ldg(ap + lane + 32) : 0.f;
+            pa[rr] = (lane < K) ? __ldg(ap + lane) : 0.f;
+            pb[rr] = (lane + 32 < K) ? __ldg(ap + lane + 32) : 0.f;
         }
+    };
+    if (gw * NW_ROWS < g.M) fetch(gw * NW_ROWS);
+    for (int64_t r0 = gw * NW_ROWS; r0 < g.M; r0 += nw * NW_ROWS) {
         __syncwarp();
+#pragma unroll
+        for (int rr = 0; rr < NW_ROWS; ++rr) { my[rr][lane] = pa[rr]; my[rr][lane + 32] = pb[rr]; }
+        __syncwarp();
+        if (r0 + nw * NW_ROWS < g.M) fetch(r0 + nw * NW_ROWS);
         float acc0[NW_ROWS], acc1[NW_ROWS];
 #pragma unroll
         for (int rr = 0; rr < NW_ROWS; ++rr) { acc0[rr] = b0; acc1[rr] = b1; }
@@ -284,20 +292,27 @@ __global__ void __launch_bounds__(NW_THREADS, 1) narrow_reduce_kernel(const Gemm
     float (*my)[64] = slab[warp];
     const int nc_n = (N + 3) >> 2;
     const int64_t gw = (int64_t)blockIdx.x * (NW_THREADS / 32) + warp, nw = (int64_t)gridDim.x * (NW_THREADS / 32);
-    for (int64_t r0 = gw * NW_ROWS; r0 < g.K; r0 += nw * NW_ROWS) {
-        float a0[NW_ROWS], a1[NW_ROWS];
-        __syncwarp();
+    float pa[NW_ROWS], pb[NW_ROWS], qa[NW_ROWS], qb[NW_ROWS];      // prefetched B row halves / own A values
+    auto fetch = [&](int64_t r0) {
 #pragma unroll
         for (int rr = 0; rr < NW_ROWS; ++rr) {
             const bool ok = r0 + rr < g.K;
             const int64_t r = ok ? r0 + rr : g.K - 1;
             const float* bp = g.B + r * g.ldb;
-            my[rr][lane] = (ok && lane < N) ? __ldg(bp + lane) : 0.f;
-            my[rr][lane + 32] = (ok && lane + 32 < N) ? __ldg(bp + lane + 32) : 0.f;
-            a0[rr] = (ok && m0 < M) ? __ldg(g.A + r * g.lda + m0) : 0.f;
-            a1[rr] = (ok && m1 < M) ? __ldg(g.A + r * g.lda + m1) : 0.f;
+            pa[rr] = (ok && lane < N) ? __ldg(bp + lane) : 0.f;
+            pb[rr] = (ok && lane + 32 < N) ? __ldg(bp + lane + 32) : 0.f;
+            qa[rr] = (ok && m0 < M) ? __ldg(g.A + r * g.lda + m0) : 0.f;
+            qb[rr] = (ok && m1 < M) ? __ldg(g.A + r * g.lda + m1) : 0.f;
         }
+    };
+    if (gw * NW_ROWS < g.K) fetch(gw * NW_ROWS);
+    for (int64_t r0 = gw * NW_ROWS; r0 < g.K; r0 += nw * NW_ROWS) {
+        float a0[NW_ROWS], a1[NW_ROWS];
         __syncwarp();
+#pragma unroll
+        for (int rr = 0; rr < NW_ROWS; ++rr) { my[rr][lane] = pa[rr]; my[rr][lane + 32] = pb[rr]; a0[rr] = qa[rr]; a1[rr] = qb[rr]; }
+        __syncwarp();
+        if (r0 + nw * NW_ROWS < g.K) fetch(r0 + nw * NW_ROWS);
 #pragma unroll
         for (int nc = 0; nc < 16; ++nc) {
             if (nc < nc_n) {
@@ -372,6 +387,27 @@ __global__ void act_bwd_kernel(const float* __restrict__ dy, const float* __rest
         const float p = pre[i];
         const float gr = (act == GAOT_ACT_GELU) ? gelu_erf_grad(p) : ((act == GAOT_ACT_RELU) ? (p > 0.f ? 1.f : 0.f) : 1.f);
         dx[i] = dy[i] * gr;
+    }
+}
+
+// dx (bf16) = dy * act'(pre); dy fp32 or bf16 - the gradient operand of the tensor-core dX / dW GEMMs
+__global__ void act_bwd_bf16_kernel(const void* __restrict__ dy, int dy_bf16, const float* __restrict__ pre,
+                                    __nv_bfloat16* __restrict__ dx, int64_t n, int act) {
+    const int64_t n4 = n >> 2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 p = __ldg(reinterpret_cast<const float4*>(pre) + i);
+        float4 gy;
+        if (dy_bf16) {
+            const uint2 pk = __ldg(reinterpret_cast<const uint2*>(dy) + i);
+            gy = make_float4(__uint_as_float(pk.x << 16), __uint_as_float(pk.x & 0xffff0000u), __uint_as_float(pk.y << 16),
+                             __uint_as_float(pk.y & 0xffff0000u));
+        } else gy = __ldg(reinterpret_cast<const float4*>(dy) + i);
+        float gr[4] = {p.x, p.y, p.z, p.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) gr[k] = (act == GAOT_ACT_GELU) ? gelu_erf_grad(gr[k]) : ((act == GAOT_ACT_RELU) ? (gr[k] > 0.f ? 1.f : 0.f) : 1.f);
+        __nv_bfloat162 t0 = __floats2bfloat162_rn(gy.x * gr[0], gy.y * gr[1]), t1 = __floats2bfloat162_rn(gy.z * gr[2], gy.w * gr[3]);
+        uint2 o; o.x = *reinterpret_cast<uint32_t*>(&t0); o.y = *reinterpret_cast<uint32_t*>(&t1);
+        reinterpret_cast<uint2*>(dx)[i] = o;
     }
 }
 
@@ -748,6 +784,14 @@ GAOT_API int gaot_act_bwd(const float* dy, const float* pre, float* dx, int64_t 
     if (!dy || !pre || !dx || n < 0 || act < 0 || act > 2) return GAOT_E_BADARG;
     if (n == 0) return 0;
     act_bwd_kernel<<<gaot_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(dy, pre, dx, n, act);
+    GAOT_RETURN_LAST();
+}
+
+GAOT_API int gaot_act_bwd_bf16(const void* dy, int dy_is_bf16, const float* pre, void* dx, int64_t n, int act, void* stream) {
+    if (!dy || !pre || !dx || n < 0 || n % 4 || act < 0 || act > 2) return GAOT_E_BADARG;
+    if ((reinterpret_cast<uintptr_t>(dy) & 15) || (reinterpret_cast<uintptr_t>(pre) & 15) || (reinterpret_cast<uintptr_t>(dx) & 7)) return GAOT_E_ALIGN;
+    if (n == 0) return 0;
+    act_bwd_bf16_kernel<<<gaot_grid(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(dy, dy_is_bf16, pre, reinterpret_cast<__nv_bfloat16*>(dx), n, act);
     GAOT_RETURN_LAST();
 }
 

@@ -82,6 +82,7 @@ struct TcArgs {
     const float* bias; const float* add; int64_t add_rows, ldadd;
     int out_bf16, splits, accumulate;
     int64_t gm, gn;                   // tile grid
+    int act; float* pre;              // optional activation (GAOT_ACT_*) and fp32 pre-activation output
     int dbg;                          // GAOT_TC_DEBUG bit mask (performance experiments only; 0 in production)
 };
 
@@ -269,6 +270,18 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
                         for (int it8 = 0; it8 < 8; ++it8) { v[it8].x += av[it8].x; v[it8].y += av[it8].y; v[it8].z += av[it8].z; v[it8].w += av[it8].w; }
                     }
+                    if (g.pre) {
+#pragma unroll
+                        for (int it8 = 0; it8 < 8; ++it8)
+                            if (coff[it8] >= 0) *reinterpret_cast<float4*>(g.pre + nc + coff[it8]) = v[it8];
+                    }
+                    if (g.act == GAOT_ACT_GELU) {
+#pragma unroll
+                        for (int it8 = 0; it8 < 8; ++it8) { v[it8].x = gelu_erf(v[it8].x); v[it8].y = gelu_erf(v[it8].y); v[it8].z = gelu_erf(v[it8].z); v[it8].w = gelu_erf(v[it8].w); }
+                    } else if (g.act == GAOT_ACT_RELU) {
+#pragma unroll
+                        for (int it8 = 0; it8 < 8; ++it8) { v[it8].x = fmaxf(v[it8].x, 0.f); v[it8].y = fmaxf(v[it8].y, 0.f); v[it8].z = fmaxf(v[it8].z, 0.f); v[it8].w = fmaxf(v[it8].w, 0.f); }
+                    }
                     if (g.out_bf16) {
                         __nv_bfloat16* cb = reinterpret_cast<__nv_bfloat16*>(g.C) + nc;
 #pragma unroll
@@ -300,6 +313,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                             float x = vv[j];
                             if (bias) x += __ldg(bias + nc + j);
                             if (add) x += __ldg(add + aoff[it8] + nc + j);
+                            if (g.pre) g.pre[coff[it8] + nc + j] = x;
+                            x = (g.act == GAOT_ACT_GELU) ? gelu_erf(x) : ((g.act == GAOT_ACT_RELU) ? fmaxf(x, 0.f) : x);
                             if (g.out_bf16) reinterpret_cast<__nv_bfloat16*>(g.C)[coff[it8] + nc + j] = __float2bfloat16_rn(x);
                             else if (atomic) atomicAdd(reinterpret_cast<float*>(g.C) + coff[it8] + nc + j, x);
                             else reinterpret_cast<float*>(g.C)[coff[it8] + nc + j] = x;
@@ -423,7 +438,7 @@ int launch_tc(const void* A, const void* B, TcArgs& g, cudaStream_t st) {
     const int64_t kblocks = (g.K + TC_BK - 1) / TC_BK, tiles = g.gm * g.gn;
     const int sms = sm_count();
     int splits = 1;
-    if (!g.out_bf16 && tiles < sms && kblocks >= 8) {          // too few tiles for the chip: split the contraction
+    if (!g.out_bf16 && !g.act && !g.pre && tiles < sms && kblocks >= 8) {   // too few tiles for the chip: split the contraction
         splits = (int)((2 * sms + tiles - 1) / tiles);
         if (splits > kblocks / 4) splits = (int)(kblocks / 4);
         if (splits > 128) splits = 128;
@@ -450,16 +465,17 @@ int launch_tc(const void* A, const void* B, TcArgs& g, cudaStream_t st) {
 }  // namespace
 
 GAOT_API int gaot_gemm_bf16(const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K, int out_bf16,
-                            const float* bias, const float* add, int64_t add_rows, int64_t ldadd, int accumulate,
-                            void* stream) {
+                            const float* bias, const float* add, int64_t add_rows, int64_t ldadd, int act, float* pre,
+                            int accumulate, void* stream) {
     if (!A || !B || !C || M < 1 || N < 1 || K < 1) return GAOT_E_BADARG;
     if (K % 8 != 0 || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15) ||
         (reinterpret_cast<uintptr_t>(C) & 15))
         return GAOT_E_ALIGN;                       // TMA: 16-byte aligned base and row pitch
     if (add && (add_rows < 1 || ldadd < N)) return GAOT_E_BADARG;
     if (out_bf16 && accumulate) return GAOT_E_BADARG;
+    if (act < 0 || act > 2 || ((act || pre) && accumulate)) return GAOT_E_BADARG;
     if (M > 0x7fffffffLL || N > 0x7fffffffLL || K > 0x7fffffffLL) return GAOT_E_BADARG;
-    TcArgs g{C, M, N, K, bias, add, add ? add_rows : 1, ldadd, out_bf16, 1, accumulate, 0, 0, 0};
+    TcArgs g{C, M, N, K, bias, add, add ? add_rows : 1, ldadd, out_bf16, 1, accumulate, 0, 0, act, pre, 0};
     cudaStream_t st = (cudaStream_t)stream;
     if (N <= 64) return launch_tc<64, false, false>(A, B, g, st);
     return launch_tc<128, false, false>(A, B, g, st);
@@ -472,7 +488,7 @@ GAOT_API int gaot_gemm_bf16_nn(const void* A, const void* B, void* C, int64_t M,
         (reinterpret_cast<uintptr_t>(C) & 15))
         return GAOT_E_ALIGN;
     if (M > 0x7fffffffLL || N > 0x7fffffffLL || K > 0x7fffffffLL) return GAOT_E_BADARG;
-    TcArgs g{C, M, N, K, nullptr, nullptr, 1, 0, out_bf16, 1, 0, 0, 0, 0};
+    TcArgs g{C, M, N, K, nullptr, nullptr, 1, 0, out_bf16, 1, 0, 0, 0, 0, nullptr, 0};
     cudaStream_t st = (cudaStream_t)stream;
     if (N <= 64) return launch_tc<64, false, true>(A, B, g, st);
     return launch_tc<128, false, true>(A, B, g, st);
@@ -485,7 +501,7 @@ GAOT_API int gaot_gemm_bf16_tn(const void* A, const void* B, float* C, int64_t M
         (reinterpret_cast<uintptr_t>(C) & 15))
         return GAOT_E_ALIGN;                       // TMA: 16-byte aligned base and row pitch
     if (M > 0x7fffffffLL || N > 0x7fffffffLL || R > 0x7fffffffLL) return GAOT_E_BADARG;
-    TcArgs g{C, M, N, R, nullptr, nullptr, 1, 0, 0, 1, accumulate, 0, 0, 0};
+    TcArgs g{C, M, N, R, nullptr, nullptr, 1, 0, 0, 1, accumulate, 0, 0, 0, nullptr, 0};
     cudaStream_t st = (cudaStream_t)stream;
     if (N <= 64) return launch_tc<64, true, true>(A, B, g, st);
     return launch_tc<128, true, true>(A, B, g, st);

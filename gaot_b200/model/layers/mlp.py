@@ -23,7 +23,11 @@ class LinearChannelMLP(nn.Module):
         shape = x.shape
         x = x.reshape(-1, shape[-1])
         for i, fc in enumerate(self.fcs):
-            x = ops.linear(x, fc.weight, fc.bias, act=ops.ACT_GELU if i < self.n_layers - 1 else ops.ACT_NONE)
+            last = i == self.n_layers - 1
+            # bf16 mode: hidden layers (K = hidden width) run on the tensor cores and hand bf16 to the next
+            # layer; the first layer consumes raw coordinates and always stays fp32 (K = 2d is tiny anyway)
+            x = ops.linear(x, fc.weight, fc.bias, act=ops.ACT_NONE if last else ops.ACT_GELU, tc=i > 0,
+                           out_bf16=(i > 0 and not last))
         return x.view(*shape[:-1], x.shape[-1])
 
 

@@ -209,12 +209,13 @@ def transpose_bf16(xb):
     return out
 
 
-def gemm_bf16(A, B, M, N, K, out_bf16=False, bias=None, add=None, add_rows=0, out=None, accumulate=False):
-    """C[M,N] = A[M,K] B[N,K]^T on the tensor cores (A, B bf16 row-major)."""
+def gemm_bf16(A, B, M, N, K, out_bf16=False, bias=None, add=None, add_rows=0, out=None, accumulate=False, act=ACT_NONE,
+              pre=None):
+    """C[M,N] = act(A[M,K] B[N,K]^T + bias + add) on the tensor cores (A, B bf16 row-major)."""
     if out is None:
         out = torch.empty((M, N), dtype=torch.bfloat16 if out_bf16 else torch.float32, device=A.device)
-    call("gaot_gemm_bf16", ptr(A), ptr(B), ptr(out), M, N, K, int(out_bf16), ptr(bias), ptr(add), int(add_rows), N,
-         int(accumulate))
+    call("gaot_gemm_bf16", ptr(A), ptr(B), ptr(out), M, N, K, int(out_bf16), ptr(bias), ptr(add), int(add_rows), N, int(act),
+         ptr(pre), int(accumulate))
     return out
 
 
@@ -238,7 +239,7 @@ class _LinearTC(torch.autograd.Function):
     already bf16; y is fp32, or bf16 when out_bf16 (feeding another tensor-core kernel)."""
 
     @staticmethod
-    def forward(ctx, x, W, bias, add, out_bf16):
+    def forward(ctx, x, W, bias, add, out_bf16, act=ACT_NONE):
         _need_cuda(x)
         x = x if x.is_contiguous() else x.contiguous()
         W = _c(W)
@@ -251,18 +252,28 @@ class _LinearTC(torch.autograd.Function):
             raise ValueError(f"broadcast-add of shape {tuple(add_c.shape)} does not tile an [{M},{N}] output")
         xb = x if x.dtype == torch.bfloat16 else cast_bf16(_c(x))[0]
         wb, _ = cast_bf16(W)
-        y = gemm_bf16(xb, wb, M, N, K, out_bf16=out_bf16, bias=bias_c, add=add_c, add_rows=add_rows)
-        ctx.save_for_backward(xb, wb)
-        ctx.has_bias, ctx.add_rows, ctx.x_bf16 = bias is not None, add_rows, x.dtype == torch.bfloat16
+        pre = torch.empty((M, N), dtype=torch.float32, device=x.device) if act != ACT_NONE else None
+        y = gemm_bf16(xb, wb, M, N, K, out_bf16=out_bf16, bias=bias_c, add=add_c, add_rows=add_rows, act=act, pre=pre)
+        ctx.save_for_backward(xb, wb, pre)
+        ctx.has_bias, ctx.add_rows, ctx.x_bf16, ctx.act = bias is not None, add_rows, x.dtype == torch.bfloat16, act
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        xb, wb = ctx.saved_tensors
+        xb, wb, pre = ctx.saved_tensors
         dy = dy if dy.is_contiguous() else dy.contiguous()
         M, K = xb.shape
         N = wb.shape[0]
         dx = dW = db = dadd = None
+        if ctx.act != ACT_NONE:
+            if (M * N) % 4 == 0:
+                dyb = torch.empty((M, N), dtype=torch.bfloat16, device=dy.device)
+                call("gaot_act_bwd_bf16", ptr(dy), int(dy.dtype == torch.bfloat16), ptr(pre), ptr(dyb), M * N, ctx.act)
+                dy = dyb                                        # from here on "dy" is the gradient w.r.t. the pre-activation
+            else:
+                dpre = torch.empty((M, N), dtype=torch.float32, device=dy.device)
+                call("gaot_act_bwd", ptr(_c(dy)), ptr(pre), ptr(dpre), M * N, ctx.act)
+                dy = dpre
         dyb = dy if dy.dtype == torch.bfloat16 else cast_bf16(dy)[0]
         if ctx.needs_input_grad[0]:
             if N % 8 == 0:
@@ -281,14 +292,14 @@ class _LinearTC(torch.autograd.Function):
                 db = col_sum(dyf, M, N)
             if ctx.add_rows and ctx.needs_input_grad[3]:
                 dadd = dyf if ctx.add_rows == M else col_sum(dyf, M // ctx.add_rows, ctx.add_rows * N).view(ctx.add_rows, N)
-        return dx, dW, db, dadd, None
+        return dx, dW, db, dadd, None, None
 
 
 def linear(x, W, bias=None, add=None, act=ACT_NONE, tc=False, out_bf16=False):
     """tc=True marks a processor layer that may run on the tensor cores when precision is 'bf16';
     out_bf16 (tensor-core path only) keeps the result in bf16 for a following tensor-core kernel."""
-    if tc and _PRECISION == "bf16" and act == ACT_NONE and x.shape[-1] % 8 == 0:
-        return _LinearTC.apply(x, W, bias, add, out_bf16)
+    if tc and _PRECISION == "bf16" and x.shape[-1] % 8 == 0 and (act == ACT_NONE or W.shape[0] % 4 == 0):
+        return _LinearTC.apply(x, W, bias, add, out_bf16, act)
     if x.dtype != torch.float32:
         x = x.float()
     return _Linear.apply(x, W, bias, add, act)

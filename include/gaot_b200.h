@@ -152,10 +152,11 @@ int gaot_gemm_f32(const float* A, const float* B, float* C, int64_t M, int64_t N
 
 /* Tensor-core (tcgen05, TMA, TMEM) variant for the processor: A [M,K] and B [N,K] are bf16 row-major
  * (B in nn.Linear layout), fp32 accumulation; C [M,N] is fp32 (out_bf16=0) or bf16 (out_bf16=1).
- * accumulate=1 (fp32 C only) adds into C.  K % 8 == 0 and 16-byte aligned bases (TMA). */
+ * act / pre as in gaot_gemm_f32 (pre is fp32).  accumulate=1 (fp32 C only, no act) adds into C.
+ * K % 8 == 0 and 16-byte aligned bases (TMA). */
 int gaot_gemm_bf16(const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K, int out_bf16,
-                   const float* bias, const float* add, int64_t add_rows, int64_t ldadd, int accumulate,
-                   void* stream);
+                   const float* bias, const float* add, int64_t add_rows, int64_t ldadd, int act, float* pre,
+                   int accumulate, void* stream);
 /* Input-gradient form: C[M,N] (fp32 or bf16) = A[M,K] B[K,N], B row-major [K,N] consumed MN-major in place
  * (dX = dY W with W in nn.Linear layout).  K % 8 == 0, N % 8 == 0. */
 int gaot_gemm_bf16_nn(const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K, int out_bf16,
@@ -172,6 +173,8 @@ int gaot_transpose_bf16(const void* in, void* out_t, int64_t rows, int64_t cols,
 
 /* out[n] (+)= sum_m x[m,n]  (bias gradients) */
 int gaot_col_sum(const float* x, int64_t M, int64_t N, float* out, int accumulate, void* stream);
+/* dx (bf16) = dy * act'(pre), dy fp32 (dy_is_bf16=0) or bf16; n % 4 == 0 */
+int gaot_act_bwd_bf16(const void* dy, int dy_is_bf16, const float* pre, void* dx, int64_t n, int act, void* stream);
 /* dx = dy * act'(pre) */
 int gaot_act_bwd(const float* dy, const float* pre, float* dx, int64_t n, int act, void* stream);
 

@@ -222,12 +222,15 @@ def gaot_gemm_f32(A, B, C, M, N, K, lda, ldb, ldc, transA, transB, bias, add, ad
     c[:] = (v + c.double()).float() if accumulate else v.float()
 
 
-def gaot_gemm_bf16(A, B, C, M, N, K, out_bf16, bias, add, add_rows, ldadd, accumulate):
+def gaot_gemm_bf16(A, B, C, M, N, K, out_bf16, bias, add, add_rows, ldadd, act, pre, accumulate):
     v = _bf(A, (M, K)).double() @ _bf(B, (N, K)).double().T
     if bias:
         v = v + _t(bias, (N,)).double()
     if add:
         v = v + _strided(add, add_rows, N, ldadd).double().repeat(M // add_rows, 1)
+    if pre:
+        _t(pre, (M, N))[:] = v.float()
+    v = _act(v, act)
     if out_bf16:
         _bf(C, (M, N))[:] = v.to(torch.bfloat16)
     else:
@@ -258,6 +261,14 @@ def gaot_act_bwd(dy, pre, dx, n, act):
         p = _t(pre, (n,)).double().requires_grad_(True)
         (gr,) = torch.autograd.grad(_act(p, act).sum(), p)
     _arr(dx, (n,))[:] = (_t(dy, (n,)).double() * gr).float().numpy()
+
+
+def gaot_act_bwd_bf16(dy, dy_is_bf16, pre, dx, n, act):
+    with torch.enable_grad():
+        p = _t(pre, (n,)).double().requires_grad_(True)
+        (gr,) = torch.autograd.grad(_act(p, act).sum(), p)
+    g = _bf(dy, (n,)).double() if dy_is_bf16 else _t(dy, (n,)).double()
+    _bf(dx, (n,))[:] = (g * gr).to(torch.bfloat16)
 
 
 def gaot_rmsnorm_fwd(x, gamma, y, y16, rstd, rows, D, eps):

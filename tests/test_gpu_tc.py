@@ -166,3 +166,23 @@ def test_gemm_bf16_nn_vs_fp64(M, N, K):
     want = a.double() @ b.double()
     assert rel_l2(ops.gemm_bf16_nn(a, b, M, N, K), want) < 2e-5
     assert rel_l2(ops.gemm_bf16_nn(a, b, M, N, K, out_bf16=True), want) < 4e-3
+
+
+def test_linear_tc_with_activation():
+    from gaot_b200 import ops
+    M, N, K = 5000, 64, 64
+    x, W, b, gy = cases.normal((M, K), 61), cases.normal((N, K), 62) / K ** 0.5, cases.normal((N,), 63), cases.normal((M, N), 64)
+    ops.set_precision("bf16")
+    try:
+        xs = [t.clone().to(DEV).requires_grad_(True) for t in (x, W, b)]
+        y = ops.linear(xs[0], xs[1], xs[2], act=ops.ACT_GELU, tc=True, out_bf16=True)
+        assert y.dtype == torch.bfloat16
+        y.backward(gy.to(DEV).to(torch.bfloat16))
+    finally:
+        ops.set_precision("fp32")
+    xr = [t.clone().double().requires_grad_(True) for t in (x, W, b)]
+    yr = torch.nn.functional.gelu(xr[0] @ xr[1].T + xr[2])
+    yr.backward(gy.double())
+    assert rel_l2(y, yr) < 8e-3
+    for a, r_ in zip(xs, xr):
+        assert rel_l2(a.grad, r_.grad) < 1.5e-2
