@@ -78,6 +78,18 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// issue only: several loads can be put in flight before one tmem_wait_ld() (each wait is a full TMEM round trip)
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,"
+        "%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]),
+          "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]),
+          "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -223,24 +235,26 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttnArgs g) {
             const bool full_tile = kv_left >= AT_BKV;      // warp-uniform: only the last tile can be ragged
             float mx = -INFINITY;                          // max of the RAW scores (scale > 0)
 #pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-                uint32_t v[32];
-                tmem_ld32(tmem_s + lane_addr + c * 32, v);
+            for (int c = 0; c < 4; c += 2) {               // two 32-column loads in flight per TMEM round trip
+                uint32_t v[32], v2[32];
+                tmem_ld32_issue(tmem_s + lane_addr + c * 32, v);
+                tmem_ld32_issue(tmem_s + lane_addr + (c + 1) * 32, v2);
+                tmem_wait_ld();
                 if (full_tile) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
+                    for (int j = 0; j < 32; ++j) mx = fmaxf(mx, fmaxf(__uint_as_float(v[j]), __uint_as_float(v2[j])));
                 } else {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) mx = fmaxf(mx, (c * 32 + j < kv_left) ? __uint_as_float(v[j]) : -INFINITY);
+                    for (int j = 0; j < 32; ++j) {
+                        mx = fmaxf(mx, (c * 32 + j < kv_left) ? __uint_as_float(v[j]) : -INFINITY);
+                        mx = fmaxf(mx, ((c + 1) * 32 + j < kv_left) ? __uint_as_float(v2[j]) : -INFINITY);
+                    }
                 }
             }
             const float mnew = fmaxf(mrun, mx * g.scale_log2);
             const float corr = ex2(mrun - mnew);
             float psum = 0.f;
-#pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-                uint32_t v[32];
-                tmem_ld32(tmem_s + lane_addr + c * 32, v);
+            auto emit = [&](const uint32_t (&v)[32], int c) {      // 32 columns -> bf16 P -> 4 x 16-byte swizzled stores
                 uint32_t pk[16];
                 if (full_tile) {
 #pragma unroll
@@ -263,6 +277,15 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttnArgs g) {
 #pragma unroll
                 for (int w = 0; w < 4; ++w)
                     *reinterpret_cast<uint4*>(blk + sw128_off(r, (c & 1) * 4 + w)) = make_uint4(pk[4 * w], pk[4 * w + 1], pk[4 * w + 2], pk[4 * w + 3]);
+            };
+#pragma unroll 1
+            for (int c = 0; c < 4; c += 2) {
+                uint32_t v[32], v2[32];
+                tmem_ld32_issue(tmem_s + lane_addr + c * 32, v);
+                tmem_ld32_issue(tmem_s + lane_addr + (c + 1) * 32, v2);
+                tmem_wait_ld();
+                emit(v, c);
+                emit(v2, c + 1);
             }
             lrun = lrun * corr + psum;
             mrun = mnew;
@@ -468,8 +491,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
 #pragma unroll 1
             for (int c = 2 * half; c < 2 * half + 2; ++c) {
                 uint32_t sv[32], dv[32];
-                tmem_ld32(tm_st + lane_addr + c * 32, sv);
-                tmem_ld32(tm_dp + lane_addr + c * 32, dv);
+                tmem_ld32_issue(tm_st + lane_addr + c * 32, sv);
+                tmem_ld32_issue(tm_dp + lane_addr + c * 32, dv);
+                tmem_wait_ld();
                 uint32_t pp[16], ds[16];
                 const float4* l4 = reinterpret_cast<const float4*>(sLse + s * 128 + c * 32);
                 const float4* d4 = reinterpret_cast<const float4*>(sDel + s * 128 + c * 32);

@@ -353,7 +353,7 @@ int launch_narrow(GemmArgs& g, cudaStream_t st) {
             if (g.ldc == g.N) GAOT_CHECK(cudaMemsetAsync(g.C, 0, sizeof(float) * (size_t)(g.M * g.N), st));
             else GAOT_CHECK(cudaMemset2DAsync(g.C, sizeof(float) * (size_t)g.ldc, 0, sizeof(float) * (size_t)g.N, (size_t)g.M, st));
         }
-        int64_t ctas = (g.K + warps * NW_ROWS * 8 - 1) / (warps * NW_ROWS * 8);    // >= 8 row groups per warp before the atomics
+        int64_t ctas = (g.K + warps * NW_ROWS * 2 - 1) / (warps * NW_ROWS * 2);    // >= 2 row groups per warp before the atomics
         if (ctas > 148) ctas = 148;
         if (ctas < 1) ctas = 1;
         narrow_reduce_kernel<<<(unsigned)ctas, NW_THREADS, 0, st>>>(g);

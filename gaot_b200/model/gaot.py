@@ -97,7 +97,7 @@ class GAOT(nn.Module):
     @torch.no_grad()
     def autoregressive_predict(self, x_batch, time_indices, t_values, stats, stepper_mode="output",
                                latent_tokens_coord=None, fixed_coord=None, encoder_nbrs=None, decoder_nbrs=None,
-                               c_batch=None):
+                               c_batch=None, use_cuda_graph=False):
         """gaot.py:307-434 (fx mode): x_batch [B,N,u_dim] normalised initial state, optional conditioning
         channels c_batch [B,N,c]; returns [B, len(time_indices)-1, N, u_dim] normalised predictions.
         stats = {"u": {mean,std}, "res": {...}, "der": {...}, "start_time": {...}, "time_diffs": {...}} of
@@ -111,15 +111,36 @@ class GAOT(nn.Module):
         um, us = t(stats["u"]["mean"]), t(stats["u"]["std"])
         skey = {1: "res", 2: "der"}.get(mode)
         sm, ss = (t(stats[skey]["mean"]), t(stats[skey]["std"])) if skey else (um, us)
+        nc = 0 if c_batch is None else c_batch.shape[-1]
+        x_in = torch.empty((B, N, U + nc + 2), dtype=torch.float32, device=dev)     # static step input [u | c | t0 | dt]
+        if c_batch is not None:
+            x_in[..., U:U + nc] = c_batch
+        graph = pred_static = None
         for i in range(len(time_indices) - 1):
             t0 = float(t_values[time_indices[i]])
             dt = float(t_values[time_indices[i + 1]]) - t0
             t0n = (t0 - float(stats["start_time"]["mean"])) / float(stats["start_time"]["std"])
             dtn = (dt - float(stats["time_diffs"]["mean"])) / float(stats["time_diffs"]["std"])
-            feats = [cur] + ([c_batch] if c_batch is not None else [])
-            feats += [torch.full((B, N, 1), t0n, device=dev), torch.full((B, N, 1), dtn, device=dev)]
-            pred = self.forward(latent_tokens_coord, fixed_coord, torch.cat(feats, dim=-1),
-                                encoder_nbrs=encoder_nbrs, decoder_nbrs=decoder_nbrs)
+            x_in[..., :U] = cur
+            x_in[..., U + nc] = t0n
+            x_in[..., U + nc + 1] = dtn
+            if use_cuda_graph and dev.type == "cuda":
+                # one forward captured on the static input buffer and replayed for every rollout step
+                if graph is None:
+                    side = torch.cuda.Stream()
+                    side.wait_stream(torch.cuda.current_stream())
+                    with torch.cuda.stream(side):
+                        self.forward(latent_tokens_coord, fixed_coord, x_in, encoder_nbrs=encoder_nbrs, decoder_nbrs=decoder_nbrs)
+                    torch.cuda.current_stream().wait_stream(side)
+                    torch.cuda.synchronize()
+                    graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(graph):
+                        pred_static = self.forward(latent_tokens_coord, fixed_coord, x_in, encoder_nbrs=encoder_nbrs,
+                                                   decoder_nbrs=decoder_nbrs)
+                graph.replay()
+                pred = pred_static
+            else:
+                pred = self.forward(latent_tokens_coord, fixed_coord, x_in, encoder_nbrs=encoder_nbrs, decoder_nbrs=decoder_nbrs)
             cur = ops.rollout_update(pred, cur, dt, mode, um, us, sm, ss)
             outs.append(cur)
         return torch.stack(outs, dim=1)

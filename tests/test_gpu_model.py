@@ -128,3 +128,32 @@ def test_train_steps_match_oracle_adamw():
     sd = model.state_dict()
     for k in p:
         assert rel_l2(sd[k], p[k]) < 2e-5, k
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_autoregressive_rollout_matches_oracle(use_graph):
+    """10-step no-grad rollout (gaot.py:365-476, stepper 'time_der') vs the oracle's forward + update rule in fp64."""
+    c = dict(cases.CASES["tiny2d"], cin=5, cout=3)       # u(3) + t0 + dt
+    torch.manual_seed(0)
+    model = build_model(c).eval()
+    lat, x, _, _ = cases.case_inputs("tiny2d")
+    u0 = cases.normal((2, 300, 3), 31)
+    stats = {"u": {"mean": torch.tensor([0.1, 0.2, 0.3]), "std": torch.tensor([1.1, 0.9, 1.2])},
+             "der": {"mean": torch.tensor([0.0, 0.1, -0.1]), "std": torch.tensor([0.5, 0.6, 0.7])},
+             "start_time": {"mean": 0.5, "std": 0.3}, "time_diffs": {"mean": 0.1, "std": 0.05}}
+    tv = torch.linspace(0, 1, 21)
+    idx = list(range(11))
+    got = model.autoregressive_predict(u0.to(DEV), idx, tv, stats, "time_der", latent_tokens_coord=lat.to(DEV),
+                                       fixed_coord=x.to(DEV), use_cuda_graph=use_graph)
+    cfg = orc.make_config(c["latent"], c["magno"], c["transformer"], c["attn"])
+    p = {k: v.detach().double().cpu() for k, v in model.state_dict().items()}
+    cur = u0.double()
+    st64 = {k: ({kk: (vv.double() if torch.is_tensor(vv) else vv) for kk, vv in v.items()}) for k, v in stats.items()}
+    with torch.no_grad():
+        for i in range(10):
+            t0, dt = float(tv[i]), float(tv[i + 1] - tv[i])
+            inp = torch.cat([cur, torch.full((2, 300, 1), (t0 - 0.5) / 0.3, dtype=torch.float64),
+                             torch.full((2, 300, 1), (dt - 0.1) / 0.05, dtype=torch.float64)], -1)
+            pred = orc.gaot_forward(p, cfg, lat.double(), x.double(), inp)
+            cur = orc.rollout_update(pred, cur, dt, st64, "time_der")
+            assert rel_l2(got[:, i], cur) < 2e-5, i          # errors compound over the 10 autoregressive steps
