@@ -205,13 +205,15 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttnArgs g) {
             mbar_wait(p_full, (uint32_t)i & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (lane == 0) {
-                const uint32_t pv = smem_u32(sV + s * TILE_BYTES), pp = smem_u32(sP);
+                // descriptors are base + compile-time offsets (start-address field counts 16-byte units): the single
+                // issuing thread must not spend its time rebuilding them
+                const uint64_t da0 = make_desc<128>(smem_u32(sP)), db0 = make_desc<ROWB>(smem_u32(sV + s * TILE_BYTES));
 #pragma unroll
                 for (int k = 0; k < AT_BKV / 16; ++k) {
                     // A: 16 keys = 32 bytes inside the 128-byte swizzle row of P's column block (k / 4)
-                    const uint64_t da = make_desc<128>(pp + (k >> 2) * (AT_BQ * 128)) + (uint64_t)(2 * (k & 3));
+                    const uint64_t da = da0 + (uint64_t)(((k >> 2) * (AT_BQ * 128) + (k & 3) * 32) >> 4);
                     // B: 16 keys = 16 rows of V, two 8-row swizzle atoms
-                    const uint64_t db = make_desc<ROWB>(pv + k * 16 * ROWB);
+                    const uint64_t db = db0 + (uint64_t)((k * 16 * ROWB) >> 4);
                     umma_f16(tmem_pv, da, db, IDESC_PV, k > 0 ? 1u : 0u);
                 }
                 umma_commit(o_full);
@@ -435,23 +437,25 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
             if (i > 0) mbar_wait(dq_empty, (uint32_t)(i - 1) & 1u);       // previous dQ tile drained from TMEM
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (lane == 0) {
-                const uint32_t pq = smem_u32(sQ + s * TILE_BYTES), pg = smem_u32(sG + s * TILE_BYTES);
-                const uint32_t ppt = smem_u32(sPt), pst = smem_u32(sSt), pk = smem_u32(sK);
+                // all descriptors = per-step base + compile-time offset (16-byte units in the start-address field)
+                const uint64_t d_q = make_desc<ROWB>(smem_u32(sQ + s * TILE_BYTES)), d_g = make_desc<ROWB>(smem_u32(sG + s * TILE_BYTES));
+                const uint64_t d_pt = make_desc<128>(smem_u32(sPt)), d_st = make_desc<128>(smem_u32(sSt)), d_k = make_desc<ROWB>(smem_u32(sK));
+                const uint32_t pst = smem_u32(sSt);
+                const uint32_t acc_first = i > 0 ? 1u : 0u;
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {      // contraction over 128 queries, 16 per MMA
-                    const uint64_t a_p = make_desc<128>(ppt + (k >> 2) * (128 * 128)) + (uint64_t)(2 * (k & 3));
-                    const uint64_t a_s = make_desc<128>(pst + (k >> 2) * (128 * 128)) + (uint64_t)(2 * (k & 3));
-                    umma_f16(tm_dv, a_p, make_desc<ROWB>(pg + k * 16 * ROWB), IDESC_KN, (i > 0 || k > 0) ? 1u : 0u);
-                    umma_f16(tm_dk, a_s, make_desc<ROWB>(pq + k * 16 * ROWB), IDESC_KN, (i > 0 || k > 0) ? 1u : 0u);
+                    const uint64_t aoff = (uint64_t)(((k >> 2) * (128 * 128) + (k & 3) * 32) >> 4);
+                    const uint64_t boff = (uint64_t)((k * 16 * ROWB) >> 4);
+                    umma_f16(tm_dv, d_pt + aoff, d_g + boff, IDESC_KN, k > 0 ? 1u : acc_first);
+                    umma_f16(tm_dk, d_st + aoff, d_q + boff, IDESC_KN, k > 0 ? 1u : acc_first);
                 }
                 // dQ[q, :] = sum_keys dS^T[key, q] K[key, :]: A = the dS^T tile as an MN-major operand
                 // (M = 128 queries = two 64-wide swizzle atoms LBO = 16 KB apart, 8-key groups SBO = 1 KB apart)
+                const uint64_t a_mn0 = (uint64_t)((pst & 0x3FFFF) >> 4) | ((uint64_t)(16384 >> 4) << 16) |
+                                       ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {      // contraction over 128 keys, 16 per MMA = 16 rows of 128 bytes
-                    const uint64_t a_mn = (uint64_t)(((pst + k * 2048) & 0x3FFFF) >> 4) | ((uint64_t)(16384 >> 4) << 16) |
-                                          ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
-                    umma_f16(tm_dq, a_mn, make_desc<ROWB>(pk + k * 16 * ROWB), IDESC_MN, k > 0 ? 1u : 0u);
-                }
+                for (int k = 0; k < 8; ++k)        // contraction over 128 keys, 16 per MMA = 16 rows of 128 bytes
+                    umma_f16(tm_dq, a_mn0 + (uint64_t)((k * 2048) >> 4), d_k + (uint64_t)((k * 16 * ROWB) >> 4), IDESC_MN, k > 0 ? 1u : 0u);
                 umma_commit(dq_full);
                 umma_commit(&q_empty[s]);
                 if (i == n_steps - 1) umma_commit(fin_bar);

@@ -191,11 +191,14 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (lane == 0) {
                     const uint32_t sa = smem_u32(smem + s * STAGE_BYTES), sb = sa + A_BYTES;
+                    const uint64_t da0 = AMN ? make_smem_desc_mn(sa) : make_smem_desc_sw128(sa);
+                    const uint64_t db0 = BMN ? make_smem_desc_mn(sb) : make_smem_desc_sw128(sb);
 #pragma unroll
                     for (int k = 0; k < ((g.dbg & 2) ? 1 : TC_BK / 16); ++k) {
-                        // K-major: +32 bytes per K=16 step inside the 128-byte swizzle row; MN-major: 16 rows = 2048 bytes
-                        const uint64_t da = AMN ? make_smem_desc_mn(sa + k * 2048) : make_smem_desc_sw128(sa) + (uint64_t)(2 * k);
-                        const uint64_t db = BMN ? make_smem_desc_mn(sb + k * 2048) : make_smem_desc_sw128(sb) + (uint64_t)(2 * k);
+                        // start-address field counts 16-byte units.  K-major: +32 bytes per K=16 step inside the
+                        // 128-byte swizzle row; MN-major: 16 contraction rows = 2048 bytes
+                        const uint64_t da = da0 + (uint64_t)(AMN ? (k * 2048) >> 4 : 2 * k);
+                        const uint64_t db = db0 + (uint64_t)(BMN ? (k * 2048) >> 4 : 2 * k);
                         umma_f16(tmem_acc, da, db, IDESC, (i > 0 || k > 0) ? 1u : 0u);
                     }
                     umma_commit(&empty_bar[s]);                    // frees the slot once these MMAs have read it
