@@ -274,6 +274,12 @@ def run_ours(args, w):
         roof = {"kernel": top_name, "bound": "hbm", "achieved": round(ach, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": round(ach / peaks["hbm_gbs"], 4), "traffic": None, "peak_src": peaks["src"],
                 "share_of_step": round(top["s"] / total_s, 3)}
+    tr = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tr):
+        ent = json.load(open(tr)).get(top_name)
+        if ent and args.workload == "cfg2":
+            roof["traffic"] = ent["bytes"]                 # ncu --set full capture of this kernel at this shape
+            roof["traffic_src"] = "profiles/" + ent["capture"] if ent["capture"].startswith("raw/") else ent["capture"]
     roof_magno = None
     if magno:
         magno_s = sum(r["us"] for r in magno) * 1e-6
