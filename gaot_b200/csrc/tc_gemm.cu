@@ -13,7 +13,6 @@
 //               (or 128-bit red.add for split-K)
 //   3 stages x 32 KB leave room for two CTAs per SM, so one CTA's epilogue overlaps the other's main loop.
 #include <cuda.h>
-#include <cstdlib>
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -83,7 +82,6 @@ struct TcArgs {
     int out_bf16, splits, accumulate;
     int64_t gm, gn;                   // tile grid
     int act; float* pre;              // optional activation (GAOT_ACT_*) and fp32 pre-activation output
-    int dbg;                          // GAOT_TC_DEBUG bit mask (performance experiments only; 0 in production)
 };
 
 // MN-major operand tile: [64 contraction rows][64 elements = 128 bytes] blocks of 8 KB, one per 64 output
@@ -155,11 +153,10 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 for (int i = 0; i < nkb; ++i, ++it) {
                     const int s = (int)(it % TC_STAGES);
                     mbar_wait(&empty_bar[s], ((it / TC_STAGES) & 1u) ^ 1u);
-                    mbar_expect_tx(&full_bar[s], (g.dbg & 4) ? B_BYTES : STAGE_BYTES);
+                    mbar_expect_tx(&full_bar[s], STAGE_BYTES);
                     uint8_t* st = smem + s * STAGE_BYTES;
                     const int kc = (int)((kb0 + i) * TC_BK);
-                    if (g.dbg & 4) {}
-                    else if (!AMN) tma_load_2d(st, &tmA, &full_bar[s], kc, (int)m0);
+                    if (!AMN) tma_load_2d(st, &tmA, &full_bar[s], kc, (int)m0);
                     else {
 #pragma unroll
                         for (int j = 0; j < TC_BM / 64; ++j) tma_load_2d(st + j * 8192, &tmA, &full_bar[s], (int)m0 + 64 * j, kc);
@@ -194,7 +191,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     const uint64_t da0 = AMN ? make_smem_desc_mn(sa) : make_smem_desc_sw128(sa);
                     const uint64_t db0 = BMN ? make_smem_desc_mn(sb) : make_smem_desc_sw128(sb);
 #pragma unroll
-                    for (int k = 0; k < ((g.dbg & 2) ? 1 : TC_BK / 16); ++k) {
+                    for (int k = 0; k < TC_BK / 16; ++k) {
                         // start-address field counts 16-byte units.  K-major: +32 bytes per K=16 step inside the
                         // 128-byte swizzle row; MN-major: 16 contraction rows = 2048 bytes
                         const uint64_t da = da0 + (uint64_t)(AMN ? (k * 2048) >> 4 : 2 * k);
@@ -248,7 +245,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     for (int j = 0; j < 32; ++j) r[j] = 0u;
                 }
                 const int64_t n = n0 + c0;
-                if (n >= g.N || (g.dbg & 1)) continue;             // warp-uniform
+                if (n >= g.N) continue;                            // warp-uniform
                 __syncwarp();
 #pragma unroll
                 for (int j = 0; j < 32; j += 4)
@@ -433,9 +430,6 @@ int launch_tc(const void* A, const void* B, TcArgs& g, cudaStream_t st) {
     if (rc) return rc;
     rc = BMN ? make_map_mn(&tb, B, g.K, g.N) : make_map(&tb, B, g.N, g.K, BN);
     if (rc) return rc;
-    static int dbg = -1;
-    if (dbg < 0) { const char* e = getenv("GAOT_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
-    g.dbg = dbg;
     g.gm = (g.M + TC_BM - 1) / TC_BM;
     g.gn = (g.N + BN - 1) / BN;
     const int64_t kblocks = (g.K + TC_BK - 1) / TC_BK, tiles = g.gm * g.gn;
@@ -478,7 +472,7 @@ GAOT_API int gaot_gemm_bf16(const void* A, const void* B, void* C, int64_t M, in
     if (out_bf16 && accumulate) return GAOT_E_BADARG;
     if (act < 0 || act > 2 || ((act || pre) && accumulate)) return GAOT_E_BADARG;
     if (M > 0x7fffffffLL || N > 0x7fffffffLL || K > 0x7fffffffLL) return GAOT_E_BADARG;
-    TcArgs g{C, M, N, K, bias, add, add ? add_rows : 1, ldadd, out_bf16, 1, accumulate, 0, 0, act, pre, 0};
+    TcArgs g{C, M, N, K, bias, add, add ? add_rows : 1, ldadd, out_bf16, 1, accumulate, 0, 0, act, pre};
     cudaStream_t st = (cudaStream_t)stream;
     if (N <= 64) return launch_tc<64, false, false>(A, B, g, st);
     return launch_tc<128, false, false>(A, B, g, st);
@@ -491,7 +485,7 @@ GAOT_API int gaot_gemm_bf16_nn(const void* A, const void* B, void* C, int64_t M,
         (reinterpret_cast<uintptr_t>(C) & 15))
         return GAOT_E_ALIGN;
     if (M > 0x7fffffffLL || N > 0x7fffffffLL || K > 0x7fffffffLL) return GAOT_E_BADARG;
-    TcArgs g{C, M, N, K, nullptr, nullptr, 1, 0, out_bf16, 1, 0, 0, 0, 0, nullptr, 0};
+    TcArgs g{C, M, N, K, nullptr, nullptr, 1, 0, out_bf16, 1, 0, 0, 0, 0, nullptr};
     cudaStream_t st = (cudaStream_t)stream;
     if (N <= 64) return launch_tc<64, false, true>(A, B, g, st);
     return launch_tc<128, false, true>(A, B, g, st);
@@ -504,7 +498,7 @@ GAOT_API int gaot_gemm_bf16_tn(const void* A, const void* B, float* C, int64_t M
         (reinterpret_cast<uintptr_t>(C) & 15))
         return GAOT_E_ALIGN;                       // TMA: 16-byte aligned base and row pitch
     if (M > 0x7fffffffLL || N > 0x7fffffffLL || R > 0x7fffffffLL) return GAOT_E_BADARG;
-    TcArgs g{C, M, N, R, nullptr, nullptr, 1, 0, 0, 1, accumulate, 0, 0, 0, nullptr, 0};
+    TcArgs g{C, M, N, R, nullptr, nullptr, 1, 0, 0, 1, accumulate, 0, 0, 0, nullptr};
     cudaStream_t st = (cudaStream_t)stream;
     if (N <= 64) return launch_tc<64, true, true>(A, B, g, st);
     return launch_tc<128, true, true>(A, B, g, st);

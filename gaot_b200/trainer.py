@@ -36,11 +36,13 @@ class TrainStep:
         self.flat_grad = torch.zeros(o, dtype=torch.float32, device=dev)
         self.exp_avg = torch.zeros(o, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(o, dtype=torch.float32, device=dev)
+        self.grad_views = []
         for p, off in zip(self.params, offs):
             view = self.flat_param[off:off + p.numel()].view_as(p)
             view.copy_(p.data)
             p.data = view
-            p.grad = self.flat_grad[off:off + p.numel()].view_as(p)
+            self.grad_views.append(self.flat_grad[off:off + p.numel()].view_as(p))
+            p.grad = None
         self.num_params = n
         self.step_count = 0
         if self.distributed and self.world > 1:
@@ -48,7 +50,21 @@ class TrainStep:
 
     # ---- the four calls of optimizers.py:252-255 ---------------------------------------------------
     def zero_grad(self):
-        self.flat_grad.zero_()
+        """Gradients are ASSIGNED by autograd (p.grad = None before backward) and gathered into the flat buffer
+        by one multi-tensor copy, instead of 60+ per-parameter accumulate kernels into pre-zeroed views."""
+        for p in self.params:
+            p.grad = None
+
+    def gather_gradients(self):
+        srcs, dsts = [], []
+        for p, v in zip(self.params, self.grad_views):
+            if p.grad is None:
+                v.zero_()
+            else:
+                srcs.append(p.grad)
+                dsts.append(v)
+        if srcs:
+            torch._foreach_copy_(dsts, srcs)
 
     def reduce_gradients(self):
         if self.distributed and self.world > 1:
@@ -62,6 +78,7 @@ class TrainStep:
     def _finish(self, pred, y):
         loss = ops.mse_loss(pred, y)
         loss.backward()
+        self.gather_gradients()
         self.reduce_gradients()
         self.optimizer_step()
         return loss.detach()
@@ -95,6 +112,7 @@ class TrainStep:
                               decoder_nbrs=decoder_nbrs)
             loss = ops.mse_loss(pred, y_static)
             loss.backward()
+            self.gather_gradients()
             return loss.detach()
 
         side = torch.cuda.Stream()

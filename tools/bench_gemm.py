@@ -1,5 +1,4 @@
-"""Micro-benchmark of the tcgen05 GEMM at the processor's shapes (GPU box).  GAOT_TC_DEBUG=1|2|4 switch off the
-epilogue stores / three quarters of the MMAs / the A-operand loads to locate the bottleneck."""
+"""Micro-benchmark of the tcgen05 GEMM at the processor's shapes (GPU box)."""
 import os
 import sys
 
@@ -24,4 +23,4 @@ for M, N, K, o16 in shapes:
     e1.record()
     torch.cuda.synchronize()
     us = e0.elapsed_time(e1) / 20 * 1e3
-    print(f"dbg={os.environ.get('GAOT_TC_DEBUG', '0')} M={M} N={N} K={K} out_bf16={o16}: {us:.1f} us  {2.0 * M * N * K / us / 1e6:.0f} TFLOP/s")
+    print(f"M={M} N={N} K={K} out_bf16={o16}: {us:.1f} us  {2.0 * M * N * K / us / 1e6:.0f} TFLOP/s")
