@@ -37,16 +37,16 @@ constexpr int FB = 8;        // samples per work item
 // ---------------------------------------------------------------------------------------------
 // (1) forward.  G lanes x float4 = one channel row; item = (row, chunk of FB samples)
 // ---------------------------------------------------------------------------------------------
+// Work items (row, chunk of FB samples) are walked with a persistent grid-stride loop; the CSR bounds of the
+// item after next and the first neighbour index of the next item are fetched while the current item is being
+// processed, so an item costs one dependent memory round trip (its feature rows) instead of three.
 template <int G, int CIN>
 __global__ void __launch_bounds__(256)
 lift_aggregate_fwd_kernel(const float* __restrict__ pn, const float* __restrict__ Wl, const float* __restrict__ bl,
                           const float* __restrict__ w, const int64_t* __restrict__ index, const int64_t* __restrict__ rs,
                           float* __restrict__ out, int B, int64_t Ns, int64_t Nd, int C, int64_t n_items) {
-    const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const int64_t ngroups = (int64_t)gridDim.x * blockDim.x / G;
     const int gl = threadIdx.x % G;
-    if (gid >= n_items) return;
-    const int64_t row = gid % Nd;
-    const int b0 = (int)(gid / Nd) * FB;
     const int nvec = C >> 2;
     const int c0 = min(gl, nvec - 1) * 4;
     float4 wl[CIN];                                   // Wl[c0..c0+3, i]
@@ -55,19 +55,28 @@ lift_aggregate_fwd_kernel(const float* __restrict__ pn, const float* __restrict_
         wl[i] = make_float4(__ldg(Wl + (c0 + 0) * CIN + i), __ldg(Wl + (c0 + 1) * CIN + i), __ldg(Wl + (c0 + 2) * CIN + i),
                             __ldg(Wl + (c0 + 3) * CIN + i));
     const float4 blv = ldg4(bl + c0);
-    int64_t boff[FB];
+    int64_t item = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    int64_t a = 0, e = 0, na = 0, ne = 0, j0 = 0;
+    if (item < n_items) { a = __ldg(rs + item % Nd); e = __ldg(rs + item % Nd + 1); }
+    if (item + ngroups < n_items) { na = __ldg(rs + (item + ngroups) % Nd); ne = __ldg(rs + (item + ngroups) % Nd + 1); }
+    if (a < e) j0 = __ldg(index + a);
+    for (; item < n_items; item += ngroups) {
+        int64_t nna = 0, nne = 0, nj0 = 0;
+        if (item + 2 * ngroups < n_items) { nna = __ldg(rs + (item + 2 * ngroups) % Nd); nne = __ldg(rs + (item + 2 * ngroups) % Nd + 1); }
+        if (na < ne) nj0 = __ldg(index + na);
+        const int64_t row = item % Nd;
+        const int b0 = (int)(item / Nd) * FB;
+        int64_t boff[FB];
 #pragma unroll
-    for (int bb = 0; bb < FB; ++bb) boff[bb] = (int64_t)min(b0 + bb, B - 1) * Ns * CIN;
-    // s[bb][i] = sum_e w[e,c] pn[b,j,i] (per lane: 4 channels), sw = sum_e w[e,c]
-    float4 s[FB][CIN];
-    float4 sw = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int bb = 0; bb < FB; ++bb) boff[bb] = (int64_t)min(b0 + bb, B - 1) * Ns * CIN;
+        // s[bb][i] = sum_e w[e,c] pn[b,j,i] (per lane: 4 channels), sw = sum_e w[e,c]
+        float4 s[FB][CIN];
+        float4 sw = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int bb = 0; bb < FB; ++bb)
+        for (int bb = 0; bb < FB; ++bb)
 #pragma unroll
-        for (int i = 0; i < CIN; ++i) s[bb][i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    const int64_t a = __ldg(rs + row), e = __ldg(rs + row + 1);
-    if (a < e) {
-        int64_t j = __ldg(index + a);
+            for (int i = 0; i < CIN; ++i) s[bb][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        int64_t j = j0;
         for (int64_t it = a; it < e; ++it) {
             const int64_t jn = __ldg(index + ((it + 1 < e) ? it + 1 : it));
             const float4 wv = ldg4(w + it * C + c0);
@@ -83,17 +92,18 @@ lift_aggregate_fwd_kernel(const float* __restrict__ pn, const float* __restrict_
                 for (int i = 0; i < CIN; ++i) fma4s(s[bb][i], wv, p[bb][i]);
             j = jn;
         }
-    }
-    if (gl < nvec) {
+        if (gl < nvec) {
 #pragma unroll
-        for (int bb = 0; bb < FB; ++bb) {
-            if (b0 + bb < B) {
-                float4 o = make_float4(blv.x * sw.x, blv.y * sw.y, blv.z * sw.z, blv.w * sw.w);
+            for (int bb = 0; bb < FB; ++bb) {
+                if (b0 + bb < B) {
+                    float4 o = make_float4(blv.x * sw.x, blv.y * sw.y, blv.z * sw.z, blv.w * sw.w);
 #pragma unroll
-                for (int i = 0; i < CIN; ++i) fma4(o, wl[i], s[bb][i]);
-                *reinterpret_cast<float4*>(out + ((int64_t)(b0 + bb) * Nd + row) * C + c0) = o;
+                    for (int i = 0; i < CIN; ++i) fma4(o, wl[i], s[bb][i]);
+                    *reinterpret_cast<float4*>(out + ((int64_t)(b0 + bb) * Nd + row) * C + c0) = o;
+                }
             }
         }
+        a = na; e = ne; j0 = nj0; na = nna; ne = nne;
     }
 }
 
@@ -197,27 +207,36 @@ __global__ void __launch_bounds__(256)
 agno_dot_fwd_kernel(const float* __restrict__ r, const float* __restrict__ u, const int64_t* __restrict__ index,
                     const int64_t* __restrict__ rs, float* __restrict__ out, int B, int64_t Ns, int64_t Nd, int64_t E,
                     int C, int64_t n_items) {
-    const int64_t gid_raw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    // persistent grid-stride walk with cross-item prefetch (see lift_aggregate_fwd_kernel); every lane of a warp
+    // iterates the same number of times because the group shuffles below need full warps
+    const int64_t ngroups = (int64_t)gridDim.x * blockDim.x / G;
     const int gl = threadIdx.x % G;
-    const bool valid = gid_raw < n_items;             // no early exit: the group shuffles below need full warps
-    const int64_t gid = valid ? gid_raw : n_items - 1;
-    const int64_t row = gid % Nd;
-    const int b0 = (int)(gid / Nd) * FB;
     const int nvec = C >> 2;
     const bool act = gl < nvec;
     const int c0 = min(gl, nvec - 1) * 4;
-    int64_t boff[FB];
+    const int64_t first = ((int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31)) / G;      // first group of this warp
+    int64_t item = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    int64_t a = 0, e = 0, na = 0, ne = 0, j0 = 0;
+    if (item < n_items) { a = __ldg(rs + item % Nd); e = __ldg(rs + item % Nd + 1); }
+    if (item + ngroups < n_items) { na = __ldg(rs + (item + ngroups) % Nd); ne = __ldg(rs + (item + ngroups) % Nd + 1); }
+    if (a < e) j0 = __ldg(index + a);
+    for (int64_t base = first; base < n_items; base += ngroups, item += ngroups) {
+        const bool valid = item < n_items;
+        int64_t nna = 0, nne = 0, nj0 = 0;
+        if (item + 2 * ngroups < n_items) { nna = __ldg(rs + (item + 2 * ngroups) % Nd); nne = __ldg(rs + (item + 2 * ngroups) % Nd + 1); }
+        if (na < ne) nj0 = __ldg(index + na);
+        const int64_t row = valid ? item % Nd : 0;
+        const int b0 = valid ? (int)(item / Nd) * FB : 0;
+        int64_t boff[FB];
 #pragma unroll
-    for (int bb = 0; bb < FB; ++bb) boff[bb] = (int64_t)min(b0 + bb, B - 1) * Ns * C;
-    float acc[FB][COUT];
+        for (int bb = 0; bb < FB; ++bb) boff[bb] = (int64_t)min(b0 + bb, B - 1) * Ns * C;
+        float acc[FB][COUT];
 #pragma unroll
-    for (int bb = 0; bb < FB; ++bb)
+        for (int bb = 0; bb < FB; ++bb)
 #pragma unroll
-        for (int o = 0; o < COUT; ++o) acc[bb][o] = 0.f;
-    const int64_t a = __ldg(rs + row), e = __ldg(rs + row + 1);
-    if (a < e) {
-        int64_t j = __ldg(index + a);
-        for (int64_t it = a; it < e; ++it) {
+            for (int o = 0; o < COUT; ++o) acc[bb][o] = 0.f;
+        int64_t j = j0;
+        for (int64_t it = a; it < e; ++it) {          // a == e for invalid items
             const int64_t jn = __ldg(index + ((it + 1 < e) ? it + 1 : it));
             float4 uv[COUT], rv[FB];
 #pragma unroll
@@ -232,23 +251,24 @@ agno_dot_fwd_kernel(const float* __restrict__ r, const float* __restrict__ u, co
             }
             j = jn;
         }
-    }
-    // reduce the per-lane partial dot products over the G lanes of the group
-#pragma unroll
-    for (int bb = 0; bb < FB; ++bb)
-#pragma unroll
-        for (int o = 0; o < COUT; ++o) {
-            float v = acc[bb][o];
-#pragma unroll
-            for (int off = G / 2; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off, G);
-            acc[bb][o] = v;
-        }
-    if (gl == 0 && valid) {
+        // reduce the per-lane partial dot products over the G lanes of the group
 #pragma unroll
         for (int bb = 0; bb < FB; ++bb)
-            if (b0 + bb < B)
 #pragma unroll
-                for (int o = 0; o < COUT; ++o) out[((int64_t)(b0 + bb) * Nd + row) * COUT + o] = acc[bb][o];
+            for (int o = 0; o < COUT; ++o) {
+                float v = acc[bb][o];
+#pragma unroll
+                for (int off = G / 2; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off, G);
+                acc[bb][o] = v;
+            }
+        if (gl == 0 && valid) {
+#pragma unroll
+            for (int bb = 0; bb < FB; ++bb)
+                if (b0 + bb < B)
+#pragma unroll
+                    for (int o = 0; o < COUT; ++o) out[((int64_t)(b0 + bb) * Nd + row) * COUT + o] = acc[bb][o];
+        }
+        a = na; e = ne; j0 = nj0; na = nna; ne = nne;
     }
 }
 
@@ -356,8 +376,8 @@ GAOT_API int gaot_lift_aggregate_fwd(const float* pn, const float* Wl, const flo
     if (Nd == 0) return 0;
     const int g_ = group_of(C);
     const int64_t n_items = Nd * ((B + FB - 1) / FB);
-    const int64_t blocks = (n_items * g_ + 255) / 256;
-    if (blocks > 0x7fffffffLL) return GAOT_E_BADARG;
+    int64_t blocks = (n_items * g_ + 255) / 256;
+    if (blocks > 148 * 2) blocks = 148 * 2;                 // persistent (2 resident CTAs/SM at 128 registers): grid-stride loop
     cudaStream_t st = (cudaStream_t)stream;
     GAOT_DISPATCH_G(g_, GAOT_DISPATCH_N((int)Cin, CIN, (lift_aggregate_fwd_kernel<G, CIN><<<(unsigned)blocks, 256, 0, st>>>(
                                                           pn, Wl, bl, w, index, row_splits, out, (int)B, Ns, Nd, (int)C, n_items))));
@@ -395,8 +415,8 @@ GAOT_API int gaot_agno_dot_fwd(const float* r, const float* u, const int64_t* in
     if (Nd == 0) return 0;
     const int g_ = group_of(C);
     const int64_t n_items = Nd * ((B + FB - 1) / FB);
-    const int64_t blocks = (n_items * g_ + 255) / 256;
-    if (blocks > 0x7fffffffLL) return GAOT_E_BADARG;
+    int64_t blocks = (n_items * g_ + 255) / 256;
+    if (blocks > 148 * 2) blocks = 148 * 2;                 // persistent (2 resident CTAs/SM at 128 registers): grid-stride loop
     cudaStream_t st = (cudaStream_t)stream;
     GAOT_DISPATCH_G(g_, GAOT_DISPATCH_N((int)Cout, COUT, (agno_dot_fwd_kernel<G, COUT><<<(unsigned)blocks, 256, 0, st>>>(
                                                             r, u, index, row_splits, out, (int)B, Ns, Nd, E, (int)C, n_items))));

@@ -41,8 +41,22 @@ for r in range(10):
     ev[2].record(); b = ops.agno_aggregate(fl, wd, pd); ev[3].record()
     torch.cuda.synchronize()
     ts.append((ev[0].elapsed_time(ev[1]) * 1e3, ev[2].elapsed_time(ev[3]) * 1e3))
+# fused operators (default encoder / decoder paths)
+pn = synth.normal((B, N, 1), 5).to(dev)
+Wl, bl = synth.normal((C, 1), 6).to(dev), synth.normal((C,), 7).to(dev)
+u = synth.normal((1, pd.E, C), 8).to(dev)
+tf = []
+for r in range(10):
+    flush.zero_()
+    ev[0].record(); a2 = ops.lift_aggregate(pn, Wl, bl, we.detach(), pe); ev[1].record()
+    flush.zero_()
+    ev[2].record(); b2 = ops.agno_dot(fl.detach(), u, pd); ev[3].record()
+    torch.cuda.synchronize()
+    tf.append((ev[0].elapsed_time(ev[1]) * 1e3, ev[2].elapsed_time(ev[3]) * 1e3))
 E = pe.E
 alg = 4 * C * B * (N + 4096) + 4 * C * E + 8 * E + 8 * 4097
 print("E", E, "enc fwd us (L2 flushed) min/med", min(t[0] for t in ts), sorted(t[0] for t in ts)[5],
       "GB/s at min", alg / min(t[0] for t in ts) / 1e3)
 print("dec fwd us min/med", min(t[1] for t in ts), sorted(t[1] for t in ts)[5], "GB/s at min", alg / min(t[1] for t in ts) / 1e3)
+print("fused lift_aggregate fwd us min/med", min(t[0] for t in tf), sorted(t[0] for t in tf)[5], "alg GB/s at min", alg / min(t[0] for t in tf) / 1e3)
+print("fused agno_dot fwd us min/med", min(t[1] for t in tf), sorted(t[1] for t in tf)[5], "alg GB/s at min", alg / min(t[1] for t in tf) / 1e3)
