@@ -32,7 +32,7 @@ __device__ __forceinline__ float dot4(const float4& x, const float4& y) {
     return fmaf(x.x, y.x, fmaf(x.y, y.y, fmaf(x.z, y.z, x.w * y.w)));
 }
 
-constexpr int FB = 8;        // samples per work item
+// FB = samples per work item: template parameter (8 / 4 / 2 / 1 by batch size, so a small batch does no redundant work)
 
 // ---------------------------------------------------------------------------------------------
 // (1) forward.  G lanes x float4 = one channel row; item = (row, chunk of FB samples)
@@ -40,7 +40,7 @@ constexpr int FB = 8;        // samples per work item
 // Work items (row, chunk of FB samples) are walked with a persistent grid-stride loop; the CSR bounds of the
 // item after next and the first neighbour index of the next item are fetched while the current item is being
 // processed, so an item costs one dependent memory round trip (its feature rows) instead of three.
-template <int G, int CIN>
+template <int G, int CIN, int FB>
 __global__ void __launch_bounds__(256)
 lift_aggregate_fwd_kernel(const float* __restrict__ pn, const float* __restrict__ Wl, const float* __restrict__ bl,
                           const float* __restrict__ w, const int64_t* __restrict__ index, const int64_t* __restrict__ rs,
@@ -108,7 +108,7 @@ lift_aggregate_fwd_kernel(const float* __restrict__ pn, const float* __restrict_
 }
 
 // (1) backward: dw (atomics over the sample chunks), dWl / dbl (CTA partial sums -> atomics)
-template <int G, int CIN>
+template <int G, int CIN, int FB>
 __global__ void __launch_bounds__(256)
 lift_aggregate_bwd_kernel(const float* __restrict__ g, const float* __restrict__ pn, const float* __restrict__ Wl,
                           const float* __restrict__ bl, const float* __restrict__ w, const int64_t* __restrict__ index,
@@ -202,7 +202,7 @@ lift_aggregate_bwd_kernel(const float* __restrict__ g, const float* __restrict__
 // ---------------------------------------------------------------------------------------------
 // (2) forward: out[b,n,o] = sum_e <u[o,e,:], r[b,idx_e,:]>
 // ---------------------------------------------------------------------------------------------
-template <int G, int COUT>
+template <int G, int COUT, int FB>
 __global__ void __launch_bounds__(256)
 agno_dot_fwd_kernel(const float* __restrict__ r, const float* __restrict__ u, const int64_t* __restrict__ index,
                     const int64_t* __restrict__ rs, float* __restrict__ out, int B, int64_t Ns, int64_t Nd, int64_t E,
@@ -273,7 +273,7 @@ agno_dot_fwd_kernel(const float* __restrict__ r, const float* __restrict__ u, co
 }
 
 // (2) dr on the transposed graph: dr[b,j,c] = sum_{k in T(j)} sum_o u[o, perm_k, c] * g[b, trow_k, o]
-template <int G, int COUT>
+template <int G, int COUT, int FB>
 __global__ void __launch_bounds__(256)
 agno_dot_bwd_r_kernel(const float* __restrict__ g, const float* __restrict__ u, const int64_t* __restrict__ t_rows,
                       const int64_t* __restrict__ t_perm, const int64_t* __restrict__ ts, float* __restrict__ dr, int B,
@@ -355,11 +355,15 @@ agno_dot_bwd_u_kernel(const float* __restrict__ g, const float* __restrict__ r, 
 }
 
 inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+inline int fb_of(int64_t B) { return B >= 8 ? 8 : (B >= 4 ? 4 : (B >= 2 ? 2 : 1)); }
 inline int group_of(int64_t C) { const int nv = (int)(C / 4); return nv <= 4 ? 4 : (nv <= 8 ? 8 : (nv <= 16 ? 16 : 32)); }
 
 #define GAOT_DISPATCH_G(G_, ...)  \
     switch (G_) { case 4: { constexpr int G = 4; __VA_ARGS__; break; } case 8: { constexpr int G = 8; __VA_ARGS__; break; } \
                   case 16: { constexpr int G = 16; __VA_ARGS__; break; } default: { constexpr int G = 32; __VA_ARGS__; break; } }
+#define GAOT_DISPATCH_FB(FB_, ...)  \
+    switch (FB_) { case 8: { constexpr int FB = 8; __VA_ARGS__; break; } case 4: { constexpr int FB = 4; __VA_ARGS__; break; } \
+                   case 2: { constexpr int FB = 2; __VA_ARGS__; break; } default: { constexpr int FB = 1; __VA_ARGS__; break; } }
 #define GAOT_DISPATCH_N(N_, NAME, ...)  \
     switch (N_) { case 1: { constexpr int NAME = 1; __VA_ARGS__; break; } case 2: { constexpr int NAME = 2; __VA_ARGS__; break; } \
                   case 3: { constexpr int NAME = 3; __VA_ARGS__; break; } case 4: { constexpr int NAME = 4; __VA_ARGS__; break; } \
@@ -375,12 +379,13 @@ GAOT_API int gaot_lift_aggregate_fwd(const float* pn, const float* Wl, const flo
     if (!al16(w) || !al16(out) || !al16(bl)) return GAOT_E_ALIGN;
     if (Nd == 0) return 0;
     const int g_ = group_of(C);
-    const int64_t n_items = Nd * ((B + FB - 1) / FB);
+    const int fb = fb_of(B);
+    const int64_t n_items = Nd * ((B + fb - 1) / fb);
     int64_t blocks = (n_items * g_ + 255) / 256;
     if (blocks > 148 * 2) blocks = 148 * 2;                 // persistent (2 resident CTAs/SM at 128 registers): grid-stride loop
     cudaStream_t st = (cudaStream_t)stream;
-    GAOT_DISPATCH_G(g_, GAOT_DISPATCH_N((int)Cin, CIN, (lift_aggregate_fwd_kernel<G, CIN><<<(unsigned)blocks, 256, 0, st>>>(
-                                                          pn, Wl, bl, w, index, row_splits, out, (int)B, Ns, Nd, (int)C, n_items))));
+    GAOT_DISPATCH_FB(fb, GAOT_DISPATCH_G(g_, GAOT_DISPATCH_N((int)Cin, CIN, (lift_aggregate_fwd_kernel<G, CIN, FB><<<(unsigned)blocks, 256, 0, st>>>(
+                                                          pn, Wl, bl, w, index, row_splits, out, (int)B, Ns, Nd, (int)C, n_items)))));
     GAOT_RETURN_LAST();
 }
 
@@ -394,16 +399,17 @@ GAOT_API int gaot_lift_aggregate_bwd(const float* g, const float* pn, const floa
     GAOT_CHECK(cudaMemsetAsync(dWl, 0, sizeof(float) * (size_t)(C * Cin), st));
     GAOT_CHECK(cudaMemsetAsync(dbl, 0, sizeof(float) * (size_t)C, st));
     if (Nd == 0 || E == 0) return 0;
-    const int chunks = (int)((B + FB - 1) / FB);
+    const int fb = fb_of(B);
+    const int chunks = (int)((B + fb - 1) / fb);
     if (chunks > 1) GAOT_CHECK(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)(E * C), st));
     const int g_ = group_of(C);
     const int64_t n_items = Nd * chunks;
     const int64_t blocks = (n_items * g_ + 255) / 256;
     if (blocks > 0x7fffffffLL) return GAOT_E_BADARG;
     const size_t smem = sizeof(float) * (size_t)(C * (Cin + 1));
-    GAOT_DISPATCH_G(g_, GAOT_DISPATCH_N((int)Cin, CIN, (lift_aggregate_bwd_kernel<G, CIN><<<(unsigned)blocks, 256, smem, st>>>(
+    GAOT_DISPATCH_FB(fb, GAOT_DISPATCH_G(g_, GAOT_DISPATCH_N((int)Cin, CIN, (lift_aggregate_bwd_kernel<G, CIN, FB><<<(unsigned)blocks, 256, smem, st>>>(
                                                           g, pn, Wl, bl, w, index, row_splits, dw, dWl, dbl, (int)B, Ns, Nd, (int)C,
-                                                          n_items, chunks))));
+                                                          n_items, chunks)))));
     GAOT_RETURN_LAST();
 }
 
@@ -414,12 +420,13 @@ GAOT_API int gaot_agno_dot_fwd(const float* r, const float* u, const int64_t* in
     if (!al16(r) || !al16(u)) return GAOT_E_ALIGN;
     if (Nd == 0) return 0;
     const int g_ = group_of(C);
-    const int64_t n_items = Nd * ((B + FB - 1) / FB);
+    const int fb = fb_of(B);
+    const int64_t n_items = Nd * ((B + fb - 1) / fb);
     int64_t blocks = (n_items * g_ + 255) / 256;
     if (blocks > 148 * 2) blocks = 148 * 2;                 // persistent (2 resident CTAs/SM at 128 registers): grid-stride loop
     cudaStream_t st = (cudaStream_t)stream;
-    GAOT_DISPATCH_G(g_, GAOT_DISPATCH_N((int)Cout, COUT, (agno_dot_fwd_kernel<G, COUT><<<(unsigned)blocks, 256, 0, st>>>(
-                                                            r, u, index, row_splits, out, (int)B, Ns, Nd, E, (int)C, n_items))));
+    GAOT_DISPATCH_FB(fb, GAOT_DISPATCH_G(g_, GAOT_DISPATCH_N((int)Cout, COUT, (agno_dot_fwd_kernel<G, COUT, FB><<<(unsigned)blocks, 256, 0, st>>>(
+                                                            r, u, index, row_splits, out, (int)B, Ns, Nd, E, (int)C, n_items)))));
     GAOT_RETURN_LAST();
 }
 
@@ -434,11 +441,12 @@ GAOT_API int gaot_agno_dot_bwd(const float* g, const float* r, const float* u, c
     const int g_ = group_of(C);
     int launches = 0;
     if (dr && Ns > 0) {
-        const int64_t n_items = Ns * ((B + FB - 1) / FB);
+        const int fb = fb_of(B);
+        const int64_t n_items = Ns * ((B + fb - 1) / fb);
         const int64_t blocks = (n_items * g_ + 255) / 256;
         if (blocks > 0x7fffffffLL) return GAOT_E_BADARG;
-        GAOT_DISPATCH_G(g_, GAOT_DISPATCH_N((int)Cout, COUT, (agno_dot_bwd_r_kernel<G, COUT><<<(unsigned)blocks, 256, 0, st>>>(
-                                                                g, u, t_rows, t_perm, t_splits, dr, (int)B, Ns, Nd, E, (int)C, n_items))));
+        GAOT_DISPATCH_FB(fb, GAOT_DISPATCH_G(g_, GAOT_DISPATCH_N((int)Cout, COUT, (agno_dot_bwd_r_kernel<G, COUT, FB><<<(unsigned)blocks, 256, 0, st>>>(
+                                                                g, u, t_rows, t_perm, t_splits, dr, (int)B, Ns, Nd, E, (int)C, n_items)))));
         ++launches;
     }
     if (du && Nd > 0 && E > 0) {
