@@ -35,6 +35,10 @@ WORKLOADS = {
                  patch=2, dh=256, layers=3, heads=8, desc="Poisson-Gauss 2D fx, N=9216, latent 64x64, B=32/GPU"),
     "cfg2_16k": dict(d=2, n=16384, latent=(64, 64), B=32, cin=1, cout=1, radius=0.033, C=64, hidden=64, mlp_layers=3,
                      patch=2, dh=256, layers=3, heads=8, desc="Poisson-Gauss 2D fx, N=16384, latent 64x64, B=32/GPU"),
+    # BASELINE.json configs[2]: airfoil-like 2-D vx mode - every sample has its own mesh and its own radius graphs
+    "cfg3": dict(d=2, n=16384, latent=(64, 64), B=64, cin=3, cout=1, radius=0.033, C=64, hidden=64, mlp_layers=3,
+                 patch=2, dh=256, layers=3, heads=8, vx=True,
+                 desc="NACA0012-like 2D vx (per-sample clustered meshes + per-sample graphs), N=16384, B=64/GPU"),
     "cfg4": dict(d=2, n=16384, latent=(64, 64), B=16, cin=4, cout=2, radius=0.033, C=64, hidden=64, mlp_layers=3,
                  patch=2, dh=256, layers=3, heads=8, desc="ns_gauss-like 2D fx training pair step, N=16384, B=16/GPU"),
     "cfg5": dict(d=3, n=262144, latent=(32, 32, 32), B=1, cin=3, cout=1, radius=0.07, C=48, hidden=64, mlp_layers=3,
@@ -45,7 +49,7 @@ WORKLOADS = {
 def make_config(w):
     from gaot_b200.model import AttentionConfig, MAGNOConfig, TransformerConfig
     mc = MAGNOConfig(coord_dim=w["d"], radius=w["radius"], hidden_size=w["hidden"], mlp_layers=w["mlp_layers"],
-                     lifting_channels=w["C"], neighbor_search_method="native")
+                     lifting_channels=w["C"], neighbor_search_method="native", precompute_edges=bool(w.get("vx")))
     tc = TransformerConfig(patch_size=w["patch"], hidden_size=w["dh"], num_layers=w["layers"],
                            attn_config=AttentionConfig(num_heads=w["heads"], num_kv_heads=w["heads"]))
     return SimpleNamespace(latent_tokens_size=tuple(w["latent"]), args=SimpleNamespace(magno=mc, transformer=tc))
@@ -54,7 +58,10 @@ def make_config(w):
 def synth(w, rank, B):
     from gaot_b200 import synth as cases
     lat = cases.latent_grid(w["latent"])
-    x = cases.uniform_points(w["n"], w["d"], 0)
+    if w.get("vx"):
+        x = torch.stack([cases.clustered_points(w["n"], w["d"], 100 + 1000 * rank + b) for b in range(B)])
+    else:
+        x = cases.uniform_points(w["n"], w["d"], 0)
     pn = cases.normal((B, w["n"], w["cin"]), 1000 + rank)
     tgt = cases.normal((B, w["n"], w["cout"]), 2000 + rank)
     return lat, x, pn, tgt
@@ -166,7 +173,16 @@ def run_ours(args, w):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms)
 
+    vx = bool(w.get("vx"))
+    enc_graphs = dec_graphs = None
+    if vx:      # per-sample graphs built on the GPU in one batched launch each (reference: graph_builder.py:28-87)
+        from gaot_b200 import ops as _o
+        enc_graphs = [[g_] for g_ in _o.radius_csr(x_d, lat_d, w["radius"])]
+        dec_graphs = [[g_] for g_ in _o.radius_csr(lat_d, x_d, w["radius"])]
+
     def eager_step():
+        if vx:
+            return step.variable_coords_step(lat_d, pn_d, tgt_d, x_d, enc_graphs, dec_graphs)
         return step.fixed_coords_step(lat_d, x_d, pn_d, tgt_d)
 
     if args.no_graph:
@@ -174,7 +190,10 @@ def run_ours(args, w):
     else:
         for _ in range(2):
             eager_step()
-        graphed = step.capture_fixed_coords(lat_d, x_d, pn_s, tgt_s)           # static input buffers pn_s / tgt_s
+        if vx:
+            graphed = step.capture_variable_coords(lat_d, pn_s, tgt_s, x_d, enc_graphs, dec_graphs)
+        else:
+            graphed = step.capture_fixed_coords(lat_d, x_d, pn_s, tgt_s)       # static input buffers pn_s / tgt_s
         pn_s.copy_(pn_d); tgt_s.copy_(tgt_d)
 
     def dev_step():
@@ -183,7 +202,12 @@ def run_ours(args, w):
     def e2e_step():
         pn_s.copy_(pn_h, non_blocking=True)
         tgt_s.copy_(tgt_h, non_blocking=True)
-        loss = graphed() if graphed is not None else step.fixed_coords_step(lat_d, x_d, pn_s, tgt_s)
+        if graphed is not None:
+            loss = graphed()
+        elif vx:
+            loss = step.variable_coords_step(lat_d, pn_s, tgt_s, x_d, enc_graphs, dec_graphs)
+        else:
+            loss = step.fixed_coords_step(lat_d, x_d, pn_s, tgt_s)
         return float(loss)                                                     # .item(): D2H read of the loss
 
     W = max(args.warmup, 3)
@@ -228,8 +252,11 @@ def run_ours(args, w):
     # MAGNO scatter (the metric BASELINE.json names).  `achieved` uses the ALGORITHMIC bytes SURVEY.md section 8d
     # assigns to the operator (gather + weight + segment-sum over [B,N,C] features); the fused kernels do that
     # job while touching fewer bytes (`min_bytes`: what the fused formulation has to move), see DESIGN.md section 4.
-    enc_g = model.encoder.neighbor_cache["graph"][1][0]
-    E = int(enc_g["neighbors_index"].numel())
+    if vx:
+        E = sum(int(g_[0]["neighbors_index"].numel()) for g_ in enc_graphs)
+    else:
+        enc_g = model.encoder.neighbor_cache["graph"][1][0]
+        E = int(enc_g["neighbors_index"].numel())
     C, N, M = w["C"], w["n"], lat.shape[0]
     Cin, Cout = w["cin"], w["cout"]
 
@@ -244,52 +271,53 @@ def run_ours(args, w):
     # (the per-call numbers of the eager breakdown step include host launch gaps that are comparable to these
     # 30-60 us kernels).  Median of 7.
     from gaot_b200 import ops as O, synth as S
-    dec_g = model.decoder.neighbor_cache["graph"][1][0]
-    pe, pd = O.graph_plan(enc_g, N), O.graph_plan(dec_g, M)
-    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
-
-    def med_us(fn):
-        ts = []
-        for _ in range(7):
-            flush.zero_()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(); fn(); e1.record()
-            torch.cuda.synchronize()
-            ts.append(e0.elapsed_time(e1) * 1e3)
-        return sorted(ts)[3]
-
-    Bc = B
-    pn_m = S.normal((Bc, N, Cin), 11).to(dev)
-    Wl_m, bl_m = S.normal((C, Cin), 12).to(dev), S.normal((C,), 13).to(dev)
-    we_m, wd_m = S.normal((pe.E, C), 14).to(dev), S.normal((Cout, pd.E, C), 15).to(dev)
-    lat_f = S.normal((Bc, M, C), 16).to(dev)
-    g_enc, g_dec = S.normal((Bc, M, C), 17).to(dev), S.normal((Bc, N, Cout), 18).to(dev)
     magno = []
-    with torch.no_grad():
-        t = med_us(lambda: O.lift_aggregate(pn_m, Wl_m, bl_m, we_m, pe))
-        magno.append(dict(kernel="lift_aggregate_fwd (encoder)", Ns=N, Nd=int(M), us=t, gbs=alg_fwd(Bc, N, M) / t / 1e3,
-                          min_bytes=4.0 * Bc * N * Cin + 4.0 * C * E + 8.0 * E + 4.0 * C * Bc * M))
-        t = med_us(lambda: O.agno_dot(lat_f, wd_m, pd))
-        magno.append(dict(kernel="agno_dot_fwd (decoder)", Ns=int(M), Nd=N, us=t, gbs=alg_fwd(Bc, M, N) / t / 1e3,
-                          min_bytes=4.0 * C * Bc * M + 4.0 * C * E * Cout + 8.0 * E + 4.0 * Bc * N * Cout))
-        dw_, dWl_, dbl_ = torch.empty_like(we_m), torch.empty_like(Wl_m), torch.empty_like(bl_m)
-        t = med_us(lambda: _lib.call("gaot_lift_aggregate_bwd", g_enc.data_ptr(), pn_m.data_ptr(), Wl_m.data_ptr(), bl_m.data_ptr(),
-                                      we_m.data_ptr(), pe.index.data_ptr(), pe.splits.data_ptr(), dw_.data_ptr(), dWl_.data_ptr(),
-                                      dbl_.data_ptr(), Bc, N, int(M), pe.E, C, Cin))
-        magno.append(dict(kernel="lift_aggregate_bwd (encoder)", Ns=N, Nd=int(M), us=t, gbs=alg_bwd(Bc, N, M) / t / 1e3,
-                          min_bytes=4.0 * Bc * N * Cin + 8.0 * C * E + 8.0 * E + 4.0 * C * Bc * M))
-        ts_, tr_, tp_ = pd.transposed()
-        df_, du_ = torch.empty_like(lat_f), torch.empty_like(wd_m)
-        t = med_us(lambda: _lib.call("gaot_agno_dot_bwd", g_dec.data_ptr(), lat_f.data_ptr(), wd_m.data_ptr(), pd.index.data_ptr(),
-                                      pd.splits.data_ptr(), ts_.data_ptr(), tr_.data_ptr(), tp_.data_ptr(), df_.data_ptr(),
-                                      du_.data_ptr(), Bc, int(M), N, pd.E, C, Cout))
-        magno.append(dict(kernel="agno_dot_bwd (decoder, 2 kernels)", Ns=int(M), Nd=N, us=t, gbs=alg_bwd(Bc, M, N) / t / 1e3,
-                          min_bytes=2 * 4.0 * C * Bc * M + 8.0 * C * E * Cout + 16.0 * E + 4.0 * Bc * N * Cout))
-        f_m = S.normal((Bc, N, C), 19).to(dev)
-        t = med_us(lambda: O.agno_aggregate(f_m, we_m, pe))
-        magno.append(dict(kernel="agno_aggregate (unfused encoder fwd)", Ns=N, Nd=int(M), us=t, gbs=alg_fwd(Bc, N, M) / t / 1e3,
-                          min_bytes=alg_fwd(Bc, N, M)))
-    del flush
+    if not vx:
+        dec_g = model.decoder.neighbor_cache["graph"][1][0]
+        pe, pd = O.graph_plan(enc_g, N), O.graph_plan(dec_g, M)
+        flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+
+        def med_us(fn):
+            ts = []
+            for _ in range(7):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); fn(); e1.record()
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1) * 1e3)
+            return sorted(ts)[3]
+
+        Bc = B
+        pn_m = S.normal((Bc, N, Cin), 11).to(dev)
+        Wl_m, bl_m = S.normal((C, Cin), 12).to(dev), S.normal((C,), 13).to(dev)
+        we_m, wd_m = S.normal((pe.E, C), 14).to(dev), S.normal((Cout, pd.E, C), 15).to(dev)
+        lat_f = S.normal((Bc, M, C), 16).to(dev)
+        g_enc, g_dec = S.normal((Bc, M, C), 17).to(dev), S.normal((Bc, N, Cout), 18).to(dev)
+        with torch.no_grad():
+            t = med_us(lambda: O.lift_aggregate(pn_m, Wl_m, bl_m, we_m, pe))
+            magno.append(dict(kernel="lift_aggregate_fwd (encoder)", Ns=N, Nd=int(M), us=t, gbs=alg_fwd(Bc, N, M) / t / 1e3,
+                              min_bytes=4.0 * Bc * N * Cin + 4.0 * C * E + 8.0 * E + 4.0 * C * Bc * M))
+            t = med_us(lambda: O.agno_dot(lat_f, wd_m, pd))
+            magno.append(dict(kernel="agno_dot_fwd (decoder)", Ns=int(M), Nd=N, us=t, gbs=alg_fwd(Bc, M, N) / t / 1e3,
+                              min_bytes=4.0 * C * Bc * M + 4.0 * C * E * Cout + 8.0 * E + 4.0 * Bc * N * Cout))
+            dw_, dWl_, dbl_ = torch.empty_like(we_m), torch.empty_like(Wl_m), torch.empty_like(bl_m)
+            t = med_us(lambda: _lib.call("gaot_lift_aggregate_bwd", g_enc.data_ptr(), pn_m.data_ptr(), Wl_m.data_ptr(), bl_m.data_ptr(),
+                                          we_m.data_ptr(), pe.index.data_ptr(), pe.splits.data_ptr(), dw_.data_ptr(), dWl_.data_ptr(),
+                                          dbl_.data_ptr(), Bc, N, int(M), pe.E, C, Cin))
+            magno.append(dict(kernel="lift_aggregate_bwd (encoder)", Ns=N, Nd=int(M), us=t, gbs=alg_bwd(Bc, N, M) / t / 1e3,
+                              min_bytes=4.0 * Bc * N * Cin + 8.0 * C * E + 8.0 * E + 4.0 * C * Bc * M))
+            ts_, tr_, tp_ = pd.transposed()
+            df_, du_ = torch.empty_like(lat_f), torch.empty_like(wd_m)
+            t = med_us(lambda: _lib.call("gaot_agno_dot_bwd", g_dec.data_ptr(), lat_f.data_ptr(), wd_m.data_ptr(), pd.index.data_ptr(),
+                                          pd.splits.data_ptr(), ts_.data_ptr(), tr_.data_ptr(), tp_.data_ptr(), df_.data_ptr(),
+                                          du_.data_ptr(), Bc, int(M), N, pd.E, C, Cout))
+            magno.append(dict(kernel="agno_dot_bwd (decoder, 2 kernels)", Ns=int(M), Nd=N, us=t, gbs=alg_bwd(Bc, M, N) / t / 1e3,
+                              min_bytes=2 * 4.0 * C * Bc * M + 8.0 * C * E * Cout + 16.0 * E + 4.0 * Bc * N * Cout))
+            f_m = S.normal((Bc, N, C), 19).to(dev)
+            t = med_us(lambda: O.agno_aggregate(f_m, we_m, pe))
+            magno.append(dict(kernel="agno_aggregate (unfused encoder fwd)", Ns=N, Nd=int(M), us=t, gbs=alg_fwd(Bc, N, M) / t / 1e3,
+                              min_bytes=alg_fwd(Bc, N, M)))
+        del flush
     best = max(magno, key=lambda r: r["us"]) if magno else None
     top_name = max(agg, key=lambda k: agg[k]["s"])
     top = agg[top_name]

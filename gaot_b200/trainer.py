@@ -98,18 +98,27 @@ class TrainStep:
         return self._finish(pred, y)
 
     # ---- CUDA-graph replay of the whole forward + loss + backward ---------------------------------
+    def capture_variable_coords(self, latent, x_static, y_static, coords, encoder_graphs, decoder_graphs, warmup=2):
+        """vx-mode counterpart of capture_fixed_coords: per-sample coordinates [B,N,d] and per-sample graphs are
+        static across replays (one batch of meshes), features/targets are fed through the static buffers."""
+        return self._capture(lambda: self.model(latent_tokens_coord=latent, xcoord=coords, pndata=x_static, query_coord=coords,
+                                                encoder_nbrs=encoder_graphs, decoder_nbrs=decoder_graphs), y_static, warmup)
+
     def capture_fixed_coords(self, latent, coord, x_static, y_static, encoder_nbrs=None, decoder_nbrs=None, warmup=2):
         """Capture zero_grad -> forward -> MSE -> backward for STATIC input buffers into one CUDA graph and
         return a `step()` callable that replays it, then all-reduces and runs the fused AdamW kernel (those
         two stay outside the graph: NCCL, and AdamW's per-step bias correction scalars).  New data is fed by
         copying into `x_static` / `y_static` before calling `step()`.  Several hundred small launches per
         step otherwise cost more host time than the GPU needs to execute them."""
+        return self._capture(lambda: self.model(latent_tokens_coord=latent, xcoord=coord, pndata=x_static,
+                                                encoder_nbrs=encoder_nbrs, decoder_nbrs=decoder_nbrs), y_static, warmup)
+
+    def _capture(self, forward, y_static, warmup):
         from . import _lib
 
         def fwd_bwd():
             self.zero_grad()
-            pred = self.model(latent_tokens_coord=latent, xcoord=coord, pndata=x_static, encoder_nbrs=encoder_nbrs,
-                              decoder_nbrs=decoder_nbrs)
+            pred = forward()
             loss = ops.mse_loss(pred, y_static)
             loss.backward()
             self.gather_gradients()
