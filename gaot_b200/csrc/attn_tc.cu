@@ -13,6 +13,9 @@
 //   warps 2-5 softmax    : one thread per query row reads its S row from TMEM (tcgen05.ld), online softmax in
 //                          base 2, writes P (bf16) to shared memory, then folds PV into its fp32 output row
 #include <cuda.h>
+#include <cstdio>
+#include <cstdlib>
+#include <type_traits>
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -21,7 +24,8 @@
 namespace {
 
 constexpr int AT_THREADS = 192;
-constexpr int AT_BWD_THREADS = 320;      // TMA warp, MMA warp, 8 compute warps (2 per TMEM lane quadrant)
+constexpr int AT_BWD_CW = 16;            // compute warps of the backward kernel (4 per TMEM lane quadrant)
+constexpr int AT_BWD_THREADS = 64 + 32 * AT_BWD_CW;   // + TMA warp, MMA warp
 constexpr int AT_BQ = 128, AT_BKV = 128;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -99,6 +103,9 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 __device__ __forceinline__ float ex2(float x) {          // single MUFU.EX2 (ex2(-inf) = 0)
+#ifdef EXP_NO_MUFU
+    return x * 0.001f;
+#endif
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
@@ -108,6 +115,58 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                  : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// explicit shared-state-space accesses on 32-bit addresses (pointers derived from the aligned dynamic-smem base are
+// generic to the compiler, which would otherwise emit LD.E / ST.E with 64-bit address arithmetic)
+__device__ __forceinline__ float4 lds_f4(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_u4(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ void sts_f32(uint32_t a, float x) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(x) : "memory"); }
+// global load the compiler may not sink to its first use (prefetch one step ahead)
+__device__ __forceinline__ float ldg_f32(const float* p) {
+    float v;
+    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+// predicated global load with nothing depending on the result until its real use (prefetch one step ahead)
+__device__ __forceinline__ float ldg_f32_pred(const float* p, bool ok, float otherwise) {
+    float v;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %2, 0;\n\t"
+        "mov.f32 %0, %3;\n\t"
+        "@p ld.global.nc.f32 %0, [%1];\n\t}"
+        : "=f"(v) : "l"(p), "r"((int)ok), "f"(otherwise));
+    return v;
+}
+// tcgen05.ld 32x32b of N (4 / 8 / 16) consecutive columns, issue only
+template <int N>
+__device__ __forceinline__ void tmem_ld_issue(uint32_t taddr, uint32_t (&r)[N]) {
+    static_assert(N == 4 || N == 8 || N == 16, "unsupported column count");
+    if constexpr (N == 4) {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr));
+    } else if constexpr (N == 8) {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                     : "r"(taddr));
+    } else {
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+              "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+            : "r"(taddr));
+    }
+}
+__device__ __forceinline__ void tmem_ld8_issue(uint32_t taddr, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
 }
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
@@ -328,13 +387,27 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttnArgs g) {
 // ------------------------------------------------------------------------------------------------
 // Backward.  One CTA per (128-key tile, KV head, sample); it loops over the query heads of its group and
 // over 128-query tiles.  Rows (TMEM lanes, threads) are KEYS for S^T, dP^T, dV, dK and QUERIES for dQ:
-//   S^T  = K Q^T            dP^T = V dO^T                         (A, B K-major)
-//   P^T  = exp2(S^T*c - lse2[q]),   dS^T = P^T * (dP^T - delta[q])   (per thread = per key row)
+//   S^T  = K Q^T            dP^T = V dO^T                         (A, B K-major)                "ST(i)"
+//   P^T  = exp2(S^T*c - lse2[q]),   dS^T = P^T * (dP^T - delta[q])   (per thread = per key row)   "compute(i)"
 //   dV  += P^T dO           dK  += dS^T Q                         (A K-major from smem, B MN-major in place)
-//   dQ   = dS K                                                    (A = dS^T tile read MN-major, B = K MN-major)
-// dV / dK accumulate in TMEM over all query tiles; dQ tiles are drained per step into an fp32 buffer
-// with 128-bit red.add (different key tiles contribute to the same dQ rows).
+//   dQ   = dS K                                                    (A = dS^T tile read MN-major, B = K MN-major)  "DVKQ(i)"
+// dV / dK accumulate in TMEM over all query tiles; dQ tiles are drained into an fp32 buffer with 128-bit
+// red.add (different key tiles contribute to the same dQ rows).
+//
+// Software pipeline (the serial ST -> compute -> DVKQ -> drain chain of one step is spread over three):
+//   * the compute warps pull their S^T / dP^T values into registers first and release the TMEM columns
+//     (st_free), so the MMA warp issues ST(i+1) while compute(i) is still running;
+//   * P^T / dS^T are double-buffered in shared memory and dQ is double-buffered in TMEM, so DVKQ(i) runs on the
+//     tensor pipe during compute(i+1) and dQ(i) is drained after compute(i+1);
+//   * Q / dO tiles go through a 3-stage TMA ring (stage i+1 is being multiplied while stage i-1 is still read).
+// Tensor-pipe order: ST(0) ST(1) DVKQ(0) ST(2) DVKQ(1) ...
 // ------------------------------------------------------------------------------------------------
+#ifdef EXP_TRACE
+__device__ long long g_trace[64 * 128];
+#define TRACE(slot) do { if (trace_on) g_trace[trace_base + (slot)] = clock64(); } while (0)
+#else
+#define TRACE(slot) do { } while (0)
+#endif
 struct AttnBwdArgs {
     const float* lse;      // [B,H,T] natural log
     const float* delta;    // [B,H,T] rowsum(dO * O)
@@ -344,33 +417,42 @@ struct AttnBwdArgs {
     float scale, scale_log2;
 };
 
+template <int HD> struct AttnBwdCfg {
+    static constexpr int NQ = HD <= 32 ? 3 : 2;        // Q / dO stages
+    static constexpr int NBUF = HD <= 32 ? 2 : 1;      // P^T / dS^T buffers (hd = 64: shared memory allows one)
+    static constexpr int TILE_BYTES = 128 * HD * 2;
+    static constexpr int PT_BYTES = 128 * 128 * 2;
+    static constexpr int SMEM = (2 + 2 * NQ) * TILE_BYTES + 2 * NBUF * PT_BYTES + 4096 + 256 + 1024;
+};
+
 template <int HD>
-__global__ void __launch_bounds__(AT_BWD_THREADS)
+__global__ void __launch_bounds__(AT_BWD_THREADS, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUtensorMap tmdo, const AttnBwdArgs g) {
+    using Cfg = AttnBwdCfg<HD>;
     constexpr int ROWB = HD * 2;
-    constexpr int TILE_BYTES = 128 * ROWB;
-    constexpr int PT_BYTES = 128 * 128 * 2;
-    constexpr uint32_t TMEM_COLS = 512;      // S^T [0,128) dP^T [128,256) dV [256,..) dK [320,..) dQ [384,..)
+    constexpr int TILE_BYTES = Cfg::TILE_BYTES;
+    constexpr int PT_BYTES = Cfg::PT_BYTES;
+    constexpr int NQ = Cfg::NQ, NBUF = Cfg::NBUF;
+    constexpr uint32_t TMEM_COLS = 512;      // S^T [0,128) dP^T [128,256) dV [256,..) dK [256+HD,..) dQ[2] [256+2HD,..)
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* sK = smem;
     uint8_t* sV = sK + TILE_BYTES;
-    uint8_t* sQ = sV + TILE_BYTES;           // [2 stages]
-    uint8_t* sG = sQ + 2 * TILE_BYTES;       // dO, [2 stages]
-    uint8_t* sPt = sG + 2 * TILE_BYTES;
-    uint8_t* sSt = sPt + PT_BYTES;
-    float* sLse = reinterpret_cast<float*>(sSt + PT_BYTES);   // [2][128] base-2 lse
-    float* sDel = sLse + 256;                                  // [2][128]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sDel + 256);
+    uint8_t* sQ = sV + TILE_BYTES;           // [NQ stages]
+    uint8_t* sG = sQ + NQ * TILE_BYTES;      // dO, [NQ stages]
+    uint8_t* sPt = sG + NQ * TILE_BYTES;     // [NBUF]
+    uint8_t* sSt = sPt + NBUF * PT_BYTES;    // [NBUF]
+    float* sStat = reinterpret_cast<float*>(sSt + NBUF * PT_BYTES);  // [16 compute warps][lse2 x 32 | delta x 32]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sStat + AT_BWD_CW * 64);
     uint64_t* kv_bar = bars;
-    uint64_t* q_full = bars + 1;     // [2]
-    uint64_t* q_empty = bars + 3;    // [2]
-    uint64_t* st_full = bars + 5;
-    uint64_t* pds_full = bars + 6;   // 128 arrivals
-    uint64_t* dq_full = bars + 7;
-    uint64_t* dq_empty = bars + 8;   // 128 arrivals
-    uint64_t* fin_bar = bars + 9;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+    uint64_t* q_full = bars + 1;     // [NQ]   TMA -> MMA
+    uint64_t* q_empty = bars + 4;    // [NQ]   DVKQ(i) finished reading stage i % NQ
+    uint64_t* st_full = bars + 7;    //        ST(i) complete
+    uint64_t* st_free = bars + 8;    //        8 warp arrivals: S^T / dP^T of step i are in registers
+    uint64_t* pds_full = bars + 9;   // [2]    8 warp arrivals: P^T / dS^T buffer written
+    uint64_t* done = bars + 11;      // [2]    DVKQ(i) complete: dQ[i & 1] ready, P^T / dS^T buffer free
+    uint64_t* dq_empty = bars + 13;  // [2]    8 warp arrivals: dQ[i & 1] drained
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int k0 = blockIdx.x * 128, hk = blockIdx.y, b = blockIdx.z;
@@ -378,11 +460,18 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
     const int row_base = b * g.T;
     const int n_qt = (g.T + 127) / 128;
     const int n_steps = rep * n_qt;
+#ifdef EXP_TRACE
+    // compute warp 2 lane 0 -> slots [0,64), MMA warp lane 0 -> slots [64,128) of CTA (0,0,z)
+    const bool trace_on = blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z < 64 && lane == 0 && (warp == 2 || warp == 1);
+    const int trace_base = blockIdx.z * 128 + (warp == 1 ? 64 : 0);
+    TRACE(0);
+#endif
 
     if (threadIdx.x == 0) {
         mbar_init(kv_bar, 1);
-        for (int s = 0; s < 2; ++s) { mbar_init(&q_full[s], 1); mbar_init(&q_empty[s], 1); }
-        mbar_init(st_full, 1); mbar_init(pds_full, 8); mbar_init(dq_full, 1); mbar_init(dq_empty, 8); mbar_init(fin_bar, 1);   // pds_full / dq_empty: one arrival per compute warp
+        for (int s = 0; s < NQ; ++s) { mbar_init(&q_full[s], 1); mbar_init(&q_empty[s], 1); }
+        mbar_init(st_full, 1); mbar_init(st_free, AT_BWD_CW);        // one arrival per compute warp
+        for (int s = 0; s < 2; ++s) { mbar_init(&pds_full[s], AT_BWD_CW); mbar_init(&done[s], 1); mbar_init(&dq_empty[s], AT_BWD_CW); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -394,19 +483,22 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *tmem_slot;
-    const uint32_t tm_st = tmem, tm_dp = tmem + 128, tm_dv = tmem + 256, tm_dk = tmem + 320, tm_dq = tmem + 384;
+    TRACE(1);
+    const uint32_t tm_st = tmem, tm_dp = tmem + 128, tm_dv = tmem + 256, tm_dk = tmem + 256 + HD, tm_dq = tmem + 256 + 2 * HD;
 
     if (warp == 0) {
         if (lane == 0) {
             mbar_expect_tx(kv_bar, 2 * TILE_BYTES);
             tma_load_2d(sK, &tm, kv_bar, g.koff + hk * HD, row_base + k0);
             tma_load_2d(sV, &tm, kv_bar, g.voff + hk * HD, row_base + k0);
+            int s = 0, use = 0, hq = 0, qt = 0;
             for (int i = 0; i < n_steps; ++i) {
-                const int s = i & 1, h = hk * rep + i / n_qt, q0 = (i % n_qt) * 128;
-                mbar_wait(&q_empty[s], ((uint32_t)(i >> 1) & 1u) ^ 1u);
+                mbar_wait(&q_empty[s], ((uint32_t)use & 1u) ^ 1u);
                 mbar_expect_tx(&q_full[s], 2 * TILE_BYTES);
-                tma_load_2d(sQ + s * TILE_BYTES, &tm, &q_full[s], h * HD, row_base + q0);
-                tma_load_2d(sG + s * TILE_BYTES, &tmdo, &q_full[s], h * HD, row_base + q0);
+                tma_load_2d(sQ + s * TILE_BYTES, &tm, &q_full[s], (hk * rep + hq) * HD, row_base + qt * 128);
+                tma_load_2d(sG + s * TILE_BYTES, &tmdo, &q_full[s], (hk * rep + hq) * HD, row_base + qt * 128);
+                if (++s == NQ) { s = 0; ++use; }
+                if (++qt == n_qt) { qt = 0; ++hq; }
             }
         }
     } else if (warp == 1) {
@@ -415,33 +507,44 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
         constexpr uint32_t IDESC_KN = BASE | (1u << 16) | ((uint32_t)(HD >> 3) << 17);               // N=HD, B MN-major
         constexpr uint32_t IDESC_MN = BASE | (1u << 15) | (1u << 16) | ((uint32_t)(HD >> 3) << 17);  // A and B MN-major
         mbar_wait(kv_bar, 0);
+        const uint64_t d_k = make_desc<ROWB>(smem_u32(sK)), d_v = make_desc<ROWB>(smem_u32(sV));
         auto issue_st = [&](int i) {
-            const int s = i & 1;
-            mbar_wait(&q_full[s], (uint32_t)(i >> 1) & 1u);
+            const int s = i % NQ;
+            mbar_wait(&q_full[s], (uint32_t)(i / NQ) & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (lane == 0) {
-                const uint64_t dk = make_desc<ROWB>(smem_u32(sK)), dv = make_desc<ROWB>(smem_u32(sV));
                 const uint64_t dq = make_desc<ROWB>(smem_u32(sQ + s * TILE_BYTES)), dg = make_desc<ROWB>(smem_u32(sG + s * TILE_BYTES));
 #pragma unroll
-                for (int k = 0; k < HD / 16; ++k) umma_f16(tm_st, dk + (uint64_t)(2 * k), dq + (uint64_t)(2 * k), IDESC_ST, k > 0 ? 1u : 0u);
+                for (int k = 0; k < HD / 16; ++k) umma_f16(tm_st, d_k + (uint64_t)(2 * k), dq + (uint64_t)(2 * k), IDESC_ST, k > 0 ? 1u : 0u);
 #pragma unroll
-                for (int k = 0; k < HD / 16; ++k) umma_f16(tm_dp, dv + (uint64_t)(2 * k), dg + (uint64_t)(2 * k), IDESC_ST, k > 0 ? 1u : 0u);
+                for (int k = 0; k < HD / 16; ++k) umma_f16(tm_dp, d_v + (uint64_t)(2 * k), dg + (uint64_t)(2 * k), IDESC_ST, k > 0 ? 1u : 0u);
                 umma_commit(st_full);
             }
             __syncwarp();
         };
         issue_st(0);
         for (int i = 0; i < n_steps; ++i) {
-            const int s = i & 1;
-            mbar_wait(pds_full, (uint32_t)i & 1u);
-            if (i > 0) mbar_wait(dq_empty, (uint32_t)(i - 1) & 1u);       // previous dQ tile drained from TMEM
+            TRACE(2 + 4 * i);
+            if (i + 1 < n_steps) {
+                mbar_wait(st_free, (uint32_t)i & 1u);                     // S^T(i) / dP^T(i) are in the compute warps' registers
+                TRACE(3 + 4 * i);
+                issue_st(i + 1);
+            }
+            TRACE(4 + 4 * i);
+            const int s = i % NQ, bf = i % NBUF, d = i & 1;
+            mbar_wait(&pds_full[bf], (uint32_t)(i / NBUF) & 1u);
+            if (i >= 2) mbar_wait(&dq_empty[d], (uint32_t)((i - 2) >> 1) & 1u);   // dQ[d] of step i-2 drained from TMEM
+            TRACE(5 + 4 * i);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (lane == 0) {
                 // all descriptors = per-step base + compile-time offset (16-byte units in the start-address field)
                 const uint64_t d_q = make_desc<ROWB>(smem_u32(sQ + s * TILE_BYTES)), d_g = make_desc<ROWB>(smem_u32(sG + s * TILE_BYTES));
-                const uint64_t d_pt = make_desc<128>(smem_u32(sPt)), d_st = make_desc<128>(smem_u32(sSt)), d_k = make_desc<ROWB>(smem_u32(sK));
-                const uint32_t pst = smem_u32(sSt);
+                const uint32_t pst = smem_u32(sSt + bf * PT_BYTES);
+                const uint64_t d_pt = make_desc<128>(smem_u32(sPt + bf * PT_BYTES)), d_st = make_desc<128>(pst);
                 const uint32_t acc_first = i > 0 ? 1u : 0u;
+#ifdef EXP_NO_DVKQ
+                if (g.scale == 12345.f)
+#endif
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {      // contraction over 128 queries, 16 per MMA
                     const uint64_t aoff = (uint64_t)(((k >> 2) * (128 * 128) + (k & 3) * 32) >> 4);
@@ -453,134 +556,172 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
                 // (M = 128 queries = two 64-wide swizzle atoms LBO = 16 KB apart, 8-key groups SBO = 1 KB apart)
                 const uint64_t a_mn0 = (uint64_t)((pst & 0x3FFFF) >> 4) | ((uint64_t)(16384 >> 4) << 16) |
                                        ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+#ifdef EXP_NO_DVKQ
+                if (g.scale == 12345.f)
+#endif
 #pragma unroll
                 for (int k = 0; k < 8; ++k)        // contraction over 128 keys, 16 per MMA = 16 rows of 128 bytes
-                    umma_f16(tm_dq, a_mn0 + (uint64_t)((k * 2048) >> 4), d_k + (uint64_t)((k * 16 * ROWB) >> 4), IDESC_MN, k > 0 ? 1u : 0u);
-                umma_commit(dq_full);
+                    umma_f16(tm_dq + d * HD, a_mn0 + (uint64_t)((k * 2048) >> 4), d_k + (uint64_t)((k * 16 * ROWB) >> 4), IDESC_MN, k > 0 ? 1u : 0u);
+                umma_commit(&done[d]);
                 umma_commit(&q_empty[s]);
-                if (i == n_steps - 1) umma_commit(fin_bar);
             }
             __syncwarp();
-            if (i + 1 < n_steps) issue_st(i + 1);
         }
     } else {
-        // 8 compute warps: warps w and w+4 share TMEM lane quadrant w%4 (the hardware restricts a warp to the lanes
-        // 32*(w%4)..+31) and split the columns: `half` 0/1 owns query columns [64*half, 64*half+64) of S^T / dP^T
-        // (= one 64-column swizzle block of the P^T / dS^T tiles) and half of the dQ / dV / dK columns.
-        const int q4 = warp & 3, half = (warp - 2) >> 2;
+        // 16 compute warps: warps w, w+4, w+8, w+12 share TMEM lane quadrant w%4 (the hardware restricts a warp to
+        // the lanes 32*(w%4)..+31) and split the columns: `qr` 0..3 owns query columns [32*qr, 32*qr+32) of S^T / dP^T
+        // (= half of a 64-column swizzle block of the P^T / dS^T tiles) and a quarter of the dQ / dV / dK columns.
+        constexpr int NC = HD / 4;                         // dQ / dV / dK columns per thread
+        const int q4 = warp & 3, qr = (warp - 2) >> 2;
         const int r = q4 * 32 + lane;                      // key row for S^T.., query row for dQ
         const uint32_t lane_addr = (uint32_t)(q4 * 32) << 16;
         const bool key_ok = k0 + r < g.T;
-        const int ct = threadIdx.x - 64;                   // 0..255
-        // per-query statistics (base-2 lse for threads < 128, delta for the rest) are fetched one step ahead so
-        // their global-load latency is off the step's critical path
-        auto fetch_stat = [&](int i) -> float {
-            const int h = hk * rep + i / n_qt, q0 = (i % n_qt) * 128, cq = ct & 127;
-            const bool ok = q0 + cq < g.T;
-            const int64_t off = ((int64_t)b * g.H + h) * g.T + q0 + cq;
-            if (ct < 128) return ok ? __ldg(g.lse + off) * 1.4426950408889634f : INFINITY;   // +inf switches a query column off
-            return ok ? __ldg(g.delta + off) : 0.f;
+        const bool tile_full = k0 + 128 <= g.T;            // CTA-uniform: only the last key tile can be ragged
+        // per-query statistics of the warp's 32 columns: [lse2 x 32 | delta x 32] in a per-warp shared-memory slab
+        // (no CTA-wide barrier), loaded from global memory one step ahead (one lse and one delta per lane)
+        const uint32_t stat_s = smem_u32(sStat) + (uint32_t)(warp - 2) * 256u;
+        const float* lse_b = g.lse + (int64_t)b * g.H * g.T;
+        const float* del_b = g.delta + (int64_t)b * g.H * g.T;
+        float st_l, st_d;
+        auto fetch_stat = [&](int h, int qt) {
+            const int q = qt * 128 + qr * 32 + lane;
+            const int64_t off = (int64_t)h * g.T + q;
+            st_l = ldg_f32_pred(lse_b + off, q < g.T, INFINITY);           // +inf switches a query column off
+            st_d = ldg_f32_pred(del_b + off, q < g.T, 0.f);
         };
-        float stat_next = n_steps > 0 ? fetch_stat(0) : 0.f;
-        for (int i = 0; i < n_steps; ++i) {
-            const int s = i & 1, h = hk * rep + i / n_qt, q0 = (i % n_qt) * 128;
-            {
-                const int cq = ct & 127;
-                if (ct < 128) sLse[s * 128 + cq] = stat_next; else sDel[s * 128 + cq] = stat_next;
-                if (i + 1 < n_steps) stat_next = fetch_stat(i + 1);
-            }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            mbar_wait(st_full, (uint32_t)i & 1u);
+        // dQ of a finished step: here the TMEM lane is the QUERY row; this warp's quarter of the HD columns
+        auto drain_dq = [&](int j, int h, int qt) {
+            const int t = qt * 128 + r, d = j & 1;
+            mbar_wait(&done[d], (uint32_t)(j >> 1) & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll 1
-            for (int c = 2 * half; c < 2 * half + 2; ++c) {
-                uint32_t sv[32], dv[32];
-                tmem_ld32_issue(tm_st + lane_addr + c * 32, sv);
-                tmem_ld32_issue(tm_dp + lane_addr + c * 32, dv);
-                tmem_wait_ld();
-                uint32_t pp[16], ds[16];
-                const float4* l4 = reinterpret_cast<const float4*>(sLse + s * 128 + c * 32);
-                const float4* d4 = reinterpret_cast<const float4*>(sDel + s * 128 + c * 32);
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    const float4 lv = l4[j >> 2], dl = d4[j >> 2];      // broadcast reads: every thread, same address
-                    float p0 = ex2(fmaf(__uint_as_float(sv[j]), g.scale_log2, -lv.x));
-                    float p1 = ex2(fmaf(__uint_as_float(sv[j + 1]), g.scale_log2, -lv.y));
-                    float p2 = ex2(fmaf(__uint_as_float(sv[j + 2]), g.scale_log2, -lv.z));
-                    float p3 = ex2(fmaf(__uint_as_float(sv[j + 3]), g.scale_log2, -lv.w));
-                    if (!key_ok) { p0 = 0.f; p1 = 0.f; p2 = 0.f; p3 = 0.f; }
-                    pp[j >> 1] = pack_bf16(p0, p1);
-                    pp[(j >> 1) + 1] = pack_bf16(p2, p3);
-                    ds[j >> 1] = pack_bf16(p0 * (__uint_as_float(dv[j]) - dl.x), p1 * (__uint_as_float(dv[j + 1]) - dl.y));
-                    ds[(j >> 1) + 1] = pack_bf16(p2 * (__uint_as_float(dv[j + 2]) - dl.z), p3 * (__uint_as_float(dv[j + 3]) - dl.w));
-                }
-                uint8_t* bp = sPt + (c >> 1) * (128 * 128);
-                uint8_t* bs = sSt + (c >> 1) * (128 * 128);
-#pragma unroll
-                for (int w = 0; w < 4; ++w) {
-                    const uint32_t off = sw128_off(r, (c & 1) * 4 + w);
-                    *reinterpret_cast<uint4*>(bp + off) = make_uint4(pp[4 * w], pp[4 * w + 1], pp[4 * w + 2], pp[4 * w + 3]);
-                    *reinterpret_cast<uint4*>(bs + off) = make_uint4(ds[4 * w], ds[4 * w + 1], ds[4 * w + 2], ds[4 * w + 3]);
-                }
-            }
+            uint32_t v[NC];
+            tmem_ld_issue<NC>(tm_dq + d * HD + lane_addr + qr * NC, v);
+            tmem_wait_ld();
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&dq_empty[d]);
+#ifndef EXP_NO_RED
+            if (t < g.T) {
+#else
+            if (t < g.T && g.scale == 12345.f) {
+#endif
+                float* dst = g.dq_acc + ((int64_t)(row_base + t) * g.H + h) * HD + qr * NC;
+#pragma unroll
+                for (int j4 = 0; j4 < NC; j4 += 4)
+                    atomicAdd(reinterpret_cast<float4*>(dst + j4),
+                              make_float4(__uint_as_float(v[j4]) * g.scale, __uint_as_float(v[j4 + 1]) * g.scale,
+                                          __uint_as_float(v[j4 + 2]) * g.scale, __uint_as_float(v[j4 + 3]) * g.scale));
+            }
+        };
+        // P^T / dS^T of the warp's 32 query columns: exp2, products, bf16 packing; 8 columns = one 16-byte swizzled
+        // store into each tile
+        auto emit = [&](auto full_tag, const uint32_t (&sv)[32], const uint32_t (&dv)[32], uint32_t bp, uint32_t bs) {
+            constexpr bool FULL = decltype(full_tag)::value;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+                uint32_t pp[4], ds[4];
+#pragma unroll
+                for (int k = 0; k < 8; k += 4) {
+                    const float4 lv = lds_f4(stat_s + (uint32_t)(j + k) * 4u);              // broadcast reads
+                    const float4 dl = lds_f4(stat_s + 128u + (uint32_t)(j + k) * 4u);
+                    float p0 = ex2(fmaf(__uint_as_float(sv[j + k]), g.scale_log2, -lv.x));
+                    float p1 = ex2(fmaf(__uint_as_float(sv[j + k + 1]), g.scale_log2, -lv.y));
+                    float p2 = ex2(fmaf(__uint_as_float(sv[j + k + 2]), g.scale_log2, -lv.z));
+                    float p3 = ex2(fmaf(__uint_as_float(sv[j + k + 3]), g.scale_log2, -lv.w));
+                    if (!FULL) {
+                        if (!key_ok) { p0 = 0.f; p1 = 0.f; p2 = 0.f; p3 = 0.f; }
+                    }
+                    pp[k >> 1] = pack_bf16(p0, p1);
+                    pp[(k >> 1) + 1] = pack_bf16(p2, p3);
+                    ds[k >> 1] = pack_bf16(p0 * (__uint_as_float(dv[j + k]) - dl.x), p1 * (__uint_as_float(dv[j + k + 1]) - dl.y));
+                    ds[(k >> 1) + 1] = pack_bf16(p2 * (__uint_as_float(dv[j + k + 2]) - dl.z), p3 * (__uint_as_float(dv[j + k + 3]) - dl.w));
+                }
+                const uint32_t off = sw128_off(r, (qr & 1) * 4 + (j >> 3));
+                sts_u4(bp + off, pp[0], pp[1], pp[2], pp[3]);
+                sts_u4(bs + off, ds[0], ds[1], ds[2], ds[3]);
+            }
+        };
+        const int h0 = hk * rep;
+        int f_h = h0, f_qt = 0;                             // step being fetched (one ahead)
+        int c_h = h0, c_qt = 0, p_h = h0, p_qt = 0;         // current / previous step
+        fetch_stat(f_h, f_qt);
+        for (int i = 0; i < n_steps; ++i) {
+            const int bf = i % NBUF;
+            sts_f32(stat_s + (uint32_t)lane * 4u, st_l * 1.4426950408889634f);
+            sts_f32(stat_s + 128u + (uint32_t)lane * 4u, st_d);
+            __syncwarp();
+            if (i + 1 < n_steps) {
+                if (++f_qt == n_qt) { f_qt = 0; ++f_h; }
+                fetch_stat(f_h, f_qt);
+            }
+            TRACE(2 + 6 * i);
+            mbar_wait(st_full, (uint32_t)i & 1u);
+            TRACE(3 + 6 * i);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            uint32_t sv[32], dv[32];
+            tmem_ld32_issue(tm_st + lane_addr + qr * 32, sv);
+            tmem_ld32_issue(tm_dp + lane_addr + qr * 32, dv);
+            tmem_wait_ld();
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(st_free);           // the MMA warp may overwrite S^T / dP^T with step i+1
+            TRACE(4 + 6 * i);
+            if (i >= NBUF) {                                // DVKQ(i - NBUF) has finished reading this P^T / dS^T buffer
+                mbar_wait(&done[(i - NBUF) & 1], (uint32_t)((i - NBUF) >> 1) & 1u);
+            }
+            TRACE(5 + 6 * i);
+            const uint32_t bp = smem_u32(sPt) + (uint32_t)(bf * PT_BYTES + (qr >> 1) * (128 * 128));
+            const uint32_t bs = smem_u32(sSt) + (uint32_t)(bf * PT_BYTES + (qr >> 1) * (128 * 128));
+            if (tile_full) emit(std::true_type{}, sv, dv, bp, bs);
+            else emit(std::false_type{}, sv, dv, bp, bs);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
-            if (lane == 0) mbar_arrive(pds_full);
-            // drain dQ: here the TMEM lane is the QUERY row
-            mbar_wait(dq_full, (uint32_t)i & 1u);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            {
-                const int t = q0 + r;
-                float* dst = g.dq_acc + ((int64_t)(row_base + t) * g.H + h) * HD;
-#pragma unroll
-                for (int c = 0; c < HD / 16; ++c) {           // this warp's half of the HD columns, 8 at a time
-                    const int col = half * (HD / 2) + c * 8;
-                    uint32_t v[8];
-                    tmem_ld8(tm_dq + lane_addr + col, v);
-                    if (t < g.T) {
-#pragma unroll
-                        for (int j = 0; j < 8; j += 4)
-                            atomicAdd(reinterpret_cast<float4*>(dst + col + j),
-                                      make_float4(__uint_as_float(v[j]) * g.scale, __uint_as_float(v[j + 1]) * g.scale,
-                                                  __uint_as_float(v[j + 2]) * g.scale, __uint_as_float(v[j + 3]) * g.scale));
-                    }
-                }
-            }
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) mbar_arrive(dq_empty);
+            if (lane == 0) mbar_arrive(&pds_full[bf]);
+            TRACE(6 + 6 * i);
+            if (i >= 1) drain_dq(i - 1, p_h, p_qt);
+            TRACE(7 + 6 * i);
+            p_h = c_h; p_qt = c_qt;
+            if (++c_qt == n_qt) { c_qt = 0; ++c_h; }
         }
-        // final: dV and dK rows of this key tile
-        mbar_wait(fin_bar, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        drain_dq(n_steps - 1, p_h, p_qt);
+        TRACE(2 + 6 * n_steps);
+        // final: dV and dK rows of this key tile (done[] of the last step has completed: every MMA has retired)
         {
             __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(g.dqkv) + (int64_t)(row_base + k0 + r) * g.ld;
+            uint32_t vv[NC], vk[NC];
+            tmem_ld_issue<NC>(tm_dv + lane_addr + qr * NC, vv);
+            tmem_ld_issue<NC>(tm_dk + lane_addr + qr * NC, vk);
+            tmem_wait_ld();
+            if (key_ok) {
+                uint32_t pv[NC / 2], pk[NC / 2];
 #pragma unroll
-            for (int c = 0; c < HD / 16; ++c) {
-                const int col = half * (HD / 2) + c * 8;
-                uint32_t vv[8], vk[8];
-                tmem_ld8(tm_dv + lane_addr + col, vv);
-                tmem_ld8(tm_dk + lane_addr + col, vk);
-                if (key_ok) {
-                    *reinterpret_cast<uint4*>(base + g.voff + hk * HD + col) = make_uint4(
-                        pack_bf16(__uint_as_float(vv[0]), __uint_as_float(vv[1])), pack_bf16(__uint_as_float(vv[2]), __uint_as_float(vv[3])),
-                        pack_bf16(__uint_as_float(vv[4]), __uint_as_float(vv[5])), pack_bf16(__uint_as_float(vv[6]), __uint_as_float(vv[7])));
-                    *reinterpret_cast<uint4*>(base + g.koff + hk * HD + col) = make_uint4(
-                        pack_bf16(__uint_as_float(vk[0]) * g.scale, __uint_as_float(vk[1]) * g.scale),
-                        pack_bf16(__uint_as_float(vk[2]) * g.scale, __uint_as_float(vk[3]) * g.scale),
-                        pack_bf16(__uint_as_float(vk[4]) * g.scale, __uint_as_float(vk[5]) * g.scale),
-                        pack_bf16(__uint_as_float(vk[6]) * g.scale, __uint_as_float(vk[7]) * g.scale));
+                for (int c = 0; c < NC; c += 2) {
+                    pv[c >> 1] = pack_bf16(__uint_as_float(vv[c]), __uint_as_float(vv[c + 1]));
+                    pk[c >> 1] = pack_bf16(__uint_as_float(vk[c]) * g.scale, __uint_as_float(vk[c + 1]) * g.scale);
+                }
+                __nv_bfloat16* dvp = base + g.voff + hk * HD + qr * NC;
+                __nv_bfloat16* dkp = base + g.koff + hk * HD + qr * NC;
+                if constexpr (NC == 4) {
+                    *reinterpret_cast<uint2*>(dvp) = make_uint2(pv[0], pv[1]);
+                    *reinterpret_cast<uint2*>(dkp) = make_uint2(pk[0], pk[1]);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < NC / 2; c += 4) {
+                        *reinterpret_cast<uint4*>(dvp + 2 * c) = make_uint4(pv[c], pv[c + 1], pv[c + 2], pv[c + 3]);
+                        *reinterpret_cast<uint4*>(dkp + 2 * c) = make_uint4(pk[c], pk[c + 1], pk[c + 2], pk[c + 3]);
+                    }
                 }
             }
         }
     }
+    TRACE(62);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS));
     }
+    TRACE(63);
 }
 
 // delta[b,h,t] = sum_d dO[t,h,d] * O[t,h,d]   (bf16 in, fp32 out); one thread per (token, head)
@@ -648,6 +789,16 @@ int make_head_map(CUtensorMap* map, const void* base, int64_t rows, int64_t ld, 
     const CUtensorMapSwizzle sw = hd == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (hd == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r == CUDA_ERROR_INVALID_CONTEXT) {
+        // driver API called on a thread (e.g. the autograd engine's) that has no current context yet: a runtime
+        // call binds the primary context, then encode again
+        cudaFree(nullptr);
+        r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
+    if (r != CUDA_SUCCESS && getenv("GAOT_DEBUG"))
+        fprintf(stderr, "gaot: cuTensorMapEncodeTiled failed (%d): base %p rows %lld ld %lld hd %d box_rows %d map %p\n", (int)r, base,
+                (long long)rows, (long long)ld, hd, box_rows, (void*)map);
     return r == CUDA_SUCCESS ? 0 : GAOT_E_BADARG;
 }
 
@@ -687,7 +838,7 @@ namespace {
 template <int HD>
 int launch_bwd(const CUtensorMap& tm, const CUtensorMap& tmdo, const AttnBwdArgs& g, const void* o, const void* dout,
                float* delta, int64_t B, cudaStream_t st) {
-    constexpr int SMEM = 6 * 128 * HD * 2 + 2 * 128 * 128 * 2 + 2048 + 1024 + 256;
+    constexpr int SMEM = AttnBwdCfg<HD>::SMEM;
     static bool done = false;
     if (!done) {
         GAOT_CHECK(cudaFuncSetAttribute(attn_bwd_tc_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
@@ -727,3 +878,7 @@ GAOT_API int gaot_attention_bwd_bf16(const void* qkv, const void* o, const float
     if (hd == 32) return launch_bwd<32>(tm, tmdo, g, o, dout, delta, B, st);
     return launch_bwd<64>(tm, tmdo, g, o, dout, delta, B, st);
 }
+
+#ifdef EXP_TRACE
+GAOT_API int gaot_debug_trace(long long* out) { return (int)cudaMemcpyFromSymbol(out, g_trace, sizeof(g_trace)); }
+#endif

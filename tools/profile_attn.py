@@ -6,7 +6,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
-from gaot_b200 import ops  # noqa: E402
+from gaot_b200 import ops, _lib  # noqa: E402
+
+if os.environ.get("GAOT_LIB"):          # experiment builds (tools/build_variants.sh)
+    _lib.LIB_PATH = os.environ["GAOT_LIB"]
 
 B, T, H, hd = 32, 1024, 8, 32
 qkv = torch.randn(B * T, 3 * H * hd, device="cuda").to(torch.bfloat16).requires_grad_(True)
