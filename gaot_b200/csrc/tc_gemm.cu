@@ -22,7 +22,7 @@ namespace {
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;          // 64 bf16 = 128 bytes = one SWIZZLE_128B row
-constexpr int TC_STAGES = 5;
+constexpr int TC_STAGES = 4;          // 4 x 32 KB in flight: the K = 256 main loop is L2 -> SM bandwidth bound, not latency bound
 constexpr int TC_THREADS = 320;        // TMA warp, MMA warp, 8 epilogue warps
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -76,12 +76,47 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,"
+        "%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]),
+          "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]),
+          "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_s(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ float4 lds_f4(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_f4(uint32_t a, float x, float y, float z, float w) {
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+__device__ __forceinline__ void sts_u4(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+    __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&t);
+}
+
 struct TcArgs {
     void* C; int64_t M, N, K;
     const float* bias; const float* add; int64_t add_rows, ldadd;
     int out_bf16, splits, accumulate;
     int64_t gm, gn;                   // tile grid
     int act; float* pre;              // optional activation (GAOT_ACT_*) and fp32 pre-activation output
+    int fast;                         // epilogue through swizzled smem boxes and TMA stores (tmC / tmAdd valid)
 };
 
 // MN-major operand tile: [64 contraction rows][64 elements = 128 bytes] blocks of 8 KB, one per 64 output
@@ -99,17 +134,20 @@ __device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t saddr) {
 // ring keeps prefetching across tile boundaries.
 template <int BN, bool AMN, bool BMN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs g) {
+gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmAdd, const TcArgs g) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     constexpr int A_BYTES = TC_BM * TC_BK * 2, B_BYTES = BN * TC_BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
-    constexpr int PITCH = 36;                                      // epilogue staging: floats per row (16-byte aligned)
+    constexpr int PITCH = 36;                                      // fallback epilogue staging: floats per row (16-byte aligned)
+    constexpr int STG_WARP = 8192;                                 // per epilogue warp: two 4 KB boxes (32 rows x 32 columns)
     float* stg_all = reinterpret_cast<float*>(smem + TC_STAGES * STAGE_BYTES);
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(stg_all + 8 * 32 * PITCH);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + TC_STAGES * STAGE_BYTES + 8 * STG_WARP);
     uint64_t* empty_bar = full_bar + TC_STAGES;
     uint64_t* acc_full = empty_bar + TC_STAGES;                    // [2]
     uint64_t* acc_empty = acc_full + 2;                            // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    uint64_t* add_bar = acc_empty + 2;                             // [8 warps][2 boxes]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(add_bar + 16);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t kblocks = (g.K + TC_BK - 1) / TC_BK;
@@ -119,12 +157,17 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 8); }
+        for (int s = 0; s < 16; ++s) mbar_init(&add_bar[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+        if (g.fast) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmC) : "memory");
+            if (g.add) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmAdd) : "memory");
+        }
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)(2 * BN)));
@@ -211,6 +254,102 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         // instruction writes 4 rows x 128 bytes (fp32) / 64 bytes (bf16).  Two warps share a lane quadrant and
         // split the BN columns.  Row offsets are hoisted out of the column loop; the store loops are specialised.
         const int q = warp & 3, half = (warp - 2) >> 2;
+        if (g.fast) {
+            // Fast epilogue.  Per warp: 32 accumulator rows x BN/2 columns, in chunks of 32 columns.  A lane owns one
+            // row: TMEM -> registers (+ bias, + the `add` tile that TMA has loaded into the same box, activation) ->
+            // 16-byte stores into a swizzled 32 x 32 box (fp32: 128-byte rows, SWIZZLE_128B; bf16: 64-byte rows,
+            // SWIZZLE_64B; both conflict-free) -> one TMA store per box.  Rows >= M / columns >= N are clipped by TMA.
+            constexpr int NCH = BN / 64;                           // chunks per warp and tile (BN = 128: 2, BN = 64: 1)
+            const uint32_t box0 = smem_u32(smem + TC_STAGES * STAGE_BYTES) + (uint32_t)(warp - 2) * STG_WARP;
+            uint64_t* abar = add_bar + (warp - 2) * 2;
+            uint32_t lt = 0, aload[NCH] = {};                      // add boxes loaded so far (mbarrier phase bookkeeping)
+            for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++lt) {
+                int64_t m0, n0, kb0; int nkb;
+                tile_coords(t, m0, n0, kb0, nkb);
+                const uint32_t ab = lt & 1u;
+                const int row0 = (int)m0 + q * 32;
+                const int64_t ncol0 = n0 + half * (BN / 2);
+                // both boxes must have been read out by the previous tile's TMA stores before they are refilled
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                __syncwarp();
+                if (g.add) {
+                    const int arow = (int)((int64_t)row0 % g.add_rows);
+#pragma unroll
+                    for (int c = 0; c < NCH; ++c) {
+                        if (ncol0 + c * 32 < g.N && row0 < g.M) {
+                            if (lane == 0) {
+                                mbar_expect_tx(&abar[c], 4096);
+                                tma_load_2d_s(box0 + c * 4096, &tmAdd, &abar[c], (int)ncol0 + c * 32, arow);
+                            }
+                            ++aload[c];
+                        }
+                    }
+                }
+                mbar_wait(&acc_full[ab], (lt >> 1) & 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t tmem_acc = tmem_base + ab * BN + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * (BN / 2));
+                uint32_t r[NCH][32];
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) tmem_ld32_issue(tmem_acc + c * 32, r[c]);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                // the accumulator is in registers: hand it back to the MMA warp before the stores
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[ab])) : "memory");
+                if (row0 >= g.M) continue;                         // warp-uniform: nothing of this warp's rows exists
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) {
+                    const int64_t n = ncol0 + c * 32;
+                    if (n >= g.N) continue;                        // warp-uniform
+                    const uint32_t box = box0 + c * 4096;
+                    float v[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[c][j]);
+                    if (g.bias) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (n + j < g.N) bv = __ldg(reinterpret_cast<const float4*>(g.bias + n + j));   // N % 4 == 0 on this path
+                            v[j] += bv.x; v[j + 1] += bv.y; v[j + 2] += bv.z; v[j + 3] += bv.w;
+                        }
+                    }
+                    if (g.add) {
+                        mbar_wait(&abar[c], (aload[c] - 1u) & 1u);
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 av = lds_f4(box + (uint32_t)lane * 128u + (uint32_t)((((j >> 2) ^ (lane & 7))) << 4));
+                            v[j] += av.x; v[j + 1] += av.y; v[j + 2] += av.z; v[j + 3] += av.w;
+                        }
+                    }
+                    if (g.act == GAOT_ACT_GELU) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+                    } else if (g.act == GAOT_ACT_RELU) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+                    }
+                    if (g.out_bf16) {
+#pragma unroll
+                        for (int w = 0; w < 4; ++w)
+                            sts_u4(box + (uint32_t)lane * 64u + (uint32_t)((w ^ ((lane >> 1) & 3)) << 4),
+                                   pack_bf16x2(v[8 * w], v[8 * w + 1]), pack_bf16x2(v[8 * w + 2], v[8 * w + 3]),
+                                   pack_bf16x2(v[8 * w + 4], v[8 * w + 5]), pack_bf16x2(v[8 * w + 6], v[8 * w + 7]));
+                    } else {
+#pragma unroll
+                        for (int w = 0; w < 8; ++w)
+                            sts_f4(box + (uint32_t)lane * 128u + (uint32_t)((w ^ (lane & 7)) << 4), v[4 * w], v[4 * w + 1], v[4 * w + 2], v[4 * w + 3]);
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(&tmC, box, (int)n, row0);
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                }
+            }
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+            __syncwarp();
+        } else {
         float* stg = stg_all + (warp - 2) * (32 * PITCH);
         const bool vec_ok = (g.N % 4 == 0) && (!g.add || (g.ldadd % 4 == 0));
         const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
@@ -327,6 +466,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             __syncwarp();
             if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[ab])) : "memory");
         }
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -429,6 +569,28 @@ int make_map_mn(CUtensorMap* map, const void* base, int64_t R, int64_t cols) {
     return r == CUDA_SUCCESS ? 0 : GAOT_E_BADARG;
 }
 
+// output / add boxes of the fast epilogue: [rows, ld] matrix of fp32 or bf16, box {32 columns, 32 rows}, swizzle span =
+// the 32-column row (128 bytes fp32 / 64 bytes bf16)
+int make_map_box32(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, bool bf16) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return GAOT_E_BADARG;
+    const int es = bf16 ? 2 : 4;
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * es};
+    cuuint32_t box[2] = {32, 32};
+    cuuint32_t estr[2] = {1, 1};
+    const CUtensorMapDataType dt = bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    const CUtensorMapSwizzle sw = bf16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
+    CUresult r = enc(map, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r == CUDA_ERROR_INVALID_CONTEXT) {
+        cudaFree(nullptr);                                     // bind the primary context on this thread, then encode again
+        r = enc(map, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
+    return r == CUDA_SUCCESS ? 0 : GAOT_E_BADARG;
+}
+
 int sm_count() {
     static int n = 0;
     if (!n) {
@@ -463,7 +625,21 @@ int launch_tc(const void* A, const void* B, TcArgs& g, cudaStream_t st) {
     }
     g.splits = splits;
     if (splits > 1 && !g.accumulate) GAOT_CHECK(cudaMemsetAsync(g.C, 0, sizeof(float) * (size_t)(g.M * g.N), st));
-    constexpr int SMEM = TC_STAGES * (TC_BM * TC_BK * 2 + BN * TC_BK * 2) + 8 * 32 * 36 * 4 + 1024 + 256;
+    // fast epilogue (TMA stores): plain stores only (no split-K / accumulate / pre-activation copy), 16-byte row pitches,
+    // and an `add` operand (fp32 output only) whose broadcast period is a whole number of 32-row boxes
+    CUtensorMap tc = ta, tadd = ta;
+    g.fast = splits == 1 && !g.accumulate && !g.pre && g.N % (g.out_bf16 ? 8 : 4) == 0 &&
+             (!g.add || (!g.out_bf16 && g.add_rows % 32 == 0 && g.ldadd % 4 == 0 && !(reinterpret_cast<uintptr_t>(g.add) & 15))) &&
+             (!g.bias || !(reinterpret_cast<uintptr_t>(g.bias) & 15));
+    if (g.fast) {
+        rc = make_map_box32(&tc, g.C, g.M, g.N, g.N, g.out_bf16 != 0);
+        if (rc) return rc;
+        if (g.add) {
+            rc = make_map_box32(&tadd, g.add, g.add_rows, g.N, g.ldadd, false);
+            if (rc) return rc;
+        }
+    }
+    constexpr int SMEM = TC_STAGES * (TC_BM * TC_BK * 2 + BN * TC_BK * 2) + 8 * 8192 + 1024 + 512;
     static bool attr_done = false;
     if (!attr_done) {
         GAOT_CHECK(cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN, AMN, BMN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
@@ -471,7 +647,7 @@ int launch_tc(const void* A, const void* B, TcArgs& g, cudaStream_t st) {
     }
     const int64_t total = tiles * splits;
     const unsigned grid = (unsigned)(total < sms ? total : sms);   // persistent: one CTA per SM
-    gemm_bf16_tc_kernel<BN, AMN, BMN><<<grid, TC_THREADS, SMEM, st>>>(ta, tb, g);
+    gemm_bf16_tc_kernel<BN, AMN, BMN><<<grid, TC_THREADS, SMEM, st>>>(ta, tb, tc, tadd, g);
     GAOT_RETURN_LAST();
 }
 
@@ -488,7 +664,7 @@ GAOT_API int gaot_gemm_bf16(const void* A, const void* B, void* C, int64_t M, in
     if (out_bf16 && accumulate) return GAOT_E_BADARG;
     if (act < 0 || act > 2 || ((act || pre) && accumulate)) return GAOT_E_BADARG;
     if (M > 0x7fffffffLL || N > 0x7fffffffLL || K > 0x7fffffffLL) return GAOT_E_BADARG;
-    TcArgs g{C, M, N, K, bias, add, add ? add_rows : 1, ldadd, out_bf16, 1, accumulate, 0, 0, act, pre};
+    TcArgs g{C, M, N, K, bias, add, add ? add_rows : 1, ldadd, out_bf16, 1, accumulate, 0, 0, act, pre, 0};
     cudaStream_t st = (cudaStream_t)stream;
     if (N <= 64) return launch_tc<64, false, false>(A, B, g, st);
     return launch_tc<128, false, false>(A, B, g, st);
@@ -501,7 +677,7 @@ GAOT_API int gaot_gemm_bf16_nn(const void* A, const void* B, void* C, int64_t M,
         (reinterpret_cast<uintptr_t>(C) & 15))
         return GAOT_E_ALIGN;
     if (M > 0x7fffffffLL || N > 0x7fffffffLL || K > 0x7fffffffLL) return GAOT_E_BADARG;
-    TcArgs g{C, M, N, K, nullptr, nullptr, 1, 0, out_bf16, 1, 0, 0, 0, 0, nullptr};
+    TcArgs g{C, M, N, K, nullptr, nullptr, 1, 0, out_bf16, 1, 0, 0, 0, 0, nullptr, 0};
     cudaStream_t st = (cudaStream_t)stream;
     if (N <= 64) return launch_tc<64, false, true>(A, B, g, st);
     return launch_tc<128, false, true>(A, B, g, st);
@@ -514,7 +690,7 @@ GAOT_API int gaot_gemm_bf16_tn(const void* A, const void* B, float* C, int64_t M
         (reinterpret_cast<uintptr_t>(C) & 15))
         return GAOT_E_ALIGN;                       // TMA: 16-byte aligned base and row pitch
     if (M > 0x7fffffffLL || N > 0x7fffffffLL || R > 0x7fffffffLL) return GAOT_E_BADARG;
-    TcArgs g{C, M, N, R, nullptr, nullptr, 1, 0, 0, 1, accumulate, 0, 0, 0, nullptr};
+    TcArgs g{C, M, N, R, nullptr, nullptr, 1, 0, 0, 1, accumulate, 0, 0, 0, nullptr, 0};
     cudaStream_t st = (cudaStream_t)stream;
     if (N <= 64) return launch_tc<64, true, true>(A, B, g, st);
     return launch_tc<128, true, true>(A, B, g, st);
