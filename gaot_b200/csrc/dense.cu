@@ -282,7 +282,8 @@ __global__ void __launch_bounds__(NW_THREADS, 1) narrow_rows_kernel(const GemmAr
 
 __global__ void __launch_bounds__(NW_THREADS, 1) narrow_reduce_kernel(const GemmArgs g) {
     // C[m,n] (+)= sum_r A[r*lda + m] * B[r*ldb + n],  m < M <= 64, n < N <= 64, r < K (the long dimension)
-    __shared__ __align__(16) float slab[NW_THREADS / 32][NW_ROWS][64];
+    __shared__ __align__(16) float slab_raw[(NW_THREADS / 32) * NW_ROWS * 64 + 64];   // + 64: the reduction buffer is 64 x 65
+    float (*slab)[NW_ROWS][64] = reinterpret_cast<float (*)[NW_ROWS][64]>(slab_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int M = (int)g.M, N = (int)g.N;
     const int m0 = lane, m1 = lane + 32;
@@ -327,12 +328,25 @@ __global__ void __launch_bounds__(NW_THREADS, 1) narrow_reduce_kernel(const Gemm
             }
         }
     }
+    // CTA-level reduction of the 8 per-warp partials in shared memory (column-major so lanes hit distinct banks),
+    // then ONE coalesced set of 64 x 64 red.adds per CTA instead of one per warp: the per-address serialisation of
+    // same-address atomics in L2 was the whole cost of this kernel
+    static_assert(sizeof(slab_raw) >= 64 * 65 * sizeof(float), "slab doubles as the 64 x 65 reduction buffer");
+    float* cs = slab_raw;                                          // cs[n * 65 + m]: conflict-free both ways
+    __syncthreads();                                               // every warp is done with its staging rows
+    for (int w = 0; w < NW_THREADS / 32; ++w) {
+        if (warp == w) {
 #pragma unroll
-    for (int n = 0; n < 64; ++n) {
-        if (n < N) {
-            if (m0 < M) atomicAdd(g.C + (int64_t)m0 * g.ldc + n, c0[n]);
-            if (m1 < M) atomicAdd(g.C + (int64_t)m1 * g.ldc + n, c1[n]);
+            for (int n = 0; n < 64; ++n) {
+                if (w == 0) { cs[n * 65 + m0] = c0[n]; cs[n * 65 + m1] = c1[n]; }
+                else { cs[n * 65 + m0] += c0[n]; cs[n * 65 + m1] += c1[n]; }
+            }
         }
+        __syncthreads();
+    }
+    for (int i = threadIdx.x; i < 64 * 64; i += NW_THREADS) {
+        const int m = i >> 6, n = i & 63;                          // consecutive threads -> consecutive n: coalesced
+        if (m < M && n < N) atomicAdd(g.C + (int64_t)m * g.ldc + n, cs[n * 65 + m]);
     }
 }
 
