@@ -13,6 +13,7 @@
 //               (or 128-bit red.add for split-K)
 //   3 stages x 32 KB leave room for two CTAs per SM, so one CTA's epilogue overlaps the other's main loop.
 #include <cuda.h>
+#include <cstdlib>
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -110,6 +111,51 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
     return *reinterpret_cast<uint32_t*>(&t);
 }
 
+// ---- CTA-pair (cta_group::2) variants: two CTAs of a cluster (one TPC) work on one 256-row tile.  Each CTA keeps its own
+// 128 rows of A and HALF of the B tile in shared memory; the MMA (issued by the leader, CTA rank 0) reads A from each CTA's
+// own memory and the two B halves from both, and writes each CTA's 128 accumulator rows into that CTA's TMEM.  Operand
+// traffic from L2 per output element is half of the single-CTA kernel's.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load whose completion bytes are counted on the LEADER CTA's mbarrier (same shared-memory offset, CTA-rank bit cleared)
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_c, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_c), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+// commit: arrive on the mbarrier at this offset in BOTH CTAs of the pair once the MMAs issued so far have completed
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+// arrive on the mbarrier at this offset in the leader CTA (rank 0) of the cluster
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, 0;\n\t"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+        ::"r"(smem_u32(bar)) : "memory");
+}
+
+#ifdef EXP_TRACE
+__device__ long long g_trace[4 * 256];
+#define TRACE(slot) do { if (trace_on && (slot) < 256) g_trace[trace_base + (slot)] = clock64(); } while (0)
+#else
+#define TRACE(slot) do { } while (0)
+#endif
 struct TcArgs {
     void* C; int64_t M, N, K;
     const float* bias; const float* add; int64_t add_rows, ldadd;
@@ -132,13 +178,23 @@ __device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t saddr) {
 // so forward / dX / dW of a Linear layer all read activations and weights in their natural layout.
 // Two TMEM accumulators (2*BN columns): the epilogue of tile i overlaps the main loop of tile i+1, and the TMA
 // ring keeps prefetching across tile boundaries.
-template <int BN, bool AMN, bool BMN>
+template <int BN, bool AMN, bool BMN, int CG>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmAdd, const TcArgs g) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    constexpr int A_BYTES = TC_BM * TC_BK * 2, B_BYTES = BN * TC_BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+    constexpr int BNL = BN / CG;                                   // B rows (output columns) held by this CTA
+    constexpr int A_BYTES = TC_BM * TC_BK * 2, B_BYTES = BNL * TC_BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+    const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;       // CG = 2: rank 0 (the leader) issues the MMAs for the pair
+    const int64_t worker = blockIdx.x / CG, n_workers = gridDim.x / CG;
+#ifdef EXP_TRACE
+    // CTA 0: MMA warp -> [0,256), epilogue warp 2 -> [256,512); CTA 1 (the peer): epilogue warp 2 -> [512,768), TMA warp -> [768,1024)
+    const bool trace_on = (threadIdx.x & 31) == 0 && ((blockIdx.x == 0 && ((threadIdx.x >> 5) == 1 || (threadIdx.x >> 5) == 2)) ||
+                                                       (blockIdx.x == 1 && ((threadIdx.x >> 5) == 2 || (threadIdx.x >> 5) == 0)));
+    const int trace_base = blockIdx.x == 0 ? ((threadIdx.x >> 5) == 1 ? 0 : 256) : ((threadIdx.x >> 5) == 2 ? 512 : 768);
+    TRACE(0);
+#endif
     constexpr int PITCH = 36;                                      // fallback epilogue staging: floats per row (16-byte aligned)
     constexpr int STG_WARP = 8192;                                 // per epilogue warp: two 4 KB boxes (32 rows x 32 columns)
     float* stg_all = reinterpret_cast<float*>(smem + TC_STAGES * STAGE_BYTES);
@@ -156,7 +212,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 8); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 8 * CG); }
         for (int s = 0; s < 16; ++s) mbar_init(&add_bar[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -169,19 +225,25 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if (g.add) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmAdd) : "memory");
         }
     }
+    if (CG == 2) cluster_sync_all();                               // the peer's mbarriers exist before anything remote touches them
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)(2 * BN)));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+        if (CG == 1) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)(2 * BN)));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)(2 * BN)));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
+    if (CG == 2) cluster_sync_all(); else __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
 
     auto tile_coords = [&](int64_t t, int64_t& m0, int64_t& n0, int64_t& kb0, int& nkb) {
         const int64_t mi = t % g.gm, rest = t / g.gm;
         const int64_t ni = rest % g.gn, sp = rest / g.gn;
-        m0 = mi * TC_BM; n0 = ni * BN;
+        m0 = mi * (TC_BM * CG) + rank * TC_BM; n0 = ni * BN;
         kb0 = sp * per;
         nkb = (int)max((int64_t)0, min(kblocks, kb0 + per) - kb0);
     };
@@ -190,44 +252,54 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         // ---------------- TMA producer ----------------
         if (lane == 0) {
             uint32_t it = 0;
-            for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            auto load = [&](void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+                if (CG == 2) tma_load_2d_pair(dst, map, bar, c0, c1); else tma_load_2d(dst, map, bar, c0, c1);
+            };
+            for (int64_t t = worker; t < n_tiles; t += n_workers) {
                 int64_t m0, n0, kb0; int nkb;
                 tile_coords(t, m0, n0, kb0, nkb);
+                const int nb0 = (int)n0 + (int)rank * BNL;           // this CTA's half of the B tile
                 for (int i = 0; i < nkb; ++i, ++it) {
                     const int s = (int)(it % TC_STAGES);
                     mbar_wait(&empty_bar[s], ((it / TC_STAGES) & 1u) ^ 1u);
-                    mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+                    TRACE(1 + it);
+                    // one arrival (the leader's) per phase; both CTAs' bytes are counted on the leader's barrier
+                    if (rank == 0) mbar_expect_tx(&full_bar[s], STAGE_BYTES * CG);
                     uint8_t* st = smem + s * STAGE_BYTES;
                     const int kc = (int)((kb0 + i) * TC_BK);
-                    if (!AMN) tma_load_2d(st, &tmA, &full_bar[s], kc, (int)m0);
+                    if (!AMN) load(st, &tmA, &full_bar[s], kc, (int)m0);
                     else {
 #pragma unroll
-                        for (int j = 0; j < TC_BM / 64; ++j) tma_load_2d(st + j * 8192, &tmA, &full_bar[s], (int)m0 + 64 * j, kc);
+                        for (int j = 0; j < TC_BM / 64; ++j) load(st + j * 8192, &tmA, &full_bar[s], (int)m0 + 64 * j, kc);
                     }
-                    if (!BMN) tma_load_2d(st + A_BYTES, &tmB, &full_bar[s], kc, (int)n0);
+                    if (!BMN) load(st + A_BYTES, &tmB, &full_bar[s], kc, nb0);
                     else {
 #pragma unroll
-                        for (int j = 0; j < BN / 64; ++j) tma_load_2d(st + A_BYTES + j * 8192, &tmB, &full_bar[s], (int)n0 + 64 * j, kc);
+                        for (int j = 0; j < BNL / 64; ++j) load(st + A_BYTES + j * 8192, &tmB, &full_bar[s], nb0 + 64 * j, kc);
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        // ---------------- MMA issuer ----------------
+      if (rank == 0) {
+        // ---------------- MMA issuer (CG = 2: the leader CTA issues for the pair) ----------------
         // instruction descriptor: D fp32, A/B bf16, majors per template, N = BN, M = 128 (cute/arch/mma_sm100_desc.hpp)
         constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (AMN ? (1u << 15) : 0u) | (BMN ? (1u << 16) : 0u) |
-                                   ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+                                   ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((TC_BM * CG) >> 4) << 24);
         uint32_t it = 0, lt = 0;
-        for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++lt) {
+        for (int64_t t = worker; t < n_tiles; t += n_workers, ++lt) {
             int64_t m0, n0, kb0; int nkb;
             tile_coords(t, m0, n0, kb0, nkb);
             const uint32_t ab = lt & 1u;
+            TRACE(1 + lt * 8);
             mbar_wait(&acc_empty[ab], ((lt >> 1) & 1u) ^ 1u);       // epilogue has drained this accumulator
+            TRACE(2 + lt * 8);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t tmem_acc = tmem_base + ab * BN;
             for (int i = 0; i < nkb; ++i, ++it) {
                 const int s = (int)(it % TC_STAGES);
                 mbar_wait(&full_bar[s], (it / TC_STAGES) & 1u);
+                if (i < 4) TRACE(3 + lt * 8 + i);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (lane == 0) {
                     const uint32_t sa = smem_u32(smem + s * STAGE_BYTES), sb = sa + A_BYTES;
@@ -239,14 +311,21 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         // 128-byte swizzle row; MN-major: 16 contraction rows = 2048 bytes
                         const uint64_t da = da0 + (uint64_t)(AMN ? (k * 2048) >> 4 : 2 * k);
                         const uint64_t db = db0 + (uint64_t)(BMN ? (k * 2048) >> 4 : 2 * k);
-                        umma_f16(tmem_acc, da, db, IDESC, (i > 0 || k > 0) ? 1u : 0u);
+                        if (CG == 2) umma_f16_pair(tmem_acc, da, db, IDESC, (i > 0 || k > 0) ? 1u : 0u);
+                        else umma_f16(tmem_acc, da, db, IDESC, (i > 0 || k > 0) ? 1u : 0u);
                     }
-                    umma_commit(&empty_bar[s]);                    // frees the slot once these MMAs have read it
-                    if (i == nkb - 1) umma_commit(&acc_full[ab]);  // accumulator complete
+                    if (CG == 2) {
+                        umma_commit_pair(&empty_bar[s]);           // frees the slot in both CTAs
+                        if (i == nkb - 1) umma_commit_pair(&acc_full[ab]);
+                    } else {
+                        umma_commit(&empty_bar[s]);                // frees the slot once these MMAs have read it
+                        if (i == nkb - 1) umma_commit(&acc_full[ab]);  // accumulator complete
+                    }
                 }
                 __syncwarp();
             }
         }
+      }
     } else {
         // ---------------- epilogue (8 warps; warp w may touch TMEM lanes 32*(w%4) .. +31) ----------------
         // TMEM hands each thread one accumulator ROW.  A per-warp 32x32 fp32 staging tile turns that into
@@ -259,92 +338,133 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             // row: TMEM -> registers (+ bias, + the `add` tile that TMA has loaded into the same box, activation) ->
             // 16-byte stores into a swizzled 32 x 32 box (fp32: 128-byte rows, SWIZZLE_128B; bf16: 64-byte rows,
             // SWIZZLE_64B; both conflict-free) -> one TMA store per box.  Rows >= M / columns >= N are clipped by TMA.
-            constexpr int NCH = BN / 64;                           // chunks per warp and tile (BN = 128: 2, BN = 64: 1)
+            constexpr int NCH = BN / 64;                           // 32-column chunks per warp and tile (BN = 256: 4, 128: 2, 64: 1)
+            constexpr int PCH = NCH < 2 ? NCH : 2;                 // chunks per pass = staging boxes per warp
+            constexpr int NPASS = NCH / PCH;
             const uint32_t box0 = smem_u32(smem + TC_STAGES * STAGE_BYTES) + (uint32_t)(warp - 2) * STG_WARP;
             uint64_t* abar = add_bar + (warp - 2) * 2;
-            uint32_t lt = 0, aload[NCH] = {};                      // add boxes loaded so far (mbarrier phase bookkeeping)
-            for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++lt) {
+            uint32_t lt = 0, aload[2] = {};                        // add boxes loaded so far (mbarrier phase bookkeeping)
+            for (int64_t t = worker; t < n_tiles; t += n_workers, ++lt) {
                 int64_t m0, n0, kb0; int nkb;
                 tile_coords(t, m0, n0, kb0, nkb);
                 const uint32_t ab = lt & 1u;
                 const int row0 = (int)m0 + q * 32;
                 const int64_t ncol0 = n0 + half * (BN / 2);
-                // both boxes must have been read out by the previous tile's TMA stores before they are refilled
-                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                __syncwarp();
-                if (g.add) {
-                    const int arow = (int)((int64_t)row0 % g.add_rows);
-#pragma unroll
-                    for (int c = 0; c < NCH; ++c) {
-                        if (ncol0 + c * 32 < g.N && row0 < g.M) {
-                            if (lane == 0) {
-                                mbar_expect_tx(&abar[c], 4096);
-                                tma_load_2d_s(box0 + c * 4096, &tmAdd, &abar[c], (int)ncol0 + c * 32, arow);
-                            }
-                            ++aload[c];
-                        }
-                    }
-                }
-                mbar_wait(&acc_full[ab], (lt >> 1) & 1u);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const int arow = g.add ? (int)((int64_t)row0 % g.add_rows) : 0;
                 const uint32_t tmem_acc = tmem_base + ab * BN + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * (BN / 2));
-                uint32_t r[NCH][32];
 #pragma unroll
-                for (int c = 0; c < NCH; ++c) tmem_ld32_issue(tmem_acc + c * 32, r[c]);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                // the accumulator is in registers: hand it back to the MMA warp before the stores
-                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                __syncwarp();
-                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[ab])) : "memory");
-                if (row0 >= g.M) continue;                         // warp-uniform: nothing of this warp's rows exists
-#pragma unroll
-                for (int c = 0; c < NCH; ++c) {
-                    const int64_t n = ncol0 + c * 32;
-                    if (n >= g.N) continue;                        // warp-uniform
-                    const uint32_t box = box0 + c * 4096;
-                    float v[32];
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[c][j]);
-                    if (g.bias) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (n + j < g.N) bv = __ldg(reinterpret_cast<const float4*>(g.bias + n + j));   // N % 4 == 0 on this path
-                            v[j] += bv.x; v[j + 1] += bv.y; v[j + 2] += bv.z; v[j + 3] += bv.w;
-                        }
-                    }
-                    if (g.add) {
-                        mbar_wait(&abar[c], (aload[c] - 1u) & 1u);
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            const float4 av = lds_f4(box + (uint32_t)lane * 128u + (uint32_t)((((j >> 2) ^ (lane & 7))) << 4));
-                            v[j] += av.x; v[j + 1] += av.y; v[j + 2] += av.z; v[j + 3] += av.w;
-                        }
-                    }
-                    if (g.act == GAOT_ACT_GELU) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-                    } else if (g.act == GAOT_ACT_RELU) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-                    }
-                    if (g.out_bf16) {
-#pragma unroll
-                        for (int w = 0; w < 4; ++w)
-                            sts_u4(box + (uint32_t)lane * 64u + (uint32_t)((w ^ ((lane >> 1) & 3)) << 4),
-                                   pack_bf16x2(v[8 * w], v[8 * w + 1]), pack_bf16x2(v[8 * w + 2], v[8 * w + 3]),
-                                   pack_bf16x2(v[8 * w + 4], v[8 * w + 5]), pack_bf16x2(v[8 * w + 6], v[8 * w + 7]));
-                    } else {
-#pragma unroll
-                        for (int w = 0; w < 8; ++w)
-                            sts_f4(box + (uint32_t)lane * 128u + (uint32_t)((w ^ (lane & 7)) << 4), v[4 * w], v[4 * w + 1], v[4 * w + 2], v[4 * w + 3]);
-                    }
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                for (int ps = 0; ps < NPASS; ++ps) {
+                    // both boxes must have been read out by the previous TMA stores before they are refilled
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                     __syncwarp();
-                    if (lane == 0) {
-                        tma_store_2d(&tmC, box, (int)n, row0);
-                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    if (g.add) {
+#pragma unroll
+                        for (int c = 0; c < PCH; ++c) {
+                            if (ncol0 + (ps * PCH + c) * 32 < g.N && row0 < g.M) {
+                                if (lane == 0) {
+                                    mbar_expect_tx(&abar[c], 4096);
+                                    tma_load_2d_s(box0 + c * 4096, &tmAdd, &abar[c], (int)ncol0 + (ps * PCH + c) * 32, arow);
+                                }
+                                ++aload[c];
+                            }
+                        }
                     }
+                    if (ps == 0) {
+                        TRACE(1 + lt * 8);
+                        mbar_wait(&acc_full[ab], (lt >> 1) & 1u);
+                        TRACE(2 + lt * 8);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    }
+                    uint32_t r[PCH][32];
+#pragma unroll
+                    for (int c = 0; c < PCH; ++c) tmem_ld32_issue(tmem_acc + (ps * PCH + c) * 32, r[c]);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    TRACE(3 + lt * 8 + 2 * ps);
+                    if (ps == NPASS - 1) {
+                        // the accumulator is in registers: hand it back to the MMA warp before the stores
+                        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                        __syncwarp();
+                        if (lane == 0) {
+                            if (CG == 2) mbar_arrive_leader(&acc_empty[ab]);
+                            else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[ab])) : "memory");
+                        }
+                    }
+                    if (row0 >= g.M) continue;                     // warp-uniform: nothing of this warp's rows exists
+#pragma unroll
+                    for (int c = 0; c < PCH; ++c) {
+                        const int64_t n = ncol0 + (ps * PCH + c) * 32;
+                        if (n >= g.N) continue;                    // warp-uniform
+                        const uint32_t box = box0 + c * 4096;
+                        float v[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[c][j]);
+                        if (g.bias) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+                                if (n + j < g.N) bv = __ldg(reinterpret_cast<const float4*>(g.bias + n + j));   // N % 4 == 0 on this path
+                                v[j] += bv.x; v[j + 1] += bv.y; v[j + 2] += bv.z; v[j + 3] += bv.w;
+                            }
+                        }
+                        if (g.add) {
+                            mbar_wait(&abar[c], (aload[c] - 1u) & 1u);
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                const float4 av = lds_f4(box + (uint32_t)lane * 128u + (uint32_t)((((j >> 2) ^ (lane & 7))) << 4));
+                                v[j] += av.x; v[j + 1] += av.y; v[j + 2] += av.z; v[j + 3] += av.w;
+                            }
+                        }
+                        if (g.act == GAOT_ACT_GELU) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+                        } else if (g.act == GAOT_ACT_RELU) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+                        }
+                        if (g.out_bf16) {
+                            if (PCH == 2) {
+                                // both chunks of the pass share ONE 32-row x 64-column box (128-byte rows, SWIZZLE_128B):
+                                // TMA stores are paced per box row, so 128-byte rows halve the row count
+#pragma unroll
+                                for (int w = 0; w < 4; ++w)
+                                    sts_u4(box0 + (uint32_t)lane * 128u + (uint32_t)(((c * 4 + w) ^ (lane & 7)) << 4),
+                                           pack_bf16x2(v[8 * w], v[8 * w + 1]), pack_bf16x2(v[8 * w + 2], v[8 * w + 3]),
+                                           pack_bf16x2(v[8 * w + 4], v[8 * w + 5]), pack_bf16x2(v[8 * w + 6], v[8 * w + 7]));
+                            } else {
+#pragma unroll
+                                for (int w = 0; w < 4; ++w)
+                                    sts_u4(box + (uint32_t)lane * 64u + (uint32_t)((w ^ ((lane >> 1) & 3)) << 4),
+                                           pack_bf16x2(v[8 * w], v[8 * w + 1]), pack_bf16x2(v[8 * w + 2], v[8 * w + 3]),
+                                           pack_bf16x2(v[8 * w + 4], v[8 * w + 5]), pack_bf16x2(v[8 * w + 6], v[8 * w + 7]));
+                            }
+                        } else {
+#pragma unroll
+                            for (int w = 0; w < 8; ++w)
+                                sts_f4(box + (uint32_t)lane * 128u + (uint32_t)((w ^ (lane & 7)) << 4), v[4 * w], v[4 * w + 1], v[4 * w + 2], v[4 * w + 3]);
+                        }
+                        if (g.out_bf16 && PCH == 2) {
+                            // one store for the pass, after its last existing chunk (clipped at N by TMA)
+                            const bool last = c == PCH - 1 || n + 32 >= g.N;
+                            if (last) {
+                                if (ps == NPASS - 1) TRACE(7 + lt * 8);
+                                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                                __syncwarp();
+                                if (ps == NPASS - 1) TRACE(8 + lt * 8);
+                                if (lane == 0) {
+                                    tma_store_2d(&tmC, box0, (int)(ncol0 + ps * PCH * 32), row0);
+                                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                                }
+                            }
+                        } else {
+                            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                            __syncwarp();
+                            if (lane == 0) {
+                                tma_store_2d(&tmC, box, (int)n, row0);
+                                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                            }
+                        }
+                    }
+                    TRACE(4 + lt * 8 + 2 * ps);
                 }
             }
             if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -355,7 +475,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
         const bool atomic = g.splits > 1 || g.accumulate;
         uint32_t lt = 0;
-        for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++lt) {
+        for (int64_t t = worker; t < n_tiles; t += n_workers, ++lt) {
             int64_t m0, n0, kb0; int nkb;
             tile_coords(t, m0, n0, kb0, nkb);
             const uint32_t ab = lt & 1u;
@@ -464,15 +584,19 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             // this warp is done with the accumulator: let the MMA warp reuse it
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
-            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[ab])) : "memory");
+            if (lane == 0) {
+                if (CG == 2) mbar_arrive_leader(&acc_empty[ab]);
+                else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[ab])) : "memory");
+            }
         }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
+    if (CG == 2) cluster_sync_all(); else __syncthreads();       // pair: nobody leaves while the peer may still touch its memory
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * BN)));
+        if (CG == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * BN)));
+        else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * BN)));
     }
 }
 
@@ -571,16 +695,16 @@ int make_map_mn(CUtensorMap* map, const void* base, int64_t R, int64_t cols) {
 
 // output / add boxes of the fast epilogue: [rows, ld] matrix of fp32 or bf16, box {32 columns, 32 rows}, swizzle span =
 // the 32-column row (128 bytes fp32 / 64 bytes bf16)
-int make_map_box32(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, bool bf16) {
+int make_map_box32(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, bool bf16, int box_cols = 32) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return GAOT_E_BADARG;
     const int es = bf16 ? 2 : 4;
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)ld * es};
-    cuuint32_t box[2] = {32, 32};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, 32};
     cuuint32_t estr[2] = {1, 1};
     const CUtensorMapDataType dt = bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
-    const CUtensorMapSwizzle sw = bf16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
+    const CUtensorMapSwizzle sw = (bf16 && box_cols == 32) ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;   // span = row bytes
     CUresult r = enc(map, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r == CUDA_ERROR_INVALID_CONTEXT) {
@@ -601,20 +725,21 @@ int sm_count() {
     return n;
 }
 
-template <int BN, bool AMN, bool BMN>
+template <int BN, bool AMN, bool BMN, int CG>
 int launch_tc(const void* A, const void* B, TcArgs& g, cudaStream_t st) {
+    constexpr int BNL = BN / CG;
     CUtensorMap ta, tb;
     int rc = AMN ? make_map_mn(&ta, A, g.K, g.M) : make_map(&ta, A, g.M, g.K, TC_BM);
     if (rc) return rc;
-    rc = BMN ? make_map_mn(&tb, B, g.K, g.N) : make_map(&tb, B, g.N, g.K, BN);
+    rc = BMN ? make_map_mn(&tb, B, g.K, g.N) : make_map(&tb, B, g.N, g.K, BNL);
     if (rc) return rc;
-    g.gm = (g.M + TC_BM - 1) / TC_BM;
+    g.gm = (g.M + TC_BM * CG - 1) / (TC_BM * CG);
     g.gn = (g.N + BN - 1) / BN;
     const int64_t kblocks = (g.K + TC_BK - 1) / TC_BK, tiles = g.gm * g.gn;
-    const int sms = sm_count();
+    const int workers = sm_count() / CG;                        // CTAs (CG = 1) or CTA pairs (CG = 2) resident on the chip
     int splits = 1;
-    if (!g.out_bf16 && !g.act && !g.pre && tiles < sms && kblocks >= 8) {   // too few tiles for the chip: split the contraction
-        splits = (int)((2 * sms + tiles - 1) / tiles);
+    if (!g.out_bf16 && !g.act && !g.pre && tiles < workers && kblocks >= 8) {   // too few tiles for the chip: split the contraction
+        splits = (int)((2 * workers + tiles - 1) / tiles);
         if (splits > kblocks / 4) splits = (int)(kblocks / 4);
         if (splits > 128) splits = 128;
         if (splits < 1) splits = 1;
@@ -632,23 +757,41 @@ int launch_tc(const void* A, const void* B, TcArgs& g, cudaStream_t st) {
              (!g.add || (!g.out_bf16 && g.add_rows % 32 == 0 && g.ldadd % 4 == 0 && !(reinterpret_cast<uintptr_t>(g.add) & 15))) &&
              (!g.bias || !(reinterpret_cast<uintptr_t>(g.bias) & 15));
     if (g.fast) {
-        rc = make_map_box32(&tc, g.C, g.M, g.N, g.N, g.out_bf16 != 0);
+        rc = make_map_box32(&tc, g.C, g.M, g.N, g.N, g.out_bf16 != 0, (g.out_bf16 && BN >= 128) ? 64 : 32);
         if (rc) return rc;
         if (g.add) {
             rc = make_map_box32(&tadd, g.add, g.add_rows, g.N, g.ldadd, false);
             if (rc) return rc;
         }
     }
-    constexpr int SMEM = TC_STAGES * (TC_BM * TC_BK * 2 + BN * TC_BK * 2) + 8 * 8192 + 1024 + 512;
+    constexpr int SMEM = TC_STAGES * (TC_BM * TC_BK * 2 + BNL * TC_BK * 2) + 8 * 8192 + 1024 + 512;
     static bool attr_done = false;
     if (!attr_done) {
-        GAOT_CHECK(cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN, AMN, BMN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+        GAOT_CHECK(cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN, AMN, BMN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
         attr_done = true;
     }
     const int64_t total = tiles * splits;
-    const unsigned grid = (unsigned)(total < sms ? total : sms);   // persistent: one CTA per SM
-    gemm_bf16_tc_kernel<BN, AMN, BMN><<<grid, TC_THREADS, SMEM, st>>>(ta, tb, tc, tadd, g);
+    const unsigned grid = (unsigned)((total < workers ? total : workers) * CG);   // persistent: one CTA per SM
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid, 1, 1);
+    cfg.blockDim = dim3(TC_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    GAOT_CHECK(cudaLaunchKernelEx(&cfg, gemm_bf16_tc_kernel<BN, AMN, BMN, CG>, ta, tb, tc, tadd, g));
     GAOT_RETURN_LAST();
+}
+
+// N >= 256: CTA pairs on 256 x 256 tiles; narrower outputs: one CTA per 128 x 128 / 128 x 64 tile
+template <bool AMN, bool BMN>
+int dispatch_tc(const void* A, const void* B, TcArgs& g, cudaStream_t st) {
+    if (g.N <= 64) return launch_tc<64, AMN, BMN, 1>(A, B, g, st);
+    if (g.N < 256 || getenv("GAOT_GEMM_NO_PAIR")) return launch_tc<128, AMN, BMN, 1>(A, B, g, st);
+    return launch_tc<256, AMN, BMN, 2>(A, B, g, st);
 }
 
 }  // namespace
@@ -666,8 +809,7 @@ GAOT_API int gaot_gemm_bf16(const void* A, const void* B, void* C, int64_t M, in
     if (M > 0x7fffffffLL || N > 0x7fffffffLL || K > 0x7fffffffLL) return GAOT_E_BADARG;
     TcArgs g{C, M, N, K, bias, add, add ? add_rows : 1, ldadd, out_bf16, 1, accumulate, 0, 0, act, pre, 0};
     cudaStream_t st = (cudaStream_t)stream;
-    if (N <= 64) return launch_tc<64, false, false>(A, B, g, st);
-    return launch_tc<128, false, false>(A, B, g, st);
+    return dispatch_tc<false, false>(A, B, g, st);
 }
 
 GAOT_API int gaot_gemm_bf16_nn(const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K, int out_bf16,
@@ -679,8 +821,7 @@ GAOT_API int gaot_gemm_bf16_nn(const void* A, const void* B, void* C, int64_t M,
     if (M > 0x7fffffffLL || N > 0x7fffffffLL || K > 0x7fffffffLL) return GAOT_E_BADARG;
     TcArgs g{C, M, N, K, nullptr, nullptr, 1, 0, out_bf16, 1, 0, 0, 0, 0, nullptr, 0};
     cudaStream_t st = (cudaStream_t)stream;
-    if (N <= 64) return launch_tc<64, false, true>(A, B, g, st);
-    return launch_tc<128, false, true>(A, B, g, st);
+    return dispatch_tc<false, true>(A, B, g, st);
 }
 
 GAOT_API int gaot_gemm_bf16_tn(const void* A, const void* B, float* C, int64_t M, int64_t N, int64_t R, int accumulate,
@@ -692,8 +833,7 @@ GAOT_API int gaot_gemm_bf16_tn(const void* A, const void* B, float* C, int64_t M
     if (M > 0x7fffffffLL || N > 0x7fffffffLL || R > 0x7fffffffLL) return GAOT_E_BADARG;
     TcArgs g{C, M, N, R, nullptr, nullptr, 1, 0, 0, 1, accumulate, 0, 0, 0, nullptr, 0};
     cudaStream_t st = (cudaStream_t)stream;
-    if (N <= 64) return launch_tc<64, true, true>(A, B, g, st);
-    return launch_tc<128, true, true>(A, B, g, st);
+    return dispatch_tc<true, true>(A, B, g, st);
 }
 
 GAOT_API int gaot_cast_bf16(const float* in, void* out, int64_t rows, int64_t cols, void* out_t, void* stream) {
@@ -722,3 +862,7 @@ GAOT_API int gaot_transpose_bf16(const void* in, void* out_t, int64_t rows, int6
                                                                                  reinterpret_cast<__nv_bfloat16*>(out_t), rows, cols);
     GAOT_RETURN_LAST();
 }
+
+#ifdef EXP_TRACE
+GAOT_API int gaot_debug_trace_gemm(long long* out) { return (int)cudaMemcpyFromSymbol(out, g_trace, sizeof(g_trace)); }
+#endif

@@ -12,19 +12,14 @@ for _ in range(3):
     ops.gemm_bf16(a, b, M, N, K, out_bf16=bool(o16))
 torch.cuda.synchronize()
 L = ctypes.CDLL(_lib.LIB_PATH)
-buf = (ctypes.c_longlong * (8 * 256))()
+buf = (ctypes.c_longlong * (4 * 256))()
 print("rc", L.gaot_debug_trace_gemm(buf))
-for cta, base in ((0, 0), (77, 1024)):
-    tma = [buf[base + k] for k in range(256)]
-    mma = [buf[base + 256 + k] for k in range(256)]
-    ep = [buf[base + 512 + k] for k in range(256)]
-    ep9 = [buf[base + 768 + k] for k in range(256)]
-    t0 = tma[0]
-    print(f"CTA {cta}: alloc done +{tma[1]-t0}")
-    print("  TMA k-block issue times:", [tma[2 + i] - t0 for i in range(24)])
-    for lt in range(6):
-        m = [mma[2 + lt * 8 + k] - t0 for k in range(6)]
-        e = [ep[2 + lt * 12 + k] - t0 for k in range(11)]
-        print(f"  tile {lt}: MMA top {m[0]} acc_empty +{m[1]-m[0]} kblocks ready {[x - m[1] for x in m[2:6]]} | "
-              f"epi(w2) top {e[0]} acc_full +{e[1]-e[0]} chunk0: ld +{e[2]-e[1]} sts +{e[3]-e[2]} lds +{e[4]-e[3]} st +{e[5]-e[4]} "
-              f"chunk1: ld +{e[6]-e[5]} sts +{e[7]-e[6]} lds +{e[8]-e[7]} st +{e[9]-e[8]} end +{e[10]-e[9]}")
+mma = [buf[k] for k in range(256)]; e0 = [buf[256 + k] for k in range(256)]; e1 = [buf[512 + k] for k in range(256)]; tma = [buf[768 + k] for k in range(256)]
+t0 = mma[0]
+print("peer TMA k-block issue times:", [tma[1 + i] - tma[0] for i in range(24)])
+for lt in range(8):
+    m = [mma[1 + lt * 8 + k] - t0 for k in range(6)]
+    a = [e0[1 + lt * 8 + k] - t0 for k in range(8)]
+    b = [e1[1 + lt * 8 + k] - e1[0] for k in range(6)]
+    print(f"tile {lt}: MMA top {m[0]} acc_empty+{m[1]-m[0]} kblk {[x - m[1] for x in m[2:6]]} | epi0 top {a[0]} acc_full+{a[1]-a[0]} "
+          f"ld0+{a[2]-a[1]} st0+{a[3]-a[2]} ld1+{a[4]-a[3]} st1+{a[5]-a[4]} (cvt+sts {a[6]-a[4]}, fence {a[7]-a[6]}, issue {a[5]-a[7]}) | epi1(peer) top {b[0]} acc_full+{b[1]-b[0]} ld0+{b[2]-b[1]} st0+{b[3]-b[2]} ld1+{b[4]-b[3]} st1+{b[5]-b[4]}")
