@@ -23,7 +23,7 @@
 
 namespace {
 
-constexpr int AT_THREADS = 192;
+constexpr int AT_THREADS = 320;           // forward: TMA warp, MMA warp, 8 softmax warps (2 per TMEM lane quadrant)
 constexpr int AT_BWD_CW = 16;            // compute warps of the backward kernel (4 per TMEM lane quadrant)
 constexpr int AT_BWD_THREADS = 64 + 32 * AT_BWD_CW;   // + TMA warp, MMA warp
 constexpr int AT_BQ = 128, AT_BKV = 128;
@@ -184,27 +184,89 @@ struct AttnArgs {
     float scale_log2;
 };
 
+// tcgen05.ld / tcgen05.st 32x32b of N (8 / 16 / 32) consecutive columns (issue only; pair with the matching wait)
+template <int N>
+__device__ __forceinline__ void tmem_ldN_issue(uint32_t taddr, uint32_t (&r)[N]) {
+    static_assert(N == 8 || N == 16 || N == 32, "unsupported column count");
+    if constexpr (N == 8) {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr));
+    } else if constexpr (N == 16) {
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+              "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+            : "r"(taddr));
+    } else {
+        tmem_ld32_issue(taddr, r);
+    }
+}
+template <int N>
+__device__ __forceinline__ void tmem_stN(uint32_t taddr, const uint32_t (&r)[N]) {
+    static_assert(N == 8 || N == 16 || N == 32, "unsupported column count");
+    if constexpr (N == 8) {
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                     ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+    } else if constexpr (N == 16) {
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+                     ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+                       "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+    } else {
+        asm volatile(
+            "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,"
+            "%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+            ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+              "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+              "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]),
+              "r"(r[29]), "r"(r[30]), "r"(r[31]) : "memory");
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float lds_f32(uint32_t a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_f32_(uint32_t a, float x) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(x) : "memory"); }
+__device__ __forceinline__ void sts_u4_(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+
+// Forward, one CTA per (128-query tile, head, sample), two CTAs per SM:
+//   warp 0    TMA producer: Q once, then K/V tiles of 128 keys through a 2-stage mbarrier ring
+//   warp 1    MMA issuer  : S = Q K^T into TMEM; O += P V with the accumulator kept in TMEM for the whole row block
+//   warps 2-9 softmax     : 2 warps per TMEM lane quadrant; a thread owns one query row and 64 of the 128 key columns of
+//                           a tile: S -> registers (the S columns are released at once, so S(i+1) is computed during the
+//                           softmax of tile i), row max exchanged with the partner warp through shared memory, base-2
+//                           exponentials on MUFU, P (bf16) into one of two swizzled shared-memory tiles.
+// The running maximum is only raised when the new row maximum exceeds it by more than 2^8 (lazy rescaling): the O
+// accumulator is then rescaled in place in TMEM (tcgen05.ld / st); otherwise P is formed against the stale maximum, which
+// is exact after the final division by the row sum.  No per-tile read-back of O.
 template <int HD>
-__global__ void __launch_bounds__(AT_THREADS)
+__global__ void __launch_bounds__(AT_THREADS, 2)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttnArgs g) {
     constexpr int ROWB = HD * 2;                         // bytes per head row = swizzle span
     constexpr int TILE_BYTES = 128 * ROWB;               // a 128-row Q / K / V tile
     constexpr int P_BYTES = AT_BQ * AT_BKV * 2;          // 32 KB: two 64-column SWIZZLE_128B blocks
-    constexpr uint32_t TMEM_COLS = 256;                  // S: [0,128), PV: [128,128+HD)
+    constexpr uint32_t TMEM_COLS = 256;                  // S: [0,128), O: [128,128+HD)
+    constexpr int NO = HD / 2;                           // O columns per thread (the two warps of a quadrant split HD)
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* sQ = smem;
     uint8_t* sK = sQ + TILE_BYTES;                       // [2 stages]
     uint8_t* sV = sK + 2 * TILE_BYTES;                   // [2 stages]
-    uint8_t* sP = sV + 2 * TILE_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + P_BYTES);
+    uint8_t* sP = sV + 2 * TILE_BYTES;                   // [2 buffers]
+    float* sX = reinterpret_cast<float*>(sP + 2 * P_BYTES);   // [2 parities][2 halves][128 rows] row-max / row-sum exchange
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sX + 512);
     uint64_t* q_bar = bars;
     uint64_t* kv_full = bars + 1;      // [2]
     uint64_t* kv_empty = bars + 3;     // [2]
-    uint64_t* s_full = bars + 5;
-    uint64_t* p_full = bars + 6;
-    uint64_t* o_full = bars + 7;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+    uint64_t* s_full = bars + 5;       //      S(i) complete
+    uint64_t* s_free = bars + 6;       //      8 warp arrivals: S(i) is in registers
+    uint64_t* p_full = bars + 7;       //      8 warp arrivals: P(i) written
+    uint64_t* p_free = bars + 8;       // [2]  PV(i) has finished reading P buffer i & 1
+    uint64_t* o_step = bars + 10;      //      PV(i) complete (one phase per tile)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int t0 = blockIdx.x * AT_BQ, h = blockIdx.y, b = blockIdx.z;
@@ -214,8 +276,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttnArgs g) {
 
     if (threadIdx.x == 0) {
         mbar_init(q_bar, 1);
-        for (int s = 0; s < 2; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
-        mbar_init(s_full, 1); mbar_init(p_full, 4); mbar_init(o_full, 1);    // p_full: one arrival per softmax warp
+        for (int s = 0; s < 2; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); mbar_init(&p_free[s], 1); }
+        mbar_init(s_full, 1); mbar_init(s_free, 8); mbar_init(p_full, 8); mbar_init(o_step, 1);   // 8: one arrival per softmax warp
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -227,7 +289,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttnArgs g) {
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *tmem_slot;
-    const uint32_t tmem_s = tmem, tmem_pv = tmem + 128;
+    const uint32_t tmem_s = tmem, tmem_o = tmem + 128;
 
     if (warp == 0) {
         if (lane == 0) {
@@ -261,119 +323,131 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttnArgs g) {
         issue_s(0);
         for (int i = 0; i < n_tiles; ++i) {
             const int s = i & 1;
+            if (i + 1 < n_tiles) {
+                mbar_wait(s_free, (uint32_t)i & 1u);                 // S(i) is in the softmax warps' registers
+                issue_s(i + 1);
+            }
             mbar_wait(p_full, (uint32_t)i & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (lane == 0) {
-                // descriptors are base + compile-time offsets (start-address field counts 16-byte units): the single
-                // issuing thread must not spend its time rebuilding them
-                const uint64_t da0 = make_desc<128>(smem_u32(sP)), db0 = make_desc<ROWB>(smem_u32(sV + s * TILE_BYTES));
+                // descriptors are base + compile-time offsets (start-address field counts 16-byte units)
+                const uint64_t da0 = make_desc<128>(smem_u32(sP + s * P_BYTES)), db0 = make_desc<ROWB>(smem_u32(sV + s * TILE_BYTES));
 #pragma unroll
                 for (int k = 0; k < AT_BKV / 16; ++k) {
                     // A: 16 keys = 32 bytes inside the 128-byte swizzle row of P's column block (k / 4)
                     const uint64_t da = da0 + (uint64_t)(((k >> 2) * (AT_BQ * 128) + (k & 3) * 32) >> 4);
                     // B: 16 keys = 16 rows of V, two 8-row swizzle atoms
                     const uint64_t db = db0 + (uint64_t)((k * 16 * ROWB) >> 4);
-                    umma_f16(tmem_pv, da, db, IDESC_PV, k > 0 ? 1u : 0u);
+                    umma_f16(tmem_o, da, db, IDESC_PV, (i > 0 || k > 0) ? 1u : 0u);
                 }
-                umma_commit(o_full);
+                umma_commit(o_step);
+                umma_commit(&p_free[s]);
                 umma_commit(&kv_empty[s]);
             }
             __syncwarp();
-            if (i + 1 < n_tiles) issue_s(i + 1);
         }
     } else {
-        const int q = warp & 3;
+        const int q = warp & 3, hf = (warp - 2) >> 2;      // TMEM lane quadrant, column half of the tile
         const int r = q * 32 + lane;                       // query row inside the tile == TMEM lane
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-        float o[HD];
-#pragma unroll
-        for (int d = 0; d < HD; ++d) o[d] = 0.f;
-        float mrun = -INFINITY, lrun = 0.f;
+        const uint32_t xs = smem_u32(sX);
+        const uint32_t bar_id = 1 + q;                     // named barrier of the two warps that share this quadrant
+        float mref = -INFINITY, lsum = 0.f;                // reference maximum (base-2 units), partial row sum (own columns)
         for (int i = 0; i < n_tiles; ++i) {
             mbar_wait(s_full, (uint32_t)i & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const int kv_left = g.T - i * AT_BKV;          // keys of this tile that exist
-            const bool full_tile = kv_left >= AT_BKV;      // warp-uniform: only the last tile can be ragged
-            float mx = -INFINITY;                          // max of the RAW scores (scale > 0)
-#pragma unroll 1
-            for (int c = 0; c < 4; c += 2) {               // two 32-column loads in flight per TMEM round trip
-                uint32_t v[32], v2[32];
-                tmem_ld32_issue(tmem_s + lane_addr + c * 32, v);
-                tmem_ld32_issue(tmem_s + lane_addr + (c + 1) * 32, v2);
-                tmem_wait_ld();
-                if (full_tile) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) mx = fmaxf(mx, fmaxf(__uint_as_float(v[j]), __uint_as_float(v2[j])));
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        mx = fmaxf(mx, (c * 32 + j < kv_left) ? __uint_as_float(v[j]) : -INFINITY);
-                        mx = fmaxf(mx, ((c + 1) * 32 + j < kv_left) ? __uint_as_float(v2[j]) : -INFINITY);
-                    }
-                }
-            }
-            const float mnew = fmaxf(mrun, mx * g.scale_log2);
-            const float corr = ex2(mrun - mnew);
-            float psum = 0.f;
-            auto emit = [&](const uint32_t (&v)[32], int c) {      // 32 columns -> bf16 P -> 4 x 16-byte swizzled stores
-                uint32_t pk[16];
-                if (full_tile) {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 2) {
-                        const float p0 = ex2(fmaf(__uint_as_float(v[j]), g.scale_log2, -mnew));
-                        const float p1 = ex2(fmaf(__uint_as_float(v[j + 1]), g.scale_log2, -mnew));
-                        psum += p0 + p1;
-                        pk[j >> 1] = pack_bf16(p0, p1);
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 2) {
-                        const float p0 = (c * 32 + j < kv_left) ? ex2(fmaf(__uint_as_float(v[j]), g.scale_log2, -mnew)) : 0.f;
-                        const float p1 = (c * 32 + j + 1 < kv_left) ? ex2(fmaf(__uint_as_float(v[j + 1]), g.scale_log2, -mnew)) : 0.f;
-                        psum += p0 + p1;
-                        pk[j >> 1] = pack_bf16(p0, p1);
-                    }
-                }
-                uint8_t* blk = sP + (c >> 1) * (AT_BQ * 128);
-#pragma unroll
-                for (int w = 0; w < 4; ++w)
-                    *reinterpret_cast<uint4*>(blk + sw128_off(r, (c & 1) * 4 + w)) = make_uint4(pk[4 * w], pk[4 * w + 1], pk[4 * w + 2], pk[4 * w + 3]);
-            };
-#pragma unroll 1
-            for (int c = 0; c < 4; c += 2) {
-                uint32_t v[32], v2[32];
-                tmem_ld32_issue(tmem_s + lane_addr + c * 32, v);
-                tmem_ld32_issue(tmem_s + lane_addr + (c + 1) * 32, v2);
-                tmem_wait_ld();
-                emit(v, c);
-                emit(v2, c + 1);
-            }
-            lrun = lrun * corr + psum;
-            mrun = mnew;
+            uint32_t sv[2][32];
+            tmem_ld32_issue(tmem_s + lane_addr + hf * 64, sv[0]);
+            tmem_ld32_issue(tmem_s + lane_addr + hf * 64 + 32, sv[1]);
+            tmem_wait_ld();
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(s_free);            // the MMA warp may overwrite S with tile i+1
+            const int kv_left = g.T - i * AT_BKV - hf * 64;   // of this thread's 64 columns, how many keys exist
+            const bool full_tile = kv_left >= 64;          // warp-uniform: only the last tile can be ragged
+            float mx = -INFINITY;                          // max of the RAW scores (scale > 0)
+            if (full_tile) {
+                float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // four independent chains
+#pragma unroll
+                for (int j = 0; j < 32; ++j) m4[j & 3] = fmaxf(m4[j & 3], fmaxf(__uint_as_float(sv[0][j]), __uint_as_float(sv[1][j])));
+                mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    mx = fmaxf(mx, (j < kv_left) ? __uint_as_float(sv[0][j]) : -INFINITY);
+                    mx = fmaxf(mx, (32 + j < kv_left) ? __uint_as_float(sv[1][j]) : -INFINITY);
+                }
+            }
+            // row maximum over all 128 columns: exchange with the partner warp (same rows, other column half)
+            const uint32_t xa = xs + (uint32_t)(((i & 1) * 2 + hf) * 128 + r) * 4u, xb = xs + (uint32_t)(((i & 1) * 2 + (hf ^ 1)) * 128 + r) * 4u;
+            sts_f32_(xa, mx);
+            asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+            const float mrow = fmaxf(mx, lds_f32(xb)) * g.scale_log2;
+            // lazy rescaling: identical decision in both warps of the quadrant (same rows, same maxima)
+            if (__any_sync(0xffffffffu, mrow > mref + 8.f)) {
+                const float mnew = fmaxf(mref, mrow);
+                const float corr = ex2(mref - mnew);       // first tile: ex2(-inf) = 0
+                lsum *= corr;
+                if (i > 0) {
+                    mbar_wait(o_step, (uint32_t)(i - 1) & 1u);        // PV(i-1) has landed in TMEM
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    uint32_t ov[NO];
+                    tmem_ldN_issue<NO>(tmem_o + lane_addr + hf * NO, ov);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int d = 0; d < NO; ++d) ov[d] = __float_as_uint(__uint_as_float(ov[d]) * corr);
+                    tmem_stN<NO>(tmem_o + lane_addr + hf * NO, ov);
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                }
+                mref = mnew;
+            }
+            if (i >= 2) mbar_wait(&p_free[i & 1], (uint32_t)((i - 2) >> 1) & 1u);   // PV(i-2) is done with this P buffer
+            const uint32_t pbase = smem_u32(sP) + (uint32_t)((i & 1) * P_BYTES + hf * (AT_BQ * 128));
+            float ps4[4] = {0.f, 0.f, 0.f, 0.f};           // four independent summation chains
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {              // 8 columns -> one 16-byte swizzled store
+                    float p[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const int j = w * 8 + k;
+                        p[k] = ex2(fmaf(__uint_as_float(sv[c][j]), g.scale_log2, -mref));
+                        if (!full_tile && c * 32 + j >= kv_left) p[k] = 0.f;
+                        ps4[k & 3] += p[k];
+                    }
+                    sts_u4_(pbase + sw128_off(r, c * 4 + w), pack_bf16(p[0], p[1]), pack_bf16(p[2], p[3]), pack_bf16(p[4], p[5]),
+                            pack_bf16(p[6], p[7]));
+                }
+            }
+            lsum += (ps4[0] + ps4[1]) + (ps4[2] + ps4[3]);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes of P -> async proxy (MMA)
             __syncwarp();
             if (lane == 0) mbar_arrive(p_full);
-            mbar_wait(o_full, (uint32_t)i & 1u);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll
-            for (int c = 0; c < HD / 16; ++c) {
-                uint32_t v[16];
-                tmem_ld16(tmem_pv + lane_addr + c * 16, v);
-#pragma unroll
-                for (int j = 0; j < 16; ++j) o[c * 16 + j] = o[c * 16 + j] * corr + __uint_as_float(v[j]);
-            }
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         }
+        // epilogue: row sum over both halves, O / l, lse
+        mbar_wait(o_step, (uint32_t)(n_tiles - 1) & 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t xa = xs + (uint32_t)((2 + hf) * 128 + r) * 4u, xb = xs + (uint32_t)((2 + (hf ^ 1)) * 128 + r) * 4u;
+        // parity slot 1 of the exchange buffer may still be read by the partner for the last tile's maximum when the number
+        // of tiles is even; one more named barrier orders that read before this write
+        asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+        sts_f32_(xa, lsum);
+        asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+        const float ltot = lsum + lds_f32(xb);
+        uint32_t ov[NO];
+        tmem_ldN_issue<NO>(tmem_o + lane_addr + hf * NO, ov);
+        tmem_wait_ld();
         const int t = t0 + r;
         if (t < g.T) {
-            const float inv = 1.f / lrun;
-            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(g.o) + ((int64_t)(row_base + t) * g.H + h) * HD;
+            const float inv = 1.f / ltot;
+            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(g.o) + ((int64_t)(row_base + t) * g.H + h) * HD + hf * NO;
 #pragma unroll
-            for (int d = 0; d < HD; d += 8)
-                *reinterpret_cast<uint4*>(op + d) = make_uint4(pack_bf16(o[d] * inv, o[d + 1] * inv), pack_bf16(o[d + 2] * inv, o[d + 3] * inv),
-                                                               pack_bf16(o[d + 4] * inv, o[d + 5] * inv), pack_bf16(o[d + 6] * inv, o[d + 7] * inv));
-            g.lse[((int64_t)b * g.H + h) * g.T + t] = (mrun + log2f(lrun)) * 0.69314718055994531f;
+            for (int d = 0; d < NO; d += 8)
+                *reinterpret_cast<uint4*>(op + d) = make_uint4(
+                    pack_bf16(__uint_as_float(ov[d]) * inv, __uint_as_float(ov[d + 1]) * inv), pack_bf16(__uint_as_float(ov[d + 2]) * inv, __uint_as_float(ov[d + 3]) * inv),
+                    pack_bf16(__uint_as_float(ov[d + 4]) * inv, __uint_as_float(ov[d + 5]) * inv), pack_bf16(__uint_as_float(ov[d + 6]) * inv, __uint_as_float(ov[d + 7]) * inv));
+            if (hf == 0) g.lse[((int64_t)b * g.H + h) * g.T + t] = (mref + log2f(ltot)) * 0.69314718055994531f;
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -804,7 +878,7 @@ int make_head_map(CUtensorMap* map, const void* base, int64_t rows, int64_t ld, 
 
 template <int HD>
 int launch_fwd(const CUtensorMap& tm, const AttnArgs& g, int64_t B, cudaStream_t st) {
-    constexpr int SMEM = 5 * 128 * HD * 2 + AT_BQ * AT_BKV * 2 + 1024 + 256;
+    constexpr int SMEM = 5 * 128 * HD * 2 + 2 * AT_BQ * AT_BKV * 2 + 2048 + 1024 + 256;
     static bool done = false;
     if (!done) {
         GAOT_CHECK(cudaFuncSetAttribute(attn_fwd_tc_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
