@@ -177,6 +177,12 @@ __device__ __forceinline__ uint32_t sw128_off(int r, int chunk) {
     return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((chunk ^ (r & 7)) << 4));
 }
 
+#ifdef EXP_TRACE_FWD
+__device__ long long g_trace_f[4 * 128];
+#define FTRACE(slot) do { if (ftrace_on && (slot) < 128) g_trace_f[ftrace_base + (slot)] = clock64(); } while (0)
+#else
+#define FTRACE(slot) do { } while (0)
+#endif
 struct AttnArgs {
     void* o;            // bf16 [B*T, H*hd]
     float* lse;         // [B,H,T] natural log
@@ -353,8 +359,14 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttnArgs g) {
         const uint32_t xs = smem_u32(sX);
         const uint32_t bar_id = 1 + q;                     // named barrier of the two warps that share this quadrant
         float mref = -INFINITY, lsum = 0.f;                // reference maximum (base-2 units), partial row sum (own columns)
+#ifdef EXP_TRACE_FWD
+        const bool ftrace_on = blockIdx.x == 0 && blockIdx.y == 0 && (blockIdx.z == 0 || blockIdx.z == 20) && lane == 0 && (warp == 2 || warp == 6);
+        const int ftrace_base = (blockIdx.z == 0 ? 0 : 256) + (warp == 6 ? 128 : 0);
+#endif
         for (int i = 0; i < n_tiles; ++i) {
+            FTRACE(i * 8);
             mbar_wait(s_full, (uint32_t)i & 1u);
+            FTRACE(i * 8 + 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             uint32_t sv[2][32];
             tmem_ld32_issue(tmem_s + lane_addr + hf * 64, sv[0]);
@@ -363,6 +375,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttnArgs g) {
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(s_free);            // the MMA warp may overwrite S with tile i+1
+            FTRACE(i * 8 + 2);
             const int kv_left = g.T - i * AT_BKV - hf * 64;   // of this thread's 64 columns, how many keys exist
             const bool full_tile = kv_left >= 64;          // warp-uniform: only the last tile can be ragged
             float mx = -INFINITY;                          // max of the RAW scores (scale > 0)
@@ -383,6 +396,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttnArgs g) {
             sts_f32_(xa, mx);
             asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
             const float mrow = fmaxf(mx, lds_f32(xb)) * g.scale_log2;
+            FTRACE(i * 8 + 3);
             // lazy rescaling: identical decision in both warps of the quadrant (same rows, same maxima)
             if (__any_sync(0xffffffffu, mrow > mref + 8.f)) {
                 const float mnew = fmaxf(mref, mrow);
@@ -401,7 +415,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttnArgs g) {
                 }
                 mref = mnew;
             }
+            FTRACE(i * 8 + 4);
             if (i >= 2) mbar_wait(&p_free[i & 1], (uint32_t)((i - 2) >> 1) & 1u);   // PV(i-2) is done with this P buffer
+            FTRACE(i * 8 + 5);
             const uint32_t pbase = smem_u32(sP) + (uint32_t)((i & 1) * P_BYTES + hf * (AT_BQ * 128));
             float ps4[4] = {0.f, 0.f, 0.f, 0.f};           // four independent summation chains
 #pragma unroll
@@ -421,9 +437,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttnArgs g) {
                 }
             }
             lsum += (ps4[0] + ps4[1]) + (ps4[2] + ps4[3]);
+            FTRACE(i * 8 + 6);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes of P -> async proxy (MMA)
             __syncwarp();
             if (lane == 0) mbar_arrive(p_full);
+            FTRACE(i * 8 + 7);
         }
         // epilogue: row sum over both halves, O / l, lse
         mbar_wait(o_step, (uint32_t)(n_tiles - 1) & 1u);
@@ -955,4 +973,8 @@ GAOT_API int gaot_attention_bwd_bf16(const void* qkv, const void* o, const float
 
 #ifdef EXP_TRACE
 GAOT_API int gaot_debug_trace(long long* out) { return (int)cudaMemcpyFromSymbol(out, g_trace, sizeof(g_trace)); }
+#endif
+
+#ifdef EXP_TRACE_FWD
+GAOT_API int gaot_debug_trace_fwd(long long* out) { return (int)cudaMemcpyFromSymbol(out, g_trace_f, sizeof(g_trace_f)); }
 #endif

@@ -91,6 +91,11 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t sr
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                  ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
 }
+// TMA reduction: global[box] += smem[box] (fp32 add performed by the memory system; split-K / accumulate epilogue)
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void tma_load_2d_s(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  ::"r"(dst), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
@@ -162,7 +167,7 @@ struct TcArgs {
     int out_bf16, splits, accumulate;
     int64_t gm, gn;                   // tile grid
     int act; float* pre;              // optional activation (GAOT_ACT_*) and fp32 pre-activation output
-    int fast;                         // epilogue through swizzled smem boxes and TMA stores (tmC / tmAdd valid)
+    int fast;                         // epilogue through swizzled smem boxes and TMA: 1 = stores, 2 = fp32 reduce-add (split-K / accumulate)
 };
 
 // MN-major operand tile: [64 contraction rows][64 elements = 128 bytes] blocks of 8 KB, one per 64 output
@@ -459,7 +464,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                             __syncwarp();
                             if (lane == 0) {
-                                tma_store_2d(&tmC, box, (int)n, row0);
+                                if (g.fast == 2) tma_reduce_add_2d(&tmC, box, (int)n, row0);
+                                else tma_store_2d(&tmC, box, (int)n, row0);
                                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                             }
                         }
@@ -739,7 +745,7 @@ int launch_tc(const void* A, const void* B, TcArgs& g, cudaStream_t st) {
     const int workers = sm_count() / CG;                        // CTAs (CG = 1) or CTA pairs (CG = 2) resident on the chip
     int splits = 1;
     if (!g.out_bf16 && !g.act && !g.pre && tiles < workers && kblocks >= 8) {   // too few tiles for the chip: split the contraction
-        splits = (int)((2 * workers + tiles - 1) / tiles);
+        splits = (int)(workers / tiles);                            // one round: every worker gets exactly one (tile, split)
         if (splits > kblocks / 4) splits = (int)(kblocks / 4);
         if (splits > 128) splits = 128;
         if (splits < 1) splits = 1;
@@ -753,9 +759,11 @@ int launch_tc(const void* A, const void* B, TcArgs& g, cudaStream_t st) {
     // fast epilogue (TMA stores): plain stores only (no split-K / accumulate / pre-activation copy), 16-byte row pitches,
     // and an `add` operand (fp32 output only) whose broadcast period is a whole number of 32-row boxes
     CUtensorMap tc = ta, tadd = ta;
-    g.fast = splits == 1 && !g.accumulate && !g.pre && g.N % (g.out_bf16 ? 8 : 4) == 0 &&
+    const bool reduce = splits > 1 || g.accumulate;
+    g.fast = !g.pre && g.N % (g.out_bf16 ? 8 : 4) == 0 &&
              (!g.add || (!g.out_bf16 && g.add_rows % 32 == 0 && g.ldadd % 4 == 0 && !(reinterpret_cast<uintptr_t>(g.add) & 15))) &&
              (!g.bias || !(reinterpret_cast<uintptr_t>(g.bias) & 15));
+    if (reduce) g.fast = (g.fast && !g.out_bf16 && !g.bias && !g.add && !g.act) ? 2 : 0;   // TMA reduce-add of fp32 partial tiles
     if (g.fast) {
         rc = make_map_box32(&tc, g.C, g.M, g.N, g.N, g.out_bf16 != 0, (g.out_bf16 && BN >= 128) ? 64 : 32);
         if (rc) return rc;
