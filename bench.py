@@ -327,6 +327,17 @@ def run_ours(args, w):
                 "frac": round(ach / peaks["bf16_tflops"], 5), "traffic": None, "peak_src": peaks["src"],
                 "share_of_step": round(top["s"] / total_s, 3),
                 "note": ("tcgen05 kernel" if "bf16" in top_name else "fp32 FFMA parity-path kernel measured against the bf16 tensor peak")}
+        if top_name.startswith("gaot_attention") and "bf16" in top_name:
+            # at head dim 32 the softmax exponentials, not the MMAs, bound attention: one ex2 per score on the MUFU pipe
+            # (16 / clk / SM on sm_100a) against 4*hd (forward) or 10*hd (backward) tensor FLOPs per score
+            a0 = top["items"][0][1]
+            hd_ = a0[7] if top_name.endswith("fwd_bf16") else a0[11]
+            per = (4.0 if top_name.endswith("fwd_bf16") else 10.0) * hd_
+            ex2s = top["flops"] / per
+            floor_s = ex2s / (16.0 * 148 * 1965e6)
+            roof["mufu_bound"] = {"ex2": ex2s, "floor_ms": round(floor_s * 1e3, 4), "measured_ms": round(top["s"] * 1e3, 4),
+                                  "frac_of_mufu_floor": round(floor_s / top["s"], 4),
+                                  "note": "MUFU.EX2 floor at 16/clk/SM, 148 SMs, 1965 MHz; tensor floor is lower at hd=%d" % hd_}
     else:
         ach = best["gbs"] if best else 0.0
         roof = {"kernel": top_name, "bound": "hbm", "achieved": round(ach, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
