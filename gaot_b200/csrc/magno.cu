@@ -66,6 +66,72 @@ __global__ void cosine_softmax_kernel(const float* __restrict__ y, int dy, const
     for (int64_t i = a; i < e; ++i) alpha[i] *= inv;
 }
 
+// ---- dot-product attention weights (agno.py:214-217): one warp per destination row, A-wide projections ----
+// alpha[e] = softmax_row( scale * <q[row], k[index[e]]> ); lanes own the columns l, l+32, ... of the projections
+__global__ void __launch_bounds__(128) dot_softmax_fwd_kernel(const float* __restrict__ q, const float* __restrict__ k, int A,
+                                                              const int64_t* __restrict__ index, const int64_t* __restrict__ rs,
+                                                              int64_t m, float scale, float* __restrict__ alpha) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= m) return;
+    const int64_t a = rs[row], e = rs[row + 1];
+    if (a == e) return;
+    float smax = -INFINITY;
+    for (int64_t i = a; i < e; ++i) {
+        const float* kp = k + index[i] * A;
+        float dot = 0.f;
+        for (int c = lane; c < A; c += 32) dot = fmaf(__ldg(q + row * A + c), __ldg(kp + c), dot);
+        const float s = warp_sum(dot) * scale;
+        if (lane == 0) alpha[i] = s;
+        smax = fmaxf(smax, s);
+    }
+    __syncwarp();
+    float den = 0.f;
+    for (int64_t i = a + lane; i < e; i += 32) { const float ex = expf(alpha[i] - smax); alpha[i] = ex; den += ex; }
+    den = warp_sum(den);
+    const float inv = 1.f / den;
+    for (int64_t i = a + lane; i < e; i += 32) alpha[i] *= inv;
+}
+
+// backward of the above: ds_e = alpha_e (dalpha_e - sum_row alpha dalpha);  dq[row] = scale sum_e ds_e k[idx_e] (row owned),
+// dk[idx_e] += scale ds_e q[row] (red.add: a source point belongs to several rows)
+__global__ void __launch_bounds__(128) dot_softmax_bwd_kernel(const float* __restrict__ dalpha, const float* __restrict__ alpha,
+                                                              const float* __restrict__ q, const float* __restrict__ k, int A,
+                                                              const int64_t* __restrict__ index, const int64_t* __restrict__ rs,
+                                                              int64_t m, float scale, float* __restrict__ dq, float* __restrict__ dk) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= m) return;
+    const int64_t a = rs[row], e = rs[row + 1];
+    float t = 0.f;
+    for (int64_t i = a + lane; i < e; i += 32) t = fmaf(alpha[i], dalpha[i], t);
+    t = warp_sum(t);
+    for (int c = lane; c < A; c += 32) {
+        const float qv = __ldg(q + row * A + c);
+        float acc = 0.f;
+        for (int64_t i = a; i < e; ++i) {
+            const float ds = alpha[i] * (dalpha[i] - t) * scale;
+            const int64_t j = index[i];
+            acc = fmaf(ds, __ldg(k + j * A + c), acc);
+            atomicAdd(dk + j * A + c, ds * qv);
+        }
+        dq[row * A + c] = acc;
+    }
+}
+
+// out[r] = sum_c a[r,c] * b[r,c]   (gradient of the row scale in scale_rows); one warp per row
+__global__ void __launch_bounds__(256) row_dot_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t rows, int C,
+                                                      float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp; r < rows; r += nw) {
+        float s = 0.f;
+        for (int c = lane; c < C; c += 32) s = fmaf(__ldg(a + r * C + c), __ldg(b + r * C + c), s);
+        s = warp_sum(s);
+        if (lane == 0) out[r] = s;
+    }
+}
+
 __global__ void scale_rows_kernel(const float* __restrict__ in, const float* __restrict__ scale, int64_t rows, int C,
                                   float* __restrict__ out) {
     const int64_t total = rows * C;
@@ -425,6 +491,32 @@ GAOT_API int gaot_edge_cosine_softmax(const float* y, int64_t dy, const float* x
     if (m == 0) return 0;
     cosine_softmax_kernel<<<gaot_blocks(m, 128), 128, 0, (cudaStream_t)stream>>>(y, (int)dy, x, (int)dx, (int)cd, index,
                                                                                  row_splits, m, alpha);
+    GAOT_RETURN_LAST();
+}
+
+GAOT_API int gaot_edge_dot_softmax_fwd(const float* q, const float* k, int64_t A, const int64_t* index, const int64_t* row_splits,
+                                       int64_t m, float scale, float* alpha, void* stream) {
+    if (!q || !k || !index || !row_splits || !alpha || A < 1 || m < 0) return GAOT_E_BADARG;
+    if (m == 0) return 0;
+    dot_softmax_fwd_kernel<<<gaot_blocks(m * 32, 128), 128, 0, (cudaStream_t)stream>>>(q, k, (int)A, index, row_splits, m, scale, alpha);
+    GAOT_RETURN_LAST();
+}
+
+GAOT_API int gaot_edge_dot_softmax_bwd(const float* dalpha, const float* alpha, const float* q, const float* k, int64_t A,
+                                       const int64_t* index, const int64_t* row_splits, int64_t m, int64_t n, float scale,
+                                       float* dq, float* dk, void* stream) {
+    if (!dalpha || !alpha || !q || !k || !index || !row_splits || !dq || !dk || A < 1 || m < 0 || n < 0) return GAOT_E_BADARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n > 0) GAOT_CHECK(cudaMemsetAsync(dk, 0, sizeof(float) * (size_t)(n * A), st));
+    if (m == 0) return 0;
+    dot_softmax_bwd_kernel<<<gaot_blocks(m * 32, 128), 128, 0, st>>>(dalpha, alpha, q, k, (int)A, index, row_splits, m, scale, dq, dk);
+    GAOT_RETURN_LAST();
+}
+
+GAOT_API int gaot_row_dot(const float* a, const float* b, int64_t rows, int64_t C, float* out, void* stream) {
+    if (!a || !b || !out || rows < 0 || C < 1) return GAOT_E_BADARG;
+    if (rows == 0) return 0;
+    row_dot_kernel<<<gaot_grid(rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(a, b, rows, (int)C, out);
     GAOT_RETURN_LAST();
 }
 

@@ -35,15 +35,25 @@ class AGNO(nn.Module):
             self.coord_dim = coord_dim
             if attention_type not in ["cosine", "dot_product"]:
                 raise ValueError(f"Invalid attention_type: {attention_type}")
-            if attention_type == "dot_product":
-                raise NotImplementedError("attention_type='dot_product' is not on the accelerated path yet")
         self.channel_mlp = channel_mlp if channel_mlp is not None else LinearChannelMLP(layers=channel_mlp_layers)
+        if use_attn and attention_type == "dot_product":
+            attention_dim = 64                                   # agno.py:106 (fixed in the reference)
+            self.query_proj = nn.Linear(self.coord_dim, attention_dim)
+            self.key_proj = nn.Linear(self.coord_dim, attention_dim)
+            self.scaling_factor = 1.0 / (attention_dim ** 0.5)
 
     def edge_weights(self, y, x, plan: ops.GraphPlan):
         """w [E, C]: kernel MLP on [y_j, x_m] (agno.py:229-242) times the attention weight (agno.py:218-224, 250)
         or 1/deg when the reduce is `mean` (agno.py:264)."""
         kappa = self.channel_mlp(ops.edge_inputs(y, x, plan))
-        if self.use_attn:
+        if self.use_attn and self.attention_type == "dot_product":
+            # the reference projects the gathered per-edge coordinates (agno.py:214-216); projecting every node once and
+            # gathering inside the softmax kernel gives the same values with m + n instead of 2E rows
+            cd = self.coord_dim
+            q = ops.linear(x[:, :cd].contiguous(), self.query_proj.weight, self.query_proj.bias)
+            k = ops.linear(y[:, :cd].contiguous(), self.key_proj.weight, self.key_proj.bias)
+            alpha = ops.edge_dot_softmax(q, k, plan, self.scaling_factor)
+        elif self.use_attn:
             alpha = ops.edge_cosine_softmax(y, x, self.coord_dim, plan)
         else:
             deg = (plan.splits[1:] - plan.splits[:-1]).clamp(min=1).to(torch.float32)

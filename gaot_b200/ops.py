@@ -502,22 +502,54 @@ def edge_cosine_softmax(y, x, cd, plan: GraphPlan):
     return alpha
 
 
+class _EdgeDotSoftmax(torch.autograd.Function):
+    """alpha[e] = softmax over the row of scale * <q[row(e)], k[index[e]]> (dot-product attention, agno.py:214-217);
+    q [m, A], k [n, A] are the per-node projections, both differentiable."""
+
+    @staticmethod
+    def forward(ctx, q, k, plan, scale):
+        q, k = _c(q), _c(k)
+        alpha = torch.empty(max(plan.E, 1), dtype=torch.float32, device=q.device)[:plan.E]
+        call("gaot_edge_dot_softmax_fwd", ptr(q), ptr(k), q.shape[1], ptr(plan.index), ptr(plan.splits), plan.m, float(scale),
+             ptr(alpha))
+        ctx.save_for_backward(q, k, alpha)
+        ctx.plan, ctx.scale = plan, float(scale)
+        return alpha
+
+    @staticmethod
+    def backward(ctx, dalpha):
+        q, k, alpha = ctx.saved_tensors
+        plan = ctx.plan
+        dq, dk = torch.empty_like(q), torch.empty_like(k)
+        call("gaot_edge_dot_softmax_bwd", ptr(_c(dalpha)), ptr(alpha), ptr(q), ptr(k), q.shape[1], ptr(plan.index), ptr(plan.splits),
+             plan.m, k.shape[0], ctx.scale, ptr(dq), ptr(dk))
+        return dq, dk, None, None
+
+
+def edge_dot_softmax(q, k, plan: GraphPlan, scale: float):
+    return _EdgeDotSoftmax.apply(q, k, plan, scale)
+
+
 class _ScaleRows(torch.autograd.Function):
     @staticmethod
     def forward(ctx, k, alpha):
         k = _c(k)
         out = torch.empty_like(k)
         call("gaot_scale_rows", ptr(k), ptr(alpha), k.shape[0], k.shape[1], ptr(out))
-        ctx.save_for_backward(alpha)
+        ctx.save_for_backward(alpha, k if alpha.requires_grad else None)
         return out
 
     @staticmethod
     def backward(ctx, g):
-        (alpha,) = ctx.saved_tensors
+        alpha, k = ctx.saved_tensors
         g = _c(g)
         out = torch.empty_like(g)
         call("gaot_scale_rows", ptr(g), ptr(alpha), g.shape[0], g.shape[1], ptr(out))
-        return out, None
+        dalpha = None
+        if k is not None and ctx.needs_input_grad[1]:      # learned attention (dot-product): dalpha[e] = <g[e,:], kappa[e,:]>
+            dalpha = torch.empty(max(g.shape[0], 1), dtype=torch.float32, device=g.device)[:g.shape[0]]
+            call("gaot_row_dot", ptr(g), ptr(k), g.shape[0], g.shape[1], ptr(dalpha))
+        return out, dalpha
 
 
 def scale_rows(k, alpha):

@@ -82,6 +82,20 @@ int gaot_edge_cosine_softmax(const float* y, int64_t dy, const float* x, int64_t
                              const int64_t* index, const int64_t* row_splits, int64_t m,
                              float* alpha, void* stream);
 
+/* Dot-product attention weights (agno.py:105-110, 214-217): q [m, A] = query_proj(x[:, :cd]) per destination row,
+ * k [n, A] = key_proj(y[:, :cd]) per source point (the reference projects per edge; same values),
+ * alpha[e] = softmax over the row of scale * <q[row(e)], k[index[e]]>   (_segment_softmax, agno.py:112-146). */
+int gaot_edge_dot_softmax_fwd(const float* q, const float* k, int64_t A, const int64_t* index, const int64_t* row_splits,
+                              int64_t m, float scale, float* alpha, void* stream);
+
+/* Backward of gaot_edge_dot_softmax_fwd: dq [m, A] is written, dk [n, A] is zeroed here and accumulated with red.add. */
+int gaot_edge_dot_softmax_bwd(const float* dalpha, const float* alpha, const float* q, const float* k, int64_t A,
+                              const int64_t* index, const int64_t* row_splits, int64_t m, int64_t n, float scale,
+                              float* dq, float* dk, void* stream);
+
+/* out[r] = sum_c a[r,c] * b[r,c]   (gradient of the row scale of gaot_scale_rows: dalpha[e] = <dW[e,:], kappa[e,:]>) */
+int gaot_row_dot(const float* a, const float* b, int64_t rows, int64_t C, float* out, void* stream);
+
 /* out[e,c] = scale[e] * in[e,c]    (agno.py:250 forward; alpha * dW in the backward) */
 int gaot_scale_rows(const float* in, const float* scale, int64_t rows, int64_t C, float* out, void* stream);
 

@@ -101,6 +101,35 @@ def gaot_edge_cosine_softmax(y, dy, x, dx, cd, index, row_splits, m, alpha):
     _arr(alpha, (E,))[:] = (ex / orc.segment_csr(ex, g["neighbors_row_splits"], "sum")[seg]).float().numpy()
 
 
+def gaot_edge_dot_softmax_fwd(q, k, A, index, row_splits, m, scale, alpha):
+    g, E = _csr(index, row_splits, m)
+    idx = g["neighbors_index"]
+    seg, _ = orc._seg_ids(g["neighbors_row_splits"])
+    n = int(idx.max()) + 1 if E else 0
+    Q, K = _t(q, (m, A)).double(), _t(k, (n, A)).double()
+    s = (Q[seg] * K[idx]).sum(-1) * scale
+    ex = torch.exp(s - orc.segment_csr(s, g["neighbors_row_splits"], "max")[seg])
+    _arr(alpha, (E,))[:] = (ex / orc.segment_csr(ex, g["neighbors_row_splits"], "sum")[seg]).float().numpy()
+
+
+def gaot_edge_dot_softmax_bwd(dalpha, alpha, q, k, A, index, row_splits, m, n, scale, dq, dk):
+    g, E = _csr(index, row_splits, m)
+    idx = g["neighbors_index"]
+    seg, _ = orc._seg_ids(g["neighbors_row_splits"])
+    Q, K = _t(q, (m, A)).double(), _t(k, (n, A)).double()
+    al, da = _t(alpha, (E,)).double(), _t(dalpha, (E,)).double()
+    t = orc.segment_csr(al * da, g["neighbors_row_splits"], "sum")[seg]
+    ds = al * (da - t) * scale
+    DQ = torch.zeros(m, A, dtype=torch.float64).index_add_(0, seg, ds[:, None] * K[idx])
+    DK = torch.zeros(n, A, dtype=torch.float64).index_add_(0, idx, ds[:, None] * Q[seg])
+    _arr(dq, (m, A))[:] = DQ.float().numpy()
+    _arr(dk, (n, A))[:] = DK.float().numpy()
+
+
+def gaot_row_dot(a, b, rows, C, out):
+    _arr(out, (rows,))[:] = (_arr(a, (rows, C)).astype(np.float64) * _arr(b, (rows, C))).sum(-1).astype(np.float32)
+
+
 def gaot_scale_rows(inp, scale, rows, C, out):
     _arr(out, (rows, C))[:] = _arr(inp, (rows, C)) * _arr(scale, (rows,))[:, None]
 

@@ -40,6 +40,18 @@ def rel_l2(a, b):
     return float((a - b).norm() / b.norm().clamp_min(1e-30))
 
 
+def grad_scale(g, keys):
+    """Largest reference gradient norm of a fixture: structurally zero gradients (e.g. the key bias of dot-product
+    attention, to which a row softmax is invariant) are pure rounding noise and are compared against this scale."""
+    return max(float(torch.as_tensor(g["grad." + str(k)]).double().norm()) for k in keys if ("grad." + str(k)) in g)
+
+
+def grad_rel(a, b, scale):
+    a = torch.as_tensor(a).detach().double().cpu()
+    b = torch.as_tensor(b).detach().double().cpu()
+    return float((a - b).norm() / max(float(b.norm()), 1e-6 * scale))
+
+
 def graphs_to(graphs, device):
     if isinstance(graphs, dict):
         return {k: v.to(device) for k, v in graphs.items()}

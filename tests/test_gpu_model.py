@@ -9,7 +9,8 @@ import pytest
 import torch
 
 from oracle import cases, gaot_oracle as orc
-from tests.helpers import (build_model, golden_graphs, golden_params, golden_shapes, graphs_to, load_golden, rel_l2)
+from tests.helpers import (build_model, golden_graphs, golden_params, golden_shapes, grad_rel, grad_scale, graphs_to, load_golden,
+                           rel_l2)
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
@@ -43,7 +44,7 @@ def _run(name, use_golden_graphs, fuse=True):
 
 @pytest.mark.parametrize("fuse", [True, False])
 @pytest.mark.parametrize("name,golden_graph", [("tiny2d", False), ("tiny2d", True), ("tiny3d", False),
-                                               ("plain2d", False), ("vx2d", True)])
+                                               ("plain2d", False), ("vx2d", True), ("dot2d", False)])
 def test_forward_backward_matches_reference(name, golden_graph, fuse):
     c, g, model, out, loss, inter = _run(name, golden_graph, fuse)
     assert rel_l2(inter["enc_out"], g["enc_out"]) < FWD_TOL
@@ -51,9 +52,10 @@ def test_forward_backward_matches_reference(name, golden_graph, fuse):
     assert abs(float(loss) - float(g["loss64"])) < 1e-5 * abs(float(g["loss64"]))
     floors = {str(k): float(e) for k, e in zip(g["keys"], g["gerr32"])}
     worst = 0.0
+    gs = grad_scale(g, g["keys"])
     for k, p in model.named_parameters():
         assert p.grad is not None, k
-        err = rel_l2(p.grad, g["grad." + k])
+        err = grad_rel(p.grad, g["grad." + k], gs)
         tol = max(1e-4, 10 * floors[k])
         assert err < tol, (k, err, tol)
         worst = max(worst, err)

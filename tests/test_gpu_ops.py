@@ -270,3 +270,36 @@ def test_fused_lift_aggregate_and_dot_vs_oracle():
         want.backward(go.double())
         got.backward(go.to(DEV))
         assert rel_l2(fg.grad, fr.grad) < 2e-6 and rel_l2(ug.grad, ur.grad) < 5e-6
+
+
+@pytest.mark.parametrize("name", ["rand2d", "dec2d", "lattice2d", "empty"])
+def test_edge_dot_softmax_fwd_bwd_vs_fp64(name):
+    """Dot-product attention weights (agno.py:214-217) and their gradients against an fp64 autograd restatement,
+    incl. empty rows and the row scale's gradient (gaot_row_dot)."""
+    ops = _ops()
+    data, q, r = cases.nbr_case(name)
+    g = orc.radius_csr(data, q, r)
+    idx, rs = g["neighbors_index"], g["neighbors_row_splits"]
+    m, n, E, A, C = q.shape[0], data.shape[0], int(idx.numel()), 64, 16
+    plan = ops.GraphPlan(idx.to(DEV), rs.to(DEV), n)
+    gen = torch.Generator().manual_seed(5)
+    Q, K = torch.randn(m, A, generator=gen), torch.randn(n, A, generator=gen)
+    kap, gout = torch.randn(E, C, generator=gen), torch.randn(E, C, generator=gen)
+    scale = 1.0 / A ** 0.5
+    qd, kd, kp = [t.clone().to(DEV).requires_grad_(True) for t in (Q, K, kap)]
+    w = ops.scale_rows(kp, ops.edge_dot_softmax(qd, kd, plan, scale))
+    w.backward(gout.to(DEV))
+    qr, kr, kpr = [t.clone().double().requires_grad_(True) for t in (Q, K, kap)]
+    seg = torch.repeat_interleave(torch.arange(m), rs[1:] - rs[:-1])
+    s = (qr[seg] * kr[idx]).sum(-1) * scale
+    ex = torch.exp(s - orc.segment_csr(s, rs, "max")[seg])
+    alpha = ex / orc.segment_csr(ex, rs, "sum")[seg]
+    wr = kpr * alpha[:, None]
+    wr.backward(gout.double())
+    if E == 0:
+        assert w.numel() == 0
+        return
+    assert rel_l2(w, wr) < 2e-6
+    assert rel_l2(kp.grad, kpr.grad) < 2e-6
+    assert rel_l2(qd.grad, qr.grad) < 2e-5
+    assert rel_l2(kd.grad, kr.grad) < 2e-5

@@ -9,7 +9,7 @@ import torch
 
 from oracle import cases, gaot_oracle as orc
 from tests import abi_emulator
-from tests.helpers import (build_model, golden_graphs, golden_params, graphs_to, load_golden, rel_l2)
+from tests.helpers import (build_model, golden_graphs, golden_params, grad_rel, grad_scale, graphs_to, load_golden, rel_l2)
 
 
 def test_library_exports_every_declared_symbol():
@@ -40,7 +40,7 @@ def test_nothing_in_the_product_imports_the_oracle():
 
 
 @pytest.mark.parametrize("fuse", [True, False])
-@pytest.mark.parametrize("name", ["tiny2d", "tiny3d", "plain2d", "vx2d"])
+@pytest.mark.parametrize("name", ["tiny2d", "tiny3d", "plain2d", "vx2d", "dot2d"])
 def test_model_wiring_matches_reference_golden(name, fuse):
     c = cases.CASES[name]
     g = load_golden(name)
@@ -65,8 +65,9 @@ def test_model_wiring_matches_reference_golden(name, fuse):
             assert "gaot_agno_dot_bwd" in calls
     assert rel_l2(out, g["out"]) < 1e-5
     assert abs(float(loss) - float(g["loss64"])) < 1e-5 * abs(float(g["loss64"]))
+    gs = grad_scale(g, g["keys"])
     for k, p in model.named_parameters():
-        assert rel_l2(p.grad, g["grad." + k]) < 1e-4, k
+        assert grad_rel(p.grad, g["grad." + k], gs) < 1e-4, k
     if not c.get("vx"):   # graphs the model built itself == the reference's
         for tag, mod in (("enc", model.encoder), ("dec", model.decoder)):
             mine = mod.neighbor_cache["graph"][1]

@@ -5,9 +5,9 @@ import pytest
 import torch
 
 from oracle import cases, gaot_oracle as orc
-from tests.helpers import golden_graphs, golden_params, golden_shapes, load_golden, rel_l2
+from tests.helpers import golden_graphs, golden_params, golden_shapes, grad_rel, grad_scale, load_golden, rel_l2
 
-FULL = ["tiny2d", "tiny3d", "vx2d", "plain2d"]
+FULL = ["tiny2d", "tiny3d", "vx2d", "plain2d", "dot2d"]
 
 
 def _cfg(name):
@@ -50,8 +50,9 @@ def test_forward_backward_matches_reference_fp64(name):
     loss = torch.nn.functional.mse_loss(out, tgt)
     assert abs(float(loss.detach()) - float(g["loss64"])) < 1e-12 * max(1.0, abs(float(g["loss64"])))
     loss.backward()
+    gs = grad_scale(g, g["keys"])
     for k in p:
-        assert rel_l2(p[k].grad, g["grad." + k]) < 2e-7, k
+        assert grad_rel(p[k].grad, g["grad." + k], gs) < 2e-7, k
 
 
 @pytest.mark.parametrize("name", ["tiny2d", "tiny3d", "plain2d"])
