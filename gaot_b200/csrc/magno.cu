@@ -496,7 +496,8 @@ GAOT_API int gaot_edge_cosine_softmax(const float* y, int64_t dy, const float* x
 
 GAOT_API int gaot_edge_dot_softmax_fwd(const float* q, const float* k, int64_t A, const int64_t* index, const int64_t* row_splits,
                                        int64_t m, float scale, float* alpha, void* stream) {
-    if (!q || !k || !index || !row_splits || !alpha || A < 1 || m < 0) return GAOT_E_BADARG;
+    // `index` / `alpha` may be null when the graph has no edge at all (every row empty): nothing is dereferenced then
+    if (!q || !k || !row_splits || A < 1 || m < 0) return GAOT_E_BADARG;
     if (m == 0) return 0;
     dot_softmax_fwd_kernel<<<gaot_blocks(m * 32, 128), 128, 0, (cudaStream_t)stream>>>(q, k, (int)A, index, row_splits, m, scale, alpha);
     GAOT_RETURN_LAST();
@@ -505,7 +506,7 @@ GAOT_API int gaot_edge_dot_softmax_fwd(const float* q, const float* k, int64_t A
 GAOT_API int gaot_edge_dot_softmax_bwd(const float* dalpha, const float* alpha, const float* q, const float* k, int64_t A,
                                        const int64_t* index, const int64_t* row_splits, int64_t m, int64_t n, float scale,
                                        float* dq, float* dk, void* stream) {
-    if (!dalpha || !alpha || !q || !k || !index || !row_splits || !dq || !dk || A < 1 || m < 0 || n < 0) return GAOT_E_BADARG;
+    if (!q || !k || !row_splits || !dq || !dk || A < 1 || m < 0 || n < 0) return GAOT_E_BADARG;
     cudaStream_t st = (cudaStream_t)stream;
     if (n > 0) GAOT_CHECK(cudaMemsetAsync(dk, 0, sizeof(float) * (size_t)(n * A), st));
     if (m == 0) return 0;
