@@ -132,6 +132,40 @@ __global__ void __launch_bounds__(256) row_dot_kernel(const float* __restrict__ 
     }
 }
 
+// z[e,k] = y[index[e], k] - x[edge_row[e], k], k < d   (neighbour coordinates centred on their query, gemb.py:212-213)
+__global__ void edge_diff_kernel(const float* __restrict__ y, int dy, const float* __restrict__ x, int dx, int d,
+                                 const int64_t* __restrict__ index, const int64_t* __restrict__ edge_row, int64_t E,
+                                 float* __restrict__ z) {
+    const int64_t total = E * d;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t e = i / d;
+        const int k = (int)(i % d);
+        z[i] = __ldg(y + index[e] * dy + k) - __ldg(x + edge_row[e] * dx + k);
+    }
+}
+
+// backward of the segment reduction out[r,:] = reduce_{e in row r} src[e,:]: sum -> dout[row], mean -> dout[row] / deg,
+// max -> dout[row] at the FIRST edge of the row that attains the maximum (torch_scatter's argmax), 0 elsewhere
+__global__ void segment_csr_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ src, const float* __restrict__ out,
+                                       const int64_t* __restrict__ rs, const int64_t* __restrict__ edge_row, float* __restrict__ dsrc,
+                                       int64_t E, int C, int reduce) {
+    const int64_t total = E * C;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t e = i / C;
+        const int c = (int)(i % C);
+        const int64_t row = edge_row[e], a = rs[row];
+        float g = dout[row * C + c];
+        if (reduce == 1) g /= (float)(rs[row + 1] - a);
+        else if (reduce == 2) {
+            const float mx = out[row * C + c];
+            bool mine = src[i] == mx;
+            for (int64_t j = a; mine && j < e; ++j) mine = src[j * C + c] != mx;
+            if (!mine) g = 0.f;
+        }
+        dsrc[i] = g;
+    }
+}
+
 __global__ void scale_rows_kernel(const float* __restrict__ in, const float* __restrict__ scale, int64_t rows, int C,
                                   float* __restrict__ out) {
     const int64_t total = rows * C;
@@ -518,6 +552,25 @@ GAOT_API int gaot_row_dot(const float* a, const float* b, int64_t rows, int64_t 
     if (!a || !b || !out || rows < 0 || C < 1) return GAOT_E_BADARG;
     if (rows == 0) return 0;
     row_dot_kernel<<<gaot_grid(rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(a, b, rows, (int)C, out);
+    GAOT_RETURN_LAST();
+}
+
+GAOT_API int gaot_edge_diff(const float* y, int64_t dy, const float* x, int64_t dx, int64_t d, const int64_t* index,
+                            const int64_t* edge_row, int64_t E, float* z, void* stream) {
+    if (!y || !x || d < 1 || d > dy || d > dx || E < 0) return GAOT_E_BADARG;
+    if (E == 0) return 0;
+    if (!index || !edge_row || !z) return GAOT_E_BADARG;
+    edge_diff_kernel<<<gaot_grid(E * d, 256), 256, 0, (cudaStream_t)stream>>>(y, (int)dy, x, (int)dx, (int)d, index, edge_row, E, z);
+    GAOT_RETURN_LAST();
+}
+
+GAOT_API int gaot_segment_csr_bwd(const float* dout, const float* src, const float* out, const int64_t* row_splits,
+                                  const int64_t* edge_row, float* dsrc, int64_t E, int64_t m, int64_t C, int reduce, void* stream) {
+    if (E < 0 || m < 0 || C < 1 || reduce < 0 || reduce > 2) return GAOT_E_BADARG;
+    if (E == 0) return 0;
+    if (!dout || !row_splits || !edge_row || !dsrc || (reduce == 2 && (!src || !out))) return GAOT_E_BADARG;
+    segment_csr_bwd_kernel<<<gaot_grid(E * C, 256), 256, 0, (cudaStream_t)stream>>>(dout, src, out, row_splits, edge_row, dsrc, E, (int)C,
+                                                                                    reduce);
     GAOT_RETURN_LAST();
 }
 

@@ -1,5 +1,7 @@
-"""Geometry embedding (reference src/model/layers/gemb.py).  'statistical' only: per-row neighbour
-statistics (gaot_geo_stats, fp64 inside) -> column standardisation -> MLP (3+2d)->64->C, ReLU, ReLU."""
+"""Geometry embedding (reference src/model/layers/gemb.py).  'statistical': per-row neighbour statistics
+(gaot_geo_stats, fp64 inside) -> column standardisation -> MLP (3+2d)->64->C, ReLU, ReLU.  'pointnet'
+(gemb.py:60-70, 173-228): MLP d->64->64 on the neighbour coordinates centred on their query, max / mean pooling over
+the row, Linear 64->C + ReLU, rows without neighbours stay zero."""
 from __future__ import annotations
 
 import math
@@ -27,7 +29,8 @@ class GeometricEmbedding(nn.Module):
         if self.method == "statistical":
             self.mlp = nn.Sequential(nn.Linear(3 + 2 * input_dim, 64), nn.ReLU(), nn.Linear(64, output_dim), nn.ReLU())
         elif self.method == "pointnet":
-            raise NotImplementedError("embedding_method='pointnet' is not on the accelerated path yet")
+            self.pointnet_mlp = nn.Sequential(nn.Linear(input_dim, 64), nn.ReLU(), nn.Linear(64, 64), nn.ReLU())
+            self.fc = nn.Sequential(nn.Linear(64, output_dim), nn.ReLU())
         else:
             raise ValueError(f"Unknown method: {self.method}")
 
@@ -37,13 +40,24 @@ class GeometricEmbedding(nn.Module):
         if cache and key in plan._geo:
             return plan._geo[key]
         with torch.no_grad():
-            feat = ops.geo_stats(input_geom, latent_queries, plan, groups)
+            if self.method == "pointnet":
+                # centred neighbour coordinates [E, d] and the has-neighbour mask [m, 1]: the parameter-free part
+                deg = plan.splits[1:] - plan.splits[:-1]
+                feat = (ops.edge_diff(input_geom, latent_queries, self.input_dim, plan), (deg > 0).to(torch.float32).unsqueeze(1), plan)
+            else:
+                feat = ops.geo_stats(input_geom, latent_queries, plan, groups)
         if cache:
             plan._geo.clear()
             plan._geo[key] = feat
         return feat
 
     def embed(self, feat):
+        if self.method == "pointnet":
+            z, mask, plan = feat
+            h = ops.linear(z, self.pointnet_mlp[0].weight, self.pointnet_mlp[0].bias, act=ops.ACT_RELU)
+            h = ops.linear(h, self.pointnet_mlp[2].weight, self.pointnet_mlp[2].bias, act=ops.ACT_RELU)
+            pooled = ops.segment_pool(h, plan, self.pooling)                       # [m, 64], empty rows 0
+            return ops.linear(pooled, self.fc[0].weight, self.fc[0].bias, act=ops.ACT_RELU) * mask   # gemb.py:224-226
         h = ops.linear(feat, self.mlp[0].weight, self.mlp[0].bias, act=ops.ACT_RELU)
         return ops.linear(h, self.mlp[2].weight, self.mlp[2].bias, act=ops.ACT_RELU)
 

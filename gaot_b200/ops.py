@@ -494,6 +494,43 @@ def edge_inputs(y, x, plan: GraphPlan):
     return z
 
 
+def edge_diff(y, x, d, plan: GraphPlan):
+    """z[e,:] = y[index[e], :d] - x[row(e), :d] (gemb.py:208-213); coordinates only, no gradient."""
+    y, x = _c(y), _c(x)
+    z = torch.empty((plan.E, d), dtype=torch.float32, device=y.device)
+    call("gaot_edge_diff", ptr(y), y.shape[1], ptr(x), x.shape[1], int(d), ptr(plan.index), ptr(plan.edge_row), plan.E, ptr(z))
+    return z
+
+
+class _SegmentPool(torch.autograd.Function):
+    """out[r,:] = reduce over the edges of row r of src[e,:] ('sum' | 'mean' | 'max', empty rows 0) with its backward;
+    'max' routes the gradient to the first maximiser of each row and column (scatter_max, gemb.py:217)."""
+
+    @staticmethod
+    def forward(ctx, src, plan, reduce):
+        code = {"sum": 0, "mean": 1, "max": 2}[reduce]
+        src = _c(src)
+        E, C = src.shape
+        out = torch.empty((plan.m, C), dtype=torch.float32, device=src.device)
+        call("gaot_segment_csr", ptr(src), ptr(plan.splits), ptr(out), 1, E, plan.m, C, code)
+        ctx.save_for_backward(src, out)
+        ctx.plan, ctx.code = plan, code
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        src, out = ctx.saved_tensors
+        plan = ctx.plan
+        dsrc = torch.empty_like(src)
+        call("gaot_segment_csr_bwd", ptr(_c(g)), ptr(src), ptr(out), ptr(plan.splits), ptr(plan.edge_row), ptr(dsrc), src.shape[0],
+             plan.m, src.shape[1], ctx.code)
+        return dsrc, None, None
+
+
+def segment_pool(src, plan: GraphPlan, reduce: str):
+    return _SegmentPool.apply(src, plan, reduce)
+
+
 def edge_cosine_softmax(y, x, cd, plan: GraphPlan):
     y, x = _c(y), _c(x)
     alpha = torch.empty(max(plan.E, 1), dtype=torch.float32, device=y.device)[:plan.E]

@@ -135,6 +135,16 @@ int gaot_agno_dot_bwd(const float* g, const float* f, const float* u, const int6
                       const int64_t* t_splits, const int64_t* t_rows, const int64_t* t_perm, float* df, float* du,
                       int64_t B, int64_t Ns, int64_t Nd, int64_t E, int64_t C, int64_t Cout, void* stream);
 
+/* z[e,k] = y[index[e],k] - x[edge_row[e],k], k < d: neighbour coordinates centred on their query point
+ * (pointnet geometry embedding, gemb.py:208-213) */
+int gaot_edge_diff(const float* y, int64_t dy, const float* x, int64_t dx, int64_t d, const int64_t* index,
+                   const int64_t* edge_row, int64_t E, float* z, void* stream);
+
+/* backward of gaot_segment_csr for one batch (B = 1): dsrc[e,:] from dout[row(e),:]; reduce 2 (max) sends the gradient to the
+ * first edge of the row that attains the maximum (scatter_max's argmax, gemb.py:217) and needs src and out. */
+int gaot_segment_csr_bwd(const float* dout, const float* src, const float* out, const int64_t* row_splits,
+                         const int64_t* edge_row, float* dsrc, int64_t E, int64_t m, int64_t C, int reduce, void* stream);
+
 /* generic segment reduction of src[B,E,C] over CSR rows, reduce 0=sum 1=mean 2=max (empty -> 0);
  * the drop-in for segment_csr(src, indptr, reduce) (segment_csr.py:14-19). */
 int gaot_segment_csr(const float* src, const int64_t* row_splits, float* out,

@@ -70,6 +70,12 @@ CASES = {
                              node_embedding=True, neighbor_search_method="native"),
                   transformer=dict(patch_size=2, hidden_size=64, num_layers=1, ffn_multiplier=2),
                   attn=dict(num_heads=2, num_kv_heads=2)),
+    # pointnet geometry embedding with max pooling (gemb.py:60-70, 173-228)
+    "pnet2d": dict(latent=(8, 8), n=300, d=2, B=2, cin=1, cout=1, seed=7,
+                   magno=dict(coord_dim=2, radius=0.3, hidden_size=16, mlp_layers=2, lifting_channels=16,
+                              embedding_method="pointnet", pooling="max", neighbor_search_method="native"),
+                   transformer=dict(patch_size=2, hidden_size=64, num_layers=1, ffn_multiplier=2),
+                   attn=dict(num_heads=2, num_kv_heads=2)),
     # BASELINE cfg-2 geometry (Poisson-Gauss hyper-parameters, config/examples/time_indep/poisson_gauss.json)
     "cfg2": dict(latent=(64, 64), n=9216, d=2, B=2, cin=1, cout=1, seed=0, summary_only=True,
                  magno=dict(coord_dim=2, radius=0.033, hidden_size=64, mlp_layers=3, lifting_channels=64,

@@ -208,8 +208,24 @@ def geo_stat_features(input_geom, queries, nbrs):
     return (feat - mean) / std
 
 
-def geo_embed(p, prefix, input_geom, queries, nbrs):
+def geo_embed_pointnet(p, prefix, input_geom, queries, nbrs, pooling="max"):
+    """GeometricEmbedding 'pointnet' (gemb.py:60-70, 173-228): MLP d->64->64 (ReLU, ReLU) on the neighbour coordinates
+    centred on their query, scatter_max / scatter_mean over each row (empty rows 0), Linear 64->C + ReLU on the rows that
+    have neighbours; the others stay zero."""
+    idx, splits = nbrs["neighbors_index"], nbrs["neighbors_row_splits"]
+    seg, deg = _seg_ids(splits)
+    z = input_geom[idx] - queries[seg]
+    h = F.relu(F.linear(z, p[f"{prefix}.pointnet_mlp.0.weight"], p[f"{prefix}.pointnet_mlp.0.bias"]))
+    h = F.relu(F.linear(h, p[f"{prefix}.pointnet_mlp.2.weight"], p[f"{prefix}.pointnet_mlp.2.bias"]))
+    pooled = segment_csr(h, splits, "max" if pooling == "max" else "mean")
+    f = F.relu(F.linear(pooled, p[f"{prefix}.fc.0.weight"], p[f"{prefix}.fc.0.bias"]))
+    return f * (deg > 0).to(f.dtype).unsqueeze(1)
+
+
+def geo_embed(p, prefix, input_geom, queries, nbrs, method="statistical", pooling="max"):
     """GeometricEmbedding.forward 'statistical' (gemb.py:54-59, 230-233): ReLU(W2 ReLU(W1 f + b1) + b2)."""
+    if method == "pointnet":
+        return geo_embed_pointnet(p, prefix, input_geom, queries, nbrs, pooling)
     f = geo_stat_features(input_geom, queries, nbrs)
     h = F.relu(F.linear(f, p[f"{prefix}.mlp.0.weight"], p[f"{prefix}.mlp.0.bias"]))
     return F.relu(F.linear(h, p[f"{prefix}.mlp.2.weight"], p[f"{prefix}.mlp.2.bias"]))
@@ -244,7 +260,7 @@ def _magno_one(p, prefix, mc, src_coord, dst_coord, feats, nbrs):
         ys, xs = src_coord, dst_coord
     out = agno(p, f"{prefix}.agno", ys, nbrs, xs, feats, mc.use_attention, mc.attention_type, ys.shape[1])
     if mc.use_geoembed:
-        g = geo_embed(p, f"{prefix}.geoembed", src_coord, dst_coord, nbrs)
+        g = geo_embed(p, f"{prefix}.geoembed", src_coord, dst_coord, nbrs, mc.embedding_method, mc.pooling)
         out = torch.cat([out, g.unsqueeze(0).expand(out.shape[0], -1, -1)], dim=-1)
         out = channel_affine(p, f"{prefix}.recovery", out)
     return out

@@ -90,6 +90,31 @@ def gaot_edge_inputs(y, dy, x, dx, index, edge_row, E, z):
     _arr(z, (E, dy + dx))[:] = np.concatenate([_arr(y, (n_y, dy))[idx], _arr(x, (n_x, dx))[row]], axis=1)
 
 
+def gaot_edge_diff(y, dy, x, dx, d, index, edge_row, E, z):
+    idx, row = _arr(index, (E,), np.int64), _arr(edge_row, (E,), np.int64)
+    n_y, n_x = (int(idx.max()) + 1 if E else 0), (int(row.max()) + 1 if E else 0)
+    _arr(z, (E, d))[:] = _arr(y, (n_y, dy))[idx][:, :d] - _arr(x, (n_x, dx))[row][:, :d]
+
+
+def gaot_segment_csr_bwd(dout, src, out, row_splits, edge_row, dsrc, E, m, C, reduce):
+    rs, row = _arr(row_splits, (m + 1,), np.int64), _arr(edge_row, (E,), np.int64)
+    g = _arr(dout, (m, C))[row].astype(np.float64)
+    if reduce == 1:
+        g = g / (rs[1:] - rs[:-1])[row][:, None]
+    elif reduce == 2:
+        S, O = _arr(src, (E, C)), _arr(out, (m, C))
+        hit = S == O[row]
+        first = np.zeros_like(hit)
+        for r in range(m):                                   # first maximiser per row and column
+            a, e = int(rs[r]), int(rs[r + 1])
+            if e > a:
+                h = hit[a:e]
+                pos = h.argmax(axis=0)
+                first[a + pos, np.arange(C)] = h[pos, np.arange(C)]
+        g = g * first
+    _arr(dsrc, (E, C))[:] = g.astype(np.float32)
+
+
 def gaot_edge_cosine_softmax(y, dy, x, dx, cd, index, row_splits, m, alpha):
     g, E = _csr(index, row_splits, m)
     idx = g["neighbors_index"]
