@@ -547,8 +547,9 @@ class _EdgeDotSoftmax(torch.autograd.Function):
     def forward(ctx, q, k, plan, scale):
         q, k = _c(q), _c(k)
         alpha = torch.empty(max(plan.E, 1), dtype=torch.float32, device=q.device)[:plan.E]
-        call("gaot_edge_dot_softmax_fwd", ptr(q), ptr(k), q.shape[1], ptr(plan.index), ptr(plan.splits), plan.m, float(scale),
-             ptr(alpha))
+        if plan.E > 0:                                     # a graph without any edge has no weights to compute
+            call("gaot_edge_dot_softmax_fwd", ptr(q), ptr(k), q.shape[1], ptr(plan.index), ptr(plan.splits), plan.m, float(scale),
+                 ptr(alpha))
         ctx.save_for_backward(q, k, alpha)
         ctx.plan, ctx.scale = plan, float(scale)
         return alpha
@@ -557,6 +558,8 @@ class _EdgeDotSoftmax(torch.autograd.Function):
     def backward(ctx, dalpha):
         q, k, alpha = ctx.saved_tensors
         plan = ctx.plan
+        if plan.E == 0:
+            return torch.zeros_like(q), torch.zeros_like(k), None, None
         dq, dk = torch.empty_like(q), torch.empty_like(k)
         call("gaot_edge_dot_softmax_bwd", ptr(_c(dalpha)), ptr(alpha), ptr(q), ptr(k), q.shape[1], ptr(plan.index), ptr(plan.splits),
              plan.m, k.shape[0], ctx.scale, ptr(dq), ptr(dk))
