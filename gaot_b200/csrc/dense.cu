@@ -921,3 +921,61 @@ GAOT_API int gaot_rollout_update(const float* pred, const float* u_in, float* u_
                                                                                u_mean, u_std, s_mean, s_std);
     GAOT_RETURN_LAST();
 }
+
+namespace {
+
+// ---- time-conditioned affine correction (ConditionedNorm.forward, mlp.py:121-124): y[b,t,:] = x[b,t,:] * s[b,:] + o[b,:] ----
+__global__ void cond_affine_fwd_kernel(const float* __restrict__ x, const float* __restrict__ s, const float* __restrict__ o,
+                                       float* __restrict__ y, int64_t B, int64_t T, int D) {
+    const int64_t total = B * T * D;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = i / (T * D);
+        const int d = (int)(i % D);
+        y[i] = fmaf(x[i], __ldg(s + b * D + d), __ldg(o + b * D + d));
+    }
+}
+// backward: dx = dy * s; ds[b,d] = sum_t dy x; do[b,d] = sum_t dy.  Block (32 columns x 8 row lanes) owns (sample, 32 columns)
+__global__ void __launch_bounds__(256) cond_affine_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                              const float* __restrict__ s, float* __restrict__ dx, float* __restrict__ ds,
+                                                              float* __restrict__ dof, int64_t T, int D) {
+    __shared__ float rs[8][33], ro[8][33];
+    const int d = blockIdx.x * 32 + threadIdx.x;
+    const int64_t b = blockIdx.y;
+    float as = 0.f, ao = 0.f;
+    if (d < D) {
+        const float sv = __ldg(s + b * D + d);
+        for (int64_t t = threadIdx.y; t < T; t += 8) {
+            const int64_t i = (b * T + t) * D + d;
+            const float g = dy[i];
+            dx[i] = g * sv;
+            as = fmaf(g, x[i], as);
+            ao += g;
+        }
+    }
+    rs[threadIdx.y][threadIdx.x] = as; ro[threadIdx.y][threadIdx.x] = ao;
+    __syncthreads();
+    if (threadIdx.y == 0 && d < D) {
+        float a = 0.f, c = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { a += rs[k][threadIdx.x]; c += ro[k][threadIdx.x]; }
+        ds[b * D + d] = a; dof[b * D + d] = c;
+    }
+}
+}  // namespace
+
+GAOT_API int gaot_cond_affine_fwd(const float* x, const float* scale, const float* bias, float* y, int64_t B, int64_t T, int64_t D,
+                                  void* stream) {
+    if (!x || !scale || !bias || !y || B < 0 || T < 0 || D < 1) return GAOT_E_BADARG;
+    if (B * T == 0) return 0;
+    cond_affine_fwd_kernel<<<gaot_grid(B * T * D, 256), 256, 0, (cudaStream_t)stream>>>(x, scale, bias, y, B, T, (int)D);
+    GAOT_RETURN_LAST();
+}
+
+GAOT_API int gaot_cond_affine_bwd(const float* dy, const float* x, const float* scale, float* dx, float* dscale, float* dbias,
+                                  int64_t B, int64_t T, int64_t D, void* stream) {
+    if (!dy || !x || !scale || !dx || !dscale || !dbias || B < 0 || T < 0 || D < 1 || B > 65535) return GAOT_E_BADARG;
+    if (B == 0) return 0;
+    dim3 grid((unsigned)((D + 31) / 32), (unsigned)B), block(32, 8);
+    cond_affine_bwd_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(dy, x, scale, dx, dscale, dbias, T, (int)D);
+    GAOT_RETURN_LAST();
+}

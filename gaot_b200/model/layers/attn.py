@@ -14,6 +14,7 @@ import torch
 from torch import nn
 
 from ... import ops
+from .mlp import ConditionedNorm
 
 
 @dataclass
@@ -61,8 +62,6 @@ class GroupQueryFlashAttention(nn.Module):
         super().__init__()
         assert hidden_size % num_heads == 0, f"hidden_size {hidden_size} must be divisible by num_heads {num_heads}"
         assert num_heads % num_kv_heads == 0, f"num_heads {num_heads} must be divisible by num_kv_heads {num_kv_heads}"
-        if use_conditional_norm:
-            raise NotImplementedError("time-conditioned norm is not on the accelerated path yet")
         if positional_embedding == "rope":
             raise NotImplementedError("positional_embedding='rope' is not on the accelerated path")
         if atten_dropout:
@@ -75,7 +74,7 @@ class GroupQueryFlashAttention(nn.Module):
         self.k_proj = nn.Linear(input_size, kv, bias=False)
         self.v_proj = nn.Linear(input_size, kv, bias=False)
         self.o_proj = nn.Linear(hidden_size, input_size, bias=False)
-        self.correction = None
+        self.correction = ConditionedNorm(1, input_size, cond_norm_hidden_size) if use_conditional_norm else None
 
     @classmethod
     def from_config(cls, input_size, hidden_size, config: AttentionConfig, positional_embedding="absolute"):
@@ -86,6 +85,8 @@ class GroupQueryFlashAttention(nn.Module):
     def forward(self, x, condition=None, relative_positions=None, residual=None):
         """x [B,T,D] -> o_proj(SDPA(...)) (+ residual, fused into the o_proj GEMM)."""
         B, T, D = x.shape
+        if self.correction is not None:
+            x = self.correction(condition, x)              # attn.py:89-90 (fp32; the GEMM below casts its operand)
         wqkv = torch.cat([self.q_proj.weight, self.k_proj.weight, self.v_proj.weight], dim=0)
         tc_attn = ops.get_precision() == "bf16" and self.head_dim in (16, 32, 64) and D % 8 == 0
         qkv = ops.linear(x.reshape(B * T, D), wqkv, tc=True, out_bf16=tc_attn)
@@ -97,18 +98,21 @@ class GroupQueryFlashAttention(nn.Module):
 class FFN(nn.Module):
     def __init__(self, input_size: int, ffn_hidden_size: int, use_conditional_norm: bool = False, cond_norm_hidden_size: int = 4):
         super().__init__()
-        if use_conditional_norm:
-            raise NotImplementedError("time-conditioned norm is not on the accelerated path yet")
         self.w1 = nn.Linear(input_size, ffn_hidden_size, bias=False)
         self.w2 = nn.Linear(ffn_hidden_size, input_size, bias=False)
         self.w3 = nn.Linear(input_size, ffn_hidden_size, bias=False)
-        self.correction = None
+        self.correction = ConditionedNorm(1, input_size, cond_norm_hidden_size) if use_conditional_norm else None
 
     def forward(self, x, condition=None, residual=None):
         shape = x.shape
         x2 = x.reshape(-1, shape[-1])
         tc16 = ops.get_precision() == "bf16" and shape[-1] % 8 == 0 and self.w1.weight.shape[0] % 8 == 0
         ab = ops.linear(x2, torch.cat([self.w1.weight, self.w3.weight], dim=0), tc=True, out_bf16=tc16)
+        if self.correction is not None:
+            # attn.py:151-154: the correction acts on the FFN output, so the residual cannot ride in the w2 epilogue
+            y = ops.linear(ops.swiglu(ab), self.w2.weight, None, tc=True).view(shape)
+            y = self.correction(condition, y)
+            return y + residual if residual is not None else y
         add = residual.reshape(-1, shape[-1]) if residual is not None else None
         return ops.linear(ops.swiglu(ab), self.w2.weight, None, add=add, tc=True).view(residual.shape if residual is not None else shape)
 
@@ -135,7 +139,7 @@ class TransformerBlock(nn.Module):
             W = self.skip_proj.weight                                    # [D, 2D] acting on cat[x, skip] (attn.py:225-227)
             t = ops.linear(skip.reshape(B * T, D), W[:, D:], None, tc=True)
             x = ops.linear(x.reshape(B * T, D), W[:, :D], self.skip_proj.bias, add=t, tc=True).view(B, T, D)
-        bf = ops.get_precision() == "bf16" and x.shape[-1] % 8 == 0
+        bf = ops.get_precision() == "bf16" and x.shape[-1] % 8 == 0 and self.attn.correction is None   # the correction wants fp32
         # bf16 mode: the norms emit the bf16 GEMM operands directly (no separate cast pass)
         h = self.attn_norm(x, "bf16" if bf else "fp32") if self.attn_norm is not None else x
         h = self.attn(h, condition=condition, relative_positions=relative_positions, residual=x)

@@ -59,3 +59,36 @@ class ChannelMLP(nn.Module):
             x = ops.linear(x, fc.weight[:, :, 0], fc.bias, add=add if last else None,
                            act=ops.ACT_NONE if last else ops.ACT_GELU)
         return x.view(*shape[:-1], x.shape[-1])
+
+
+class MLP(nn.Module):
+    """Parameter container of reference mlp.py:43-72 as ConditionedNorm uses it (num_layers <= 2: one Linear, no activation)."""
+
+    def __init__(self, input_size: int, output_size: int, hidden_size: int, num_layers: int = 3, activation: str = "swish"):
+        super().__init__()
+        if num_layers > 2:
+            raise NotImplementedError("only the single-layer MLP of ConditionedNorm is on the accelerated path")
+        self.layers = nn.ModuleList([nn.Linear(input_size, output_size)])
+
+    def forward(self, x):
+        return ops.linear(x, self.layers[-1].weight, self.layers[-1].bias)
+
+
+class ConditionedNorm(nn.Module):
+    """Time-conditioned affine correction (mlp.py:74-124): x * (1 + c * mlp_scale(c)) + c * mlp_bias(c), c [B,1]."""
+
+    def __init__(self, input_size: int, output_size: int, hidden_size: int):
+        super().__init__()
+        self.mlp_scale = MLP(input_size, output_size, hidden_size, num_layers=2, activation="none")
+        self.mlp_bias = MLP(input_size, output_size, hidden_size, num_layers=2, activation="none")
+        for m in (self.mlp_scale, self.mlp_bias):
+            for layer in m.layers:
+                nn.init.normal_(layer.weight, std=0.01)
+
+    def forward(self, c, x):
+        if c is None:
+            raise ValueError("use_conditional_norm=True needs a `condition` tensor [B, 1]")
+        c = torch.as_tensor(c, dtype=torch.float32, device=x.device).reshape(x.shape[0], -1)
+        scale = 1.0 + c * self.mlp_scale(c)            # [B, D]   (tiny: B x D)
+        bias = c * self.mlp_bias(c)
+        return ops.cond_affine(x, scale, bias)

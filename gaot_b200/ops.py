@@ -305,6 +305,35 @@ def linear(x, W, bias=None, add=None, act=ACT_NONE, tc=False, out_bf16=False):
     return _Linear.apply(x, W, bias, add, act)
 
 
+class _CondAffine(torch.autograd.Function):
+    """y[b,t,:] = x[b,t,:] * scale[b,:] + bias[b,:]  (ConditionedNorm.forward, mlp.py:121-124)."""
+
+    @staticmethod
+    def forward(ctx, x, scale, bias):
+        _need_cuda(x)
+        x, scale, bias = _c(x.float()), _c(scale), _c(bias)
+        B, T, D = x.shape
+        if scale.shape != (B, D) or bias.shape != (B, D):
+            raise ValueError(f"scale/bias must be [{B},{D}], got {tuple(scale.shape)} / {tuple(bias.shape)}")
+        y = torch.empty_like(x)
+        call("gaot_cond_affine_fwd", ptr(x), ptr(scale), ptr(bias), ptr(y), B, T, D)
+        ctx.save_for_backward(x, scale)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, scale = ctx.saved_tensors
+        B, T, D = x.shape
+        dy = _c(dy.float())
+        dx, ds, db = torch.empty_like(x), torch.empty_like(scale), torch.empty_like(scale)
+        call("gaot_cond_affine_bwd", ptr(dy), ptr(x), ptr(scale), ptr(dx), ptr(ds), ptr(db), B, T, D)
+        return dx, ds, db
+
+
+def cond_affine(x, scale, bias):
+    return _CondAffine.apply(x, scale, bias)
+
+
 class _RMSNorm(torch.autograd.Function):
     """mode 'fp32' -> y; 'bf16' -> y16 (GEMM input only); 'both' -> (y, y16) (residual + GEMM input)."""
 

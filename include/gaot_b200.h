@@ -266,6 +266,14 @@ int gaot_rollout_update(const float* pred, const float* u_in, float* u_next, int
                         float dt, int mode, const float* u_mean, const float* u_std,
                         const float* s_mean, const float* s_std, void* stream);
 
+/* Time-conditioned affine correction (ConditionedNorm.forward, src/model/layers/mlp.py:121-124; attn.py:89-90, 153-154):
+ * y[b,t,:] = x[b,t,:] * scale[b,:] + bias[b,:] with per-sample scale / bias [B, D]; the backward writes dx and the per-sample
+ * sums dscale[b,:] = sum_t dy * x, dbias[b,:] = sum_t dy. */
+int gaot_cond_affine_fwd(const float* x, const float* scale, const float* bias, float* y, int64_t B, int64_t T, int64_t D,
+                         void* stream);
+int gaot_cond_affine_bwd(const float* dy, const float* x, const float* scale, float* dx, float* dscale, float* dbias,
+                         int64_t B, int64_t T, int64_t D, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

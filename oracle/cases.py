@@ -76,6 +76,12 @@ CASES = {
                               embedding_method="pointnet", pooling="max", neighbor_search_method="native"),
                    transformer=dict(patch_size=2, hidden_size=64, num_layers=1, ffn_multiplier=2),
                    attn=dict(num_heads=2, num_kv_heads=2)),
+    # time-conditioned affine corrections in attention and FFN (attn.py:70-71, 89-90, 145-146, 153-154; mlp.py:74-124)
+    "cond2d": dict(latent=(8, 8), n=300, d=2, B=3, cin=2, cout=1, seed=8, cond=True,
+                   magno=dict(coord_dim=2, radius=0.35, hidden_size=16, mlp_layers=2, lifting_channels=16,
+                              neighbor_search_method="native"),
+                   transformer=dict(patch_size=2, hidden_size=64, num_layers=3, ffn_multiplier=2),
+                   attn=dict(num_heads=2, num_kv_heads=2, use_conditional_norm=True)),
     # BASELINE cfg-2 geometry (Poisson-Gauss hyper-parameters, config/examples/time_indep/poisson_gauss.json)
     "cfg2": dict(latent=(64, 64), n=9216, d=2, B=2, cin=1, cout=1, seed=0, summary_only=True,
                  magno=dict(coord_dim=2, radius=0.033, hidden_size=64, mlp_layers=3, lifting_channels=64,
@@ -95,6 +101,14 @@ def case_inputs(name: str):
     pn = normal((c["B"], c["n"], c["cin"]), 1000 + c["seed"])
     tgt = normal((c["B"], c["n"], c["cout"]), 2000 + c["seed"])
     return lat, x, pn, tgt
+
+
+def case_condition(name: str):
+    """[B, 1] conditioning values (time differences in (0, 1)) for cases with `cond`, else None."""
+    c = CASES[name]
+    if not c.get("cond"):
+        return None
+    return torch.rand(c["B"], 1, generator=torch.Generator().manual_seed(3000 + c["seed"]), dtype=torch.float32)
 
 
 # ---- neighbour-search cases ---------------------------------------------------------------------

@@ -329,8 +329,18 @@ def rmsnorm(x, w, eps):
     return (xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + eps)).type_as(x) * w
 
 
-def attention(p, prefix, x, num_heads, num_kv_heads):
+def conditioned_norm(p, prefix, c, x):
+    """ConditionedNorm.forward (mlp.py:108-124) with its 2-"layer" MLPs (one Linear each, mlp.py:50-53):
+    x * (1 + c * (Ws c + bs)) + c * (Wb c + bb), c [B, 1]."""
+    scale = 1 + c * F.linear(c, p[f"{prefix}.mlp_scale.layers.0.weight"], p[f"{prefix}.mlp_scale.layers.0.bias"])
+    bias = c * F.linear(c, p[f"{prefix}.mlp_bias.layers.0.weight"], p[f"{prefix}.mlp_bias.layers.0.bias"])
+    return x * scale[:, None, :] + bias[:, None, :]
+
+
+def attention(p, prefix, x, num_heads, num_kv_heads, condition=None):
     """GroupQueryFlashAttention.forward (attn.py:78-119), non-causal, dropout 0."""
+    if f"{prefix}.correction.mlp_scale.layers.0.weight" in p:        # attn.py:89-90
+        x = conditioned_norm(p, f"{prefix}.correction", condition, x)
     b, t, _ = x.shape
     q = F.linear(x, p[f"{prefix}.q_proj.weight"])
     k = F.linear(x, p[f"{prefix}.k_proj.weight"])
@@ -347,38 +357,41 @@ def attention(p, prefix, x, num_heads, num_kv_heads):
     return F.linear(o, p[f"{prefix}.o_proj.weight"])
 
 
-def ffn(p, prefix, x):
+def ffn(p, prefix, x, condition=None):
     """FFN.forward SwiGLU (attn.py:150-156)."""
-    return F.linear(F.silu(F.linear(x, p[f"{prefix}.w1.weight"])) * F.linear(x, p[f"{prefix}.w3.weight"]),
-                    p[f"{prefix}.w2.weight"])
+    y = F.linear(F.silu(F.linear(x, p[f"{prefix}.w1.weight"])) * F.linear(x, p[f"{prefix}.w3.weight"]),
+                 p[f"{prefix}.w2.weight"])
+    if f"{prefix}.correction.mlp_scale.layers.0.weight" in p:        # attn.py:153-154
+        y = conditioned_norm(p, f"{prefix}.correction", condition, y)
+    return y
 
 
-def transformer_block(p, prefix, tc, x, skip=None):
+def transformer_block(p, prefix, tc, x, skip=None, condition=None):
     """TransformerBlock.forward (attn.py:225-233) - note the non-standard residual: the second
     residual branch starts from the *normalised* h."""
     ac = tc.attn_config
     if skip is not None and f"{prefix}.skip_proj.weight" in p:
         x = F.linear(torch.cat([x, skip], dim=-1), p[f"{prefix}.skip_proj.weight"], p[f"{prefix}.skip_proj.bias"])
     h = rmsnorm(x, p[f"{prefix}.attn_norm.weight"], tc.norm_eps) if tc.use_attn_norm else x
-    h = x + attention(p, f"{prefix}.attn", h, ac.num_heads, ac.num_kv_heads)
+    h = x + attention(p, f"{prefix}.attn", h, ac.num_heads, ac.num_kv_heads, condition)
     h = rmsnorm(h, p[f"{prefix}.ffn_norm.weight"], tc.norm_eps) if tc.use_ffn_norm else h
-    return h + ffn(p, f"{prefix}.ffn", h)
+    return h + ffn(p, f"{prefix}.ffn", h, condition)
 
 
-def transformer(p, prefix, tc, x):
+def transformer(p, prefix, tc, x, condition=None):
     """Transformer.forward (attn.py:290-317): U-ViT with long skips."""
     if f"{prefix}.input_proj.weight" in p:
         x = F.linear(x, p[f"{prefix}.input_proj.weight"], p[f"{prefix}.input_proj.bias"])
     n_half = tc.num_layers // 2
     skips = []
     for i in range(n_half):
-        x = transformer_block(p, f"{prefix}.encoder_layers.{i}", tc, x)
+        x = transformer_block(p, f"{prefix}.encoder_layers.{i}", tc, x, None, condition)
         skips.append(x)
     if tc.num_layers % 2 == 1:
-        x = transformer_block(p, f"{prefix}.middle_layer", tc, x)
+        x = transformer_block(p, f"{prefix}.middle_layer", tc, x, None, condition)
     for i in range(n_half):
         skip = skips.pop() if tc.use_long_range_skip else None
-        x = transformer_block(p, f"{prefix}.decoder_layers.{i}", tc, x, skip)
+        x = transformer_block(p, f"{prefix}.decoder_layers.{i}", tc, x, skip, condition)
     if f"{prefix}.output_proj.weight" in p:
         x = F.linear(x, p[f"{prefix}.output_proj.weight"], p[f"{prefix}.output_proj.bias"])
     return x
@@ -418,7 +431,7 @@ def unpatchify(x, latent_size, P, c):
     return x.view(b, H * W * D, c)
 
 
-def process(p, cfg, rndata):
+def process(p, cfg, rndata, condition=None):
     """GAOT.process (gaot.py:145-233), positional_embedding='absolute'."""
     tc = cfg.args.transformer
     P = tc.patch_size
@@ -427,23 +440,23 @@ def process(p, cfg, rndata):
     x = patchify(rndata, ls, P)
     x = F.linear(x, p["patch_linear.weight"], p["patch_linear.bias"])
     x = x + absolute_pos_emb([g // P for g in ls], x.shape[-1], x.dtype)
-    x = transformer(p, "processor", tc, x)
+    x = transformer(p, "processor", tc, x, condition)
     return unpatchify(x, ls, P, c)
 
 
-def gaot_forward(p, cfg, latent, xcoord, pndata, query_coord=None, encoder_nbrs=None, decoder_nbrs=None):
+def gaot_forward(p, cfg, latent, xcoord, pndata, query_coord=None, encoder_nbrs=None, decoder_nbrs=None, condition=None):
     """GAOT.forward (gaot.py:248-305)."""
     mc = cfg.args.magno
     rn = magno_encoder(p, mc, xcoord, pndata, latent, encoder_nbrs)
-    rn = process(p, cfg, rn)
+    rn = process(p, cfg, rn, condition)
     if query_coord is None:
         query_coord = xcoord
     return magno_decoder(p, mc, latent, rn, query_coord, decoder_nbrs)
 
 
-def train_step_loss(p, cfg, latent, xcoord, x, y, encoder_nbrs=None, decoder_nbrs=None):
+def train_step_loss(p, cfg, latent, xcoord, x, y, encoder_nbrs=None, decoder_nbrs=None, condition=None):
     """static_trainer.py:160-178 + base_trainer.py:71: MSE(mean) of the forward against y."""
-    return F.mse_loss(gaot_forward(p, cfg, latent, xcoord, x, None, encoder_nbrs, decoder_nbrs), y)
+    return F.mse_loss(gaot_forward(p, cfg, latent, xcoord, x, None, encoder_nbrs, decoder_nbrs, condition), y)
 
 
 def adamw_step(params, grads, m, v, step, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=1e-2):

@@ -62,7 +62,9 @@ def run_reference(name, dtype):
         inter = {}
         hooks = [model.encoder.register_forward_hook(lambda m, i, o: inter.__setitem__("enc_out", o.detach())),
                  model.processor.register_forward_hook(lambda m, i, o: inter.__setitem__("proc_out", o.detach()))]
-        out = model(lat, x, pn, encoder_nbrs=enc_n, decoder_nbrs=dec_n)
+        cond = cases.case_condition(name)
+        cond = cond.to(dtype) if cond is not None else None
+        out = model(lat, x, pn, encoder_nbrs=enc_n, decoder_nbrs=dec_n, condition=cond)
         loss = torch.nn.functional.mse_loss(out, tgt)
         loss.backward()
         for h in hooks:
@@ -97,12 +99,14 @@ def check_oracle(name, ref64):
     enc_n = dec_n = None
     if c.get("vx"):
         enc_n, dec_n = ref64["graphs"]["enc"], ref64["graphs"]["dec"]
-    loss = orc.train_step_loss(p, cfg, lat, x, pn, tgt, enc_n, dec_n)
+    cond = cases.case_condition(name)
+    cond = cond.double() if cond is not None else None
+    loss = orc.train_step_loss(p, cfg, lat, x, pn, tgt, enc_n, dec_n, cond)
     loss.backward()
     e_loss = abs(float(loss.detach()) - float(ref64["loss"])) / abs(float(ref64["loss"]))
     gscale = max(float(v.double().norm()) for v in ref64["grads"].values())
     e_g = max(grel(p[k].grad, ref64["grads"][k], gscale) for k in p)
-    out = orc.gaot_forward({k: v.detach() for k, v in p.items()}, cfg, lat, x, pn, None, enc_n, dec_n)
+    out = orc.gaot_forward({k: v.detach() for k, v in p.items()}, cfg, lat, x, pn, None, enc_n, dec_n, cond)
     e_out = rel(out, ref64["out"])
     print(f"  oracle-vs-reference fp64: out {e_out:.2e} loss {e_loss:.2e} worst grad {e_g:.2e}")
     assert e_out < 1e-10 and e_loss < 1e-10 and e_g < 1e-8, "oracle restatement diverges from the reference"
@@ -110,7 +114,8 @@ def check_oracle(name, ref64):
     p32 = {k: v.detach().clone().float().requires_grad_(True) for k, v in ref64["params"].items()}
     if enc_n is None:
         enc_n, dec_n = ref64["graphs"]["enc"], ref64["graphs"]["dec"]
-    l32 = orc.train_step_loss(p32, cfg, lat.float(), x.float(), pn.float(), tgt.float(), enc_n, dec_n)
+    l32 = orc.train_step_loss(p32, cfg, lat.float(), x.float(), pn.float(), tgt.float(), enc_n, dec_n,
+                              cond.float() if cond is not None else None)
     l32.backward()
     ref64["gerr32"] = {k: grel(p32[k].grad, ref64["grads"][k], gscale) for k in p32}
     print(f"  fp32 noise floor (oracle fp32 vs fp64, same graph): worst grad {max(ref64['gerr32'].values()):.2e}")

@@ -222,6 +222,17 @@ def gaot_agno_dot_bwd(gr, f, u, index, row_splits, ts, tr, tp, df, du, B, Ns, Nd
         _arr(du, (Cout, E, C))[:] = U.grad.float().numpy()
 
 
+def gaot_cond_affine_fwd(x, scale, bias, y, B, T, D):
+    _arr(y, (B, T, D))[:] = _arr(x, (B, T, D)) * _arr(scale, (B, D))[:, None, :] + _arr(bias, (B, D))[:, None, :]
+
+
+def gaot_cond_affine_bwd(dy, x, scale, dx, dscale, dbias, B, T, D):
+    g, xx = _arr(dy, (B, T, D)).astype(np.float64), _arr(x, (B, T, D)).astype(np.float64)
+    _arr(dx, (B, T, D))[:] = (g * _arr(scale, (B, D))[:, None, :]).astype(np.float32)
+    _arr(dscale, (B, D))[:] = (g * xx).sum(1).astype(np.float32)
+    _arr(dbias, (B, D))[:] = g.sum(1).astype(np.float32)
+
+
 def gaot_segment_csr(src, row_splits, out, B, E, m, C, reduce):
     rs = _t(row_splits, (m + 1,), np.int64)
     _arr(out, (B, m, C))[:] = orc.segment_csr(_t(src, (B, E, C)), rs, ("sum", "mean", "max")[reduce]).numpy()

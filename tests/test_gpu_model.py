@@ -33,7 +33,8 @@ def _run(name, use_golden_graphs, fuse=True):
     inter = {}
     hooks = [model.encoder.register_forward_hook(lambda m, i, o: inter.__setitem__("enc_out", o.detach())),
              model.processor.register_forward_hook(lambda m, i, o: inter.__setitem__("proc_out", o.detach()))]
-    out = model(lat, x, pn, encoder_nbrs=enc, decoder_nbrs=dec)
+    cond = cases.case_condition(name)
+    out = model(lat, x, pn, encoder_nbrs=enc, decoder_nbrs=dec, condition=cond.to(DEV) if cond is not None else None)
     for h in hooks:
         h.remove()
     from gaot_b200 import ops
@@ -44,7 +45,8 @@ def _run(name, use_golden_graphs, fuse=True):
 
 @pytest.mark.parametrize("fuse", [True, False])
 @pytest.mark.parametrize("name,golden_graph", [("tiny2d", False), ("tiny2d", True), ("tiny3d", False),
-                                               ("plain2d", False), ("vx2d", True), ("dot2d", False), ("npe2d", False), ("pnet2d", False)])
+                                               ("plain2d", False), ("vx2d", True), ("dot2d", False), ("npe2d", False), ("pnet2d", False),
+                                               ("cond2d", False)])
 def test_forward_backward_matches_reference(name, golden_graph, fuse):
     c, g, model, out, loss, inter = _run(name, golden_graph, fuse)
     assert rel_l2(inter["enc_out"], g["enc_out"]) < FWD_TOL

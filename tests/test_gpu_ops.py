@@ -303,3 +303,20 @@ def test_edge_dot_softmax_fwd_bwd_vs_fp64(name):
     assert rel_l2(kp.grad, kpr.grad) < 2e-6
     assert rel_l2(qd.grad, qr.grad) < 2e-5
     assert rel_l2(kd.grad, kr.grad) < 2e-5
+
+
+@pytest.mark.parametrize("B,T,D", [(3, 16, 64), (2, 257, 40), (32, 1024, 256)])
+def test_cond_affine_fwd_bwd_vs_fp64(B, T, D):
+    """Time-conditioned affine correction (mlp.py:121-124): y = x * s[b] + o[b], gradients incl. the per-sample sums."""
+    ops = _ops()
+    gen = torch.Generator().manual_seed(B * 31 + D)
+    x, s, o, g = torch.randn(B, T, D, generator=gen), torch.randn(B, D, generator=gen), torch.randn(B, D, generator=gen), torch.randn(B, T, D, generator=gen)
+    a = [t.clone().to(DEV).requires_grad_(True) for t in (x, s, o)]
+    y = ops.cond_affine(*a)
+    y.backward(g.to(DEV))
+    r = [t.clone().double().requires_grad_(True) for t in (x, s, o)]
+    yr = r[0] * r[1][:, None, :] + r[2][:, None, :]
+    yr.backward(g.double())
+    assert rel_l2(y, yr) < 1e-6
+    for got, want in zip(a, r):
+        assert rel_l2(got.grad, want.grad) < 5e-6

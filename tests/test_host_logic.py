@@ -40,7 +40,7 @@ def test_nothing_in_the_product_imports_the_oracle():
 
 
 @pytest.mark.parametrize("fuse", [True, False])
-@pytest.mark.parametrize("name", ["tiny2d", "tiny3d", "plain2d", "vx2d", "dot2d", "npe2d", "pnet2d"])
+@pytest.mark.parametrize("name", ["tiny2d", "tiny3d", "plain2d", "vx2d", "dot2d", "npe2d", "pnet2d", "cond2d"])
 def test_model_wiring_matches_reference_golden(name, fuse):
     c = cases.CASES[name]
     g = load_golden(name)
@@ -53,7 +53,7 @@ def test_model_wiring_matches_reference_golden(name, fuse):
         enc = dec = None
         if c.get("vx"):
             enc, dec = golden_graphs(g, "enc", True), golden_graphs(g, "dec", True)
-        out = model(lat, x, pn, encoder_nbrs=enc, decoder_nbrs=dec)
+        out = model(lat, x, pn, encoder_nbrs=enc, decoder_nbrs=dec, condition=cases.case_condition(name))
         loss = ops.mse_loss(out, tgt)
         loss.backward()
         assert "gaot_attention_bwd" in calls

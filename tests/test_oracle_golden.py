@@ -7,7 +7,7 @@ import torch
 from oracle import cases, gaot_oracle as orc
 from tests.helpers import golden_graphs, golden_params, golden_shapes, grad_rel, grad_scale, load_golden, rel_l2
 
-FULL = ["tiny2d", "tiny3d", "vx2d", "plain2d", "dot2d", "npe2d", "pnet2d"]
+FULL = ["tiny2d", "tiny3d", "vx2d", "plain2d", "dot2d", "npe2d", "pnet2d", "cond2d"]
 
 
 def _cfg(name):
@@ -45,7 +45,8 @@ def test_forward_backward_matches_reference_fp64(name):
     p = {k: v.double().requires_grad_(True) for k, v in golden_params(g).items()}
     enc = golden_graphs(g, "enc", bool(c.get("vx")))
     dec = golden_graphs(g, "dec", bool(c.get("vx")))
-    out = orc.gaot_forward(p, cfg, lat, x, pn, None, enc, dec)
+    cond = cases.case_condition(name)
+    out = orc.gaot_forward(p, cfg, lat, x, pn, None, enc, dec, cond.double() if cond is not None else None)
     assert rel_l2(out, g["out"]) < 2e-7          # fixtures are stored as fp32
     loss = torch.nn.functional.mse_loss(out, tgt)
     assert abs(float(loss.detach()) - float(g["loss64"])) < 1e-12 * max(1.0, abs(float(g["loss64"])))
