@@ -77,8 +77,21 @@ def note_launches(n: int):
     lib().gaot_launch_counter_add(int(n))
 
 
+_dummies = {}
+
+
 def ptr(t):
-    return 0 if t is None else t.data_ptr()
+    """Raw address for the ABI.  None -> NULL (optional argument).  A zero-element tensor (e.g. the edge arrays of a graph
+    without any edge) has data_ptr() == 0 in torch; the library treats NULL as "argument missing", so it gets the address
+    of a small per-device dummy buffer instead - it is never dereferenced because the matching size is 0."""
+    if t is None:
+        return 0
+    if t.numel() == 0:
+        d = _dummies.get(t.device)
+        if d is None:
+            d = _dummies[t.device] = torch.zeros(16, dtype=torch.int64, device=t.device)
+        return d.data_ptr()
+    return t.data_ptr()
 
 
 def stream():
