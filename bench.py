@@ -199,7 +199,23 @@ def run_ours(args, w):
     def dev_step():
         return graphed() if graphed is not None else eager_step()
 
+    feeder = None
+    if graphed is not None:
+        from gaot_b200.trainer import InputPrefetcher
+        feeder = InputPrefetcher([pn_s, tgt_s])
+    staged = {"ok": False}
+
     def e2e_step():
+        if feeder is not None:
+            # every step's batch goes pinned host -> device inside the timed region; the copy of batch i+1 is issued on the
+            # copy stream right after step i's graph has been launched, so it runs under step i's kernels
+            if not staged["ok"]:
+                feeder.prefetch([pn_h, tgt_h])
+            feeder.commit()
+            loss = graphed()
+            feeder.prefetch([pn_h, tgt_h])
+            staged["ok"] = True
+            return float(loss)                                                 # .item(): D2H read of the loss
         pn_s.copy_(pn_h, non_blocking=True)
         tgt_s.copy_(tgt_h, non_blocking=True)
         if graphed is not None:
@@ -219,6 +235,8 @@ def run_ours(args, w):
     launches = _lib.launch_count() - n0
     clocks = sampler.stop() if sampler else None
     e2e_step()
+    torch.cuda.synchronize()
+    staged["ok"] = False                   # the first timed step copies its own batch inside the timed region
     ms_e2e = timed(e2e_step, args.steps)
 
     # per-kernel breakdown: one extra step with CUDA events around every ABI call (same stream)

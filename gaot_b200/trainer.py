@@ -156,3 +156,33 @@ class TrainStep:
             x, y, coords, enc, dec = batch
             return self.variable_coords_step(latent, x, y, coords, enc, dec)
         raise ValueError(f"unsupported batch tuple of length {len(batch)}")
+
+
+class InputPrefetcher:
+    """Feeds the static input buffers of a captured step from pinned host memory without stalling the compute stream:
+    `prefetch(host_tensors)` copies the NEXT batch host -> device staging buffers on a dedicated copy stream (it runs under
+    the kernels of the current step); `commit()` moves staging -> the graph's static buffers on the compute stream
+    (device-to-device, microseconds) right before the next replay.  The reference moves every batch with a blocking
+    `.to(device)` inside the step (static_trainer.py:169-170)."""
+
+    def __init__(self, static_tensors):
+        self.static = list(static_tensors)
+        self.stage = [torch.empty_like(t) for t in self.static]
+        self.stream = torch.cuda.Stream()
+        self.ready = torch.cuda.Event()
+        self.consumed = torch.cuda.Event()
+        self.consumed.record(torch.cuda.current_stream())
+
+    def prefetch(self, host_tensors):
+        self.stream.wait_event(self.consumed)               # the previous staged batch has been moved out
+        with torch.cuda.stream(self.stream):
+            for s, h in zip(self.stage, host_tensors):
+                s.copy_(h, non_blocking=True)
+            self.ready.record(self.stream)
+
+    def commit(self):
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self.ready)
+        for t, s in zip(self.static, self.stage):
+            t.copy_(s, non_blocking=True)
+        self.consumed.record(cur)

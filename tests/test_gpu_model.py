@@ -161,3 +161,16 @@ def test_autoregressive_rollout_matches_oracle(use_graph):
             pred = orc.gaot_forward(p, cfg, lat.double(), x.double(), inp)
             cur = orc.rollout_update(pred, cur, dt, st64, "time_der")
             assert rel_l2(got[:, i], cur) < 2e-5, i          # errors compound over the 10 autoregressive steps
+
+
+def test_input_prefetcher_feeds_static_buffers():
+    """Pinned host batch -> staging on the copy stream -> static buffers on the compute stream (trainer.InputPrefetcher)."""
+    from gaot_b200.trainer import InputPrefetcher
+    a_s, b_s = torch.zeros(4, 100, 3, device=DEV), torch.zeros(4, 100, 1, device=DEV)
+    feeder = InputPrefetcher([a_s, b_s])
+    for k in range(3):
+        a_h, b_h = torch.full((4, 100, 3), float(k + 1)).pin_memory(), torch.full((4, 100, 1), -float(k + 1)).pin_memory()
+        feeder.prefetch([a_h, b_h])
+        feeder.commit()
+        torch.cuda.synchronize()
+        assert torch.equal(a_s.cpu(), a_h) and torch.equal(b_s.cpu(), b_h)
