@@ -113,6 +113,9 @@ def call_work(name, a):
     if name == "gaot_gemm_bf16":
         M, N, K = a[3], a[4], a[5]
         return 2.0 * M * N * K, 2.0 * (M * K + N * K) + (2.0 if a[6] else 4.0) * M * N
+    if name in ("gaot_gemm_bf16_nn", "gaot_gemm_bf16_tn"):
+        M, N, K = a[3], a[4], a[5]
+        return 2.0 * M * N * K, 2.0 * (M * K + N * K) + 4.0 * M * N
     if name == "gaot_attention_fwd":
         B, T, H, hd = a[5], a[6], a[7], a[9]
         return 4.0 * B * H * T * T * hd, 4.0 * B * T * H * hd * 4
@@ -378,6 +381,10 @@ def run_ours(args, w):
                       "traffic": None}
     breakdown = {k: {"calls": d["calls"], "ms": round(d["s"] * 1e3, 3), "share": round(d["s"] / total_s, 4)}
                  for k, d in sorted(agg.items(), key=lambda kv: -kv[1]["s"])}
+    for k, d in agg.items():                           # tensor-pipe kernels: achieved TFLOP/s of the eager-timed calls
+        if d["flops"] > 0:                             # (host launch gaps included, so a lower bound) vs the measured bf16 peak
+            breakdown[k]["tflops"] = round(d["flops"] / d["s"] / 1e12, 1)
+            breakdown[k]["frac_of_bf16_peak"] = round(d["flops"] / d["s"] / 1e12 / peaks["bf16_tflops"], 4)
 
     pts = world * B * w["n"] * args.steps
     out = {
