@@ -34,6 +34,8 @@ class GAOT(nn.Module):
         self.processor = Transformer(input_size=self.node_latent_size * pv, output_size=self.node_latent_size * pv,
                                      config=config.args.transformer)
         self.decoder = MAGNODecoder(in_channels=self.node_latent_size, out_channels=output_size, config=config.args.magno)
+        self.overlap_decoder_prep = True        # run the decoder's batch-independent work on a side stream (CUDA only)
+        self._side_stream = None
         self._pos_emb = None
 
     def _grid(self):
@@ -88,10 +90,29 @@ class GAOT(nn.Module):
 
     def forward(self, latent_tokens_coord, xcoord, pndata, query_coord=None, encoder_nbrs=None, decoder_nbrs=None,
                 condition: Optional[float] = None):
-        rndata = self.encode(xcoord, pndata, latent_tokens_coord, encoder_nbrs)
-        rndata = self.process(rndata, condition=condition)
         if query_coord is None:
             query_coord = xcoord
+        C = self.decoder.recovery.fcs[0].weight.shape[0] if self.decoder.use_geoembed else self.decoder.projection.fcs[0].weight.shape[1]
+        if self.overlap_decoder_prep and pndata.is_cuda and self.decoder.fusable(C):
+            # The decoder's batch-independent work (edge MLP, attention weights, geometry term: ~30 small latency-bound
+            # kernels forward + backward) depends on coordinates and parameters only: fork it onto a side stream so it runs
+            # under the processor (in a captured CUDA graph the two branches replay concurrently; autograd runs the
+            # backward of these ops on the same side stream, i.e. under the processor's backward).
+            cur = torch.cuda.current_stream()
+            if self._side_stream is None:
+                self._side_stream = torch.cuda.Stream()
+            side = self._side_stream
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                prep = self.decoder.prepare_fused(latent_tokens_coord, query_coord, decoder_nbrs, pndata.shape[0], C)
+            rndata = self.encode(xcoord, pndata, latent_tokens_coord, encoder_nbrs)
+            rndata = self.process(rndata, condition=condition)
+            cur.wait_stream(side)
+            for t in (prep["u"], prep["const"]):
+                t.record_stream(cur)                       # produced on the side stream, consumed on this one
+            return self.decoder.apply_fused(rndata, prep)
+        rndata = self.encode(xcoord, pndata, latent_tokens_coord, encoder_nbrs)
+        rndata = self.process(rndata, condition=condition)
         return self.decode(latent_tokens_coord, rndata, query_coord, decoder_nbrs)
 
     @torch.no_grad()

@@ -253,20 +253,36 @@ class MAGNODecoder(_MAGNOBase):
         dec = self._combine(outs, query_coord if not vx else query_coord[0])
         return self.projection(dec)                                       # [B,Nq,Cout]  (magno.py:640-641)
 
-    def _forward_fused(self, latent, rndata, query_coord, decoder_nbrs, vx, Wp, bp):
-        """Single-scale decoder with recovery and projection (both affine, no activation between them:
-        magno.py:684-688, 640-641) folded into the aggregate:
-            out[b,n,:] = (Wp Wa) A[b,n,:] + Wp (Wg G[n,:] + b_rec) + bp,   A = AGNO output
-        so the kernel reduces <u[o,e,:], r[b,j,:]> with u = (Wp Wa)[o,:] * w[e,:] and writes Cout scalars per
-        point; the [B,N,C] decoder activations are never formed."""
-        B, M, C = rndata.shape
+    def fusable(self, C: int) -> bool:
+        Wp = self.projection.fcs[0].weight
+        return (self.fuse_affine and len(self.scales) == 1 and Wp.shape[0] <= ops.FUSE_MAX_COUT and C % 4 == 0
+                and C <= ops.FUSE_MAX_C)
+
+    def prepare_fused(self, latent, query_coord, decoder_nbrs, B: int, C: int, resolved: bool = False):
+        """Batch-independent half of the fused decoder: graph plan, edge weights (kernel MLP + attention), geometry term and
+        the folded read-out weights.  It depends on coordinates and parameters only, so GAOT.forward runs it on a side
+        stream while the processor is busy (its many small latency-bound kernels then cost nothing); the backward of these
+        ops runs on the same side stream under the processor's backward."""
+        if query_coord.ndim not in (2, 3):
+            raise ValueError(f"query_coord must be 2D or 3D, got {query_coord.ndim}D")
+        vx = query_coord.ndim == 3
+        if query_coord.shape[-1] != self.coord_dim or latent.shape[-1] != self.coord_dim:
+            raise ValueError(f"Expected coord_dim={self.coord_dim}")
+        if not resolved:
+            if self.precompute_edges:
+                if decoder_nbrs is None:
+                    raise ValueError("decoder_nbrs is required when precompute_edges is True")
+            else:
+                decoder_nbrs = self._search(latent, query_coord)
+        M = latent.shape[0]
         Nq = query_coord.shape[-2]
+        Wp, bp = self.projection.fcs[0].weight[:, :, 0], self.projection.fcs[0].bias
         if not vx:
             plan = ops.graph_plan(self._drop(decoder_nbrs[0]), M)
-            src, dst, feats, groups = latent, query_coord, rndata, 1
+            src, dst, groups = latent, query_coord, 1
         else:
             plan = self._merged_plan([self._drop(decoder_nbrs[b][0]) for b in range(B)], M)
-            src, dst, feats, groups = latent.repeat(B, 1), query_coord.reshape(B * Nq, -1), rndata.reshape(1, B * M, C), B
+            src, dst, groups = latent.repeat(B, 1), query_coord.reshape(B * Nq, -1), B
         w = self._edge_weights(plan, src, dst)                            # [E, C]
         if self.use_geoembed:
             Wrec = self.recovery.fcs[0].weight[:, :, 0]                   # [C, 2C]
@@ -278,5 +294,22 @@ class MAGNODecoder(_MAGNOBase):
         else:
             const, Wfold = bp.view(1, -1), Wp
         u = Wfold.unsqueeze(1) * w.unsqueeze(0)                           # [Cout, E, C]
-        out = ops.agno_dot(feats, u, plan)                                # [Bf, rows, Cout]
-        return (out + const.unsqueeze(0)).view(B, Nq, -1)
+        return dict(plan=plan, u=u, const=const, vx=vx, Nq=Nq)
+
+    def apply_fused(self, rndata, prep):
+        B, M, C = rndata.shape
+        if rndata.shape[1] != prep["plan"].n_src // (B if prep["vx"] else 1):
+            raise ValueError(f"rndata has {rndata.shape[1]} tokens but latent_tokens_coord has {prep['plan'].n_src // (B if prep['vx'] else 1)}")
+        feats = rndata.reshape(1, B * M, C) if prep["vx"] else rndata
+        out = ops.agno_dot(feats, prep["u"], prep["plan"])               # [Bf, rows, Cout]
+        return (out + prep["const"].unsqueeze(0)).view(B, prep["Nq"], -1)
+
+    def _forward_fused(self, latent, rndata, query_coord, decoder_nbrs, vx, Wp, bp):
+        """Single-scale decoder with recovery and projection (both affine, no activation between them:
+        magno.py:684-688, 640-641) folded into the aggregate:
+            out[b,n,:] = (Wp Wa) A[b,n,:] + Wp (Wg G[n,:] + b_rec) + bp,   A = AGNO output
+        so the kernel reduces <u[o,e,:], r[b,j,:]> with u = (Wp Wa)[o,:] * w[e,:] and writes Cout scalars per
+        point; the [B,N,C] decoder activations are never formed."""
+        B, M, C = rndata.shape
+        prep = self.prepare_fused(latent, query_coord, decoder_nbrs, B, C, resolved=True)
+        return self.apply_fused(rndata, prep)
