@@ -92,6 +92,7 @@ class GAOT(nn.Module):
                 condition: Optional[float] = None):
         if query_coord is None:
             query_coord = xcoord
+        ops.clear_prepared()                               # prepared bf16 weights never outlive the forward that made them
         C = self.decoder.recovery.fcs[0].weight.shape[0] if self.decoder.use_geoembed else self.decoder.projection.fcs[0].weight.shape[1]
         if self.overlap_decoder_prep and pndata.is_cuda and self.decoder.fusable(C):
             # The decoder's batch-independent work (edge MLP, attention weights, geometry term: ~30 small latency-bound
@@ -103,10 +104,23 @@ class GAOT(nn.Module):
                 self._side_stream = torch.cuda.Stream()
             side = self._side_stream
             side.wait_stream(cur)
+            wready = None
             with torch.cuda.stream(side):
+                if ops.get_precision() == "bf16":
+                    # bf16 copies / concatenations of the processor's weights: ~40 tiny kernels that would otherwise sit
+                    # between the processor's GEMMs; here they run under the encoder
+                    ops.clear_prepared()
+                    wts = self.processor.prep_weights() + [ops.prepare_weight(self.patch_linear.weight)]
+                    wready = torch.cuda.Event()
+                    wready.record(side)
                 prep = self.decoder.prepare_fused(latent_tokens_coord, query_coord, decoder_nbrs, pndata.shape[0], C)
             rndata = self.encode(xcoord, pndata, latent_tokens_coord, encoder_nbrs)
+            if wready is not None:
+                cur.wait_event(wready)
+                for t in wts:
+                    t.record_stream(cur)
             rndata = self.process(rndata, condition=condition)
+            ops.clear_prepared()
             cur.wait_stream(side)
             for t in (prep["u"], prep["const"]):
                 t.record_stream(cur)                       # produced on the side stream, consumed on this one

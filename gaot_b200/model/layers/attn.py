@@ -75,6 +75,12 @@ class GroupQueryFlashAttention(nn.Module):
         self.v_proj = nn.Linear(input_size, kv, bias=False)
         self.o_proj = nn.Linear(hidden_size, input_size, bias=False)
         self.correction = ConditionedNorm(1, input_size, cond_norm_hidden_size) if use_conditional_norm else None
+        self._wqkv = None
+
+    def prep_weights(self):
+        """Concatenated q/k/v weight and the bf16 operands of this layer's GEMMs, ahead of time (ops.prepare_weight)."""
+        self._wqkv = torch.cat([self.q_proj.weight, self.k_proj.weight, self.v_proj.weight], dim=0)
+        return [self._wqkv, ops.prepare_weight(self._wqkv), ops.prepare_weight(self.o_proj.weight)]
 
     @classmethod
     def from_config(cls, input_size, hidden_size, config: AttentionConfig, positional_embedding="absolute"):
@@ -87,7 +93,8 @@ class GroupQueryFlashAttention(nn.Module):
         B, T, D = x.shape
         if self.correction is not None:
             x = self.correction(condition, x)              # attn.py:89-90 (fp32; the GEMM below casts its operand)
-        wqkv = torch.cat([self.q_proj.weight, self.k_proj.weight, self.v_proj.weight], dim=0)
+        wqkv = self._wqkv if self._wqkv is not None else torch.cat([self.q_proj.weight, self.k_proj.weight, self.v_proj.weight], dim=0)
+        self._wqkv = None
         tc_attn = ops.get_precision() == "bf16" and self.head_dim in (16, 32, 64) and D % 8 == 0
         qkv = ops.linear(x.reshape(B * T, D), wqkv, tc=True, out_bf16=tc_attn)
         o = ops.attention(qkv, B, T, self.num_heads, self.num_kv_heads, self.head_dim)
@@ -102,12 +109,19 @@ class FFN(nn.Module):
         self.w2 = nn.Linear(ffn_hidden_size, input_size, bias=False)
         self.w3 = nn.Linear(input_size, ffn_hidden_size, bias=False)
         self.correction = ConditionedNorm(1, input_size, cond_norm_hidden_size) if use_conditional_norm else None
+        self._w13 = None
+
+    def prep_weights(self):
+        self._w13 = torch.cat([self.w1.weight, self.w3.weight], dim=0)
+        return [self._w13, ops.prepare_weight(self._w13), ops.prepare_weight(self.w2.weight)]
 
     def forward(self, x, condition=None, residual=None):
         shape = x.shape
         x2 = x.reshape(-1, shape[-1])
         tc16 = ops.get_precision() == "bf16" and shape[-1] % 8 == 0 and self.w1.weight.shape[0] % 8 == 0
-        ab = ops.linear(x2, torch.cat([self.w1.weight, self.w3.weight], dim=0), tc=True, out_bf16=tc16)
+        w13 = self._w13 if self._w13 is not None else torch.cat([self.w1.weight, self.w3.weight], dim=0)
+        self._w13 = None
+        ab = ops.linear(x2, w13, tc=True, out_bf16=tc16)
         if self.correction is not None:
             # attn.py:151-154: the correction acts on the FFN output, so the residual cannot ride in the w2 epilogue
             y = ops.linear(ops.swiglu(ab), self.w2.weight, None, tc=True).view(shape)
@@ -165,6 +179,14 @@ class Transformer(nn.Module):
         self.encoder_layers = nn.ModuleList([TransformerBlock(working, config, False) for _ in range(L // 2)])
         self.middle_layer = TransformerBlock(working, config, False) if L % 2 == 1 else None
         self.decoder_layers = nn.ModuleList([TransformerBlock(working, config, True) for _ in range(L // 2)])
+
+    def prep_weights(self):
+        """bf16 GEMM operands of every block, prepared ahead of the blocks' forward (see ops.prepare_weight)."""
+        out = []
+        blocks = list(self.encoder_layers) + ([self.middle_layer] if self.middle_layer is not None else []) + list(self.decoder_layers)
+        for blk in blocks:
+            out += blk.attn.prep_weights() + blk.ffn.prep_weights()
+        return out
 
     @staticmethod
     def _proj(layer, x):

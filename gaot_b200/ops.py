@@ -234,12 +234,30 @@ def gemm_bf16_tn(A, B, M, N, R, out=None, accumulate=False):
     return out
 
 
+# bf16 copies of weights prepared ahead of their GEMM (GAOT.forward does this on a side stream at the start of the step so
+# the ~30 small cast / concatenation kernels run under the encoder instead of between the processor's GEMMs).  Keyed by the
+# identity of the fp32 weight tensor object that the layer will pass to `linear`; the entry keeps that object alive.
+_PREPARED = {}
+
+
+def prepare_weight(W):
+    """Register the bf16 copy of W (2-D, fp32) for the next tensor-core `linear(x, W, ...)` call with this very object."""
+    Wc = _c(W)
+    wb = cast_bf16(Wc)[0]
+    _PREPARED[id(W)] = (W, wb)
+    return wb
+
+
+def clear_prepared():
+    _PREPARED.clear()
+
+
 class _LinearTC(torch.autograd.Function):
     """y = x W^T + bias + add[row % add_rows] with bf16 operands on tcgen05.  x may be fp32 (cast here) or
     already bf16; y is fp32, or bf16 when out_bf16 (feeding another tensor-core kernel)."""
 
     @staticmethod
-    def forward(ctx, x, W, bias, add, out_bf16, act=ACT_NONE):
+    def forward(ctx, x, W, bias, add, out_bf16, act=ACT_NONE, prepared=None):
         _need_cuda(x)
         x = x if x.is_contiguous() else x.contiguous()
         W = _c(W)
@@ -251,7 +269,7 @@ class _LinearTC(torch.autograd.Function):
         if add_c is not None and (add_c.shape[1] != N or M % add_rows != 0):
             raise ValueError(f"broadcast-add of shape {tuple(add_c.shape)} does not tile an [{M},{N}] output")
         xb = x if x.dtype == torch.bfloat16 else cast_bf16(_c(x))[0]
-        wb, _ = cast_bf16(W)
+        wb = prepared if prepared is not None else cast_bf16(W)[0]
         pre = torch.empty((M, N), dtype=torch.float32, device=x.device) if act != ACT_NONE else None
         y = gemm_bf16(xb, wb, M, N, K, out_bf16=out_bf16, bias=bias_c, add=add_c, add_rows=add_rows, act=act, pre=pre)
         ctx.save_for_backward(xb, wb, pre)
@@ -292,14 +310,15 @@ class _LinearTC(torch.autograd.Function):
                 db = col_sum(dyf, M, N)
             if ctx.add_rows and ctx.needs_input_grad[3]:
                 dadd = dyf if ctx.add_rows == M else col_sum(dyf, M // ctx.add_rows, ctx.add_rows * N).view(ctx.add_rows, N)
-        return dx, dW, db, dadd, None, None
+        return dx, dW, db, dadd, None, None, None
 
 
 def linear(x, W, bias=None, add=None, act=ACT_NONE, tc=False, out_bf16=False):
     """tc=True marks a processor layer that may run on the tensor cores when precision is 'bf16';
     out_bf16 (tensor-core path only) keeps the result in bf16 for a following tensor-core kernel."""
     if tc and _PRECISION == "bf16" and x.shape[-1] % 8 == 0 and (act == ACT_NONE or W.shape[0] % 4 == 0):
-        return _LinearTC.apply(x, W, bias, add, out_bf16, act)
+        ent = _PREPARED.get(id(W))
+        return _LinearTC.apply(x, W, bias, add, out_bf16, act, ent[1] if ent is not None else None)
     if x.dtype != torch.float32:
         x = x.float()
     return _Linear.apply(x, W, bias, add, act)
