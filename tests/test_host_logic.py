@@ -183,7 +183,8 @@ def test_data_parallel_step_equals_single_process_gloo():
         assert rel_l2(torch.from_numpy(sd_dp[k]), t) < 1e-5, k
 
 
-def test_rollout_matches_oracle_update_rules():
+@pytest.mark.parametrize("mode", ["time_der", "residual", "output"])
+def test_rollout_matches_oracle_update_rules(mode):
     c = dict(cases.CASES["tiny2d"], cin=5, cout=3)       # u(3) + t0 + dt
     with abi_emulator.install():
         torch.manual_seed(0)
@@ -192,16 +193,17 @@ def test_rollout_matches_oracle_update_rules():
         u0 = cases.normal((2, 300, 3), 31)
         stats = {"u": {"mean": torch.tensor([0.1, 0.2, 0.3]), "std": torch.tensor([1.1, 0.9, 1.2])},
                  "der": {"mean": torch.tensor([0.0, 0.1, -0.1]), "std": torch.tensor([0.5, 0.6, 0.7])},
+                 "res": {"mean": torch.tensor([0.05, -0.1, 0.2]), "std": torch.tensor([0.3, 0.4, 0.2])},
                  "start_time": {"mean": 0.5, "std": 0.3}, "time_diffs": {"mean": 0.1, "std": 0.05}}
         tv = torch.linspace(0, 1, 21)
-        got = model.autoregressive_predict(u0, [0, 2, 4], tv, stats, "time_der", latent_tokens_coord=lat, fixed_coord=x)
+        got = model.autoregressive_predict(u0, [0, 2, 4], tv, stats, mode, latent_tokens_coord=lat, fixed_coord=x)
         # oracle: same forward through the emulator, update rule from oracle.rollout_update
         cur = u0
         for i, (a, b) in enumerate(((0, 2), (2, 4))):
             t0, dt = float(tv[a]), float(tv[b] - tv[a])
             inp = torch.cat([cur, torch.full((2, 300, 1), (t0 - 0.5) / 0.3), torch.full((2, 300, 1), (dt - 0.1) / 0.05)], -1)
             pred = model(lat, x, inp)
-            cur = orc.rollout_update(pred, cur, dt, stats, "time_der")
+            cur = orc.rollout_update(pred, cur, dt, stats, mode)
             assert rel_l2(got[:, i], cur) < 1e-6
 
 
