@@ -132,11 +132,13 @@ class GAOT(nn.Module):
     @torch.no_grad()
     def autoregressive_predict(self, x_batch, time_indices, t_values, stats, stepper_mode="output",
                                latent_tokens_coord=None, fixed_coord=None, encoder_nbrs=None, decoder_nbrs=None,
-                               c_batch=None, use_cuda_graph=False):
+                               c_batch=None, use_cuda_graph=False, use_conditional_norm=False):
         """gaot.py:307-434 (fx mode): x_batch [B,N,u_dim] normalised initial state, optional conditioning
         channels c_batch [B,N,c]; returns [B, len(time_indices)-1, N, u_dim] normalised predictions.
         stats = {"u": {mean,std}, "res": {...}, "der": {...}, "start_time": {...}, "time_diffs": {...}} of
-        per-channel tensors / floats as the reference's sequential trainer supplies them."""
+        per-channel tensors / floats as the reference's sequential trainer supplies them.  With use_conditional_norm the
+        last input channel (the time difference) is not fed to the encoder and the conditioning value is
+        x_input[..., 0, -2:-1], exactly as gaot.py:392-408 does."""
         dev = x_batch.device
         B, N, U = x_batch.shape
         cur = x_batch
@@ -151,6 +153,13 @@ class GAOT(nn.Module):
         if c_batch is not None:
             x_in[..., U:U + nc] = c_batch
         graph = pred_static = None
+
+        def fwd():
+            if use_conditional_norm:
+                return self.forward(latent_tokens_coord, fixed_coord, x_in[..., :-1], encoder_nbrs=encoder_nbrs,
+                                    decoder_nbrs=decoder_nbrs, condition=x_in[..., 0, -2:-1])
+            return self.forward(latent_tokens_coord, fixed_coord, x_in, encoder_nbrs=encoder_nbrs, decoder_nbrs=decoder_nbrs)
+
         for i in range(len(time_indices) - 1):
             t0 = float(t_values[time_indices[i]])
             dt = float(t_values[time_indices[i + 1]]) - t0
@@ -165,17 +174,16 @@ class GAOT(nn.Module):
                     side = torch.cuda.Stream()
                     side.wait_stream(torch.cuda.current_stream())
                     with torch.cuda.stream(side):
-                        self.forward(latent_tokens_coord, fixed_coord, x_in, encoder_nbrs=encoder_nbrs, decoder_nbrs=decoder_nbrs)
+                        fwd()
                     torch.cuda.current_stream().wait_stream(side)
                     torch.cuda.synchronize()
                     graph = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(graph):
-                        pred_static = self.forward(latent_tokens_coord, fixed_coord, x_in, encoder_nbrs=encoder_nbrs,
-                                                   decoder_nbrs=decoder_nbrs)
+                        pred_static = fwd()
                 graph.replay()
                 pred = pred_static
             else:
-                pred = self.forward(latent_tokens_coord, fixed_coord, x_in, encoder_nbrs=encoder_nbrs, decoder_nbrs=decoder_nbrs)
+                pred = fwd()
             cur = ops.rollout_update(pred, cur, dt, mode, um, us, sm, ss)
             outs.append(cur)
         return torch.stack(outs, dim=1)

@@ -207,6 +207,31 @@ def test_rollout_matches_oracle_update_rules(mode):
             assert rel_l2(got[:, i], cur) < 1e-6
 
 
+def test_rollout_with_conditional_norm_feeds_time_as_condition():
+    """gaot.py:392-408: with use_conditional_norm the time-difference channel is dropped from the encoder input and the
+    conditioning value is x_input[..., 0, -2:-1]."""
+    c = dict(cases.CASES["cond2d"], cin=4, cout=3)       # encoder sees u(3) + t0; dt is held back
+    with abi_emulator.install():
+        torch.manual_seed(0)
+        model = build_model(c, "cpu").eval()
+        lat, x, _, _ = cases.case_inputs("cond2d")
+        u0 = cases.normal((3, 300, 3), 41)
+        stats = {"u": {"mean": torch.tensor([0.1, 0.2, 0.3]), "std": torch.tensor([1.1, 0.9, 1.2])},
+                 "der": {"mean": torch.tensor([0.0, 0.1, -0.1]), "std": torch.tensor([0.5, 0.6, 0.7])},
+                 "start_time": {"mean": 0.5, "std": 0.3}, "time_diffs": {"mean": 0.1, "std": 0.05}}
+        tv = torch.linspace(0, 1, 21)
+        got = model.autoregressive_predict(u0, [0, 3, 5], tv, stats, "time_der", latent_tokens_coord=lat, fixed_coord=x,
+                                           use_conditional_norm=True)
+        cur = u0
+        for i, (a, b) in enumerate(((0, 3), (3, 5))):
+            t0, dt = float(tv[a]), float(tv[b] - tv[a])
+            t0n = (t0 - 0.5) / 0.3
+            inp = torch.cat([cur, torch.full((3, 300, 1), t0n)], -1)
+            pred = model(lat, x, inp, condition=torch.full((3, 1), t0n))
+            cur = orc.rollout_update(pred, cur, dt, stats, "time_der")
+            assert rel_l2(got[:, i], cur) < 1e-6
+
+
 def test_bf16_mode_wiring_close_to_reference():
     """precision='bf16' routes the processor's Linear layers through the tensor-core ABI (emulated here);
     bf16 operand rounding keeps the output within a few 1e-3 of the fp64 reference on the tiny model."""
