@@ -103,9 +103,6 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 __device__ __forceinline__ float ex2(float x) {          // single MUFU.EX2 (ex2(-inf) = 0)
-#ifdef EXP_NO_MUFU
-    return x * 0.001f;
-#endif
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
@@ -634,9 +631,6 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
                 const uint32_t pst = smem_u32(sSt + bf * PT_BYTES);
                 const uint64_t d_pt = make_desc<128>(smem_u32(sPt + bf * PT_BYTES)), d_st = make_desc<128>(pst);
                 const uint32_t acc_first = i > 0 ? 1u : 0u;
-#ifdef EXP_NO_DVKQ
-                if (g.scale == 12345.f)
-#endif
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {      // contraction over 128 queries, 16 per MMA
                     const uint64_t aoff = (uint64_t)(((k >> 2) * (128 * 128) + (k & 3) * 32) >> 4);
@@ -648,9 +642,6 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
                 // (M = 128 queries = two 64-wide swizzle atoms LBO = 16 KB apart, 8-key groups SBO = 1 KB apart)
                 const uint64_t a_mn0 = (uint64_t)((pst & 0x3FFFF) >> 4) | ((uint64_t)(16384 >> 4) << 16) |
                                        ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
-#ifdef EXP_NO_DVKQ
-                if (g.scale == 12345.f)
-#endif
 #pragma unroll
                 for (int k = 0; k < 8; ++k)        // contraction over 128 keys, 16 per MMA = 16 rows of 128 bytes
                     umma_f16(tm_dq + d * HD, a_mn0 + (uint64_t)((k * 2048) >> 4), d_k + (uint64_t)((k * 16 * ROWB) >> 4), IDESC_MN, k > 0 ? 1u : 0u);
@@ -692,11 +683,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(&dq_empty[d]);
-#ifndef EXP_NO_RED
             if (t < g.T) {
-#else
-            if (t < g.T && g.scale == 12345.f) {
-#endif
                 float* dst = g.dq_acc + ((int64_t)(row_base + t) * g.H + h) * HD + qr * NC;
 #pragma unroll
                 for (int j4 = 0; j4 < NC; j4 += 4)
