@@ -82,6 +82,14 @@ CASES = {
                               neighbor_search_method="native"),
                    transformer=dict(patch_size=2, hidden_size=64, num_layers=3, ffn_multiplier=2),
                    attn=dict(num_heads=2, num_kv_heads=2, use_conditional_norm=True)),
+    # the optional paths together, in vx mode: per-sample meshes/graphs + dot-product attention + pointnet (mean pooling)
+    # + node position encoding
+    "vxmix": dict(latent=(8, 8), n=220, d=2, B=3, cin=2, cout=2, seed=9, vx=True,
+                  magno=dict(coord_dim=2, radius=0.4, hidden_size=16, mlp_layers=2, lifting_channels=16,
+                             attention_type="dot_product", embedding_method="pointnet", pooling="mean", node_embedding=True,
+                             precompute_edges=True, neighbor_search_method="native"),
+                  transformer=dict(patch_size=2, hidden_size=64, num_layers=2, ffn_multiplier=2),
+                  attn=dict(num_heads=2, num_kv_heads=2)),
     # BASELINE cfg-2 geometry (Poisson-Gauss hyper-parameters, config/examples/time_indep/poisson_gauss.json)
     "cfg2": dict(latent=(64, 64), n=9216, d=2, B=2, cin=1, cout=1, seed=0, summary_only=True,
                  magno=dict(coord_dim=2, radius=0.033, hidden_size=64, mlp_layers=3, lifting_channels=64,

@@ -40,7 +40,7 @@ def test_nothing_in_the_product_imports_the_oracle():
 
 
 @pytest.mark.parametrize("fuse", [True, False])
-@pytest.mark.parametrize("name", ["tiny2d", "tiny3d", "plain2d", "vx2d", "dot2d", "npe2d", "pnet2d", "cond2d"])
+@pytest.mark.parametrize("name", ["tiny2d", "tiny3d", "plain2d", "vx2d", "dot2d", "npe2d", "pnet2d", "cond2d", "vxmix"])
 def test_model_wiring_matches_reference_golden(name, fuse):
     c = cases.CASES[name]
     g = load_golden(name)
