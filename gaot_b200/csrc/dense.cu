@@ -669,31 +669,35 @@ __global__ void swiglu_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ du, con
     }
 }
 
-template <typename T>
-__global__ void patch_permute_kernel(const T* __restrict__ in, T* __restrict__ out, int64_t B, int dims,
-                                     int64_t H, int64_t W, int64_t D, int64_t P, int64_t C, int to_tokens) {
+// IDX = uint32_t whenever the element count fits (it does for every BASELINE config): the index decomposition is a chain of
+// divisions / remainders, and 64-bit integer division costs ~5x the 32-bit one - this copy kernel was bound by it, not by HBM
+template <typename T, typename IDX>
+__global__ void patch_permute_kernel(const T* __restrict__ in, T* __restrict__ out, int64_t B_, int dims,
+                                     int64_t H_, int64_t W_, int64_t D_, int64_t P_, int64_t C_, int to_tokens) {
     // iterate over token-layout elements (T = float, or float4 with C counted in vectors); channel fastest ->
     // both sides move contiguous C-runs
-    const int64_t nodes = H * W * (dims == 3 ? D : 1);
-    const int64_t total = B * nodes * C;
-    const int64_t pw = W / P, pd = (dims == 3) ? D / P : 1;
-    const int64_t pv = (dims == 3) ? P * P * P : P * P;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t c = i % C;
-        int64_t r = i / C;
-        const int64_t pin = r % pv; r /= pv;          // position inside the patch
-        const int64_t t = r % (nodes / pv);            // token
-        const int64_t b = r / (nodes / pv);
-        int64_t node;
+    const IDX B = (IDX)B_, H = (IDX)H_, W = (IDX)W_, D = (IDX)D_, P = (IDX)P_, C = (IDX)C_;
+    const IDX nodes = H * W * (dims == 3 ? D : 1);
+    const IDX total = B * nodes * C;
+    const IDX pw = W / P, pd = (dims == 3) ? D / P : 1;
+    const IDX pv = (dims == 3) ? P * P * P : P * P;
+    const IDX ntok = nodes / pv;
+    for (IDX i = (IDX)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (IDX)gridDim.x * blockDim.x) {
+        const IDX c = i % C;
+        IDX r = i / C;
+        const IDX pin = r % pv; r /= pv;             // position inside the patch
+        const IDX t = r % ntok;                        // token
+        const IDX b = r / ntok;
+        IDX node;
         if (dims == 2) {
-            const int64_t ti = t / pw, tj = t % pw, pi = pin / P, pj = pin % P;
+            const IDX ti = t / pw, tj = t % pw, pi = pin / P, pj = pin % P;
             node = (ti * P + pi) * W + (tj * P + pj);
         } else {
-            const int64_t tk = t % pd, tj = (t / pd) % pw, ti = t / (pd * pw);
-            const int64_t pk = pin % P, pj = (pin / P) % P, pi = pin / (P * P);
+            const IDX tk = t % pd, tj = (t / pd) % pw, ti = t / (pd * pw);
+            const IDX pk = pin % P, pj = (pin / P) % P, pi = pin / (P * P);
             node = ((ti * P + pi) * W + (tj * P + pj)) * D + (tk * P + pk);
         }
-        const int64_t g = (b * nodes + node) * C + c;
+        const IDX g = (b * nodes + node) * C + c;
         if (to_tokens) out[i] = in[g]; else out[g] = in[i];
     }
 }
@@ -882,11 +886,19 @@ GAOT_API int gaot_patch_permute(const float* in, float* out, int64_t B, int dims
     if (!in || !out || B < 1 || (dims != 2 && dims != 3) || P < 1 || C < 1) return GAOT_E_BADARG;
     if (H % P || W % P || (dims == 3 && D % P)) return GAOT_E_BADARG;
     const int64_t total = B * H * W * (dims == 3 ? D : 1) * C;
-    if (C % 4 == 0 && !(reinterpret_cast<uintptr_t>(in) & 15) && !(reinterpret_cast<uintptr_t>(out) & 15))
-        patch_permute_kernel<float4><<<gaot_grid(total / 4, 256), 256, 0, (cudaStream_t)stream>>>(
-            reinterpret_cast<const float4*>(in), reinterpret_cast<float4*>(out), B, dims, H, W, D, P, C / 4, to_tokens);
-    else
-        patch_permute_kernel<float><<<gaot_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(in, out, B, dims, H, W, D, P, C, to_tokens);
+    const bool small = total < 0x7fffffffLL;           // 32-bit index arithmetic (grid-stride loop counter included)
+    if (C % 4 == 0 && !(reinterpret_cast<uintptr_t>(in) & 15) && !(reinterpret_cast<uintptr_t>(out) & 15)) {
+        if (small)
+            patch_permute_kernel<float4, uint32_t><<<gaot_grid(total / 4, 256), 256, 0, (cudaStream_t)stream>>>(
+                reinterpret_cast<const float4*>(in), reinterpret_cast<float4*>(out), B, dims, H, W, D, P, C / 4, to_tokens);
+        else
+            patch_permute_kernel<float4, int64_t><<<gaot_grid(total / 4, 256), 256, 0, (cudaStream_t)stream>>>(
+                reinterpret_cast<const float4*>(in), reinterpret_cast<float4*>(out), B, dims, H, W, D, P, C / 4, to_tokens);
+    } else if (small) {
+        patch_permute_kernel<float, uint32_t><<<gaot_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(in, out, B, dims, H, W, D, P, C, to_tokens);
+    } else {
+        patch_permute_kernel<float, int64_t><<<gaot_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(in, out, B, dims, H, W, D, P, C, to_tokens);
+    }
     GAOT_RETURN_LAST();
 }
 
