@@ -255,3 +255,29 @@ def test_bf16_mode_wiring_close_to_reference():
     assert rel_l2(out, g["out"]) < 2e-2
     for k, p in model.named_parameters():
         assert rel_l2(p.grad, g["grad." + k]) < 6e-2, k
+
+
+def test_prepared_weights_are_used_once_and_never_outlive_a_forward():
+    """ops.prepare_weight registers the bf16 copy of a weight for the next tensor-core linear on that very tensor object
+    (GAOT.forward prepares the processor's weights on a side stream); clear_prepared() drops every entry."""
+    with abi_emulator.install() as calls:
+        from gaot_b200 import ops
+        ops.set_precision("bf16")
+        try:
+            x, W = cases.normal((64, 32), 51), torch.nn.Parameter(cases.normal((16, 32), 52))
+            y_ref = ops.linear(x, W, tc=True)
+            n_cast = calls.count("gaot_cast_bf16")
+            ops.prepare_weight(W)
+            assert calls.count("gaot_cast_bf16") == n_cast + 1
+            y = ops.linear(x, W, tc=True)                          # casts x only: the weight's bf16 copy is the prepared one
+            assert calls.count("gaot_cast_bf16") == n_cast + 2
+            assert torch.equal(y, y_ref)
+            y.sum().backward()                                     # the prepared copy also serves dX in the backward
+            assert W.grad is not None
+            ops.clear_prepared()
+            n_now = calls.count("gaot_cast_bf16")
+            ops.linear(x, W, tc=True)
+            assert calls.count("gaot_cast_bf16") == n_now + 2      # x and W again
+        finally:
+            ops.clear_prepared()
+            ops.set_precision("fp32")
