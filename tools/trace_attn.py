@@ -14,11 +14,15 @@ torch.cuda.synchronize()
 L = ctypes.CDLL(_lib.LIB_PATH)
 buf = (ctypes.c_longlong * (64 * 128))()
 print("rc", L.gaot_debug_trace(buf))
-for z in (0, 31):
-    for name, off in (("group A (warp 2)", 0), ("group B (warp 10)", 64)):
-        c = [buf[z * 128 + off + k] for k in range(64)]
-        t0 = buf[z * 128]
-        print(f"CTA z={z} {name}: alloc {c[1]-t0}, end {c[62]-t0}")
-        for i in range(8):
-            a = [c[2 + 6 * i + k] - t0 for k in range(6)]
-            print(f"  step {i}: top {a[0]} st_full+{a[1]-a[0]} ld+free+{a[2]-a[1]} done-wait+{a[3]-a[2]} emit+{a[4]-a[3]} drain+{a[5]-a[4]}")
+for z in (0, 5, 31):
+    c = [buf[z * 128 + k] for k in range(64)]            # compute warp (first compute warp of the CTA), 6 slots per step
+    m = [buf[z * 128 + 64 + k] for k in range(64)]       # MMA warp, 4 slots per step
+    t0 = c[0]
+    print(f"CTA z={z}: start->alloc {c[1]-t0}, end {c[62]-t0}, after dealloc {c[63]-t0}")
+    for i in range(8):
+        a = [c[2 + 6 * i + k] - t0 for k in range(6)]
+        print(f"  step {i}: top {a[0]} st_full+{a[1]-a[0]} ld+free+{a[2]-a[1]} done-wait+{a[3]-a[2]} emit+{a[4]-a[3]} drain+{a[5]-a[4]}")
+    print("  final", c[2 + 48] - t0)
+    for i in range(7):
+        a = [m[2 + 4 * i + k] - t0 for k in range(4)]
+        print(f"  mma {i}: top {a[0]} st_free-wait+{a[1]-a[0]} issueST+{a[2]-a[1]} pds/dq wait+{a[3]-a[2]}")
