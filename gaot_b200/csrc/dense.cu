@@ -737,17 +737,24 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
     }
 }
 
-__global__ void rollout_kernel(const float* __restrict__ pred, const float* __restrict__ u_in, float* __restrict__ u_next,
-                               int64_t rows, int C, float dt, int mode, const float* __restrict__ um,
+// Rollout update (gaot.py:436-476 + 431-434): u_phys = the de-normalised prediction of the step (what the reference returns),
+// u_next = (u_phys - u_mean) / u_std, the normalised state carried into the next step.
+__global__ void rollout_kernel(const float* __restrict__ pred, const float* __restrict__ u_in, float* __restrict__ u_phys,
+                               float* __restrict__ u_next, int64_t rows, int C, float dt, int mode, const float* __restrict__ um,
                                const float* __restrict__ us, const float* __restrict__ sm, const float* __restrict__ ss) {
     const int64_t total = rows * C;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int c = (int)(i % C);
-        if (mode == 0) { u_next[i] = pred[i]; continue; }
-        const float ucur = u_in[i] * us[c] + um[c];
-        const float inc = pred[i] * ss[c] + sm[c];
-        const float un = ucur + (mode == 2 ? dt * inc : inc);
-        u_next[i] = (un - um[c]) / us[c];
+        float un;
+        if (mode == 0) {
+            un = pred[i] * us[c] + um[c];
+        } else {
+            const float ucur = u_in[i] * us[c] + um[c];
+            const float inc = pred[i] * ss[c] + sm[c];
+            un = ucur + (mode == 2 ? dt * inc : inc);
+        }
+        u_phys[i] = un;
+        if (u_next) u_next[i] = (un - um[c]) / us[c];
     }
 }
 
@@ -923,13 +930,13 @@ GAOT_API int gaot_adamw_step(float* param, const float* grad, float* exp_avg, fl
     GAOT_RETURN_LAST();
 }
 
-GAOT_API int gaot_rollout_update(const float* pred, const float* u_in, float* u_next, int64_t rows, int64_t C, float dt,
-                                 int mode, const float* u_mean, const float* u_std, const float* s_mean,
+GAOT_API int gaot_rollout_update(const float* pred, const float* u_in, float* u_phys, float* u_next, int64_t rows, int64_t C,
+                                 float dt, int mode, const float* u_mean, const float* u_std, const float* s_mean,
                                  const float* s_std, void* stream) {
-    if (!pred || !u_next || rows < 0 || C < 1 || mode < 0 || mode > 2) return GAOT_E_BADARG;
-    if (mode != 0 && (!u_in || !u_mean || !u_std || !s_mean || !s_std)) return GAOT_E_BADARG;
+    if (!pred || !u_phys || rows < 0 || C < 1 || mode < 0 || mode > 2 || !u_mean || !u_std) return GAOT_E_BADARG;
+    if (mode != 0 && (!u_in || !s_mean || !s_std)) return GAOT_E_BADARG;
     if (rows == 0) return 0;
-    rollout_kernel<<<gaot_grid(rows * C, 256), 256, 0, (cudaStream_t)stream>>>(pred, u_in, u_next, rows, (int)C, dt, mode,
+    rollout_kernel<<<gaot_grid(rows * C, 256), 256, 0, (cudaStream_t)stream>>>(pred, u_in, u_phys, u_next, rows, (int)C, dt, mode,
                                                                                u_mean, u_std, s_mean, s_std);
     GAOT_RETURN_LAST();
 }

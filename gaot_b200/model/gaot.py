@@ -132,26 +132,31 @@ class GAOT(nn.Module):
     @torch.no_grad()
     def autoregressive_predict(self, x_batch, time_indices, t_values, stats, stepper_mode="output",
                                latent_tokens_coord=None, fixed_coord=None, encoder_nbrs=None, decoder_nbrs=None,
-                               c_batch=None, use_cuda_graph=False, use_conditional_norm=False):
-        """gaot.py:307-434 (fx mode): x_batch [B,N,u_dim] normalised initial state, optional conditioning
-        channels c_batch [B,N,c]; returns [B, len(time_indices)-1, N, u_dim] normalised predictions.
-        stats = {"u": {mean,std}, "res": {...}, "der": {...}, "start_time": {...}, "time_diffs": {...}} of
-        per-channel tensors / floats as the reference's sequential trainer supplies them.  With use_conditional_norm the
-        last input channel (the time difference) is not fed to the encoder and the conditioning value is
-        x_input[..., 0, -2:-1], exactly as gaot.py:392-408 does."""
+                               use_conditional_norm=False, use_cuda_graph=False):
+        """gaot.py:307-434, same arguments in the same order (use_cuda_graph is the one addition).
+        x_batch [B,N,>=u_dim+c_dim]: normalised initial state in the first u_dim = len(stats["u"]["mean"]) channels, static
+        conditioning channels next when stats has a "c" entry (gaot.py:349-358); anything after them (the time channels of a
+        dataset sample) is ignored, as in the reference.  Returns the DE-NORMALISED predictions
+        [B, len(time_indices)-1, N, u_dim] (gaot.py:425-434); only the carried state is re-normalised.
+        stats = {"u": {mean,std}, "res": {...}, "der": {...}, "c": {...}?, "start_time": {...}, "time_diffs": {...}} as the
+        reference's sequential trainer supplies them.  With use_conditional_norm the last input channel (the time difference) is
+        not fed to the encoder and the conditioning value is x_input[..., 0, -2:-1], exactly as gaot.py:392-408 does."""
+        if stepper_mode not in ("output", "residual", "time_der"):
+            raise ValueError(f"Unsupported stepper_mode: {stepper_mode}")
         dev = x_batch.device
-        B, N, U = x_batch.shape
-        cur = x_batch
+        B, N, _ = x_batch.shape
+        U = int(torch.as_tensor(stats["u"]["mean"]).numel())
+        nc = int(torch.as_tensor(stats["c"]["mean"]).numel()) if "c" in stats else 0
+        cur = x_batch[..., :U].contiguous().float()
         outs = []
         mode = {"output": 0, "residual": 1, "time_der": 2}[stepper_mode]
         t = lambda v: torch.as_tensor(v, dtype=torch.float32, device=dev).reshape(-1).expand(U).contiguous()  # noqa: E731
         um, us = t(stats["u"]["mean"]), t(stats["u"]["std"])
         skey = {1: "res", 2: "der"}.get(mode)
         sm, ss = (t(stats[skey]["mean"]), t(stats[skey]["std"])) if skey else (um, us)
-        nc = 0 if c_batch is None else c_batch.shape[-1]
         x_in = torch.empty((B, N, U + nc + 2), dtype=torch.float32, device=dev)     # static step input [u | c | t0 | dt]
-        if c_batch is not None:
-            x_in[..., U:U + nc] = c_batch
+        if nc:
+            x_in[..., U:U + nc] = x_batch[..., U:U + nc]
         graph = pred_static = None
 
         def fwd():
@@ -184,6 +189,6 @@ class GAOT(nn.Module):
                 pred = pred_static
             else:
                 pred = fwd()
-            cur = ops.rollout_update(pred, cur, dt, mode, um, us, sm, ss)
-            outs.append(cur)
+            phys, cur = ops.rollout_update(pred, cur, dt, mode, um, us, sm, ss)
+            outs.append(phys)
         return torch.stack(outs, dim=1)

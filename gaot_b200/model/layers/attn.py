@@ -40,6 +40,9 @@ class TransformerConfig:
     attn_config: AttentionConfig = field(default_factory=AttentionConfig)
 
 
+SUPPORTED_HEAD_DIMS = (16, 32, 64)          # template instances of csrc/attn.cu and csrc/attn_tc.cu
+
+
 class RMSNorm(nn.Module):
     def __init__(self, dim: int, eps: float = 1e-6):
         super().__init__()
@@ -69,6 +72,9 @@ class GroupQueryFlashAttention(nn.Module):
         self.num_heads, self.num_kv_heads = num_heads, num_kv_heads
         self.num_repeat = num_heads // num_kv_heads
         self.head_dim = hidden_size // num_heads
+        if self.head_dim not in SUPPORTED_HEAD_DIMS:
+            raise ValueError(f"head_dim = hidden_size / num_heads = {hidden_size} / {num_heads} = {self.head_dim} is not "
+                             f"instantiated in the attention kernels; supported: {SUPPORTED_HEAD_DIMS}")
         kv = self.head_dim * num_kv_heads
         self.q_proj = nn.Linear(input_size, hidden_size, bias=False)
         self.k_proj = nn.Linear(input_size, kv, bias=False)
@@ -147,7 +153,8 @@ class TransformerBlock(nn.Module):
         if skip_connection:
             self.skip_proj = nn.Linear(input_size * 2, input_size)
 
-    def forward(self, x, skip=None, condition=None, relative_positions=None):
+    def forward(self, x, condition=None, relative_positions=None, skip=None):
+        """Positional order as the reference (attn.py:208): (x, condition, relative_positions, skip)."""
         if self.skip_connection and skip is not None:
             B, T, D = x.shape
             W = self.skip_proj.weight                                    # [D, 2D] acting on cat[x, skip] (attn.py:225-227)

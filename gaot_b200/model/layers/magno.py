@@ -192,7 +192,10 @@ class MAGNOEncoder(_MAGNOBase):
         M = latent_tokens_coord.shape[0]
         Wl, bl = self.lifting.fcs[0].weight[:, :, 0], self.lifting.fcs[0].bias
         C, Cin = Wl.shape
-        fuse = self.fuse_affine and Cin <= ops.FUSE_MAX_CIN and C % 4 == 0 and C <= ops.FUSE_MAX_C
+        # the fused lift+gather kernel produces no gradient for its raw inputs (they are data at every BASELINE config);
+        # when something upstream does need d/d pndata the unfused lifting + aggregate path propagates it
+        fuse = (self.fuse_affine and Cin <= ops.FUSE_MAX_CIN and C % 4 == 0 and C <= ops.FUSE_MAX_C
+                and not (pndata.requires_grad and torch.is_grad_enabled()))
         lift = (Wl, bl) if fuse else None
         f = pndata if fuse else self.lifting(pndata)                      # [B,N,C]  (magno.py:273-274)
         Cf = f.shape[-1]

@@ -704,6 +704,9 @@ class _LiftAggregate(torch.autograd.Function):
     def backward(ctx, g):
         pn, Wl, bl, w = ctx.saved_tensors
         plan = ctx.plan
+        if ctx.needs_input_grad[0]:
+            raise _lib.GaotLibraryError("lift_aggregate has no gradient for its raw inputs; use the unfused lifting + "
+                                        "agno_aggregate path (MAGNOEncoder does when pndata.requires_grad)")
         g = _c(g)
         B, Ns, Cin = pn.shape
         C = Wl.shape[0]
@@ -821,10 +824,12 @@ def adamw_step(param, grad, exp_avg, exp_avg_sq, step, lr, betas=(0.9, 0.999), e
 
 
 def rollout_update(pred, u_in, dt, mode, u_mean, u_std, s_mean, s_std):
+    """(u_phys, u_next): the de-normalised prediction of the step (what the reference returns, gaot.py:425-430, 436-476)
+    and the re-normalised state carried into the next step (gaot.py:433)."""
     pred = _c(pred)
     u_in = _c(u_in) if u_in is not None else None
     C = pred.shape[-1]
-    out = torch.empty_like(pred)
-    call("gaot_rollout_update", ptr(pred), ptr(u_in), ptr(out), pred.numel() // C, C,
+    phys, nxt = torch.empty_like(pred), torch.empty_like(pred)
+    call("gaot_rollout_update", ptr(pred), ptr(u_in), ptr(phys), ptr(nxt), pred.numel() // C, C,
          float(dt), int(mode), ptr(u_mean), ptr(u_std), ptr(s_mean), ptr(s_std))
-    return out
+    return phys, nxt

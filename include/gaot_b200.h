@@ -260,9 +260,11 @@ int gaot_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_
                     float lr, float beta1, float beta2, float eps, float weight_decay,
                     int64_t step, float grad_scale, void* stream);
 
-/* Rollout update rule of GAOT._process_autoregressive_prediction (src/model/gaot.py:436-476).
- * mode 0 output, 1 residual, 2 time_der.  All tensors [rows, C]; stats are per channel [C]. */
-int gaot_rollout_update(const float* pred, const float* u_in, float* u_next, int64_t rows, int64_t C,
+/* Rollout update rule of GAOT._process_autoregressive_prediction (src/model/gaot.py:436-476) and the state carry of
+ * src/model/gaot.py:431-434.  mode 0 output, 1 residual, 2 time_der.  All tensors [rows, C]; stats are per channel [C].
+ * u_phys = the de-normalised prediction (the value the reference appends and returns); u_next (optional) =
+ * (u_phys - u_mean) / u_std, the normalised state fed to the next step.  u_in / s_mean / s_std are unused in mode 0. */
+int gaot_rollout_update(const float* pred, const float* u_in, float* u_phys, float* u_next, int64_t rows, int64_t C,
                         float dt, int mode, const float* u_mean, const float* u_std,
                         const float* s_mean, const float* s_std, void* stream);
 

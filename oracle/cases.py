@@ -99,6 +99,25 @@ CASES = {
 }
 
 
+# autoregressive rollout fixture (gaot.py:307-476): tiny2d geometry, u(3) + c(1) + t0 + dt input channels, all stepper modes
+ROLLOUT = dict(base="tiny2d", u_dim=3, c_dim=1, B=2, seed=31, time_indices=[0, 2, 3, 6, 7], n_times=11)
+
+
+def rollout_case():
+    """(case dict, x_batch [B,N,u+c], t_values, stats) for the rollout fixture; stats in the layout the reference's
+    sequential trainer passes (per-channel tensors for u / res / der / c, floats for the time statistics)."""
+    r = ROLLOUT
+    c = dict(CASES[r["base"]], cin=r["u_dim"] + r["c_dim"] + 2, cout=r["u_dim"], B=r["B"])
+    x0 = normal((r["B"], c["n"], r["u_dim"] + r["c_dim"]), r["seed"])
+    tv = torch.linspace(0, 1, r["n_times"])
+    stats = {"u": {"mean": torch.tensor([0.1, 0.2, 0.3]), "std": torch.tensor([1.1, 0.9, 1.2])},
+             "c": {"mean": torch.tensor([0.4]), "std": torch.tensor([2.0])},
+             "der": {"mean": torch.tensor([0.0, 0.1, -0.1]), "std": torch.tensor([0.5, 0.6, 0.7])},
+             "res": {"mean": torch.tensor([0.05, -0.1, 0.2]), "std": torch.tensor([0.3, 0.4, 0.2])},
+             "start_time": {"mean": 0.5, "std": 0.3}, "time_diffs": {"mean": 0.1, "std": 0.05}}
+    return c, x0, tv, stats
+
+
 def case_inputs(name: str):
     c = CASES[name]
     lat = latent_grid(c["latent"])

@@ -478,19 +478,47 @@ def adamw_step(params, grads, m, v, step, lr, beta1=0.9, beta2=0.999, eps=1e-8, 
 # --------------------------------------------------------------------------------------------
 
 def rollout_update(pred, u_in_norm, dt, stats, stepper_mode):
-    """GAOT._process_autoregressive_prediction (gaot.py:436-476): de-normalise by stepper mode, then
-    re-normalise the new state with the u stats."""
+    """GAOT._process_autoregressive_prediction (gaot.py:436-476) and the state carry of gaot.py:425-434.
+    Returns (pred_denorm, next_state): pred_denorm is what the reference appends to its output list (physical units);
+    next_state = (pred_denorm - u_mean) / u_std is the normalised state fed to the next step (gaot.py:433)."""
     u_mean, u_std = stats["u"]["mean"], stats["u"]["std"]
     if stepper_mode == "output":
-        return pred
-    u_cur = u_in_norm * u_std + u_mean
-    if stepper_mode == "residual":
-        u_next = u_cur + (pred * stats["res"]["std"] + stats["res"]["mean"])
+        u_next = pred * u_std + u_mean
+    elif stepper_mode == "residual":
+        u_next = (u_in_norm * u_std + u_mean) + (pred * stats["res"]["std"] + stats["res"]["mean"])
     elif stepper_mode == "time_der":
-        u_next = u_cur + dt * (pred * stats["der"]["std"] + stats["der"]["mean"])
+        u_next = (u_in_norm * u_std + u_mean) + dt * (pred * stats["der"]["std"] + stats["der"]["mean"])
     else:
-        raise ValueError(stepper_mode)
-    return (u_next - u_mean) / u_std
+        raise ValueError(f"Unsupported stepper_mode: {stepper_mode}")
+    return u_next, (u_next - u_mean) / u_std
+
+
+def autoregressive_predict(params, cfg, x_batch, time_indices, t_values, stats, stepper_mode, latent, coord,
+                           use_conditional_norm=False):
+    """GAOT.autoregressive_predict (gaot.py:307-434), fx mode: returns the DE-NORMALISED predictions
+    [B, len(time_indices)-1, N, u_dim]; x_batch carries [u | c | ...] channels, c present iff "c" in stats."""
+    B, N, _ = x_batch.shape
+    u_dim = stats["u"]["mean"].shape[0]
+    c_dim = stats["c"]["mean"].shape[0] if "c" in stats else 0
+    c_feat = x_batch[..., u_dim:u_dim + c_dim] if c_dim > 0 else None
+    cur = x_batch[..., :u_dim]
+    outs = []
+    for i in range(1, len(time_indices)):
+        t0 = float(t_values[time_indices[i - 1]])
+        dt = float(t_values[time_indices[i]]) - t0
+        t0n = (t0 - stats["start_time"]["mean"]) / stats["start_time"]["std"]
+        dtn = (dt - stats["time_diffs"]["mean"]) / stats["time_diffs"]["std"]
+        feats = [cur] + ([c_feat] if c_feat is not None else [])
+        feats += [torch.full((B, N, 1), t0n, dtype=x_batch.dtype), torch.full((B, N, 1), dtn, dtype=x_batch.dtype)]
+        x_in = torch.cat(feats, dim=-1)
+        with torch.no_grad():
+            if use_conditional_norm:
+                pred = gaot_forward(params, cfg, latent, coord, x_in[..., :-1], None, None, None, x_in[..., 0, -2:-1])
+            else:
+                pred = gaot_forward(params, cfg, latent, coord, x_in)
+        phys, cur = rollout_update(pred, cur, dt, stats, stepper_mode)
+        outs.append(phys)
+    return torch.stack(outs, dim=1)
 
 
 # --------------------------------------------------------------------------------------------

@@ -142,9 +142,47 @@ def graph_arrays(graphs, vx):
     return out
 
 
+def rollout_golden():
+    """Reference GAOT.autoregressive_predict (gaot.py:307-476) in fp64 on the rollout fixture, every stepper mode;
+    the oracle's restatement must match it to 1e-10."""
+    c, x0, tv, stats = cases.rollout_case()
+    torch.set_default_dtype(torch.float64)
+    try:
+        torch.manual_seed(42)
+        model = GAOT(c["cin"], c["cout"], ref_config(c)).eval()
+        shapes = {k: list(v.shape) for k, v in model.state_dict().items()}
+        params = cases.synth_params(shapes, 7 + cases.ROLLOUT["seed"])
+        model.load_state_dict({k: v.double() for k, v in params.items()})
+        lat, x, _, _ = cases.case_inputs(cases.ROLLOUT["base"])
+        st64 = {k: {kk: (vv.double() if torch.is_tensor(vv) else vv) for kk, vv in v.items()} for k, v in stats.items()}
+        cfg = orc.make_config(c["latent"], c["magno"], c["transformer"], c["attn"])
+        arrs = {"keys": np.array(list(shapes.keys())), "shapes": np.array([",".join(map(str, s)) for s in shapes.values()])}
+        for k, v in params.items():
+            arrs["param." + k] = v.numpy().astype(np.float32)
+        ti = np.array(cases.ROLLOUT["time_indices"])
+        for mode in ("output", "residual", "time_der"):
+            # a dataset sample also carries its own time channels after [u | c]; the reference ignores them
+            xb = torch.cat([x0.double(), torch.zeros(x0.shape[0], x0.shape[1], 2, dtype=torch.float64)], -1)
+            ref = model.autoregressive_predict(xb, ti, tv.double().numpy(), st64, stepper_mode=mode,
+                                               latent_tokens_coord=lat.double(), fixed_coord=x.double())
+            mine = orc.autoregressive_predict({k: v.double() for k, v in params.items()}, cfg, xb, ti, tv.double(), st64, mode,
+                                              lat.double(), x.double())
+            e = rel(mine, ref)
+            print(f"[rollout {mode}] oracle-vs-reference fp64: {e:.2e}, |pred| {float(ref.norm()):.3f}")
+            assert e < 1e-10
+            arrs["pred." + mode] = ref.numpy().astype(np.float32)
+        np.savez_compressed(os.path.join(OUT, "rollout.npz"), **arrs)
+    finally:
+        torch.set_default_dtype(torch.float32)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     only = sys.argv[1:]                                   # optional: regenerate just these model cases
+    if not only or "rollout" in only:
+        rollout_golden()
+        if only == ["rollout"]:
+            return
     for name, c in cases.CASES.items():
         if only and name not in only:
             continue

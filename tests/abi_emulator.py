@@ -481,14 +481,18 @@ def gaot_adamw_step(param, grad, m, v, n, lr, b1, b2, eps, wd, step, gscale):
     mm[:], vv[:] = m2.astype(np.float32), v2.astype(np.float32)
 
 
-def gaot_rollout_update(pred, u_in, u_next, rows, C, dt, mode, um, us, sm, ss):
+def gaot_rollout_update(pred, u_in, u_phys, u_next, rows, C, dt, mode, um, us, sm, ss):
     P = _arr(pred, (rows, C)).astype(np.float64)
+    m_, s_ = _arr(um, (C,)).astype(np.float64), _arr(us, (C,)).astype(np.float64)
     if mode == 0:
-        _arr(u_next, (rows, C))[:] = P.astype(np.float32)
-        return
-    ucur = _arr(u_in, (rows, C)) * _arr(us, (C,)) + _arr(um, (C,))
-    inc = P * _arr(ss, (C,)) + _arr(sm, (C,))
-    _arr(u_next, (rows, C))[:] = ((ucur + (dt * inc if mode == 2 else inc) - _arr(um, (C,))) / _arr(us, (C,))).astype(np.float32)
+        un = P * s_ + m_
+    else:
+        ucur = _arr(u_in, (rows, C)) * s_ + m_
+        inc = P * _arr(ss, (C,)) + _arr(sm, (C,))
+        un = ucur + (dt * inc if mode == 2 else inc)
+    _arr(u_phys, (rows, C))[:] = un.astype(np.float32)
+    if u_next:
+        _arr(u_next, (rows, C))[:] = ((un - m_) / s_).astype(np.float32)
 
 
 _TABLE = {k: v for k, v in list(globals().items()) if k.startswith("gaot_")}

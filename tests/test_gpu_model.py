@@ -136,7 +136,8 @@ def test_train_steps_match_oracle_adamw():
 
 @pytest.mark.parametrize("use_graph", [False, True])
 def test_autoregressive_rollout_matches_oracle(use_graph):
-    """10-step no-grad rollout (gaot.py:365-476, stepper 'time_der') vs the oracle's forward + update rule in fp64."""
+    """10-step no-grad rollout (gaot.py:307-476, stepper 'time_der') vs the oracle's restatement in fp64; the return value
+    is the de-normalised prediction of every step."""
     c = dict(cases.CASES["tiny2d"], cin=5, cout=3)       # u(3) + t0 + dt
     torch.manual_seed(0)
     model = build_model(c).eval()
@@ -151,16 +152,25 @@ def test_autoregressive_rollout_matches_oracle(use_graph):
                                        fixed_coord=x.to(DEV), use_cuda_graph=use_graph)
     cfg = orc.make_config(c["latent"], c["magno"], c["transformer"], c["attn"])
     p = {k: v.detach().double().cpu() for k, v in model.state_dict().items()}
-    cur = u0.double()
     st64 = {k: ({kk: (vv.double() if torch.is_tensor(vv) else vv) for kk, vv in v.items()}) for k, v in stats.items()}
-    with torch.no_grad():
-        for i in range(10):
-            t0, dt = float(tv[i]), float(tv[i + 1] - tv[i])
-            inp = torch.cat([cur, torch.full((2, 300, 1), (t0 - 0.5) / 0.3, dtype=torch.float64),
-                             torch.full((2, 300, 1), (dt - 0.1) / 0.05, dtype=torch.float64)], -1)
-            pred = orc.gaot_forward(p, cfg, lat.double(), x.double(), inp)
-            cur = orc.rollout_update(pred, cur, dt, st64, "time_der")
-            assert rel_l2(got[:, i], cur) < 2e-5, i          # errors compound over the 10 autoregressive steps
+    want = orc.autoregressive_predict(p, cfg, u0.double(), idx, tv.double(), st64, "time_der", lat.double(), x.double())
+    for i in range(10):
+        assert rel_l2(got[:, i], want[:, i]) < 2e-5, i          # errors compound over the 10 autoregressive steps
+
+
+@pytest.mark.parametrize("mode", ["output", "residual", "time_der"])
+def test_rollout_matches_reference_golden_gpu(mode):
+    """CUDA rollout vs the reference's own GAOT.autoregressive_predict output (tests/golden/rollout.npz)."""
+    c, x0, tv, stats = cases.rollout_case()
+    g = load_golden("rollout")
+    model = build_model(c).eval()
+    model.load_state_dict({k: v.to(DEV) for k, v in golden_params(g).items()})
+    lat, x, _, _ = cases.case_inputs(cases.ROLLOUT["base"])
+    got = model.autoregressive_predict(x0.to(DEV), cases.ROLLOUT["time_indices"], tv, stats, mode,
+                                       latent_tokens_coord=lat.to(DEV), fixed_coord=x.to(DEV))
+    want = torch.from_numpy(g["pred." + mode])
+    for i in range(want.shape[1]):
+        assert rel_l2(got[:, i], want[:, i]) < 1e-5, (mode, i)
 
 
 def test_input_prefetcher_feeds_static_buffers():

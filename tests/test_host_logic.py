@@ -106,6 +106,115 @@ def test_error_conventions_match_reference():
         MAGNOConfig(sampling_strategy="ratio")
 
 
+def _rand_csr(m, n_src, max_deg, seed):
+    g = torch.Generator().manual_seed(seed)
+    deg = torch.randint(0, max_deg + 1, (m,), generator=g)
+    rs = torch.zeros(m + 1, dtype=torch.int64)
+    rs[1:] = torch.cumsum(deg, 0)
+    # ascending distinct sources inside a row (what the radius search produces)
+    idx = torch.cat([torch.sort(torch.randperm(n_src, generator=g)[:int(d)]).values for d in deg]) if int(rs[-1]) else \
+        torch.zeros(0, dtype=torch.int64)
+    return {"neighbors_index": idx, "neighbors_row_splits": rs}
+
+
+def _check_sub_csr(out, src):
+    """`out` is a valid CSR whose every row is an order-preserving subset of the same row of `src`."""
+    rs, ro = src["neighbors_row_splits"], out["neighbors_row_splits"]
+    assert ro.shape == rs.shape and int(ro[0]) == 0 and int(ro[-1]) == out["neighbors_index"].numel()
+    assert bool((ro[1:] >= ro[:-1]).all())
+    for r in range(rs.numel() - 1):
+        full = src["neighbors_index"][rs[r]:rs[r + 1]].tolist()
+        sub = out["neighbors_index"][ro[r]:ro[r + 1]].tolist()
+        it = iter(full)
+        assert all(any(a == b for b in it) for a in sub), r       # subsequence test
+
+
+def test_edge_drop_identity_cases_follow_the_reference():
+    """edge_drop.py:38-42, 55-56, 71-72, 79-80, 98-99: every early return hands back the SAME dict."""
+    from gaot_b200.model.layers.utils.edge_drop import apply_edge_drop_csr as drop
+    g = _rand_csr(50, 40, 9, 0)
+    assert drop(g, None) is g
+    assert drop(g, "ratio", sample_ratio=0.5, training=False) is g
+    assert drop(g, "ratio", sample_ratio=None) is g
+    assert drop(g, "ratio", sample_ratio=1.0) is g
+    assert drop(g, "max_neighbors", max_neighbors=None) is g
+    assert drop(g, "max_neighbors", max_neighbors=9) is g            # no row above the cap
+    assert drop(g, "something_else") is g
+    empty = {"neighbors_index": torch.zeros(0, dtype=torch.int64), "neighbors_row_splits": torch.zeros(6, dtype=torch.int64)}
+    assert drop(empty, "ratio", sample_ratio=0.5) is empty
+    bad = {"neighbors_index": g["neighbors_index"], "neighbors_row_splits": g["neighbors_row_splits"].flip(0)}
+    with pytest.raises(ValueError):
+        drop(bad, "ratio", sample_ratio=0.5)
+    with pytest.raises(ValueError):
+        drop(bad, "max_neighbors", max_neighbors=2)
+
+
+def test_edge_drop_ratio_sampling_statistics():
+    """edge_drop.py:50-68: i.i.d. Bernoulli(sample_ratio) per edge; result is a valid sub-CSR."""
+    from gaot_b200.model.layers.utils.edge_drop import apply_edge_drop_csr as drop
+    g = _rand_csr(400, 300, 40, 1)
+    E = g["neighbors_index"].numel()
+    torch.manual_seed(0)
+    out = drop(g, "ratio", sample_ratio=0.3)
+    _check_sub_csr(out, g)
+    kept = out["neighbors_index"].numel()
+    assert abs(kept - 0.3 * E) < 5 * (0.3 * 0.7 * E) ** 0.5           # 5 sigma of Binomial(E, 0.3)
+    assert out["neighbors_row_splits"].dtype == g["neighbors_row_splits"].dtype
+
+
+def test_edge_drop_max_neighbors_cap_and_uniformity():
+    """edge_drop.py:70-97: rows above the cap keep EXACTLY max_neighbors edges, a uniformly random subset; other rows are
+    untouched.  Uniformity: over many draws every edge of an over-full row is kept with frequency cap/deg - also for a
+    row index large enough that a fp32 `rand + 2*row` key would lose its random bits (the round-1 bug)."""
+    from gaot_b200.model.layers.utils.edge_drop import apply_edge_drop_csr as drop
+    g = _rand_csr(300, 200, 30, 2)
+    torch.manual_seed(1)
+    out = drop(g, "max_neighbors", max_neighbors=7)
+    _check_sub_csr(out, g)
+    deg = g["neighbors_row_splits"][1:] - g["neighbors_row_splits"][:-1]
+    deg_o = out["neighbors_row_splits"][1:] - out["neighbors_row_splits"][:-1]
+    assert torch.equal(deg_o, torch.clamp(deg, max=7))
+    rs, ro = g["neighbors_row_splits"], out["neighbors_row_splits"]
+    for r in torch.where(deg <= 7)[0].tolist():
+        assert torch.equal(out["neighbors_index"][ro[r]:ro[r + 1]], g["neighbors_index"][rs[r]:rs[r + 1]])
+    # one over-full row placed at a very large row index: 12 edges, cap 4 -> each edge kept with probability 1/3
+    m = 5_000_000
+    rs_big = torch.zeros(m + 1, dtype=torch.int64)
+    rs_big[m:] = 12
+    big = {"neighbors_index": torch.arange(12), "neighbors_row_splits": rs_big}
+    hits = torch.zeros(12)
+    trials = 150
+    torch.manual_seed(2)
+    for _ in range(trials):
+        o = drop(big, "max_neighbors", max_neighbors=4)
+        assert o["neighbors_index"].numel() == 4
+        hits[o["neighbors_index"]] += 1
+    p = 1.0 / 3.0
+    assert float((hits / trials - p).abs().max()) < 5 * (p * (1 - p) / trials) ** 0.5
+    assert len({tuple(drop(big, "max_neighbors", max_neighbors=4)["neighbors_index"].tolist()) for _ in range(20)}) > 5
+
+
+def test_edge_drop_inside_the_encoder_training_vs_eval():
+    """MAGNO applies the sampling in training mode only (magno.py:279, 309): eval output is deterministic and equals the
+    no-sampling model; training output differs (edges were dropped)."""
+    c = dict(cases.CASES["tiny2d"])
+    c["magno"] = dict(c["magno"], sampling_strategy="ratio", sample_ratio=0.5)
+    g = load_golden("tiny2d")
+    with abi_emulator.install():
+        model = build_model(c, "cpu")
+        model.load_state_dict(golden_params(g))
+        lat, x, pn, _ = cases.case_inputs("tiny2d")
+        model.eval()
+        with torch.no_grad():
+            e1 = model(lat, x, pn)
+        assert rel_l2(e1, g["out"]) < 1e-5                          # eval: sampling off -> the reference golden
+        model.train()
+        torch.manual_seed(3)
+        with torch.no_grad():
+            t1 = model(lat, x, pn)
+        assert rel_l2(t1, g["out"]) > 1e-3
+
+
 def test_train_step_flat_buffers_and_adamw():
     name = "tiny2d"
     c = cases.CASES[name]
@@ -184,27 +293,30 @@ def test_data_parallel_step_equals_single_process_gloo():
 
 
 @pytest.mark.parametrize("mode", ["time_der", "residual", "output"])
-def test_rollout_matches_oracle_update_rules(mode):
-    c = dict(cases.CASES["tiny2d"], cin=5, cout=3)       # u(3) + t0 + dt
+def test_rollout_matches_reference_golden(mode):
+    """GAOT.autoregressive_predict (gaot.py:307-476) through the ABI emulator vs the reference's own fp64 output
+    (tests/golden/rollout.npz): de-normalised predictions are returned, [u | c | ...] input layout with stats['c']."""
+    c, x0, tv, stats = cases.rollout_case()
+    g = load_golden("rollout")
     with abi_emulator.install():
-        torch.manual_seed(0)
         model = build_model(c, "cpu").eval()
-        lat, x, _, _ = cases.case_inputs("tiny2d")
-        u0 = cases.normal((2, 300, 3), 31)
-        stats = {"u": {"mean": torch.tensor([0.1, 0.2, 0.3]), "std": torch.tensor([1.1, 0.9, 1.2])},
-                 "der": {"mean": torch.tensor([0.0, 0.1, -0.1]), "std": torch.tensor([0.5, 0.6, 0.7])},
-                 "res": {"mean": torch.tensor([0.05, -0.1, 0.2]), "std": torch.tensor([0.3, 0.4, 0.2])},
-                 "start_time": {"mean": 0.5, "std": 0.3}, "time_diffs": {"mean": 0.1, "std": 0.05}}
-        tv = torch.linspace(0, 1, 21)
-        got = model.autoregressive_predict(u0, [0, 2, 4], tv, stats, mode, latent_tokens_coord=lat, fixed_coord=x)
-        # oracle: same forward through the emulator, update rule from oracle.rollout_update
-        cur = u0
-        for i, (a, b) in enumerate(((0, 2), (2, 4))):
-            t0, dt = float(tv[a]), float(tv[b] - tv[a])
-            inp = torch.cat([cur, torch.full((2, 300, 1), (t0 - 0.5) / 0.3), torch.full((2, 300, 1), (dt - 0.1) / 0.05)], -1)
-            pred = model(lat, x, inp)
-            cur = orc.rollout_update(pred, cur, dt, stats, mode)
-            assert rel_l2(got[:, i], cur) < 1e-6
+        model.load_state_dict(golden_params(g))
+        lat, x, _, _ = cases.case_inputs(cases.ROLLOUT["base"])
+        xb = torch.cat([x0, torch.zeros(x0.shape[0], x0.shape[1], 2)], -1)      # trailing dataset time channels are ignored
+        got = model.autoregressive_predict(xb, cases.ROLLOUT["time_indices"], tv, stats, mode, latent_tokens_coord=lat,
+                                           fixed_coord=x)
+    want = torch.from_numpy(g["pred." + mode])
+    assert got.shape == want.shape
+    for i in range(want.shape[1]):
+        assert rel_l2(got[:, i], want[:, i]) < 1e-5, (mode, i)
+
+
+def test_rollout_rejects_unknown_stepper_mode():
+    c, x0, tv, stats = cases.rollout_case()
+    with abi_emulator.install():
+        model = build_model(c, "cpu").eval()
+        with pytest.raises(ValueError):
+            model.autoregressive_predict(x0, [0, 1], tv, stats, "euler")
 
 
 def test_rollout_with_conditional_norm_feeds_time_as_condition():
@@ -228,8 +340,8 @@ def test_rollout_with_conditional_norm_feeds_time_as_condition():
             t0n = (t0 - 0.5) / 0.3
             inp = torch.cat([cur, torch.full((3, 300, 1), t0n)], -1)
             pred = model(lat, x, inp, condition=torch.full((3, 1), t0n))
-            cur = orc.rollout_update(pred, cur, dt, stats, "time_der")
-            assert rel_l2(got[:, i], cur) < 1e-6
+            phys, cur = orc.rollout_update(pred, cur, dt, stats, "time_der")
+            assert rel_l2(got[:, i], phys) < 1e-6
 
 
 def test_bf16_mode_wiring_close_to_reference():

@@ -112,3 +112,18 @@ def test_adamw_matches_torch():
         opt.step()
         params, m, v = orc.adamw_step(params, {"w": gr}, m, v, step, 1e-3)
         assert rel_l2(params["w"], ref.detach()) < 1e-14
+
+
+@pytest.mark.parametrize("mode", ["output", "residual", "time_der"])
+def test_rollout_matches_reference_golden(mode):
+    """oracle.autoregressive_predict vs the reference's GAOT.autoregressive_predict output (de-normalised predictions,
+    [u | c | ...] input layout with stats['c'], gaot.py:307-476)."""
+    c, x0, tv, stats = cases.rollout_case()
+    g = load_golden("rollout")
+    cfg = orc.make_config(c["latent"], c["magno"], c["transformer"], c["attn"])
+    p = {k: v.double() for k, v in golden_params(g).items()}
+    st64 = {k: {kk: (vv.double() if torch.is_tensor(vv) else vv) for kk, vv in v.items()} for k, v in stats.items()}
+    lat, x, _, _ = cases.case_inputs(cases.ROLLOUT["base"])
+    got = orc.autoregressive_predict(p, cfg, x0.double(), cases.ROLLOUT["time_indices"], tv.double(), st64, mode, lat.double(),
+                                     x.double())
+    assert rel_l2(got, g["pred." + mode]) < 2e-7
