@@ -17,6 +17,7 @@
 #include <cstdlib>
 #include <type_traits>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 #include "../../include/gaot_b200.h"
@@ -52,6 +53,11 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+// 3-D form: coordinate c2 selects the hi / lo plane of a split-precision tensor ([2, rows, ld] fp16)
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -169,6 +175,14 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&t);
 }
+// split-precision packing: x = hi + lo with hi = fp16(x), lo = fp16(x - hi); two values per 32-bit word
+__device__ __forceinline__ void pack_split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    const __half2 h = __floats2half2_rn(a, b);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
 // address of the 16-byte piece `chunk` (0..7) of row r inside a K-major SWIZZLE_128B tile of 128-byte rows
 __device__ __forceinline__ uint32_t sw128_off(int r, int chunk) {
     return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((chunk ^ (r & 7)) << 4));
@@ -181,11 +195,18 @@ __device__ long long g_trace_f[4 * 128];
 #define FTRACE(slot) do { } while (0)
 #endif
 struct AttnArgs {
-    void* o;            // bf16 [B*T, H*hd]
+    void* o;            // bf16 [B*T, H*hd]  (SPLIT: fp32)
     float* lse;         // [B,H,T] natural log
     int T, H, Hkv, koff, voff;   // column offsets (elements) of the key / value blocks inside a qkv row
     float scale_log2;
+    const float* qs;    // SPLIT: {scale, 1 / scale} of the qkv planes (device)
 };
+
+// Split-precision (parity) variants, SPLIT = true: qkv arrives as fp16 hi / lo planes of qkv * s (gaot_split_f16); every
+// product runs as three tensor-core terms (lo*hi + hi*lo + hi*hi) into the same TMEM accumulator; the probabilities are
+// split the same way (P * 2^7 = hi + lo in the forward, where the lazily rescaled P is < 2^8; P * 2^14 in the backward,
+// where P <= 1); the softmax itself stays fp32.  Outputs are fp32.
+constexpr float AT_PSCALE_FWD = 128.f;
 
 // tcgen05.ld / tcgen05.st 32x32b of N (8 / 16 / 32) consecutive columns (issue only; pair with the matching wait)
 template <int N>
@@ -245,12 +266,15 @@ __device__ __forceinline__ void sts_u4_(uint32_t a, uint32_t x, uint32_t y, uint
 // The running maximum is only raised when the new row maximum exceeds it by more than 2^8 (lazy rescaling): the O
 // accumulator is then rescaled in place in TMEM (tcgen05.ld / st); otherwise P is formed against the stale maximum, which
 // is exact after the final division by the row sum.  No per-tile read-back of O.
-template <int HD>
-__global__ void __launch_bounds__(AT_THREADS, 2)
+template <int HD, bool SPLIT>
+__global__ void __launch_bounds__(AT_THREADS, SPLIT ? 1 : 2)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttnArgs g) {
     constexpr int ROWB = HD * 2;                         // bytes per head row = swizzle span
-    constexpr int TILE_BYTES = 128 * ROWB;               // a 128-row Q / K / V tile
-    constexpr int P_BYTES = AT_BQ * AT_BKV * 2;          // 32 KB: two 64-column SWIZZLE_128B blocks
+    constexpr int NPL = SPLIT ? 2 : 1;                   // planes per operand tile (hi, lo)
+    constexpr int PLANE_BYTES = 128 * ROWB;              // one plane of a 128-row Q / K / V tile
+    constexpr int TILE_BYTES = NPL * PLANE_BYTES;        // a 128-row Q / K / V tile
+    constexpr int PP_BYTES = AT_BQ * AT_BKV * 2;         // one plane of P: 32 KB, two 64-column SWIZZLE_128B blocks
+    constexpr int P_BYTES = NPL * PP_BYTES;
     constexpr uint32_t TMEM_COLS = 256;                  // S: [0,128), O: [128,128+HD)
     constexpr int NO = HD / 2;                           // O columns per thread (the two warps of a quadrant split HD)
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -296,20 +320,30 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttnArgs g) {
 
     if (warp == 0) {
         if (lane == 0) {
+            auto load = [&](uint8_t* dst, uint64_t* bar, int col, int row) {
+                if constexpr (SPLIT) {
+                    tma_load_3d(dst, &tm, bar, col, row, 0);
+                    tma_load_3d(dst + PLANE_BYTES, &tm, bar, col, row, 1);
+                } else {
+                    tma_load_2d(dst, &tm, bar, col, row);
+                }
+            };
             mbar_expect_tx(q_bar, TILE_BYTES);
-            tma_load_2d(sQ, &tm, q_bar, h * HD, row_base + t0);
+            load(sQ, q_bar, h * HD, row_base + t0);
             for (int i = 0; i < n_tiles; ++i) {
                 const int s = i & 1;
                 mbar_wait(&kv_empty[s], ((uint32_t)(i >> 1) & 1u) ^ 1u);
                 mbar_expect_tx(&kv_full[s], 2 * TILE_BYTES);
-                tma_load_2d(sK + s * TILE_BYTES, &tm, &kv_full[s], g.koff + hk * HD, row_base + i * AT_BKV);
-                tma_load_2d(sV + s * TILE_BYTES, &tm, &kv_full[s], g.voff + hk * HD, row_base + i * AT_BKV);
+                load(sK + s * TILE_BYTES, &kv_full[s], g.koff + hk * HD, row_base + i * AT_BKV);
+                load(sV + s * TILE_BYTES, &kv_full[s], g.voff + hk * HD, row_base + i * AT_BKV);
             }
         }
     } else if (warp == 1) {
         // S: M=128, N=128, A (Q) and B (K) K-major.  PV: M=128, N=HD, A (P) K-major, B (V) MN-major (bit 16).
-        constexpr uint32_t IDESC_S = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(AT_BKV >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-        constexpr uint32_t IDESC_PV = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(HD >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        constexpr uint32_t FMT = SPLIT ? 0u : ((1u << 7) | (1u << 10));   // operand format: bf16 (1) or, for the split planes, fp16 (0)
+        constexpr uint32_t IDESC_S = (1u << 4) | FMT | ((uint32_t)(AT_BKV >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        constexpr uint32_t IDESC_PV = (1u << 4) | FMT | (1u << 16) | ((uint32_t)(HD >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        constexpr int NTERM = SPLIT ? 3 : 1;                 // SPLIT terms, small to large: (A lo, B hi), (A hi, B lo), (A hi, B hi)
         mbar_wait(q_bar, 0);
         auto issue_s = [&](int i) {
             const int s = i & 1;
@@ -318,7 +352,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttnArgs g) {
             if (lane == 0) {
                 const uint64_t dq = make_desc<ROWB>(smem_u32(sQ)), dk = make_desc<ROWB>(smem_u32(sK + s * TILE_BYTES));
 #pragma unroll
-                for (int k = 0; k < HD / 16; ++k) umma_f16(tmem_s, dq + (uint64_t)(2 * k), dk + (uint64_t)(2 * k), IDESC_S, k > 0 ? 1u : 0u);
+                for (int t = 0; t < NTERM; ++t) {
+                    const uint64_t pa = (uint64_t)(((SPLIT && t == 0) ? PLANE_BYTES : 0) >> 4), pb = (uint64_t)(((SPLIT && t == 1) ? PLANE_BYTES : 0) >> 4);
+#pragma unroll
+                    for (int k = 0; k < HD / 16; ++k)
+                        umma_f16(tmem_s, dq + pa + (uint64_t)(2 * k), dk + pb + (uint64_t)(2 * k), IDESC_S, (t > 0 || k > 0) ? 1u : 0u);
+                }
                 umma_commit(s_full);
             }
             __syncwarp();
@@ -336,12 +375,16 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttnArgs g) {
                 // descriptors are base + compile-time offsets (start-address field counts 16-byte units)
                 const uint64_t da0 = make_desc<128>(smem_u32(sP + s * P_BYTES)), db0 = make_desc<ROWB>(smem_u32(sV + s * TILE_BYTES));
 #pragma unroll
-                for (int k = 0; k < AT_BKV / 16; ++k) {
-                    // A: 16 keys = 32 bytes inside the 128-byte swizzle row of P's column block (k / 4)
-                    const uint64_t da = da0 + (uint64_t)(((k >> 2) * (AT_BQ * 128) + (k & 3) * 32) >> 4);
-                    // B: 16 keys = 16 rows of V, two 8-row swizzle atoms
-                    const uint64_t db = db0 + (uint64_t)((k * 16 * ROWB) >> 4);
-                    umma_f16(tmem_o, da, db, IDESC_PV, (i > 0 || k > 0) ? 1u : 0u);
+                for (int t = 0; t < NTERM; ++t) {
+                    const uint64_t pa = (uint64_t)(((SPLIT && t == 0) ? PP_BYTES : 0) >> 4), pb = (uint64_t)(((SPLIT && t == 1) ? PLANE_BYTES : 0) >> 4);
+#pragma unroll
+                    for (int k = 0; k < AT_BKV / 16; ++k) {
+                        // A: 16 keys = 32 bytes inside the 128-byte swizzle row of P's column block (k / 4)
+                        const uint64_t da = da0 + pa + (uint64_t)(((k >> 2) * (AT_BQ * 128) + (k & 3) * 32) >> 4);
+                        // B: 16 keys = 16 rows of V, two 8-row swizzle atoms
+                        const uint64_t db = db0 + pb + (uint64_t)((k * 16 * ROWB) >> 4);
+                        umma_f16(tmem_o, da, db, IDESC_PV, (i > 0 || t > 0 || k > 0) ? 1u : 0u);
+                    }
                 }
                 umma_commit(o_step);
                 umma_commit(&p_free[s]);
@@ -356,6 +399,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttnArgs g) {
         const uint32_t xs = smem_u32(sX);
         const uint32_t bar_id = 1 + q;                     // named barrier of the two warps that share this quadrant
         float mref = -INFINITY, lsum = 0.f;                // reference maximum (base-2 units), partial row sum (own columns)
+        // SPLIT: the scores are those of (s q)(s k): fold 1 / s^2 into the softmax scale
+        float sl2 = g.scale_log2, inv_s = 1.f;
+        if constexpr (SPLIT) { inv_s = __ldg(g.qs + 1); sl2 *= inv_s * inv_s; }
 #ifdef EXP_TRACE_FWD
         const bool ftrace_on = blockIdx.x == 0 && blockIdx.y == 0 && (blockIdx.z == 0 || blockIdx.z == 20) && lane == 0 && (warp == 2 || warp == 6);
         const int ftrace_base = (blockIdx.z == 0 ? 0 : 256) + (warp == 6 ? 128 : 0);
@@ -392,7 +438,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttnArgs g) {
             const uint32_t xa = xs + (uint32_t)(((i & 1) * 2 + hf) * 128 + r) * 4u, xb = xs + (uint32_t)(((i & 1) * 2 + (hf ^ 1)) * 128 + r) * 4u;
             sts_f32_(xa, mx);
             asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
-            const float mrow = fmaxf(mx, lds_f32(xb)) * g.scale_log2;
+            const float mrow = fmaxf(mx, lds_f32(xb)) * sl2;
             FTRACE(i * 8 + 3);
             // lazy rescaling: identical decision in both warps of the quadrant (same rows, same maxima)
             if (__any_sync(0xffffffffu, mrow > mref + 8.f)) {
@@ -425,12 +471,20 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttnArgs g) {
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
                         const int j = w * 8 + k;
-                        p[k] = ex2(fmaf(__uint_as_float(sv[c][j]), g.scale_log2, -mref));
+                        p[k] = ex2(fmaf(__uint_as_float(sv[c][j]), sl2, -mref));
                         if (!full_tile && c * 32 + j >= kv_left) p[k] = 0.f;
                         ps4[k & 3] += p[k];
                     }
-                    sts_u4_(pbase + sw128_off(r, c * 4 + w), pack_bf16(p[0], p[1]), pack_bf16(p[2], p[3]), pack_bf16(p[4], p[5]),
-                            pack_bf16(p[6], p[7]));
+                    if constexpr (SPLIT) {
+                        uint32_t ph[4], pl[4];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) pack_split2(p[2 * k] * AT_PSCALE_FWD, p[2 * k + 1] * AT_PSCALE_FWD, ph[k], pl[k]);
+                        sts_u4_(pbase + sw128_off(r, c * 4 + w), ph[0], ph[1], ph[2], ph[3]);
+                        sts_u4_(pbase + PP_BYTES + sw128_off(r, c * 4 + w), pl[0], pl[1], pl[2], pl[3]);
+                    } else {
+                        sts_u4_(pbase + sw128_off(r, c * 4 + w), pack_bf16(p[0], p[1]), pack_bf16(p[2], p[3]), pack_bf16(p[4], p[5]),
+                                pack_bf16(p[6], p[7]));
+                    }
                 }
             }
             lsum += (ps4[0] + ps4[1]) + (ps4[2] + ps4[3]);
@@ -455,6 +509,15 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttnArgs g) {
         tmem_wait_ld();
         const int t = t0 + r;
         if (t < g.T) {
+            if constexpr (SPLIT) {
+                // O accumulated (2^7 P)(s V): undo both factors together with the row sum
+                const float inv = inv_s / (ltot * AT_PSCALE_FWD);
+                float* op = reinterpret_cast<float*>(g.o) + ((int64_t)(row_base + t) * g.H + h) * HD + hf * NO;
+#pragma unroll
+                for (int d = 0; d < NO; d += 4)
+                    *reinterpret_cast<float4*>(op + d) = make_float4(__uint_as_float(ov[d]) * inv, __uint_as_float(ov[d + 1]) * inv,
+                                                                     __uint_as_float(ov[d + 2]) * inv, __uint_as_float(ov[d + 3]) * inv);
+            } else {
             const float inv = 1.f / ltot;
             __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(g.o) + ((int64_t)(row_base + t) * g.H + h) * HD + hf * NO;
 #pragma unroll
@@ -462,6 +525,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttnArgs g) {
                 *reinterpret_cast<uint4*>(op + d) = make_uint4(
                     pack_bf16(__uint_as_float(ov[d]) * inv, __uint_as_float(ov[d + 1]) * inv), pack_bf16(__uint_as_float(ov[d + 2]) * inv, __uint_as_float(ov[d + 3]) * inv),
                     pack_bf16(__uint_as_float(ov[d + 4]) * inv, __uint_as_float(ov[d + 5]) * inv), pack_bf16(__uint_as_float(ov[d + 6]) * inv, __uint_as_float(ov[d + 7]) * inv));
+            }
             if (hf == 0) g.lse[((int64_t)b * g.H + h) * g.T + t] = (mref + log2f(ltot)) * 0.69314718055994531f;
         }
     }
@@ -500,28 +564,42 @@ __device__ long long g_trace[64 * 128];
 struct AttnBwdArgs {
     const float* lse;      // [B,H,T] natural log
     const float* delta;    // [B,H,T] rowsum(dO * O)
-    float* dq_acc;         // fp32 [B*T, H*hd], zero-initialised
-    void* dqkv;            // bf16 [B*T, ld]: dK and dV are written here (dQ is converted afterwards)
+    float* dq_acc;         // fp32 [B*T, H*hd], zero-initialised  (SPLIT: unused, dQ is reduced straight into dqkv)
+    void* dqkv;            // bf16 [B*T, ld]: dK and dV are written here (dQ is converted afterwards)  (SPLIT: fp32, Q columns zeroed)
     int T, H, Hkv, koff, voff, ld;
     float scale, scale_log2;
+    const float* qs;       // SPLIT: {scale, 1 / scale} of the qkv planes
+    const float* gs;       // SPLIT: {scale, 1 / scale} of the dO planes
 };
 
-template <int HD> struct AttnBwdCfg {
-    static constexpr int NQ = HD <= 32 ? 3 : 2;        // Q / dO stages
-    static constexpr int NBUF = HD <= 32 ? 2 : 1;      // P^T / dS^T buffers (hd = 64: shared memory allows one)
-    static constexpr int TILE_BYTES = 128 * HD * 2;
-    static constexpr int PT_BYTES = 128 * 128 * 2;
-    static constexpr int SMEM = (2 + 2 * NQ) * TILE_BYTES + 2 * NBUF * PT_BYTES + 4096 + 256 + 1024;
+// SPLIT (HD <= 32): every tile exists as a hi and a lo plane, so the P^T / dS^T tiles are single-buffered and Q / dO go
+// through a 2-stage ring; with the per-warp statistics slab shrunk to one slab per column group and step parity the tile
+// set is exactly the 227 KB a CTA may use.
+template <int HD, bool SPLIT> struct AttnBwdCfg {
+    static constexpr int NPL = SPLIT ? 2 : 1;
+    static constexpr int NQ = SPLIT ? 2 : (HD <= 32 ? 3 : 2);        // Q / dO stages
+    static constexpr int NBUF = SPLIT ? 1 : (HD <= 32 ? 2 : 1);      // P^T / dS^T buffers (hd = 64: shared memory allows one)
+    static constexpr int PLANE_BYTES = 128 * HD * 2;
+    static constexpr int TILE_BYTES = NPL * PLANE_BYTES;
+    static constexpr int PP_BYTES = 128 * 128 * 2;
+    static constexpr int PT_BYTES = NPL * PP_BYTES;
+    static constexpr int STAT_BYTES = SPLIT ? 2048 : 4096;
+    static constexpr int SMEM = (2 + 2 * NQ) * TILE_BYTES + 2 * NBUF * PT_BYTES + STAT_BYTES + 256 + (SPLIT ? 768 : 1024);
+    static_assert(SMEM <= 227 * 1024, "backward attention tile set exceeds shared memory");
 };
+constexpr float AT_PSCALE_BWD = 16384.f;               // P <= 1 in the backward (true row statistics): P * 2^14 = hi + lo
 
-template <int HD>
+template <int HD, bool SPLIT>
 __global__ void __launch_bounds__(AT_BWD_THREADS, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUtensorMap tmdo, const AttnBwdArgs g) {
-    using Cfg = AttnBwdCfg<HD>;
+    using Cfg = AttnBwdCfg<HD, SPLIT>;
     constexpr int ROWB = HD * 2;
     constexpr int TILE_BYTES = Cfg::TILE_BYTES;
+    constexpr int PLANE_BYTES = Cfg::PLANE_BYTES;
     constexpr int PT_BYTES = Cfg::PT_BYTES;
+    constexpr int PP_BYTES = Cfg::PP_BYTES;
     constexpr int NQ = Cfg::NQ, NBUF = Cfg::NBUF;
+    constexpr int NTERM = SPLIT ? 3 : 1;               // SPLIT terms, small to large: (A lo, B hi), (A hi, B lo), (A hi, B hi)
     constexpr uint32_t TMEM_COLS = 512;      // S^T [0,128) dP^T [128,256) dV [256,..) dK [256+HD,..) dQ[2] [256+2HD,..)
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -531,8 +609,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
     uint8_t* sG = sQ + NQ * TILE_BYTES;      // dO, [NQ stages]
     uint8_t* sPt = sG + NQ * TILE_BYTES;     // [NBUF]
     uint8_t* sSt = sPt + NBUF * PT_BYTES;    // [NBUF]
-    float* sStat = reinterpret_cast<float*>(sSt + NBUF * PT_BYTES);  // [16 compute warps][lse2 x 32 | delta x 32]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sStat + AT_BWD_CW * 64);
+    // statistics slabs [lse2 x 32 | delta x 32]: one per compute warp, or (SPLIT) one per column group and step parity,
+    // shared by the four warps of the group (they write identical values)
+    float* sStat = reinterpret_cast<float*>(sSt + NBUF * PT_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sStat) + Cfg::STAT_BYTES);
+    if (SPLIT && (uintptr_t)(smem - smem_raw) > 768) __trap();      // the split tile set leaves 768 bytes of alignment slack
     uint64_t* kv_bar = bars;
     uint64_t* q_full = bars + 1;     // [NQ]   TMA -> MMA
     uint64_t* q_empty = bars + 4;    // [NQ]   DVKQ(i) finished reading stage i % NQ
@@ -577,21 +658,30 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
 
     if (warp == 0) {
         if (lane == 0) {
+            auto load = [&](uint8_t* dst, const CUtensorMap* map, uint64_t* bar, int col, int row) {
+                if constexpr (SPLIT) {
+                    tma_load_3d(dst, map, bar, col, row, 0);
+                    tma_load_3d(dst + PLANE_BYTES, map, bar, col, row, 1);
+                } else {
+                    tma_load_2d(dst, map, bar, col, row);
+                }
+            };
             mbar_expect_tx(kv_bar, 2 * TILE_BYTES);
-            tma_load_2d(sK, &tm, kv_bar, g.koff + hk * HD, row_base + k0);
-            tma_load_2d(sV, &tm, kv_bar, g.voff + hk * HD, row_base + k0);
+            load(sK, &tm, kv_bar, g.koff + hk * HD, row_base + k0);
+            load(sV, &tm, kv_bar, g.voff + hk * HD, row_base + k0);
             int s = 0, use = 0, hq = 0, qt = 0;
             for (int i = 0; i < n_steps; ++i) {
                 mbar_wait(&q_empty[s], ((uint32_t)use & 1u) ^ 1u);
                 mbar_expect_tx(&q_full[s], 2 * TILE_BYTES);
-                tma_load_2d(sQ + s * TILE_BYTES, &tm, &q_full[s], (hk * rep + hq) * HD, row_base + qt * 128);
-                tma_load_2d(sG + s * TILE_BYTES, &tmdo, &q_full[s], (hk * rep + hq) * HD, row_base + qt * 128);
+                load(sQ + s * TILE_BYTES, &tm, &q_full[s], (hk * rep + hq) * HD, row_base + qt * 128);
+                load(sG + s * TILE_BYTES, &tmdo, &q_full[s], (hk * rep + hq) * HD, row_base + qt * 128);
                 if (++s == NQ) { s = 0; ++use; }
                 if (++qt == n_qt) { qt = 0; ++hq; }
             }
         }
     } else if (warp == 1) {
-        constexpr uint32_t BASE = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 4) << 24);
+        constexpr uint32_t BASE = (1u << 4) | (SPLIT ? 0u : ((1u << 7) | (1u << 10))) | ((uint32_t)(128 >> 4) << 24);   // fp16 planes when SPLIT
+        constexpr uint64_t PL = (uint64_t)(PLANE_BYTES >> 4), PPL = (uint64_t)(PP_BYTES >> 4);   // lo-plane offsets in descriptor units
         constexpr uint32_t IDESC_ST = BASE | ((uint32_t)(128 >> 3) << 17);                           // N=128, K-major x K-major
         constexpr uint32_t IDESC_KN = BASE | (1u << 16) | ((uint32_t)(HD >> 3) << 17);               // N=HD, B MN-major
         constexpr uint32_t IDESC_MN = BASE | (1u << 15) | (1u << 16) | ((uint32_t)(HD >> 3) << 17);  // A and B MN-major
@@ -604,9 +694,19 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
             if (lane == 0) {
                 const uint64_t dq = make_desc<ROWB>(smem_u32(sQ + s * TILE_BYTES)), dg = make_desc<ROWB>(smem_u32(sG + s * TILE_BYTES));
 #pragma unroll
-                for (int k = 0; k < HD / 16; ++k) umma_f16(tm_st, d_k + (uint64_t)(2 * k), dq + (uint64_t)(2 * k), IDESC_ST, k > 0 ? 1u : 0u);
+                for (int t = 0; t < NTERM; ++t) {
+                    const uint64_t pa = (SPLIT && t == 0) ? PL : 0, pb = (SPLIT && t == 1) ? PL : 0;
 #pragma unroll
-                for (int k = 0; k < HD / 16; ++k) umma_f16(tm_dp, d_v + (uint64_t)(2 * k), dg + (uint64_t)(2 * k), IDESC_ST, k > 0 ? 1u : 0u);
+                    for (int k = 0; k < HD / 16; ++k)
+                        umma_f16(tm_st, d_k + pa + (uint64_t)(2 * k), dq + pb + (uint64_t)(2 * k), IDESC_ST, (t > 0 || k > 0) ? 1u : 0u);
+                }
+#pragma unroll
+                for (int t = 0; t < NTERM; ++t) {
+                    const uint64_t pa = (SPLIT && t == 0) ? PL : 0, pb = (SPLIT && t == 1) ? PL : 0;
+#pragma unroll
+                    for (int k = 0; k < HD / 16; ++k)
+                        umma_f16(tm_dp, d_v + pa + (uint64_t)(2 * k), dg + pb + (uint64_t)(2 * k), IDESC_ST, (t > 0 || k > 0) ? 1u : 0u);
+                }
                 umma_commit(st_full);
             }
             __syncwarp();
@@ -632,19 +732,28 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
                 const uint64_t d_pt = make_desc<128>(smem_u32(sPt + bf * PT_BYTES)), d_st = make_desc<128>(pst);
                 const uint32_t acc_first = i > 0 ? 1u : 0u;
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {      // contraction over 128 queries, 16 per MMA
-                    const uint64_t aoff = (uint64_t)(((k >> 2) * (128 * 128) + (k & 3) * 32) >> 4);
-                    const uint64_t boff = (uint64_t)((k * 16 * ROWB) >> 4);
-                    umma_f16(tm_dv, d_pt + aoff, d_g + boff, IDESC_KN, k > 0 ? 1u : acc_first);
-                    umma_f16(tm_dk, d_st + aoff, d_q + boff, IDESC_KN, k > 0 ? 1u : acc_first);
+                for (int t = 0; t < NTERM; ++t) {
+                    const uint64_t pa = (SPLIT && t == 0) ? PPL : 0, pb = (SPLIT && t == 1) ? PL : 0;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {      // contraction over 128 queries, 16 per MMA
+                        const uint64_t aoff = pa + (uint64_t)(((k >> 2) * (128 * 128) + (k & 3) * 32) >> 4);
+                        const uint64_t boff = pb + (uint64_t)((k * 16 * ROWB) >> 4);
+                        umma_f16(tm_dv, d_pt + aoff, d_g + boff, IDESC_KN, (t > 0 || k > 0) ? 1u : acc_first);
+                        umma_f16(tm_dk, d_st + aoff, d_q + boff, IDESC_KN, (t > 0 || k > 0) ? 1u : acc_first);
+                    }
                 }
                 // dQ[q, :] = sum_keys dS^T[key, q] K[key, :]: A = the dS^T tile as an MN-major operand
                 // (M = 128 queries = two 64-wide swizzle atoms LBO = 16 KB apart, 8-key groups SBO = 1 KB apart)
                 const uint64_t a_mn0 = (uint64_t)((pst & 0x3FFFF) >> 4) | ((uint64_t)(16384 >> 4) << 16) |
                                        ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 #pragma unroll
-                for (int k = 0; k < 8; ++k)        // contraction over 128 keys, 16 per MMA = 16 rows of 128 bytes
-                    umma_f16(tm_dq + d * HD, a_mn0 + (uint64_t)((k * 2048) >> 4), d_k + (uint64_t)((k * 16 * ROWB) >> 4), IDESC_MN, k > 0 ? 1u : 0u);
+                for (int t = 0; t < NTERM; ++t) {
+                    const uint64_t pa = (SPLIT && t == 0) ? PPL : 0, pb = (SPLIT && t == 1) ? PL : 0;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)        // contraction over 128 keys, 16 per MMA = 16 rows of 128 bytes
+                        umma_f16(tm_dq + d * HD, a_mn0 + pa + (uint64_t)((k * 2048) >> 4), d_k + pb + (uint64_t)((k * 16 * ROWB) >> 4), IDESC_MN,
+                                 (t > 0 || k > 0) ? 1u : 0u);
+                }
                 umma_commit(&done[d]);
                 umma_commit(&q_empty[s]);
             }
@@ -662,7 +771,21 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
         const bool tile_full = k0 + 128 <= g.T;            // CTA-uniform: only the last key tile can be ragged
         // per-query statistics of the warp's 32 columns: [lse2 x 32 | delta x 32] in a per-warp shared-memory slab
         // (no CTA-wide barrier), loaded from global memory one step ahead (one lse and one delta per lane)
-        const uint32_t stat_s = smem_u32(sStat) + (uint32_t)(warp - 2) * 256u;
+        uint32_t stat_s = smem_u32(sStat) + (uint32_t)(SPLIT ? qr * 2 : warp - 2) * 256u;   // SPLIT: + 256 on odd steps (set per step)
+        const uint32_t stat_s0 = stat_s;
+        // SPLIT scale bookkeeping (all factors are powers of two except the softmax scale):
+        //   scores arrive as (s q).(s k), dP^T as (s v).(sg dO);   dS'' = P (dP' kd - delta kdel) = (sigma s sg) dS,  sigma = 2^-14 / HD
+        //   keeps |dS''| < 2^15 for any input (|dP'| <= HD 2^28) while typical entries stay ~2^40 above the fp16 hi / lo error floor
+        float sl2 = g.scale_log2, kd = 1.f, kdel = 1.f, f_dqk = g.scale, f_dv = 1.f;
+        if constexpr (SPLIT) {
+            const float sq = __ldg(g.qs), inv_s = __ldg(g.qs + 1), sg = __ldg(g.gs), inv_g = __ldg(g.gs + 1);
+            constexpr float SIGMA = 1.f / (16384.f * (float)HD);
+            sl2 *= inv_s * inv_s;
+            kd = SIGMA;
+            kdel = sq * sg * SIGMA;
+            f_dqk = g.scale * (inv_s * inv_s) * inv_g * (16384.f * (float)HD);
+            f_dv = inv_g * (1.f / AT_PSCALE_BWD);
+        }
         const float* lse_b = g.lse + (int64_t)b * g.H * g.T;
         const float* del_b = g.delta + (int64_t)b * g.H * g.T;
         float st_l, st_d;
@@ -684,12 +807,13 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
             __syncwarp();
             if (lane == 0) mbar_arrive(&dq_empty[d]);
             if (t < g.T) {
-                float* dst = g.dq_acc + ((int64_t)(row_base + t) * g.H + h) * HD + qr * NC;
+                float* dst = SPLIT ? reinterpret_cast<float*>(g.dqkv) + (int64_t)(row_base + t) * g.ld + h * HD + qr * NC
+                                   : g.dq_acc + ((int64_t)(row_base + t) * g.H + h) * HD + qr * NC;
 #pragma unroll
                 for (int j4 = 0; j4 < NC; j4 += 4)
                     atomicAdd(reinterpret_cast<float4*>(dst + j4),
-                              make_float4(__uint_as_float(v[j4]) * g.scale, __uint_as_float(v[j4 + 1]) * g.scale,
-                                          __uint_as_float(v[j4 + 2]) * g.scale, __uint_as_float(v[j4 + 3]) * g.scale));
+                              make_float4(__uint_as_float(v[j4]) * f_dqk, __uint_as_float(v[j4 + 1]) * f_dqk,
+                                          __uint_as_float(v[j4 + 2]) * f_dqk, __uint_as_float(v[j4 + 3]) * f_dqk));
             }
         };
         // P^T / dS^T of the warp's 32 query columns: exp2, products, bf16 packing; 8 columns = one 16-byte swizzled
@@ -699,25 +823,39 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
                 uint32_t pp[4], ds[4];
+                [[maybe_unused]] uint32_t ppl[4], dsl[4];
 #pragma unroll
                 for (int k = 0; k < 8; k += 4) {
                     const float4 lv = lds_f4(stat_s + (uint32_t)(j + k) * 4u);              // broadcast reads
                     const float4 dl = lds_f4(stat_s + 128u + (uint32_t)(j + k) * 4u);
-                    float p0 = ex2(fmaf(__uint_as_float(sv[j + k]), g.scale_log2, -lv.x));
-                    float p1 = ex2(fmaf(__uint_as_float(sv[j + k + 1]), g.scale_log2, -lv.y));
-                    float p2 = ex2(fmaf(__uint_as_float(sv[j + k + 2]), g.scale_log2, -lv.z));
-                    float p3 = ex2(fmaf(__uint_as_float(sv[j + k + 3]), g.scale_log2, -lv.w));
+                    float p0 = ex2(fmaf(__uint_as_float(sv[j + k]), sl2, -lv.x));
+                    float p1 = ex2(fmaf(__uint_as_float(sv[j + k + 1]), sl2, -lv.y));
+                    float p2 = ex2(fmaf(__uint_as_float(sv[j + k + 2]), sl2, -lv.z));
+                    float p3 = ex2(fmaf(__uint_as_float(sv[j + k + 3]), sl2, -lv.w));
                     if (!FULL) {
                         if (!key_ok) { p0 = 0.f; p1 = 0.f; p2 = 0.f; p3 = 0.f; }
                     }
+                    if constexpr (SPLIT) {
+                        pack_split2(p0 * AT_PSCALE_BWD, p1 * AT_PSCALE_BWD, pp[k >> 1], ppl[k >> 1]);
+                        pack_split2(p2 * AT_PSCALE_BWD, p3 * AT_PSCALE_BWD, pp[(k >> 1) + 1], ppl[(k >> 1) + 1]);
+                        pack_split2(p0 * fmaf(__uint_as_float(dv[j + k]), kd, -dl.x * kdel), p1 * fmaf(__uint_as_float(dv[j + k + 1]), kd, -dl.y * kdel),
+                                    ds[k >> 1], dsl[k >> 1]);
+                        pack_split2(p2 * fmaf(__uint_as_float(dv[j + k + 2]), kd, -dl.z * kdel), p3 * fmaf(__uint_as_float(dv[j + k + 3]), kd, -dl.w * kdel),
+                                    ds[(k >> 1) + 1], dsl[(k >> 1) + 1]);
+                    } else {
                     pp[k >> 1] = pack_bf16(p0, p1);
                     pp[(k >> 1) + 1] = pack_bf16(p2, p3);
                     ds[k >> 1] = pack_bf16(p0 * (__uint_as_float(dv[j + k]) - dl.x), p1 * (__uint_as_float(dv[j + k + 1]) - dl.y));
                     ds[(k >> 1) + 1] = pack_bf16(p2 * (__uint_as_float(dv[j + k + 2]) - dl.z), p3 * (__uint_as_float(dv[j + k + 3]) - dl.w));
+                    }
                 }
                 const uint32_t off = sw128_off(r, (qr & 1) * 4 + (j >> 3));
                 sts_u4(bp + off, pp[0], pp[1], pp[2], pp[3]);
                 sts_u4(bs + off, ds[0], ds[1], ds[2], ds[3]);
+                if constexpr (SPLIT) {
+                    sts_u4(bp + PP_BYTES + off, ppl[0], ppl[1], ppl[2], ppl[3]);
+                    sts_u4(bs + PP_BYTES + off, dsl[0], dsl[1], dsl[2], dsl[3]);
+                }
             }
         };
         const int h0 = hk * rep;
@@ -726,6 +864,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
         fetch_stat(f_h, f_qt);
         for (int i = 0; i < n_steps; ++i) {
             const int bf = i % NBUF;
+            if constexpr (SPLIT) stat_s = stat_s0 + (uint32_t)(i & 1) * 256u;
             sts_f32(stat_s + (uint32_t)lane * 4u, st_l * 1.4426950408889634f);
             sts_f32(stat_s + 128u + (uint32_t)lane * 4u, st_d);
             __syncwarp();
@@ -765,7 +904,24 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
         drain_dq(n_steps - 1, p_h, p_qt);
         TRACE(2 + 6 * n_steps);
         // final: dV and dK rows of this key tile (done[] of the last step has completed: every MMA has retired)
-        {
+        if constexpr (SPLIT) {
+            float* base = reinterpret_cast<float*>(g.dqkv) + (int64_t)(row_base + k0 + r) * g.ld;
+            uint32_t vv[NC], vk[NC];
+            tmem_ld_issue<NC>(tm_dv + lane_addr + qr * NC, vv);
+            tmem_ld_issue<NC>(tm_dk + lane_addr + qr * NC, vk);
+            tmem_wait_ld();
+            if (key_ok) {
+                float* dvp = base + g.voff + hk * HD + qr * NC;
+                float* dkp = base + g.koff + hk * HD + qr * NC;
+#pragma unroll
+                for (int c = 0; c < NC; c += 4) {
+                    *reinterpret_cast<float4*>(dvp + c) = make_float4(__uint_as_float(vv[c]) * f_dv, __uint_as_float(vv[c + 1]) * f_dv,
+                                                                      __uint_as_float(vv[c + 2]) * f_dv, __uint_as_float(vv[c + 3]) * f_dv);
+                    *reinterpret_cast<float4*>(dkp + c) = make_float4(__uint_as_float(vk[c]) * f_dqk, __uint_as_float(vk[c + 1]) * f_dqk,
+                                                                      __uint_as_float(vk[c + 2]) * f_dqk, __uint_as_float(vk[c + 3]) * f_dqk);
+                }
+            }
+        } else {
             __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(g.dqkv) + (int64_t)(row_base + k0 + r) * g.ld;
             uint32_t vv[NC], vk[NC];
             tmem_ld_issue<NC>(tm_dv + lane_addr + qr * NC, vv);
@@ -829,6 +985,26 @@ __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __n
     }
 }
 
+// fp32 variant for the split-precision path
+template <int HD>
+__global__ void attn_delta_f32_kernel(const float* __restrict__ o, const float* __restrict__ dout, float* __restrict__ delta,
+                                      int64_t B, int64_t T, int H) {
+    const int64_t total = B * T * H;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int h = (int)(i % H);
+        const int64_t bt = i / H;
+        const float4* po = reinterpret_cast<const float4*>(o + i * HD);
+        const float4* pg = reinterpret_cast<const float4*>(dout + i * HD);
+        float acc = 0.f;
+#pragma unroll
+        for (int c = 0; c < HD / 4; ++c) {
+            const float4 a = __ldg(po + c), b4 = __ldg(pg + c);
+            acc = fmaf(a.x, b4.x, acc); acc = fmaf(a.y, b4.y, acc); acc = fmaf(a.z, b4.z, acc); acc = fmaf(a.w, b4.w, acc);
+        }
+        delta[((bt / T) * H + h) * T + (bt % T)] = acc;
+    }
+}
+
 // dqkv[row, 0:W] = bf16(dq_acc[row, 0:W])   (W = H*hd query columns of the fused gradient)
 __global__ void attn_dq_store_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dqkv, int64_t rows, int W, int ld) {
     const int64_t total = rows * (W / 4);
@@ -881,17 +1057,37 @@ int make_head_map(CUtensorMap* map, const void* base, int64_t rows, int64_t ld, 
     return r == CUDA_SUCCESS ? 0 : GAOT_E_BADARG;
 }
 
-template <int HD>
+template <int HD, bool SPLIT = false>
 int launch_fwd(const CUtensorMap& tm, const AttnArgs& g, int64_t B, cudaStream_t st) {
-    constexpr int SMEM = 5 * 128 * HD * 2 + 2 * AT_BQ * AT_BKV * 2 + 2048 + 1024 + 256;
+    constexpr int SMEM = (SPLIT ? 2 : 1) * (5 * 128 * HD * 2 + 2 * AT_BQ * AT_BKV * 2) + 2048 + 1024 + 256;
+    static_assert(SMEM <= 227 * 1024, "forward attention tile set exceeds shared memory");
     static bool done = false;
     if (!done) {
-        GAOT_CHECK(cudaFuncSetAttribute(attn_fwd_tc_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+        GAOT_CHECK(cudaFuncSetAttribute(attn_fwd_tc_kernel<HD, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
         done = true;
     }
     dim3 grid((unsigned)((g.T + AT_BQ - 1) / AT_BQ), (unsigned)g.H, (unsigned)B);
-    attn_fwd_tc_kernel<HD><<<grid, AT_THREADS, SMEM, st>>>(tm, g);
+    attn_fwd_tc_kernel<HD, SPLIT><<<grid, AT_THREADS, SMEM, st>>>(tm, g);
     GAOT_RETURN_LAST();
+}
+
+// split-precision planes [2, rows, ld] fp16 -> 3-D map {ld, rows, 2}, box {hd, box_rows, 1}, swizzle span = hd*2 bytes
+int make_head_map_planes(CUtensorMap* map, const void* base, int64_t rows, int64_t ld, int hd, int box_rows) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return GAOT_E_BADARG;
+    cuuint64_t dims[3] = {(cuuint64_t)ld, (cuuint64_t)rows, 2};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)ld * (cuuint64_t)rows * 2};
+    cuuint32_t box[3] = {(cuuint32_t)hd, (cuuint32_t)box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    const CUtensorMapSwizzle sw = hd == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (hd == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r == CUDA_ERROR_INVALID_CONTEXT) {
+        cudaFree(nullptr);                                     // bind the primary context on this thread, then encode again
+        r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
+    return r == CUDA_SUCCESS ? 0 : GAOT_E_BADARG;
 }
 
 }  // namespace
@@ -906,21 +1102,56 @@ GAOT_API int gaot_attention_fwd_bf16(const void* qkv, void* o, float* lse, int64
     CUtensorMap tm;
     int rc = make_head_map(&tm, qkv, B * T, ld, (int)hd, 128);
     if (rc) return rc;
-    AttnArgs g{o, lse, (int)T, (int)H, (int)Hkv, (int)(H * hd), (int)((H + Hkv) * hd), scale * 1.4426950408889634f};
+    AttnArgs g{o, lse, (int)T, (int)H, (int)Hkv, (int)(H * hd), (int)((H + Hkv) * hd), scale * 1.4426950408889634f, nullptr};
     cudaStream_t st = (cudaStream_t)stream;
     if (hd == 16) return launch_fwd<16>(tm, g, B, st);
     if (hd == 32) return launch_fwd<32>(tm, g, B, st);
     return launch_fwd<64>(tm, g, B, st);
 }
 
+GAOT_API int gaot_attention_fwd_split(const void* qkv_planes, const float* qscale, float* o, float* lse, int64_t B, int64_t T,
+                                      int64_t H, int64_t Hkv, int64_t hd, int64_t ld, float scale, void* stream) {
+    if (!qkv_planes || !qscale || !o || !lse || B < 1 || T < 1 || H < 1 || Hkv < 1 || H % Hkv) return GAOT_E_BADARG;
+    if (hd != 16 && hd != 32) return GAOT_E_BADARG;        // hd = 64 does not fit the doubled tile set; callers use the FFMA kernels
+    if (ld < (H + 2 * Hkv) * hd || ld % 8 || (reinterpret_cast<uintptr_t>(qkv_planes) & 15) || (reinterpret_cast<uintptr_t>(o) & 15))
+        return GAOT_E_ALIGN;
+    if (B > 65535 || H > 65535 || B * T > 0x7fffffffLL) return GAOT_E_BADARG;
+    CUtensorMap tm;
+    int rc = make_head_map_planes(&tm, qkv_planes, B * T, ld, (int)hd, 128);
+    if (rc) return rc;
+    AttnArgs g{o, lse, (int)T, (int)H, (int)Hkv, (int)(H * hd), (int)((H + Hkv) * hd), scale * 1.4426950408889634f, qscale};
+    cudaStream_t st = (cudaStream_t)stream;
+    if (hd == 16) return launch_fwd<16, true>(tm, g, B, st);
+    return launch_fwd<32, true>(tm, g, B, st);
+}
+
 namespace {
+template <int HD>
+int launch_bwd_split(const CUtensorMap& tm, const CUtensorMap& tmdo, const AttnBwdArgs& g, const float* o, const float* dout,
+                     float* delta, int64_t B, cudaStream_t st) {
+    constexpr int SMEM = AttnBwdCfg<HD, true>::SMEM;
+    static bool done = false;
+    if (!done) {
+        GAOT_CHECK(cudaFuncSetAttribute(attn_bwd_tc_kernel<HD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+        done = true;
+    }
+    const int64_t rows = B * g.T;
+    attn_delta_f32_kernel<HD><<<gaot_grid(rows * g.H, 256), 256, 0, st>>>(o, dout, delta, B, g.T, g.H);
+    // dQ is reduced into the query columns of dqkv by several key tiles: zero them first
+    GAOT_CHECK(cudaMemset2DAsync(g.dqkv, sizeof(float) * (size_t)g.ld, 0, sizeof(float) * (size_t)(g.H * HD), (size_t)rows, st));
+    dim3 grid((unsigned)((g.T + 127) / 128), (unsigned)g.Hkv, (unsigned)B);
+    attn_bwd_tc_kernel<HD, true><<<grid, AT_BWD_THREADS, SMEM, st>>>(tm, tmdo, g);
+    GAOT_NOTE_LAUNCHES(1);
+    GAOT_RETURN_LAST();
+}
+
 template <int HD>
 int launch_bwd(const CUtensorMap& tm, const CUtensorMap& tmdo, const AttnBwdArgs& g, const void* o, const void* dout,
                float* delta, int64_t B, cudaStream_t st) {
-    constexpr int SMEM = AttnBwdCfg<HD>::SMEM;
+    constexpr int SMEM = AttnBwdCfg<HD, false>::SMEM;
     static bool done = false;
     if (!done) {
-        GAOT_CHECK(cudaFuncSetAttribute(attn_bwd_tc_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+        GAOT_CHECK(cudaFuncSetAttribute(attn_bwd_tc_kernel<HD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
         done = true;
     }
     const int64_t rows = B * g.T;
@@ -928,7 +1159,7 @@ int launch_bwd(const CUtensorMap& tm, const CUtensorMap& tmdo, const AttnBwdArgs
                                                                      reinterpret_cast<const __nv_bfloat16*>(dout), delta, B, g.T, g.H);
     GAOT_CHECK(cudaMemsetAsync(g.dq_acc, 0, sizeof(float) * (size_t)(rows * g.H * HD), st));
     dim3 grid((unsigned)((g.T + 127) / 128), (unsigned)g.Hkv, (unsigned)B);
-    attn_bwd_tc_kernel<HD><<<grid, AT_BWD_THREADS, SMEM, st>>>(tm, tmdo, g);
+    attn_bwd_tc_kernel<HD, false><<<grid, AT_BWD_THREADS, SMEM, st>>>(tm, tmdo, g);
     attn_dq_store_kernel<<<gaot_grid(rows * g.H * HD / 4, 256), 256, 0, st>>>(g.dq_acc, reinterpret_cast<__nv_bfloat16*>(g.dqkv), rows,
                                                                             g.H * HD, g.ld);
     GAOT_NOTE_LAUNCHES(2);
@@ -951,11 +1182,35 @@ GAOT_API int gaot_attention_bwd_bf16(const void* qkv, const void* o, const float
     rc = make_head_map(&tmdo, dout, B * T, H * hd, (int)hd, 128);
     if (rc) return rc;
     AttnBwdArgs g{lse, delta, dq_acc, dqkv, (int)T, (int)H, (int)Hkv, (int)(H * hd), (int)((H + Hkv) * hd), (int)ld, scale,
-                  scale * 1.4426950408889634f};
+                  scale * 1.4426950408889634f, nullptr, nullptr};
     cudaStream_t st = (cudaStream_t)stream;
     if (hd == 16) return launch_bwd<16>(tm, tmdo, g, o, dout, delta, B, st);
     if (hd == 32) return launch_bwd<32>(tm, tmdo, g, o, dout, delta, B, st);
     return launch_bwd<64>(tm, tmdo, g, o, dout, delta, B, st);
+}
+
+GAOT_API int gaot_attention_bwd_split(const void* qkv_planes, const float* qscale, const float* o, const float* lse,
+                                      const float* dout, const void* dout_planes, const float* gscale, float* delta, float* dqkv,
+                                      int64_t B, int64_t T, int64_t H, int64_t Hkv, int64_t hd, int64_t ld, float scale,
+                                      void* stream) {
+    if (!qkv_planes || !qscale || !o || !lse || !dout || !dout_planes || !gscale || !delta || !dqkv || B < 1 || T < 1 || H < 1 ||
+        Hkv < 1 || H % Hkv)
+        return GAOT_E_BADARG;
+    if (hd != 16 && hd != 32) return GAOT_E_BADARG;
+    if (ld < (H + 2 * Hkv) * hd || ld % 8 || (reinterpret_cast<uintptr_t>(qkv_planes) & 15) || (reinterpret_cast<uintptr_t>(dout) & 15) ||
+        (reinterpret_cast<uintptr_t>(dout_planes) & 15) || (reinterpret_cast<uintptr_t>(dqkv) & 15) || (reinterpret_cast<uintptr_t>(o) & 15))
+        return GAOT_E_ALIGN;
+    if (B > 65535 || Hkv > 65535 || B * T > 0x7fffffffLL) return GAOT_E_BADARG;
+    CUtensorMap tm, tmdo;
+    int rc = make_head_map_planes(&tm, qkv_planes, B * T, ld, (int)hd, 128);
+    if (rc) return rc;
+    rc = make_head_map_planes(&tmdo, dout_planes, B * T, H * hd, (int)hd, 128);
+    if (rc) return rc;
+    AttnBwdArgs g{lse, delta, nullptr, dqkv, (int)T, (int)H, (int)Hkv, (int)(H * hd), (int)((H + Hkv) * hd), (int)ld, scale,
+                  scale * 1.4426950408889634f, qscale, gscale};
+    cudaStream_t st = (cudaStream_t)stream;
+    if (hd == 16) return launch_bwd_split<16>(tm, tmdo, g, o, dout, delta, B, st);
+    return launch_bwd_split<32>(tm, tmdo, g, o, dout, delta, B, st);
 }
 
 #ifdef EXP_TRACE

@@ -15,6 +15,7 @@
 #include <cuda.h>
 #include <cstdlib>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 #include "../../include/gaot_b200.h"
@@ -48,6 +49,11 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+// 3-D form: coordinate c2 selects the hi / lo plane of a split-precision operand ([2, rows, cols] fp16)
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -134,6 +140,10 @@ __device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* m
     asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ void tma_load_3d_pair(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
 __device__ __forceinline__ void umma_f16_pair(uint32_t tmem_c, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -168,6 +178,9 @@ struct TcArgs {
     int64_t gm, gn;                   // tile grid
     int act; float* pre;              // optional activation (GAOT_ACT_*) and fp32 pre-activation output
     int fast;                         // epilogue through swizzled smem boxes and TMA: 1 = stores, 2 = fp32 reduce-add (split-K / accumulate)
+    // split-precision mode (SPLIT): operands are [2, rows, cols] fp16 hi / lo planes of x * scale; sa / sb point at the
+    // {scale, 1 / scale} pair written by gaot_split_f16; kb_real = k-blocks of ONE term (the virtual contraction is 3 terms long)
+    const float* sa; const float* sb; int64_t kb_real;
 };
 
 // MN-major operand tile: [64 contraction rows][64 elements = 128 bytes] blocks of 8 KB, one per 64 output
@@ -183,7 +196,13 @@ __device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t saddr) {
 // so forward / dX / dW of a Linear layer all read activations and weights in their natural layout.
 // Two TMEM accumulators (2*BN columns): the epilogue of tile i overlaps the main loop of tile i+1, and the TMA
 // ring keeps prefetching across tile boundaries.
-template <int BN, bool AMN, bool BMN, int CG>
+//
+// SPLIT = true is the split-precision (parity) variant: x = (hi + lo) / scale with hi, lo fp16, and
+//     A B^T = (A_lo B_hi + A_hi B_lo + A_hi B_hi) / (scale_a scale_b)          (the lo x lo term is below 2^-22 relative)
+// runs as ONE accumulation over a contraction that is three terms long: the producer maps the virtual k-block index to
+// (term, real k-block) and picks the hi / lo plane of each operand with the third TMA coordinate; MMA issue, pipeline and
+// epilogue are unchanged except for kind::f16 reading fp16 instead of bf16 and the 1 / (scale_a scale_b) factor.
+template <int BN, bool AMN, bool BMN, int CG, bool SPLIT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmAdd, const TcArgs g) {
@@ -257,8 +276,9 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         // ---------------- TMA producer ----------------
         if (lane == 0) {
             uint32_t it = 0;
-            auto load = [&](void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
-                if (CG == 2) tma_load_2d_pair(dst, map, bar, c0, c1); else tma_load_2d(dst, map, bar, c0, c1);
+            auto load = [&](void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int plane) {
+                if (SPLIT) { if (CG == 2) tma_load_3d_pair(dst, map, bar, c0, c1, plane); else tma_load_3d(dst, map, bar, c0, c1, plane); }
+                else { if (CG == 2) tma_load_2d_pair(dst, map, bar, c0, c1); else tma_load_2d(dst, map, bar, c0, c1); }
             };
             for (int64_t t = worker; t < n_tiles; t += n_workers) {
                 int64_t m0, n0, kb0; int nkb;
@@ -271,16 +291,20 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     // one arrival (the leader's) per phase; both CTAs' bytes are counted on the leader's barrier
                     if (rank == 0) mbar_expect_tx(&full_bar[s], STAGE_BYTES * CG);
                     uint8_t* st = smem + s * STAGE_BYTES;
-                    const int kc = (int)((kb0 + i) * TC_BK);
-                    if (!AMN) load(st, &tmA, &full_bar[s], kc, (int)m0);
+                    // SPLIT: terms in increasing magnitude, (A lo, B hi), (A hi, B lo), (A hi, B hi)
+                    const int64_t vk = kb0 + i;
+                    const int term = SPLIT ? (int)(vk / g.kb_real) : 0;
+                    const int kc = (int)((SPLIT ? vk - term * g.kb_real : vk) * TC_BK);
+                    const int pa = term == 0 ? 1 : 0, pb = term == 1 ? 1 : 0;
+                    if (!AMN) load(st, &tmA, &full_bar[s], kc, (int)m0, pa);
                     else {
 #pragma unroll
-                        for (int j = 0; j < TC_BM / 64; ++j) load(st + j * 8192, &tmA, &full_bar[s], (int)m0 + 64 * j, kc);
+                        for (int j = 0; j < TC_BM / 64; ++j) load(st + j * 8192, &tmA, &full_bar[s], (int)m0 + 64 * j, kc, pa);
                     }
-                    if (!BMN) load(st + A_BYTES, &tmB, &full_bar[s], kc, nb0);
+                    if (!BMN) load(st + A_BYTES, &tmB, &full_bar[s], kc, nb0, pb);
                     else {
 #pragma unroll
-                        for (int j = 0; j < BNL / 64; ++j) load(st + A_BYTES + j * 8192, &tmB, &full_bar[s], nb0 + 64 * j, kc);
+                        for (int j = 0; j < BNL / 64; ++j) load(st + A_BYTES + j * 8192, &tmB, &full_bar[s], nb0 + 64 * j, kc, pb);
                     }
                 }
             }
@@ -289,7 +313,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if (rank == 0) {
         // ---------------- MMA issuer (CG = 2: the leader CTA issues for the pair) ----------------
         // instruction descriptor: D fp32, A/B bf16, majors per template, N = BN, M = 128 (cute/arch/mma_sm100_desc.hpp)
-        constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (AMN ? (1u << 15) : 0u) | (BMN ? (1u << 16) : 0u) |
+        // (A/B format field 1 = bf16, 0 = fp16: the split-precision planes are fp16)
+        constexpr uint32_t IDESC = (1u << 4) | (SPLIT ? 0u : ((1u << 7) | (1u << 10))) | (AMN ? (1u << 15) : 0u) | (BMN ? (1u << 16) : 0u) |
                                    ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((TC_BM * CG) >> 4) << 24);
         uint32_t it = 0, lt = 0;
         for (int64_t t = worker; t < n_tiles; t += n_workers, ++lt) {
@@ -338,6 +363,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         // instruction writes 4 rows x 128 bytes (fp32) / 64 bytes (bf16).  Two warps share a lane quadrant and
         // split the BN columns.  Row offsets are hoisted out of the column loop; the store loops are specialised.
         const int q = warp & 3, half = (warp - 2) >> 2;
+        float alpha = 1.f;                                         // SPLIT: 1 / (scale_a * scale_b), exact powers of two
+        if (SPLIT) alpha = __ldg(g.sa + 1) * __ldg(g.sb + 1);
         if (g.fast) {
             // Fast epilogue.  Per warp: 32 accumulator rows x BN/2 columns, in chunks of 32 columns.  A lane owns one
             // row: TMEM -> registers (+ bias, + the `add` tile that TMA has loaded into the same box, activation) ->
@@ -403,6 +430,10 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         float v[32];
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[c][j]);
+                        if (SPLIT) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] *= alpha;
+                        }
                         if (g.bias) {
 #pragma unroll
                             for (int j = 0; j < 32; j += 4) {
@@ -515,7 +546,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
                 for (int j = 0; j < 32; j += 4)
                     *reinterpret_cast<float4*>(stg + lane * PITCH + j) =
-                        make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+                        make_float4(__uint_as_float(r[j]) * alpha, __uint_as_float(r[j + 1]) * alpha, __uint_as_float(r[j + 2]) * alpha,
+                                    __uint_as_float(r[j + 3]) * alpha);
                 __syncwarp();
                 const int64_t nc = n + sub_c;
                 if ((n + 32 <= g.N) && vec_ok) {
@@ -639,6 +671,77 @@ __global__ void __launch_bounds__(256) transpose_bf16_kernel(const TIn* __restri
     }
 }
 
+// ---- split-precision operands: x * scale = hi + lo (fp16 each, ~22 significant bits), scale a power of two that puts the
+// tensor's largest magnitude just below 2^14 (fp16 overflows at 65504; the lo plane keeps absolute errors at 2^-25 of that) ----
+constexpr int SPLIT_PARTS = 1024;                                  // upper bound on absmax partials
+
+__global__ void __launch_bounds__(256) absmax_partial_kernel(const float* __restrict__ in, int64_t n, float* __restrict__ part) {
+    const int64_t n4 = n >> 2;
+    float m = 0.f;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(in) + i);
+        m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+    }
+    for (int64_t i = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        m = fmaxf(m, fabsf(in[i]));
+    __shared__ float sm[8];
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        m = sm[threadIdx.x];
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffu, m, o));
+        if (threadIdx.x == 0) part[blockIdx.x] = m;
+    }
+}
+
+__global__ void __launch_bounds__(256) split_f16_kernel(const float* __restrict__ in, __half* __restrict__ hi, __half* __restrict__ lo,
+                                                        int64_t n, const float* __restrict__ part, int nparts,
+                                                        float* __restrict__ scale_out) {
+    __shared__ float sm[8];
+    __shared__ float s_scale;
+    float m = 0.f;
+    for (int i = threadIdx.x; i < nparts; i += blockDim.x) m = fmaxf(m, part[i]);
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float a = sm[0];
+#pragma unroll
+        for (int w = 1; w < 8; ++w) a = fmaxf(a, sm[w]);
+        float sc = 1.f, inv = 1.f;
+        if (a > 0.f && a <= 3.0e38f) {                             // zero / inf / nan tensors are passed through unscaled
+            int e;
+            frexpf(a, &e);                                         // a = f * 2^e, f in [0.5, 1)  =>  a * 2^(14 - e) < 2^14
+            int se = 14 - e;
+            if (se > 126) se = 126;
+            sc = ldexpf(1.f, se);
+            inv = ldexpf(1.f, -se);
+        }
+        s_scale = sc;
+        if (blockIdx.x == 0) { scale_out[0] = sc; scale_out[1] = inv; }
+    }
+    __syncthreads();
+    const float sc = s_scale;
+    const int64_t n4 = n >> 2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(in) + i);
+        const float x[4] = {v.x * sc, v.y * sc, v.z * sc, v.w * sc};
+        __half h[4], l[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { h[k] = __float2half_rn(x[k]); l[k] = __float2half_rn(x[k] - __half2float(h[k])); }
+        reinterpret_cast<uint2*>(hi)[i] = *reinterpret_cast<uint2*>(h);
+        reinterpret_cast<uint2*>(lo)[i] = *reinterpret_cast<uint2*>(l);
+    }
+    for (int64_t i = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float x = in[i] * sc;
+        const __half h = __float2half_rn(x);
+        hi[i] = h;
+        lo[i] = __float2half_rn(x - __half2float(h));
+    }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -699,6 +802,27 @@ int make_map_mn(CUtensorMap* map, const void* base, int64_t R, int64_t cols) {
     return r == CUDA_SUCCESS ? 0 : GAOT_E_BADARG;
 }
 
+// Split-precision operand planes [2, rows, cols] fp16 -> 3-D map {cols, rows, 2} with box {64, box_rows, 1}, SWIZZLE_128B.
+// K-major use: cols = contraction, box_rows = tile rows; MN-major use: rows = contraction, box {64, 64, 1}.
+int make_map_planes(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int box_rows) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return GAOT_E_BADARG;
+    cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, 2};
+    cuuint64_t strides[2] = {(cuuint64_t)cols * 2, (cuuint64_t)cols * (cuuint64_t)rows * 2};
+    cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r == CUDA_ERROR_INVALID_CONTEXT) {
+        cudaFree(nullptr);                                     // bind the primary context on this thread, then encode again
+        r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
+    return r == CUDA_SUCCESS ? 0 : GAOT_E_BADARG;
+}
+
 // output / add boxes of the fast epilogue: [rows, ld] matrix of fp32 or bf16, box {32 columns, 32 rows}, swizzle span =
 // the 32-column row (128 bytes fp32 / 64 bytes bf16)
 int make_map_box32(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, bool bf16, int box_cols = 32) {
@@ -731,17 +855,26 @@ int sm_count() {
     return n;
 }
 
-template <int BN, bool AMN, bool BMN, int CG>
+template <int BN, bool AMN, bool BMN, int CG, bool SPLIT = false>
 int launch_tc(const void* A, const void* B, TcArgs& g, cudaStream_t st) {
     constexpr int BNL = BN / CG;
     CUtensorMap ta, tb;
-    int rc = AMN ? make_map_mn(&ta, A, g.K, g.M) : make_map(&ta, A, g.M, g.K, TC_BM);
-    if (rc) return rc;
-    rc = BMN ? make_map_mn(&tb, B, g.K, g.N) : make_map(&tb, B, g.N, g.K, BNL);
+    int rc;
+    if (SPLIT) {
+        rc = AMN ? make_map_planes(&ta, A, g.K, g.M, 64) : make_map_planes(&ta, A, g.M, g.K, TC_BM);
+        if (rc) return rc;
+        rc = BMN ? make_map_planes(&tb, B, g.K, g.N, 64) : make_map_planes(&tb, B, g.N, g.K, BNL);
+    } else {
+        rc = AMN ? make_map_mn(&ta, A, g.K, g.M) : make_map(&ta, A, g.M, g.K, TC_BM);
+        if (rc) return rc;
+        rc = BMN ? make_map_mn(&tb, B, g.K, g.N) : make_map(&tb, B, g.N, g.K, BNL);
+    }
     if (rc) return rc;
     g.gm = (g.M + TC_BM * CG - 1) / (TC_BM * CG);
     g.gn = (g.N + BN - 1) / BN;
-    const int64_t kblocks = (g.K + TC_BK - 1) / TC_BK, tiles = g.gm * g.gn;
+    g.kb_real = (g.K + TC_BK - 1) / TC_BK;
+    const int64_t kblocks = g.kb_real * (SPLIT ? 3 : 1), tiles = g.gm * g.gn;   // SPLIT: three terms along the contraction
+    if (SPLIT) g.K = kblocks * TC_BK;                           // the kernel derives its k-block count from K
     const int workers = sm_count() / CG;                        // CTAs (CG = 1) or CTA pairs (CG = 2) resident on the chip
     int splits = 1;
     if (!g.out_bf16 && !g.act && !g.pre && tiles < workers && kblocks >= 8) {   // too few tiles for the chip: split the contraction
@@ -775,7 +908,7 @@ int launch_tc(const void* A, const void* B, TcArgs& g, cudaStream_t st) {
     constexpr int SMEM = TC_STAGES * (TC_BM * TC_BK * 2 + BNL * TC_BK * 2) + 8 * 8192 + 1024 + 512;
     static bool attr_done = false;
     if (!attr_done) {
-        GAOT_CHECK(cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN, AMN, BMN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+        GAOT_CHECK(cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN, AMN, BMN, CG, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
         attr_done = true;
     }
     const int64_t total = tiles * splits;
@@ -790,16 +923,16 @@ int launch_tc(const void* A, const void* B, TcArgs& g, cudaStream_t st) {
     attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    GAOT_CHECK(cudaLaunchKernelEx(&cfg, gemm_bf16_tc_kernel<BN, AMN, BMN, CG>, ta, tb, tc, tadd, g));
+    GAOT_CHECK(cudaLaunchKernelEx(&cfg, gemm_bf16_tc_kernel<BN, AMN, BMN, CG, SPLIT>, ta, tb, tc, tadd, g));
     GAOT_RETURN_LAST();
 }
 
 // N >= 256: CTA pairs on 256 x 256 tiles; narrower outputs: one CTA per 128 x 128 / 128 x 64 tile
-template <bool AMN, bool BMN>
+template <bool AMN, bool BMN, bool SPLIT = false>
 int dispatch_tc(const void* A, const void* B, TcArgs& g, cudaStream_t st) {
-    if (g.N <= 64) return launch_tc<64, AMN, BMN, 1>(A, B, g, st);
-    if (g.N < 256 || getenv("GAOT_GEMM_NO_PAIR")) return launch_tc<128, AMN, BMN, 1>(A, B, g, st);
-    return launch_tc<256, AMN, BMN, 2>(A, B, g, st);
+    if (g.N <= 64) return launch_tc<64, AMN, BMN, 1, SPLIT>(A, B, g, st);
+    if (g.N < 256 || getenv("GAOT_GEMM_NO_PAIR")) return launch_tc<128, AMN, BMN, 1, SPLIT>(A, B, g, st);
+    return launch_tc<256, AMN, BMN, 2, SPLIT>(A, B, g, st);
 }
 
 }  // namespace
@@ -842,6 +975,41 @@ GAOT_API int gaot_gemm_bf16_tn(const void* A, const void* B, float* C, int64_t M
     TcArgs g{C, M, N, R, nullptr, nullptr, 1, 0, 0, 1, accumulate, 0, 0, 0, nullptr, 0};
     cudaStream_t st = (cudaStream_t)stream;
     return dispatch_tc<true, true>(A, B, g, st);
+}
+
+GAOT_API int gaot_split_ws_floats(void) { return SPLIT_PARTS; }
+
+GAOT_API int gaot_split_f16(const float* in, void* planes, float* scale, float* ws, int64_t n, void* stream) {
+    if (!in || !planes || !scale || !ws || n < 1) return GAOT_E_BADARG;
+    if ((reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(planes) & 15) || n % 8 != 0) return GAOT_E_ALIGN;
+    cudaStream_t st = (cudaStream_t)stream;
+    int64_t parts = (n / 4 + 256 * 8 - 1) / (256 * 8);
+    if (parts > SPLIT_PARTS) parts = SPLIT_PARTS;
+    if (parts < 1) parts = 1;
+    absmax_partial_kernel<<<(unsigned)parts, 256, 0, st>>>(in, n, ws);
+    GAOT_NOTE_LAUNCHES(1);
+    __half* hi = reinterpret_cast<__half*>(planes);
+    split_f16_kernel<<<gaot_grid(n / 4 + 1, 256), 256, 0, st>>>(in, hi, hi + n, n, ws, (int)parts, scale);
+    GAOT_RETURN_LAST();
+}
+
+GAOT_API int gaot_gemm_split(const void* A, const void* B, float* C, int64_t M, int64_t N, int64_t K, int a_mn, int b_mn,
+                             const float* sa, const float* sb, const float* bias, const float* add, int64_t add_rows,
+                             int64_t ldadd, int act, float* pre, int accumulate, void* stream) {
+    if (!A || !B || !C || !sa || !sb || M < 1 || N < 1 || K < 1) return GAOT_E_BADARG;
+    if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15) || (reinterpret_cast<uintptr_t>(C) & 15))
+        return GAOT_E_ALIGN;
+    // TMA: 16-byte row pitch of every plane (the stored row length is K for a K-major operand, M / N for an MN-major one)
+    if ((a_mn ? M : K) % 8 != 0 || (b_mn ? N : K) % 8 != 0) return GAOT_E_ALIGN;
+    if (a_mn && !b_mn) return GAOT_E_BADARG;                       // (A^T, B^T-stored) is not a form any layer needs
+    if (add && (add_rows < 1 || ldadd < N)) return GAOT_E_BADARG;
+    if (act < 0 || act > 2 || ((act || pre) && accumulate)) return GAOT_E_BADARG;
+    if (M > 0x7fffffffLL || N > 0x7fffffffLL || 3 * K > 0x7fffffffLL) return GAOT_E_BADARG;
+    TcArgs g{C, M, N, K, bias, add, add ? add_rows : 1, ldadd, 0, 1, accumulate, 0, 0, act, pre, 0, sa, sb, 0};
+    cudaStream_t st = (cudaStream_t)stream;
+    if (a_mn) return dispatch_tc<true, true, true>(A, B, g, st);
+    if (b_mn) return dispatch_tc<false, true, true>(A, B, g, st);
+    return dispatch_tc<false, false, true>(A, B, g, st);
 }
 
 GAOT_API int gaot_cast_bf16(const float* in, void* out, int64_t rows, int64_t cols, void* out_t, void* stream) {

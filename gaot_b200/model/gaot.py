@@ -106,11 +106,12 @@ class GAOT(nn.Module):
             side.wait_stream(cur)
             wready = None
             with torch.cuda.stream(side):
-                if ops.get_precision() == "bf16":
-                    # bf16 copies / concatenations of the processor's weights: ~40 tiny kernels that would otherwise sit
-                    # between the processor's GEMMs; here they run under the encoder
+                if ops.get_precision() in ("bf16", "fp32"):
+                    # tensor-core operands (bf16 copies, or fp16 hi / lo planes in the parity mode) and concatenations of the
+                    # processor's weights: ~40 tiny kernels that would otherwise sit between the processor's GEMMs; here
+                    # they run under the encoder
                     ops.clear_prepared()
-                    wts = self.processor.prep_weights() + [ops.prepare_weight(self.patch_linear.weight)]
+                    wts = self.processor.prep_weights() + ops.prepare_weight(self.patch_linear.weight)
                     wready = torch.cuda.Event()
                     wready.record(side)
                 prep = self.decoder.prepare_fused(latent_tokens_coord, query_coord, decoder_nbrs, pndata.shape[0], C)

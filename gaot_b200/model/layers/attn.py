@@ -86,7 +86,7 @@ class GroupQueryFlashAttention(nn.Module):
     def prep_weights(self):
         """Concatenated q/k/v weight and the bf16 operands of this layer's GEMMs, ahead of time (ops.prepare_weight)."""
         self._wqkv = torch.cat([self.q_proj.weight, self.k_proj.weight, self.v_proj.weight], dim=0)
-        return [self._wqkv, ops.prepare_weight(self._wqkv), ops.prepare_weight(self.o_proj.weight)]
+        return [self._wqkv] + ops.prepare_weight(self._wqkv) + ops.prepare_weight(self.o_proj.weight)
 
     @classmethod
     def from_config(cls, input_size, hidden_size, config: AttentionConfig, positional_embedding="absolute"):
@@ -119,7 +119,7 @@ class FFN(nn.Module):
 
     def prep_weights(self):
         self._w13 = torch.cat([self.w1.weight, self.w3.weight], dim=0)
-        return [self._w13, ops.prepare_weight(self._w13), ops.prepare_weight(self.w2.weight)]
+        return [self._w13] + ops.prepare_weight(self._w13) + ops.prepare_weight(self.w2.weight)
 
     def forward(self, x, condition=None, residual=None):
         shape = x.shape

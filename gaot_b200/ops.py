@@ -16,16 +16,20 @@ from ._lib import call, ptr
 
 ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
 
-# Numerics mode of the processor's dense layers.  "fp32": FFMA kernels, the parity path (<= 1e-5 vs the
-# reference).  "bf16": tcgen05 tensor-core kernels with bf16 operands and fp32 accumulation, the
-# performance path (tolerance stated in tests/test_gpu_tc.py).  MAGNO stays fp32 in both modes.
+# Numerics mode of the processor's dense layers and attention.
+#   "fp32": the parity path (<= 1e-5 vs the reference, which computes in fp32) ON THE TENSOR CORES: every operand is split
+#           into fp16 hi + lo planes (~22 bits) and each product runs as three tcgen05 terms with fp32 accumulation
+#           (gaot_gemm_split / gaot_attention_*_split); shapes the split kernels do not take fall back to the FFMA kernels.
+#   "ffma": fp32 FFMA kernels everywhere (the round-1 parity path; kept as the cross-check of the split kernels).
+#   "bf16": tcgen05 kernels with bf16 operands and fp32 accumulation, the performance path (tolerances in tests/test_gpu_tc.py).
+# MAGNO's gather / reduce kernels stay fp32 in every mode.
 _PRECISION = "fp32"
 
 
 def set_precision(mode: str):
     global _PRECISION
-    if mode not in ("fp32", "bf16"):
-        raise ValueError("precision must be 'fp32' or 'bf16'")
+    if mode not in ("fp32", "ffma", "bf16"):
+        raise ValueError("precision must be 'fp32', 'ffma' or 'bf16'")
     _PRECISION = mode
 
 
@@ -241,15 +245,98 @@ _PREPARED = {}
 
 
 def prepare_weight(W):
-    """Register the bf16 copy of W (2-D, fp32) for the next tensor-core `linear(x, W, ...)` call with this very object."""
+    """Register the tensor-core operand of W (2-D, fp32) - its bf16 copy, or in 'fp32' mode its fp16 hi / lo planes and
+    scale - for the next `linear(x, W, ...)` call with this very object.  Returns the tensors it created (a caller that
+    prepares on a side stream must record_stream them on the consuming stream)."""
     Wc = _c(W)
+    if _PRECISION == "fp32":
+        if not _split_ok(Wc.shape[0], Wc.shape[1]):
+            return []
+        ent = split_f16(Wc)
+        _PREPARED[id(W)] = (W, ent)
+        return list(ent)
     wb = cast_bf16(Wc)[0]
     _PREPARED[id(W)] = (W, wb)
-    return wb
+    return [wb]
 
 
 def clear_prepared():
     _PREPARED.clear()
+
+
+# ---- split-precision (parity) tensor-core path -------------------------------------------------------------------------
+SPLIT_WS_FLOATS = 1024                        # == gaot_split_ws_floats() (checked by tests/test_abi.py)
+
+
+def split_f16(x2d):
+    """(planes fp16 [2, rows, cols], scale fp32 [2] = {s, 1/s}) with x * s = hi + lo; s is a power of two set from max|x| on
+    the device (no host read)."""
+    rows, cols = x2d.shape
+    planes = torch.empty((2, rows, cols), dtype=torch.float16, device=x2d.device)
+    scale = torch.empty(2, dtype=torch.float32, device=x2d.device)
+    ws = torch.empty(SPLIT_WS_FLOATS, dtype=torch.float32, device=x2d.device)
+    call("gaot_split_f16", ptr(x2d), ptr(planes), ptr(scale), ptr(ws), rows * cols)
+    return planes, scale
+
+
+def _split_ok(N, K):
+    return N % 8 == 0 and K % 8 == 0
+
+
+def gemm_split(A, sa, B, sb, M, N, K, a_mn=False, b_mn=False, bias=None, add=None, add_rows=0, act=ACT_NONE, pre=None,
+               out=None, accumulate=False):
+    """C[M,N] fp32 = act(opA opB + bias + add) on split operands (see include/gaot_b200.h: gaot_gemm_split)."""
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device=A.device)
+    call("gaot_gemm_split", ptr(A), ptr(B), ptr(out), M, N, K, int(a_mn), int(b_mn), ptr(sa), ptr(sb), ptr(bias), ptr(add),
+         int(add_rows), N, int(act), ptr(pre), int(accumulate))
+    return out
+
+
+class _LinearSplit(torch.autograd.Function):
+    """y = act(x W^T + bias + add[row % add_rows]) in fp32-equivalent precision on tcgen05 (three-term fp16 split)."""
+
+    @staticmethod
+    def forward(ctx, x, W, bias, add, act, prepared):
+        _need_cuda(x)
+        x, W = _c(x), _c(W)
+        M, K = x.shape
+        N = W.shape[0]
+        bias_c = _c(bias) if bias is not None else None
+        add_c = _c(add) if add is not None else None
+        add_rows = add_c.shape[0] if add_c is not None else 0
+        if add_c is not None and (add_c.shape[1] != N or M % add_rows != 0):
+            raise ValueError(f"broadcast-add of shape {tuple(add_c.shape)} does not tile an [{M},{N}] output")
+        xs, sx = split_f16(x)
+        ws, sw = prepared if prepared is not None else split_f16(W)
+        pre = torch.empty((M, N), dtype=torch.float32, device=x.device) if act != ACT_NONE else None
+        y = gemm_split(xs, sx, ws, sw, M, N, K, bias=bias_c, add=add_c, add_rows=add_rows, act=act, pre=pre)
+        ctx.save_for_backward(xs, sx, ws, sw, pre)
+        ctx.has_bias, ctx.add_rows, ctx.act = bias is not None, add_rows, act
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xs, sx, ws, sw, pre = ctx.saved_tensors
+        dy = _c(dy)
+        M, K = xs.shape[1], xs.shape[2]
+        N = ws.shape[1]
+        if ctx.act != ACT_NONE:
+            dpre = torch.empty_like(dy)
+            call("gaot_act_bwd", ptr(dy), ptr(pre), ptr(dpre), dy.numel(), ctx.act)
+            dy = dpre
+        dx = dW = db = dadd = None
+        if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+            dys, sdy = split_f16(dy)
+            if ctx.needs_input_grad[0]:
+                dx = gemm_split(dys, sdy, ws, sw, M, K, N, b_mn=True)                 # dY W, W planes read MN-major
+            if ctx.needs_input_grad[1]:
+                dW = gemm_split(dys, sdy, xs, sx, N, K, M, a_mn=True, b_mn=True)      # dY^T X, both read MN-major in place
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = col_sum(dy, M, N)
+        if ctx.add_rows and ctx.needs_input_grad[3]:
+            dadd = dy if ctx.add_rows == M else col_sum(dy, M // ctx.add_rows, ctx.add_rows * N).view(ctx.add_rows, N)
+        return dx, dW, db, dadd, None, None
 
 
 class _LinearTC(torch.autograd.Function):
@@ -319,6 +406,10 @@ def linear(x, W, bias=None, add=None, act=ACT_NONE, tc=False, out_bf16=False):
     if tc and _PRECISION == "bf16" and x.shape[-1] % 8 == 0 and (act == ACT_NONE or W.shape[0] % 4 == 0):
         ent = _PREPARED.get(id(W))
         return _LinearTC.apply(x, W, bias, add, out_bf16, act, ent[1] if ent is not None else None)
+    if tc and _PRECISION == "fp32" and _split_ok(W.shape[0], x.shape[-1]):
+        ent = _PREPARED.get(id(W))
+        return _LinearSplit.apply(x.float() if x.dtype != torch.float32 else x, W, bias, add, act,
+                                  ent[1] if ent is not None else None)
     if x.dtype != torch.float32:
         x = x.float()
     return _Linear.apply(x, W, bias, add, act)
@@ -498,9 +589,40 @@ class _AttentionTC(torch.autograd.Function):
         return dqkv, None, None, None, None, None
 
 
+class _AttentionSplit(torch.autograd.Function):
+    """Split-precision tensor-core attention: qkv fp32 [B*T, (H+2Hkv)*hd] -> o fp32 [B*T, H*hd] (hd 16 / 32)."""
+
+    @staticmethod
+    def forward(ctx, qkv, B, T, H, Hkv, hd):
+        qkv = _c(qkv)
+        ld = qkv.shape[1]
+        qs, sq = split_f16(qkv)
+        o = torch.empty((B * T, H * hd), dtype=torch.float32, device=qkv.device)
+        lse = torch.empty((B, H, T), dtype=torch.float32, device=qkv.device)
+        scale = 1.0 / (hd ** 0.5)
+        call("gaot_attention_fwd_split", ptr(qs), ptr(sq), ptr(o), ptr(lse), B, T, H, Hkv, hd, ld, scale)
+        ctx.save_for_backward(qs, sq, o, lse)
+        ctx.dims = (B, T, H, Hkv, hd, scale, ld)
+        return o
+
+    @staticmethod
+    def backward(ctx, do):
+        qs, sq, o, lse = ctx.saved_tensors
+        B, T, H, Hkv, hd, scale, ld = ctx.dims
+        do = _c(do)
+        dos, sg = split_f16(do)
+        dqkv = torch.empty((B * T, ld), dtype=torch.float32, device=do.device)
+        delta = torch.empty_like(lse)
+        call("gaot_attention_bwd_split", ptr(qs), ptr(sq), ptr(o), ptr(lse), ptr(do), ptr(dos), ptr(sg), ptr(delta), ptr(dqkv),
+             B, T, H, Hkv, hd, ld, scale)
+        return dqkv, None, None, None, None, None
+
+
 def attention(qkv, B, T, H, Hkv, hd):
     if qkv.dtype == torch.bfloat16:
         return _AttentionTC.apply(qkv, B, T, H, Hkv, hd)
+    if _PRECISION == "fp32" and hd in (16, 32) and qkv.shape[1] % 8 == 0 and qkv.shape[1] == (H + 2 * Hkv) * hd:
+        return _AttentionSplit.apply(qkv, B, T, H, Hkv, hd)
     return _Attention.apply(qkv, B, T, H, Hkv, hd)
 
 

@@ -190,6 +190,25 @@ int gaot_gemm_bf16_nn(const void* A, const void* B, void* C, int64_t M, int64_t 
  * M % 8 == 0, N % 8 == 0. */
 int gaot_gemm_bf16_tn(const void* A, const void* B, float* C, int64_t M, int64_t N, int64_t R, int accumulate,
                       void* stream);
+/* Split-precision (parity) tensor-core path.  The reference computes every nn.Linear of the processor in fp32
+ * (src/core/base_trainer.py:63-68 admits only fp32/fp64); north_star asks for <= 1e-5 of it.  An fp32 tensor x is
+ * written as two fp16 planes, x * scale = hi + lo (~22 significant bits), scale a power of two chosen from max|x| so that
+ * the largest magnitude sits just below 2^14; a product then needs three tensor-core terms (lo*hi + hi*lo + hi*hi, the
+ * lo*lo term is < 2^-22 relative) accumulated in fp32 in TMEM - the same tcgen05 / TMA kernel as gaot_gemm_bf16 with a
+ * contraction that is three terms long.
+ * gaot_split_f16: planes = fp16 [2, n] (hi plane then lo plane), scale = {scale, 1 / scale} (device), ws = workspace of
+ * gaot_split_ws_floats() floats; n % 8 == 0. */
+int gaot_split_ws_floats(void);
+int gaot_split_f16(const float* in, void* planes, float* scale, float* ws, int64_t n, void* stream);
+/* C[M,N] (fp32) = act(opA opB / (scale_a scale_b) + bias + add[(m % add_rows), n]) on split operands:
+ *   a_mn = 0: A planes [2, M, K] (contraction along the stored row);   a_mn = 1: A planes [2, K, M] (contraction over rows)
+ *   b_mn = 0: B planes [2, N, K] (nn.Linear weight layout);            b_mn = 1: B planes [2, K, N]
+ * i.e. forward (0,0): x W^T, input gradient (0,1): dY W, weight gradient (1,1): dY^T X, each operand in its natural
+ * layout.  sa / sb: the {scale, 1 / scale} pairs of gaot_split_f16.  bias / add / act / pre / accumulate as in
+ * gaot_gemm_bf16. */
+int gaot_gemm_split(const void* A, const void* B, float* C, int64_t M, int64_t N, int64_t K, int a_mn, int b_mn,
+                    const float* sa, const float* sb, const float* bias, const float* add, int64_t add_rows,
+                    int64_t ldadd, int act, float* pre, int accumulate, void* stream);
 /* out[r,c] = bf16(in[r,c]) (out nullable) and/or out_t[c,r] = bf16(in[r,c]) (out_t nullable) */
 int gaot_cast_bf16(const float* in, void* out, int64_t rows, int64_t cols, void* out_t, void* stream);
 /* out_t[c,r] = in[r,c], bf16 */
@@ -242,6 +261,19 @@ int gaot_attention_fwd_bf16(const void* qkv, void* o, float* lse, int64_t B, int
 int gaot_attention_bwd_bf16(const void* qkv, const void* o, const float* lse, const void* dout, float* delta,
                             float* dq_acc, void* dqkv, int64_t B, int64_t T, int64_t H, int64_t Hkv, int64_t hd,
                             int64_t ld, float scale, void* stream);
+
+/* Split-precision (parity) tensor-core attention: the same tcgen05 kernels with fp16 hi / lo operand planes
+ * (gaot_split_f16 of the fp32 fused qkv matrix [B*T, ld] -> qkv_planes [2, B*T, ld], qscale = its {scale, 1/scale}),
+ * three tensor-core terms per product, fp32 softmax, probabilities split the same way, fp32 outputs.
+ * o [B*T, H*hd] fp32, lse [B,H,T].  hd in {16, 32}. */
+int gaot_attention_fwd_split(const void* qkv_planes, const float* qscale, float* o, float* lse, int64_t B, int64_t T,
+                             int64_t H, int64_t Hkv, int64_t hd, int64_t ld, float scale, void* stream);
+/* Backward: dout [B*T, H*hd] fp32 and its planes / scale; delta [B,H,T] workspace; dqkv [B*T, ld] fp32 receives
+ * dQ | dK | dV in the layout of qkv. */
+int gaot_attention_bwd_split(const void* qkv_planes, const float* qscale, const float* o, const float* lse,
+                             const float* dout, const void* dout_planes, const float* gscale, float* delta, float* dqkv,
+                             int64_t B, int64_t T, int64_t H, int64_t Hkv, int64_t hd, int64_t ld, float scale,
+                             void* stream);
 
 /* Patchify / un-patchify permutations of GAOT.process (src/model/gaot.py:182-185, 202-205, 225-231).
  * grid [B, H*W*(D), C] <-> tokens [B, T, P^dims * C]; dims 2 or 3; to_tokens 1 = patchify. */

@@ -453,6 +453,77 @@ def gaot_attention_bwd_bf16(qkv, o, lse, dout, delta, dq_acc, dqkv, B, T, H, Hkv
     d[:, (H + Hkv) * hd:(H + 2 * Hkv) * hd] = V.grad.reshape(B * T, Hkv * hd).to(torch.bfloat16)
 
 
+# ---- split-precision path: planes hold fp16(hi), fp16(lo) of x * scale; products use the three terms the kernel issues ----
+def _f16(ptr, shape):
+    n = int(np.prod(shape))
+    raw = np.ctypeslib.as_array(ctypes.cast(int(ptr), ctypes.POINTER(ctypes.c_uint16)), shape=(n,))
+    return torch.from_numpy(raw.view(np.int16)).view(torch.float16).view(shape)
+
+
+def gaot_split_f16(inp, planes, scale, ws, n):
+    x = _t(inp, (n,))
+    a = float(x.abs().max())
+    sc = 1.0
+    if 0.0 < a <= 3.0e38:
+        _, e = math.frexp(a)
+        sc = math.ldexp(1.0, min(14 - e, 126))
+    xs = x * sc                                           # power-of-two scale: exact in fp32
+    hi = xs.to(torch.float16)
+    lo = (xs - hi.float()).to(torch.float16)
+    pl = _f16(planes, (2, n))
+    pl[0], pl[1] = hi, lo
+    _arr(scale, (2,))[:] = (sc, 1.0 / sc)
+
+
+def _split3(A, B):
+    """(A_lo B_hi + A_hi B_lo + A_hi B_hi) with the contraction over the last axis of A and the first of B"""
+    ah, al, bh, bl = A[0].double(), A[1].double(), B[0].double(), B[1].double()
+    return al @ bh + ah @ bl + ah @ bh
+
+
+def gaot_gemm_split(A, B, C, M, N, K, a_mn, b_mn, sa, sb, bias, add, add_rows, ldadd, act, pre, accumulate):
+    a = _f16(A, (2, K, M)).transpose(1, 2) if a_mn else _f16(A, (2, M, K))
+    b = _f16(B, (2, K, N)) if b_mn else _f16(B, (2, N, K)).transpose(1, 2)
+    v = _split3(a, b) * float(_arr(sa, (2,))[1]) * float(_arr(sb, (2,))[1])
+    if bias:
+        v = v + _t(bias, (N,)).double()
+    if add:
+        v = v + _strided(add, add_rows, N, ldadd).double().repeat(M // add_rows, 1)
+    if pre:
+        _t(pre, (M, N))[:] = v.float()
+    v = _act(v, act)
+    c = _t(C, (M, N))
+    c[:] = (v + c.double()).float() if accumulate else v.float()
+
+
+def _plane_heads(planes, B, T, ld, H, hd, col0):
+    p = _f16(planes, (2, B * T, ld))[:, :, col0:col0 + H * hd].double()
+    return (p[0] + p[1]).reshape(B, T, H, hd)
+
+
+def gaot_attention_fwd_split(qkv, qscale, o, lse, B, T, H, Hkv, hd, ld, scale):
+    inv = float(_arr(qscale, (2,))[1])
+    Q, K, V = (_plane_heads(qkv, B, T, ld, H, hd, 0) * inv, _plane_heads(qkv, B, T, ld, Hkv, hd, H * hd) * inv,
+               _plane_heads(qkv, B, T, ld, Hkv, hd, (H + Hkv) * hd) * inv)
+    out, l = _attn_ref(Q, K, V, H, Hkv, scale)
+    _arr(o, (B, T, H, hd))[:] = out.float().numpy()
+    _arr(lse, (B, H, T))[:] = l.float().numpy()
+
+
+def gaot_attention_bwd_split(qkv, qscale, o, lse, dout, dout_planes, gscale, delta, dqkv, B, T, H, Hkv, hd, ld, scale):
+    inv, invg = float(_arr(qscale, (2,))[1]), float(_arr(gscale, (2,))[1])
+    with torch.enable_grad():
+        Q = (_plane_heads(qkv, B, T, ld, H, hd, 0) * inv).requires_grad_(True)
+        K = (_plane_heads(qkv, B, T, ld, Hkv, hd, H * hd) * inv).requires_grad_(True)
+        V = (_plane_heads(qkv, B, T, ld, Hkv, hd, (H + Hkv) * hd) * inv).requires_grad_(True)
+        out, _ = _attn_ref(Q, K, V, H, Hkv, scale)
+        out.backward(_plane_heads(dout_planes, B, T, H * hd, H, hd, 0) * invg)
+    d = _t(dqkv, (B * T, ld))
+    d[:, :H * hd] = Q.grad.reshape(B * T, H * hd).float()
+    d[:, H * hd:(H + Hkv) * hd] = K.grad.reshape(B * T, Hkv * hd).float()
+    d[:, (H + Hkv) * hd:(H + 2 * Hkv) * hd] = V.grad.reshape(B * T, Hkv * hd).float()
+
+
 def gaot_patch_permute(inp, out, B, dims, H, W, D, P, C, to_tokens):
     grid = (H, W) if dims == 2 else (H, W, D)
     nodes, pv = int(np.prod(grid)), P ** dims

@@ -17,6 +17,16 @@ DEV = "cuda"
 FWD_TOL = 1e-5
 
 
+@pytest.fixture(params=["fp32", "ffma"])
+def parity_mode(request):
+    """Both parity modes of the processor: 'fp32' = split-precision tcgen05 kernels (three fp16 terms per product),
+    'ffma' = fp32 FFMA kernels.  Same tolerances."""
+    from gaot_b200 import ops
+    ops.set_precision(request.param)
+    yield request.param
+    ops.set_precision("fp32")
+
+
 def _run(name, use_golden_graphs, fuse=True):
     c = cases.CASES[name]
     g = load_golden(name)
@@ -47,7 +57,7 @@ def _run(name, use_golden_graphs, fuse=True):
 @pytest.mark.parametrize("name,golden_graph", [("tiny2d", False), ("tiny2d", True), ("tiny3d", False),
                                                ("plain2d", False), ("vx2d", True), ("dot2d", False), ("npe2d", False), ("pnet2d", False),
                                                ("cond2d", False), ("vxmix", True)])
-def test_forward_backward_matches_reference(name, golden_graph, fuse):
+def test_forward_backward_matches_reference(name, golden_graph, fuse, parity_mode):
     c, g, model, out, loss, inter = _run(name, golden_graph, fuse)
     assert rel_l2(inter["enc_out"], g["enc_out"]) < FWD_TOL
     assert rel_l2(out, g["out"]) < FWD_TOL
@@ -78,7 +88,7 @@ def test_vx_graphs_built_on_gpu_match_reference():
             assert torch.equal(mine["neighbors_row_splits"].cpu(), ref["neighbors_row_splits"])
 
 
-def test_cfg2_matches_reference_summary():
+def test_cfg2_matches_reference_summary(parity_mode):
     """BASELINE cfg-2 geometry (N=9216, latent 64x64, r=0.033, 3.4 M parameters), B=2."""
     c = cases.CASES["cfg2"]
     g = load_golden("cfg2")

@@ -1,6 +1,7 @@
 """CPU tests of the host side above the C ABI: the library loads and exports the header's symbols, the
 product refuses CPU tensors, and - with the ABI routed to tests/abi_emulator.py - the module wiring,
 autograd formulas, vx graph merging and the flat-buffer trainer reproduce the reference's golden vectors."""
+import contextlib
 import os
 
 import numpy as np
@@ -30,6 +31,17 @@ def test_product_path_has_no_cpu_fallback():
         ops.radius_csr(torch.zeros(4, 2), torch.zeros(4, 2), 0.1)
 
 
+@contextlib.contextmanager
+def _precision(mode):
+    from gaot_b200 import ops
+    old = ops.get_precision()
+    ops.set_precision(mode)
+    try:
+        yield
+    finally:
+        ops.set_precision(old)
+
+
 def test_nothing_in_the_product_imports_the_oracle():
     root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gaot_b200")
     for dp, _, fs in os.walk(root):
@@ -39,12 +51,15 @@ def test_nothing_in_the_product_imports_the_oracle():
                 assert "import oracle" not in src and "from oracle" not in src and "abi_emulator" not in src, f
 
 
+@pytest.mark.parametrize("precision", ["fp32", "ffma"])
 @pytest.mark.parametrize("fuse", [True, False])
 @pytest.mark.parametrize("name", ["tiny2d", "tiny3d", "plain2d", "vx2d", "dot2d", "npe2d", "pnet2d", "cond2d", "vxmix"])
-def test_model_wiring_matches_reference_golden(name, fuse):
+def test_model_wiring_matches_reference_golden(name, fuse, precision):
+    """Both parity modes through the emulated ABI: 'fp32' = split-precision tensor-core entry points (the emulator forms
+    the same fp16 hi / lo planes and the same three product terms as the kernels), 'ffma' = plain fp32 entry points."""
     c = cases.CASES[name]
     g = load_golden(name)
-    with abi_emulator.install() as calls:
+    with abi_emulator.install() as calls, _precision(precision):
         from gaot_b200 import ops
         model = build_model(c, "cpu")
         model.encoder.fuse_affine = model.decoder.fuse_affine = fuse
@@ -56,7 +71,8 @@ def test_model_wiring_matches_reference_golden(name, fuse):
         out = model(lat, x, pn, encoder_nbrs=enc, decoder_nbrs=dec, condition=cases.case_condition(name))
         loss = ops.mse_loss(out, tgt)
         loss.backward()
-        assert "gaot_attention_bwd" in calls
+        assert ("gaot_attention_bwd_split" if precision == "fp32" else "gaot_attention_bwd") in calls
+        assert ("gaot_gemm_split" in calls) == (precision == "fp32")
         fusable = fuse and c["magno"]["lifting_channels"] % 4 == 0        # tiny3d has C = 6: falls back
         assert ("gaot_lift_aggregate_bwd" in calls) == fusable
         if not fusable:
