@@ -113,6 +113,15 @@ def call_work(name, a):
     if name == "gaot_gemm_bf16":
         M, N, K = a[3], a[4], a[5]
         return 2.0 * M * N * K, 2.0 * (M * K + N * K) + (2.0 if a[6] else 4.0) * M * N
+    if name == "gaot_gemm_split":
+        M, N, K = a[3], a[4], a[5]
+        return 2.0 * M * N * K, 4.0 * (M * K + N * K + M * N)
+    if name == "gaot_attention_fwd_split":
+        B, T, H, hd = a[4], a[5], a[6], a[8]
+        return 4.0 * B * H * T * T * hd, 4.0 * B * T * H * hd * 4
+    if name == "gaot_attention_bwd_split":
+        B, T, H, hd = a[9], a[10], a[11], a[13]
+        return 10.0 * B * H * T * T * hd, 4.0 * B * T * H * hd * 8
     if name in ("gaot_gemm_bf16_nn", "gaot_gemm_bf16_tn"):
         M, N, K = a[3], a[4], a[5]
         return 2.0 * M * N * K, 2.0 * (M * K + N * K) + 4.0 * M * N
@@ -480,7 +489,7 @@ def main():
     ap.add_argument("--no-fp32-leg", action="store_true", help="skip the extra fp32-parity-mode timing")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
     ap.add_argument("--dump-calls", default="", help="write the per-ABI-call timing list of one step to this file")
-    ap.add_argument("--precision", default=os.environ.get("GAOT_B200_PRECISION", "bf16"), choices=["fp32", "bf16"],
+    ap.add_argument("--precision", default=os.environ.get("GAOT_B200_PRECISION", "bf16"), choices=["fp32", "ffma", "bf16"],
                     help="processor numerics: fp32 parity path or bf16 tensor-core path")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
