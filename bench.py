@@ -1,6 +1,7 @@
 """bench.py - mesh-points/sec of one GAOT training step (forward + backward + AdamW) on synthetic meshes.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg2_16k|cfg4|cfg5]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg2_16k|cfg3|cfg4|cfg5]
+                    [--precision bf16|fp32|ffma] [--scaling weak|strong --global-batch G]
     torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...      (one rank per GPU, NCCL)
 
 One "step" = zero_grad -> GAOT.forward -> MSE -> backward -> (gradient all-reduce) -> AdamW over one
@@ -8,8 +9,10 @@ batch of synthetic input (reference src/utils/optimizers.py:252-255).  Default w
 configs[1]: Poisson-Gauss 2-D, N = 9216 points, latent 64x64, batch 32 PER GPU (weak scaling).
 Prints ONE JSON line (rank 0).  `value` = points/s with inputs resident in HBM; `e2e` = the same metric
 through the public API with pinned-host inputs copied H2D and the loss read back D2H every step.
-`--impl reference` times the reference algorithm's CPU port (oracle/, all host threads) on a bounded
-sample of the same workload.
+`roofline` = the hot kernels timed in isolation (attention backward is the dominant one by the committed ncu launch list);
+`fp32_parity_mode` = the same step in the 1e-5 parity mode; `strong_scaling_cfg5` / `rollout_cfg4` = BASELINE configs[4] /
+configs[3] as extra blocks of the default line.  `--impl reference` times the reference algorithm's CPU port (oracle/, all
+host threads) on the same workload, batch and warm-up.
 """
 from __future__ import annotations
 
@@ -105,116 +108,382 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-# algorithmic work per ABI call (DESIGN.md section "kernels"): (flops, bytes) from the call's own arguments
-def call_work(name, a):
-    if name == "gaot_gemm_f32":
-        M, N, K = a[3], a[4], a[5]
-        return 2.0 * M * N * K, 4.0 * (M * K + N * K + M * N)
-    if name == "gaot_gemm_bf16":
-        M, N, K = a[3], a[4], a[5]
-        return 2.0 * M * N * K, 2.0 * (M * K + N * K) + (2.0 if a[6] else 4.0) * M * N
-    if name == "gaot_gemm_split":
-        M, N, K = a[3], a[4], a[5]
-        return 2.0 * M * N * K, 4.0 * (M * K + N * K + M * N)
-    if name == "gaot_attention_fwd_split":
-        B, T, H, hd = a[4], a[5], a[6], a[8]
-        return 4.0 * B * H * T * T * hd, 4.0 * B * T * H * hd * 4
-    if name == "gaot_attention_bwd_split":
-        B, T, H, hd = a[9], a[10], a[11], a[13]
-        return 10.0 * B * H * T * T * hd, 4.0 * B * T * H * hd * 8
-    if name in ("gaot_gemm_bf16_nn", "gaot_gemm_bf16_tn"):
-        M, N, K = a[3], a[4], a[5]
-        return 2.0 * M * N * K, 2.0 * (M * K + N * K) + 4.0 * M * N
-    if name == "gaot_attention_fwd":
-        B, T, H, hd = a[5], a[6], a[7], a[9]
-        return 4.0 * B * H * T * T * hd, 4.0 * B * T * H * hd * 4
-    if name == "gaot_attention_fwd_bf16":
-        B, T, H, hd = a[3], a[4], a[5], a[7]
-        return 4.0 * B * H * T * T * hd, 2.0 * B * T * H * hd * 4
-    if name == "gaot_attention_bwd_bf16":
-        B, T, H, hd = a[7], a[8], a[9], a[11]
-        return 10.0 * B * H * T * T * hd, 2.0 * B * T * H * hd * 8
-    if name == "gaot_attention_bwd":
-        B, T, H, hd = a[10], a[11], a[12], a[14]
-        return 10.0 * B * H * T * T * hd, 4.0 * B * T * H * hd * 8
-    return None, None
+def load_peaks():
+    """Roofline denominators: MEASURED_PEAKS.json (driver-written) or the profiling guide's fallback."""
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        j = json.load(open(pk))
+        return {"hbm_gbs": j["hbm_gbs"], "bf16_burst": j["bf16_tflops"], "bf16_sustained": j["bf16_tflops_sustained"],
+                "sm_max_mhz": j.get("sm_max_mhz", 1965.0), "src": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_burst": 1590.0, "bf16_sustained": 1400.0, "sm_max_mhz": 1965.0, "src": "fallback"}
 
 
-def run_ours(args, w):
-    import torch.distributed as dist
-    from gaot_b200 import _lib
-    from gaot_b200.model import GAOT
-    from gaot_b200.trainer import TrainStep
+class Dist:
+    """torch.distributed plumbing of one rank (one process per GPU, NCCL)."""
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py (impl ours) needs a CUDA device: the product has no CPU path")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    B = args.batch or w["B"]
-    from gaot_b200 import ops as _ops
-    _ops.set_precision(args.precision)
-    torch.manual_seed(42)
-    model = GAOT(w["cin"], w["cout"], make_config(w)).to(dev)
-    step = TrainStep(model, lr=1e-3, weight_decay=1e-2)
-    lat, x, pn, tgt = synth(w, rank, B)
-    lat_d, x_d = lat.to(dev), x.to(dev)
-    pn_d, tgt_d = pn.to(dev), tgt.to(dev)
-    pn_h, tgt_h = pn.pin_memory(), tgt.pin_memory()
-    pn_s, tgt_s = torch.empty_like(pn_d), torch.empty_like(tgt_d)
+    def __init__(self):
+        import torch.distributed as dist
+        self.dist = dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py (impl ours) needs a CUDA device: the product has no CPU path")
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, K):
-        barrier()
+    def timed(self, fn, K):
+        """K calls of fn between a barrier + synchronize on both sides; CUDA events; max over ranks (ms)."""
+        self.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(K):
             fn()
         e1.record()
-        barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        self.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(ms, op=self.dist.ReduceOp.MAX)
         return float(ms)
 
-    vx = bool(w.get("vx"))
-    enc_graphs = dec_graphs = None
-    if vx:      # per-sample graphs built on the GPU in one batched launch each (reference: graph_builder.py:28-87)
-        from gaot_b200 import ops as _o
-        enc_graphs = [[g_] for g_ in _o.radius_csr(x_d, lat_d, w["radius"])]
-        dec_graphs = [[g_] for g_ in _o.radius_csr(lat_d, x_d, w["radius"])]
+    def close(self):
+        if self.world > 1:
+            self.dist.barrier()
+            self.dist.destroy_process_group()
 
-    def eager_step():
-        if vx:
-            return step.variable_coords_step(lat_d, pn_d, tgt_d, x_d, enc_graphs, dec_graphs)
-        return step.fixed_coords_step(lat_d, x_d, pn_d, tgt_d)
 
-    if args.no_graph:
-        graphed = None
+class Case:
+    """One workload on this rank: model, flat-buffer trainer, synthetic batch, captured step."""
+
+    def __init__(self, D, w, B, precision, use_graph=True):
+        from gaot_b200 import ops as O
+        from gaot_b200.model import GAOT
+        from gaot_b200.trainer import TrainStep
+        self.D, self.w, self.B, self.precision = D, w, B, precision
+        dev = D.dev
+        O.set_precision(precision)
+        torch.manual_seed(42)
+        self.model = GAOT(w["cin"], w["cout"], make_config(w)).to(dev)
+        self.step = TrainStep(self.model, lr=1e-3, weight_decay=1e-2)
+        lat, x, pn, tgt = synth(w, D.rank, B)
+        self.lat, self.x, self.pn, self.tgt = lat, x, pn, tgt
+        self.lat_d, self.x_d = lat.to(dev), x.to(dev)
+        self.pn_d, self.tgt_d = pn.to(dev), tgt.to(dev)
+        self.pn_s, self.tgt_s = torch.empty_like(self.pn_d), torch.empty_like(self.tgt_d)
+        self.vx = bool(w.get("vx"))
+        self.enc_graphs = self.dec_graphs = None
+        if self.vx:   # per-sample graphs built on the GPU in one batched launch each (reference: graph_builder.py:28-87)
+            self.enc_graphs = [[g_] for g_ in O.radius_csr(self.x_d, self.lat_d, w["radius"])]
+            self.dec_graphs = [[g_] for g_ in O.radius_csr(self.lat_d, self.x_d, w["radius"])]
+        self.graphed = None
+        if use_graph:
+            for _ in range(2):
+                self.eager_step()
+            if self.vx:
+                self.graphed = self.step.capture_variable_coords(self.lat_d, self.pn_s, self.tgt_s, self.x_d, self.enc_graphs,
+                                                                 self.dec_graphs)
+            else:
+                self.graphed = self.step.capture_fixed_coords(self.lat_d, self.x_d, self.pn_s, self.tgt_s)
+            self.pn_s.copy_(self.pn_d)
+            self.tgt_s.copy_(self.tgt_d)
+
+    def eager_step(self):
+        from gaot_b200 import ops as O
+        O.set_precision(self.precision)
+        if self.vx:
+            return self.step.variable_coords_step(self.lat_d, self.pn_d, self.tgt_d, self.x_d, self.enc_graphs, self.dec_graphs)
+        return self.step.fixed_coords_step(self.lat_d, self.x_d, self.pn_d, self.tgt_d)
+
+    def dev_step(self):
+        return self.graphed() if self.graphed is not None else self.eager_step()
+
+    def edges(self):
+        if self.vx:
+            return sum(int(g_[0]["neighbors_index"].numel()) for g_ in self.enc_graphs)
+        return int(self.model.encoder.neighbor_cache["graph"][1][0]["neighbors_index"].numel())
+
+
+def rotating(make, copies):
+    """`copies` independent argument sets so that back-to-back launches never find their inputs in the 126 MB L2."""
+    return [make(i) for i in range(copies)]
+
+
+def time_launches(fns, reps):
+    """Average device time (us) of one launch: `reps` launches, cycling through the argument sets, between ONE pair of CUDA
+    events on the launching stream (torch's current stream is the stream _lib.call launches on)."""
+    for f in fns:
+        f()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(reps):
+        fns[i % len(fns)]()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e3 / reps
+
+
+def isolated_tensor_kernels(w, B, dev, peaks, precision):
+    """Each hot tensor-core entry point timed ALONE (20 launches between one event pair, inputs rotated through > 2 L2s of
+    memory): attention backward / forward and the three GEMM forms of the largest processor layer (SwiGLU up-projection).
+    Algorithmic FLOPs: attention 4 / 10 * B*H*T^2*hd, GEMM 2*M*N*K.  Peak: the measured cuBLAS bf16 BURST
+    figure (kernels timed in isolation)."""
+    from gaot_b200 import ops as O
+    from gaot_b200._lib import call, ptr
+    T = 1
+    for g_ in w["latent"]:
+        T *= g_ // w["patch"]
+    H, hd, Dh = w["heads"], w["dh"] // w["heads"], w["dh"]
+    F = 4 * Dh
+    rows = B * T
+    Wq = 3 * H * hd
+    scale = 1.0 / hd ** 0.5
+    peak = peaks["bf16_burst"]
+    out = []
+    split = precision != "bf16"
+    gen = torch.Generator(device=dev).manual_seed(5)
+
+    def rnd(shape, dtype=torch.float32, s=1.0):
+        return (torch.randn(shape, generator=gen, device=dev, dtype=torch.float32) * s).to(dtype)
+
+    def entry(name, kernel, flops, us, note=None):
+        d = {"entry": name, "kernel": kernel, "bound": "tensor", "us": round(us, 2), "achieved": round(flops / us / 1e6, 1),
+             "peak": peak, "unit": "TFLOP/s", "frac": round(flops / us / 1e6 / peak, 4)}
+        if note:
+            d["note"] = note
+        out.append(d)
+
+    copies = max(2, int(300e6 // (rows * Wq * (4 if split else 2))) + 1)
+    if not split:
+        sets = []
+        for i in range(copies):
+            qkv = rnd((rows, Wq), torch.bfloat16)
+            o = torch.empty((rows, H * hd), dtype=torch.bfloat16, device=dev)
+            lse = torch.empty((B, H, T), device=dev)
+            sets.append((qkv, o, lse, rnd((rows, H * hd), torch.bfloat16, 1e-3), torch.empty((B, H, T), device=dev),
+                         torch.empty((rows, H * hd), device=dev), torch.empty((rows, Wq), dtype=torch.bfloat16, device=dev)))
+        fw = [lambda s_=s_: call("gaot_attention_fwd_bf16", ptr(s_[0]), ptr(s_[1]), ptr(s_[2]), B, T, H, H, hd, Wq, scale) for s_ in sets]
+        us = time_launches(fw, 20)
+        entry("gaot_attention_fwd_bf16", f"attn_fwd_tc_kernel<{hd}>", 4.0 * B * H * T * T * hd, us)
+        bw = [lambda s_=s_: call("gaot_attention_bwd_bf16", ptr(s_[0]), ptr(s_[1]), ptr(s_[2]), ptr(s_[3]), ptr(s_[4]), ptr(s_[5]),
+                                 ptr(s_[6]), B, T, H, H, hd, Wq, scale) for s_ in sets]
+        us = time_launches(bw, 20)
+        entry("gaot_attention_bwd_bf16", f"attn_bwd_tc_kernel<{hd}>", 10.0 * B * H * T * T * hd, us,
+              "entry point = delta + memset + attn_bwd_tc_kernel + dq store; the tcgen05 kernel is ~95 % of it")
+        del sets, fw, bw
+        xs = [rnd((rows, Dh), torch.bfloat16) for _ in range(4)]
+        w13 = rnd((2 * F, Dh), torch.bfloat16, Dh ** -0.5)
+        ys = [torch.empty((rows, 2 * F), dtype=torch.bfloat16, device=dev) for _ in range(4)]
+        us = time_launches([lambda i=i: call("gaot_gemm_bf16", ptr(xs[i]), ptr(w13), ptr(ys[i]), rows, 2 * F, Dh, 1, 0, 0, 0, 2 * F, 0, 0, 0)
+                            for i in range(4)], 20)
+        entry("gaot_gemm_bf16", "gemm_bf16_tc_kernel<256,0,0,2>", 2.0 * rows * 2 * F * Dh, us, f"forward x W^T, {rows}x{2 * F}x{Dh}, bf16 out")
+        dxs = [torch.empty((rows, Dh), dtype=torch.bfloat16, device=dev) for _ in range(4)]
+        us = time_launches([lambda i=i: call("gaot_gemm_bf16_nn", ptr(ys[i]), ptr(w13), ptr(dxs[i]), rows, Dh, 2 * F, 1) for i in range(4)], 20)
+        entry("gaot_gemm_bf16_nn", "gemm_bf16_tc_kernel<256,0,1,2>", 2.0 * rows * 2 * F * Dh, us, f"input gradient dY W, {rows}x{Dh}x{2 * F}")
+        dW = torch.empty((2 * F, Dh), device=dev)
+        us = time_launches([lambda i=i: call("gaot_gemm_bf16_tn", ptr(ys[i]), ptr(xs[i]), ptr(dW), 2 * F, Dh, rows, 0) for i in range(4)], 20)
+        entry("gaot_gemm_bf16_tn", "gemm_bf16_tc_kernel<256,1,1,2>", 2.0 * rows * 2 * F * Dh, us, f"weight gradient dY^T X, {2 * F}x{Dh}x{rows}")
     else:
-        for _ in range(2):
-            eager_step()
-        if vx:
-            graphed = step.capture_variable_coords(lat_d, pn_s, tgt_s, x_d, enc_graphs, dec_graphs)
-        else:
-            graphed = step.capture_fixed_coords(lat_d, x_d, pn_s, tgt_s)       # static input buffers pn_s / tgt_s
-        pn_s.copy_(pn_d); tgt_s.copy_(tgt_d)
+        sets = []
+        for i in range(copies):
+            qp, qs = O.split_f16(rnd((rows, Wq)))
+            do = rnd((rows, H * hd), s=1e-3)
+            dp, ds = O.split_f16(do)
+            sets.append((qp, qs, torch.empty((rows, H * hd), device=dev), torch.empty((B, H, T), device=dev), do, dp, ds,
+                         torch.empty((B, H, T), device=dev), torch.empty((rows, Wq), device=dev)))
+        fw = [lambda s_=s_: call("gaot_attention_fwd_split", ptr(s_[0]), ptr(s_[1]), ptr(s_[2]), ptr(s_[3]), B, T, H, H, hd, Wq, scale)
+              for s_ in sets]
+        us = time_launches(fw, 20)
+        entry("gaot_attention_fwd_split", f"attn_fwd_tc_kernel<{hd},split>", 4.0 * B * H * T * T * hd, us,
+              "fp32-equivalent FLOPs; the kernel issues 3x the tensor-core work")
+        bw = [lambda s_=s_: call("gaot_attention_bwd_split", ptr(s_[0]), ptr(s_[1]), ptr(s_[2]), ptr(s_[3]), ptr(s_[4]), ptr(s_[5]), ptr(s_[6]),
+                                 ptr(s_[7]), ptr(s_[8]), B, T, H, H, hd, Wq, scale) for s_ in sets]
+        us = time_launches(bw, 20)
+        entry("gaot_attention_bwd_split", f"attn_bwd_tc_kernel<{hd},split>", 10.0 * B * H * T * T * hd, us,
+              "fp32-equivalent FLOPs; the kernel issues 3x the tensor-core work")
+        del sets, fw, bw
+        xs = [O.split_f16(rnd((rows, Dh))) for _ in range(3)]
+        wp, wsc = O.split_f16(rnd((2 * F, Dh), s=Dh ** -0.5))
+        ys = [torch.empty((rows, 2 * F), device=dev) for _ in range(3)]
+        us = time_launches([lambda i=i: O.gemm_split(xs[i][0], xs[i][1], wp, wsc, rows, 2 * F, Dh, out=ys[i]) for i in range(3)], 20)
+        entry("gaot_gemm_split", "gemm_bf16_tc_kernel<256,0,0,2,split>", 2.0 * rows * 2 * F * Dh, us,
+              f"forward x W^T, {rows}x{2 * F}x{Dh}; fp32-equivalent FLOPs (3 tensor-core terms)")
+    return out
 
-    def dev_step():
-        return graphed() if graphed is not None else eager_step()
+
+def magno_kernels(case, peaks):
+    """Each MAGNO gather / reduce operator timed on its own: one launch bracketed by CUDA events on the launching stream,
+    preceded by a 512 MB memset that flushes the 126 MB L2; median of 7.  `achieved` uses the ALGORITHMIC bytes SURVEY.md
+    section 8d assigns to the operator (gather + weight + segment-sum over [B,N,C] features); `min_gbs` = the bytes the
+    fused formulation has to move / time."""
+    from gaot_b200 import _lib, ops as O, synth as S
+    w, B, dev, model = case.w, case.B, case.D.dev, case.model
+    C, N, M = w["C"], w["n"], case.lat.shape[0]
+    Cin, Cout = w["cin"], w["cout"]
+    enc_g = model.encoder.neighbor_cache["graph"][1][0]
+    dec_g = model.decoder.neighbor_cache["graph"][1][0]
+    E = int(enc_g["neighbors_index"].numel())
+
+    def alg_fwd(Bc, Ns, Nd):
+        return 4.0 * C * Bc * (Ns + Nd) + 4.0 * C * E + 8.0 * E + 8.0 * (Nd + 1)
+
+    def alg_bwd(Bc, Ns, Nd):
+        return 4.0 * C * Bc * (2 * Ns + Nd) + 8.0 * C * E + 2 * (8.0 * E + 8.0 * (Nd + 1))
+
+    pe, pd = O.graph_plan(enc_g, N), O.graph_plan(dec_g, M)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+
+    def med_us(fn):
+        ts = []
+        for _ in range(7):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1) * 1e3)
+        return sorted(ts)[3]
+
+    rows = []
+
+    def add(kernel, Ns, Nd, us, alg, min_bytes):
+        rows.append(dict(kernel=kernel, bound="hbm", Ns=int(Ns), Nd=int(Nd), us=round(us, 1), achieved=round(alg / us / 1e3, 1),
+                         peak=peaks["hbm_gbs"], unit="GB/s", frac=round(alg / us / 1e3 / peaks["hbm_gbs"], 4),
+                         alg_bytes=int(alg), min_gbs=round(min_bytes / us / 1e3, 1)))
+
+    Bc = B
+    pn_m = S.normal((Bc, N, Cin), 11).to(dev)
+    Wl_m, bl_m = S.normal((C, Cin), 12).to(dev), S.normal((C,), 13).to(dev)
+    we_m, wd_m = S.normal((pe.E, C), 14).to(dev), S.normal((Cout, pd.E, C), 15).to(dev)
+    lat_f = S.normal((Bc, M, C), 16).to(dev)
+    g_enc, g_dec = S.normal((Bc, M, C), 17).to(dev), S.normal((Bc, N, Cout), 18).to(dev)
+    with torch.no_grad():
+        t = med_us(lambda: O.lift_aggregate(pn_m, Wl_m, bl_m, we_m, pe))
+        add("lift_aggregate_fwd (encoder)", N, M, t, alg_fwd(Bc, N, M), 4.0 * Bc * N * Cin + 4.0 * C * E + 8.0 * E + 4.0 * C * Bc * M)
+        t = med_us(lambda: O.agno_dot(lat_f, wd_m, pd))
+        add("agno_dot_fwd (decoder)", M, N, t, alg_fwd(Bc, M, N), 4.0 * C * Bc * M + 4.0 * C * E * Cout + 8.0 * E + 4.0 * Bc * N * Cout)
+        dw_, dWl_, dbl_ = torch.empty_like(we_m), torch.empty_like(Wl_m), torch.empty_like(bl_m)
+        t = med_us(lambda: _lib.call("gaot_lift_aggregate_bwd", g_enc.data_ptr(), pn_m.data_ptr(), Wl_m.data_ptr(), bl_m.data_ptr(),
+                                      we_m.data_ptr(), pe.index.data_ptr(), pe.splits.data_ptr(), dw_.data_ptr(), dWl_.data_ptr(),
+                                      dbl_.data_ptr(), Bc, N, int(M), pe.E, C, Cin))
+        add("lift_aggregate_bwd (encoder)", N, M, t, alg_bwd(Bc, N, M), 4.0 * Bc * N * Cin + 8.0 * C * E + 8.0 * E + 4.0 * C * Bc * M)
+        ts_, tr_, tp_ = pd.transposed()
+        df_, du_ = torch.empty_like(lat_f), torch.empty_like(wd_m)
+        t = med_us(lambda: _lib.call("gaot_agno_dot_bwd", g_dec.data_ptr(), lat_f.data_ptr(), wd_m.data_ptr(), pd.index.data_ptr(),
+                                      pd.splits.data_ptr(), ts_.data_ptr(), tr_.data_ptr(), tp_.data_ptr(), df_.data_ptr(),
+                                      du_.data_ptr(), Bc, int(M), N, pd.E, C, Cout))
+        add("agno_dot_bwd (decoder)", M, N, t, alg_bwd(Bc, M, N), 2 * 4.0 * C * Bc * M + 8.0 * C * E * Cout + 16.0 * E + 4.0 * Bc * N * Cout)
+        f_m = S.normal((Bc, N, C), 19).to(dev)
+        t = med_us(lambda: O.agno_aggregate(f_m, we_m, pe))
+        add("agno_aggregate (unfused encoder fwd)", N, M, t, alg_fwd(Bc, N, M), alg_fwd(Bc, N, M))
+    del flush
+    return rows
+
+
+def kernel_breakdown(case, dump=""):
+    """One extra eager step with CUDA events around every ABI call (same stream).  Host launch gaps are inside these numbers:
+    they rank the entry points and count the calls; the roofline figures come from the isolated timings instead."""
+    from gaot_b200 import _lib
+    rec = []
+    _lib.set_profile(rec)
+    case.eager_step()
+    torch.cuda.synchronize()
+    _lib.set_profile(None)
+    agg = {}
+    for name, a, e0, e1 in rec:
+        d = agg.setdefault(name, dict(calls=0, s=0.0))
+        d["calls"] += 1
+        d["s"] += e0.elapsed_time(e1) * 1e-3
+    total = sum(d["s"] for d in agg.values())
+    if dump and case.D.rank == 0:
+        with open(dump, "w") as fh:
+            for name, a, e0, e1 in rec:
+                dims = [int(v) for v in a if isinstance(v, int) and 0 < v < 10 ** 9]
+                fh.write(f"{e0.elapsed_time(e1) * 1e3:9.1f} us  {name:28s} {dims[:8]}\n")
+    return {k: {"calls": d["calls"], "ms": round(d["s"] * 1e3, 3), "share": round(d["s"] / total, 4)}
+            for k, d in sorted(agg.items(), key=lambda kv: -kv[1]["s"])}
+
+
+def strong_scaling_leg(D, args):
+    """BASELINE.json configs[4]: synthetic 3-D, N = 262 144, GLOBAL batch 8 sharded over the ranks (strong scaling): every
+    rank takes 8 / world samples; coordinates, graphs and the batch-independent edge work are replicated."""
+    G = 8
+    if G % D.world != 0:
+        return {"skipped": f"global batch {G} does not divide over {D.world} ranks"}
+    w = WORKLOADS["cfg5"]
+    B = G // D.world
+    case = Case(D, w, B, args.precision)
+    for _ in range(3):
+        case.dev_step()
+    K = 5
+    ms = D.timed(case.dev_step, K)
+    out = {"workload": "cfg5", "desc": w["desc"].replace("B=1/GPU", f"global batch {G}"), "scaling": "strong", "global_batch": G,
+           "batch_per_gpu": B, "n_gpus": D.world, "ms_per_step": ms / K, "value": G * w["n"] * K / (ms * 1e-3), "unit": "points/s",
+           "edges": case.edges(), "steps": K}
+    del case
+    torch.cuda.empty_cache()
+    return out
+
+
+def rollout_leg(D, args):
+    """BASELINE.json configs[3]: ns_gauss-like 2-D time-dependent model, 10-step no-grad autoregressive rollout, batch 16 per
+    GPU (GAOT.autoregressive_predict, gaot.py:307-476), one captured forward replayed per step."""
+    from gaot_b200 import ops as O
+    from gaot_b200.model import GAOT
+    w = WORKLOADS["cfg4"]
+    B, U = w["B"], w["cout"]
+    O.set_precision(args.precision)
+    torch.manual_seed(42)
+    model = GAOT(w["cin"], w["cout"], make_config(w)).to(D.dev).eval()
+    lat, x, pn, _ = synth(w, D.rank, B)
+    lat_d, x_d, u0 = lat.to(D.dev), x.to(D.dev), pn[..., :U].contiguous().to(D.dev)
+    one = torch.ones(U)
+    stats = {"u": {"mean": 0 * one, "std": one}, "der": {"mean": 0 * one, "std": one}, "start_time": {"mean": 0.0, "std": 1.0},
+             "time_diffs": {"mean": 0.0, "std": 1.0}}
+    tv = torch.linspace(0, 1, 21)[:11]
+    idx = list(range(11))
+
+    def run():
+        return model.autoregressive_predict(u0, idx, tv, stats, "time_der", latent_tokens_coord=lat_d, fixed_coord=x_d,
+                                            use_cuda_graph=True)
+    run()
+    K = 3
+    ms = D.timed(run, K)
+    out = {"workload": "cfg4", "desc": "ns_gauss-like 2D fx, 10-step autoregressive rollout (no grad), N=16384, B=16/GPU",
+           "rollout_steps": 10, "batch_per_gpu": B, "n_gpus": D.world, "ms_per_rollout": ms / K,
+           "value": D.world * B * w["n"] * 10 * K / (ms * 1e-3), "unit": "points/s (mesh points x rollout steps)", "scaling": "weak"}
+    del model
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_ours(args, w):
+    from gaot_b200 import _lib, ops as _ops
+    D = Dist()
+    world, rank, dev = D.world, D.rank, D.dev
+    strong = args.scaling == "strong"
+    if strong:
+        G = args.global_batch or 8
+        if G % world != 0:
+            raise SystemExit(f"--global-batch {G} must divide over {world} ranks")
+        B = G // world
+    else:
+        B = args.batch or w["B"]
+    peaks = load_peaks()
+    case = Case(D, w, B, args.precision, use_graph=not args.no_graph)
+    step, graphed = case.step, case.graphed
+    pn_h, tgt_h = case.pn.pin_memory(), case.tgt.pin_memory()
 
     feeder = None
     if graphed is not None:
         from gaot_b200.trainer import InputPrefetcher
-        feeder = InputPrefetcher([pn_s, tgt_s])
+        feeder = InputPrefetcher([case.pn_s, case.tgt_s])
     staged = {"ok": False}
 
     def e2e_step():
@@ -228,207 +497,128 @@ def run_ours(args, w):
             feeder.prefetch([pn_h, tgt_h])
             staged["ok"] = True
             return float(loss)                                                 # .item(): D2H read of the loss
-        pn_s.copy_(pn_h, non_blocking=True)
-        tgt_s.copy_(tgt_h, non_blocking=True)
-        if graphed is not None:
-            loss = graphed()
-        elif vx:
-            loss = step.variable_coords_step(lat_d, pn_s, tgt_s, x_d, enc_graphs, dec_graphs)
+        case.pn_s.copy_(pn_h, non_blocking=True)
+        case.tgt_s.copy_(tgt_h, non_blocking=True)
+        if case.vx:
+            loss = step.variable_coords_step(case.lat_d, case.pn_s, case.tgt_s, case.x_d, case.enc_graphs, case.dec_graphs)
         else:
-            loss = step.fixed_coords_step(lat_d, x_d, pn_s, tgt_s)
+            loss = step.fixed_coords_step(case.lat_d, case.x_d, case.pn_s, case.tgt_s)
         return float(loss)                                                     # .item(): D2H read of the loss
 
     W = max(args.warmup, 3)
     for _ in range(W):
-        dev_step()
-    sampler = ClockSampler(local) if rank == 0 else None
+        case.dev_step()
+    sampler = ClockSampler(D.local) if rank == 0 else None
     n0 = _lib.launch_count()
-    ms = timed(dev_step, args.steps)
+    ms = D.timed(case.dev_step, args.steps)
     launches = _lib.launch_count() - n0
     clocks = sampler.stop() if sampler else None
     e2e_step()
     torch.cuda.synchronize()
     staged["ok"] = False                   # the first timed step copies its own batch inside the timed region
-    ms_e2e = timed(e2e_step, args.steps)
+    ms_e2e = D.timed(e2e_step, args.steps)
 
-    # per-kernel breakdown: one extra step with CUDA events around every ABI call (same stream)
-    rec = []
-    _lib.set_profile(rec)
-    eager_step()
+    # working set of one step vs the L2: activations saved for the backward dominate; measured, not assumed
+    torch.cuda.reset_peak_memory_stats()
+    m0 = torch.cuda.memory_allocated()
+    case.eager_step()
     torch.cuda.synchronize()
-    _lib.set_profile(None)
-    agg = {}
-    for name, a, e0, e1 in rec:
-        t = e0.elapsed_time(e1) * 1e-3
-        fl, by = call_work(name, a)
-        d = agg.setdefault(name, dict(calls=0, s=0.0, flops=0.0, bytes=0.0, items=[]))
-        d["calls"] += 1; d["s"] += t
-        if fl:
-            d["flops"] += fl
-        d["items"].append((t, a))
-    total_s = sum(d["s"] for d in agg.values())
-    if args.dump_calls and rank == 0:
-        with open(args.dump_calls, "w") as fh:
-            for name, a, e0, e1 in rec:
-                dims = [int(v) for v in a if isinstance(v, int) and 0 < v < (1 << 40) and v < 10 ** 9]
-                fh.write(f"{e0.elapsed_time(e1) * 1e3:9.1f} us  {name:28s} {dims[:8]}\n")
+    step_bytes = torch.cuda.max_memory_allocated() - m0
+    l2_bytes = torch.cuda.get_device_properties(dev).L2_cache_size
+    breakdown = kernel_breakdown(case, args.dump_calls)
 
-    peaks = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "src": "fallback"}
-    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(pk):
-        j = json.load(open(pk))
-        peaks = {"hbm_gbs": j["hbm_gbs"], "bf16_tflops": j["bf16_tflops_sustained"], "src": "measured"}
-
-    # MAGNO scatter (the metric BASELINE.json names).  `achieved` uses the ALGORITHMIC bytes SURVEY.md section 8d
-    # assigns to the operator (gather + weight + segment-sum over [B,N,C] features); the fused kernels do that
-    # job while touching fewer bytes (`min_bytes`: what the fused formulation has to move), see DESIGN.md section 4.
-    if vx:
-        E = sum(int(g_[0]["neighbors_index"].numel()) for g_ in enc_graphs)
-    else:
-        enc_g = model.encoder.neighbor_cache["graph"][1][0]
-        E = int(enc_g["neighbors_index"].numel())
-    C, N, M = w["C"], w["n"], lat.shape[0]
-    Cin, Cout = w["cin"], w["cout"]
-
-    def alg_fwd(Bc, Ns, Nd):
-        return 4.0 * C * Bc * (Ns + Nd) + 4.0 * C * E + 8.0 * E + 8.0 * (Nd + 1)
-
-    def alg_bwd(Bc, Ns, Nd):
-        return 4.0 * C * Bc * (2 * Ns + Nd) + 8.0 * C * E + 2 * (8.0 * E + 8.0 * (Nd + 1))
-
-    # Each MAGNO gather/reduce operator is timed on its own: one launch bracketed by CUDA events on the launching
-    # stream, preceded by a 512 MB memset that flushes the 126 MB L2 and keeps the GPU busy while the host enqueues
-    # (the per-call numbers of the eager breakdown step include host launch gaps that are comparable to these
-    # 30-60 us kernels).  Median of 7.
-    from gaot_b200 import ops as O, synth as S
-    magno = []
-    if not vx:
-        dec_g = model.decoder.neighbor_cache["graph"][1][0]
-        pe, pd = O.graph_plan(enc_g, N), O.graph_plan(dec_g, M)
-        flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
-
-        def med_us(fn):
-            ts = []
-            for _ in range(7):
-                flush.zero_()
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record(); fn(); e1.record()
-                torch.cuda.synchronize()
-                ts.append(e0.elapsed_time(e1) * 1e3)
-            return sorted(ts)[3]
-
-        Bc = B
-        pn_m = S.normal((Bc, N, Cin), 11).to(dev)
-        Wl_m, bl_m = S.normal((C, Cin), 12).to(dev), S.normal((C,), 13).to(dev)
-        we_m, wd_m = S.normal((pe.E, C), 14).to(dev), S.normal((Cout, pd.E, C), 15).to(dev)
-        lat_f = S.normal((Bc, M, C), 16).to(dev)
-        g_enc, g_dec = S.normal((Bc, M, C), 17).to(dev), S.normal((Bc, N, Cout), 18).to(dev)
-        with torch.no_grad():
-            t = med_us(lambda: O.lift_aggregate(pn_m, Wl_m, bl_m, we_m, pe))
-            magno.append(dict(kernel="lift_aggregate_fwd (encoder)", Ns=N, Nd=int(M), us=t, gbs=alg_fwd(Bc, N, M) / t / 1e3,
-                              min_bytes=4.0 * Bc * N * Cin + 4.0 * C * E + 8.0 * E + 4.0 * C * Bc * M))
-            t = med_us(lambda: O.agno_dot(lat_f, wd_m, pd))
-            magno.append(dict(kernel="agno_dot_fwd (decoder)", Ns=int(M), Nd=N, us=t, gbs=alg_fwd(Bc, M, N) / t / 1e3,
-                              min_bytes=4.0 * C * Bc * M + 4.0 * C * E * Cout + 8.0 * E + 4.0 * Bc * N * Cout))
-            dw_, dWl_, dbl_ = torch.empty_like(we_m), torch.empty_like(Wl_m), torch.empty_like(bl_m)
-            t = med_us(lambda: _lib.call("gaot_lift_aggregate_bwd", g_enc.data_ptr(), pn_m.data_ptr(), Wl_m.data_ptr(), bl_m.data_ptr(),
-                                          we_m.data_ptr(), pe.index.data_ptr(), pe.splits.data_ptr(), dw_.data_ptr(), dWl_.data_ptr(),
-                                          dbl_.data_ptr(), Bc, N, int(M), pe.E, C, Cin))
-            magno.append(dict(kernel="lift_aggregate_bwd (encoder)", Ns=N, Nd=int(M), us=t, gbs=alg_bwd(Bc, N, M) / t / 1e3,
-                              min_bytes=4.0 * Bc * N * Cin + 8.0 * C * E + 8.0 * E + 4.0 * C * Bc * M))
-            ts_, tr_, tp_ = pd.transposed()
-            df_, du_ = torch.empty_like(lat_f), torch.empty_like(wd_m)
-            t = med_us(lambda: _lib.call("gaot_agno_dot_bwd", g_dec.data_ptr(), lat_f.data_ptr(), wd_m.data_ptr(), pd.index.data_ptr(),
-                                          pd.splits.data_ptr(), ts_.data_ptr(), tr_.data_ptr(), tp_.data_ptr(), df_.data_ptr(),
-                                          du_.data_ptr(), Bc, int(M), N, pd.E, C, Cout))
-            magno.append(dict(kernel="agno_dot_bwd (decoder, 2 kernels)", Ns=int(M), Nd=N, us=t, gbs=alg_bwd(Bc, M, N) / t / 1e3,
-                              min_bytes=2 * 4.0 * C * Bc * M + 8.0 * C * E * Cout + 16.0 * E + 4.0 * Bc * N * Cout))
-            f_m = S.normal((Bc, N, C), 19).to(dev)
-            t = med_us(lambda: O.agno_aggregate(f_m, we_m, pe))
-            magno.append(dict(kernel="agno_aggregate (unfused encoder fwd)", Ns=N, Nd=int(M), us=t, gbs=alg_fwd(Bc, N, M) / t / 1e3,
-                              min_bytes=alg_fwd(Bc, N, M)))
-        del flush
-    best = max(magno, key=lambda r: r["us"]) if magno else None
-    top_name = max(agg, key=lambda k: agg[k]["s"])
-    top = agg[top_name]
-    if top["flops"] > 0:
-        ach = top["flops"] / top["s"] / 1e12
-        roof = {"kernel": top_name, "bound": "tensor", "achieved": round(ach, 3), "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                "frac": round(ach / peaks["bf16_tflops"], 5), "traffic": None, "peak_src": peaks["src"],
-                "share_of_step": round(top["s"] / total_s, 3),
-                "note": ("tcgen05 kernel" if "bf16" in top_name else "fp32 FFMA parity-path kernel measured against the bf16 tensor peak")}
-        if top_name.startswith("gaot_attention") and "bf16" in top_name:
-            # at head dim 32 the softmax exponentials, not the MMAs, bound attention: one ex2 per score on the MUFU pipe
-            # (16 / clk / SM on sm_100a) against 4*hd (forward) or 10*hd (backward) tensor FLOPs per score
-            a0 = top["items"][0][1]
-            hd_ = a0[7] if top_name.endswith("fwd_bf16") else a0[11]
-            per = (4.0 if top_name.endswith("fwd_bf16") else 10.0) * hd_
-            ex2s = top["flops"] / per
-            floor_s = ex2s / (16.0 * 148 * 1965e6)
-            roof["mufu_bound"] = {"ex2": ex2s, "floor_ms": round(floor_s * 1e3, 4), "measured_ms": round(top["s"] * 1e3, 4),
-                                  "frac_of_mufu_floor": round(floor_s / top["s"], 4),
-                                  "note": "MUFU.EX2 floor at 16/clk/SM, 148 SMs, 1965 MHz; tensor floor is lower at hd=%d" % hd_}
-    else:
-        ach = best["gbs"] if best else 0.0
-        roof = {"kernel": top_name, "bound": "hbm", "achieved": round(ach, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": round(ach / peaks["hbm_gbs"], 4), "traffic": None, "peak_src": peaks["src"],
-                "share_of_step": round(top["s"] / total_s, 3)}
-    tr = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    if os.path.exists(tr):
-        ent = json.load(open(tr)).get(top_name)
-        if ent and args.workload == "cfg2":
-            roof["traffic"] = ent["bytes"]                 # ncu --set full capture of this kernel at this shape
-            roof["traffic_src"] = "profiles/" + ent["capture"] if ent["capture"].startswith("raw/") else ent["capture"]
-    roof_magno = None
-    if magno:
-        roof_magno = {"bound": "hbm", "unit": "GB/s", "peak": peaks["hbm_gbs"], "peak_src": peaks["src"],
-                      "bytes": "algorithmic bytes of the unfused operator (SURVEY 8d); min_gbs = bytes the fused kernel must move / time",
-                      "launches": [dict(kernel=r["kernel"], Ns=r["Ns"], Nd=r["Nd"], us=round(r["us"], 1), achieved=round(r["gbs"], 1),
-                                        frac=round(r["gbs"] / peaks["hbm_gbs"], 4), min_gbs=round(r["min_bytes"] / r["us"] / 1e3, 1))
-                                   for r in magno],
-                      "share_of_step": round(sum(agg[k]["s"] for k in agg if "aggregate" in k or "agno_dot" in k) / total_s, 4),
-                      "traffic": None}
-    breakdown = {k: {"calls": d["calls"], "ms": round(d["s"] * 1e3, 3), "share": round(d["s"] / total_s, 4)}
-                 for k, d in sorted(agg.items(), key=lambda kv: -kv[1]["s"])}
-    for k, d in agg.items():                           # tensor-pipe kernels: achieved TFLOP/s of the eager-timed calls
-        if d["flops"] > 0:                             # (host launch gaps included, so a lower bound) vs the measured bf16 peak
-            breakdown[k]["tflops"] = round(d["flops"] / d["s"] / 1e12, 1)
-            breakdown[k]["frac_of_bf16_peak"] = round(d["flops"] / d["s"] / 1e12 / peaks["bf16_tflops"], 4)
-
-    pts = world * B * w["n"] * args.steps
+    E, M = case.edges(), int(case.lat.shape[0])
+    total_pts = (B * world) * w["n"] * args.steps
     out = {
-        "metric": "mesh-points/sec fwd+bwd", "value": pts / (ms * 1e-3), "unit": "points/s", "n_gpus": world,
-        "steps": args.steps, "warmup": W, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "metric": "mesh-points/sec fwd+bwd", "value": total_pts / (ms * 1e-3), "unit": "points/s", "n_gpus": world,
+        "steps": args.steps, "warmup": W, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "strong" if strong else "weak",
         "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "precision": args.precision, "desc": w["desc"], "batch_per_gpu": B, "points": w["n"], "latent_tokens": int(M),
-                   "edges": E, "params": step.num_params, "parallelism": f"dp{world}", "cuda_graph": graphed is not None,
-                   "l2": "no flush: per-step working set (~3 GB of activations at B=32) exceeds the 126 MB L2"},
-        "e2e": {"value": pts / (ms_e2e * 1e-3), "unit": "points/s", "ms_per_step": ms_e2e / args.steps,
-                "h2d_bytes_per_step": int(pn.numel() * 4 + tgt.numel() * 4), "d2h_bytes_per_step": 4},
-        "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "roofline_magno": roof_magno,
-        "kernel_breakdown": breakdown,
+        "config": {"workload": args.workload, "precision": args.precision, "desc": w["desc"], "batch_per_gpu": B,
+                   "global_batch": B * world, "points": w["n"], "latent_tokens": M, "edges": E, "params": step.num_params,
+                   "parallelism": f"dp{world}", "cuda_graph": graphed is not None,
+                   "l2": f"no flush between steps: one step allocates {step_bytes / 1e6:.0f} MB of activations / workspaces "
+                         f"(measured), {step_bytes / max(l2_bytes, 1):.0f}x the {l2_bytes / 1e6:.0f} MB L2"},
+        "e2e": {"value": total_pts / (ms_e2e * 1e-3), "unit": "points/s", "ms_per_step": ms_e2e / args.steps,
+                "h2d_bytes_per_step": int(case.pn.numel() * 4 + case.tgt.numel() * 4), "d2h_bytes_per_step": 4},
+        "gpu_launches": int(launches), "clocks": clocks, "kernel_breakdown": breakdown,
     }
+
+    # ---- roofline: the hot kernels timed in isolation on rank 0's GPU (every rank runs them so ranks stay in step) ----
+    if not args.no_roofline:
+        try:
+            tk = isolated_tensor_kernels(w, B, dev, peaks, args.precision)
+            mk = magno_kernels(case, peaks) if not case.vx else []
+            # dominant kernel by a fixed rule: the attention backward kernel, the largest single kernel of the step in the
+            # committed ncu launch list (profiles/README.md section 1); the others are listed beside it
+            dom = next(k for k in tk if "attention_bwd" in k["entry"])
+            roof = {k: dom[k] for k in ("kernel", "bound", "achieved", "peak", "unit", "frac")}
+            roof.update({"entry": dom["entry"], "us": dom["us"], "peak_src": peaks["src"] + " (bf16 burst: kernel timed alone)",
+                         "traffic": None, "timing": "20 launches between one CUDA-event pair, inputs rotated through > 2x L2",
+                         "share_of_step": round(dom["us"] * 1e-3 * w["layers"] / (ms / args.steps), 4)})
+            sms = torch.cuda.get_device_properties(dev).multi_processor_count
+            hd = w["dh"] // w["heads"]
+            ex2 = dom["achieved"] * 1e12 * dom["us"] * 1e-6 / (10.0 * hd)
+            roof["mufu_floor_us"] = round(ex2 / (16.0 * sms * peaks["sm_max_mhz"] * 1e6) * 1e6, 1)
+            tr = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+            if os.path.exists(tr):
+                tj = json.load(open(tr))
+                for k in tk + mk:
+                    ent = tj.get(k.get("entry") or k["kernel"].split(" ")[0])
+                    if ent and args.workload == "cfg2":
+                        k["traffic"] = ent["bytes"]
+                        k["traffic_src"] = "profiles/" + ent["capture"]
+                if dom.get("traffic"):
+                    roof["traffic"], roof["traffic_src"] = dom["traffic"], dom["traffic_src"]
+            roof["tensor_kernels"] = tk
+            roof["magno_hbm"] = mk            # the metric BASELINE.json names: MAGNO gather / scatter GB/s vs the measured HBM peak
+            out["roofline"] = roof
+            if mk:
+                out["roofline_magno"] = {"bound": "hbm", "unit": "GB/s", "peak": peaks["hbm_gbs"], "peak_src": peaks["src"],
+                                         "launches": mk}
+        except Exception as e:                                   # never lose the headline line to a diagnostics failure
+            out["roofline"] = {"error": repr(e)}
+
+    # ---- the same step in the 1e-5 parity mode (split-precision tensor cores), captured the same way ----
     if args.precision == "bf16" and not args.no_fp32_leg:
-        # the same step in the fp32 parity mode (the mode the 1e-5 parity tests run in), eager launches
-        _ops.set_precision("fp32")
-        for _ in range(3):
-            eager_step()
-        ms32 = timed(eager_step, 5)
-        _ops.set_precision(args.precision)
-        out["fp32_parity_mode"] = {"value": world * B * w["n"] * 5 / (ms32 * 1e-3), "unit": "points/s", "ms_per_step": ms32 / 5}
+        try:
+            c32 = Case(D, w, B, "fp32", use_graph=not args.no_graph)
+            for _ in range(3):
+                c32.dev_step()
+            ms32 = D.timed(c32.dev_step, 10)
+            out["fp32_parity_mode"] = {"value": world * B * w["n"] * 10 / (ms32 * 1e-3), "unit": "points/s", "ms_per_step": ms32 / 10,
+                                       "precision": "fp32 (fp16 hi/lo split operands, 3 tcgen05 terms per product, fp32 accumulate)",
+                                       "parity": "forward <= 1e-5 rel-L2 vs the reference (tests/test_gpu_model.py)", "cuda_graph": c32.graphed is not None}
+            del c32
+            torch.cuda.empty_cache()
+            _ops.set_precision(args.precision)
+        except Exception as e:
+            out["fp32_parity_mode"] = {"error": repr(e)}
+
+    # ---- the other BASELINE configurations, as extra blocks of the default line ----
+    if args.workload == "cfg2" and not strong and not args.no_extra:
+        del case, graphed, feeder
+        torch.cuda.empty_cache()
+        try:
+            out["strong_scaling_cfg5"] = strong_scaling_leg(D, args)
+        except Exception as e:
+            out["strong_scaling_cfg5"] = {"error": repr(e)}
+        try:
+            out["rollout_cfg4"] = rollout_leg(D, args)
+        except Exception as e:
+            out["rollout_cfg4"] = {"error": repr(e)}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        out["cpu_baseline"] = cpu_reference(w, steps=2, warmup=1, sample_B=min(8, w["B"]))
+        out["cpu_baseline"] = cpu_reference(w, steps=2, warmup=1, sample_B=B)
     if rank == 0:
         print(json.dumps(out))
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    D.close()
 
 
 def cpu_reference(w, steps, warmup, sample_B):
-    """The reference algorithm's CPU port (oracle/gaot_oracle.py, torch-CPU, all host threads) on a bounded
-    sample (sample_B samples of the same mesh/model) - the reported baseline, not the target."""
-    from oracle import cases, gaot_oracle as orc
+    """The reference algorithm's CPU port (oracle/gaot_oracle.py, torch-CPU, all host threads; pinned to the unmodified
+    reference by tests/golden) on the workload's mesh and model - the reported baseline, not the target.
+    `sample_B` samples per step (the full per-GPU batch unless stated otherwise in `sample`)."""
+    from oracle import gaot_oracle as orc
     from gaot_b200.model import GAOT
     torch.set_num_threads(os.cpu_count() or 1)
     torch.manual_seed(42)
@@ -454,23 +644,36 @@ def cpu_reference(w, steps, warmup, sample_B):
         p = {k: t.requires_grad_(True) for k, t in newp.items()}
         times.append(time.perf_counter() - t0)
     dt = sum(times[warmup:]) / steps
+    full = sample_B == w["B"]
     return {"value": sample_B * w["n"] / dt, "unit": "points/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{steps} steps of batch {sample_B} (of the workload's batch) after {warmup} warm-up; graphs prebuilt; "
-                      f"{dt:.3f} s/step", "s_per_step": dt}
+            "sample": f"{steps} steps of batch {sample_B} ({'the full per-GPU batch' if full else 'of the workload batch ' + str(w['B'])}) "
+                      f"after {warmup} warm-up; graphs prebuilt; {dt:.3f} s/step",
+            "s_per_step": dt, "batch": sample_B}
 
 
 def run_reference(args, w):
+    """Reference arm: the reference's own CPU implementation of the path (the oracle port: the reference is pure Python
+    with no installable package), all host threads, on OUR arm's config - the same workload, the same
+    per-GPU batch, the same warm-up count.  The step count is bounded so the run ends within a few minutes."""
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
-    sample_B = min(8, w["B"])
-    base = cpu_reference(w, steps=args.steps, warmup=max(1, min(args.warmup, 2)), sample_B=sample_B)
+    B = args.batch or w["B"]
+    W = max(args.warmup, 3)
+    steps = args.steps
+    base = cpu_reference(w, steps=1, warmup=1, sample_B=B)          # probe: seconds per step on this box
+    budget = 150.0                                                  # seconds for the timed region + warm-up
+    fit = max(1, int(budget / max(base["s_per_step"], 1e-3)) - W)
+    timed_steps = min(steps, fit)
+    base = cpu_reference(w, steps=timed_steps, warmup=W, sample_B=B)
+    if timed_steps < steps:
+        base["sample"] += f"; {timed_steps} of the requested {steps} steps timed (bounded to ~{budget:.0f} s), per-step time reported"
     out = {"impl": "reference", "metric": "mesh-points/sec fwd+bwd", "value": base["value"], "unit": "points/s",
-           "n_gpus": world, "steps": args.steps, "warmup": max(1, min(args.warmup, 2)), "ms_per_step": base["s_per_step"] * 1e3,
+           "n_gpus": world, "steps": steps, "warmup": W, "ms_per_step": base["s_per_step"] * 1e3,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": args.workload, "desc": w["desc"], "batch_per_gpu": args.batch or w["B"], "points": w["n"],
-                      "parallelism": "cpu"},
+           "config": {"workload": args.workload, "precision": "fp32", "desc": w["desc"], "batch_per_gpu": B, "global_batch": B,
+                      "points": w["n"], "parallelism": "cpu (rank 0 only; the reference has no working data parallelism)"},
            "cpu_baseline": base,
            "e2e": {"value": base["value"], "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
@@ -484,13 +687,18 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
-    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch override")
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch override (weak scaling)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="strong: --global-batch samples are sharded over the ranks (BASELINE configs[4]: cfg5, global batch 8)")
+    ap.add_argument("--global-batch", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fp32-leg", action="store_true", help="skip the extra fp32-parity-mode timing")
+    ap.add_argument("--no-roofline", action="store_true", help="skip the isolated kernel timings")
+    ap.add_argument("--no-extra", action="store_true", help="skip the cfg5 strong-scaling and cfg4 rollout blocks of the default line")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
     ap.add_argument("--dump-calls", default="", help="write the per-ABI-call timing list of one step to this file")
     ap.add_argument("--precision", default=os.environ.get("GAOT_B200_PRECISION", "bf16"), choices=["fp32", "ffma", "bf16"],
-                    help="processor numerics: fp32 parity path or bf16 tensor-core path")
+                    help="processor numerics: bf16 tensor cores, fp32 = split-precision tensor cores (parity), ffma = fp32 FFMA")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     if args.impl == "reference":
