@@ -366,19 +366,31 @@ def magno_kernels(case, peaks):
     with torch.no_grad():
         t = med_us(lambda: O.lift_aggregate(pn_m, Wl_m, bl_m, we_m, pe))
         add("lift_aggregate_fwd (encoder)", N, M, t, alg_fwd(Bc, N, M), 4.0 * Bc * N * Cin + 4.0 * C * E + 8.0 * E + 4.0 * C * Bc * M)
-        t = med_us(lambda: O.agno_dot(lat_f, wd_m, pd))
-        add("agno_dot_fwd (decoder)", M, N, t, alg_fwd(Bc, M, N), 4.0 * C * Bc * M + 4.0 * C * E * Cout + 8.0 * E + 4.0 * Bc * N * Cout)
+        ts_, tr_, tp_ = pd.transposed()
+        out_d = torch.empty((Bc, N, Cout), device=dev)
+        df_, du_ = torch.empty_like(lat_f), torch.empty_like(wd_m)
+        dec_min_f = 4.0 * C * Bc * M + 4.0 * C * E * Cout + 8.0 * E + 4.0 * Bc * N * Cout
+        dec_min_b = 2 * 4.0 * C * Bc * M + 8.0 * C * E * Cout + 16.0 * E + 4.0 * Bc * N * Cout
+        t = med_us(lambda: _lib.call("gaot_agno_dot_fwd_t", lat_f.data_ptr(), wd_m.data_ptr(), ts_.data_ptr(), tr_.data_ptr(),
+                                      tp_.data_ptr(), out_d.data_ptr(), Bc, int(M), N, pd.E, C, Cout))
+        add("agno_dot_fwd_t (decoder, source walk: default)", M, N, t, alg_fwd(Bc, M, N), dec_min_f)
         dw_, dWl_, dbl_ = torch.empty_like(we_m), torch.empty_like(Wl_m), torch.empty_like(bl_m)
         t = med_us(lambda: _lib.call("gaot_lift_aggregate_bwd", g_enc.data_ptr(), pn_m.data_ptr(), Wl_m.data_ptr(), bl_m.data_ptr(),
                                       we_m.data_ptr(), pe.index.data_ptr(), pe.splits.data_ptr(), dw_.data_ptr(), dWl_.data_ptr(),
                                       dbl_.data_ptr(), Bc, N, int(M), pe.E, C, Cin))
         add("lift_aggregate_bwd (encoder)", N, M, t, alg_bwd(Bc, N, M), 4.0 * Bc * N * Cin + 8.0 * C * E + 8.0 * E + 4.0 * C * Bc * M)
-        ts_, tr_, tp_ = pd.transposed()
-        df_, du_ = torch.empty_like(lat_f), torch.empty_like(wd_m)
+        t = med_us(lambda: _lib.call("gaot_agno_dot_bwd_t", g_dec.data_ptr(), lat_f.data_ptr(), wd_m.data_ptr(), pd.index.data_ptr(),
+                                      pd.splits.data_ptr(), ts_.data_ptr(), tr_.data_ptr(), tp_.data_ptr(), df_.data_ptr(), du_.data_ptr(),
+                                      Bc, int(M), N, pd.E, C, Cout))
+        add("agno_dot_bwd_t (decoder, source walk: default)", M, N, t, alg_bwd(Bc, M, N), dec_min_b)
+        # the row-walk forms (deterministic summation order; GAOT_B200_ROW_WALK=1), for comparison
+        t = med_us(lambda: _lib.call("gaot_agno_dot_fwd", lat_f.data_ptr(), wd_m.data_ptr(), pd.index.data_ptr(), pd.splits.data_ptr(),
+                                      out_d.data_ptr(), Bc, int(M), N, pd.E, C, Cout))
+        add("agno_dot_fwd (decoder, row walk)", M, N, t, alg_fwd(Bc, M, N), dec_min_f)
         t = med_us(lambda: _lib.call("gaot_agno_dot_bwd", g_dec.data_ptr(), lat_f.data_ptr(), wd_m.data_ptr(), pd.index.data_ptr(),
                                       pd.splits.data_ptr(), ts_.data_ptr(), tr_.data_ptr(), tp_.data_ptr(), df_.data_ptr(),
                                       du_.data_ptr(), Bc, int(M), N, pd.E, C, Cout))
-        add("agno_dot_bwd (decoder)", M, N, t, alg_bwd(Bc, M, N), 2 * 4.0 * C * Bc * M + 8.0 * C * E * Cout + 16.0 * E + 4.0 * Bc * N * Cout)
+        add("agno_dot_bwd (decoder, row walk, 2 kernels)", M, N, t, alg_bwd(Bc, M, N), dec_min_b)
         f_m = S.normal((Bc, N, C), 19).to(dev)
         t = med_us(lambda: O.agno_aggregate(f_m, we_m, pe))
         add("agno_aggregate (unfused encoder fwd)", N, M, t, alg_fwd(Bc, N, M), alg_fwd(Bc, N, M))

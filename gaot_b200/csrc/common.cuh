@@ -17,10 +17,21 @@ extern "C" long long gaot_launch_counter_add(long long n);
 
 static inline int gaot_blocks(int64_t work, int threads) { return (int)((work + threads - 1) / threads); }
 
-// Grid size for grid-stride kernels: a multiple of the SM count (148 on B200), capped by the work.
+// SM count of the current device (148 on B200), queried once per process
+static inline int gaot_sm_count() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
+}
+
+// Grid size for grid-stride kernels: a multiple of the SM count, capped by the work.
 static inline int gaot_grid(int64_t work, int threads, int ctas_per_sm = 8) {
     int64_t need = (work + threads - 1) / threads;
-    int64_t cap = (int64_t)148 * ctas_per_sm;
+    int64_t cap = (int64_t)gaot_sm_count() * ctas_per_sm;
     if (need < 1) need = 1;
     return (int)(need < cap ? need : cap);
 }

@@ -180,8 +180,8 @@ int launch_gemm(GemmArgs& g, cudaStream_t st) {
     const int64_t tiles = gm * gn, ktiles = (g.K + BK - 1) / BK;
     int splits = 1;
     const bool can_split = (g.act == GAOT_ACT_NONE) && !g.pre && (g.ldc == g.N);
-    if (can_split && tiles < 148 && ktiles >= 16) {
-        splits = (int)((148 * 4 + tiles - 1) / tiles);
+    if (can_split && tiles < gaot_sm_count() && ktiles >= 16) {
+        splits = (int)((gaot_sm_count() * 4 + tiles - 1) / tiles);
         if (splits > ktiles / 8) splits = (int)(ktiles / 8);
         if (splits < 1) splits = 1;
         if (splits > 1024) splits = 1024;
@@ -359,7 +359,7 @@ int launch_narrow(GemmArgs& g, cudaStream_t st) {
     const int warps = NW_THREADS / 32;
     if (rows_mode) {
         int64_t ctas = (g.M + warps * NW_ROWS - 1) / (warps * NW_ROWS);
-        if (ctas > 148 * 4) ctas = 148 * 4;
+        if (ctas > gaot_sm_count() * 4) ctas = gaot_sm_count() * 4;
         if (g.transB) narrow_rows_kernel<true><<<(unsigned)ctas, NW_THREADS, 0, st>>>(g);
         else narrow_rows_kernel<false><<<(unsigned)ctas, NW_THREADS, 0, st>>>(g);
     } else {
@@ -368,7 +368,7 @@ int launch_narrow(GemmArgs& g, cudaStream_t st) {
             else GAOT_CHECK(cudaMemset2DAsync(g.C, sizeof(float) * (size_t)g.ldc, 0, sizeof(float) * (size_t)g.N, (size_t)g.M, st));
         }
         int64_t ctas = (g.K + warps * NW_ROWS * 2 - 1) / (warps * NW_ROWS * 2);    // >= 2 row groups per warp before the atomics
-        if (ctas > 148) ctas = 148;
+        if (ctas > gaot_sm_count()) ctas = gaot_sm_count();
         if (ctas < 1) ctas = 1;
         narrow_reduce_kernel<<<(unsigned)ctas, NW_THREADS, 0, st>>>(g);
     }
@@ -797,7 +797,7 @@ GAOT_API int gaot_col_sum(const float* x, int64_t M, int64_t N, float* out, int 
     if (!accumulate) GAOT_CHECK(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)N, st));
     if (M == 0) return 0;
     const int64_t gx = (N + 31) / 32;
-    int64_t slices = (148 * 8 + gx - 1) / gx;
+    int64_t slices = (gaot_sm_count() * 8 + gx - 1) / gx;
     if (slices > (M + 63) / 64) slices = (M + 63) / 64;
     if (slices < 1) slices = 1;
     const int64_t rows_per = (M + slices - 1) / slices;

@@ -361,7 +361,7 @@ int launch_weight_grad(const float* g, const float* f, const int64_t* index, con
                        int64_t B, int64_t Ns, int64_t Nd, int64_t C, int64_t E, cudaStream_t st) {
     // enough groups to fill the chip: target >= 148 SMs * 2048 threads
     int bsplit = 1;
-    const int64_t want = 148LL * 2048;
+    const int64_t want = (int64_t)gaot_sm_count() * 2048;
     while (bsplit < B && Nd * G * bsplit < want && bsplit < 8) bsplit <<= 1;
     if (bsplit > B) bsplit = (int)B;
     if (bsplit > 1) GAOT_CHECK(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)(E * C), st));

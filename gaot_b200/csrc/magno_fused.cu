@@ -16,6 +16,8 @@
 //     resident) and writes Cout scalars per point.
 //     Backward: dr[b,j,c] = sum_{e: idx_e=j} sum_o u[o,e,c] g[b,row_e,o]   (transposed graph)
 //               du[o,e,c] = sum_b g[b,row_e,o] r[b,idx_e,c]
+#include <cstdlib>
+
 #include "common.cuh"
 #include "../../include/gaot_b200.h"
 
@@ -40,11 +42,15 @@ __device__ __forceinline__ float dot4(const float4& x, const float4& y) {
 // Work items (row, chunk of FB samples) are walked with a persistent grid-stride loop; the CSR bounds of the
 // item after next and the first neighbour index of the next item are fetched while the current item is being
 // processed, so an item costs one dependent memory round trip (its feature rows) instead of three.
+// Edges are taken U at a time: the U neighbour indices and U weight rows of a batch are independent loads, and the U*FB*CIN
+// feature loads that depend on the indices are issued together - one dependent round trip per U edges instead of per edge.
+// The register budget is bounded per instantiation (3 CTAs per SM when FB*CIN <= 8) so more warps hide that round trip.
 template <int G, int CIN, int FB>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, (FB * CIN <= 16) ? 2 : 1)
 lift_aggregate_fwd_kernel(const float* __restrict__ pn, const float* __restrict__ Wl, const float* __restrict__ bl,
                           const float* __restrict__ w, const int64_t* __restrict__ index, const int64_t* __restrict__ rs,
                           float* __restrict__ out, int B, int64_t Ns, int64_t Nd, int C, int64_t n_items) {
+    constexpr int U = (FB * CIN <= 8) ? 4 : 2;
     const int64_t ngroups = (int64_t)gridDim.x * blockDim.x / G;
     const int gl = threadIdx.x % G;
     const int nvec = C >> 2;
@@ -56,19 +62,18 @@ lift_aggregate_fwd_kernel(const float* __restrict__ pn, const float* __restrict_
                             __ldg(Wl + (c0 + 3) * CIN + i));
     const float4 blv = ldg4(bl + c0);
     int64_t item = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
-    int64_t a = 0, e = 0, na = 0, ne = 0, j0 = 0;
+    int64_t a = 0, e = 0, na = 0, ne = 0;
     if (item < n_items) { a = __ldg(rs + item % Nd); e = __ldg(rs + item % Nd + 1); }
     if (item + ngroups < n_items) { na = __ldg(rs + (item + ngroups) % Nd); ne = __ldg(rs + (item + ngroups) % Nd + 1); }
-    if (a < e) j0 = __ldg(index + a);
     for (; item < n_items; item += ngroups) {
-        int64_t nna = 0, nne = 0, nj0 = 0;
+        int64_t nna = 0, nne = 0;
         if (item + 2 * ngroups < n_items) { nna = __ldg(rs + (item + 2 * ngroups) % Nd); nne = __ldg(rs + (item + 2 * ngroups) % Nd + 1); }
-        if (na < ne) nj0 = __ldg(index + na);
         const int64_t row = item % Nd;
         const int b0 = (int)(item / Nd) * FB;
-        int64_t boff[FB];
+        const float* pb0 = pn + (int64_t)min(b0, B - 1) * Ns * CIN;
+        int pb[FB];                                   // sample offsets relative to the chunk's first sample (FB * Ns * CIN < 2^31)
 #pragma unroll
-        for (int bb = 0; bb < FB; ++bb) boff[bb] = (int64_t)min(b0 + bb, B - 1) * Ns * CIN;
+        for (int bb = 0; bb < FB; ++bb) pb[bb] = (int)((int64_t)(min(b0 + bb, B - 1) - min(b0, B - 1)) * Ns * CIN);
         // s[bb][i] = sum_e w[e,c] pn[b,j,i] (per lane: 4 channels), sw = sum_e w[e,c]
         float4 s[FB][CIN];
         float4 sw = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -76,21 +81,24 @@ lift_aggregate_fwd_kernel(const float* __restrict__ pn, const float* __restrict_
         for (int bb = 0; bb < FB; ++bb)
 #pragma unroll
             for (int i = 0; i < CIN; ++i) s[bb][i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        int64_t j = j0;
-        for (int64_t it = a; it < e; ++it) {
-            const int64_t jn = __ldg(index + ((it + 1 < e) ? it + 1 : it));
-            const float4 wv = ldg4(w + it * C + c0);
-            float p[FB][CIN];
+        for (int64_t it = a; it < e; it += U) {
+            int jj[U];
+            float4 wv[U];
 #pragma unroll
-            for (int bb = 0; bb < FB; ++bb)
+            for (int q = 0; q < U; ++q) {
+                const bool ok = it + q < e;
+                const int64_t ee = ok ? it + q : it;
+                jj[q] = (int)__ldg(index + ee) * CIN;
+                wv[q] = ok ? ldg4(w + ee * C + c0) : make_float4(0.f, 0.f, 0.f, 0.f);      // a zero weight masks the tail
+            }
 #pragma unroll
-                for (int i = 0; i < CIN; ++i) p[bb][i] = __ldg(pn + boff[bb] + j * CIN + i);
-            sw.x += wv.x; sw.y += wv.y; sw.z += wv.z; sw.w += wv.w;
+            for (int q = 0; q < U; ++q) {
+                sw.x += wv[q].x; sw.y += wv[q].y; sw.z += wv[q].z; sw.w += wv[q].w;
 #pragma unroll
-            for (int bb = 0; bb < FB; ++bb)
+                for (int bb = 0; bb < FB; ++bb)
 #pragma unroll
-                for (int i = 0; i < CIN; ++i) fma4s(s[bb][i], wv, p[bb][i]);
-            j = jn;
+                    for (int i = 0; i < CIN; ++i) fma4s(s[bb][i], wv[q], __ldg(pb0 + (pb[bb] + jj[q] + i)));
+            }
         }
         if (gl < nvec) {
 #pragma unroll
@@ -103,7 +111,7 @@ lift_aggregate_fwd_kernel(const float* __restrict__ pn, const float* __restrict_
                 }
             }
         }
-        a = na; e = ne; j0 = nj0; na = nna; ne = nne;
+        a = na; e = ne; na = nna; ne = nne;
     }
 }
 
@@ -308,42 +316,47 @@ agno_dot_bwd_r_kernel(const float* __restrict__ g, const float* __restrict__ u, 
     }
 }
 
-// (2) du[o,e,c] = sum_b g[b,row_e,o] r[b,idx_e,c]; group owns a destination row and a slice of the batch
+// (2) du[o,e,c] = sum_b g[b,row_e,o] r[b,idx_e,c]; a group owns a destination row and a slice of 8 samples: the slice's
+// upstream gradients g[b,row,:] are loaded once per row, every edge then costs 8 independent row loads and 8*COUT FMAs per
+// lane; slices are combined with 128-bit red.add when the batch has more than one.
 template <int G, int COUT>
 __global__ void __launch_bounds__(256)
 agno_dot_bwd_u_kernel(const float* __restrict__ g, const float* __restrict__ r, const int64_t* __restrict__ index,
                       const int64_t* __restrict__ rs, float* __restrict__ du, int B, int64_t Ns, int64_t Nd, int64_t E, int C,
                       int bsplit, int64_t n_items) {
+    constexpr int PB = 8;
     const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
     const int gl = threadIdx.x % G;
     if (gid >= n_items) return;
     const int64_t row = gid % Nd;
-    const int slice = (int)(gid / Nd);
-    const int per = (B + bsplit - 1) / bsplit;
-    const int b_lo = slice * per, b_hi = min(B, b_lo + per);
+    const int b_lo = (int)(gid / Nd) * PB;
     const int nvec = C >> 2;
     const int c0 = min(gl, nvec - 1) * 4;
     const int64_t a = __ldg(rs + row), e = __ldg(rs + row + 1);
+    if (a == e) return;
+    float gs[PB][COUT];
+    const float* rb[PB];
+#pragma unroll
+    for (int q = 0; q < PB; ++q) {
+        const int bq = min(b_lo + q, B - 1);
+        rb[q] = r + (int64_t)bq * Ns * C + c0;
+#pragma unroll
+        for (int o = 0; o < COUT; ++o) gs[q][o] = (b_lo + q < B) ? __ldg(g + ((int64_t)bq * Nd + row) * COUT + o) : 0.f;
+    }
+    int64_t j = __ldg(index + a);
     for (int64_t it = a; it < e; ++it) {
-        const int64_t j = __ldg(index + it);
+        const int64_t jn = __ldg(index + ((it + 1 < e) ? it + 1 : it));
+        const int64_t joff = j * C;
+        float4 rv[PB];
+#pragma unroll
+        for (int q = 0; q < PB; ++q) rv[q] = ldg4(rb[q] + joff);
         float4 acc[COUT];
 #pragma unroll
         for (int o = 0; o < COUT; ++o) acc[o] = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int b = b_lo; b < b_hi; b += 4) {
-            float4 rv[4];
-            float gs[4][COUT];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int bq = min(b + q, b_hi - 1);
-                rv[q] = ldg4(r + ((int64_t)bq * Ns + j) * C + c0);
+        for (int q = 0; q < PB; ++q)
 #pragma unroll
-                for (int o = 0; o < COUT; ++o) gs[q][o] = (b + q < b_hi) ? __ldg(g + ((int64_t)bq * Nd + row) * COUT + o) : 0.f;
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-#pragma unroll
-                for (int o = 0; o < COUT; ++o) fma4s(acc[o], rv[q], gs[q][o]);
-        }
+            for (int o = 0; o < COUT; ++o) fma4s(acc[o], rv[q], gs[q][o]);
         if (gl < nvec) {
 #pragma unroll
             for (int o = 0; o < COUT; ++o) {
@@ -351,11 +364,241 @@ agno_dot_bwd_u_kernel(const float* __restrict__ g, const float* __restrict__ r, 
                 if (bsplit > 1) atomicAdd(dst, acc[o]); else *dst = acc[o];
             }
         }
+        j = jn;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// (2') the decoder operator walked by SOURCE node (latent token) on the transposed graph.
+// Row-wise, every edge gathers the 256-byte latent row of every sample again: E * B * C * 4 bytes (257 MB at cfg-2) cross
+// the L2 -> SM fabric for 33.5 MB of distinct data.  Source-wise, a group owns one latent row j: it reads r[b, j, :] ONCE
+// per sample and serves all edges leaving j (7.7 on average) from registers:
+//   forward : out[b, row_k, o] += < u[o, e_k, :], r[b, j, :] >            16-lane shuffle reduction, one fp32 red.add per (b, edge)
+//   backward: dr[b, j, :]       = sum_k sum_o u[o, e_k, :] g[b, row_k, o]   owned by the group: plain stores
+//             du[o, e_k, :]     = sum_b g[b, row_k, o] r[b, j, :]           owned by the group: plain stores, ONE pass for dr and du
+// KE edges of the source are held in registers per pass (sources with more edges take several passes).
+// item = (source j, slice of the batch); with bslices > 1 the du of a source is reduced over its slices with red.add.
+// ---------------------------------------------------------------------------------------------
+template <int G, int COUT, int KE>
+__global__ void __launch_bounds__(256)
+agno_dot_fwd_t_kernel(const float* __restrict__ r, const float* __restrict__ u, const int64_t* __restrict__ t_rows,
+                      const int64_t* __restrict__ t_perm, const int64_t* __restrict__ ts, float* __restrict__ out, int B,
+                      int Ns, int Nd, int64_t E, int C, int64_t n_items, int bslices) {
+    const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const int gl = threadIdx.x % G;
+    const bool valid = gid < n_items;                  // whole groups fall out together, but shuffles want full warps
+    const int j = valid ? (int)(gid % Ns) : 0;
+    const int slice = valid ? (int)(gid / Ns) : 0;
+    const int per = (B + bslices - 1) / bslices;
+    const int b_lo = slice * per, b_hi = valid ? min(B, b_lo + per) : b_lo;
+    const int nvec = C >> 2;
+    const bool act = gl < nvec;
+    const int c0 = min(gl, nvec - 1) * 4;
+    const int64_t a = valid ? __ldg(ts + j) : 0, e = valid ? __ldg(ts + j + 1) : 0;
+    // the groups of a warp run different trip counts (degree, batch slice): shuffles synchronise the group's own lanes only
+    const unsigned gmask = G == 32 ? 0xffffffffu : (((1u << (G & 31)) - 1u) << (((threadIdx.x & 31) / G) * G));
+    for (int64_t k0 = a; k0 < e; k0 += KE) {
+        int rows[KE];
+        float4 uv[COUT][KE];
+#pragma unroll
+        for (int k = 0; k < KE; ++k) {
+            const bool ok = k0 + k < e;
+            const int64_t kk = ok ? k0 + k : k0;
+            rows[k] = ok ? (int)__ldg(t_rows + kk) : -1;
+            const int64_t pe = __ldg(t_perm + kk);
+#pragma unroll
+            for (int o = 0; o < COUT; ++o)
+                uv[o][k] = (ok && act) ? ldg4(u + ((int64_t)o * E + pe) * C + c0) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll 2
+        for (int b = b_lo; b < b_hi; ++b) {
+            const float4 rv = ldg4(r + ((int64_t)b * Ns + j) * C + c0);
+            float v[COUT][KE];
+#pragma unroll
+            for (int o = 0; o < COUT; ++o)
+#pragma unroll
+                for (int k = 0; k < KE; ++k) {
+                    float x = dot4(uv[o][k], rv);
+#pragma unroll
+                    for (int off = G / 2; off > 0; off >>= 1) x += __shfl_xor_sync(gmask, x, off, G);
+                    v[o][k] = x;
+                }
+            // lane k of the group issues the reduction of edge k
+#pragma unroll
+            for (int k = 0; k < KE; ++k) {
+                if (gl == (k % G) && rows[k] >= 0) {
+#pragma unroll
+                    for (int o = 0; o < COUT; ++o) atomicAdd(out + ((int64_t)b * Nd + rows[k]) * COUT + o, v[o][k]);
+                }
+            }
+        }
+    }
+}
+
+template <int G, int COUT, int KE>
+__global__ void __launch_bounds__(256, 2)
+agno_dot_bwd_t_kernel(const float* __restrict__ g, const float* __restrict__ r, const float* __restrict__ u,
+                      const int64_t* __restrict__ t_rows, const int64_t* __restrict__ t_perm, const int64_t* __restrict__ ts,
+                      float* __restrict__ dr, float* __restrict__ du, int B, int Ns, int Nd, int64_t E, int C, int64_t n_items,
+                      int bslices) {
+    const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const int gl = threadIdx.x % G;
+    if (gid >= n_items) return;
+    const int j = (int)(gid % Ns);
+    const int slice = (int)(gid / Ns);
+    const int per = (B + bslices - 1) / bslices;
+    const int b_lo = slice * per, b_hi = min(B, b_lo + per);
+    const int nvec = C >> 2;
+    const bool act = gl < nvec;
+    const int c0 = min(gl, nvec - 1) * 4;
+    const int64_t a = __ldg(ts + j), e = __ldg(ts + j + 1);
+    if (a == e) {                                      // a source without edges: dr = 0
+        if (dr && act)
+            for (int b = b_lo; b < b_hi; ++b) *reinterpret_cast<float4*>(dr + ((int64_t)b * Ns + j) * C + c0) = make_float4(0.f, 0.f, 0.f, 0.f);
+        return;
+    }
+    for (int64_t k0 = a; k0 < e; k0 += KE) {
+        int rows[KE];
+        int pes[KE];                                   // edge ids fit 32 bits (E * C * 4 bytes of weights would not exist otherwise)
+        float4 uv[COUT][KE], acc[COUT][KE];
+#pragma unroll
+        for (int k = 0; k < KE; ++k) {
+            const bool ok = k0 + k < e;
+            const int64_t kk = ok ? k0 + k : k0;
+            rows[k] = (int)__ldg(t_rows + kk);
+            pes[k] = ok ? (int)__ldg(t_perm + kk) : -1;
+#pragma unroll
+            for (int o = 0; o < COUT; ++o) {
+                uv[o][k] = (ok && dr) ? ldg4(u + ((int64_t)o * E + pes[k]) * C + c0) : make_float4(0.f, 0.f, 0.f, 0.f);
+                acc[o][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+#pragma unroll 2
+        for (int b = b_lo; b < b_hi; ++b) {
+            const float4 rv = ldg4(r + ((int64_t)b * Ns + j) * C + c0);
+            float gk[COUT][KE];
+#pragma unroll
+            for (int k = 0; k < KE; ++k)
+#pragma unroll
+                for (int o = 0; o < COUT; ++o) gk[o][k] = pes[k] >= 0 ? __ldg(g + ((int64_t)b * Nd + rows[k]) * COUT + o) : 0.f;
+            float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int k = 0; k < KE; ++k)
+#pragma unroll
+                for (int o = 0; o < COUT; ++o) { fma4s(d, uv[o][k], gk[o][k]); fma4s(acc[o][k], rv, gk[o][k]); }
+            if (dr && act) {
+                float4* dst = reinterpret_cast<float4*>(dr + ((int64_t)b * Ns + j) * C + c0);
+                if (k0 > a) { const float4 old = *dst; d.x += old.x; d.y += old.y; d.z += old.z; d.w += old.w; }   // later pass of the same owner
+                *dst = d;
+            }
+        }
+        if (du && act) {
+#pragma unroll
+            for (int k = 0; k < KE; ++k) {
+                if (pes[k] < 0) continue;
+#pragma unroll
+                for (int o = 0; o < COUT; ++o) {
+                    float4* dst = reinterpret_cast<float4*>(du + ((int64_t)o * E + pes[k]) * C + c0);
+                    if (bslices > 1) atomicAdd(dst, acc[o][k]); else *dst = acc[o][k];
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// (2'') decoder operator with one LANE per SAMPLE (batches of >= 16 samples).  A warp owns a source node j and 32 samples:
+// lane b keeps the whole latent row r[b, j, :] (C floats) in registers, the weight rows u[e, :] of the edges leaving j are
+// warp-uniform (broadcast) loads, so a dot product needs no cross-lane reduction at all:
+//   forward : out[b, row_k, o] += < u[o, e_k, :], r[b, j, :] >     C FMAs per lane and edge, one red.add per lane
+//   backward: dr[b, j, :] = sum_k sum_o g[b, row_k, o] u[o, e_k, :]  C FMAs per lane and edge, the row is stored once
+// ~85 instructions per (edge, 32 samples) against ~650 for the 16-lanes-per-row forms above (shuffle reductions, per-lane
+// address arithmetic); every latent row is read exactly once.  du is the one product that reduces over samples and
+// stays on the row-walk kernel.
+// ---------------------------------------------------------------------------------------------
+// The weight rows of ALL edges of a pass (up to 16 rows of C floats) are staged in shared memory by the whole warp with
+// coalesced 256-byte requests issued together - one memory round trip per pass instead of one per edge - and then read back
+// as warp-uniform (broadcast) LDS.128.
+template <int C4, int COUT, bool BWD>
+__global__ void __launch_bounds__(128)
+agno_dot_s_kernel(const float* __restrict__ r, const float* __restrict__ u, const float* __restrict__ g,
+                  const int64_t* __restrict__ t_rows, const int64_t* __restrict__ t_perm, const int64_t* __restrict__ ts,
+                  float* __restrict__ out, int B, int Ns, int Nd, int64_t E, int64_t n_items) {
+    constexpr int C = C4 * 4;
+    constexpr int EK = 16 / COUT;                      // edges per pass: EK * COUT <= 16 staged rows per warp
+    __shared__ float4 su_all[4][16][C4];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    float4 (*su)[C4] = su_all[wib];
+    const int64_t item = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (item >= n_items) return;                       // whole warps leave together
+    const int j = (int)(item % Ns);
+    const int b = (int)(item / Ns) * 32 + lane;
+    const bool valid = b < B;
+    const int bc = valid ? b : B - 1;
+    const int64_t a = __ldg(ts + j), e = __ldg(ts + j + 1);
+    float4 acc[C4];                                    // FWD: r[b, j, :]   BWD: dr[b, j, :]
+    const float4* rrow = reinterpret_cast<const float4*>(r + ((int64_t)bc * Ns + j) * C);
+#pragma unroll
+    for (int q = 0; q < C4; ++q) acc[q] = BWD ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldg(rrow + q);
+    for (int64_t k0 = a; k0 < e; k0 += EK) {
+        const int ne = (int)min((int64_t)EK, e - k0);
+        int myrow = 0, mype = 0;
+        if (lane < ne) { myrow = (int)__ldg(t_rows + k0 + lane); mype = (int)__ldg(t_perm + k0 + lane); }
+        const int tot = ne * COUT * C4;                // float4 pieces to stage
+        for (int i0 = 0; i0 < tot; i0 += 32) {
+            const int i = i0 + lane;
+            const bool ok = i < tot;
+            const int kk = ok ? i / (COUT * C4) : 0, rem = ok ? i % (COUT * C4) : 0;
+            const int pe = __shfl_sync(0xffffffffu, mype, kk);
+            if (ok) su[kk * COUT + rem / C4][rem % C4] = ldg4(u + (((int64_t)(rem / C4) * E + pe) * C4 + rem % C4) * 4);
+        }
+        float gk[BWD ? EK * COUT : 1];
+        if (BWD) {
+#pragma unroll
+            for (int kk = 0; kk < EK; ++kk) {
+                const int row = __shfl_sync(0xffffffffu, myrow, kk);
+#pragma unroll
+                for (int o = 0; o < COUT; ++o) gk[kk * COUT + o] = kk < ne ? __ldg(g + ((int64_t)bc * Nd + row) * COUT + o) : 0.f;
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int kk = 0; kk < EK; ++kk) {
+            if (kk >= ne) break;                        // warp-uniform
+            const int row = __shfl_sync(0xffffffffu, myrow, kk);
+#pragma unroll
+            for (int o = 0; o < COUT; ++o) {
+                const float4* urow = su[kk * COUT + o];
+                if (BWD) {
+#pragma unroll
+                    for (int q = 0; q < C4; ++q) fma4s(acc[q], urow[q], gk[kk * COUT + o]);
+                } else {
+                    float d0 = 0.f, d1 = 0.f;            // two chains
+#pragma unroll
+                    for (int q = 0; q < C4; q += 2) {
+                        d0 += dot4(urow[q], acc[q]);
+                        if (q + 1 < C4) d1 += dot4(urow[q + 1], acc[q + 1]);
+                    }
+                    if (valid) atomicAdd(out + ((int64_t)b * Nd + row) * COUT + o, d0 + d1);
+                }
+            }
+        }
+        __syncwarp();                                  // the next pass overwrites the staged rows
+    }
+    if (BWD && valid) {
+        float4* drow = reinterpret_cast<float4*>(out + ((int64_t)b * Ns + j) * C);
+#pragma unroll
+        for (int q = 0; q < C4; ++q) drow[q] = acc[q];
     }
 }
 
 inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
-inline int fb_of(int64_t B) { return B >= 8 ? 8 : (B >= 4 ? 4 : (B >= 2 ? 2 : 1)); }
+inline int fb_of(int64_t B) {
+    static int cap = 0;                                // GAOT_B200_FB: experiment knob, samples per work item of the encoder kernels
+    if (!cap) { const char* e = getenv("GAOT_B200_FB"); cap = e ? atoi(e) : 8; if (cap != 1 && cap != 2 && cap != 4 && cap != 8) cap = 8; }
+    const int fb = B >= 8 ? 8 : (B >= 4 ? 4 : (B >= 2 ? 2 : 1));
+    return fb < cap ? fb : cap;
+}
 inline int group_of(int64_t C) { const int nv = (int)(C / 4); return nv <= 4 ? 4 : (nv <= 8 ? 8 : (nv <= 16 ? 16 : 32)); }
 
 #define GAOT_DISPATCH_G(G_, ...)  \
@@ -382,7 +625,8 @@ GAOT_API int gaot_lift_aggregate_fwd(const float* pn, const float* Wl, const flo
     const int fb = fb_of(B);
     const int64_t n_items = Nd * ((B + fb - 1) / fb);
     int64_t blocks = (n_items * g_ + 255) / 256;
-    if (blocks > 148 * 2) blocks = 148 * 2;                 // persistent (2 resident CTAs/SM at 128 registers): grid-stride loop
+    const int resident = fb * (int)Cin <= 16 ? 2 : 1;                                 // CTAs per SM the kernel's register bound allows
+    if (blocks > (int64_t)gaot_sm_count() * resident) blocks = (int64_t)gaot_sm_count() * resident;   // persistent grid-stride loop
     cudaStream_t st = (cudaStream_t)stream;
     GAOT_DISPATCH_FB(fb, GAOT_DISPATCH_G(g_, GAOT_DISPATCH_N((int)Cin, CIN, (lift_aggregate_fwd_kernel<G, CIN, FB><<<(unsigned)blocks, 256, 0, st>>>(
                                                           pn, Wl, bl, w, index, row_splits, out, (int)B, Ns, Nd, (int)C, n_items)))));
@@ -423,7 +667,7 @@ GAOT_API int gaot_agno_dot_fwd(const float* r, const float* u, const int64_t* in
     const int fb = fb_of(B);
     const int64_t n_items = Nd * ((B + fb - 1) / fb);
     int64_t blocks = (n_items * g_ + 255) / 256;
-    if (blocks > 148 * 2) blocks = 148 * 2;                 // persistent (2 resident CTAs/SM at 128 registers): grid-stride loop
+    if (blocks > gaot_sm_count() * 2) blocks = gaot_sm_count() * 2;                 // persistent (2 resident CTAs/SM at 128 registers): grid-stride loop
     cudaStream_t st = (cudaStream_t)stream;
     GAOT_DISPATCH_FB(fb, GAOT_DISPATCH_G(g_, GAOT_DISPATCH_N((int)Cout, COUT, (agno_dot_fwd_kernel<G, COUT, FB><<<(unsigned)blocks, 256, 0, st>>>(
                                                             r, u, index, row_splits, out, (int)B, Ns, Nd, E, (int)C, n_items)))));
@@ -450,9 +694,7 @@ GAOT_API int gaot_agno_dot_bwd(const float* g, const float* r, const float* u, c
         ++launches;
     }
     if (du && Nd > 0 && E > 0) {
-        int bsplit = 1;
-        while (bsplit < B && Nd * g_ * bsplit < 148LL * 2048 && bsplit < 8) bsplit <<= 1;
-        if (bsplit > B) bsplit = (int)B;
+        const int bsplit = (int)((B + 7) / 8);                  // slices of 8 samples (agno_dot_bwd_u_kernel)
         if (bsplit > 1) GAOT_CHECK(cudaMemsetAsync(du, 0, sizeof(float) * (size_t)(Cout * E * C), st));
         const int64_t n_items = Nd * bsplit;
         const int64_t blocks = (n_items * g_ + 255) / 256;
@@ -463,5 +705,115 @@ GAOT_API int gaot_agno_dot_bwd(const float* g, const float* r, const float* u, c
     }
     if (launches == 0) return 0;
     if (launches == 2) GAOT_NOTE_LAUNCHES(1);
+    GAOT_RETURN_LAST();
+}
+
+namespace {
+// lane-per-sample kernels: C4 in {4, 8, 12, 16} (C = 16 ... 64), batches of at least 16 samples
+template <bool BWD>
+bool launch_dot_s(const float* r, const float* u, const float* g, const int64_t* t_rows, const int64_t* t_perm, const int64_t* ts,
+                  float* out, int B, int Ns, int Nd, int64_t E, int C, int Cout, cudaStream_t st) {
+    if (B < 16 || C % 16 || C > 64) return false;
+    const int64_t n_items = (int64_t)Ns * ((B + 31) / 32);
+    const int64_t blocks = (n_items * 32 + 127) / 128;
+    if (blocks > 0x7fffffffLL) return false;
+#define GAOT_S_CASE(C4_, CO_) if (C == 4 * C4_ && Cout == CO_) { \
+        agno_dot_s_kernel<C4_, CO_, BWD><<<(unsigned)blocks, 128, 0, st>>>(r, u, g, t_rows, t_perm, ts, out, B, Ns, Nd, E, n_items); return true; }
+    GAOT_S_CASE(4, 1) GAOT_S_CASE(8, 1) GAOT_S_CASE(12, 1) GAOT_S_CASE(16, 1)
+    GAOT_S_CASE(4, 2) GAOT_S_CASE(8, 2) GAOT_S_CASE(12, 2) GAOT_S_CASE(16, 2)
+    GAOT_S_CASE(4, 3) GAOT_S_CASE(8, 3) GAOT_S_CASE(12, 3) GAOT_S_CASE(16, 3)
+    GAOT_S_CASE(4, 4) GAOT_S_CASE(8, 4) GAOT_S_CASE(12, 4) GAOT_S_CASE(16, 4)
+#undef GAOT_S_CASE
+    return false;
+}
+template <int G, int COUT, int KE>
+void launch_dot_fwd_t(const float* r, const float* u, const int64_t* t_rows, const int64_t* t_perm, const int64_t* ts, float* out,
+                      int B, int Ns, int Nd, int64_t E, int C, int64_t n_items, int bslices, cudaStream_t st) {
+    const int64_t blocks = (n_items * G + 255) / 256;
+    agno_dot_fwd_t_kernel<G, COUT, KE><<<(unsigned)blocks, 256, 0, st>>>(r, u, t_rows, t_perm, ts, out, B, Ns, Nd, E, C, n_items, bslices);
+}
+template <int G, int COUT, int KE>
+void launch_dot_bwd_t(const float* g, const float* r, const float* u, const int64_t* t_rows, const int64_t* t_perm, const int64_t* ts,
+                      float* dr, float* du, int B, int Ns, int Nd, int64_t E, int C, int64_t n_items, int bslices, cudaStream_t st) {
+    const int64_t blocks = (n_items * G + 255) / 256;
+    agno_dot_bwd_t_kernel<G, COUT, KE><<<(unsigned)blocks, 256, 0, st>>>(g, r, u, t_rows, t_perm, ts, dr, du, B, Ns, Nd, E, C, n_items,
+                                                                        bslices);
+}
+// batch slices per source: enough groups to fill the chip (sources alone do when the batch is small and the mesh is large)
+inline int slices_of(int64_t Ns, int g_, int64_t B) {
+    const int64_t want = (int64_t)gaot_sm_count() * 1536;               // threads for ~75 % occupancy
+    int s = 1;
+    while (s < B && Ns * g_ * s < want && s < 8) s <<= 1;
+    return (int)(s > B ? B : s);
+}
+}  // namespace
+
+// Source-walk form of gaot_agno_dot_fwd (see the kernel comment): needs the transposed graph; `out` is zeroed here and reduced
+// into with fp32 red.add (summation order inside a row is not fixed; the row-walk gaot_agno_dot_fwd is the deterministic form).
+GAOT_API int gaot_agno_dot_fwd_t(const float* r, const float* u, const int64_t* t_splits, const int64_t* t_rows,
+                                 const int64_t* t_perm, float* out, int64_t B, int64_t Ns, int64_t Nd, int64_t E, int64_t C,
+                                 int64_t Cout, void* stream) {
+    if (!r || !u || !t_splits || !t_rows || !t_perm || !out || B < 1 || Ns < 0 || Nd < 0 || E < 0) return GAOT_E_BADARG;
+    if (C % 4 || C > 128 || Cout < 1 || Cout > 4) return GAOT_E_BADARG;
+    if (Ns > 0x7fffffffLL || Nd > 0x7fffffffLL) return GAOT_E_BADARG;
+    if (!al16(r) || !al16(u)) return GAOT_E_ALIGN;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (Nd == 0) return 0;
+    GAOT_CHECK(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)(B * Nd * Cout), st));
+    if (Ns == 0 || E == 0) return 0;
+    if (launch_dot_s<false>(r, u, nullptr, t_rows, t_perm, t_splits, out, (int)B, (int)Ns, (int)Nd, E, (int)C, (int)Cout, st)) GAOT_RETURN_LAST();
+    const int g_ = group_of(C);
+    const int sl = slices_of(Ns, g_, B);
+    const int64_t n_items = Ns * sl;
+    if ((n_items * g_ + 255) / 256 > 0x7fffffffLL) return GAOT_E_BADARG;
+    GAOT_DISPATCH_G(g_, {
+        if (Cout == 1) launch_dot_fwd_t<G, 1, 8>(r, u, t_rows, t_perm, t_splits, out, (int)B, (int)Ns, (int)Nd, E, (int)C, n_items, sl, st);
+        else if (Cout == 2) launch_dot_fwd_t<G, 2, 4>(r, u, t_rows, t_perm, t_splits, out, (int)B, (int)Ns, (int)Nd, E, (int)C, n_items, sl, st);
+        else if (Cout == 3) launch_dot_fwd_t<G, 3, 2>(r, u, t_rows, t_perm, t_splits, out, (int)B, (int)Ns, (int)Nd, E, (int)C, n_items, sl, st);
+        else launch_dot_fwd_t<G, 4, 2>(r, u, t_rows, t_perm, t_splits, out, (int)B, (int)Ns, (int)Nd, E, (int)C, n_items, sl, st);
+    });
+    GAOT_RETURN_LAST();
+}
+
+// Source-walk backward: dr and du in ONE pass over the transposed graph, no gather of latent rows per edge.
+GAOT_API int gaot_agno_dot_bwd_t(const float* g, const float* r, const float* u, const int64_t* index, const int64_t* row_splits,
+                                 const int64_t* t_splits, const int64_t* t_rows, const int64_t* t_perm, float* dr, float* du,
+                                 int64_t B, int64_t Ns, int64_t Nd, int64_t E, int64_t C, int64_t Cout, void* stream) {
+    if (!g || !r || !u || !t_splits || !t_rows || !t_perm || (!dr && !du) || B < 1 || Ns < 0 || Nd < 0 || E < 0) return GAOT_E_BADARG;
+    if (C % 4 || C > 128 || Cout < 1 || Cout > 4) return GAOT_E_BADARG;
+    if (Ns > 0x7fffffffLL || Nd > 0x7fffffffLL) return GAOT_E_BADARG;
+    if (!al16(r) || !al16(u) || (dr && !al16(dr)) || (du && !al16(du))) return GAOT_E_ALIGN;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (Ns == 0) return 0;
+    const int g_ = group_of(C);
+    if (index && row_splits && B >= 16 && C % 16 == 0 && C <= 64) {
+        // batches of >= 16 samples: dr with one lane per sample on the transposed graph (each latent-row gradient is
+        // formed in registers and stored once); du, the product that reduces over samples, on the row-sorted graph
+        int launches = 0;
+        if (dr && launch_dot_s<true>(r, u, g, t_rows, t_perm, t_splits, dr, (int)B, (int)Ns, (int)Nd, E, (int)C, (int)Cout, st)) ++launches;
+        if (du && Nd > 0 && E > 0) {
+            const int bsplit = (int)((B + 7) / 8);
+            if (bsplit > 1) GAOT_CHECK(cudaMemsetAsync(du, 0, sizeof(float) * (size_t)(Cout * E * C), st));
+            const int64_t n_items = Nd * bsplit;
+            const int64_t blocks = (n_items * g_ + 255) / 256;
+            if (blocks > 0x7fffffffLL) return GAOT_E_BADARG;
+            GAOT_DISPATCH_G(g_, GAOT_DISPATCH_N((int)Cout, COUT, (agno_dot_bwd_u_kernel<G, COUT><<<(unsigned)blocks, 256, 0, st>>>(
+                                                                    g, r, index, row_splits, du, (int)B, Ns, Nd, E, (int)C, bsplit, n_items))));
+            ++launches;
+        }
+        if (launches == 0) return 0;
+        if (launches == 2) GAOT_NOTE_LAUNCHES(1);
+        GAOT_RETURN_LAST();
+    }
+    const int sl = slices_of(Ns, g_, B);
+    if (du && sl > 1 && E > 0) GAOT_CHECK(cudaMemsetAsync(du, 0, sizeof(float) * (size_t)(Cout * E * C), st));
+    const int64_t n_items = Ns * sl;
+    if ((n_items * g_ + 255) / 256 > 0x7fffffffLL) return GAOT_E_BADARG;
+    GAOT_DISPATCH_G(g_, {
+        if (Cout == 1) launch_dot_bwd_t<G, 1, 8>(g, r, u, t_rows, t_perm, t_splits, dr, du, (int)B, (int)Ns, (int)Nd, E, (int)C, n_items, sl, st);
+        else if (Cout == 2) launch_dot_bwd_t<G, 2, 4>(g, r, u, t_rows, t_perm, t_splits, dr, du, (int)B, (int)Ns, (int)Nd, E, (int)C, n_items, sl, st);
+        else if (Cout == 3) launch_dot_bwd_t<G, 3, 2>(g, r, u, t_rows, t_perm, t_splits, dr, du, (int)B, (int)Ns, (int)Nd, E, (int)C, n_items, sl, st);
+        else launch_dot_bwd_t<G, 4, 2>(g, r, u, t_rows, t_perm, t_splits, dr, du, (int)B, (int)Ns, (int)Nd, E, (int)C, n_items, sl, st);
+    });
     GAOT_RETURN_LAST();
 }

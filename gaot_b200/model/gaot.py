@@ -37,6 +37,7 @@ class GAOT(nn.Module):
         self.overlap_decoder_prep = True        # run the decoder's batch-independent work on a side stream (CUDA only)
         self._side_stream = None
         self._pos_emb = None
+        self._rollout_graph = None              # captured rollout forward (autoregressive_predict(use_cuda_graph=True))
 
     def _grid(self):
         return (self.H, self.W) if self.coord_dim == 2 else (self.H, self.W, self.D)
@@ -155,10 +156,17 @@ class GAOT(nn.Module):
         um, us = t(stats["u"]["mean"]), t(stats["u"]["std"])
         skey = {1: "res", 2: "der"}.get(mode)
         sm, ss = (t(stats[skey]["mean"]), t(stats[skey]["std"])) if skey else (um, us)
-        x_in = torch.empty((B, N, U + nc + 2), dtype=torch.float32, device=dev)     # static step input [u | c | t0 | dt]
+        # static step input [u | c | t0 | dt]; with use_cuda_graph the buffer, the captured forward and its output live on the
+        # model and are reused by every later rollout over the same mesh and batch shape (capture costs ~30 forwards)
+        key = (B, N, U, nc, bool(use_conditional_norm), ops.get_precision(),
+               None if latent_tokens_coord is None else latent_tokens_coord.data_ptr(),
+               None if fixed_coord is None else fixed_coord.data_ptr(), id(encoder_nbrs), id(decoder_nbrs))
+        cached = self._rollout_graph if (use_cuda_graph and dev.type == "cuda" and self._rollout_graph is not None
+                                         and self._rollout_graph["key"] == key) else None
+        x_in = cached["x_in"] if cached else torch.empty((B, N, U + nc + 2), dtype=torch.float32, device=dev)
         if nc:
             x_in[..., U:U + nc] = x_batch[..., U:U + nc]
-        graph = pred_static = None
+        graph, pred_static = (cached["graph"], cached["pred"]) if cached else (None, None)
 
         def fwd():
             if use_conditional_norm:
@@ -186,6 +194,7 @@ class GAOT(nn.Module):
                     graph = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(graph):
                         pred_static = fwd()
+                    self._rollout_graph = {"key": key, "graph": graph, "pred": pred_static, "x_in": x_in}
                 graph.replay()
                 pred = pred_static
             else:

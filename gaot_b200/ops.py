@@ -126,14 +126,28 @@ def graph_plan(nbrs, n_src: int) -> GraphPlan:
 
 def merge_graphs(graphs: List[dict], n_src_each: int) -> GraphPlan:
     """Block-diagonal merge of per-sample CSR graphs (vx mode): sample b's sources are offset by
-    b*n_src_each and its rows appended after sample b-1's rows.  One launch then serves the batch."""
-    idx = torch.cat([g["neighbors_index"].to(torch.int64) + b * n_src_each for b, g in enumerate(graphs)])
-    parts, off = [graphs[0]["neighbors_row_splits"][:1].to(torch.int64)], 0
-    for g in graphs:
-        rs = g["neighbors_row_splits"].to(torch.int64)
-        parts.append(rs[1:] + off)
-        off += int(g["neighbors_index"].numel())
-    return GraphPlan(idx, torch.cat(parts), n_src_each * len(graphs))
+    b*n_src_each and its rows appended after sample b-1's rows.  One launch then serves the batch.
+    A fixed number of device ops whatever the batch size, and no device -> host read: the per-sample edge counts are
+    tensor shapes, i.e. already on the host."""
+    B = len(graphs)
+    dev = graphs[0]["neighbors_index"].device
+    Es = [int(g["neighbors_index"].numel()) for g in graphs]
+    E = sum(Es)
+    idx = torch.cat([g["neighbors_index"] for g in graphs]).to(torch.int64)
+    e_off = [0]
+    for e in Es[:-1]:
+        e_off.append(e_off[-1] + e)
+    host = torch.tensor([Es, e_off], dtype=torch.int64)
+    if dev.type == "cuda":
+        host = host.pin_memory()
+    meta = host.to(dev, non_blocking=True)
+    if E > 0:
+        src_off = torch.repeat_interleave(torch.arange(B, device=dev, dtype=torch.int64) * n_src_each, meta[0], output_size=E)
+        idx = idx + src_off
+    rs = torch.stack([g["neighbors_row_splits"].to(torch.int64) for g in graphs])         # [B, m + 1], equal m per sample
+    body = (rs[:, 1:] + meta[1][:, None]).reshape(-1)
+    splits = torch.cat([rs.new_zeros(1), body])
+    return GraphPlan(idx, splits, n_src_each * B)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -842,6 +856,18 @@ def lift_aggregate(pn, Wl, bl, w, plan):
     return _LiftAggregate.apply(pn, Wl, bl, w, plan)
 
 
+# Decoder aggregate: walk the graph by source node (default; reads every latent row once per sample) or by destination row
+# (deterministic summation order; GAOT_B200_ROW_WALK=1 or ops.ROW_WALK = True).
+import os as _os
+ROW_WALK = bool(int(_os.environ.get("GAOT_B200_ROW_WALK", "0")))
+
+
+def source_walk_pays(B, C):
+    """The lane-per-sample source-walk kernels need a batch that fills most of a warp and a latent row that fits a lane's
+    registers; small batches (vx mode's merged graphs, B = 1 per GPU) stay on the row-walk kernels."""
+    return B >= 16 and C % 16 == 0 and C <= 64
+
+
 class _AgnoDot(torch.autograd.Function):
     """out[b,r,o] = sum_{e in r} <u[o,e,:], f[b,index[e],:]>: aggregate fused with an affine read-out."""
 
@@ -853,7 +879,12 @@ class _AgnoDot(torch.autograd.Function):
         if Ns != plan.n_src or u.shape[1] != plan.E or u.shape[2] != C:
             raise ValueError(f"agno_dot: f {tuple(f.shape)} / u {tuple(u.shape)} do not match graph")
         out = torch.empty((B, plan.m, Cout), dtype=torch.float32, device=f.device)
-        call("gaot_agno_dot_fwd", ptr(f), ptr(u), ptr(plan.index), ptr(plan.splits), ptr(out), B, Ns, plan.m, plan.E, C, Cout)
+        ctx.row_walk = ROW_WALK or not source_walk_pays(B, C)
+        if ctx.row_walk:
+            call("gaot_agno_dot_fwd", ptr(f), ptr(u), ptr(plan.index), ptr(plan.splits), ptr(out), B, Ns, plan.m, plan.E, C, Cout)
+        else:
+            ts, tr, tp = plan.transposed()
+            call("gaot_agno_dot_fwd_t", ptr(f), ptr(u), ptr(ts), ptr(tr), ptr(tp), ptr(out), B, Ns, plan.m, plan.E, C, Cout)
         ctx.save_for_backward(f, u)
         ctx.plan = plan
         return out
@@ -867,9 +898,16 @@ class _AgnoDot(torch.autograd.Function):
         Cout = u.shape[0]
         df = torch.empty_like(f) if ctx.needs_input_grad[0] else None
         du = torch.empty_like(u) if ctx.needs_input_grad[1] else None
-        ts, tr, tp = plan.transposed() if df is not None else (None, None, None)
-        call("gaot_agno_dot_bwd", ptr(g), ptr(f), ptr(u), ptr(plan.index), ptr(plan.splits), ptr(ts), ptr(tr), ptr(tp), ptr(df),
-             ptr(du), B, Ns, plan.m, plan.E, C, Cout)
+        if df is None and du is None:
+            return None, None, None
+        if ctx.row_walk:
+            ts, tr, tp = plan.transposed() if df is not None else (None, None, None)
+            call("gaot_agno_dot_bwd", ptr(g), ptr(f), ptr(u), ptr(plan.index), ptr(plan.splits), ptr(ts), ptr(tr), ptr(tp), ptr(df),
+                 ptr(du), B, Ns, plan.m, plan.E, C, Cout)
+        else:
+            ts, tr, tp = plan.transposed()
+            call("gaot_agno_dot_bwd_t", ptr(g), ptr(f), ptr(u), ptr(plan.index), ptr(plan.splits), ptr(ts), ptr(tr), ptr(tp), ptr(df),
+                 ptr(du), B, Ns, plan.m, plan.E, C, Cout)
         return df, du, None
 
 

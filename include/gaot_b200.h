@@ -135,6 +135,23 @@ int gaot_agno_dot_bwd(const float* g, const float* f, const float* u, const int6
                       const int64_t* t_splits, const int64_t* t_rows, const int64_t* t_perm, float* df, float* du,
                       int64_t B, int64_t Ns, int64_t Nd, int64_t E, int64_t C, int64_t Cout, void* stream);
 
+/* Source-walk forms of the two entry points above (the default decoder path).  A group of lanes owns one SOURCE node j
+ * (latent token) of the transposed graph {t_splits [Ns+1], t_rows [E] destination row of each edge, t_perm [E] edge id in the
+ * row-sorted order}: it reads r[b, j, :] once per sample and serves every edge leaving j from registers, instead of
+ * gathering the 256-byte latent row again for every edge and sample (agno.py:198 materialises exactly that gather).
+ * Forward: `out` is zeroed, then reduced into with fp32 red.add (order inside a row not fixed; gaot_agno_dot_fwd is the
+ * deterministic form).  Backward: dr and du in one pass, plain stores (du by red.add only when the batch is split).
+ * Batches of >= 16 samples with C in {16, 32, 48, 64} take the lane-per-sample kernels: one warp owns a source node and 32
+ * samples, a lane keeps its sample's whole latent row in registers and the edge weights are warp-uniform loads, so no
+ * cross-lane reduction is needed; du (the product that reduces over samples) then runs on the row-sorted graph, which the
+ * optional index / row_splits arguments of the backward provide. */
+int gaot_agno_dot_fwd_t(const float* r, const float* u, const int64_t* t_splits, const int64_t* t_rows,
+                        const int64_t* t_perm, float* out, int64_t B, int64_t Ns, int64_t Nd, int64_t E, int64_t C,
+                        int64_t Cout, void* stream);
+int gaot_agno_dot_bwd_t(const float* g, const float* r, const float* u, const int64_t* index, const int64_t* row_splits,
+                        const int64_t* t_splits, const int64_t* t_rows, const int64_t* t_perm, float* dr, float* du,
+                        int64_t B, int64_t Ns, int64_t Nd, int64_t E, int64_t C, int64_t Cout, void* stream);
+
 /* z[e,k] = y[index[e],k] - x[edge_row[e],k], k < d: neighbour coordinates centred on their query point
  * (pointnet geometry embedding, gemb.py:208-213) */
 int gaot_edge_diff(const float* y, int64_t dy, const float* x, int64_t dx, int64_t d, const int64_t* index,

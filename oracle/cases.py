@@ -166,3 +166,30 @@ def nbr_case(name: str):
 
 
 NBR_CASES = ["rand2d", "rand3d", "dec2d", "lattice2d", "lattice3d", "empty"]
+
+
+# ---- dataset-side fixtures (graph builder, time-pair dataset) -----------------------------------------------------
+def graph_builder_case():
+    """(x_data [S, 1, n, 2] UN-scaled sample meshes, latent [M, 2], radius, scales): the builder rescales every sample to
+    [-1, 1] by its own min / max (graph_builder.py:60) before searching."""
+    S, n = 4, 180
+    xs = []
+    for b in range(S):
+        x = clustered_points(n, 2, 500 + b)
+        xs.append(x * torch.tensor([1.0 + 0.5 * b, 2.0]) + torch.tensor([3.0 * b, -1.0]))      # different boxes per sample
+    return torch.stack(xs).unsqueeze(1), latent_grid((8, 8)), 0.3, [1.0, 1.5]
+
+
+def pair_dataset_case():
+    """u [S, T, N, U], c [S, T, N, 1], t_values [T], x [S, T, N, 2], stats - small sequential dataset."""
+    S, T, N, U = 3, 9, 40, 2
+    u = normal((S, T, N, U), 601)
+    c = normal((S, T, N, 1), 602)
+    x = uniform_points(S * T * N, 2, 603).view(S, T, N, 2)
+    tv = torch.linspace(0.0, 1.6, T)
+    stats = {"u": {"mean": torch.tensor([0.1, -0.2]), "std": torch.tensor([1.2, 0.8])},
+             "c": {"mean": torch.tensor([0.3]), "std": torch.tensor([1.5])},
+             "res": {"mean": torch.tensor([0.01, 0.02]), "std": torch.tensor([0.5, 0.6])},
+             "der": {"mean": torch.tensor([0.0, 0.1]), "std": torch.tensor([2.0, 3.0])},
+             "start_time": {"mean": 0.5, "std": 0.4}, "time_diffs": {"mean": 0.6, "std": 0.3}}
+    return u, c, tv, x, stats

@@ -176,13 +176,71 @@ def rollout_golden():
         torch.set_default_dtype(torch.float32)
 
 
+def _load_ref_file(name, path, package=None):
+    """Import ONE reference source file without running its package __init__ (src/datasets/__init__.py needs xarray,
+    src/utils/__init__.py needs matplotlib - both absent here)."""
+    import importlib.util
+    import types
+    if package and package not in sys.modules:
+        pkg = types.ModuleType(package)
+        pkg.__path__ = []
+        sys.modules[package] = pkg
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def datasets_golden():
+    """Reference GraphBuilder.build_graphs_for_split (graph_builder.py:28-87, with utils/scaling.rescale) and
+    DynamicPairDataset (data_utils.py:73-235) run on the dataset fixtures of oracle/cases.py."""
+    _load_ref_file("src.utils.scaling", "/root/reference/src/utils/scaling.py", "src.utils")
+    gb = _load_ref_file("src.datasets.graph_builder", "/root/reference/src/datasets/graph_builder.py", "src.datasets")
+    du = _load_ref_file("src.datasets.data_utils", "/root/reference/src/datasets/data_utils.py", "src.datasets")
+    arrs = {}
+    x_data, lat, r, scales = cases.graph_builder_case()
+    enc, dec = gb.GraphBuilder("native").build_graphs_for_split(x_data, lat, r, scales)
+    for tag, graphs in (("enc", enc), ("dec", dec)):
+        for b, per_scale in enumerate(graphs):
+            for s_, g in enumerate(per_scale):
+                arrs[f"gb.{tag}.{b}.{s_}.index"] = g["neighbors_index"].numpy().astype(np.int32)
+                arrs[f"gb.{tag}.{b}.{s_}.splits"] = g["neighbors_row_splits"].numpy().astype(np.int32)
+    print(f"[graph builder] {len(enc)} samples x {len(scales)} scales, E(enc) = "
+          f"{[int(g[0]['neighbors_index'].numel()) for g in enc]}")
+    u, c, tv, x, stats = cases.pair_dataset_case()
+    for mode in ("output", "residual", "time_der"):
+        for vx in (False, True):
+            ds = du.DynamicPairDataset(u, c, tv, None, max_time_diff=6, time_step=2, stepper_mode=mode, stats=stats,
+                                       x_data=x if vx else None, is_variable_coords=vx)
+            tag = f"pairs.{mode}.{'vx' if vx else 'fx'}"
+            arrs[tag + ".len"] = np.int64(len(ds))
+            arrs[tag + ".t_in"], arrs[tag + ".t_out"] = ds.t_in_indices, ds.t_out_indices
+            pick = list(range(0, len(ds), 5))
+            items = [ds[i] for i in pick]
+            arrs[tag + ".pick"] = np.array(pick)
+            arrs[tag + ".input"] = torch.stack([it[0] for it in items]).numpy()
+            arrs[tag + ".target"] = torch.stack([it[1] for it in items]).numpy()
+            if vx:
+                arrs[tag + ".x"] = torch.stack([it[2] for it in items]).numpy()
+    ds = du.DynamicPairDataset(u, None, tv, None, max_time_diff=14, time_step=1, stepper_mode="residual", stats=None,
+                               use_time_norm=False)
+    arrs["pairs.nostats.len"] = np.int64(len(ds))
+    arrs["pairs.nostats.input"] = torch.stack([ds[i][0] for i in range(0, len(ds), 7)]).numpy()
+    arrs["pairs.nostats.target"] = torch.stack([ds[i][1] for i in range(0, len(ds), 7)]).numpy()
+    print(f"[pair dataset] {int(arrs['pairs.output.fx.len'])} pairs per configuration")
+    np.savez_compressed(os.path.join(OUT, "datasets.npz"), **arrs)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     only = sys.argv[1:]                                   # optional: regenerate just these model cases
     if not only or "rollout" in only:
         rollout_golden()
-        if only == ["rollout"]:
-            return
+    if not only or "datasets" in only:
+        datasets_golden()
+    if only and all(o in ("rollout", "datasets") for o in only):
+        return
     for name, c in cases.CASES.items():
         if only and name not in only:
             continue

@@ -222,6 +222,31 @@ def gaot_agno_dot_bwd(gr, f, u, index, row_splits, ts, tr, tp, df, du, B, Ns, Nd
         _arr(du, (Cout, E, C))[:] = U.grad.float().numpy()
 
 
+def gaot_agno_dot_fwd_t(f, u, ts, tr, tp, out, B, Ns, Nd, E, C, Cout):
+    F, U = _t(f, (B, Ns, C)).double(), _t(u, (Cout, E, C)).double()
+    tsp, rows, perm = _arr(ts, (Ns + 1,), np.int64), _arr(tr, (E,), np.int64), _arr(tp, (E,), np.int64)
+    src = np.repeat(np.arange(Ns, dtype=np.int64), np.diff(tsp))          # source node of transposed slot k
+    o = torch.zeros((B, Nd, Cout), dtype=torch.float64)
+    contrib = torch.einsum("oec,bec->beo", U[:, perm, :], F[:, src, :])   # [B, E, Cout] in transposed slot order
+    o.index_add_(1, torch.from_numpy(rows), contrib)
+    _t(out, (B, Nd, Cout))[:] = o.float()
+
+
+def gaot_agno_dot_bwd_t(gr, f, u, index, row_splits, ts, tr, tp, df, du, B, Ns, Nd, E, C, Cout):
+    G, F, U = _t(gr, (B, Nd, Cout)).double(), _t(f, (B, Ns, C)).double(), _t(u, (Cout, E, C)).double()
+    tsp, rows, perm = _arr(ts, (Ns + 1,), np.int64), _arr(tr, (E,), np.int64), _arr(tp, (E,), np.int64)
+    src = torch.from_numpy(np.repeat(np.arange(Ns, dtype=np.int64), np.diff(tsp)))
+    gk = G[:, torch.from_numpy(rows), :]                                   # [B, E, Cout] in transposed slot order
+    if df:
+        d = torch.zeros((B, Ns, C), dtype=torch.float64)
+        d.index_add_(1, src, torch.einsum("beo,oec->bec", gk, U[:, perm, :]))
+        _t(df, (B, Ns, C))[:] = d.float()
+    if du:
+        D = torch.zeros((Cout, E, C), dtype=torch.float64)
+        D[:, perm, :] = torch.einsum("beo,bec->oec", gk, F[:, src, :])
+        _t(du, (Cout, E, C))[:] = D.float()
+
+
 def gaot_cond_affine_fwd(x, scale, bias, y, B, T, D):
     _arr(y, (B, T, D))[:] = _arr(x, (B, T, D)) * _arr(scale, (B, D))[:, None, :] + _arr(bias, (B, D))[:, None, :]
 

@@ -259,17 +259,38 @@ def test_fused_lift_aggregate_and_dot_vs_oracle():
         got.backward(go.to(DEV))
         for a, b in zip(mine, ref):
             assert rel_l2(a.grad, b.grad) < 5e-6
-    for C, B, Cout in ((64, 11, 1), (48, 3, 3), (16, 8, 2)):
-        f, u = cases.normal((B, n, C), 36), cases.normal((Cout, E, C), 37)
-        fr, ur = f.double().requires_grad_(True), u.double().requires_grad_(True)
-        want = orc.segment_csr(torch.einsum("oec,bec->beo", ur, fr[:, g["neighbors_index"], :]), g["neighbors_row_splits"], "sum")
-        fg, ug = f.to(DEV).requires_grad_(True), u.to(DEV).requires_grad_(True)
-        got = ops.agno_dot(fg, ug, plan)
-        assert rel_l2(got, want) < 2e-6
-        go = cases.normal(tuple(want.shape), 38)
-        want.backward(go.double())
-        got.backward(go.to(DEV))
-        assert rel_l2(fg.grad, fr.grad) < 2e-6 and rel_l2(ug.grad, ur.grad) < 5e-6
+
+
+@pytest.mark.parametrize("row_walk", [False, True])
+@pytest.mark.parametrize("name", ["rand2d", "dec2d", "lattice2d", "rand3d", "empty"])
+def test_agno_dot_both_walks_vs_oracle(name, row_walk):
+    """Decoder aggregate + affine read-out, forward and backward, in both traversal orders: by source node on the transposed
+    graph (default: gaot_agno_dot_{fwd,bwd}_t) and by destination row (gaot_agno_dot_{fwd,bwd}); graphs with empty rows,
+    sources without edges, duplicate points and degrees above the 8 edges a pass holds in registers."""
+    ops = _ops()
+    data, q, r = cases.nbr_case(name)
+    g = orc.radius_csr(data, q, r)
+    E, n, m = g["neighbors_index"].numel(), data.shape[0], q.shape[0]
+    plan = ops.GraphPlan(g["neighbors_index"].to(DEV), g["neighbors_row_splits"].to(DEV), n)
+    old = ops.ROW_WALK
+    ops.ROW_WALK = row_walk
+    try:
+        for C, B, Cout in ((64, 11, 1), (48, 3, 3), (16, 8, 2), (64, 32, 1), (32, 1, 4), (48, 16, 2), (16, 40, 3), (32, 33, 4)):
+            f, u = cases.normal((B, n, C), 36), cases.normal((Cout, E, C), 37)
+            fr, ur = f.double().requires_grad_(True), u.double().requires_grad_(True)
+            want = orc.segment_csr(torch.einsum("oec,bec->beo", ur, fr[:, g["neighbors_index"], :]), g["neighbors_row_splits"], "sum")
+            fg, ug = f.to(DEV).requires_grad_(True), u.to(DEV).requires_grad_(True)
+            got = ops.agno_dot(fg, ug, plan)
+            go = cases.normal(tuple(want.shape), 38)
+            want.backward(go.double())
+            got.backward(go.to(DEV))
+            if E == 0:
+                assert float(got.abs().max()) == 0.0 and float(fg.grad.abs().max()) == 0.0
+                continue
+            assert rel_l2(got, want) < 2e-6
+            assert rel_l2(fg.grad, fr.grad) < 2e-6 and rel_l2(ug.grad, ur.grad) < 5e-6
+    finally:
+        ops.ROW_WALK = old
 
 
 @pytest.mark.parametrize("name", ["rand2d", "dec2d", "lattice2d", "empty"])

@@ -78,7 +78,7 @@ def test_model_wiring_matches_reference_golden(name, fuse, precision):
         if not fusable:
             assert "gaot_agno_aggregate" in calls and "gaot_agno_weight_grad" in calls
         elif len(c["magno"].get("scales", [1.0])) == 1:
-            assert "gaot_agno_dot_bwd" in calls
+            assert "gaot_agno_dot_bwd" in calls and "gaot_agno_dot_fwd" in calls       # B < 16: row walk
     assert rel_l2(out, g["out"]) < 1e-5
     assert abs(float(loss) - float(g["loss64"])) < 1e-5 * abs(float(g["loss64"]))
     gs = grad_scale(g, g["keys"])
