@@ -864,10 +864,21 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
         fetch_stat(f_h, f_qt);
         for (int i = 0; i < n_steps; ++i) {
             const int bf = i % NBUF;
-            if constexpr (SPLIT) stat_s = stat_s0 + (uint32_t)(i & 1) * 256u;
-            sts_f32(stat_s + (uint32_t)lane * 4u, st_l * 1.4426950408889634f);
-            sts_f32(stat_s + 128u + (uint32_t)lane * 4u, st_d);
-            __syncwarp();
+            if constexpr (SPLIT) {
+                // one slab per column group and step parity: the group's first warp writes it, a 128-thread named barrier
+                // publishes it to the other three (the barrier of step i+1 also orders their reads of step i before the
+                // rewrite of this parity's slab at step i+2)
+                stat_s = stat_s0 + (uint32_t)(i & 1) * 256u;
+                if (q4 == 0) {
+                    sts_f32(stat_s + (uint32_t)lane * 4u, st_l * 1.4426950408889634f);
+                    sts_f32(stat_s + 128u + (uint32_t)lane * 4u, st_d);
+                }
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + qr) : "memory");
+            } else {
+                sts_f32(stat_s + (uint32_t)lane * 4u, st_l * 1.4426950408889634f);
+                sts_f32(stat_s + 128u + (uint32_t)lane * 4u, st_d);
+                __syncwarp();
+            }
             if (i + 1 < n_steps) {
                 if (++f_qt == n_qt) { f_qt = 0; ++f_h; }
                 fetch_stat(f_h, f_qt);
@@ -1034,9 +1045,16 @@ EncodeTiledFn get_encode() {
 }
 
 // [rows, ld] bf16 matrix, box {hd, box_rows}, swizzle span = hd*2 bytes
+// the driver-API encode needs a current context: the autograd engine's threads have none until a runtime call binds it
+inline void bind_context_once() {
+    static thread_local bool bound = false;
+    if (!bound) { cudaFree(nullptr); bound = true; }
+}
+
 int make_head_map(CUtensorMap* map, const void* base, int64_t rows, int64_t ld, int hd, int box_rows) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return GAOT_E_BADARG;
+    bind_context_once();
     cuuint64_t dims[2] = {(cuuint64_t)ld, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
     cuuint32_t box[2] = {(cuuint32_t)hd, (cuuint32_t)box_rows};
@@ -1075,6 +1093,7 @@ int launch_fwd(const CUtensorMap& tm, const AttnArgs& g, int64_t B, cudaStream_t
 int make_head_map_planes(CUtensorMap* map, const void* base, int64_t rows, int64_t ld, int hd, int box_rows) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return GAOT_E_BADARG;
+    bind_context_once();
     cuuint64_t dims[3] = {(cuuint64_t)ld, (cuuint64_t)rows, 2};
     cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)ld * (cuuint64_t)rows * 2};
     cuuint32_t box[3] = {(cuuint32_t)hd, (cuuint32_t)box_rows, 1};

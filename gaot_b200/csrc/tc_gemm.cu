@@ -746,7 +746,14 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+// the driver-API encode needs a current context: the autograd engine's threads have none until a runtime call binds it
+inline void bind_context_once() {
+    static thread_local bool bound = false;
+    if (!bound) { cudaFree(nullptr); bound = true; }
+}
+
 EncodeTiledFn get_encode() {
+    bind_context_once();
     static EncodeTiledFn fn = nullptr;
     if (!fn) {
         void* p = nullptr;

@@ -51,19 +51,66 @@ def _need_cuda(t: torch.Tensor):
 # ------------------------------------------------------------------------------------------------
 # graphs
 # ------------------------------------------------------------------------------------------------
+GRID_SEARCH_MIN_PAIRS = 1 << 22      # n * m above which the cell-binned search replaces the O(n m) sweep (None cap only)
+
+
+def _grid_geometry(data, radius):
+    """Uniform grid over the bounding box of the data points: pitch >= 1.001 r, about two points per cell, at most 2^22
+    cells.  One small device -> host read (the box); the graph build reads E back anyway."""
+    d = data.shape[-1]
+    flat = data.reshape(-1, d)
+    box = torch.stack([flat.amin(0), flat.amax(0)]).cpu()
+    lo, hi = box[0].tolist(), box[1].tolist()
+    n = data.shape[-2]
+    ext = [max(h_ - l_, 0.0) for l_, h_ in zip(lo, hi)]
+    vol = 1.0
+    for e in ext:
+        vol *= max(e, 1e-12)
+    h = max(1.001 * float(radius), (2.0 * vol / max(n, 1)) ** (1.0 / d))
+    while True:
+        g = [int(e / h) + 1 for e in ext]
+        total = 1
+        for v in g:
+            total *= v
+        if total <= (1 << 22):
+            break
+        h *= 1.26
+    return lo + [0.0] * (3 - d), h, g + [1] * (3 - d)
+
+
 def radius_csr(data: torch.Tensor, queries: torch.Tensor, radius: float, inclusive: bool = True,
-               max_num_neighbors: Optional[int] = None) -> Dict[str, torch.Tensor]:
+               max_num_neighbors: Optional[int] = None, method: str = "auto") -> Dict[str, torch.Tensor]:
     """Fixed-radius graph in the reference's CSR container (neighbor_search.py:65-106).
-    data [n,d] (or [S,n,d]), queries [m,d] (or [S,m,d]); a batched side yields a list of S dicts."""
+    data [n,d] (or [S,n,d]), queries [m,d] (or [S,m,d]); a batched side yields a list of S dicts.
+    method: 'sweep' (O(n m) warp sweep), 'grid' (cell-binned), 'auto' (grid for large problems without a neighbour cap);
+    both produce the same bit-exact graph."""
     _need_cuda(data)
     data, queries = _c(data), _c(queries)
     db, qb = data.ndim == 3, queries.ndim == 3
     S = data.shape[0] if db else (queries.shape[0] if qb else 1)
     n, m, d = data.shape[-2], queries.shape[-2], data.shape[-1]
     cap = 0 if max_num_neighbors is None else int(max_num_neighbors)
+    if method not in ("auto", "sweep", "grid"):
+        raise ValueError(f"unknown radius search method {method!r}")
+    if method == "grid" and cap:
+        raise ValueError("the cell-binned search returns all neighbours (max_num_neighbors must be None)")
+    use_grid = n > 0 and m > 0 and (method == "grid" or (method == "auto" and cap == 0 and n * m >= GRID_SEARCH_MIN_PAIRS))
     splits = torch.empty((S, m + 1), dtype=torch.int64, device=data.device)
-    call("gaot_radius_count", ptr(data), n, ptr(queries), m, d, float(radius), int(inclusive), cap, S, int(db), int(qb),
-         ptr(splits))
+    if use_grid:
+        lo, h, g = _grid_geometry(data, radius)
+        ncell = g[0] * g[1] * g[2]
+        Sd = S if db else 1
+        i32 = dict(dtype=torch.int32, device=data.device)
+        cell_start, srt = torch.empty((Sd, ncell + 1), **i32), torch.empty((Sd, n), **i32)
+        cell_ws, cursor_ws = torch.empty((Sd, n), **i32), torch.empty((Sd, ncell), **i32)     # distinct live workspaces
+        call("gaot_grid_bin", ptr(data), n, d, Sd, lo[0], lo[1], lo[2], float(h), g[0], g[1], g[2], ptr(cell_start), ptr(srt),
+             ptr(cell_ws), ptr(cursor_ws))
+        geom = (lo[0], lo[1], lo[2], float(h), g[0], g[1], g[2], ptr(cell_start), ptr(srt))
+        call("gaot_radius_count_grid", ptr(data), n, ptr(queries), m, d, float(radius), int(inclusive), S, int(db), int(qb), *geom,
+             ptr(splits))
+    else:
+        call("gaot_radius_count", ptr(data), n, ptr(queries), m, d, float(radius), int(inclusive), cap, S, int(db), int(qb),
+             ptr(splits))
     counts = splits[:, m].clone()
     offs = torch.zeros(S, dtype=torch.int64, device=data.device)
     if S > 1:
@@ -72,8 +119,12 @@ def radius_csr(data: torch.Tensor, queries: torch.Tensor, radius: float, inclusi
     total = int(counts_h.sum())
     index = torch.empty(max(total, 1), dtype=torch.int64, device=data.device)[:total]
     if total > 0:
-        call("gaot_radius_fill", ptr(data), n, ptr(queries), m, d, float(radius), int(inclusive), cap, S, int(db), int(qb),
-             ptr(splits), ptr(offs), ptr(index))
+        if use_grid:
+            call("gaot_radius_fill_grid", ptr(data), n, ptr(queries), m, d, float(radius), int(inclusive), S, int(db), int(qb), *geom,
+                 ptr(splits), ptr(offs), ptr(index))
+        else:
+            call("gaot_radius_fill", ptr(data), n, ptr(queries), m, d, float(radius), int(inclusive), cap, S, int(db), int(qb),
+                 ptr(splits), ptr(offs), ptr(index))
     out, o = [], 0
     for s in range(S):
         e = int(counts_h[s])

@@ -58,6 +58,24 @@ int gaot_radius_fill(const float* data, int64_t n, const float* queries, int64_t
                      const int64_t* row_splits, const int64_t* index_offsets,
                      int64_t* index, void* stream);
 
+/* Cell-binned form of the two entry points above: the SAME graph (same fp32 distance arithmetic, rows in ascending j) in
+ * O(points of the 3^d cells around a query) instead of O(n) per query; for max_nbrs = 0 (all neighbours) only.
+ * Replaces the reference's pure-Python `grid` back-end (neighbor_search.py:183-272).
+ * gaot_grid_bin: counting sort of the data points [batch, n, d] by cell of a uniform grid with origin lo, pitch
+ * h >= 1.0005 * radius and g = (gx, gy, gz) cells (gz = 1 for d = 2): cell_start [batch, ncell + 1], sorted [batch, n]
+ * (point ids, ascending inside a cell); cell_ws [batch, n] and cursor_ws [batch, ncell] are int32 workspaces.
+ * count / fill: as gaot_radius_count / gaot_radius_fill; data_batched = 0 shares one binned point set between the samples. */
+int gaot_grid_bin(const float* data, int64_t n, int d, int64_t batch, float lox, float loy, float loz, float h, int gx,
+                  int gy, int gz, int* cell_start, int* sorted, int* cell_ws, int* cursor_ws, void* stream);
+int gaot_radius_count_grid(const float* data, int64_t n, const float* queries, int64_t m, int d, float radius, int inclusive,
+                           int64_t batch, int data_batched, int queries_batched, float lox, float loy, float loz, float h,
+                           int gx, int gy, int gz, const int* cell_start, const int* sorted, int64_t* row_splits,
+                           void* stream);
+int gaot_radius_fill_grid(const float* data, int64_t n, const float* queries, int64_t m, int d, float radius, int inclusive,
+                          int64_t batch, int data_batched, int queries_batched, float lox, float loy, float loz, float h,
+                          int gx, int gy, int gz, const int* cell_start, const int* sorted, const int64_t* row_splits,
+                          const int64_t* index_offsets, int64_t* index, void* stream);
+
 /* edge_row[e] = the CSR row of edge e (the reference materialises the same thing with
  * torch.repeat_interleave, src/model/layers/agno.py:206-207). */
 int gaot_csr_edge_rows(const int64_t* row_splits, int64_t m, int64_t* edge_row, void* stream);

@@ -70,6 +70,21 @@ def gaot_radius_fill(data, n, queries, m, d, radius, inclusive, cap, batch, db, 
         _arr(index + 8 * int(offs[b]), (e,), np.int64)[:] = g["neighbors_index"].numpy()
 
 
+def gaot_grid_bin(data, n, d, batch, lox, loy, loz, h, gx, gy, gz, cell_start, srt, cell_ws, cursor_ws):
+    pass        # the emulated search below does not need the cell structure
+
+
+def gaot_radius_count_grid(data, n, queries, m, d, radius, inclusive, batch, db, qb, lox, loy, loz, h, gx, gy, gz, cell_start, srt,
+                           row_splits):
+    assert h >= radius * 1.0005
+    gaot_radius_count(data, n, queries, m, d, radius, inclusive, 0, batch, db, qb, row_splits)
+
+
+def gaot_radius_fill_grid(data, n, queries, m, d, radius, inclusive, batch, db, qb, lox, loy, loz, h, gx, gy, gz, cell_start, srt,
+                          row_splits, offsets, index):
+    gaot_radius_fill(data, n, queries, m, d, radius, inclusive, 0, batch, db, qb, row_splits, offsets, index)
+
+
 def gaot_csr_edge_rows(row_splits, m, edge_row):
     rs = _arr(row_splits, (m + 1,), np.int64)
     _arr(edge_row, (int(rs[-1]),), np.int64)[:] = np.repeat(np.arange(m, dtype=np.int64), np.diff(rs))

@@ -27,6 +27,41 @@ def test_radius_csr_bit_exact_vs_reference_golden(name):
     assert np.array_equal(out["neighbors_row_splits"].cpu().numpy(), g[f"{name}.splits"].astype(np.int64))
 
 
+@pytest.mark.parametrize("name", cases.NBR_CASES)
+def test_radius_csr_grid_bit_exact_vs_reference_golden(name):
+    """The cell-binned search against the reference `native` goldens: exact-boundary lattices, duplicates, empty rows,
+    queries far outside the data box."""
+    ops = _ops()
+    g = load_golden("neighbors")
+    data, q, r = cases.nbr_case(name)
+    out = ops.radius_csr(data.to(DEV), q.to(DEV), r, method="grid")
+    assert np.array_equal(out["neighbors_index"].cpu().numpy(), g[f"{name}.index"].astype(np.int64))
+    assert np.array_equal(out["neighbors_row_splits"].cpu().numpy(), g[f"{name}.splits"].astype(np.int64))
+    strict = ops.radius_csr(data.to(DEV), q.to(DEV), r, inclusive=False, method="grid")
+    want = orc.radius_csr(data, q, r, inclusive=False)
+    assert torch.equal(strict["neighbors_index"].cpu(), want["neighbors_index"])
+    with pytest.raises(ValueError):
+        ops.radius_csr(data.to(DEV), q.to(DEV), r, max_num_neighbors=4, method="grid")
+
+
+@pytest.mark.parametrize("d,n,m,r", [(2, 30000, 7000, 0.02), (3, 40000, 5000, 0.09), (2, 5000, 20000, 0.05), (3, 300, 300, 1.5)])
+def test_radius_csr_grid_equals_sweep(d, n, m, r):
+    """Same bit-exact graph from both searches on larger random clouds (uniform data, clustered queries; a radius larger
+    than the box in the last case), incl. the batched forms the vx-mode graph builder uses."""
+    ops = _ops()
+    data = cases.uniform_points(n, d, 91).to(DEV)
+    q = cases.clustered_points(m, d, 92).to(DEV)
+    a, b = ops.radius_csr(data, q, r, method="sweep"), ops.radius_csr(data, q, r, method="grid")
+    assert torch.equal(a["neighbors_row_splits"], b["neighbors_row_splits"]) and torch.equal(a["neighbors_index"], b["neighbors_index"])
+    assert int(a["neighbors_index"].numel()) > 0
+    xs = torch.stack([cases.clustered_points(min(n, 4000), d, 93 + s) for s in range(3)]).to(DEV)
+    lat = cases.uniform_points(900, d, 97).to(DEV)
+    for dd, qq in ((xs, lat), (lat, xs)):
+        sa, sb = ops.radius_csr(dd, qq, r, method="sweep"), ops.radius_csr(dd, qq, r, method="grid")
+        for ga, gb in zip(sa, sb):
+            assert torch.equal(ga["neighbors_row_splits"], gb["neighbors_row_splits"]) and torch.equal(ga["neighbors_index"], gb["neighbors_index"])
+
+
 @pytest.mark.parametrize("name", ["lattice2d", "rand3d"])
 def test_radius_csr_torch_cluster_semantics(name):
     ops = _ops()
