@@ -19,6 +19,7 @@ class AGNO(nn.Module):
                  transform_type="linear", use_attn=None, attention_type="cosine", coord_dim=None, use_torch_scatter=True):
         super().__init__()
         self.transform_type = transform_type
+        self.fuse_edge_mlp = True                        # bf16 mode: one fused kernel for the edge weights where the shape allows
         self.use_torch_scatter = use_torch_scatter
         self.use_attn = use_attn
         self.attention_type = attention_type
@@ -45,6 +46,23 @@ class AGNO(nn.Module):
     def edge_weights(self, y, x, plan: ops.GraphPlan):
         """w [E, C]: kernel MLP on [y_j, x_m] (agno.py:229-242) times the attention weight (agno.py:218-224, 250)
         or 1/deg when the reduce is `mean` (agno.py:264)."""
+        fcs = self.channel_mlp.fcs
+        learned_alpha = self.use_attn and self.attention_type == "dot_product"
+        if (self.fuse_edge_mlp and ops.get_precision() == "bf16" and not learned_alpha and y.shape[1] == x.shape[1]
+                and ops.edge_mlp_supported(fcs[0].weight.shape[1], fcs[0].weight.shape[0], len(fcs) - 2, fcs[-1].weight.shape[0])
+                and all(tuple(fc.weight.shape) == (64, 64) for fc in fcs[1:-1]) and fcs[-1].weight.shape[1] == 64
+                and fcs[0].weight.shape[1] == 2 * y.shape[1]):
+            # bf16 mode: gather, kernel MLP and the attention-weight product in ONE tensor-core kernel (forward and backward);
+            # the attention weights are parameter free here (cosine similarity of coordinates, or 1 / degree)
+            if self.use_attn:
+                alpha = ops.edge_cosine_softmax(y, x, self.coord_dim, plan)
+            else:
+                deg = (plan.splits[1:] - plan.splits[:-1]).clamp(min=1).to(torch.float32)
+                alpha = (1.0 / deg)[plan.edge_row]
+            params = []
+            for fc in fcs:
+                params += [fc.weight, fc.bias]
+            return ops.edge_mlp(y, x, plan, alpha, params)
         kappa = self.channel_mlp(ops.edge_inputs(y, x, plan))
         if self.use_attn and self.attention_type == "dot_product":
             # the reference projects the gathered per-edge coordinates (agno.py:214-216); projecting every node once and

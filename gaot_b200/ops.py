@@ -805,6 +805,58 @@ def edge_dot_softmax(q, k, plan: GraphPlan, scale: float):
     return _EdgeDotSoftmax.apply(q, k, plan, scale)
 
 
+def edge_mlp_supported(kin: int, hidden: int, n_hidden: int, C: int) -> bool:
+    """Shapes the fused edge-weight kernels are instantiated for (== gaot_edge_mlp_supported)."""
+    return kin in (4, 6, 32, 48) and hidden == 64 and n_hidden in (1, 2) and 16 <= C <= 64 and C % 16 == 0
+
+
+class _EdgeMlp(torch.autograd.Function):
+    """w[e,:] = alpha[e] * MLP(cat[y[index[e]], x[row(e)]]) in one kernel, forward and backward (gaot_edge_mlp_{fwd,bwd});
+    params = (W1, b1, Wh0, bh0[, Wh1, bh1], Wo, bo).  alpha and the coordinates carry no gradient."""
+
+    @staticmethod
+    def forward(ctx, y, x, plan, alpha, *params):
+        _need_cuda(y)
+        y, x = _c(y), _c(x)
+        params = [_c(p) for p in params]
+        n_hidden = len(params) // 2 - 2
+        W1, b1, Wo, bo = params[0], params[1], params[-2], params[-1]
+        hid = params[2:-2]
+        kc = W1.shape[1] // 2
+        C = Wo.shape[0]
+        if not edge_mlp_supported(W1.shape[1], W1.shape[0], n_hidden, C) or y.shape[1] < kc or x.shape[1] < kc:
+            raise ValueError("edge_mlp: shape not instantiated in the fused kernels")
+        alpha_c = _c(alpha) if alpha is not None else None
+        w = torch.empty((plan.E, C), dtype=torch.float32, device=y.device)
+        ph = [ptr(t) for t in hid] + [0, 0] * (2 - n_hidden)
+        if plan.E > 0:
+            call("gaot_edge_mlp_fwd", ptr(y), y.shape[1], ptr(x), x.shape[1], kc, ptr(plan.index), ptr(plan.edge_row), plan.E,
+                 ptr(alpha_c), ptr(W1), ptr(b1), ph[0], ph[1], ph[2], ph[3], n_hidden, ptr(Wo), ptr(bo), C, ptr(w))
+        ctx.save_for_backward(y, x, alpha_c if alpha_c is not None else y.new_zeros(0), *params)
+        ctx.plan, ctx.has_alpha, ctx.n_hidden, ctx.kc, ctx.C = plan, alpha_c is not None, n_hidden, kc, C
+        return w
+
+    @staticmethod
+    def backward(ctx, dw):
+        y, x, alpha, *params = ctx.saved_tensors
+        plan, n_hidden, kc, C = ctx.plan, ctx.n_hidden, ctx.kc, ctx.C
+        dw = _c(dw)
+        W1, b1, Wo, bo = params[0], params[1], params[-2], params[-1]
+        hid = params[2:-2]
+        grads = [torch.empty_like(p) for p in params]
+        ph = [ptr(t) for t in hid] + [0, 0] * (2 - n_hidden)
+        gh = [ptr(t) for t in grads[2:-2]] + [0, 0] * (2 - n_hidden)
+        call("gaot_edge_mlp_bwd", ptr(y), y.shape[1], ptr(x), x.shape[1], kc, ptr(plan.index), ptr(plan.edge_row), plan.E,
+             ptr(alpha) if ctx.has_alpha else 0, ptr(W1), ptr(b1), ph[0], ph[1], ph[2], ph[3], n_hidden, ptr(Wo), ptr(bo), C,
+             ptr(dw), ptr(grads[0]), ptr(grads[1]), gh[0], gh[1], gh[2], gh[3], ptr(grads[-2]), ptr(grads[-1]))
+        return (None, None, None, None, *grads)
+
+
+def edge_mlp(y, x, plan: GraphPlan, alpha, params):
+    """Fused edge weights (see _EdgeMlp); `params` = [W1, b1, Wh0, bh0, (Wh1, bh1,) Wo, bo]."""
+    return _EdgeMlp.apply(y, x, plan, alpha, *params)
+
+
 class _ScaleRows(torch.autograd.Function):
     @staticmethod
     def forward(ctx, k, alpha):

@@ -327,6 +327,30 @@ int gaot_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_
                     float lr, float beta1, float beta2, float eps, float weight_decay,
                     int64_t step, float grad_scale, void* stream);
 
+/* Fused edge-weight operator of AGNO on the tensor cores (bf16 mode):
+ *     w[e, :] = alpha[e] * MLP(cat[y[index[e], :kc], x[edge_row[e], :kc]]),
+ *     MLP = Linear(2kc -> 64) GELU [Linear(64 -> 64) GELU] x n_hidden, Linear(64 -> C)     (exact-erf GELU)
+ * replacing the gather / repeat of the edge coordinates (agno.py:206-207), the kernel MLP (agno.py:229-242 with
+ * LinearChannelMLP, mlp.py:329-337) and the attention-weight product (agno.py:250), forward and backward, without ever
+ * writing an [E, 64] activation or gradient to memory: one CTA keeps a 128-edge tile's whole chain in shared memory / TMEM,
+ * the hidden and output layers run as tcgen05.mma on bf16 operands (first layer on the FP32 pipe from fp32 coordinates),
+ * and the backward accumulates dW_l = delta_l^T h_{l-1} on the tensor cores into TMEM for the CTA's lifetime.
+ * y [*, dy], x [*, dx] fp32 coordinate (or position-encoding) rows; index / edge_row [E]; alpha [E] (nullable);
+ * W1 [64, 2kc], Wh0 / Wh1 [64, 64] (Wh1 unused when n_hidden == 1), Wo [C, 64] and their biases, all fp32;
+ * gaot_edge_mlp_supported(2kc, H, n_hidden, C) tells whether the shape is instantiated (H = 64, C % 16 == 0, C <= 64,
+ * 2kc in {4, 6, 32, 48}, n_hidden in {1, 2}).  The backward ZEROES and then reduces into dW1 ... dbo; alpha and the
+ * coordinates receive no gradient (cosine / mean weights are parameter free). */
+int gaot_edge_mlp_supported(int64_t kin, int64_t H, int64_t n_hidden, int64_t C);
+int gaot_edge_mlp_fwd(const float* y, int64_t dy, const float* x, int64_t dx, int64_t kc, const int64_t* index,
+                      const int64_t* edge_row, int64_t E, const float* alpha, const float* W1, const float* b1,
+                      const float* Wh0, const float* bh0, const float* Wh1, const float* bh1, int64_t n_hidden,
+                      const float* Wo, const float* bo, int64_t C, float* w, void* stream);
+int gaot_edge_mlp_bwd(const float* y, int64_t dy, const float* x, int64_t dx, int64_t kc, const int64_t* index,
+                      const int64_t* edge_row, int64_t E, const float* alpha, const float* W1, const float* b1,
+                      const float* Wh0, const float* bh0, const float* Wh1, const float* bh1, int64_t n_hidden,
+                      const float* Wo, const float* bo, int64_t C, const float* dw, float* dW1, float* db1, float* dWh0,
+                      float* dbh0, float* dWh1, float* dbh1, float* dWo, float* dbo, void* stream);
+
 /* Rollout update rule of GAOT._process_autoregressive_prediction (src/model/gaot.py:436-476) and the state carry of
  * src/model/gaot.py:431-434.  mode 0 output, 1 residual, 2 time_der.  All tensors [rows, C]; stats are per channel [C].
  * u_phys = the de-normalised prediction (the value the reference appends and returns); u_next (optional) =

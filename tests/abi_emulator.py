@@ -262,6 +262,41 @@ def gaot_agno_dot_bwd_t(gr, f, u, index, row_splits, ts, tr, tp, df, du, B, Ns, 
         _t(du, (Cout, E, C))[:] = D.float()
 
 
+def _edge_mlp_ref(y, dy, x, dx, kc, index, edge_row, E, alpha, W1, b1, Wh0, bh0, Wh1, bh1, n_hidden, Wo, bo, C, grad=False):
+    idx, row = _arr(index, (E,), np.int64), _arr(edge_row, (E,), np.int64)
+    n_y, n_x = int(idx.max()) + 1, int(row.max()) + 1
+    z = torch.cat([_t(y, (n_y, dy))[idx][:, :kc], _t(x, (n_x, dx))[row][:, :kc]], 1).double()
+    ps = [_t(W1, (64, 2 * kc)), _t(b1, (64,)), _t(Wh0, (64, 64)), _t(bh0, (64,))]
+    if n_hidden == 2:
+        ps += [_t(Wh1, (64, 64)), _t(bh1, (64,))]
+    ps += [_t(Wo, (C, 64)), _t(bo, (C,))]
+    ps = [p.double().requires_grad_(grad) for p in ps]
+    h = z
+    for i in range(0, len(ps) - 2, 2):
+        h = torch.nn.functional.gelu(h @ ps[i].T + ps[i + 1])
+    k = h @ ps[-2].T + ps[-1]
+    a = _t(alpha, (E,)).double() if alpha else torch.ones(E, dtype=torch.float64)
+    return k * a[:, None], ps
+
+
+def gaot_edge_mlp_fwd(y, dy, x, dx, kc, index, edge_row, E, alpha, W1, b1, Wh0, bh0, Wh1, bh1, n_hidden, Wo, bo, C, w):
+    out, _ = _edge_mlp_ref(y, dy, x, dx, kc, index, edge_row, E, alpha, W1, b1, Wh0, bh0, Wh1, bh1, n_hidden, Wo, bo, C)
+    _t(w, (E, C))[:] = out.float()
+
+
+def gaot_edge_mlp_bwd(y, dy, x, dx, kc, index, edge_row, E, alpha, W1, b1, Wh0, bh0, Wh1, bh1, n_hidden, Wo, bo, C, dw, dW1, db1,
+                      dWh0, dbh0, dWh1, dbh1, dWo, dbo):
+    with torch.enable_grad():
+        out, ps = _edge_mlp_ref(y, dy, x, dx, kc, index, edge_row, E, alpha, W1, b1, Wh0, bh0, Wh1, bh1, n_hidden, Wo, bo, C, grad=True)
+        out.backward(_t(dw, (E, C)).double())
+    dst = [(dW1, (64, 2 * kc)), (db1, (64,)), (dWh0, (64, 64)), (dbh0, (64,))]
+    if n_hidden == 2:
+        dst += [(dWh1, (64, 64)), (dbh1, (64,))]
+    dst += [(dWo, (C, 64)), (dbo, (C,))]
+    for (p_, shp), t in zip(dst, ps):
+        _t(p_, shp)[:] = t.grad.float()
+
+
 def gaot_cond_affine_fwd(x, scale, bias, y, B, T, D):
     _arr(y, (B, T, D))[:] = _arr(x, (B, T, D)) * _arr(scale, (B, D))[:, None, :] + _arr(bias, (B, D))[:, None, :]
 

@@ -390,3 +390,75 @@ def test_rollout_bf16_mode_vs_reference_golden(use_graph):
     want = torch.from_numpy(g["pred.time_der"])
     for i in range(want.shape[1]):
         assert rel_l2(got[:, i], want[:, i]) < BF16_FWD_TOL, i
+
+
+# ------------------------------------------------------------------------------------------------
+# fused edge-weight kernels (gather + kernel MLP + attention weight, forward and backward, bf16 tensor cores)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,n_hidden,C,with_alpha", [("rand2d", 2, 64, True), ("rand3d", 1, 48, True), ("dec2d", 2, 16, False),
+                                                        ("lattice2d", 1, 32, True), ("empty", 2, 64, True)])
+def test_edge_mlp_fused_vs_fp64(name, n_hidden, C, with_alpha):
+    """gaot_edge_mlp_{fwd,bwd} against an fp64 autograd restatement of agno.py:206-207, 229-242, 250.  Tolerances are those of
+    the bf16 mode: hidden activations and hidden / output weights are rounded to bf16 (8 mantissa bits) at every MMA input,
+    the first layer and all accumulations are fp32."""
+    from oracle import gaot_oracle as orc
+    from gaot_b200 import ops
+    data, q, r = cases.nbr_case(name)
+    g = orc.radius_csr(data, q, r)
+    idx, rs = g["neighbors_index"], g["neighbors_row_splits"]
+    kc, E = data.shape[1], int(idx.numel())
+    plan = ops.GraphPlan(idx.to(DEV), rs.to(DEV), data.shape[0])
+    gen = torch.Generator().manual_seed(11)
+    dims = [2 * kc] + [64] * (n_hidden + 1) + [C]
+    params = []
+    for a, b in zip(dims[:-1], dims[1:]):
+        params += [torch.randn(b, a, generator=gen) / a ** 0.5, 0.1 * torch.randn(b, generator=gen)]
+    alpha = torch.rand(E, generator=gen) if with_alpha else None
+    gw = torch.randn(E, C, generator=gen)
+    pd = [p.clone().to(DEV).requires_grad_(True) for p in params]
+    w = ops.edge_mlp(data.to(DEV), q.to(DEV), plan, alpha.to(DEV) if alpha is not None else None, pd)
+    assert w.shape == (E, C)
+    if E == 0:
+        return
+    w.backward(gw.to(DEV))
+    pr = [p.clone().double().requires_grad_(True) for p in params]
+    row = torch.repeat_interleave(torch.arange(q.shape[0]), rs[1:] - rs[:-1])
+    h = torch.cat([data[idx], q[row]], 1).double()
+    for i in range(0, len(pr) - 2, 2):
+        h = torch.nn.functional.gelu(h @ pr[i].T + pr[i + 1])
+    want = h @ pr[-2].T + pr[-1]
+    if alpha is not None:
+        want = want * alpha.double()[:, None]
+    want.backward(gw.double())
+    assert rel_l2(w, want) < 1e-2
+    mine = torch.cat([p.grad.flatten().double().cpu() for p in pd])
+    ref = torch.cat([p.grad.flatten() for p in pr])
+    assert rel_l2(mine, ref) < 2e-2
+    for a, b in zip(pd, pr):
+        assert rel_l2(a.grad, b.grad) < 4e-2
+
+
+def test_edge_mlp_fused_many_tiles_matches_unfused_bf16_chain():
+    """E = 31 k edges (245 tiles, persistent CTAs take several tiles each: TMEM weight-gradient accumulators live across tiles)
+    against the unfused bf16-mode chain on the same graph."""
+    from gaot_b200 import ops
+    from gaot_b200.model.layers.agno import AGNO
+    x = cases.uniform_points(9216, 2, 0).to(DEV)
+    lat = cases.latent_grid((64, 64)).to(DEV)
+    plan = ops.graph_plan(ops.radius_csr(x, lat, 0.033), 9216)
+    torch.manual_seed(3)
+    agno = AGNO(channel_mlp_layers=[4, 64, 64, 64, 64], use_attn=True, attention_type="cosine", coord_dim=2).to(DEV)
+    gw = cases.normal((plan.E, 64), 9).to(DEV)
+    res = {}
+    ops.set_precision("bf16")
+    try:
+        for fused in (True, False):
+            agno.fuse_edge_mlp = fused
+            agno.zero_grad()
+            w = agno.edge_weights(x, lat, plan)
+            w.backward(gw)
+            res[fused] = (w.detach().clone(), torch.cat([p.grad.flatten() for p in agno.parameters()]))
+    finally:
+        ops.set_precision("fp32")
+    assert rel_l2(res[True][0], res[False][0]) < 1e-2
+    assert rel_l2(res[True][1], res[False][1]) < 2e-2

@@ -231,6 +231,36 @@ def test_edge_drop_inside_the_encoder_training_vs_eval():
         assert rel_l2(t1, g["out"]) > 1e-3
 
 
+@pytest.mark.parametrize("n_hidden,kc,C,attn", [(2, 2, 64, True), (1, 3, 48, False)])
+def test_fused_edge_mlp_wiring_equals_unfused(n_hidden, kc, C, attn):
+    """AGNO.edge_weights in bf16 mode takes the fused edge-weight entry points (emulated in fp64 here) when the kernel MLP has
+    the instantiated shape; values and parameter gradients equal the unfused chain of the fp32 mode."""
+    from gaot_b200 import ops
+    from gaot_b200.model.layers.agno import AGNO
+    data, q, r = cases.nbr_case("rand2d" if kc == 2 else "rand3d")
+    g = orc.radius_csr(data, q, r)
+    with abi_emulator.install() as calls:
+        torch.manual_seed(0)
+        agno = AGNO(channel_mlp_layers=[2 * kc] + [64] * (n_hidden + 1) + [C], use_attn=attn, attention_type="cosine", coord_dim=kc)
+        plan = ops.GraphPlan(g["neighbors_index"], g["neighbors_row_splits"], data.shape[0])
+        gw = cases.normal((plan.E, C), 5)
+        res = {}
+        for mode in ("bf16", "ffma"):
+            with _precision(mode):
+                agno.zero_grad()
+                w = agno.edge_weights(data, q, plan)
+                w.backward(gw)
+                res[mode] = (w.detach().clone(), [p.grad.clone() for p in agno.parameters()])
+        assert "gaot_edge_mlp_fwd" in calls and "gaot_edge_mlp_bwd" in calls
+    assert rel_l2(res["bf16"][0], res["ffma"][0]) < 1e-5
+    for a, b in zip(res["bf16"][1], res["ffma"][1]):
+        assert rel_l2(a, b) < 1e-5
+    assert ops.edge_mlp_supported(4, 64, 2, 64) and not ops.edge_mlp_supported(4, 16, 2, 16) and not ops.edge_mlp_supported(4, 64, 3, 64)
+    from gaot_b200 import _lib
+    for args in ((4, 64, 2, 64), (6, 64, 1, 48), (4, 16, 2, 16), (5, 64, 2, 64), (4, 64, 2, 24)):
+        assert bool(_lib.lib().gaot_edge_mlp_supported(*args)) == ops.edge_mlp_supported(*args)
+
+
 def test_train_step_flat_buffers_and_adamw():
     name = "tiny2d"
     c = cases.CASES[name]
