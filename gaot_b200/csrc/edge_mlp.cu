@@ -5,7 +5,7 @@
 // [E, 2d] edge inputs and one [E, H] activation per layer (plus their gradients); unfused, that was ~30 passes over
 // [E, 64] tensors per step and the largest part of the vx-mode (E = 3.6 M) and 3-D (E = 1.4 M) steps.
 //
-// Here a CTA owns 128-edge tiles (one edge = one TMEM lane = one thread) and keeps the whole chain on chip:
+// Here a CTA owns 128-edge tiles (one edge = one TMEM lane = two threads, 32 columns each) and keeps the whole chain on chip:
 //   layer 1 (K = 2kc <= 64, coordinates) on the FP32 pipe from registers (fp32, as everywhere else);
 //   hidden / output layers as tcgen05.mma M=128, N=H|C, K=H with the bf16 activation tile written by the threads as a
 //   K-major SWIZZLE_128B operand and the bf16 weights resident in shared memory for the CTA's lifetime;
@@ -25,7 +25,8 @@ namespace {
 
 constexpr int EM_H = 64;                // hidden width = bf16 elements per 128-byte swizzle row
 constexpr int EM_TILE = 128;            // edges per tile = TMEM lanes
-constexpr int EM_THREADS = 128;
+constexpr int EM_THREADS = 256;          // two threads per edge row: each owns 32 of the 64 columns (warps w and w + 4 share a TMEM lane quadrant)
+constexpr int EM_HW = 32;                // columns per thread
 constexpr int EM_MAXHID = 2;            // H x H layers
 constexpr int EM_MAXKIN = 64;
 constexpr int EM_WBYTES = EM_H * EM_H * 2;          // one bf16 [64 rows x 64] weight tile (8 KB)
@@ -95,11 +96,32 @@ __device__ __forceinline__ float2 unpack_bf16(uint32_t v) {
 __device__ __forceinline__ uint32_t sw128_off(int r, int chunk) {
     return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((chunk ^ (r & 7)) << 4));
 }
-// GELU'(x) = Phi(x) + x phi(x)
+// GELU(x) = x Phi(x) and GELU'(x) = Phi(x) + x phi(x) from ONE exponential: erf by Abramowitz-Stegun 7.1.26
+// (|error| < 1.5e-7, far below the bf16 rounding of every value these kernels hand to an MMA):
+//   erf(u) = 1 - (a1 t + ... + a5 t^5) exp(-u^2),  t = 1 / (1 + p u),  u = |x| / sqrt(2),  exp(-u^2) = exp(-x^2 / 2) = sqrt(2 pi) phi(x)
+// one MUFU.RCP + one MUFU.EX2 + ~12 FMA-pipe instructions, branch free (erff is ~2x that and branches on |x|).
+__device__ __forceinline__ float ex2f(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ void gelu_both(float x, float& y, float& dy) {
-    const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
+    const float u = fabsf(x) * 0.70710678118654752f;
+    const float t = __frcp_rn(fmaf(0.3275911f, u, 1.0f));
+    const float ex = ex2f(x * x * -0.72134752044448170f);           // exp(-x^2 / 2)
+    float p = fmaf(1.061405429f, t, -1.453152027f);
+    p = fmaf(p, t, 1.421413741f);
+    p = fmaf(p, t, -0.284496736f);
+    p = fmaf(p, t, 0.254829592f);
+    const float tail = 0.5f * p * t * ex;                            // (1 - erf(u)) / 2
+    const float cdf = x >= 0.f ? 1.0f - tail : tail;
     y = x * cdf;
-    dy = cdf + x * (0.39894228040143268f * __expf(-0.5f * x * x));
+    dy = fmaf(x * 0.39894228040143268f, ex, cdf);
+}
+__device__ __forceinline__ float gelu_fast(float x) {
+    float y, dy;
+    gelu_both(x, y, dy);
+    return y;
 }
 
 struct EdgeMlpArgs {
@@ -132,22 +154,22 @@ __device__ __forceinline__ void stage_weight(uint8_t* tile, const float* __restr
     }
 }
 
-// one thread's activation row (64 fp32 values) -> bf16 row r of a K-major SWIZZLE_128B tile
-__device__ __forceinline__ void store_row_bf16(uint32_t tile, int r, const float (&v)[EM_H]) {
+// one thread's half row (32 fp32 values, columns 32*hf ..) -> bf16 row r of a K-major SWIZZLE_128B tile
+__device__ __forceinline__ void store_row_bf16(uint32_t tile, int r, int hf, const float (&v)[EM_HW]) {
 #pragma unroll
-    for (int c = 0; c < 8; ++c)
-        sts_u4(tile + sw128_off(r, c), pack_bf16(v[8 * c], v[8 * c + 1]), pack_bf16(v[8 * c + 2], v[8 * c + 3]),
+    for (int c = 0; c < 4; ++c)
+        sts_u4(tile + sw128_off(r, 4 * hf + c), pack_bf16(v[8 * c], v[8 * c + 1]), pack_bf16(v[8 * c + 2], v[8 * c + 3]),
                pack_bf16(v[8 * c + 4], v[8 * c + 5]), pack_bf16(v[8 * c + 6], v[8 * c + 7]));
 }
 
-// layer 1 on the FP32 pipe: z[o] = b1[o] + sum_i W1[o, i] * z0[i]; W1 / b1 in shared memory (broadcast reads)
+// layer 1 on the FP32 pipe, this thread's 32 outputs: z[o] = b1[o] + sum_i W1[o, i] * z0[i]; W1 / b1 in shared memory
 template <int KIN>
-__device__ __forceinline__ void layer1(const float* sW1, const float* sb1, const float (&z0)[KIN], float (&z)[EM_H]) {
+__device__ __forceinline__ void layer1(const float* sW1, const float* sb1, int hf, const float (&z0)[KIN], float (&z)[EM_HW]) {
 #pragma unroll
-    for (int o = 0; o < EM_H; ++o) {
-        float acc = sb1[o];
+    for (int o = 0; o < EM_HW; ++o) {
+        float acc = sb1[hf * EM_HW + o];
 #pragma unroll
-        for (int i = 0; i < KIN; ++i) acc = fmaf(sW1[o * KIN + i], z0[i], acc);
+        for (int i = 0; i < KIN; ++i) acc = fmaf(sW1[(hf * EM_HW + o) * KIN + i], z0[i], acc);
         z[o] = acc;
     }
 }
@@ -165,7 +187,7 @@ __device__ __forceinline__ void mma_forward(uint32_t tmem_acc, uint32_t a_tile, 
 // forward
 // ---------------------------------------------------------------------------------------------
 template <int KIN>
-__global__ void __launch_bounds__(EM_THREADS, 4)
+__global__ void __launch_bounds__(EM_THREADS, 3)
 edge_mlp_fwd_tc_kernel(const EdgeMlpArgs g) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -176,6 +198,7 @@ edge_mlp_fwd_tc_kernel(const EdgeMlpArgs g) {
     uint64_t* bar = reinterpret_cast<uint64_t*>(sb + (EM_MAXHID + 2) * EM_H);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q = warp & 3, hf = warp >> 2;                          // TMEM lane quadrant, column half
     const int nh = g.n_hidden, C = g.C;
 
     if (threadIdx.x == 0) {
@@ -199,9 +222,9 @@ edge_mlp_fwd_tc_kernel(const EdgeMlpArgs g) {
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *tmem_slot;
-    const uint32_t tacc = tmem + ((uint32_t)(warp * 32) << 16);      // this warp's TMEM lanes
+    const uint32_t tacc = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(hf * EM_HW);   // this thread's lane and column half
     const uint32_t a_tile = smem_u32(sA);
-    const int r = threadIdx.x;                                       // edge row inside the tile
+    const int r = q * 32 + lane;                                     // edge row inside the tile == TMEM lane
     uint32_t phase = 0;
     constexpr int KC = KIN / 2;
 
@@ -209,18 +232,18 @@ edge_mlp_fwd_tc_kernel(const EdgeMlpArgs g) {
     for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
         const int64_t e = t * EM_TILE + r;
         const bool ok = e < g.E;
-        float z0[KIN];
+        float v[EM_HW];
         {
+            float z0[KIN];
             const int64_t j = ok ? __ldg(g.index + e) : 0, m = ok ? __ldg(g.edge_row + e) : 0;
 #pragma unroll
             for (int i = 0; i < KC; ++i) { z0[i] = __ldg(g.y + j * g.dy + i); z0[KC + i] = __ldg(g.x + m * g.dx + i); }
+            layer1<KIN>(sW1, sb, hf, z0, v);
         }
-        float v[EM_H];
-        layer1<KIN>(sW1, sb, z0, v);
 #pragma unroll
-        for (int o = 0; o < EM_H; ++o) v[o] = gelu_erf(v[o]);
+        for (int o = 0; o < EM_HW; ++o) v[o] = gelu_fast(v[o]);
         for (int l = 0; l <= nh; ++l) {
-            store_row_bf16(a_tile, r, v);
+            store_row_bf16(a_tile, r, hf, v);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> async proxy (MMA)
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncthreads();
@@ -231,28 +254,24 @@ edge_mlp_fwd_tc_kernel(const EdgeMlpArgs g) {
             mbar_wait(bar, phase);
             phase ^= 1u;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const float* bl = sb + (1 + l) * EM_H;
+            const float* bl = sb + (1 + l) * EM_H + hf * EM_HW;
+            uint32_t acc[32];
+            tmem_ld32(tacc, acc);
+            tmem_wait_ld();
+            if (l < nh) {
 #pragma unroll
-            for (int hf = 0; hf < 2; ++hf) {                           // 32 accumulator columns at a time (register budget)
-                if (hf == 1 && l == nh && C <= 32) break;
-                uint32_t acc[32];
-                tmem_ld32(tacc + hf * 32, acc);
-                tmem_wait_ld();
-                if (l < nh) {
+                for (int o = 0; o < EM_HW; ++o) v[o] = gelu_fast(__uint_as_float(acc[o]) + bl[o]);
+            } else {
 #pragma unroll
-                    for (int o = 0; o < 32; ++o) v[hf * 32 + o] = gelu_erf(__uint_as_float(acc[o]) + bl[hf * 32 + o]);
-                } else {
-#pragma unroll
-                    for (int o = 0; o < 32; ++o) v[hf * 32 + o] = __uint_as_float(acc[o]) + bl[hf * 32 + o];
-                }
+                for (int o = 0; o < EM_HW; ++o) v[o] = __uint_as_float(acc[o]) + bl[o];
             }
         }
         if (ok) {
             const float al = g.alpha ? __ldg(g.alpha + e) : 1.f;
-            float* dst = g.w + e * C;
+            float* dst = g.w + e * C + hf * EM_HW;
 #pragma unroll
-            for (int o = 0; o < EM_H; o += 4)
-                if (o < C) *reinterpret_cast<float4*>(dst + o) = make_float4(v[o] * al, v[o + 1] * al, v[o + 2] * al, v[o + 3] * al);
+            for (int o = 0; o < EM_HW; o += 4)
+                if (hf * EM_HW + o < C) *reinterpret_cast<float4*>(dst + o) = make_float4(v[o] * al, v[o + 1] * al, v[o + 2] * al, v[o + 3] * al);
         }
         // the next tile's store_row_bf16 overwrites the activation tile: its last reader (the output MMA) has completed
     }
@@ -273,7 +292,7 @@ int launch_fwd(const EdgeMlpArgs& g, cudaStream_t st) {
         done = true;
     }
     const int64_t n_tiles = (g.E + EM_TILE - 1) / EM_TILE;
-    const int64_t cap = (int64_t)gaot_sm_count() * 4;
+    const int64_t cap = (int64_t)gaot_sm_count() * 3;
     edge_mlp_fwd_tc_kernel<KIN><<<(unsigned)(n_tiles < cap ? n_tiles : cap), EM_THREADS, EM_FWD_SMEM, st>>>(g);
     GAOT_RETURN_LAST();
 }
@@ -281,12 +300,12 @@ int launch_fwd(const EdgeMlpArgs& g, cudaStream_t st) {
 // ---------------------------------------------------------------------------------------------
 // backward
 // ---------------------------------------------------------------------------------------------
-// read one bf16 row (64 values) of a SWIZZLE_128B tile back as fp32
-__device__ __forceinline__ void load_row_bf16(uint32_t tile, int r, float (&v)[EM_H]) {
+// read this thread's half of a bf16 row of a SWIZZLE_128B tile back as fp32
+__device__ __forceinline__ void load_row_bf16(uint32_t tile, int r, int hf, float (&v)[EM_HW]) {
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        const uint4 q = lds_u4(tile + sw128_off(r, c));
-        const float2 a = unpack_bf16(q.x), b = unpack_bf16(q.y), cc = unpack_bf16(q.z), d = unpack_bf16(q.w);
+    for (int c = 0; c < 4; ++c) {
+        const uint4 qd = lds_u4(tile + sw128_off(r, 4 * hf + c));
+        const float2 a = unpack_bf16(qd.x), b = unpack_bf16(qd.y), cc = unpack_bf16(qd.z), d = unpack_bf16(qd.w);
         v[8 * c] = a.x; v[8 * c + 1] = a.y; v[8 * c + 2] = b.x; v[8 * c + 3] = b.y;
         v[8 * c + 4] = cc.x; v[8 * c + 5] = cc.y; v[8 * c + 6] = d.x; v[8 * c + 7] = d.y;
     }
@@ -335,6 +354,7 @@ edge_mlp_bwd_tc_kernel(const EdgeMlpArgs g) {
     uint64_t* bar = reinterpret_cast<uint64_t*>(sb + (EM_MAXHID + 2) * EM_H);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q = warp & 3, hf = warp >> 2;                          // TMEM lane quadrant, column half
     const int nh = g.n_hidden, C = g.C;
 
     if (threadIdx.x == 0) {
@@ -358,9 +378,10 @@ edge_mlp_bwd_tc_kernel(const EdgeMlpArgs g) {
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *tmem_slot;
-    const uint32_t tacc = tmem + ((uint32_t)(warp * 32) << 16);      // this warp's TMEM lanes; columns [0,64): activations / g
+    // this thread's TMEM lane and column half; columns [0,64): activations / g, [64,128) ...: weight-gradient accumulators
+    const uint32_t tacc = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(hf * EM_HW);
     const uint32_t s_tile = smem_u32(sS), d_tile = smem_u32(sD);
-    const int r = threadIdx.x;
+    const int r = q * 32 + lane;
     uint32_t phase = 0;
     constexpr int KC = KIN / 2;
     // dW1 | db1 on the FP32 pipe: thread-owned (output o, input i) pairs, i == KIN is the bias (ones column of sZ0)
@@ -394,40 +415,45 @@ edge_mlp_bwd_tc_kernel(const EdgeMlpArgs g) {
             dbacc[slot] += s0 + s1;
         }
     };
+    auto gelu_pair = [&](float (&v)[EM_HW], uint32_t (&gp)[EM_HW / 2]) {   // v -> GELU(v), gp = GELU'(v) packed bf16
+#pragma unroll
+        for (int o = 0; o < EM_HW; o += 2) {
+            float h0, h1, d0, d1;
+            gelu_both(v[o], h0, d0); gelu_both(v[o + 1], h1, d1);
+            v[o] = h0; v[o + 1] = h1;
+            gp[o >> 1] = pack_bf16(d0, d1);
+        }
+    };
 
     const int64_t n_tiles = (g.E + EM_TILE - 1) / EM_TILE;
     bool first_tile = true;
     for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, first_tile = false) {
         const int64_t e = t * EM_TILE + r;
         const bool ok = e < g.E;
-        float v[EM_H];
-        uint32_t gp[EM_H / 2];                                       // GELU'(z_l) of the layer being back-propagated, packed bf16
+        float v[EM_HW];
+        uint32_t gp[EM_HW / 2];                                      // GELU'(z_l) of the layer being back-propagated
         {
             float z0[KIN];
             const int64_t j = ok ? __ldg(g.index + e) : 0, m = ok ? __ldg(g.edge_row + e) : 0;
 #pragma unroll
             for (int i = 0; i < KC; ++i) { z0[i] = __ldg(g.y + j * g.dy + i); z0[KC + i] = __ldg(g.x + m * g.dx + i); }
+            if (hf == 0) {
 #pragma unroll
-            for (int i = 0; i < KIN; ++i) sZ0[r * (KIN + 1) + i] = z0[i];
-            sZ0[r * (KIN + 1) + KIN] = 1.f;
-            layer1<KIN>(sW1, sb, z0, v);
+                for (int i = 0; i < KIN; ++i) sZ0[r * (KIN + 1) + i] = z0[i];
+                sZ0[r * (KIN + 1) + KIN] = 1.f;
+            }
+            layer1<KIN>(sW1, sb, hf, z0, v);
         }
         // ---- forward recompute: z_1 .. z_{nh+1}; z_1..z_nh kept as bf16 tiles, the last one only through GELU' ----
         for (int l = 1; l <= nh + 1; ++l) {
-            if (l <= nh) store_row_bf16(smem_u32(sZ + (l - 1) * EM_ABYTES), r, v);
-            if (l == nh + 1) {
+            if (l <= nh) {
+                store_row_bf16(smem_u32(sZ + (l - 1) * EM_ABYTES), r, hf, v);
 #pragma unroll
-                for (int o = 0; o < EM_H; o += 2) {
-                    float h0, h1, d0, d1;
-                    gelu_both(v[o], h0, d0); gelu_both(v[o + 1], h1, d1);
-                    v[o] = h0; v[o + 1] = h1;
-                    gp[o >> 1] = pack_bf16(d0, d1);
-                }
+                for (int o = 0; o < EM_HW; ++o) v[o] = gelu_fast(v[o]);
             } else {
-#pragma unroll
-                for (int o = 0; o < EM_H; ++o) v[o] = gelu_erf(v[o]);
+                gelu_pair(v, gp);
             }
-            store_row_bf16(s_tile, r, v);
+            store_row_bf16(s_tile, r, hf, v);
             if (l <= nh) {
                 sync_mma();
                 if (threadIdx.x == 0) {
@@ -435,30 +461,27 @@ edge_mlp_bwd_tc_kernel(const EdgeMlpArgs g) {
                     mma_forward(tmem, s_tile, smem_u32(sWt + (l - 1) * EM_WBYTES), EM_H, bar);
                 }
                 wait_mma();
-                const float* bl = sb + l * EM_H;
+                const float* bl = sb + l * EM_H + hf * EM_HW;
+                uint32_t acc[32];
+                tmem_ld32(tacc, acc);
+                tmem_wait_ld();
 #pragma unroll
-                for (int hf = 0; hf < 2; ++hf) {
-                    uint32_t acc[32];
-                    tmem_ld32(tacc + hf * 32, acc);
-                    tmem_wait_ld();
-#pragma unroll
-                    for (int o = 0; o < 32; ++o) v[hf * 32 + o] = __uint_as_float(acc[o]) + bl[hf * 32 + o];
-                }
+                for (int o = 0; o < EM_HW; ++o) v[o] = __uint_as_float(acc[o]) + bl[o];
             }
         }
         // ---- output layer: delta_out = alpha * dw (zero beyond C and for rows past E) ----
         {
             const float al = ok ? (g.alpha ? __ldg(g.alpha + e) : 1.f) : 0.f;
-            const float* src = g.dw + (ok ? e : 0) * C;
+            const float* src = g.dw + (ok ? e : 0) * C + hf * EM_HW;
 #pragma unroll
-            for (int o = 0; o < EM_H; o += 4) {
-                float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (o < C) q = __ldg(reinterpret_cast<const float4*>(src + o));
-                v[o] = q.x * al; v[o + 1] = q.y * al; v[o + 2] = q.z * al; v[o + 3] = q.w * al;
+            for (int o = 0; o < EM_HW; o += 4) {
+                float4 qd = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (hf * EM_HW + o < C) qd = __ldg(reinterpret_cast<const float4*>(src + o));
+                v[o] = qd.x * al; v[o + 1] = qd.y * al; v[o + 2] = qd.z * al; v[o + 3] = qd.w * al;
             }
-            store_row_bf16(d_tile, r, v);
+            store_row_bf16(d_tile, r, hf, v);
         }
-        // ---- back-propagate: layer index L = nh+1 (output weights Wo) down to the hidden weights Wh[0] ----
+        // ---- back-propagate: weight tile L = nh (Wo) down to 0 (Wh[0]) ----
         for (int L = nh; L >= 0; --L) {
             // delta tile (sD) and h tile (sS = h_{L+1}) are written: g = delta W_L, dW_L += delta^T h
             sync_mma();
@@ -470,30 +493,23 @@ edge_mlp_bwd_tc_kernel(const EdgeMlpArgs g) {
             wait_mma();
             __syncthreads();                                         // every column-sum read of sD precedes its rewrite below
             // delta of the GELU layer below: delta = g * GELU'(z)
-#pragma unroll
-            for (int hf = 0; hf < 2; ++hf) {
+            {
                 uint32_t acc[32];
-                tmem_ld32(tacc + hf * 32, acc);
+                tmem_ld32(tacc, acc);
                 tmem_wait_ld();
 #pragma unroll
-                for (int o = 0; o < 32; o += 2) {
-                    const float2 d = unpack_bf16(gp[(hf * 32 + o) >> 1]);
-                    v[hf * 32 + o] = __uint_as_float(acc[o]) * d.x;
-                    v[hf * 32 + o + 1] = __uint_as_float(acc[o + 1]) * d.y;
+                for (int o = 0; o < EM_HW; o += 2) {
+                    const float2 d = unpack_bf16(gp[o >> 1]);
+                    v[o] = __uint_as_float(acc[o]) * d.x;
+                    v[o + 1] = __uint_as_float(acc[o + 1]) * d.y;
                 }
             }
-            store_row_bf16(d_tile, r, v);                            // its readers (both MMAs, the column sums) are done
+            store_row_bf16(d_tile, r, hf, v);                        // its readers (both MMAs, the column sums) are done
             if (L > 0) {
-                // h_L and GELU'(z_L) from the stored pre-activation tile (a thread reads back the row it wrote)
-                load_row_bf16(smem_u32(sZ + (L - 1) * EM_ABYTES), r, v);
-#pragma unroll
-                for (int o = 0; o < EM_H; o += 2) {
-                    float h0, h1, d0, d1;
-                    gelu_both(v[o], h0, d0); gelu_both(v[o + 1], h1, d1);
-                    v[o] = h0; v[o + 1] = h1;
-                    gp[o >> 1] = pack_bf16(d0, d1);
-                }
-                store_row_bf16(s_tile, r, v);
+                // h_L and GELU'(z_L) from the stored pre-activation tile (a thread reads back the half row it wrote)
+                load_row_bf16(smem_u32(sZ + (L - 1) * EM_ABYTES), r, hf, v);
+                gelu_pair(v, gp);
+                store_row_bf16(s_tile, r, hf, v);
             }
         }
         // ---- first layer: dW1[o, i] += sum_e delta_1[e, o] z0[e, i], db1[o] += sum_e delta_1[e, o] (FP32 pipe) ----
@@ -517,20 +533,16 @@ edge_mlp_bwd_tc_kernel(const EdgeMlpArgs g) {
     // ---- CTA-level results -> global (fp32 red.add) ----
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     for (int L = nh; L >= 0; --L) {
-        // M = 64 accumulator: row m lives in TMEM lane (m % 16) + 32 * (m / 16), i.e. in the first 16 lanes of warp m / 16
+        // M = 64 accumulator: row m lives in TMEM lane (m % 16) + 32 * (m / 16), i.e. in the first 16 lanes of quadrant m / 16
         float* dst = L == nh ? g.dWo : g.dWh[L];
         const int rows = L == nh ? C : EM_H;
-        const uint32_t base = tacc + 64u * (uint32_t)(1 + (nh - L));
+        uint32_t acc[32];
+        tmem_ld32(tacc + 64u * (uint32_t)(1 + (nh - L)), acc);
+        tmem_wait_ld();
+        const int row = q * 16 + lane;
+        if (lane < 16 && row < rows) {
 #pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-            uint32_t acc[32];
-            tmem_ld32(base + hf * 32, acc);
-            tmem_wait_ld();
-            const int row = warp * 16 + lane;
-            if (lane < 16 && row < rows) {
-#pragma unroll
-                for (int o = 0; o < 32; ++o) atomicAdd(dst + row * EM_H + hf * 32 + o, __uint_as_float(acc[o]));
-            }
+            for (int o = 0; o < EM_HW; ++o) atomicAdd(dst + row * EM_H + hf * EM_HW + o, __uint_as_float(acc[o]));
         }
         if (threadIdx.x < EM_H) {
             float* db = L == nh ? g.dbo : g.dbh[L];

@@ -51,7 +51,9 @@ class GeometricEmbedding(nn.Module):
             plan._geo[key] = feat
         return feat
 
-    def embed(self, feat):
+    def embed(self, feat, tc: bool = False):
+        """tc: let the K = 64 layer run on the tensor cores in bf16 mode (vx mode embeds B * rows points per step; in fx
+        mode the embedding is a once-per-graph-sized side computation and stays fp32)."""
         if self.method == "pointnet":
             z, mask, plan = feat
             h = ops.linear(z, self.pointnet_mlp[0].weight, self.pointnet_mlp[0].bias, act=ops.ACT_RELU)
@@ -59,7 +61,7 @@ class GeometricEmbedding(nn.Module):
             pooled = ops.segment_pool(h, plan, self.pooling)                       # [m, 64], empty rows 0
             return ops.linear(pooled, self.fc[0].weight, self.fc[0].bias, act=ops.ACT_RELU) * mask   # gemb.py:224-226
         h = ops.linear(feat, self.mlp[0].weight, self.mlp[0].bias, act=ops.ACT_RELU)
-        return ops.linear(h, self.mlp[2].weight, self.mlp[2].bias, act=ops.ACT_RELU)
+        return ops.linear(h, self.mlp[2].weight, self.mlp[2].bias, act=ops.ACT_RELU, tc=tc)
 
     def forward(self, input_geom, latent_queries, spatial_nbrs):
         plan = ops.graph_plan(spatial_nbrs, input_geom.shape[0])

@@ -139,9 +139,9 @@ class _MAGNOBase(nn.Module):
         if self.use_geoembed:
             C = out.shape[-1]
             feat = self.geoembed.features(src_coord, dst_coord, plan, groups, cache=(groups == 1))
-            g = self.geoembed.embed(feat)                                # [m, C], batch independent
+            g = self.geoembed.embed(feat, tc=groups > 1)                 # [m, C], batch independent
             W = self.recovery.fcs[0].weight[:, :, 0]                     # [C, 2C]: cat[agno, geo] (magno.py:346-350)
-            gterm = ops.linear(g, W[:, C:], self.recovery.fcs[0].bias)   # batch-independent half of the recovery
+            gterm = ops.linear(g, W[:, C:], self.recovery.fcs[0].bias, tc=groups > 1)   # batch-independent half of the recovery
             # [B*m, C] x [C, C]: the one big dense layer of MAGNO; tensor cores in bf16 mode, FFMA in fp32 mode
             out = ops.linear(out.view(-1, C), W[:, :C], None, add=gterm, tc=True).view(out.shape)
         return out
@@ -290,9 +290,12 @@ class MAGNODecoder(_MAGNOBase):
         if self.use_geoembed:
             Wrec = self.recovery.fcs[0].weight[:, :, 0]                   # [C, 2C]
             feat = self.geoembed.features(src, dst, plan, groups, cache=(groups == 1))
-            g = self.geoembed.embed(feat)                                 # [rows, C]
-            gterm = ops.linear(g, Wrec[:, C:], self.recovery.fcs[0].bias)
-            const = ops.linear(gterm, Wp, bp)                             # [rows, Cout]
+            g = self.geoembed.embed(feat, tc=groups > 1)                  # [rows, C]
+            # projection o recovery folded on the parameter side: const = (Wp Wg) g + (Wp b_rec + bp); the [rows, C]
+            # recovery output of the geometry half is never formed (rows = B * Nq in vx mode)
+            Wgeo = ops.linear(Wp, Wrec[:, C:].t())                        # Wp @ Wg   [Cout, C]
+            bgeo = ops.linear(self.recovery.fcs[0].bias.view(1, -1), Wp, bp).view(-1)
+            const = ops.linear(g, Wgeo, bgeo)                             # [rows, Cout]
             Wfold = ops.linear(Wp, Wrec[:, :C].t())                       # Wp @ Wa   [Cout, C]
         else:
             const, Wfold = bp.view(1, -1), Wp
