@@ -139,9 +139,9 @@ class _MAGNOBase(nn.Module):
         if self.use_geoembed:
             C = out.shape[-1]
             feat = self.geoembed.features(src_coord, dst_coord, plan, groups, cache=(groups == 1))
-            g = self.geoembed.embed(feat, tc=groups > 1)                 # [m, C], batch independent
+            g = self.geoembed.embed(feat, tc=self._embed_on_tc(groups, feat))   # [m, C], batch independent
             W = self.recovery.fcs[0].weight[:, :, 0]                     # [C, 2C]: cat[agno, geo] (magno.py:346-350)
-            gterm = ops.linear(g, W[:, C:], self.recovery.fcs[0].bias, tc=groups > 1)   # batch-independent half of the recovery
+            gterm = ops.linear(g, W[:, C:], self.recovery.fcs[0].bias, tc=self._embed_on_tc(groups, feat))   # batch-independent half of the recovery
             # [B*m, C] x [C, C]: the one big dense layer of MAGNO; tensor cores in bf16 mode, FFMA in fp32 mode
             out = ops.linear(out.view(-1, C), W[:, :C], None, add=gterm, tc=True).view(out.shape)
         return out
@@ -158,6 +158,15 @@ class _MAGNOBase(nn.Module):
                 acc = t if acc is None else acc + t
             return acc
         return torch.stack(outs, 0).mean(dim=0)
+
+    EMBED_TC_MIN_ROWS = 1 << 16
+
+    @classmethod
+    def _embed_on_tc(cls, groups: int, feat) -> bool:
+        """vx mode embeds B * rows points per step: from 65 536 rows on, the K = 64 layers of the geometry embedding go to
+        the tensor cores in bf16 mode; fx mode (a once-per-graph-sized side computation) and small batches stay fp32."""
+        rows = feat.shape[0] if torch.is_tensor(feat) else feat[1].shape[0]
+        return groups > 1 and rows >= cls.EMBED_TC_MIN_ROWS
 
     def _drop(self, nbrs):
         return apply_edge_drop_csr(nbrs, self.sampling_strategy, self.max_neighbors, self.sample_ratio, self.training)
@@ -290,7 +299,7 @@ class MAGNODecoder(_MAGNOBase):
         if self.use_geoembed:
             Wrec = self.recovery.fcs[0].weight[:, :, 0]                   # [C, 2C]
             feat = self.geoembed.features(src, dst, plan, groups, cache=(groups == 1))
-            g = self.geoembed.embed(feat, tc=groups > 1)                  # [rows, C]
+            g = self.geoembed.embed(feat, tc=self._embed_on_tc(groups, feat))   # [rows, C]
             # projection o recovery folded on the parameter side: const = (Wp Wg) g + (Wp b_rec + bp); the [rows, C]
             # recovery output of the geometry half is never formed (rows = B * Nq in vx mode)
             Wgeo = ops.linear(Wp, Wrec[:, C:].t())                        # Wp @ Wg   [Cout, C]
