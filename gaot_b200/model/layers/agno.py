@@ -54,11 +54,7 @@ class AGNO(nn.Module):
                 and fcs[0].weight.shape[1] == 2 * y.shape[1]):
             # bf16 mode: gather, kernel MLP and the attention-weight product in ONE tensor-core kernel (forward and backward);
             # the attention weights are parameter free here (cosine similarity of coordinates, or 1 / degree)
-            if self.use_attn:
-                alpha = ops.edge_cosine_softmax(y, x, self.coord_dim, plan)
-            else:
-                deg = (plan.splits[1:] - plan.splits[:-1]).clamp(min=1).to(torch.float32)
-                alpha = (1.0 / deg)[plan.edge_row]
+            alpha = self._parameter_free_alpha(y, x, plan)
             params = []
             for fc in fcs:
                 params += [fc.weight, fc.bias]
@@ -71,12 +67,29 @@ class AGNO(nn.Module):
             q = ops.linear(x[:, :cd].contiguous(), self.query_proj.weight, self.query_proj.bias)
             k = ops.linear(y[:, :cd].contiguous(), self.key_proj.weight, self.key_proj.bias)
             alpha = ops.edge_dot_softmax(q, k, plan, self.scaling_factor)
-        elif self.use_attn:
-            alpha = ops.edge_cosine_softmax(y, x, self.coord_dim, plan)
         else:
-            deg = (plan.splits[1:] - plan.splits[:-1]).clamp(min=1).to(torch.float32)
-            alpha = (1.0 / deg)[plan.edge_row]
+            alpha = self._parameter_free_alpha(y, x, plan)
         return ops.scale_rows(kappa, alpha)
+
+    def _parameter_free_alpha(self, y, x, plan: ops.GraphPlan):
+        """Cosine attention weights (agno.py:212-224) or 1 / degree (agno.py:264): pure functions of the coordinates and
+        the graph, so they are cached on the graph plan (fx mode keeps one plan for the whole run; the reference recomputes
+        them in every forward)."""
+        key = ("alpha", self.use_attn, y.data_ptr(), y._version, x.data_ptr(), x._version)
+        hit = plan._geo.get(key)
+        if hit is not None:
+            return hit
+        with torch.no_grad():
+            if self.use_attn:
+                alpha = ops.edge_cosine_softmax(y, x, self.coord_dim, plan)
+            else:
+                deg = (plan.splits[1:] - plan.splits[:-1]).clamp(min=1).to(torch.float32)
+                alpha = (1.0 / deg)[plan.edge_row]
+        if not torch.cuda.is_available() or not torch.cuda.is_current_stream_capturing():
+            for k in [k for k in plan._geo if isinstance(k, tuple) and k and k[0] == "alpha"]:
+                del plan._geo[k]                     # one entry per plan (vx mode hands in fresh coordinate tensors every batch)
+            plan._geo[key] = alpha
+        return alpha
 
     def forward(self, y, neighbors, x=None, f_y=None, weights=None):
         if weights is not None:

@@ -47,7 +47,8 @@ class GeometricEmbedding(nn.Module):
             else:
                 feat = ops.geo_stats(input_geom, latent_queries, plan, groups)
         if cache:
-            plan._geo.clear()
+            for k in [k for k in plan._geo if not (isinstance(k, tuple) and k and k[0] == "alpha")]:
+                del plan._geo[k]                     # one feature entry per plan (the attention-weight cache lives beside it)
             plan._geo[key] = feat
         return feat
 
