@@ -162,7 +162,7 @@ class Dist:
 class Case:
     """One workload on this rank: model, flat-buffer trainer, synthetic batch, captured step."""
 
-    def __init__(self, D, w, B, precision, use_graph=True):
+    def __init__(self, D, w, B, precision, use_graph=True, fresh_meshes=0):
         from gaot_b200 import ops as O
         from gaot_b200.model import GAOT
         from gaot_b200.trainer import TrainStep
@@ -179,9 +179,24 @@ class Case:
         self.pn_s, self.tgt_s = torch.empty_like(self.pn_d), torch.empty_like(self.tgt_d)
         self.vx = bool(w.get("vx"))
         self.enc_graphs = self.dec_graphs = None
-        if self.vx:   # per-sample graphs built on the GPU in one batched launch each (reference: graph_builder.py:28-87)
-            self.enc_graphs = [[g_] for g_ in O.radius_csr(self.x_d, self.lat_d, w["radius"])]
-            self.dec_graphs = [[g_] for g_ in O.radius_csr(self.lat_d, self.x_d, w["radius"])]
+        self.rotate = []
+        if self.vx:
+            # per-sample graphs built on the GPU by the GraphBuilder drop-in (reference: graph_builder.py:28-87: before training)
+            from gaot_b200.datasets import GraphBuilder
+            gb = GraphBuilder("native")
+            self.enc_graphs, self.dec_graphs = gb.build_graphs_for_split(self.x_d, self.lat_d, w["radius"], [1.0])
+            if fresh_meshes:
+                # real vx training sees a NEW set of meshes every step: `fresh_meshes` more batches (meshes, graphs, features);
+                # the step then runs eagerly and rebuilds the block-diagonal merged graph, its transpose and the geometry
+                # statistics for every batch (no CUDA-graph replay of a fixed batch)
+                self.rotate = [(self.x_d, self.pn_d, self.tgt_d, self.enc_graphs, self.dec_graphs)]
+                for k in range(1, fresh_meshes):
+                    _, xk, pnk, tgtk = synth(w, D.rank + 100 * k, B)
+                    xk = xk.to(dev)
+                    ek, dk = gb.build_graphs_for_split(xk, self.lat_d, w["radius"], [1.0])
+                    self.rotate.append((xk, pnk.to(dev), tgtk.to(dev), ek, dk))
+                use_graph = False
+        self._it = 0
         self.graphed = None
         if use_graph:
             for _ in range(2):
@@ -197,6 +212,13 @@ class Case:
     def eager_step(self):
         from gaot_b200 import ops as O
         O.set_precision(self.precision)
+        if self.vx and self.rotate:
+            x, pn, tgt, enc, dec = self.rotate[self._it % len(self.rotate)]
+            self._it += 1
+            # forget the merged plans of earlier batches: a training loader never repeats a combination of samples
+            self.model.encoder._merged_cache.clear()
+            self.model.decoder._merged_cache.clear()
+            return self.step.variable_coords_step(self.lat_d, pn, tgt, x, enc, dec)
         if self.vx:
             return self.step.variable_coords_step(self.lat_d, self.pn_d, self.tgt_d, self.x_d, self.enc_graphs, self.dec_graphs)
         return self.step.fixed_coords_step(self.lat_d, self.x_d, self.pn_d, self.tgt_d)
@@ -488,9 +510,11 @@ def run_ours(args, w):
     else:
         B = args.batch or w["B"]
     peaks = load_peaks()
-    case = Case(D, w, B, args.precision, use_graph=not args.no_graph)
+    case = Case(D, w, B, args.precision, use_graph=not args.no_graph, fresh_meshes=args.fresh_meshes if w.get("vx") else 0)
     step, graphed = case.step, case.graphed
     pn_h, tgt_h = case.pn.pin_memory(), case.tgt.pin_memory()
+    x_h = case.x.pin_memory() if case.vx else None
+    x_stage = torch.empty_like(case.x_d) if case.vx else None
 
     feeder = None
     if graphed is not None:
@@ -511,7 +535,15 @@ def run_ours(args, w):
             return float(loss)                                                 # .item(): D2H read of the loss
         case.pn_s.copy_(pn_h, non_blocking=True)
         case.tgt_s.copy_(tgt_h, non_blocking=True)
-        if case.vx:
+        if case.vx and case.rotate:
+            # fresh meshes every step: the coordinates go host -> device as well (graphs are prebuilt, as in the reference)
+            x, _, _, enc, dec = case.rotate[case._it % len(case.rotate)]
+            case._it += 1
+            x_stage.copy_(x_h, non_blocking=True)
+            case.model.encoder._merged_cache.clear()
+            case.model.decoder._merged_cache.clear()
+            loss = step.variable_coords_step(case.lat_d, case.pn_s, case.tgt_s, x, enc, dec)
+        elif case.vx:
             loss = step.variable_coords_step(case.lat_d, case.pn_s, case.tgt_s, case.x_d, case.enc_graphs, case.dec_graphs)
         else:
             loss = step.fixed_coords_step(case.lat_d, case.x_d, case.pn_s, case.tgt_s)
@@ -549,10 +581,12 @@ def run_ours(args, w):
         "config": {"workload": args.workload, "precision": args.precision, "desc": w["desc"], "batch_per_gpu": B,
                    "global_batch": B * world, "points": w["n"], "latent_tokens": M, "edges": E, "params": step.num_params,
                    "parallelism": f"dp{world}", "cuda_graph": graphed is not None,
+                   "vx_fresh_mesh_batches": len(case.rotate) if case.vx else None,
                    "l2": f"no flush between steps: one step allocates {step_bytes / 1e6:.0f} MB of activations / workspaces "
                          f"(measured), {step_bytes / max(l2_bytes, 1):.0f}x the {l2_bytes / 1e6:.0f} MB L2"},
         "e2e": {"value": total_pts / (ms_e2e * 1e-3), "unit": "points/s", "ms_per_step": ms_e2e / args.steps,
-                "h2d_bytes_per_step": int(case.pn.numel() * 4 + case.tgt.numel() * 4), "d2h_bytes_per_step": 4},
+                "h2d_bytes_per_step": int(case.pn.numel() * 4 + case.tgt.numel() * 4 + (case.x.numel() * 4 if case.vx and case.rotate else 0)),
+                "d2h_bytes_per_step": 4},
         "gpu_launches": int(launches), "clocks": clocks, "kernel_breakdown": breakdown,
     }
 
@@ -708,6 +742,9 @@ def main():
     ap.add_argument("--no-roofline", action="store_true", help="skip the isolated kernel timings")
     ap.add_argument("--no-extra", action="store_true", help="skip the cfg5 strong-scaling and cfg4 rollout blocks of the default line")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
+    ap.add_argument("--fresh-meshes", type=int, default=3,
+                    help="vx workloads: number of distinct mesh batches cycled through, a new one every step (eager step, merged "
+                         "graphs rebuilt per batch); 0 = replay one fixed batch through a CUDA graph")
     ap.add_argument("--dump-calls", default="", help="write the per-ABI-call timing list of one step to this file")
     ap.add_argument("--precision", default=os.environ.get("GAOT_B200_PRECISION", "bf16"), choices=["fp32", "ffma", "bf16"],
                     help="processor numerics: bf16 tensor cores, fp32 = split-precision tensor cores (parity), ffma = fp32 FFMA")

@@ -229,15 +229,28 @@ edge_mlp_fwd_tc_kernel(const EdgeMlpArgs g) {
     constexpr int KC = KIN / 2;
 
     const int64_t n_tiles = (g.E + EM_TILE - 1) / EM_TILE;
+    // the edge's endpoints and attention weight are fetched one tile ahead: the dependent chain index -> coordinates ->
+    // layer 1 otherwise starts every tile with two exposed memory round trips
+    int nj = 0, nm = 0;
+    float nal = 1.f;
+    {
+        const int64_t e0 = (int64_t)blockIdx.x * EM_TILE + r;
+        if (e0 < g.E) { nj = (int)__ldg(g.index + e0); nm = (int)__ldg(g.edge_row + e0); nal = g.alpha ? __ldg(g.alpha + e0) : 1.f; }
+    }
     for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
         const int64_t e = t * EM_TILE + r;
         const bool ok = e < g.E;
+        const int j = nj, m = nm;
+        const float al = nal;
+        {
+            const int64_t en = e + (int64_t)gridDim.x * EM_TILE;
+            if (en < g.E) { nj = (int)__ldg(g.index + en); nm = (int)__ldg(g.edge_row + en); nal = g.alpha ? __ldg(g.alpha + en) : 1.f; }
+        }
         float v[EM_HW];
         {
             float z0[KIN];
-            const int64_t j = ok ? __ldg(g.index + e) : 0, m = ok ? __ldg(g.edge_row + e) : 0;
 #pragma unroll
-            for (int i = 0; i < KC; ++i) { z0[i] = __ldg(g.y + j * g.dy + i); z0[KC + i] = __ldg(g.x + m * g.dx + i); }
+            for (int i = 0; i < KC; ++i) { z0[i] = __ldg(g.y + (int64_t)j * g.dy + i); z0[KC + i] = __ldg(g.x + (int64_t)m * g.dx + i); }
             layer1<KIN>(sW1, sb, hf, z0, v);
         }
 #pragma unroll
@@ -267,7 +280,6 @@ edge_mlp_fwd_tc_kernel(const EdgeMlpArgs g) {
             }
         }
         if (ok) {
-            const float al = g.alpha ? __ldg(g.alpha + e) : 1.f;
             float* dst = g.w + e * C + hf * EM_HW;
 #pragma unroll
             for (int o = 0; o < EM_HW; o += 4)
@@ -389,8 +401,8 @@ edge_mlp_bwd_tc_kernel(const EdgeMlpArgs g) {
     float acc1[NPAIR];
 #pragma unroll
     for (int p = 0; p < NPAIR; ++p) acc1[p] = 0.f;
-    float dbacc[EM_MAXHID + 1];                                      // threads 0..63: column sums of delta for bh[.] / bo
-#pragma unroll
+    float dbacc[EM_MAXHID + 1];                                      // column sums of delta (bias gradients of bh[.] / bo): thread t
+#pragma unroll                                                       // owns column t % 64 over the 32 rows of quarter t / 64
     for (int l = 0; l <= EM_MAXHID; ++l) dbacc[l] = 0.f;
 
     auto sync_mma = [&]() {                                          // operand tiles written by all threads -> visible to the MMA
@@ -403,17 +415,15 @@ edge_mlp_bwd_tc_kernel(const EdgeMlpArgs g) {
         phase ^= 1u;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     };
-    auto colsum = [&](int slot) {                                    // thread t < 64: sum of column t of the delta tile
-        if (threadIdx.x < EM_H) {
-            const int c = threadIdx.x;
-            float s0 = 0.f, s1 = 0.f;
+    auto colsum = [&](int slot) {                                    // every thread: 32 rows of one column of the delta tile
+        const int c = threadIdx.x & (EM_H - 1), e0 = (threadIdx.x >> 6) * 32;
+        float s0 = 0.f, s1 = 0.f;
 #pragma unroll 8
-            for (int e = 0; e < EM_TILE; e += 2) {
-                s0 += lds_bf16(d_tile + sw128_off(e, c >> 3) + (uint32_t)(c & 7) * 2u);
-                s1 += lds_bf16(d_tile + sw128_off(e + 1, c >> 3) + (uint32_t)(c & 7) * 2u);
-            }
-            dbacc[slot] += s0 + s1;
+        for (int e = 0; e < 32; e += 2) {
+            s0 += lds_bf16(d_tile + sw128_off(e0 + e, c >> 3) + (uint32_t)(c & 7) * 2u);
+            s1 += lds_bf16(d_tile + sw128_off(e0 + e + 1, c >> 3) + (uint32_t)(c & 7) * 2u);
         }
+        dbacc[slot] += s0 + s1;
     };
     auto gelu_pair = [&](float (&v)[EM_HW], uint32_t (&gp)[EM_HW / 2]) {   // v -> GELU(v), gp = GELU'(v) packed bf16
 #pragma unroll
@@ -427,16 +437,44 @@ edge_mlp_bwd_tc_kernel(const EdgeMlpArgs g) {
 
     const int64_t n_tiles = (g.E + EM_TILE - 1) / EM_TILE;
     bool first_tile = true;
+    // endpoints / attention weight one tile ahead (see the forward kernel); the upstream-gradient rows of the next tile are
+    // pulled towards the SM with prefetch instructions while this tile is being processed
+    int nj = 0, nm = 0;
+    float nal = 0.f;
+    {
+        const int64_t e0 = (int64_t)blockIdx.x * EM_TILE + r;
+        if (e0 < g.E) { nj = (int)__ldg(g.index + e0); nm = (int)__ldg(g.edge_row + e0); nal = g.alpha ? __ldg(g.alpha + e0) : 1.f; }
+    }
     for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, first_tile = false) {
         const int64_t e = t * EM_TILE + r;
         const bool ok = e < g.E;
+        const int j = nj, m = nm;
+        const float al = ok ? nal : 0.f;
+        {
+            const int64_t en = e + (int64_t)gridDim.x * EM_TILE;
+            if (en < g.E) {
+                nj = (int)__ldg(g.index + en); nm = (int)__ldg(g.edge_row + en); nal = g.alpha ? __ldg(g.alpha + en) : 1.f;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(g.dw + en * C + hf * EM_HW));
+            }
+        }
         float v[EM_HW];
+        // output layer first: delta_out = alpha * dw (zero beyond C and for rows past E) goes straight into the delta tile
+        // (free since the previous tile's last barrier; its rows were prefetched into the L2 one tile ago)
+        {
+            const float* src = g.dw + (ok ? e : 0) * C + hf * EM_HW;
+#pragma unroll
+            for (int o = 0; o < EM_HW; o += 4) {
+                float4 qd = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (hf * EM_HW + o < C) qd = __ldg(reinterpret_cast<const float4*>(src + o));
+                v[o] = qd.x * al; v[o + 1] = qd.y * al; v[o + 2] = qd.z * al; v[o + 3] = qd.w * al;
+            }
+            store_row_bf16(d_tile, r, hf, v);
+        }
         uint32_t gp[EM_HW / 2];                                      // GELU'(z_l) of the layer being back-propagated
         {
             float z0[KIN];
-            const int64_t j = ok ? __ldg(g.index + e) : 0, m = ok ? __ldg(g.edge_row + e) : 0;
 #pragma unroll
-            for (int i = 0; i < KC; ++i) { z0[i] = __ldg(g.y + j * g.dy + i); z0[KC + i] = __ldg(g.x + m * g.dx + i); }
+            for (int i = 0; i < KC; ++i) { z0[i] = __ldg(g.y + (int64_t)j * g.dy + i); z0[KC + i] = __ldg(g.x + (int64_t)m * g.dx + i); }
             if (hf == 0) {
 #pragma unroll
                 for (int i = 0; i < KIN; ++i) sZ0[r * (KIN + 1) + i] = z0[i];
@@ -468,18 +506,6 @@ edge_mlp_bwd_tc_kernel(const EdgeMlpArgs g) {
 #pragma unroll
                 for (int o = 0; o < EM_HW; ++o) v[o] = __uint_as_float(acc[o]) + bl[o];
             }
-        }
-        // ---- output layer: delta_out = alpha * dw (zero beyond C and for rows past E) ----
-        {
-            const float al = ok ? (g.alpha ? __ldg(g.alpha + e) : 1.f) : 0.f;
-            const float* src = g.dw + (ok ? e : 0) * C + hf * EM_HW;
-#pragma unroll
-            for (int o = 0; o < EM_HW; o += 4) {
-                float4 qd = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (hf * EM_HW + o < C) qd = __ldg(reinterpret_cast<const float4*>(src + o));
-                v[o] = qd.x * al; v[o + 1] = qd.y * al; v[o + 2] = qd.z * al; v[o + 3] = qd.w * al;
-            }
-            store_row_bf16(d_tile, r, hf, v);
         }
         // ---- back-propagate: weight tile L = nh (Wo) down to 0 (Wh[0]) ----
         for (int L = nh; L >= 0; --L) {
@@ -544,9 +570,10 @@ edge_mlp_bwd_tc_kernel(const EdgeMlpArgs g) {
 #pragma unroll
             for (int o = 0; o < EM_HW; ++o) atomicAdd(dst + row * EM_H + hf * EM_HW + o, __uint_as_float(acc[o]));
         }
-        if (threadIdx.x < EM_H) {
+        {
             float* db = L == nh ? g.dbo : g.dbh[L];
-            if (threadIdx.x < rows) atomicAdd(db + threadIdx.x, dbacc[nh - L]);
+            const int c = threadIdx.x & (EM_H - 1);
+            if (c < rows) atomicAdd(db + c, dbacc[nh - L]);
         }
     }
 #pragma unroll
