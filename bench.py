@@ -450,18 +450,28 @@ def strong_scaling_leg(D, args):
     G = 8
     if G % D.world != 0:
         return {"skipped": f"global batch {G} does not divide over {D.world} ranks"}
+    from gaot_b200 import ops as O
     w = WORKLOADS["cfg5"]
     B = G // D.world
-    case = Case(D, w, B, args.precision)
-    for _ in range(3):
-        case.dev_step()
     K = 5
-    ms = D.timed(case.dev_step, K)
+    res = {}
+    for shard in ((False, True) if D.world > 1 else (False,)):
+        # sharded: every rank evaluates 1 / world of the (batch-independent) edge-weight MLP, all-gather / reduce-scatter over
+        # NVLink (ops.enable_edge_sharding); replicated: plain data parallelism
+        O.enable_edge_sharding(True if shard else None)
+        case = Case(D, w, B, args.precision)
+        for _ in range(3):
+            case.dev_step()
+        res[shard] = D.timed(case.dev_step, K) / K
+        E = case.edges()
+        del case
+        torch.cuda.empty_cache()
+    O.enable_edge_sharding(None)
+    ms = min(res.values())
     out = {"workload": "cfg5", "desc": w["desc"].replace("B=1/GPU", f"global batch {G}"), "scaling": "strong", "global_batch": G,
-           "batch_per_gpu": B, "n_gpus": D.world, "ms_per_step": ms / K, "value": G * w["n"] * K / (ms * 1e-3), "unit": "points/s",
-           "edges": case.edges(), "steps": K}
-    del case
-    torch.cuda.empty_cache()
+           "batch_per_gpu": B, "n_gpus": D.world, "ms_per_step": ms, "value": G * w["n"] / (ms * 1e-3), "unit": "points/s",
+           "edges": E, "steps": K, "ms_per_step_replicated_edge_mlp": res[False],
+           "ms_per_step_sharded_edge_mlp": res.get(True)}
     return out
 
 

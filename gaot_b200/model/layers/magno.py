@@ -127,15 +127,36 @@ class _MAGNOBase(nn.Module):
         ys, xs = (node_pos_encode(src_coord), node_pos_encode(dst_coord)) if self.node_embedding else (src_coord, dst_coord)
         return self.agno.edge_weights(ys, xs, plan)
 
+    # ---- destination rows sharded over the data-parallel ranks (ops.enable_edge_sharding) --------------------------------
+    @staticmethod
+    def _row_sharding(plan, n_rows: int):
+        """(world, rank, group) when the MAGNO operator on this graph runs row-sharded: every rank owns 1 / world of the
+        destination rows for ALL samples of the global batch (edge-weight MLP, gather / reduce and their backward on that
+        slice only), samples are exchanged with one all-gather in and one all-to-all out.  Otherwise world = 1."""
+        world, rank, grp = ops.edge_shard_world()
+        if world > 1 and plan.E >= ops.SHARD_EDGES_MIN and n_rows % world == 0:
+            return world, rank, grp
+        return 1, 0, None
+
     def _one_scale(self, plan, src_coord, dst_coord, feats, groups: int, lift=None):
         """AGNO + geo-embedding + recovery on one graph (magno.py:322-350 / 660-688).
         src/dst coords are [n_src,d] / [m,d] matching the plan; feats [Bf, n_src, C] - or, with
         lift=(Wl, bl), the raw inputs [Bf, n_src, Cin] whose affine lifting is fused into the gather."""
-        w = self._edge_weights(plan, src_coord, dst_coord)
-        if lift is not None:
-            out = ops.lift_aggregate(feats, lift[0], lift[1], w, plan)   # [Bf, m, C], lifted features never materialised
+        world, rank, grp = self._row_sharding(plan, plan.m) if groups == 1 else (1, 0, None)
+        if world > 1:
+            # my slice of the latent rows for the WHOLE global batch, then samples <-> rows exchange; the edge weights of the
+            # other slices are never computed on this rank
+            sl = plan.row_slice(rank, world)
+            w = self._edge_weights(sl, src_coord, dst_coord[sl.row_lo:sl.row_hi])
+            f_all = ops.all_gather_batch(feats, grp)                      # [B_global, n_src, Cin | C]
+            out_s = ops.lift_aggregate(f_all, lift[0], lift[1], w, sl) if lift is not None else ops.agno_aggregate(f_all, w, sl)
+            out = ops.rows_to_samples(out_s, grp)                         # [B_local, m, C]
         else:
-            out = ops.agno_aggregate(feats, w, plan)                     # [Bf, m, C]
+            w = self._edge_weights(plan, src_coord, dst_coord)
+            if lift is not None:
+                out = ops.lift_aggregate(feats, lift[0], lift[1], w, plan)   # [Bf, m, C], lifted features never materialised
+            else:
+                out = ops.agno_aggregate(feats, w, plan)                     # [Bf, m, C]
         if self.use_geoembed:
             C = out.shape[-1]
             feat = self.geoembed.features(src_coord, dst_coord, plan, groups, cache=(groups == 1))
@@ -295,10 +316,25 @@ class MAGNODecoder(_MAGNOBase):
         else:
             plan = self._merged_plan([self._drop(decoder_nbrs[b][0]) for b in range(B)], M)
             src, dst, groups = latent.repeat(B, 1), query_coord.reshape(B * Nq, -1), B
+        world, rank, grp = self._row_sharding(plan, Nq) if not vx else (1, 0, None)
+        full_plan = plan
+        if world > 1:
+            # row-sharded: this rank prepares its slice of the query rows only (edge weights, geometry term, read-out
+            # weights); apply_fused runs that slice for the whole global batch and exchanges samples <-> rows
+            plan = full_plan.row_slice(rank, world)
+            dst = dst[plan.row_lo:plan.row_hi]
         w = self._edge_weights(plan, src, dst)                            # [E, C]
         if self.use_geoembed:
             Wrec = self.recovery.fcs[0].weight[:, :, 0]                   # [C, 2C]
-            feat = self.geoembed.features(src, dst, plan, groups, cache=(groups == 1))
+            if world > 1:
+                # the statistics are standardised over ALL rows (gemb.py:160-166): computed on the full graph (cached), sliced
+                feat = self.geoembed.features(src, query_coord, full_plan, 1, cache=True)
+                if torch.is_tensor(feat):
+                    feat = feat[plan.row_lo:plan.row_hi]
+                else:
+                    raise NotImplementedError("row sharding with the pointnet embedding")
+            else:
+                feat = self.geoembed.features(src, dst, plan, groups, cache=(groups == 1))
             g = self.geoembed.embed(feat, tc=self._embed_on_tc(groups, feat))   # [rows, C]
             # projection o recovery folded on the parameter side: const = (Wp Wg) g + (Wp b_rec + bp); the [rows, C]
             # recovery output of the geometry half is never formed (rows = B * Nq in vx mode)
@@ -309,12 +345,17 @@ class MAGNODecoder(_MAGNOBase):
         else:
             const, Wfold = bp.view(1, -1), Wp
         u = Wfold.unsqueeze(1) * w.unsqueeze(0)                           # [Cout, E, C]
-        return dict(plan=plan, u=u, const=const, vx=vx, Nq=Nq)
+        return dict(plan=plan, u=u, const=const, vx=vx, Nq=Nq, shard=(world, grp), n_src=M)
 
     def apply_fused(self, rndata, prep):
         B, M, C = rndata.shape
-        if rndata.shape[1] != prep["plan"].n_src // (B if prep["vx"] else 1):
+        if rndata.shape[1] != prep["plan"].n_src // (B if prep["vx"] else 1):   # (a row slice keeps the full source numbering)
             raise ValueError(f"rndata has {rndata.shape[1]} tokens but latent_tokens_coord has {prep['plan'].n_src // (B if prep['vx'] else 1)}")
+        world, grp = prep.get("shard", (1, None))
+        if world > 1:
+            r_all = ops.all_gather_batch(rndata, grp)                     # [B_global, M, C]: the latent of every sample
+            out_s = ops.agno_dot(r_all, prep["u"], prep["plan"]) + prep["const"].unsqueeze(0)   # my query rows, all samples
+            return ops.rows_to_samples(out_s, grp)                        # [B_local, Nq, Cout]
         feats = rndata.reshape(1, B * M, C) if prep["vx"] else rndata
         out = ops.agno_dot(feats, prep["u"], prep["plan"])               # [Bf, rows, Cout]
         return (out + prep["const"].unsqueeze(0)).view(B, prep["Nq"], -1)

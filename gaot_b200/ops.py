@@ -149,6 +149,21 @@ class GraphPlan:
         call("gaot_csr_edge_rows", ptr(self.splits), self.m, ptr(self.edge_row))
         self._t = None
         self._geo: Dict = {}
+        self._slices: Dict = {}
+
+    def row_slice(self, part: int, parts: int) -> "GraphPlan":
+        """Sub-graph of the destination rows [part * m / parts, (part + 1) * m / parts) as a plan of its own (sources keep
+        their numbering); needs m % parts == 0.  Cached (one host read of two row offsets on first use)."""
+        key = (part, parts)
+        hit = self._slices.get(key)
+        if hit is None:
+            per = self.m // parts
+            lo, hi = part * per, (part + 1) * per
+            a, b = (int(v) for v in self.splits[[lo, hi]].cpu())
+            hit = GraphPlan(self.index[a:b], self.splits[lo:hi + 1] - a, self.n_src)
+            hit.row_lo, hit.row_hi, hit.edge_lo, hit.edge_hi = lo, hi, a, b
+            self._slices[key] = hit
+        return hit
 
     def transposed(self):
         if self._t is None:
@@ -855,6 +870,109 @@ class _EdgeMlp(torch.autograd.Function):
 def edge_mlp(y, x, plan: GraphPlan, alpha, params):
     """Fused edge weights (see _EdgeMlp); `params` = [W1, b1, Wh0, bh0, (Wh1, bh1,) Wo, bo]."""
     return _EdgeMlp.apply(y, x, plan, alpha, *params)
+
+
+# ---- edge-sharded evaluation of the (batch-independent) edge weights under data parallelism --------------------------------
+# Data parallelism replicates everything that does not depend on the sample - above all the edge-weight MLP over all E edges,
+# forward and backward.  With a small per-GPU batch and a large mesh (BASELINE configs[4]: 262 k points, global batch 8) that
+# replicated work IS the step.  Sharding it by DESTINATION ROW: rank r owns 1 / world of the rows of a MAGNO graph (latent
+# tokens in the encoder, query points in the decoder) for ALL samples of the global batch - it evaluates the edge-weight MLP,
+# the gather / reduce and their backward for the edges of its rows only.  Samples are exchanged twice per operator, on
+# activations that are small next to the [E, C] edge tensors: an all-gather of the operator's input over the batch and an
+# all-to-all that turns (all samples, my rows) into (my samples, all rows); the backward runs the inverse exchanges
+# (reduce-scatter / all-to-all).  Parameter gradients produced this way are partial per rank and are completed by the gradient
+# all-reduce of the step, which sums over ranks anyway.
+SHARD_EDGES_MIN = 1 << 18          # edges from which sharding pays
+_shard_group = None                # None: sharding off; set by enable_edge_sharding(process_group)
+
+
+def enable_edge_sharding(group=True):
+    """Switch the edge-sharded evaluation on (group=True: the default process group) or off (None / False)."""
+    global _shard_group
+    _shard_group = group if group else None
+
+
+def edge_shard_world():
+    import torch.distributed as dist
+    if _shard_group is None or not dist.is_available() or not dist.is_initialized():
+        return 1, 0, None
+    grp = None if _shard_group is True else _shard_group
+    return dist.get_world_size(grp), dist.get_rank(grp), grp
+
+
+def _all_gather_rows(out, x, group):
+    import torch.distributed as dist
+    if dist.get_backend(group) == "nccl":
+        dist.all_gather_into_tensor(out, x, group=group)
+    else:                                                  # gloo (CPU tests of the host logic)
+        dist.all_gather(list(out.chunk(dist.get_world_size(group), 0)), x, group=group)
+
+
+def _reduce_scatter_rows(out, g, group):
+    import torch.distributed as dist
+    if dist.get_backend(group) == "nccl":
+        dist.reduce_scatter_tensor(out, g, op=dist.ReduceOp.SUM, group=group)
+    else:
+        tmp = g.clone()
+        dist.all_reduce(tmp, op=dist.ReduceOp.SUM, group=group)
+        out.copy_(tmp.chunk(dist.get_world_size(group), 0)[dist.get_rank(group)])
+
+
+class _AllGatherBatch(torch.autograd.Function):
+    """x [Bl, ...] of every rank -> [world * Bl, ...] in rank order; backward: reduce-scatter (sum over ranks) of the gradient."""
+
+    @staticmethod
+    def forward(ctx, x, group):
+        import torch.distributed as dist
+        world = dist.get_world_size(group)
+        out = torch.empty((world * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+        _all_gather_rows(out, x.contiguous(), group)
+        ctx.group = group
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        import torch.distributed as dist
+        world = dist.get_world_size(ctx.group)
+        out = torch.empty((g.shape[0] // world,) + tuple(g.shape[1:]), dtype=g.dtype, device=g.device)
+        _reduce_scatter_rows(out, g.contiguous(), ctx.group)
+        return out, None
+
+
+def _exchange(x, group):
+    import torch.distributed as dist
+    out = torch.empty_like(x)
+    dist.all_to_all_single(out, x, group=group)
+    return out
+
+
+class _RowsToSamples(torch.autograd.Function):
+    """[world * Bl, rows_s, C] (ALL samples, MY destination rows) -> [Bl, world * rows_s, C] (MY samples, ALL rows): one
+    all-to-all over NVLink; the backward is the inverse exchange."""
+
+    @staticmethod
+    def forward(ctx, x, group):
+        import torch.distributed as dist
+        world = dist.get_world_size(group)
+        Bg, rows_s, C = x.shape
+        Bl = Bg // world
+        got = _exchange(x.contiguous(), group).view(world, Bl, rows_s, C)          # [source rank = row block, my samples, rows, C]
+        ctx.group, ctx.dims = group, (world, Bl, rows_s, C)
+        return got.permute(1, 0, 2, 3).reshape(Bl, world * rows_s, C)
+
+    @staticmethod
+    def backward(ctx, g):
+        world, Bl, rows_s, C = ctx.dims
+        send = g.view(Bl, world, rows_s, C).permute(1, 0, 2, 3).contiguous()         # [row block, my samples, rows, C]
+        return _exchange(send.view(world * Bl, rows_s, C), ctx.group), None
+
+
+def all_gather_batch(x, group):
+    return _AllGatherBatch.apply(x, group)
+
+
+def rows_to_samples(x, group):
+    return _RowsToSamples.apply(x, group)
 
 
 class _ScaleRows(torch.autograd.Function):

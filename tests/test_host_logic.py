@@ -286,7 +286,7 @@ def test_train_step_flat_buffers_and_adamw():
         assert rel_l2(t, p[k]) < 1e-5, k
 
 
-def _dp_worker(rank, world, port, q):
+def _dp_worker(rank, world, port, q, row_shard=False):
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -295,7 +295,11 @@ def _dp_worker(rank, world, port, q):
     c = cases.CASES[name]
     g = load_golden(name)
     with abi_emulator.install():
+        from gaot_b200 import ops
         from gaot_b200.trainer import TrainStep
+        if row_shard:                                     # MAGNO rows sharded over the ranks (ops.enable_edge_sharding)
+            ops.SHARD_EDGES_MIN = 1
+            ops.enable_edge_sharding(True)
         model = build_model(c, "cpu")
         sd = golden_params(g)
         if rank != 0:                                     # replicas must be re-synchronised from rank 0
@@ -312,13 +316,16 @@ def _dp_worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-def test_data_parallel_step_equals_single_process_gloo():
-    """world_size 2 over gloo: sample-sharded step (sum all-reduce, 1/world in AdamW) == full-batch step."""
+@pytest.mark.parametrize("row_shard", [False, True])
+def test_data_parallel_step_equals_single_process_gloo(row_shard):
+    """world_size 2 over gloo: sample-sharded step (sum all-reduce, 1/world in AdamW) == full-batch step; with row_shard the
+    MAGNO operators additionally run row-sharded (every rank owns half of the latent / query rows for both ranks' samples:
+    all-gather in, all-to-all out, inverse exchanges in the backward, partial parameter gradients summed by the all-reduce)."""
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + os.getpid() % 2000
-    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, q)) for r in range(2)]
+    port = 29500 + (os.getpid() + 7 * int(row_shard)) % 2000
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, q, row_shard)) for r in range(2)]
     for p in procs:
         p.start()
     sd_dp, _ = q.get(timeout=300)
