@@ -520,6 +520,8 @@ def run_ours(args, w):
     else:
         B = args.batch or w["B"]
     peaks = load_peaks()
+    if strong and world > 1 and not args.no_row_shard:
+        _ops.enable_edge_sharding(True)            # MAGNO rows sharded over the ranks (see gaot_b200/ops.py)
     case = Case(D, w, B, args.precision, use_graph=not args.no_graph, fresh_meshes=args.fresh_meshes if w.get("vx") else 0)
     step, graphed = case.step, case.graphed
     pn_h, tgt_h = case.pn.pin_memory(), case.tgt.pin_memory()
@@ -590,7 +592,8 @@ def run_ours(args, w):
         "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
         "config": {"workload": args.workload, "precision": args.precision, "desc": w["desc"], "batch_per_gpu": B,
                    "global_batch": B * world, "points": w["n"], "latent_tokens": M, "edges": E, "params": step.num_params,
-                   "parallelism": f"dp{world}", "cuda_graph": graphed is not None,
+                   "parallelism": f"dp{world}" + ("+magno-rows-sharded" if _ops.edge_shard_world()[0] > 1 else ""),
+                   "cuda_graph": graphed is not None,
                    "vx_fresh_mesh_batches": len(case.rotate) if case.vx else None,
                    "l2": f"no flush between steps: one step allocates {step_bytes / 1e6:.0f} MB of activations / workspaces "
                          f"(measured), {step_bytes / max(l2_bytes, 1):.0f}x the {l2_bytes / 1e6:.0f} MB L2"},
@@ -747,6 +750,8 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="strong: --global-batch samples are sharded over the ranks (BASELINE configs[4]: cfg5, global batch 8)")
     ap.add_argument("--global-batch", type=int, default=0)
+    ap.add_argument("--no-row-shard", action="store_true",
+                    help="strong scaling: plain data parallelism (edge-weight MLP replicated) instead of row-sharded MAGNO")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fp32-leg", action="store_true", help="skip the extra fp32-parity-mode timing")
     ap.add_argument("--no-roofline", action="store_true", help="skip the isolated kernel timings")
