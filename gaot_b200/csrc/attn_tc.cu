@@ -25,8 +25,6 @@
 namespace {
 
 constexpr int AT_THREADS = 320;           // forward: TMA warp, MMA warp, 8 softmax warps (2 per TMEM lane quadrant)
-constexpr int AT_BWD_CW = 16;            // compute warps of the backward kernel (4 per TMEM lane quadrant)
-constexpr int AT_BWD_THREADS = 64 + 32 * AT_BWD_CW;   // + TMA warp, MMA warp
 constexpr int AT_BQ = 128, AT_BKV = 128;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -59,6 +57,11 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
                  ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
+// shared tile -> global, element-wise fp32 add (TMA reduce; completion tracked by the issuing thread's bulk groups)
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -68,6 +71,14 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_c, uint64_t da, uint64_t 
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_c), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+// A operand read from tensor memory ([lanes = M rows] x [K elements, two 16-bit values per 32-bit column]), B from shared memory
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_c, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_c), "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
 }
 // shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp): rows of ROWB bytes, swizzle span == ROWB,
 // 8-row atoms SBO bytes apart; layout code 2 = SWIZZLE_128B, 4 = SWIZZLE_64B, 6 = SWIZZLE_32B
@@ -246,6 +257,12 @@ __device__ __forceinline__ void tmem_stN(uint32_t taddr, const uint32_t (&r)[N])
     }
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
+// tcgen05.st of 8 consecutive columns, issue only (pair with tmem_wait_st)
+__device__ __forceinline__ void tmem_st8_issue(uint32_t taddr, const uint32_t (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ float lds_f32(uint32_t a) {
     float v;
     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
@@ -575,43 +592,76 @@ struct AttnBwdArgs {
 // SPLIT (HD <= 32): every tile exists as a hi and a lo plane, so the P^T / dS^T tiles are single-buffered and Q / dO go
 // through a 2-stage ring; with the per-warp statistics slab shrunk to one slab per column group and step parity the tile
 // set is exactly the 227 KB a CTA may use.
-template <int HD, bool SPLIT> struct AttnBwdCfg {
+//
+// QW = queries per step.  128: one CTA per SM (TMEM 2 x 128 + 4 HD columns), 16 compute warps.  64 (bf16, HD <= 32): the
+// step is 128 keys x 64 queries, TMEM 2 x 64 + 4 HD = 256 columns and 106 KB of tiles, so TWO CTAs of 8 compute warps share
+// an SM and one CTA's exponentials run under the other's MMA / TMEM / reduction latencies; the dQ product then has M = 64.
+template <int HD, bool SPLIT, int QW> struct AttnBwdCfg {
+    static_assert(QW == 128 || (QW == 64 && !SPLIT && HD <= 32), "64-query steps: bf16, head dimension <= 32");
+    static constexpr int CW = QW / 8;                                // compute warps: QW / 32 column groups x 4 TMEM lane quadrants
+    static constexpr int THREADS = 64 + 32 * CW;                     // + TMA warp, MMA warp
     static constexpr int NPL = SPLIT ? 2 : 1;
     static constexpr int NQ = SPLIT ? 2 : (HD <= 32 ? 3 : 2);        // Q / dO stages
     static constexpr int NBUF = SPLIT ? 1 : (HD <= 32 ? 2 : 1);      // P^T / dS^T buffers (hd = 64: shared memory allows one)
-    static constexpr int PLANE_BYTES = 128 * HD * 2;
+    static constexpr int PLANE_BYTES = 128 * HD * 2;                 // K / V tile (128 keys)
     static constexpr int TILE_BYTES = NPL * PLANE_BYTES;
-    static constexpr int PP_BYTES = 128 * 128 * 2;
+    static constexpr int QPLANE_BYTES = QW * HD * 2;                 // Q / dO tile (QW queries)
+    static constexpr int QTILE_BYTES = NPL * QPLANE_BYTES;
+    static constexpr int PP_BYTES = 128 * QW * 2;                    // P^T / dS^T tile: 128 keys x QW queries
     static constexpr int PT_BYTES = NPL * PP_BYTES;
-    static constexpr int STAT_BYTES = SPLIT ? 2048 : 4096;
-    static constexpr int SMEM = (2 + 2 * NQ) * TILE_BYTES + 2 * NBUF * PT_BYTES + STAT_BYTES + 256 + (SPLIT ? 768 : 1024);
-    static_assert(SMEM <= 227 * 1024, "backward attention tile set exceeds shared memory");
+    static constexpr int STAT_BYTES = SPLIT ? 2048 : CW * 256;
+    // TPT (bf16, HD <= 32): P^T is handed to the dV product as a TENSOR-MEMORY A operand (tcgen05.st, QW/2 packed columns)
+    // instead of a shared-memory tile; TDS (128-query steps, where the columns exist): dS^T likewise for the dK product - it
+    // still goes to shared memory as well, for the transposed read of the dQ product.  The kernel is bound by the
+    // shared-memory data pipe (LSU wavefronts + MMA operand fetches); per 128 x 128 scores this removes 32 KB of stores and
+    // 32 (64 with TDS) KB of operand fetches.
+    static constexpr bool TPT = !SPLIT && HD <= 32;
+    static constexpr bool TDS = TPT && QW == 128;
+    static constexpr bool DQ1 = QW == 64;                            // one dQ accumulator (TMEM columns), drained before the next emit
+    static constexpr int ND = DQ1 ? 1 : 2;
+    static constexpr bool TRED = TPT;                                // dQ tiles leave through one TMA reduction per step
+    static constexpr int NBUF_P = TPT ? 0 : NBUF;                    // shared-memory P^T buffers
+    static constexpr int DQ_BYTES = TRED ? QW * HD * 4 : 0;          // fp32 dQ tile staged for the TMA reduction
+    static constexpr int SMEM = 2 * TILE_BYTES + 2 * NQ * QTILE_BYTES + (NBUF_P + NBUF) * PT_BYTES + DQ_BYTES + STAT_BYTES + 256 + (SPLIT ? 768 : 1024);
+    static constexpr uint32_t TMEM_COLS = QW == 64 ? 256 : 512;
+    static constexpr int CTAS = QW == 64 ? 2 : 1;                    // CTAs per SM
+    static_assert(SMEM <= 227 * 1024 / CTAS - (CTAS - 1) * 1024, "backward attention tile set exceeds shared memory");
+    static constexpr int ACC0 = 2 * QW + (TPT ? QW / 2 : 0) + (TDS ? QW / 2 : 0);   // first accumulator column
+    static_assert(ACC0 + (2 + ND) * HD <= (int)TMEM_COLS, "backward attention accumulators exceed the TMEM allocation");
 };
 constexpr float AT_PSCALE_BWD = 16384.f;               // P <= 1 in the backward (true row statistics): P * 2^14 = hi + lo
 
-template <int HD, bool SPLIT>
-__global__ void __launch_bounds__(AT_BWD_THREADS, 1)
-attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUtensorMap tmdo, const AttnBwdArgs g) {
-    using Cfg = AttnBwdCfg<HD, SPLIT>;
+// tm: qkv with a 128-row box (K / V tiles); tmq, tmdo: qkv and dO with a QW-row box (Q / dO tiles); tmacc (QW = 64): the
+// fp32 dQ accumulator [B*T, H*hd] with a {hd, 64} box, swizzle span = hd * 4 bytes
+template <int HD, bool SPLIT, int QW>
+__global__ void __launch_bounds__((AttnBwdCfg<HD, SPLIT, QW>::THREADS), (AttnBwdCfg<HD, SPLIT, QW>::CTAS))
+attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUtensorMap tmq,
+                   const __grid_constant__ CUtensorMap tmdo, const __grid_constant__ CUtensorMap tmacc, const AttnBwdArgs g) {
+    using Cfg = AttnBwdCfg<HD, SPLIT, QW>;
     constexpr int ROWB = HD * 2;
     constexpr int TILE_BYTES = Cfg::TILE_BYTES;
     constexpr int PLANE_BYTES = Cfg::PLANE_BYTES;
+    constexpr int QTILE_BYTES = Cfg::QTILE_BYTES;
+    constexpr int QPLANE_BYTES = Cfg::QPLANE_BYTES;
     constexpr int PT_BYTES = Cfg::PT_BYTES;
     constexpr int PP_BYTES = Cfg::PP_BYTES;
-    constexpr int NQ = Cfg::NQ, NBUF = Cfg::NBUF;
+    constexpr int NQ = Cfg::NQ, NBUF = Cfg::NBUF, CW = Cfg::CW;
+    constexpr bool TPT = Cfg::TPT, TDS = Cfg::TDS, TRED = Cfg::TRED;
+    constexpr int ND = Cfg::ND;
     constexpr int NTERM = SPLIT ? 3 : 1;               // SPLIT terms, small to large: (A lo, B hi), (A hi, B lo), (A hi, B hi)
-    constexpr uint32_t TMEM_COLS = 512;      // S^T [0,128) dP^T [128,256) dV [256,..) dK [256+HD,..) dQ[2] [256+2HD,..)
+    constexpr uint32_t TMEM_COLS = Cfg::TMEM_COLS;     // S^T [0,QW) dP^T [QW,2QW) dV [2QW,..) dK [2QW+HD,..) dQ[2] [2QW+2HD,..)
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* sK = smem;
     uint8_t* sV = sK + TILE_BYTES;
     uint8_t* sQ = sV + TILE_BYTES;           // [NQ stages]
-    uint8_t* sG = sQ + NQ * TILE_BYTES;      // dO, [NQ stages]
-    uint8_t* sPt = sG + NQ * TILE_BYTES;     // [NBUF]
-    uint8_t* sSt = sPt + NBUF * PT_BYTES;    // [NBUF]
+    uint8_t* sG = sQ + NQ * QTILE_BYTES;     // dO, [NQ stages]
+    uint8_t* sPt = sG + NQ * QTILE_BYTES;    // [NBUF]
+    uint8_t* sSt = sPt + Cfg::NBUF_P * PT_BYTES;   // [NBUF]
     // statistics slabs [lse2 x 32 | delta x 32]: one per compute warp, or (SPLIT) one per column group and step parity,
     // shared by the four warps of the group (they write identical values)
-    float* sStat = reinterpret_cast<float*>(sSt + NBUF * PT_BYTES);
+    uint8_t* sDq = sSt + NBUF * PT_BYTES;    // QW = 64: fp32 dQ tile [64 queries][HD], rows swizzled like the tensor map
+    float* sStat = reinterpret_cast<float*>(sDq + Cfg::DQ_BYTES);
     uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sStat) + Cfg::STAT_BYTES);
     if (SPLIT && (uintptr_t)(smem - smem_raw) > 768) __trap();      // the split tile set leaves 768 bytes of alignment slack
     uint64_t* kv_bar = bars;
@@ -622,13 +672,16 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
     uint64_t* pds_full = bars + 9;   // [2]    8 warp arrivals: P^T / dS^T buffer written
     uint64_t* done = bars + 11;      // [2]    DVKQ(i) complete: dQ[i & 1] ready, P^T / dS^T buffer free
     uint64_t* dq_empty = bars + 13;  // [2]    8 warp arrivals: dQ[i & 1] drained
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+    uint64_t* stage_full = bars + 15; //       CW warp arrivals: the dQ tile is staged in shared memory
+    uint64_t* stage_free = bars + 16; //       the TMA reduction has read the staged tile
+    uint64_t* pt_free = bars + 17;    //       TPT: the dV / dK products of a step have read P^T / dS^T from tensor memory
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int k0 = blockIdx.x * 128, hk = blockIdx.y, b = blockIdx.z;
     const int rep = g.H / g.Hkv;
     const int row_base = b * g.T;
-    const int n_qt = (g.T + 127) / 128;
+    const int n_qt = (g.T + QW - 1) / QW;
     const int n_steps = rep * n_qt;
 #ifdef EXP_TRACE
     // compute warp 2 lane 0 -> slots [0,64), MMA warp lane 0 -> slots [64,128) of CTA (0,0,z)
@@ -640,8 +693,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
     if (threadIdx.x == 0) {
         mbar_init(kv_bar, 1);
         for (int s = 0; s < NQ; ++s) { mbar_init(&q_full[s], 1); mbar_init(&q_empty[s], 1); }
-        mbar_init(st_full, 1); mbar_init(st_free, AT_BWD_CW);        // one arrival per compute warp
-        for (int s = 0; s < 2; ++s) { mbar_init(&pds_full[s], AT_BWD_CW); mbar_init(&done[s], 1); mbar_init(&dq_empty[s], AT_BWD_CW); }
+        mbar_init(st_full, 1); mbar_init(st_free, CW);               // one arrival per compute warp
+        for (int s = 0; s < 2; ++s) { mbar_init(&pds_full[s], CW); mbar_init(&done[s], 1); mbar_init(&dq_empty[s], CW); }
+        mbar_init(stage_full, CW); mbar_init(stage_free, 1); mbar_init(pt_free, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -654,37 +708,40 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *tmem_slot;
     TRACE(1);
-    const uint32_t tm_st = tmem, tm_dp = tmem + 128, tm_dv = tmem + 256, tm_dk = tmem + 256 + HD, tm_dq = tmem + 256 + 2 * HD;
+    constexpr uint32_t ACC0 = Cfg::ACC0;   // TPT: P^T (bf16 pairs) in [2QW, 2QW + QW/2); TDS: dS^T in [2QW + QW/2, 3QW)
+    const uint32_t tm_st = tmem, tm_dp = tmem + QW, tm_pt = tmem + 2 * QW, tm_ds = tmem + 2 * QW + QW / 2;
+    const uint32_t tm_dv = tmem + ACC0, tm_dk = tmem + ACC0 + HD, tm_dq = tmem + ACC0 + 2 * HD;
 
     if (warp == 0) {
         if (lane == 0) {
-            auto load = [&](uint8_t* dst, const CUtensorMap* map, uint64_t* bar, int col, int row) {
+            auto load = [&](uint8_t* dst, int plane_bytes, const CUtensorMap* map, uint64_t* bar, int col, int row) {
                 if constexpr (SPLIT) {
                     tma_load_3d(dst, map, bar, col, row, 0);
-                    tma_load_3d(dst + PLANE_BYTES, map, bar, col, row, 1);
+                    tma_load_3d(dst + plane_bytes, map, bar, col, row, 1);
                 } else {
                     tma_load_2d(dst, map, bar, col, row);
                 }
             };
             mbar_expect_tx(kv_bar, 2 * TILE_BYTES);
-            load(sK, &tm, kv_bar, g.koff + hk * HD, row_base + k0);
-            load(sV, &tm, kv_bar, g.voff + hk * HD, row_base + k0);
+            load(sK, PLANE_BYTES, &tm, kv_bar, g.koff + hk * HD, row_base + k0);
+            load(sV, PLANE_BYTES, &tm, kv_bar, g.voff + hk * HD, row_base + k0);
             int s = 0, use = 0, hq = 0, qt = 0;
             for (int i = 0; i < n_steps; ++i) {
                 mbar_wait(&q_empty[s], ((uint32_t)use & 1u) ^ 1u);
-                mbar_expect_tx(&q_full[s], 2 * TILE_BYTES);
-                load(sQ + s * TILE_BYTES, &tm, &q_full[s], (hk * rep + hq) * HD, row_base + qt * 128);
-                load(sG + s * TILE_BYTES, &tmdo, &q_full[s], (hk * rep + hq) * HD, row_base + qt * 128);
+                mbar_expect_tx(&q_full[s], 2 * QTILE_BYTES);
+                load(sQ + s * QTILE_BYTES, QPLANE_BYTES, &tmq, &q_full[s], (hk * rep + hq) * HD, row_base + qt * QW);
+                load(sG + s * QTILE_BYTES, QPLANE_BYTES, &tmdo, &q_full[s], (hk * rep + hq) * HD, row_base + qt * QW);
                 if (++s == NQ) { s = 0; ++use; }
                 if (++qt == n_qt) { qt = 0; ++hq; }
             }
         }
     } else if (warp == 1) {
-        constexpr uint32_t BASE = (1u << 4) | (SPLIT ? 0u : ((1u << 7) | (1u << 10))) | ((uint32_t)(128 >> 4) << 24);   // fp16 planes when SPLIT
-        constexpr uint64_t PL = (uint64_t)(PLANE_BYTES >> 4), PPL = (uint64_t)(PP_BYTES >> 4);   // lo-plane offsets in descriptor units
-        constexpr uint32_t IDESC_ST = BASE | ((uint32_t)(128 >> 3) << 17);                           // N=128, K-major x K-major
+        constexpr uint32_t FMT = (1u << 4) | (SPLIT ? 0u : ((1u << 7) | (1u << 10)));                // fp16 planes when SPLIT
+        constexpr uint32_t BASE = FMT | ((uint32_t)(128 >> 4) << 24);                                // M = 128 keys
+        constexpr uint64_t PL = (uint64_t)(PLANE_BYTES >> 4), QPL = (uint64_t)(QPLANE_BYTES >> 4), PPL = (uint64_t)(PP_BYTES >> 4);   // lo-plane offsets in descriptor units
+        constexpr uint32_t IDESC_ST = BASE | ((uint32_t)(QW >> 3) << 17);                            // N=QW, K-major x K-major
         constexpr uint32_t IDESC_KN = BASE | (1u << 16) | ((uint32_t)(HD >> 3) << 17);               // N=HD, B MN-major
-        constexpr uint32_t IDESC_MN = BASE | (1u << 15) | (1u << 16) | ((uint32_t)(HD >> 3) << 17);  // A and B MN-major
+        constexpr uint32_t IDESC_MN = FMT | ((uint32_t)(QW >> 4) << 24) | (1u << 15) | (1u << 16) | ((uint32_t)(HD >> 3) << 17);  // M=QW queries, A and B MN-major
         mbar_wait(kv_bar, 0);
         const uint64_t d_k = make_desc<ROWB>(smem_u32(sK)), d_v = make_desc<ROWB>(smem_u32(sV));
         auto issue_st = [&](int i) {
@@ -692,17 +749,17 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
             mbar_wait(&q_full[s], (uint32_t)(i / NQ) & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (lane == 0) {
-                const uint64_t dq = make_desc<ROWB>(smem_u32(sQ + s * TILE_BYTES)), dg = make_desc<ROWB>(smem_u32(sG + s * TILE_BYTES));
+                const uint64_t dq = make_desc<ROWB>(smem_u32(sQ + s * QTILE_BYTES)), dg = make_desc<ROWB>(smem_u32(sG + s * QTILE_BYTES));
 #pragma unroll
                 for (int t = 0; t < NTERM; ++t) {
-                    const uint64_t pa = (SPLIT && t == 0) ? PL : 0, pb = (SPLIT && t == 1) ? PL : 0;
+                    const uint64_t pa = (SPLIT && t == 0) ? PL : 0, pb = (SPLIT && t == 1) ? QPL : 0;
 #pragma unroll
                     for (int k = 0; k < HD / 16; ++k)
                         umma_f16(tm_st, d_k + pa + (uint64_t)(2 * k), dq + pb + (uint64_t)(2 * k), IDESC_ST, (t > 0 || k > 0) ? 1u : 0u);
                 }
 #pragma unroll
                 for (int t = 0; t < NTERM; ++t) {
-                    const uint64_t pa = (SPLIT && t == 0) ? PL : 0, pb = (SPLIT && t == 1) ? PL : 0;
+                    const uint64_t pa = (SPLIT && t == 0) ? PL : 0, pb = (SPLIT && t == 1) ? QPL : 0;
 #pragma unroll
                     for (int k = 0; k < HD / 16; ++k)
                         umma_f16(tm_dp, d_v + pa + (uint64_t)(2 * k), dg + pb + (uint64_t)(2 * k), IDESC_ST, (t > 0 || k > 0) ? 1u : 0u);
@@ -720,30 +777,54 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
                 issue_st(i + 1);
             }
             TRACE(4 + 4 * i);
-            const int s = i % NQ, bf = i % NBUF, d = i & 1;
+            const int s = i % NQ, bf = i % NBUF, d = i % ND;
             mbar_wait(&pds_full[bf], (uint32_t)(i / NBUF) & 1u);
-            if (i >= 2) mbar_wait(&dq_empty[d], (uint32_t)((i - 2) >> 1) & 1u);   // dQ[d] of step i-2 drained from TMEM
+            if constexpr (!Cfg::DQ1) {
+                if (i >= ND) mbar_wait(&dq_empty[d], (uint32_t)((i - ND) / ND) & 1u);   // dQ[d] of step i-ND drained from TMEM
+            }
             TRACE(5 + 4 * i);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (lane == 0) {
                 // all descriptors = per-step base + compile-time offset (16-byte units in the start-address field)
-                const uint64_t d_q = make_desc<ROWB>(smem_u32(sQ + s * TILE_BYTES)), d_g = make_desc<ROWB>(smem_u32(sG + s * TILE_BYTES));
+                const uint64_t d_q = make_desc<ROWB>(smem_u32(sQ + s * QTILE_BYTES)), d_g = make_desc<ROWB>(smem_u32(sG + s * QTILE_BYTES));
                 const uint32_t pst = smem_u32(sSt + bf * PT_BYTES);
                 const uint64_t d_pt = make_desc<128>(smem_u32(sPt + bf * PT_BYTES)), d_st = make_desc<128>(pst);
                 const uint32_t acc_first = i > 0 ? 1u : 0u;
+                if constexpr (TPT) {
+#pragma unroll
+                    for (int k = 0; k < QW / 16; ++k) {   // A: 16 queries = 8 packed tensor-memory columns
+                        const uint64_t boff = (uint64_t)((k * 16 * ROWB) >> 4);
+                        umma_f16_ts(tm_dv, tm_pt + (uint32_t)(k * 8), d_g + boff, IDESC_KN, k > 0 ? 1u : acc_first);
+                        if constexpr (TDS) umma_f16_ts(tm_dk, tm_ds + (uint32_t)(k * 8), d_q + boff, IDESC_KN, k > 0 ? 1u : acc_first);
+                    }
+                    umma_commit(pt_free);
+                    if constexpr (!TDS) {
+#pragma unroll
+                        for (int k = 0; k < QW / 16; ++k)
+                            umma_f16(tm_dk, d_st + (uint64_t)(((k >> 2) * (128 * 128) + (k & 3) * 32) >> 4), d_q + (uint64_t)((k * 16 * ROWB) >> 4),
+                                     IDESC_KN, k > 0 ? 1u : acc_first);
+                    }
+                } else {
 #pragma unroll
                 for (int t = 0; t < NTERM; ++t) {
-                    const uint64_t pa = (SPLIT && t == 0) ? PPL : 0, pb = (SPLIT && t == 1) ? PL : 0;
+                    const uint64_t pa = (SPLIT && t == 0) ? PPL : 0, pb = (SPLIT && t == 1) ? QPL : 0;
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) {      // contraction over 128 queries, 16 per MMA
+                    for (int k = 0; k < QW / 16; ++k) {   // contraction over the QW queries, 16 per MMA
                         const uint64_t aoff = pa + (uint64_t)(((k >> 2) * (128 * 128) + (k & 3) * 32) >> 4);
                         const uint64_t boff = pb + (uint64_t)((k * 16 * ROWB) >> 4);
                         umma_f16(tm_dv, d_pt + aoff, d_g + boff, IDESC_KN, (t > 0 || k > 0) ? 1u : acc_first);
                         umma_f16(tm_dk, d_st + aoff, d_q + boff, IDESC_KN, (t > 0 || k > 0) ? 1u : acc_first);
                     }
                 }
+                }
+                if constexpr (Cfg::DQ1) {                   // single dQ accumulator: step i-1 must have been drained (the dV / dK
+                    if (i >= 1) {                           // products above are already queued on the tensor pipe)
+                        mbar_wait(&dq_empty[0], (uint32_t)(i - 1) & 1u);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    }
+                }
                 // dQ[q, :] = sum_keys dS^T[key, q] K[key, :]: A = the dS^T tile as an MN-major operand
-                // (M = 128 queries = two 64-wide swizzle atoms LBO = 16 KB apart, 8-key groups SBO = 1 KB apart)
+                // (M = QW queries = 64-wide swizzle atoms LBO = 16 KB apart, 8-key groups SBO = 1 KB apart)
                 const uint64_t a_mn0 = (uint64_t)((pst & 0x3FFFF) >> 4) | ((uint64_t)(16384 >> 4) << 16) |
                                        ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 #pragma unroll
@@ -760,10 +841,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
             __syncwarp();
         }
     } else {
-        // 16 compute warps: warps w, w+4, w+8, w+12 share TMEM lane quadrant w%4 (the hardware restricts a warp to
-        // the lanes 32*(w%4)..+31) and split the columns: `qr` 0..3 owns query columns [32*qr, 32*qr+32) of S^T / dP^T
-        // (= half of a 64-column swizzle block of the P^T / dS^T tiles) and a quarter of the dQ / dV / dK columns.
-        constexpr int NC = HD / 4;                         // dQ / dV / dK columns per thread
+        // CW compute warps: warps w, w+4, .. share TMEM lane quadrant w%4 (the hardware restricts a warp to the lanes
+        // 32*(w%4)..+31) and split the columns: `qr` owns query columns [32*qr, 32*qr+32) of S^T / dP^T (= half of a
+        // 64-column swizzle block of the P^T / dS^T tiles) and a 4/CW share of the dQ / dV / dK columns.
+        constexpr int NC = HD / (CW / 4);                  // dQ / dV / dK columns per thread
         const int q4 = warp & 3, qr = (warp - 2) >> 2;
         const int r = q4 * 32 + lane;                      // key row for S^T.., query row for dQ
         const uint32_t lane_addr = (uint32_t)(q4 * 32) << 16;
@@ -790,15 +871,16 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
         const float* del_b = g.delta + (int64_t)b * g.H * g.T;
         float st_l, st_d;
         auto fetch_stat = [&](int h, int qt) {
-            const int q = qt * 128 + qr * 32 + lane;
+            const int q = qt * QW + qr * 32 + lane;
             const int64_t off = (int64_t)h * g.T + q;
             st_l = ldg_f32_pred(lse_b + off, q < g.T, INFINITY);           // +inf switches a query column off
             st_d = ldg_f32_pred(del_b + off, q < g.T, 0.f);
         };
-        // dQ of a finished step: here the TMEM lane is the QUERY row; this warp's quarter of the HD columns
+        // dQ of a finished step: here the TMEM lane is the QUERY row; this warp's share of the HD columns.  QW = 64: an
+        // M = 64 accumulator keeps row m in lane 32 * (m / 16) + m % 16, i.e. the lower half of each warp's lanes
         auto drain_dq = [&](int j, int h, int qt) {
-            const int t = qt * 128 + r, d = j & 1;
-            mbar_wait(&done[d], (uint32_t)(j >> 1) & 1u);
+            const int t = QW == 64 ? (lane < 16 ? qt * QW + q4 * 16 + lane : g.T) : qt * QW + r, d = j % ND;
+            mbar_wait(&done[d], (uint32_t)(j / ND) & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             uint32_t v[NC];
             tmem_ld_issue<NC>(tm_dq + d * HD + lane_addr + qr * NC, v);
@@ -806,7 +888,47 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(&dq_empty[d]);
+            if constexpr (TRED) {
+                // the tile goes to global memory as ONE TMA reduction (a per-thread red.add touches a different 128-byte
+                // line in every lane: 32 LSU wavefronts per instruction).  Warp 2 issues it once all CW warps have staged
+                // their share, and releases the staging tile at its next drain, when the reduction has read it.
+                constexpr int RB = HD * 4;                               // bytes per staged row = swizzle span
+                const bool issuer = warp == 2;
+                if (j >= 1) {
+                    if (issuer && lane == 0) {
+                        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                        mbar_arrive(stage_free);
+                    }
+                    mbar_wait(stage_free, (uint32_t)(j - 1) & 1u);
+                }
+                if (QW == 128 || lane < 16) {
+                    const uint32_t rr = (uint32_t)(QW == 64 ? q4 * 16 + lane : r);
+#pragma unroll
+                    for (int j4 = 0; j4 < NC; j4 += 4) {
+                        uint32_t a = rr * RB + (uint32_t)(qr * NC + j4) * 4u;
+                        a ^= ((a >> 7) & (uint32_t)(RB / 16 - 1)) << 4;
+                        sts_u4(smem_u32(sDq) + a, __float_as_uint(__uint_as_float(v[j4]) * f_dqk), __float_as_uint(__uint_as_float(v[j4 + 1]) * f_dqk),
+                               __float_as_uint(__uint_as_float(v[j4 + 2]) * f_dqk), __float_as_uint(__uint_as_float(v[j4 + 3]) * f_dqk));
+                    }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(stage_full);
+                if (issuer) {
+                    mbar_wait(stage_full, (uint32_t)j & 1u);
+                    if (lane == 0) {
+                        tma_reduce_add_2d(&tmacc, sDq, h * HD, row_base + qt * QW);
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                    __syncwarp();
+                }
+                return;
+            }
+#ifdef EXP_NO_RED
+            if (t < 0) {
+#else
             if (t < g.T) {
+#endif
                 float* dst = SPLIT ? reinterpret_cast<float*>(g.dqkv) + (int64_t)(row_base + t) * g.ld + h * HD + qr * NC
                                    : g.dq_acc + ((int64_t)(row_base + t) * g.H + h) * HD + qr * NC;
 #pragma unroll
@@ -820,14 +942,19 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
         // store into each tile
         auto emit = [&](auto full_tag, const uint32_t (&sv)[32], const uint32_t (&dv)[32], uint32_t bp, uint32_t bs) {
             constexpr bool FULL = decltype(full_tag)::value;
+            [[maybe_unused]] uint32_t tp[8], td[8];        // TPT: 16 columns of P^T / dS^T as bf16 pairs -> one tcgen05.st each
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
                 uint32_t pp[4], ds[4];
                 [[maybe_unused]] uint32_t ppl[4], dsl[4];
 #pragma unroll
                 for (int k = 0; k < 8; k += 4) {
+#ifdef EXP_NO_LDS
+                    const float4 lv = make_float4(st_l, st_l, st_l, st_l), dl = make_float4(st_d, st_d, st_d, st_d);
+#else
                     const float4 lv = lds_f4(stat_s + (uint32_t)(j + k) * 4u);              // broadcast reads
                     const float4 dl = lds_f4(stat_s + 128u + (uint32_t)(j + k) * 4u);
+#endif
                     float p0 = ex2(fmaf(__uint_as_float(sv[j + k]), sl2, -lv.x));
                     float p1 = ex2(fmaf(__uint_as_float(sv[j + k + 1]), sl2, -lv.y));
                     float p2 = ex2(fmaf(__uint_as_float(sv[j + k + 2]), sl2, -lv.z));
@@ -850,8 +977,23 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
                     }
                 }
                 const uint32_t off = sw128_off(r, (qr & 1) * 4 + (j >> 3));
+                if constexpr (TPT) {
+                    sts_u4(bs + off, ds[0], ds[1], ds[2], ds[3]);          // dS^T tile: transposed read of the dQ product (and dK without TDS)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) { tp[(j & 8) / 2 + k] = pp[k]; td[(j & 8) / 2 + k] = ds[k]; }
+                    if (j & 8) {
+                        tmem_st8_issue(tm_pt + lane_addr + (uint32_t)(qr * 16 + (j >> 4) * 8), tp);
+                        if constexpr (TDS) tmem_st8_issue(tm_ds + lane_addr + (uint32_t)(qr * 16 + (j >> 4) * 8), td);
+                    }
+                } else {
+#ifdef EXP_NO_STS
+                if (pp[0] == 0x12345u && ds[1] == 0x777u)
+#endif
+                {
                 sts_u4(bp + off, pp[0], pp[1], pp[2], pp[3]);
                 sts_u4(bs + off, ds[0], ds[1], ds[2], ds[3]);
+                }
+                }
                 if constexpr (SPLIT) {
                     sts_u4(bp + PP_BYTES + off, ppl[0], ppl[1], ppl[2], ppl[3]);
                     sts_u4(bs + PP_BYTES + off, dsl[0], dsl[1], dsl[2], dsl[3]);
@@ -895,14 +1037,26 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
             __syncwarp();
             if (lane == 0) mbar_arrive(st_free);           // the MMA warp may overwrite S^T / dP^T with step i+1
             TRACE(4 + 6 * i);
-            if (i >= NBUF) {                                // DVKQ(i - NBUF) has finished reading this P^T / dS^T buffer
-                mbar_wait(&done[(i - NBUF) & 1], (uint32_t)((i - NBUF) >> 1) & 1u);
+            if constexpr (!Cfg::DQ1) {                      // (DQ1: implied by the drain of step i-2, which waited for done(i-2))
+                if (i >= NBUF) {                            // DVKQ(i - NBUF) has finished reading this P^T / dS^T buffer
+                    mbar_wait(&done[(i - NBUF) % ND], (uint32_t)((i - NBUF) / ND) & 1u);
+                }
+            }
+            if constexpr (TPT) {
+                if (i >= 1) {                               // the dV / dK products of step i-1 have read P^T / dS^T from TMEM
+                    mbar_wait(pt_free, (uint32_t)(i - 1) & 1u);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                }
             }
             TRACE(5 + 6 * i);
-            const uint32_t bp = smem_u32(sPt) + (uint32_t)(bf * PT_BYTES + (qr >> 1) * (128 * 128));
+            const uint32_t bp = smem_u32(sPt) + (uint32_t)(bf * PT_BYTES + (qr >> 1) * (128 * 128));   // 64-query swizzle block
             const uint32_t bs = smem_u32(sSt) + (uint32_t)(bf * PT_BYTES + (qr >> 1) * (128 * 128));
             if (tile_full) emit(std::true_type{}, sv, dv, bp, bs);
             else emit(std::false_type{}, sv, dv, bp, bs);
+            if constexpr (TPT) {
+                tmem_wait_st();
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(&pds_full[bf]);
@@ -913,6 +1067,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
             if (++c_qt == n_qt) { c_qt = 0; ++c_h; }
         }
         drain_dq(n_steps - 1, p_h, p_qt);
+        if constexpr (TRED) {
+            if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        }
         TRACE(2 + 6 * n_steps);
         // final: dV and dK rows of this key tile (done[] of the last step has completed: every MMA has retired)
         if constexpr (SPLIT) {
@@ -1075,6 +1232,21 @@ int make_head_map(CUtensorMap* map, const void* base, int64_t rows, int64_t ld, 
     return r == CUDA_SUCCESS ? 0 : GAOT_E_BADARG;
 }
 
+// fp32 [rows, cols] accumulator, box {hd, box_rows}, swizzle span = hd*4 bytes (the staged dQ tile of the backward)
+int make_acc_map(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int hd, int box_rows) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return GAOT_E_BADARG;
+    bind_context_once();
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)cols * 4};
+    cuuint32_t box[2] = {(cuuint32_t)hd, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    const CUtensorMapSwizzle sw = hd == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : GAOT_E_BADARG;
+}
+
 template <int HD, bool SPLIT = false>
 int launch_fwd(const CUtensorMap& tm, const AttnArgs& g, int64_t B, cudaStream_t st) {
     constexpr int SMEM = (SPLIT ? 2 : 1) * (5 * 128 * HD * 2 + 2 * AT_BQ * AT_BKV * 2) + 2048 + 1024 + 256;
@@ -1148,10 +1320,11 @@ namespace {
 template <int HD>
 int launch_bwd_split(const CUtensorMap& tm, const CUtensorMap& tmdo, const AttnBwdArgs& g, const float* o, const float* dout,
                      float* delta, int64_t B, cudaStream_t st) {
-    constexpr int SMEM = AttnBwdCfg<HD, true>::SMEM;
+    using Cfg = AttnBwdCfg<HD, true, 128>;
+    constexpr int SMEM = Cfg::SMEM;
     static bool done = false;
     if (!done) {
-        GAOT_CHECK(cudaFuncSetAttribute(attn_bwd_tc_kernel<HD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+        GAOT_CHECK(cudaFuncSetAttribute(attn_bwd_tc_kernel<HD, true, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
         done = true;
     }
     const int64_t rows = B * g.T;
@@ -1159,18 +1332,19 @@ int launch_bwd_split(const CUtensorMap& tm, const CUtensorMap& tmdo, const AttnB
     // dQ is reduced into the query columns of dqkv by several key tiles: zero them first
     GAOT_CHECK(cudaMemset2DAsync(g.dqkv, sizeof(float) * (size_t)g.ld, 0, sizeof(float) * (size_t)(g.H * HD), (size_t)rows, st));
     dim3 grid((unsigned)((g.T + 127) / 128), (unsigned)g.Hkv, (unsigned)B);
-    attn_bwd_tc_kernel<HD, true><<<grid, AT_BWD_THREADS, SMEM, st>>>(tm, tmdo, g);
+    attn_bwd_tc_kernel<HD, true, 128><<<grid, Cfg::THREADS, SMEM, st>>>(tm, tm, tmdo, tm, g);
     GAOT_NOTE_LAUNCHES(1);
     GAOT_RETURN_LAST();
 }
 
-template <int HD>
-int launch_bwd(const CUtensorMap& tm, const CUtensorMap& tmdo, const AttnBwdArgs& g, const void* o, const void* dout,
-               float* delta, int64_t B, cudaStream_t st) {
-    constexpr int SMEM = AttnBwdCfg<HD, false>::SMEM;
+template <int HD, int QW>
+int launch_bwd(const CUtensorMap& tm, const CUtensorMap& tmq, const CUtensorMap& tmdo, const AttnBwdArgs& g, const void* o,
+               const void* dout, float* delta, int64_t B, cudaStream_t st) {
+    using Cfg = AttnBwdCfg<HD, false, QW>;
+    constexpr int SMEM = Cfg::SMEM;
     static bool done = false;
     if (!done) {
-        GAOT_CHECK(cudaFuncSetAttribute(attn_bwd_tc_kernel<HD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+        GAOT_CHECK(cudaFuncSetAttribute(attn_bwd_tc_kernel<HD, false, QW>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
         done = true;
     }
     const int64_t rows = B * g.T;
@@ -1178,7 +1352,12 @@ int launch_bwd(const CUtensorMap& tm, const CUtensorMap& tmdo, const AttnBwdArgs
                                                                      reinterpret_cast<const __nv_bfloat16*>(dout), delta, B, g.T, g.H);
     GAOT_CHECK(cudaMemsetAsync(g.dq_acc, 0, sizeof(float) * (size_t)(rows * g.H * HD), st));
     dim3 grid((unsigned)((g.T + 127) / 128), (unsigned)g.Hkv, (unsigned)B);
-    attn_bwd_tc_kernel<HD, false><<<grid, AT_BWD_THREADS, SMEM, st>>>(tm, tmdo, g);
+    CUtensorMap tmacc = tm;                                  // 128-query steps reduce dQ with red.add: no accumulator map
+    if constexpr (Cfg::TRED) {
+        int rc = make_acc_map(&tmacc, g.dq_acc, rows, (int64_t)g.H * HD, HD, QW);
+        if (rc) return rc;
+    }
+    attn_bwd_tc_kernel<HD, false, QW><<<grid, Cfg::THREADS, SMEM, st>>>(tm, tmq, tmdo, tmacc, g);
     attn_dq_store_kernel<<<gaot_grid(rows * g.H * HD / 4, 256), 256, 0, st>>>(g.dq_acc, reinterpret_cast<__nv_bfloat16*>(g.dqkv), rows,
                                                                             g.H * HD, g.ld);
     GAOT_NOTE_LAUNCHES(2);
@@ -1195,17 +1374,26 @@ GAOT_API int gaot_attention_bwd_bf16(const void* qkv, const void* o, const float
         (reinterpret_cast<uintptr_t>(dqkv) & 15) || (reinterpret_cast<uintptr_t>(dq_acc) & 15) || (reinterpret_cast<uintptr_t>(o) & 15))
         return GAOT_E_ALIGN;
     if (B > 65535 || Hkv > 65535 || B * T > 0x7fffffffLL) return GAOT_E_BADARG;
-    CUtensorMap tm, tmdo;
+    // head dimensions up to 32: 64-query steps, two CTAs per SM (GAOT_B200_ATTN_BWD_QW=128 selects the one-CTA kernel)
+    static const bool wide = [] { const char* e = getenv("GAOT_B200_ATTN_BWD_QW"); return e && atoi(e) == 128; }();
+    const int qw = (hd == 64 || wide) ? 128 : 64;
+    CUtensorMap tm, tmq, tmdo;
     int rc = make_head_map(&tm, qkv, B * T, ld, (int)hd, 128);
     if (rc) return rc;
-    rc = make_head_map(&tmdo, dout, B * T, H * hd, (int)hd, 128);
+    rc = make_head_map(&tmq, qkv, B * T, ld, (int)hd, qw);
+    if (rc) return rc;
+    rc = make_head_map(&tmdo, dout, B * T, H * hd, (int)hd, qw);
     if (rc) return rc;
     AttnBwdArgs g{lse, delta, dq_acc, dqkv, (int)T, (int)H, (int)Hkv, (int)(H * hd), (int)((H + Hkv) * hd), (int)ld, scale,
                   scale * 1.4426950408889634f, nullptr, nullptr};
     cudaStream_t st = (cudaStream_t)stream;
-    if (hd == 16) return launch_bwd<16>(tm, tmdo, g, o, dout, delta, B, st);
-    if (hd == 32) return launch_bwd<32>(tm, tmdo, g, o, dout, delta, B, st);
-    return launch_bwd<64>(tm, tmdo, g, o, dout, delta, B, st);
+    if (qw == 64) {
+        if (hd == 16) return launch_bwd<16, 64>(tm, tmq, tmdo, g, o, dout, delta, B, st);
+        return launch_bwd<32, 64>(tm, tmq, tmdo, g, o, dout, delta, B, st);
+    }
+    if (hd == 16) return launch_bwd<16, 128>(tm, tmq, tmdo, g, o, dout, delta, B, st);
+    if (hd == 32) return launch_bwd<32, 128>(tm, tmq, tmdo, g, o, dout, delta, B, st);
+    return launch_bwd<64, 128>(tm, tmq, tmdo, g, o, dout, delta, B, st);
 }
 
 GAOT_API int gaot_attention_bwd_split(const void* qkv_planes, const float* qscale, const float* o, const float* lse,
