@@ -574,7 +574,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttnArgs g) {
 // ------------------------------------------------------------------------------------------------
 #ifdef EXP_TRACE
 __device__ long long g_trace[64 * 128];
-#define TRACE(slot) do { if (trace_on) g_trace[trace_base + (slot)] = clock64(); } while (0)
+#define TRACE(slot) do { if (trace_on && (slot) < 64) g_trace[trace_base + (slot)] = clock64(); } while (0)
 #else
 #define TRACE(slot) do { } while (0)
 #endif
@@ -734,6 +734,19 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
                 if (++s == NQ) { s = 0; ++use; }
                 if (++qt == n_qt) { qt = 0; ++hq; }
             }
+        } else if (TRED && lane == 1) {
+            // second lane of the producer warp: one TMA reduction per step moves the dQ tile staged by the compute warps
+            // into the fp32 accumulator (off the compute warps' critical path), then hands the staging tile back
+            int hq = 0, qt = 0;
+            for (int j = 0; j < n_steps; ++j) {
+                mbar_wait(stage_full, (uint32_t)j & 1u);
+                tma_reduce_add_2d(&tmacc, sDq, (hk * rep + hq) * HD, row_base + qt * QW);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                mbar_arrive(stage_free);
+                if (++qt == n_qt) { qt = 0; ++hq; }
+            }
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         }
     } else if (warp == 1) {
         constexpr uint32_t FMT = (1u << 4) | (SPLIT ? 0u : ((1u << 7) | (1u << 10)));                // fp16 planes when SPLIT
@@ -890,17 +903,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
             if (lane == 0) mbar_arrive(&dq_empty[d]);
             if constexpr (TRED) {
                 // the tile goes to global memory as ONE TMA reduction (a per-thread red.add touches a different 128-byte
-                // line in every lane: 32 LSU wavefronts per instruction).  Warp 2 issues it once all CW warps have staged
-                // their share, and releases the staging tile at its next drain, when the reduction has read it.
+                // line in every lane: 32 LSU wavefronts per instruction), issued by the producer warp once all CW warps
+                // have staged their share; it hands the staging tile back when the reduction has read it.
                 constexpr int RB = HD * 4;                               // bytes per staged row = swizzle span
-                const bool issuer = warp == 2;
-                if (j >= 1) {
-                    if (issuer && lane == 0) {
-                        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                        mbar_arrive(stage_free);
-                    }
-                    mbar_wait(stage_free, (uint32_t)(j - 1) & 1u);
-                }
+                if (j >= 1) mbar_wait(stage_free, (uint32_t)(j - 1) & 1u);
                 if (QW == 128 || lane < 16) {
                     const uint32_t rr = (uint32_t)(QW == 64 ? q4 * 16 + lane : r);
 #pragma unroll
@@ -914,14 +920,6 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) mbar_arrive(stage_full);
-                if (issuer) {
-                    mbar_wait(stage_full, (uint32_t)j & 1u);
-                    if (lane == 0) {
-                        tma_reduce_add_2d(&tmacc, sDq, h * HD, row_base + qt * QW);
-                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                    }
-                    __syncwarp();
-                }
                 return;
             }
 #ifdef EXP_NO_RED
@@ -1067,9 +1065,6 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
             if (++c_qt == n_qt) { c_qt = 0; ++c_h; }
         }
         drain_dq(n_steps - 1, p_h, p_qt);
-        if constexpr (TRED) {
-            if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-        }
         TRACE(2 + 6 * n_steps);
         // final: dV and dK rows of this key tile (done[] of the last step has completed: every MMA has retired)
         if constexpr (SPLIT) {

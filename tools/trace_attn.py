@@ -19,10 +19,10 @@ for z in (0, 5, 31):
     m = [buf[z * 128 + 64 + k] for k in range(64)]       # MMA warp, 4 slots per step
     t0 = c[0]
     print(f"CTA z={z}: start->alloc {c[1]-t0}, end {c[62]-t0}, after dealloc {c[63]-t0}")
-    for i in range(8):
+    for i in range(9):
         a = [c[2 + 6 * i + k] - t0 for k in range(6)]
         print(f"  step {i}: top {a[0]} st_full+{a[1]-a[0]} ld+free+{a[2]-a[1]} done-wait+{a[3]-a[2]} emit+{a[4]-a[3]} drain+{a[5]-a[4]}")
     print("  final", c[2 + 48] - t0)
-    for i in range(7):
+    for i in range(14):
         a = [m[2 + 4 * i + k] - t0 for k in range(4)]
         print(f"  mma {i}: top {a[0]} st_free-wait+{a[1]-a[0]} issueST+{a[2]-a[1]} pds/dq wait+{a[3]-a[2]}")
