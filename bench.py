@@ -154,9 +154,20 @@ class Dist:
         return float(ms)
 
     def close(self):
+        """Barrier, then tear the process group down.  CUDA graphs that captured NCCL work (the bucketed gradient
+        all-reduces, the row-sharded MAGNO exchanges) must be gone before the communicator is destroyed, so callers drop
+        their captured steps first; a watchdog ends the process if the teardown still blocks (the result line is already out)."""
         if self.world > 1:
+            import gc
+            import threading
+            gc.collect()
+            torch.cuda.synchronize()
             self.dist.barrier()
+            torch.cuda.synchronize()
+            sys.stdout.flush()
+            threading.Timer(20.0, lambda: os._exit(0)).start()
             self.dist.destroy_process_group()
+            os._exit(0)
 
 
 class Case:
@@ -669,7 +680,8 @@ def run_ours(args, w):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_reference(w, steps=2, warmup=1, sample_B=B)
     if rank == 0:
-        print(json.dumps(out))
+        print(json.dumps(out), flush=True)
+    case = graphed = feeder = step = None      # captured steps hold NCCL work: release them before the communicator goes
     D.close()
 
 

@@ -3,9 +3,11 @@
 src/trainer/static_trainer.py:160-202: forward + MSE; src/core/base_trainer.py:71).
 
 B200-native differences: parameters, gradients and both AdamW moments live in four flat fp32
-buffers (one fused optimizer kernel, one all-reduce over the whole gradient); data parallelism is
-one process per GPU with a single NCCL all-reduce of the flat gradient per step (the reference has
-no working DP at all)."""
+buffers (one fused optimizer kernel); data parallelism is one process per GPU, the flat gradient
+is all-reduced in a few contiguous BUCKETS, each launched on a communication stream as soon as
+autograd has produced the last gradient of the bucket, so the reductions run under the rest of
+the backward pass (inside the captured CUDA graph when the step is captured).  The reference has
+no working DP at all."""
 from __future__ import annotations
 
 from typing import Optional
@@ -18,7 +20,8 @@ from . import ops
 
 class TrainStep:
     def __init__(self, model: torch.nn.Module, lr: float = 1e-3, weight_decay: float = 1e-2, betas=(0.9, 0.999),
-                 eps: float = 1e-8, process_group: Optional[dist.ProcessGroup] = None, distributed: Optional[bool] = None):
+                 eps: float = 1e-8, process_group: Optional[dist.ProcessGroup] = None, distributed: Optional[bool] = None,
+                 bucket_bytes: int = 4 << 20):
         self.model = model
         self.lr, self.weight_decay, self.betas, self.eps = lr, weight_decay, betas, eps
         self.group = process_group
@@ -45,8 +48,60 @@ class TrainStep:
             p.grad = None
         self.num_params = n
         self.step_count = 0
+        self._buckets, self._bucket_of, self._pending, self._fired, self._work = [], {}, [], [], []
+        self._comm = None
         if self.distributed and self.world > 1:
             dist.broadcast(self.flat_param, src=0, group=self.group)     # identical replicas
+            self._make_buckets(offs, o, bucket_bytes)
+
+    # ---- bucketed, overlapped gradient all-reduce ---------------------------------------------------
+    def _make_buckets(self, offs, total, bucket_bytes):
+        """Contiguous parameter ranges of about `bucket_bytes` of the flat gradient, cut from the END of the parameter list
+        (autograd produces the decoder's gradients first); one post-accumulate hook per parameter counts a bucket down."""
+        lo_idx, hi_idx = len(self.params), len(self.params)
+        while hi_idx > 0:
+            lo_idx = hi_idx - 1
+            while lo_idx > 0 and (offs[hi_idx] if hi_idx < len(offs) else total) - offs[lo_idx - 1] <= bucket_bytes // 4:
+                lo_idx -= 1
+            flat_hi = offs[hi_idx] if hi_idx < len(offs) else total
+            self._buckets.append((lo_idx, hi_idx, offs[lo_idx], flat_hi))
+            hi_idx = lo_idx
+        for b, (lo, hi, _, _) in enumerate(self._buckets):
+            for i in range(lo, hi):
+                self._bucket_of[id(self.params[i])] = b
+                self.params[i].register_post_accumulate_grad_hook(self._on_grad)
+        self._pending = [hi - lo for lo, hi, _, _ in self._buckets]
+        self._fired = [False] * len(self._buckets)
+        if self.flat_grad.is_cuda:
+            self._comm = torch.cuda.Stream()
+
+    def _on_grad(self, p):
+        b = self._bucket_of[id(p)]
+        self._pending[b] -= 1
+        if self._pending[b] == 0 and not self._fired[b]:
+            self._fire(b)
+
+    def _fire(self, b):
+        """Gradients of bucket b -> its slice of the flat buffer (one multi-tensor copy on the stream that produced them),
+        then the all-reduce of that slice on the communication stream."""
+        lo, hi, flat_lo, flat_hi = self._buckets[b]
+        self._fired[b] = True
+        srcs, dsts = [], []
+        for p, v in zip(self.params[lo:hi], self.grad_views[lo:hi]):
+            if p.grad is None:
+                v.zero_()
+            else:
+                srcs.append(p.grad)
+                dsts.append(v)
+        if srcs:
+            torch._foreach_copy_(dsts, srcs)
+        chunk = self.flat_grad[flat_lo:flat_hi]
+        if self._comm is not None:
+            self._comm.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self._comm):
+                dist.all_reduce(chunk, op=dist.ReduceOp.SUM, group=self.group)
+        else:
+            self._work.append(dist.all_reduce(chunk, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
 
     # ---- the four calls of optimizers.py:252-255 ---------------------------------------------------
     def zero_grad(self):
@@ -54,8 +109,16 @@ class TrainStep:
         by one multi-tensor copy, instead of 60+ per-parameter accumulate kernels into pre-zeroed views."""
         for p in self.params:
             p.grad = None
+        if self._buckets:
+            self._pending = [hi - lo for lo, hi, _, _ in self._buckets]
+            self._fired = [False] * len(self._buckets)
 
     def gather_gradients(self):
+        if self._buckets:                      # data parallel: the hooks have copied (and started reducing) every complete
+            for b in range(len(self._buckets)):    # bucket; parameters without a gradient leave theirs to be flushed here
+                if not self._fired[b]:
+                    self._fire(b)
+            return
         srcs, dsts = [], []
         for p, v in zip(self.params, self.grad_views):
             if p.grad is None:
@@ -67,8 +130,12 @@ class TrainStep:
             torch._foreach_copy_(dsts, srcs)
 
     def reduce_gradients(self):
-        if self.distributed and self.world > 1:
-            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.group)
+        """Joins the bucket reductions started during backward (see _fire)."""
+        if self._comm is not None:
+            torch.cuda.current_stream().wait_stream(self._comm)
+        for w in self._work:
+            w.wait()
+        self._work = []
 
     def optimizer_step(self):
         self.step_count += 1
@@ -106,8 +173,9 @@ class TrainStep:
 
     def capture_fixed_coords(self, latent, coord, x_static, y_static, encoder_nbrs=None, decoder_nbrs=None, warmup=2):
         """Capture zero_grad -> forward -> MSE -> backward for STATIC input buffers into one CUDA graph and
-        return a `step()` callable that replays it, then all-reduces and runs the fused AdamW kernel (those
-        two stay outside the graph: NCCL, and AdamW's per-step bias correction scalars).  New data is fed by
+        return a `step()` callable that replays it, then runs the fused AdamW kernel (outside the graph: its bias
+        correction scalars change per step).  Under data parallelism the bucketed NCCL all-reduces are captured too, on
+        their communication stream, overlapping the rest of the backward pass.  New data is fed by
         copying into `x_static` / `y_static` before calling `step()`.  Several hundred small launches per
         step otherwise cost more host time than the GPU needs to execute them."""
         return self._capture(lambda: self.model(latent_tokens_coord=latent, xcoord=coord, pndata=x_static,
@@ -122,6 +190,7 @@ class TrainStep:
             loss = ops.mse_loss(pred, y_static)
             loss.backward()
             self.gather_gradients()
+            self.reduce_gradients()                    # joins the communication stream (captured with the graph)
             return loss.detach()
 
         side = torch.cuda.Stream()
@@ -140,7 +209,6 @@ class TrainStep:
         def step():
             graph.replay()
             _lib.note_launches(launches)
-            self.reduce_gradients()
             self.optimizer_step()
             return loss_static
 

@@ -308,8 +308,12 @@ def _dp_worker(rank, world, port, q, row_shard=False):
         lat, x, pn, tgt = cases.case_inputs(name)
         per = c["B"] // world
         sl = slice(rank * per, (rank + 1) * per)
-        step = TrainStep(model, lr=1e-3, weight_decay=1e-2)
+        step = TrainStep(model, lr=1e-3, weight_decay=1e-2, bucket_bytes=16 << 10)   # small buckets: several reductions in flight
+        assert len(step._buckets) > 3 and sum(hi - lo for lo, hi, _, _ in step._buckets) == len(step.params)
+        assert step._buckets[0][3] == step.flat_grad.numel() and step._buckets[-1][2] == 0           # cover the flat buffer
+        assert all(a[2] == b[3] for a, b in zip(step._buckets, step._buckets[1:]))                   # ... contiguously
         loss = step.fixed_coords_step(lat, x, pn[sl].contiguous(), tgt[sl].contiguous())
+        assert all(step._fired)
     if rank == 0:
         q.put(({k: v.detach().numpy().copy() for k, v in model.state_dict().items()}, float(loss)))
     dist.barrier()
