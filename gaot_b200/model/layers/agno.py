@@ -27,9 +27,12 @@ class AGNO(nn.Module):
             raise ValueError("Either channel_mlp or channel_mlp_layers must be provided.")
         if transform_type not in ["linear_kernelonly", "linear", "nonlinear_kernelonly", "nonlinear"]:
             raise ValueError(f"Invalid transform_type: {transform_type}")
-        if transform_type != "linear":
-            # nonlinear* are shape-broken in the reference itself; *_kernelonly is "next"
+        if transform_type in ("nonlinear", "nonlinear_kernelonly"):
+            # shape-broken in the reference itself (the kernel MLP is built for 2 * coord_dim inputs,
+            # agno.py:236-241 concatenates the features onto them)
             raise NotImplementedError(f"transform_type={transform_type!r} is not on the accelerated path")
+        # 'linear_kernelonly' follows the same arithmetic as 'linear' in the reference (agno.py:229-247: the type only
+        # changes the nonlinear* branches); the kernel-only transform proper is f_y=None (forward below)
         if use_attn:
             if coord_dim is None:
                 raise ValueError("coord_dim must be specified when use_attn is True")
@@ -43,11 +46,25 @@ class AGNO(nn.Module):
             self.key_proj = nn.Linear(self.coord_dim, attention_dim)
             self.scaling_factor = 1.0 / (attention_dim ** 0.5)
 
-    def edge_weights(self, y, x, plan: ops.GraphPlan):
+    def edge_weights(self, y, x, plan: ops.GraphPlan, weights=None):
         """w [E, C]: kernel MLP on [y_j, x_m] (agno.py:229-242) times the attention weight (agno.py:218-224, 250)
-        or 1/deg when the reduce is `mean` (agno.py:264)."""
+        or 1/deg when the reduce is `mean` (agno.py:264).  With integration `weights` [n] (agno.py:252-262) every edge is
+        scaled by weights[idx_e] and the reduce is a plain sum (no 1/deg)."""
         fcs = self.channel_mlp.fcs
         learned_alpha = self.use_attn and self.attention_type == "dot_product"
+        if weights is not None:
+            if weights.ndim != 1:
+                raise AssertionError("Weights must be of dimension 1 in all cases")
+            kappa = self.channel_mlp(ops.edge_inputs(y, x, plan))
+            nbr = weights.to(kappa.dtype)[plan.index.long()]
+            if learned_alpha:
+                cd = self.coord_dim
+                q = ops.linear(x[:, :cd].contiguous(), self.query_proj.weight, self.query_proj.bias)
+                k = ops.linear(y[:, :cd].contiguous(), self.key_proj.weight, self.key_proj.bias)
+                nbr = nbr * ops.edge_dot_softmax(q, k, plan, self.scaling_factor)
+            elif self.use_attn:
+                nbr = nbr * self._parameter_free_alpha(y, x, plan)
+            return ops.scale_rows(kappa, nbr.contiguous())
         if (self.fuse_edge_mlp and ops.get_precision() == "bf16" and not learned_alpha and y.shape[1] == x.shape[1]
                 and ops.edge_mlp_supported(fcs[0].weight.shape[1], fcs[0].weight.shape[0], len(fcs) - 2, fcs[-1].weight.shape[0])
                 and all(tuple(fc.weight.shape) == (64, 64) for fc in fcs[1:-1]) and fcs[-1].weight.shape[1] == 64
@@ -92,14 +109,15 @@ class AGNO(nn.Module):
         return alpha
 
     def forward(self, y, neighbors, x=None, f_y=None, weights=None):
-        if weights is not None:
-            raise NotImplementedError("integration weights are not on the accelerated path")
+        """agno.py:150-273.  f_y=None is the kernel-only transform (a): out[m,:] = reduce_e w_e.  `weights` [n] are
+        integration weights (agno.py:252-262; the reference multiplies an [E] vector into [E, C] without unsqueezing, which
+        only broadcasts when C == E or C == 1 - the documented per-edge scaling is what runs here)."""
         if x is None:
             x = y
-        if f_y is None:
-            raise NotImplementedError("f_y=None (kernel-only transform) is not on the accelerated path")
         plan = ops.graph_plan(neighbors, y.shape[0])
-        w = self.edge_weights(y, x, plan)
+        w = self.edge_weights(y, x, plan, weights)
+        if f_y is None:
+            return ops.segment_pool(w, plan, "sum")
         if f_y.ndim == 3:
             return ops.agno_aggregate(f_y, w, plan)
         if f_y.ndim == 2:

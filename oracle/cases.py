@@ -90,6 +90,12 @@ CASES = {
                              precompute_edges=True, neighbor_search_method="native"),
                   transformer=dict(patch_size=2, hidden_size=64, num_layers=2, ffn_multiplier=2),
                   attn=dict(num_heads=2, num_kv_heads=2)),
+    # transform_type 'linear_kernelonly' (agno.py:229-247: same arithmetic as 'linear' once f_y is given), mean reduce
+    "konly2d": dict(latent=(8, 8), n=300, d=2, B=2, cin=2, cout=2, seed=10,
+                    magno=dict(coord_dim=2, radius=0.35, hidden_size=16, mlp_layers=2, lifting_channels=16,
+                               transform_type="linear_kernelonly", use_attention=False, neighbor_search_method="native"),
+                    transformer=dict(patch_size=2, hidden_size=64, num_layers=1, ffn_multiplier=2),
+                    attn=dict(num_heads=2, num_kv_heads=2)),
     # BASELINE cfg-2 geometry (Poisson-Gauss hyper-parameters, config/examples/time_indep/poisson_gauss.json)
     "cfg2": dict(latent=(64, 64), n=9216, d=2, B=2, cin=1, cout=1, seed=0, summary_only=True,
                  magno=dict(coord_dim=2, radius=0.033, hidden_size=64, mlp_layers=3, lifting_channels=64,
@@ -169,6 +175,17 @@ NBR_CASES = ["rand2d", "rand3d", "dec2d", "lattice2d", "lattice3d", "empty"]
 
 
 # ---- dataset-side fixtures (graph builder, time-pair dataset) -----------------------------------------------------
+def agno_case():
+    """(y [n,2], x [m,2], f_y [2,n,8], weights [n], layers) for the AGNO option fixtures (kernel-only transform, integration
+    weights): clustered source points against a 6 x 6 query grid, radius 0.45; one query is moved away so its row is empty."""
+    y = clustered_points(120, 2, 700)
+    x = latent_grid((6, 6)).clone()
+    x[5] = torch.tensor([7.0, 7.0])
+    f_y = normal((2, 120, 8), 701)
+    wts = torch.rand(120, generator=torch.Generator().manual_seed(702), dtype=torch.float32) * 0.9 + 0.1
+    return y, x, f_y, wts, [4, 16, 8], 0.45
+
+
 def graph_builder_case():
     """(x_data [S, 1, n, 2] UN-scaled sample meshes, latent [M, 2], radius, scales): the builder rescales every sample to
     [-1, 1] by its own min / max (graph_builder.py:60) before searching."""

@@ -174,6 +174,24 @@ def agno(p, prefix, y, nbrs, x, f_y, use_attn=True, attention_type="cosine", coo
     return segment_csr(msg, nbrs["neighbors_row_splits"], "sum" if use_attn else "mean")
 
 
+def agno_kernel_only(p, prefix, y, nbrs, x, use_attn=True, attention_type="cosine", coord_dim=None, weights=None):
+    """AGNO.forward with f_y=None (transform (a), agno.py:229-271): out[m,:] = reduce_e w_e, reduce = sum with attention,
+    mean without; with integration `weights` [n] (agno.py:252-262) every edge is scaled by weights[idx_e] and the reduce
+    is a sum.  (The reference multiplies the [E] weight vector into the [E, C] kernel values without unsqueezing it, which
+    only broadcasts for C == E or C == 1; this restates the documented per-edge scaling.)"""
+    w = agno_edge_weight(p, prefix, y, x, nbrs, use_attn, attention_type, coord_dim)
+    if weights is not None:
+        return segment_csr(weights[nbrs["neighbors_index"]].unsqueeze(-1) * w, nbrs["neighbors_row_splits"], "sum")
+    return segment_csr(w, nbrs["neighbors_row_splits"], "sum" if use_attn else "mean")
+
+
+def agno_weighted(p, prefix, y, nbrs, x, f_y, weights, use_attn=True, attention_type="cosine", coord_dim=None):
+    """AGNO.forward with f_y and integration weights (agno.py:245-262): sum_e weights[idx_e] w_e f_y[b, idx_e, :]."""
+    w = agno_edge_weight(p, prefix, y, x, nbrs, use_attn, attention_type, coord_dim)
+    msg = (weights[nbrs["neighbors_index"]].unsqueeze(-1) * w).unsqueeze(0) * f_y[:, nbrs["neighbors_index"], :]
+    return segment_csr(msg, nbrs["neighbors_row_splits"], "sum")
+
+
 # --------------------------------------------------------------------------------------------
 # A4. statistical geometry embedding (layers/gemb.py:83-171, 230-233)
 # --------------------------------------------------------------------------------------------

@@ -232,14 +232,54 @@ def datasets_golden():
     np.savez_compressed(os.path.join(OUT, "datasets.npz"), **arrs)
 
 
+def agno_golden():
+    """AGNO options outside the MAGNO call sites, against the reference's own AGNO module (agno.py:67-273): the
+    kernel-only transform (f_y=None) and the f_y transform, with cosine attention (sum) and without (mean).  The
+    integration-weights branch (agno.py:252-262) cannot run in the reference for C > 1 (an [E] vector is multiplied into
+    [E, C] without unsqueezing), so `weights=` is pinned by the oracle restatement of its documented meaning only."""
+    from src.model.layers.agno import AGNO
+    y, x, f_y, wts, layers, radius = cases.agno_case()
+    nbrs = NeighborSearch("native")(y, x, radius)
+    arrs = {"index": nbrs["neighbors_index"].numpy(), "splits": nbrs["neighbors_row_splits"].numpy()}
+    torch.set_default_dtype(torch.float64)
+    try:
+        for tag, use_attn in (("attn", True), ("mean", False)):
+            m = AGNO(channel_mlp_layers=layers, use_attn=use_attn, attention_type="cosine", coord_dim=2, use_torch_scatter=True)
+            shapes = {k: list(v.shape) for k, v in m.state_dict().items()}
+            params = cases.synth_params(shapes, 710 + int(use_attn))
+            m.load_state_dict({k: v.double() for k, v in params.items()})
+            y64, x64, f64 = y.double(), x.double(), f_y.double()
+            konly = m(y64, nbrs, x64, f_y=None)
+            full = m(y64, nbrs, x64, f_y=f64)
+            p = {"agno." + k: v.double() for k, v in params.items()}
+            o1 = orc.agno_kernel_only(p, "agno", y64, nbrs, x64, use_attn=use_attn, coord_dim=2)
+            o2 = orc.agno(p, "agno", y64, nbrs, x64, f64, use_attn=use_attn, coord_dim=2)
+            assert rel(o1, konly) < 1e-10 and rel(o2, full) < 1e-10, (tag, rel(o1, konly), rel(o2, full))
+            for k, v in params.items():
+                arrs[f"{tag}.param.{k}"] = v.numpy()
+            arrs[f"{tag}.kernel_only"] = konly.detach().numpy().astype(np.float32)
+            arrs[f"{tag}.full"] = full.detach().numpy().astype(np.float32)
+            # integration weights: oracle restatement only (see above)
+            arrs[f"{tag}.kernel_only_weighted"] = orc.agno_kernel_only(p, "agno", y64, nbrs, x64, use_attn=use_attn, coord_dim=2,
+                                                                      weights=wts.double()).numpy().astype(np.float32)
+            arrs[f"{tag}.full_weighted"] = orc.agno_weighted(p, "agno", y64, nbrs, x64, f64, wts.double(), use_attn=use_attn,
+                                                             coord_dim=2).numpy().astype(np.float32)
+    finally:
+        torch.set_default_dtype(torch.float32)
+    print(f"[agno options] E = {arrs['index'].size}, kernel-only / f_y transforms match the reference AGNO")
+    np.savez_compressed(os.path.join(OUT, "agno.npz"), **arrs)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     only = sys.argv[1:]                                   # optional: regenerate just these model cases
+    if not only or "agno" in only:
+        agno_golden()
     if not only or "rollout" in only:
         rollout_golden()
     if not only or "datasets" in only:
         datasets_golden()
-    if only and all(o in ("rollout", "datasets") for o in only):
+    if only and all(o in ("rollout", "datasets", "agno") for o in only):
         return
     for name, c in cases.CASES.items():
         if only and name not in only:

@@ -53,7 +53,7 @@ def test_nothing_in_the_product_imports_the_oracle():
 
 @pytest.mark.parametrize("precision", ["fp32", "ffma"])
 @pytest.mark.parametrize("fuse", [True, False])
-@pytest.mark.parametrize("name", ["tiny2d", "tiny3d", "plain2d", "vx2d", "dot2d", "npe2d", "pnet2d", "cond2d", "vxmix"])
+@pytest.mark.parametrize("name", ["tiny2d", "tiny3d", "plain2d", "vx2d", "dot2d", "npe2d", "pnet2d", "cond2d", "vxmix", "konly2d"])
 def test_model_wiring_matches_reference_golden(name, fuse, precision):
     """Both parity modes through the emulated ABI: 'fp32' = split-precision tensor-core entry points (the emulator forms
     the same fp16 hi / lo planes and the same three product terms as the kernels), 'ffma' = plain fp32 entry points."""
@@ -143,6 +143,33 @@ def _check_sub_csr(out, src):
         sub = out["neighbors_index"][ro[r]:ro[r + 1]].tolist()
         it = iter(full)
         assert all(any(a == b for b in it) for a in sub), r       # subsequence test
+
+
+@pytest.mark.parametrize("tag,use_attn", [("attn", True), ("mean", False)])
+def test_agno_kernel_only_and_integration_weights_match_golden(tag, use_attn):
+    """AGNO options outside MAGNO's call sites (agno.py:150-273) through the emulated ABI: f_y=None (kernel-only transform)
+    and the f_y transform against the reference's own AGNO module; `weights=` against the oracle restatement (the
+    reference's line only broadcasts for C == E; tests/golden/agno.npz comes from `oracle/make_golden.py agno`)."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "agno.npz"))
+    y, x, f_y, wts, layers, _ = cases.agno_case()
+    nbrs = {"neighbors_index": torch.from_numpy(g["index"]), "neighbors_row_splits": torch.from_numpy(g["splits"])}
+    with abi_emulator.install():
+        from gaot_b200.model.layers.agno import AGNO
+        m = AGNO(channel_mlp_layers=layers, use_attn=use_attn, attention_type="cosine", coord_dim=2)
+        m.load_state_dict({k: torch.from_numpy(g[f"{tag}.param.{k}"]) for k in m.state_dict()})
+        assert rel_l2(m(y, nbrs, x, f_y=None), g[f"{tag}.kernel_only"]) < 1e-5
+        assert rel_l2(m(y, nbrs, x, f_y=f_y), g[f"{tag}.full"]) < 1e-5
+        assert rel_l2(m(y, nbrs, x, f_y=f_y[0]), g[f"{tag}.full"][0]) < 1e-5                     # un-batched f_y [n, C]
+        assert rel_l2(m(y, nbrs, x, f_y=None, weights=wts), g[f"{tag}.kernel_only_weighted"]) < 1e-5
+        out = m(y, nbrs, x, f_y=f_y, weights=wts)
+        assert rel_l2(out, g[f"{tag}.full_weighted"]) < 1e-5
+        out.sum().backward()                                                                     # the option paths are differentiable
+        assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.parameters())
+        with pytest.raises(AssertionError):
+            m(y, nbrs, x, f_y=f_y, weights=wts[:, None])                                         # agno.py:254
+        with pytest.raises(NotImplementedError):
+            AGNO(channel_mlp_layers=layers, transform_type="nonlinear")                          # shape-broken in the reference
+        AGNO(channel_mlp_layers=layers, transform_type="linear_kernelonly")                      # == 'linear' (agno.py:229-247)
 
 
 def test_edge_drop_identity_cases_follow_the_reference():
