@@ -382,8 +382,8 @@ def test_cond_affine_fwd_bwd_vs_fp64(B, T, D):
 @pytest.mark.parametrize("tag,use_attn", [("attn", True), ("mean", False)])
 def test_agno_kernel_only_and_integration_weights_vs_golden(tag, use_attn, precision):
     """AGNO options outside MAGNO's call sites (agno.py:150-273): f_y=None (kernel-only transform) and the f_y transform
-    against the reference's own AGNO module, `weights=` against the oracle restatement (tests/golden/agno.npz).  The kernel
-    MLP here is 4 -> 16 -> 8, outside the fused tensor-core kernel's shapes, so both modes run it in fp32: 1e-5."""
+    against the reference's own AGNO module, `weights=` against the oracle restatement (tests/golden/agno.npz).
+    Tolerance: 1e-5 in the parity mode; 2e-2 in 'bf16' mode, where the kernel MLP's 16 -> 8 layer takes bf16 operands."""
     import os
     ops = _ops()
     from gaot_b200.model.layers.agno import AGNO
@@ -391,14 +391,15 @@ def test_agno_kernel_only_and_integration_weights_vs_golden(tag, use_attn, preci
     y, x, f_y, wts, layers, _ = [t.to(DEV) if torch.is_tensor(t) else t for t in cases.agno_case()]
     nbrs = {"neighbors_index": torch.from_numpy(g["index"]).to(DEV), "neighbors_row_splits": torch.from_numpy(g["splits"]).to(DEV)}
     ops.set_precision(precision)
+    tol = 1e-5 if precision == "fp32" else 2e-2
     try:
         m = AGNO(channel_mlp_layers=layers, use_attn=use_attn, attention_type="cosine", coord_dim=2).to(DEV)
         m.load_state_dict({k: torch.from_numpy(g[f"{tag}.param.{k}"]).to(DEV) for k in m.state_dict()})
-        assert rel_l2(m(y, nbrs, x, f_y=None), g[f"{tag}.kernel_only"]) < 1e-5
-        assert rel_l2(m(y, nbrs, x, f_y=f_y), g[f"{tag}.full"]) < 1e-5
-        assert rel_l2(m(y, nbrs, x, f_y=None, weights=wts), g[f"{tag}.kernel_only_weighted"]) < 1e-5
+        assert rel_l2(m(y, nbrs, x, f_y=None), g[f"{tag}.kernel_only"]) < tol
+        assert rel_l2(m(y, nbrs, x, f_y=f_y), g[f"{tag}.full"]) < tol
+        assert rel_l2(m(y, nbrs, x, f_y=None, weights=wts), g[f"{tag}.kernel_only_weighted"]) < tol
         out = m(y, nbrs, x, f_y=f_y, weights=wts)
-        assert rel_l2(out, g[f"{tag}.full_weighted"]) < 1e-5
+        assert rel_l2(out, g[f"{tag}.full_weighted"]) < tol
         out.sum().backward()
         assert all(p.grad is not None and bool(torch.isfinite(p.grad).all()) for p in m.parameters())
     finally:
