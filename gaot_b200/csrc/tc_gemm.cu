@@ -181,7 +181,27 @@ struct TcArgs {
     // split-precision mode (SPLIT): operands are [2, rows, cols] fp16 hi / lo planes of x * scale; sa / sb point at the
     // {scale, 1 / scale} pair written by gaot_split_f16; kb_real = k-blocks of ONE term (the virtual contraction is 3 terms long)
     const float* sa; const float* sb; int64_t kb_real;
+    const void* aux;                  // TC_ACT_SWIGLU_FWD: U output [M, N/2]; TC_ACT_SWIGLU_BWD: saved pre-activations [M, 2N]
 };
+
+// Fused SwiGLU epilogues (internal `act` codes; bf16 output, fast epilogue, two 32-column chunks per pass):
+//   TC_ACT_SWIGLU_FWD: the output columns come in blocks of 64 = [a(32 features) | b(32 features)] (weight rows interleaved
+//     by the caller); besides the [M, N] pre-activations the epilogue stores u = silu(a) * b into U [M, N/2] (tmAdd = U map)
+//   TC_ACT_SWIGLU_BWD: the accumulator holds dU [M, N]; the epilogue loads the matching [32 x 64] box of the saved
+//     pre-activations (tmAdd = their map), forms (dA | dB) = (dU b silu'(a) | dU silu(a)) in place and stores it into
+//     dAB [M, 2N] (tmC): dU itself never reaches memory
+constexpr int TC_ACT_SWIGLU_FWD = 3, TC_ACT_SWIGLU_BWD = 4;
+__device__ __forceinline__ float sigmoid_fast(float x) {
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * x));
+    return __fdividef(1.f, 1.f + e);
+}
+__device__ __forceinline__ float2 unpack_bf16x2(uint32_t p) { return make_float2(__uint_as_float(p << 16), __uint_as_float(p & 0xffff0000u)); }
+__device__ __forceinline__ uint4 lds_u4(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
 
 // MN-major operand tile: [64 contraction rows][64 elements = 128 bytes] blocks of 8 KB, one per 64 output
 // rows/columns; SWIZZLE_128B; LBO = 8 KB between the 64-wide blocks, SBO = 1 KB between 8-row groups
@@ -401,6 +421,18 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                             }
                         }
                     }
+                    if (g.act == TC_ACT_SWIGLU_BWD) {              // the [32 x 64] (a | b) boxes of this pass's two chunks
+#pragma unroll
+                        for (int c = 0; c < PCH; ++c) {
+                            if (ncol0 + (ps * PCH + c) * 32 < g.N && row0 < g.M) {
+                                if (lane == 0) {
+                                    mbar_expect_tx(&abar[c], 4096);
+                                    tma_load_2d_s(box0 + c * 4096, &tmAdd, &abar[c], 2 * ((int)ncol0 + (ps * PCH + c) * 32), row0);
+                                }
+                                ++aload[c];
+                            }
+                        }
+                    }
                     if (ps == 0) {
                         TRACE(1 + lt * 8);
                         mbar_wait(&acc_full[ab], (lt >> 1) & 1u);
@@ -430,6 +462,52 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         float v[32];
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[c][j]);
+                        if (PCH == 2 && g.act == TC_ACT_SWIGLU_BWD) {
+                            // own row of the (a | b) box -> (dA | dB) in place, one TMA store of the [32 x 64] box
+                            mbar_wait(&abar[c], (aload[c] - 1u) & 1u);
+                            const uint32_t rowa = box + (uint32_t)lane * 128u;
+#pragma unroll
+                            for (int w = 0; w < 4; ++w) {
+                                const uint4 pa = lds_u4(rowa + (uint32_t)((w ^ (lane & 7)) << 4));
+                                const uint4 pb = lds_u4(rowa + (uint32_t)(((w + 4) ^ (lane & 7)) << 4));
+                                const uint32_t pav[4] = {pa.x, pa.y, pa.z, pa.w}, pbv[4] = {pb.x, pb.y, pb.z, pb.w};
+                                uint32_t oa[4], ob[4];
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    const float2 a2 = unpack_bf16x2(pav[k]), b2 = unpack_bf16x2(pbv[k]);
+                                    const float d0 = v[8 * w + 2 * k], d1 = v[8 * w + 2 * k + 1];
+                                    const float s0 = sigmoid_fast(a2.x), s1 = sigmoid_fast(a2.y);
+                                    oa[k] = pack_bf16x2(d0 * b2.x * s0 * (1.f + a2.x * (1.f - s0)), d1 * b2.y * s1 * (1.f + a2.y * (1.f - s1)));
+                                    ob[k] = pack_bf16x2(d0 * a2.x * s0, d1 * a2.y * s1);
+                                }
+                                sts_u4(rowa + (uint32_t)((w ^ (lane & 7)) << 4), oa[0], oa[1], oa[2], oa[3]);
+                                sts_u4(rowa + (uint32_t)(((w + 4) ^ (lane & 7)) << 4), ob[0], ob[1], ob[2], ob[3]);
+                            }
+                            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                            __syncwarp();
+                            if (lane == 0) {
+                                tma_store_2d(&tmC, box, 2 * (int)n, row0);
+                                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                            }
+                            continue;
+                        }
+                        if (PCH == 2 && g.act == TC_ACT_SWIGLU_FWD) {
+                            if (c == 1) {
+                                // u = silu(a) * b (a = chunk 0 of the pass, still in registers) -> the warp's second staging box
+                                // as a [32 x 32] bf16 tile (64-byte rows)
+                                float u[32];
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) {
+                                    const float a = __uint_as_float(r[0][j]);
+                                    u[j] = a * sigmoid_fast(a) * v[j];
+                                }
+#pragma unroll
+                                for (int w = 0; w < 4; ++w)
+                                    sts_u4(box0 + 4096u + (uint32_t)lane * 64u + (uint32_t)((w ^ ((lane >> 1) & 3)) << 4),
+                                           pack_bf16x2(u[8 * w], u[8 * w + 1]), pack_bf16x2(u[8 * w + 2], u[8 * w + 3]),
+                                           pack_bf16x2(u[8 * w + 4], u[8 * w + 5]), pack_bf16x2(u[8 * w + 6], u[8 * w + 7]));
+                            }
+                        }
                         if (SPLIT) {
 #pragma unroll
                             for (int j = 0; j < 32; ++j) v[j] *= alpha;
@@ -488,6 +566,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                 if (ps == NPASS - 1) TRACE(8 + lt * 8);
                                 if (lane == 0) {
                                     tma_store_2d(&tmC, box0, (int)(ncol0 + ps * PCH * 32), row0);
+                                    if (g.act == TC_ACT_SWIGLU_FWD) tma_store_2d(&tmAdd, box0 + 4096u, (int)((ncol0 + ps * PCH * 32) >> 1), row0);
                                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                                 }
                             }
@@ -904,7 +983,19 @@ int launch_tc(const void* A, const void* B, TcArgs& g, cudaStream_t st) {
              (!g.add || (!g.out_bf16 && g.add_rows % 32 == 0 && g.ldadd % 4 == 0 && !(reinterpret_cast<uintptr_t>(g.add) & 15))) &&
              (!g.bias || !(reinterpret_cast<uintptr_t>(g.bias) & 15));
     if (reduce) g.fast = (g.fast && !g.out_bf16 && !g.bias && !g.add && !g.act) ? 2 : 0;   // TMA reduce-add of fp32 partial tiles
-    if (g.fast) {
+    if (g.act == TC_ACT_SWIGLU_FWD || g.act == TC_ACT_SWIGLU_BWD) {
+        if (!g.fast || BN < 128 || !g.out_bf16 || SPLIT) return GAOT_E_BADARG;   // these epilogues exist in the two-chunk bf16 pass only
+        if (g.act == TC_ACT_SWIGLU_BWD) {                      // output and saved pre-activations: [M, 2N], boxes of 32 x 64
+            rc = make_map_box32(&tc, g.C, g.M, 2 * g.N, 2 * g.N, true, 64);
+            if (rc) return rc;
+            rc = make_map_box32(&tadd, g.aux, g.M, 2 * g.N, 2 * g.N, true, 64);
+        } else {                                                // pre-activations [M, N] as usual, U [M, N/2] in boxes of 32 x 32
+            rc = make_map_box32(&tc, g.C, g.M, g.N, g.N, true, 64);
+            if (rc) return rc;
+            rc = make_map_box32(&tadd, g.aux, g.M, g.N / 2, g.N / 2, true, 32);
+        }
+        if (rc) return rc;
+    } else if (g.fast) {
         rc = make_map_box32(&tc, g.C, g.M, g.N, g.N, g.out_bf16 != 0, (g.out_bf16 && BN >= 128) ? 64 : 32);
         if (rc) return rc;
         if (g.add) {
@@ -970,6 +1061,32 @@ GAOT_API int gaot_gemm_bf16_nn(const void* A, const void* B, void* C, int64_t M,
     TcArgs g{C, M, N, K, nullptr, nullptr, 1, 0, out_bf16, 1, 0, 0, 0, 0, nullptr, 0};
     cudaStream_t st = (cudaStream_t)stream;
     return dispatch_tc<false, true>(A, B, g, st);
+}
+
+GAOT_API int gaot_gemm_bf16_swiglu(const void* A, const void* B, void* AB, void* U, int64_t M, int64_t N, int64_t K,
+                                   void* stream) {
+    if (!A || !B || !AB || !U || M < 1 || N < 128 || K < 1 || N % 64 != 0) return GAOT_E_BADARG;
+    if (K % 8 != 0 || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15) ||
+        (reinterpret_cast<uintptr_t>(AB) & 15) || (reinterpret_cast<uintptr_t>(U) & 15))
+        return GAOT_E_ALIGN;
+    if (M > 0x7fffffffLL || N > 0x7fffffffLL || K > 0x7fffffffLL) return GAOT_E_BADARG;
+    TcArgs g{AB, M, N, K, nullptr, nullptr, 1, 0, 1, 1, 0, 0, 0, TC_ACT_SWIGLU_FWD, nullptr, 0};
+    g.aux = U;
+    cudaStream_t st = (cudaStream_t)stream;
+    return dispatch_tc<false, false>(A, B, g, st);
+}
+
+GAOT_API int gaot_gemm_bf16_nn_swiglu_bwd(const void* dY, const void* W, const void* AB, void* dAB, int64_t M, int64_t N,
+                                          int64_t K, void* stream) {
+    if (!dY || !W || !AB || !dAB || M < 1 || N < 128 || K < 1 || N % 32 != 0) return GAOT_E_BADARG;
+    if (K % 8 != 0 || (reinterpret_cast<uintptr_t>(dY) & 15) || (reinterpret_cast<uintptr_t>(W) & 15) ||
+        (reinterpret_cast<uintptr_t>(AB) & 15) || (reinterpret_cast<uintptr_t>(dAB) & 15))
+        return GAOT_E_ALIGN;
+    if (M > 0x7fffffffLL || N > 0x3fffffffLL || K > 0x7fffffffLL) return GAOT_E_BADARG;
+    TcArgs g{dAB, M, N, K, nullptr, nullptr, 1, 0, 1, 1, 0, 0, 0, TC_ACT_SWIGLU_BWD, nullptr, 0};
+    g.aux = AB;
+    cudaStream_t st = (cudaStream_t)stream;
+    return dispatch_tc<false, true>(dY, W, g, st);
 }
 
 GAOT_API int gaot_gemm_bf16_tn(const void* A, const void* B, float* C, int64_t M, int64_t N, int64_t R, int accumulate,

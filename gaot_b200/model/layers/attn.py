@@ -117,14 +117,27 @@ class FFN(nn.Module):
         self.correction = ConditionedNorm(1, input_size, cond_norm_hidden_size) if use_conditional_norm else None
         self._w13 = None
 
+    def _fused(self):
+        """bf16 mode: the SwiGLU rides in the GEMM epilogues (ops.swiglu_ffn) when the widths fit and the output is not
+        corrected before the residual (attn.py:151-154)."""
+        return self.correction is None and ops.ffn_fusable(self.w1.weight.shape[1], self.w1.weight.shape[0])
+
     def prep_weights(self):
-        self._w13 = torch.cat([self.w1.weight, self.w3.weight], dim=0)
+        if self._fused():
+            self._w13 = ops.interleave_w13(self.w1.weight, self.w3.weight)
+        else:
+            self._w13 = torch.cat([self.w1.weight, self.w3.weight], dim=0)
         return [self._w13] + ops.prepare_weight(self._w13) + ops.prepare_weight(self.w2.weight)
 
     def forward(self, x, condition=None, residual=None):
         shape = x.shape
         x2 = x.reshape(-1, shape[-1])
         tc16 = ops.get_precision() == "bf16" and shape[-1] % 8 == 0 and self.w1.weight.shape[0] % 8 == 0
+        if self._fused():
+            w13 = self._w13 if self._w13 is not None else ops.interleave_w13(self.w1.weight, self.w3.weight)
+            self._w13 = None
+            add = residual.reshape(-1, shape[-1]) if residual is not None else None
+            return ops.swiglu_ffn(x2, w13, self.w2.weight, add=add).view(residual.shape if residual is not None else shape)
         w13 = self._w13 if self._w13 is not None else torch.cat([self.w1.weight, self.w3.weight], dim=0)
         self._w13 = None
         ab = ops.linear(x2, w13, tc=True, out_bf16=tc16)

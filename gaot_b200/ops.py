@@ -7,6 +7,8 @@ Shapes are row-major contiguous fp32; CSR arrays are int64 as in the reference c
 """
 from __future__ import annotations
 
+import os
+
 from typing import Dict, List, Optional
 
 import torch
@@ -600,6 +602,72 @@ class _SwiGLU16(torch.autograd.Function):
         dab = torch.empty_like(ab)
         call("gaot_swiglu_bwd_bf16", ptr(du), ptr(ab), ptr(dab), ab.shape[0], ab.shape[1] // 2)
         return dab
+
+
+# ---- gated FFN with the SwiGLU fused into the GEMM epilogues (bf16 mode) -------------------------------------------------
+def ffn_fusable(D: int, F: int) -> bool:
+    """Shapes the fused epilogues cover (gaot_gemm_bf16_swiglu / gaot_gemm_bf16_nn_swiglu_bwd): hidden width F in blocks
+    of 32 and at least 128 (the two-chunk epilogue pass of the 128- and 256-column GEMM tiles)."""
+    return _PRECISION == "bf16" and D % 8 == 0 and F % 32 == 0 and F >= 128 and not os.environ.get("GAOT_B200_NO_FFN_FUSE")
+
+
+def interleave_w13(w1, w3):
+    """[2F, D] weight of the fused w1 | w3 product with rows interleaved in blocks of 32 (w1[32j..], w3[32j..], ...), so an
+    output tile holds a and b of the same features; differentiable (the gradient un-interleaves through autograd)."""
+    F, D = w1.shape
+    return torch.stack([w1.reshape(F // 32, 32, D), w3.reshape(F // 32, 32, D)], dim=1).reshape(2 * F, D)
+
+
+class _SwiGLUFFN(torch.autograd.Function):
+    """y = (silu(x w1^T) * (x w3^T)) w2^T + add  (reference FFN.forward, attn.py:137-146) as three tensor-core GEMMs:
+    w13 with the SwiGLU in its epilogue (writes the pre-activations once, for the backward, and u), w2 with the residual
+    in its epilogue; backward: dU = dY w2 is consumed inside its own epilogue (-> dA | dB), then dX and the two weight
+    gradients.  No stand-alone SwiGLU pass, dU never reaches memory."""
+
+    @staticmethod
+    def forward(ctx, x, w13i, w2, add, prep13, prep2):
+        _need_cuda(x)
+        x = x if x.is_contiguous() else x.contiguous()
+        M, D = x.shape
+        F2, Dout = w13i.shape[0], w2.shape[0]
+        xb = x if x.dtype == torch.bfloat16 else cast_bf16(_c(x))[0]
+        w13b = prep13 if prep13 is not None else cast_bf16(_c(w13i))[0]
+        w2b = prep2 if prep2 is not None else cast_bf16(_c(w2))[0]
+        add_c = _c(add) if add is not None else None
+        add_rows = add_c.shape[0] if add_c is not None else 0
+        if add_c is not None and (add_c.shape[1] != Dout or M % add_rows != 0):
+            raise ValueError(f"broadcast-add of shape {tuple(add_c.shape)} does not tile an [{M},{Dout}] output")
+        ab = torch.empty((M, F2), dtype=torch.bfloat16, device=x.device)
+        u = torch.empty((M, F2 // 2), dtype=torch.bfloat16, device=x.device)
+        call("gaot_gemm_bf16_swiglu", ptr(xb), ptr(w13b), ptr(ab), ptr(u), M, F2, D)
+        y = gemm_bf16(u, w2b, M, Dout, F2 // 2, bias=None, add=add_c, add_rows=add_rows)
+        ctx.save_for_backward(xb, w13b, w2b, ab, u)
+        ctx.add_rows, ctx.x_bf16 = add_rows, x.dtype == torch.bfloat16
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xb, w13b, w2b, ab, u = ctx.saved_tensors
+        M, D = xb.shape
+        F2, Dout = w13b.shape[0], w2b.shape[0]
+        dy = dy if dy.is_contiguous() else dy.contiguous()
+        dyb = dy if dy.dtype == torch.bfloat16 else cast_bf16(dy)[0]
+        dab = torch.empty_like(ab)
+        call("gaot_gemm_bf16_nn_swiglu_bwd", ptr(dyb), ptr(w2b), ptr(ab), ptr(dab), M, F2 // 2, Dout)
+        dW2 = gemm_bf16_tn(dyb, u, Dout, F2 // 2, M) if ctx.needs_input_grad[2] else None
+        dx = gemm_bf16_nn(dab, w13b, M, D, F2, out_bf16=ctx.x_bf16) if ctx.needs_input_grad[0] else None
+        dW13 = gemm_bf16_tn(dab, xb, F2, D, M) if ctx.needs_input_grad[1] else None
+        dadd = None
+        if ctx.add_rows and ctx.needs_input_grad[3]:
+            dyf = dy if dy.dtype == torch.float32 else dy.float()
+            dadd = dyf if ctx.add_rows == M else col_sum(dyf, M // ctx.add_rows, ctx.add_rows * Dout).view(ctx.add_rows, Dout)
+        return dx, dW13, dW2, dadd, None, None
+
+
+def swiglu_ffn(x, w13i, w2, add=None):
+    """x [M, D] (bf16 or fp32), w13i = interleave_w13(w1, w3) [2F, D], w2 [Dout, F]: see _SwiGLUFFN."""
+    e13, e2 = _PREPARED.get(id(w13i)), _PREPARED.get(id(w2))
+    return _SwiGLUFFN.apply(x, w13i, w2, add, e13[1] if e13 is not None else None, e2[1] if e2 is not None else None)
 
 
 def swiglu(ab):

@@ -216,6 +216,17 @@ int gaot_gemm_f32(const float* A, const float* B, float* C, int64_t M, int64_t N
 int gaot_gemm_bf16(const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K, int out_bf16,
                    const float* bias, const float* add, int64_t add_rows, int64_t ldadd, int act, float* pre,
                    int accumulate, void* stream);
+/* Gated FFN, forward (reference FFN.forward, src/model/layers/attn.py:137-146: w2(silu(w1 x) * w3 x)): the w1 / w3
+ * product with the SwiGLU fused into the epilogue.  B [N,K] holds the w1 and w3 rows INTERLEAVED in blocks of 32
+ * (rows [64j, 64j+32) = w1[32j..], rows [64j+32, 64j+64) = w3[32j..]), so AB [M,N] (bf16, kept for the backward) carries
+ * (a | b) in column blocks of 64 and U [M,N/2] (bf16) = silu(a) * b in the feature order of w1.  N % 64 == 0, N >= 128,
+ * K % 8 == 0, 16-byte aligned bases. */
+int gaot_gemm_bf16_swiglu(const void* A, const void* B, void* AB, void* U, int64_t M, int64_t N, int64_t K, void* stream);
+/* Gated FFN, backward of the same lines: dU = dY[M,K] W[K,N] (W = w2 in nn.Linear layout, consumed MN-major) never
+ * reaches memory - the epilogue reads the saved (a | b) blocks of AB [M,2N] and writes dAB [M,2N] (bf16) =
+ * (dU b silu'(a) | dU silu(a)) in the same interleaved layout.  N % 32 == 0, N >= 128, K % 8 == 0. */
+int gaot_gemm_bf16_nn_swiglu_bwd(const void* dY, const void* W, const void* AB, void* dAB, int64_t M, int64_t N, int64_t K,
+                                 void* stream);
 /* Input-gradient form: C[M,N] (fp32 or bf16) = A[M,K] B[K,N], B row-major [K,N] consumed MN-major in place
  * (dX = dY W with W in nn.Linear layout).  K % 8 == 0, N % 8 == 0. */
 int gaot_gemm_bf16_nn(const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K, int out_bf16,

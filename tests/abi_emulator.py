@@ -459,6 +459,29 @@ def gaot_swiglu_bwd_bf16(du, ab, dab, rows, F):
     _bf(dab, (rows, 2 * F))[:] = a.grad.to(torch.bfloat16)
 
 
+def _swiglu_blocks(x, F):
+    """[rows, 2F] in (a | b) column blocks of 64 -> a [rows, F], b [rows, F] (the layout of gaot_gemm_bf16_swiglu)."""
+    v = x.reshape(x.shape[0], F // 32, 2, 32)
+    return v[:, :, 0, :].reshape(x.shape[0], F), v[:, :, 1, :].reshape(x.shape[0], F)
+
+
+def gaot_gemm_bf16_swiglu(A, B, AB, U, M, N, K):
+    v = _bf(A, (M, K)).double() @ _bf(B, (N, K)).double().T          # interleaved weight rows -> interleaved columns
+    _bf(AB, (M, N))[:] = v.to(torch.bfloat16)
+    a, b_ = _swiglu_blocks(v, N // 2)
+    _bf(U, (M, N // 2))[:] = (torch.nn.functional.silu(a) * b_).to(torch.bfloat16)
+
+
+def gaot_gemm_bf16_nn_swiglu_bwd(dY, W, AB, dAB, M, N, K):
+    du = _bf(dY, (M, K)).double() @ _bf(W, (K, N)).double()
+    a, b_ = _swiglu_blocks(_bf(AB, (M, 2 * N)).double(), N)
+    sg = torch.sigmoid(a)
+    da = du * b_ * sg * (1 + a * (1 - sg))
+    db = du * a * sg
+    out = torch.stack([da.reshape(M, N // 32, 32), db.reshape(M, N // 32, 32)], dim=2).reshape(M, 2 * N)
+    _bf(dAB, (M, 2 * N))[:] = out.to(torch.bfloat16)
+
+
 def gaot_gemm_bf16_nn(A, B, C, M, N, K, out_bf16):
     v = _bf(A, (M, K)).double() @ _bf(B, (K, N)).double()
     if out_bf16:

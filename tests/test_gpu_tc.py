@@ -462,3 +462,36 @@ def test_edge_mlp_fused_many_tiles_matches_unfused_bf16_chain():
         ops.set_precision("fp32")
     assert rel_l2(res[True][0], res[False][0]) < 1e-2
     assert rel_l2(res[True][1], res[False][1]) < 2e-2
+
+
+# ------------------------------------------------------------------------------------------------
+# gated FFN with the SwiGLU fused into the GEMM epilogues (gaot_gemm_bf16_swiglu / gaot_gemm_bf16_nn_swiglu_bwd)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,D,F", [(256, 64, 128), (1000, 256, 1024), (4100, 64, 160), (32768, 256, 1024)])
+def test_swiglu_ffn_fused_vs_fp64(M, D, F):
+    """y = (silu(x w1^T) * (x w3^T)) w2^T + residual and its gradients against fp64 on the bf16-rounded operands
+    (attn.py:137-146).  Tolerances: the saved pre-activations, u, dA | dB and dX are bf16 tensors (8 mantissa bits each):
+    2e-2 on y and every gradient.  Shapes cover full and clipped tiles of the 256- and 128-column kernels."""
+    from gaot_b200 import ops
+    gen = torch.Generator().manual_seed(M + F)
+    x = torch.randn(M, D, generator=gen).to(DEV).to(torch.bfloat16).requires_grad_(True)
+    w1 = (torch.randn(F, D, generator=gen) / D ** 0.5).to(DEV).requires_grad_(True)
+    w3 = (torch.randn(F, D, generator=gen) / D ** 0.5).to(DEV).requires_grad_(True)
+    w2 = (torch.randn(D, F, generator=gen) / F ** 0.5).to(DEV).requires_grad_(True)
+    res = torch.randn(M, D, generator=gen).to(DEV).requires_grad_(True)
+    gy = torch.randn(M, D, generator=gen).to(DEV)
+    ops.set_precision("bf16")
+    try:
+        assert ops.ffn_fusable(D, F)
+        y = ops.swiglu_ffn(x, ops.interleave_w13(w1, w3), w2, add=res)
+        y.backward(gy)
+    finally:
+        ops.set_precision("fp32")
+    bf = lambda t: t.detach().to(torch.bfloat16).double()          # noqa: E731
+    xr, w1r, w3r, w2r, rr = [bf(t).requires_grad_(True) for t in (x, w1, w3, w2)] + [res.detach().double().requires_grad_(True)]
+    yr = (torch.nn.functional.silu(xr @ w1r.T) * (xr @ w3r.T)) @ w2r.T + rr
+    yr.backward(bf(gy))
+    assert rel_l2(y, yr) < 2e-2
+    for got, ref, nm in ((x.grad, xr.grad, "dx"), (w1.grad, w1r.grad, "dw1"), (w3.grad, w3r.grad, "dw3"), (w2.grad, w2r.grad, "dw2"),
+                         (res.grad, rr.grad, "dres")):
+        assert rel_l2(got.float(), ref) < 2e-2, (nm, rel_l2(got.float(), ref))

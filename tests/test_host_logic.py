@@ -447,7 +447,8 @@ def test_bf16_mode_wiring_close_to_reference():
         finally:
             ops.set_precision("fp32")
         assert "gaot_gemm_bf16" in calls and "gaot_gemm_bf16_tn" in calls and "gaot_attention_bwd_bf16" in calls
-        assert "gaot_swiglu_bwd_bf16" in calls
+        # the gated FFN (hidden 128 = 4 blocks of 32) runs with the SwiGLU inside the GEMM epilogues, forward and backward
+        assert "gaot_gemm_bf16_swiglu" in calls and "gaot_gemm_bf16_nn_swiglu_bwd" in calls and "gaot_swiglu_bwd_bf16" not in calls
     assert rel_l2(out, g["out"]) < 2e-2
     for k, p in model.named_parameters():
         assert rel_l2(p.grad, g["grad." + k]) < 6e-2, k
