@@ -182,6 +182,7 @@ struct TcArgs {
     // {scale, 1 / scale} pair written by gaot_split_f16; kb_real = k-blocks of ONE term (the virtual contraction is 3 terms long)
     const float* sa; const float* sb; int64_t kb_real;
     const void* aux;                  // TC_ACT_SWIGLU_FWD: U output [M, N/2]; TC_ACT_SWIGLU_BWD: saved pre-activations [M, 2N]
+    int no_alt;                       // experiment switch (GAOT_GEMM_NO_ALT): bf16 epilogue passes do not alternate staging boxes
 };
 
 // Fused SwiGLU epilogues (internal `act` codes; bf16 output, fast epilogue, two 32-column chunks per pass):
@@ -284,9 +285,14 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
 
+    // (32-bit index arithmetic: the launcher bounds gm * gn * splits below 2^31; a 64-bit divide costs ~150 cycles and every
+    // role walks this once per tile - on the MMA warp that was 600 cycles of a 5 000-cycle tile)
+    const uint32_t gm32 = (uint32_t)g.gm, gn32 = (uint32_t)g.gn;
     auto tile_coords = [&](int64_t t, int64_t& m0, int64_t& n0, int64_t& kb0, int& nkb) {
-        const int64_t mi = t % g.gm, rest = t / g.gm;
-        const int64_t ni = rest % g.gn, sp = rest / g.gn;
+        const uint32_t t32 = (uint32_t)t;
+        const uint32_t rest32 = t32 / gm32, mi32 = t32 - rest32 * gm32;
+        const uint32_t sp32 = rest32 / gn32, ni32 = rest32 - sp32 * gn32;
+        const int64_t mi = mi32, ni = ni32, sp = sp32;
         m0 = mi * (TC_BM * CG) + rank * TC_BM; n0 = ni * BN;
         kb0 = sp * per;
         nkb = (int)max((int64_t)0, min(kblocks, kb0 + per) - kb0);
@@ -406,8 +412,15 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 const uint32_t tmem_acc = tmem_base + ab * BN + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * (BN / 2));
 #pragma unroll
                 for (int ps = 0; ps < NPASS; ++ps) {
-                    // both boxes must have been read out by the previous TMA stores before they are refilled
-                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    // both boxes must have been read out by the previous TMA stores before they are refilled.  The plain bf16
+                    // pass fills ONE 4 KB box: passes alternate between the warp's two boxes, so only the store of the pass
+                    // before the previous one has to be done (the previous store drains under this pass)
+                    const bool alt = PCH == 2 && g.out_bf16 && g.act < TC_ACT_SWIGLU_FWD && !g.no_alt;
+                    const uint32_t boxp = box0 + ((alt && (ps & 1)) ? 4096u : 0u);
+                    if (lane == 0) {
+                        if (alt) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                        else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    }
                     __syncwarp();
                     if (g.add) {
 #pragma unroll
@@ -541,7 +554,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                 // TMA stores are paced per box row, so 128-byte rows halve the row count
 #pragma unroll
                                 for (int w = 0; w < 4; ++w)
-                                    sts_u4(box0 + (uint32_t)lane * 128u + (uint32_t)(((c * 4 + w) ^ (lane & 7)) << 4),
+                                    sts_u4(boxp + (uint32_t)lane * 128u + (uint32_t)(((c * 4 + w) ^ (lane & 7)) << 4),
                                            pack_bf16x2(v[8 * w], v[8 * w + 1]), pack_bf16x2(v[8 * w + 2], v[8 * w + 3]),
                                            pack_bf16x2(v[8 * w + 4], v[8 * w + 5]), pack_bf16x2(v[8 * w + 6], v[8 * w + 7]));
                             } else {
@@ -565,7 +578,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                 __syncwarp();
                                 if (ps == NPASS - 1) TRACE(8 + lt * 8);
                                 if (lane == 0) {
-                                    tma_store_2d(&tmC, box0, (int)(ncol0 + ps * PCH * 32), row0);
+                                    tma_store_2d(&tmC, boxp, (int)(ncol0 + ps * PCH * 32), row0);
                                     if (g.act == TC_ACT_SWIGLU_FWD) tma_store_2d(&tmAdd, box0 + 4096u, (int)((ncol0 + ps * PCH * 32) >> 1), row0);
                                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                                 }
@@ -956,6 +969,8 @@ int launch_tc(const void* A, const void* B, TcArgs& g, cudaStream_t st) {
         rc = BMN ? make_map_mn(&tb, B, g.K, g.N) : make_map(&tb, B, g.N, g.K, BNL);
     }
     if (rc) return rc;
+    static const int no_alt = getenv("GAOT_GEMM_NO_ALT") ? 1 : 0;
+    g.no_alt = no_alt;
     g.gm = (g.M + TC_BM * CG - 1) / (TC_BM * CG);
     g.gn = (g.N + BN - 1) / BN;
     g.kb_real = (g.K + TC_BK - 1) / TC_BK;
@@ -1010,6 +1025,7 @@ int launch_tc(const void* A, const void* B, TcArgs& g, cudaStream_t st) {
         attr_done = true;
     }
     const int64_t total = tiles * splits;
+    if (total > 0x7fffffffLL) return GAOT_E_BADARG;
     const unsigned grid = (unsigned)((total < workers ? total : workers) * CG);   // persistent: one CTA per SM
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid, 1, 1);
