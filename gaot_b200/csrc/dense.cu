@@ -210,15 +210,27 @@ constexpr int NW_ROWS = 8;               // rows in flight per warp
 
 template <bool BT>
 __global__ void __launch_bounds__(NW_THREADS, 1) narrow_rows_kernel(const GemmArgs g) {
-    __shared__ __align__(16) float slab[NW_THREADS / 32][NW_ROWS][64];
+    __shared__ __align__(16) float slab_raw[(NW_THREADS / 32) * NW_ROWS * 64 + 64];   // + 64: doubles as the 64 x 65 weight staging
+    float (*slab)[NW_ROWS][64] = reinterpret_cast<float (*)[NW_ROWS][64]>(slab_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int K = (int)g.K, N = (int)g.N;
     const int n0 = lane, n1 = lane + 32;
+    // the weight block reaches the registers through shared memory: one coalesced pass of the CTA over B, then every lane
+    // picks its two columns (a lane reading its own row of B straight from global memory touches 32 lines per instruction,
+    // 128 instructions per warp - that prologue was most of the kernel at a few thousand rows)
     float w0[64], w1[64];
+    {
+        float* ws = slab_raw;                                    // 64 x 65 floats
+        static_assert(sizeof(slab_raw) >= 64 * 65 * sizeof(float), "weight staging does not fit the row slab");
+        for (int i = threadIdx.x; i < 64 * 64; i += NW_THREADS) {
+            const int r = i >> 6, c = i & 63;                    // element (r, c) of B as stored: BT [N, K] -> (n, k); else [K, N] -> (k, n)
+            const int n = BT ? r : c, k = BT ? c : r;
+            ws[n * 65 + k] = (n < N && k < K) ? __ldg(g.B + (int64_t)r * g.ldb + c) : 0.f;
+        }
+        __syncthreads();
 #pragma unroll
-    for (int k = 0; k < 64; ++k) {
-        w0[k] = (k < K && n0 < N) ? __ldg(BT ? g.B + (int64_t)n0 * g.ldb + k : g.B + (int64_t)k * g.ldb + n0) : 0.f;
-        w1[k] = (k < K && n1 < N) ? __ldg(BT ? g.B + (int64_t)n1 * g.ldb + k : g.B + (int64_t)k * g.ldb + n1) : 0.f;
+        for (int k = 0; k < 64; ++k) { w0[k] = ws[n0 * 65 + k]; w1[k] = ws[n1 * 65 + k]; }
+        __syncthreads();
     }
     const float b0 = (g.bias && n0 < N) ? __ldg(g.bias + n0) : 0.f, b1 = (g.bias && n1 < N) ? __ldg(g.bias + n1) : 0.f;
     float (*my)[64] = slab[warp];
