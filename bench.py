@@ -309,7 +309,7 @@ def isolated_tensor_kernels(w, B, dev, peaks, precision):
                                  ptr(s_[6]), B, T, H, H, hd, Wq, scale) for s_ in sets]
         us = time_launches(bw, 20)
         entry("gaot_attention_bwd_bf16", f"attn_bwd_tc_kernel<{hd}>", 10.0 * B * H * T * T * hd, us,
-              "entry point = delta + memset + attn_bwd_tc_kernel + dq store; the tcgen05 kernel is ~95 % of it")
+              "entry point = delta + memset + attn_bwd_tc_kernel + dq store; the tcgen05 kernel is ~92 % of it")
         del sets, fw, bw
         xs = [rnd((rows, Dh), torch.bfloat16) for _ in range(4)]
         w13 = rnd((2 * F, Dh), torch.bfloat16, Dh ** -0.5)
@@ -323,6 +323,18 @@ def isolated_tensor_kernels(w, B, dev, peaks, precision):
         dW = torch.empty((2 * F, Dh), device=dev)
         us = time_launches([lambda i=i: call("gaot_gemm_bf16_tn", ptr(ys[i]), ptr(xs[i]), ptr(dW), 2 * F, Dh, rows, 0) for i in range(4)], 20)
         entry("gaot_gemm_bf16_tn", "gemm_bf16_tc_kernel<256,1,1,2>", 2.0 * rows * 2 * F * Dh, us, f"weight gradient dY^T X, {2 * F}x{Dh}x{rows}")
+        # the two GEMMs of the gated FFN that carry the SwiGLU in their epilogues (what the model runs for this layer)
+        us_ = [torch.empty((rows, F), dtype=torch.bfloat16, device=dev) for _ in range(4)]
+        us = time_launches([lambda i=i: call("gaot_gemm_bf16_swiglu", ptr(xs[i]), ptr(w13), ptr(ys[i]), ptr(us_[i]), rows, 2 * F, Dh)
+                            for i in range(4)], 20)
+        entry("gaot_gemm_bf16_swiglu", "gemm_bf16_tc_kernel<256,0,0,2> + SwiGLU epilogue", 2.0 * rows * 2 * F * Dh, us,
+              f"x W13^T with u = silu(a) * b in the epilogue, {rows}x{2 * F}x{Dh}: writes {rows * 3 * F * 2 / 1e6:.0f} MB")
+        w2 = rnd((Dh, F), torch.bfloat16, F ** -0.5)
+        dabs = [torch.empty((rows, 2 * F), dtype=torch.bfloat16, device=dev) for _ in range(2)]
+        us = time_launches([lambda i=i: call("gaot_gemm_bf16_nn_swiglu_bwd", ptr(xs[i]), ptr(w2), ptr(ys[i]), ptr(dabs[i % 2]), rows, F, Dh)
+                            for i in range(4)], 20)
+        entry("gaot_gemm_bf16_nn_swiglu_bwd", "gemm_bf16_tc_kernel<256,0,1,2> + SwiGLU backward epilogue", 2.0 * rows * F * Dh, us,
+              f"dU = dY W2 consumed in the epilogue, {rows}x{F}x{Dh}: reads and writes {rows * 2 * F * 2 / 1e6:.0f} MB each")
     else:
         sets = []
         for i in range(copies):
@@ -754,7 +766,7 @@ def run_reference(args, w):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
