@@ -24,7 +24,7 @@ namespace {
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;          // 64 bf16 = 128 bytes = one SWIZZLE_128B row
-constexpr int TC_STAGES = 4;          // 4 x 32 KB in flight: the K = 256 main loop is L2 -> SM bandwidth bound, not latency bound
+constexpr int TC_STAGES = 5;          // 5 x 32 KB in flight (with 64 KB of epilogue staging: 225 KB): one stage more than a K = 256 tile, so the ring runs ahead across tiles
 constexpr int TC_THREADS = 320;        // TMA warp, MMA warp, 8 epilogue warps
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
