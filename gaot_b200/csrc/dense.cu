@@ -480,8 +480,10 @@ __global__ void __launch_bounds__(256) rmsnorm_fwd_vec_kernel(const float* __res
     }
 }
 
+// (register cap: without it ptxas spends 105 registers per thread at KMAX = 2 on address arithmetic it keeps live across the row
+// loop, two CTAs per SM fit, and the kernel runs at 3.3 TB/s on the latency of its one row per warp in flight)
 template <int KMAX>
-__global__ void __launch_bounds__(256) rmsnorm_bwd_vec_kernel(const float* __restrict__ dy, const __nv_bfloat16* __restrict__ dy16,
+__global__ void __launch_bounds__(256, KMAX <= 2 ? 4 : (KMAX <= 4 ? 2 : 1)) rmsnorm_bwd_vec_kernel(const float* __restrict__ dy, const __nv_bfloat16* __restrict__ dy16,
                                                               const float* __restrict__ x, const float* __restrict__ gamma,
                                                               const float* __restrict__ rstd, float* __restrict__ dx,
                                                               float* __restrict__ dgamma, int64_t rows, int D) {
@@ -539,7 +541,12 @@ __global__ void __launch_bounds__(256) rmsnorm_bwd_vec_kernel(const float* __res
         }
     }
     __syncthreads();
-    for (int c = threadIdx.x; c < D; c += blockDim.x) atomicAdd(dgamma + c, sdg[c]);
+    if ((reinterpret_cast<uintptr_t>(dgamma) & 15) == 0) {
+        for (int c = threadIdx.x * 4; c < D; c += blockDim.x * 4)      // D % 4 == 0 on this path
+            atomicAdd(reinterpret_cast<float4*>(dgamma + c), make_float4(sdg[c], sdg[c + 1], sdg[c + 2], sdg[c + 3]));
+    } else {
+        for (int c = threadIdx.x; c < D; c += blockDim.x) atomicAdd(dgamma + c, sdg[c]);
+    }
 }
 
 
