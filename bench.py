@@ -585,6 +585,8 @@ def run_ours(args, w):
         return float(loss)                                                     # .item(): D2H read of the loss
 
     W = max(args.warmup, 3)
+    if case.vx and case.rotate:
+        W = max(W, 2 * len(case.rotate))       # every distinct mesh batch twice: the allocator has seen all edge counts
     for _ in range(W):
         case.dev_step()
     sampler = ClockSampler(D.local) if rank == 0 else None
