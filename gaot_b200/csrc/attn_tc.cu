@@ -480,30 +480,39 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttnArgs g) {
             FTRACE(i * 8 + 5);
             const uint32_t pbase = smem_u32(sP) + (uint32_t)((i & 1) * P_BYTES + hf * (AT_BQ * 128));
             float ps4[4] = {0.f, 0.f, 0.f, 0.f};           // four independent summation chains
+            // two copies of the loop behind ONE warp-uniform branch: the ragged-tile masks (a compare and a select per
+            // score) otherwise run on every element of every tile and kept the ALU pipe as busy as the MUFU pipe
+            auto emit_p = [&](auto full_tag) {
+                constexpr bool FULL = decltype(full_tag)::value;
 #pragma unroll
-            for (int c = 0; c < 2; ++c) {
+                for (int c = 0; c < 2; ++c) {
 #pragma unroll
-                for (int w = 0; w < 4; ++w) {              // 8 columns -> one 16-byte swizzled store
-                    float p[8];
+                    for (int w = 0; w < 4; ++w) {          // 8 columns -> one 16-byte swizzled store
+                        float p[8];
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        const int j = w * 8 + k;
-                        p[k] = ex2(fmaf(__uint_as_float(sv[c][j]), sl2, -mref));
-                        if (!full_tile && c * 32 + j >= kv_left) p[k] = 0.f;
-                        ps4[k & 3] += p[k];
-                    }
-                    if constexpr (SPLIT) {
-                        uint32_t ph[4], pl[4];
+                        for (int k = 0; k < 8; ++k) {
+                            const int j = w * 8 + k;
+                            p[k] = ex2(fmaf(__uint_as_float(sv[c][j]), sl2, -mref));
+                            if constexpr (!FULL) {
+                                if (c * 32 + j >= kv_left) p[k] = 0.f;
+                            }
+                            ps4[k & 3] += p[k];
+                        }
+                        if constexpr (SPLIT) {
+                            uint32_t ph[4], pl[4];
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) pack_split2(p[2 * k] * AT_PSCALE_FWD, p[2 * k + 1] * AT_PSCALE_FWD, ph[k], pl[k]);
-                        sts_u4_(pbase + sw128_off(r, c * 4 + w), ph[0], ph[1], ph[2], ph[3]);
-                        sts_u4_(pbase + PP_BYTES + sw128_off(r, c * 4 + w), pl[0], pl[1], pl[2], pl[3]);
-                    } else {
-                        sts_u4_(pbase + sw128_off(r, c * 4 + w), pack_bf16(p[0], p[1]), pack_bf16(p[2], p[3]), pack_bf16(p[4], p[5]),
-                                pack_bf16(p[6], p[7]));
+                            for (int k = 0; k < 4; ++k) pack_split2(p[2 * k] * AT_PSCALE_FWD, p[2 * k + 1] * AT_PSCALE_FWD, ph[k], pl[k]);
+                            sts_u4_(pbase + sw128_off(r, c * 4 + w), ph[0], ph[1], ph[2], ph[3]);
+                            sts_u4_(pbase + PP_BYTES + sw128_off(r, c * 4 + w), pl[0], pl[1], pl[2], pl[3]);
+                        } else {
+                            sts_u4_(pbase + sw128_off(r, c * 4 + w), pack_bf16(p[0], p[1]), pack_bf16(p[2], p[3]), pack_bf16(p[4], p[5]),
+                                    pack_bf16(p[6], p[7]));
+                        }
                     }
                 }
-            }
+            };
+            if (full_tile) emit_p(std::true_type{});
+            else emit_p(std::false_type{});
             lsum += (ps4[0] + ps4[1]) + (ps4[2] + ps4[3]);
             FTRACE(i * 8 + 6);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes of P -> async proxy (MMA)

@@ -90,7 +90,8 @@ def test_model_bf16_mode_close_to_reference(name):
             assert rel_l2(p.grad, g["grad." + k]) < 0.1, k
 
 
-@pytest.mark.parametrize("B,T,H,Hkv,hd", [(2, 256, 2, 2, 32), (1, 1024, 8, 8, 32), (2, 200, 4, 2, 32), (1, 384, 2, 2, 64), (1, 130, 2, 1, 16)])
+@pytest.mark.parametrize("B,T,H,Hkv,hd", [(2, 256, 2, 2, 32), (1, 1024, 8, 8, 32), (2, 200, 4, 2, 32), (1, 384, 2, 2, 64), (1, 130, 2, 1, 16),
+                                          (3, 40, 2, 2, 32), (2, 72, 2, 1, 16)])
 def test_attention_fwd_bf16_vs_fp64(B, T, H, Hkv, hd):
     from gaot_b200 import _lib
     from gaot_b200._lib import call, ptr
@@ -110,7 +111,8 @@ def test_attention_fwd_bf16_vs_fp64(B, T, H, Hkv, hd):
     assert rel_l2(o, want) < 8e-3            # P and O are rounded to bf16
 
 
-@pytest.mark.parametrize("B,T,H,Hkv,hd", [(2, 256, 2, 2, 32), (1, 1024, 8, 8, 32), (2, 200, 4, 2, 32), (1, 384, 2, 2, 64), (1, 130, 2, 1, 16)])
+@pytest.mark.parametrize("B,T,H,Hkv,hd", [(2, 256, 2, 2, 32), (1, 1024, 8, 8, 32), (2, 200, 4, 2, 32), (1, 384, 2, 2, 64), (1, 130, 2, 1, 16),
+                                          (3, 40, 2, 2, 32), (2, 72, 2, 1, 16)])
 def test_attention_bwd_bf16_vs_fp64(B, T, H, Hkv, hd):
     from gaot_b200 import ops
     W = (H + 2 * Hkv) * hd
