@@ -408,6 +408,7 @@ def magno_kernels(case, peaks):
     we_m, wd_m = S.normal((pe.E, C), 14).to(dev), S.normal((Cout, pd.E, C), 15).to(dev)
     lat_f = S.normal((Bc, M, C), 16).to(dev)
     g_enc, g_dec = S.normal((Bc, M, C), 17).to(dev), S.normal((Bc, N, Cout), 18).to(dev)
+    pn_t_m = pn_m.permute(1, 0, 2).contiguous() if Bc % 8 == 0 else None     # sample-minor copy, as ops.lift_aggregate makes it
     with torch.no_grad():
         t = med_us(lambda: O.lift_aggregate(pn_m, Wl_m, bl_m, we_m, pe))
         add("lift_aggregate_fwd (encoder)", N, M, t, alg_fwd(Bc, N, M), 4.0 * Bc * N * Cin + 4.0 * C * E + 8.0 * E + 4.0 * C * Bc * M)
@@ -422,7 +423,7 @@ def magno_kernels(case, peaks):
         dw_, dWl_, dbl_ = torch.empty_like(we_m), torch.empty_like(Wl_m), torch.empty_like(bl_m)
         t = med_us(lambda: _lib.call("gaot_lift_aggregate_bwd", g_enc.data_ptr(), pn_m.data_ptr(), Wl_m.data_ptr(), bl_m.data_ptr(),
                                       we_m.data_ptr(), pe.index.data_ptr(), pe.splits.data_ptr(), dw_.data_ptr(), dWl_.data_ptr(),
-                                      dbl_.data_ptr(), Bc, N, int(M), pe.E, C, Cin))
+                                      dbl_.data_ptr(), Bc, N, int(M), pe.E, C, Cin, pn_t_m.data_ptr() if pn_t_m is not None else 0))
         add("lift_aggregate_bwd (encoder)", N, M, t, alg_bwd(Bc, N, M), 4.0 * Bc * N * Cin + 8.0 * C * E + 8.0 * E + 4.0 * C * Bc * M)
         t = med_us(lambda: _lib.call("gaot_agno_dot_bwd_t", g_dec.data_ptr(), lat_f.data_ptr(), wd_m.data_ptr(), pd.index.data_ptr(),
                                       pd.splits.data_ptr(), ts_.data_ptr(), tr_.data_ptr(), tp_.data_ptr(), df_.data_ptr(), du_.data_ptr(),

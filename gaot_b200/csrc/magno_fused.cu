@@ -45,7 +45,10 @@ __device__ __forceinline__ float dot4(const float4& x, const float4& y) {
 // Edges are taken U at a time: the U neighbour indices and U weight rows of a batch are independent loads, and the U*FB*CIN
 // feature loads that depend on the indices are issued together - one dependent round trip per U edges instead of per edge.
 // The register budget is bounded per instantiation (3 CTAs per SM when FB*CIN <= 8) so more warps hide that round trip.
-template <int G, int CIN, int FB>
+// TP = true: the raw features come from the SAMPLE-MINOR copy pn_t [Ns, B, CIN]: the FB * CIN values an edge needs for the
+// item's chunk of samples are contiguous, i.e. FB * CIN / 4 128-bit loads and ONE address computation per edge instead of
+// FB * CIN scalar loads with an address each (integer address arithmetic was half of this kernel's issue slots).
+template <int G, int CIN, int FB, bool TP>
 __global__ void __launch_bounds__(256, (FB * CIN <= 16) ? 2 : 1)
 lift_aggregate_fwd_kernel(const float* __restrict__ pn, const float* __restrict__ Wl, const float* __restrict__ bl,
                           const float* __restrict__ w, const int64_t* __restrict__ index, const int64_t* __restrict__ rs,
@@ -70,10 +73,12 @@ lift_aggregate_fwd_kernel(const float* __restrict__ pn, const float* __restrict_
         if (item + 2 * ngroups < n_items) { nna = __ldg(rs + (item + 2 * ngroups) % Nd); nne = __ldg(rs + (item + 2 * ngroups) % Nd + 1); }
         const int64_t row = item % Nd;
         const int b0 = (int)(item / Nd) * FB;
-        const float* pb0 = pn + (int64_t)min(b0, B - 1) * Ns * CIN;
-        int pb[FB];                                   // sample offsets relative to the chunk's first sample (FB * Ns * CIN < 2^31)
+        const float* pb0 = TP ? pn + (int64_t)b0 * CIN : pn + (int64_t)min(b0, B - 1) * Ns * CIN;
+        [[maybe_unused]] int pb[FB];                  // sample offsets relative to the chunk's first sample (FB * Ns * CIN < 2^31)
+        if constexpr (!TP) {
 #pragma unroll
-        for (int bb = 0; bb < FB; ++bb) pb[bb] = (int)((int64_t)(min(b0 + bb, B - 1) - min(b0, B - 1)) * Ns * CIN);
+            for (int bb = 0; bb < FB; ++bb) pb[bb] = (int)((int64_t)(min(b0 + bb, B - 1) - min(b0, B - 1)) * Ns * CIN);
+        }
         // s[bb][i] = sum_e w[e,c] pn[b,j,i] (per lane: 4 channels), sw = sum_e w[e,c]
         float4 s[FB][CIN];
         float4 sw = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -88,9 +93,26 @@ lift_aggregate_fwd_kernel(const float* __restrict__ pn, const float* __restrict_
             for (int q = 0; q < U; ++q) {
                 const bool ok = it + q < e;
                 const int64_t ee = ok ? it + q : it;
-                jj[q] = (int)__ldg(index + ee) * CIN;
+                jj[q] = (int)__ldg(index + ee) * (TP ? B * CIN : CIN);
                 wv[q] = ok ? ldg4(w + ee * C + c0) : make_float4(0.f, 0.f, 0.f, 0.f);      // a zero weight masks the tail
             }
+            if constexpr (TP) {
+                constexpr int V4 = FB * CIN / 4;
+                float4 pv[U][V4];
+#pragma unroll
+                for (int q = 0; q < U; ++q)
+#pragma unroll
+                    for (int v = 0; v < V4; ++v) pv[q][v] = ldg4(pb0 + jj[q] + 4 * v);
+#pragma unroll
+                for (int q = 0; q < U; ++q) {
+                    sw.x += wv[q].x; sw.y += wv[q].y; sw.z += wv[q].z; sw.w += wv[q].w;
+                    const float* pf = reinterpret_cast<const float*>(pv[q]);
+#pragma unroll
+                    for (int bb = 0; bb < FB; ++bb)
+#pragma unroll
+                        for (int i = 0; i < CIN; ++i) fma4s(s[bb][i], wv[q], pf[bb * CIN + i]);
+                }
+            } else {
 #pragma unroll
             for (int q = 0; q < U; ++q) {
                 sw.x += wv[q].x; sw.y += wv[q].y; sw.z += wv[q].z; sw.w += wv[q].w;
@@ -98,6 +120,7 @@ lift_aggregate_fwd_kernel(const float* __restrict__ pn, const float* __restrict_
                 for (int bb = 0; bb < FB; ++bb)
 #pragma unroll
                     for (int i = 0; i < CIN; ++i) fma4s(s[bb][i], wv[q], __ldg(pb0 + (pb[bb] + jj[q] + i)));
+            }
             }
         }
         if (gl < nvec) {
@@ -116,7 +139,7 @@ lift_aggregate_fwd_kernel(const float* __restrict__ pn, const float* __restrict_
 }
 
 // (1) backward: dw (atomics over the sample chunks), dWl / dbl (CTA partial sums -> atomics)
-template <int G, int CIN, int FB>
+template <int G, int CIN, int FB, bool TP>
 __global__ void __launch_bounds__(256)
 lift_aggregate_bwd_kernel(const float* __restrict__ g, const float* __restrict__ pn, const float* __restrict__ Wl,
                           const float* __restrict__ bl, const float* __restrict__ w, const int64_t* __restrict__ index,
@@ -147,7 +170,7 @@ lift_aggregate_bwd_kernel(const float* __restrict__ g, const float* __restrict__
 #pragma unroll
         for (int bb = 0; bb < FB; ++bb) {
             const bool ok = b0 + bb < B;
-            boff[bb] = (int64_t)min(b0 + bb, B - 1) * Ns * CIN;
+            boff[bb] = TP ? 0 : (int64_t)min(b0 + bb, B - 1) * Ns * CIN;
             gv[bb] = ok ? ldg4(g + ((int64_t)(b0 + bb) * Nd + row) * C + c0) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         const int64_t a = __ldg(rs + row), e = __ldg(rs + row + 1);
@@ -157,10 +180,23 @@ lift_aggregate_bwd_kernel(const float* __restrict__ g, const float* __restrict__
                 const int64_t jn = __ldg(index + ((it + 1 < e) ? it + 1 : it));
                 const float4 wv = ldg4(w + it * C + c0);
                 float p[FB][CIN];
+                if constexpr (TP) {
+                    constexpr int V4 = FB * CIN / 4;
+                    const float* src = pn + (j * B + b0) * CIN;          // sample-minor copy [Ns, B, CIN]
+                    float4 pv[V4];
+#pragma unroll
+                    for (int v = 0; v < V4; ++v) pv[v] = ldg4(src + 4 * v);
+                    const float* pf = reinterpret_cast<const float*>(pv);
+#pragma unroll
+                    for (int bb = 0; bb < FB; ++bb)
+#pragma unroll
+                        for (int i = 0; i < CIN; ++i) p[bb][i] = pf[bb * CIN + i];
+                } else {
 #pragma unroll
                 for (int bb = 0; bb < FB; ++bb)
 #pragma unroll
                     for (int i = 0; i < CIN; ++i) p[bb][i] = __ldg(pn + boff[bb] + j * CIN + i);
+                }
                 float4 dwe = make_float4(0.f, 0.f, 0.f, 0.f);        // sum_b g * f
                 float4 gsum = make_float4(0.f, 0.f, 0.f, 0.f);       // sum_b g
                 float4 gp[CIN];                                       // sum_b g * pn_i
@@ -612,11 +648,15 @@ inline int group_of(int64_t C) { const int nv = (int)(C / 4); return nv <= 4 ? 4
                   case 3: { constexpr int NAME = 3; __VA_ARGS__; break; } case 4: { constexpr int NAME = 4; __VA_ARGS__; break; } \
                   default: return GAOT_E_BADARG; }
 
+// the sample-minor copy serves a launch when every work item reads whole 16-byte pieces of it
+inline bool use_pn_t(const float* pn_t, int fb, int64_t B, int64_t Ns, int64_t Cin) {
+    return pn_t && al16(pn_t) && (fb * Cin) % 4 == 0 && B % fb == 0 && Ns * B * Cin < 0x7fffffffLL;
+}
 }  // namespace
 
 GAOT_API int gaot_lift_aggregate_fwd(const float* pn, const float* Wl, const float* bl, const float* w, const int64_t* index,
                                      const int64_t* row_splits, float* out, int64_t B, int64_t Ns, int64_t Nd, int64_t C,
-                                     int64_t Cin, void* stream) {
+                                     int64_t Cin, const float* pn_t, void* stream) {
     if (!pn || !Wl || !bl || !w || !index || !row_splits || !out || B < 1 || Ns < 0 || Nd < 0) return GAOT_E_BADARG;
     if (C % 4 || C > 128 || Cin < 1 || Cin > 4) return GAOT_E_BADARG;
     if (!al16(w) || !al16(out) || !al16(bl)) return GAOT_E_ALIGN;
@@ -628,14 +668,20 @@ GAOT_API int gaot_lift_aggregate_fwd(const float* pn, const float* Wl, const flo
     const int resident = fb * (int)Cin <= 16 ? 2 : 1;                                 // CTAs per SM the kernel's register bound allows
     if (blocks > (int64_t)gaot_sm_count() * resident) blocks = (int64_t)gaot_sm_count() * resident;   // persistent grid-stride loop
     cudaStream_t st = (cudaStream_t)stream;
-    GAOT_DISPATCH_FB(fb, GAOT_DISPATCH_G(g_, GAOT_DISPATCH_N((int)Cin, CIN, (lift_aggregate_fwd_kernel<G, CIN, FB><<<(unsigned)blocks, 256, 0, st>>>(
-                                                          pn, Wl, bl, w, index, row_splits, out, (int)B, Ns, Nd, (int)C, n_items)))));
+    if (use_pn_t(pn_t, fb, B, Ns, Cin)) {
+        GAOT_DISPATCH_FB(fb, GAOT_DISPATCH_G(g_, GAOT_DISPATCH_N((int)Cin, CIN, (lift_aggregate_fwd_kernel<G, CIN, FB, (FB * CIN) % 4 == 0><<<(unsigned)blocks, 256, 0, st>>>(
+                                                              pn_t, Wl, bl, w, index, row_splits, out, (int)B, Ns, Nd, (int)C, n_items)))));
+    } else {
+        GAOT_DISPATCH_FB(fb, GAOT_DISPATCH_G(g_, GAOT_DISPATCH_N((int)Cin, CIN, (lift_aggregate_fwd_kernel<G, CIN, FB, false><<<(unsigned)blocks, 256, 0, st>>>(
+                                                              pn, Wl, bl, w, index, row_splits, out, (int)B, Ns, Nd, (int)C, n_items)))));
+    }
     GAOT_RETURN_LAST();
 }
 
 GAOT_API int gaot_lift_aggregate_bwd(const float* g, const float* pn, const float* Wl, const float* bl, const float* w,
                                      const int64_t* index, const int64_t* row_splits, float* dw, float* dWl, float* dbl,
-                                     int64_t B, int64_t Ns, int64_t Nd, int64_t E, int64_t C, int64_t Cin, void* stream) {
+                                     int64_t B, int64_t Ns, int64_t Nd, int64_t E, int64_t C, int64_t Cin, const float* pn_t,
+                                     void* stream) {
     if (!g || !pn || !Wl || !bl || !w || !index || !row_splits || !dw || !dWl || !dbl || B < 1 || E < 0) return GAOT_E_BADARG;
     if (C % 4 || C > 128 || Cin < 1 || Cin > 4) return GAOT_E_BADARG;
     if (!al16(w) || !al16(g) || !al16(dw) || !al16(bl)) return GAOT_E_ALIGN;
@@ -651,9 +697,15 @@ GAOT_API int gaot_lift_aggregate_bwd(const float* g, const float* pn, const floa
     const int64_t blocks = (n_items * g_ + 255) / 256;
     if (blocks > 0x7fffffffLL) return GAOT_E_BADARG;
     const size_t smem = sizeof(float) * (size_t)(C * (Cin + 1));
-    GAOT_DISPATCH_FB(fb, GAOT_DISPATCH_G(g_, GAOT_DISPATCH_N((int)Cin, CIN, (lift_aggregate_bwd_kernel<G, CIN, FB><<<(unsigned)blocks, 256, smem, st>>>(
-                                                          g, pn, Wl, bl, w, index, row_splits, dw, dWl, dbl, (int)B, Ns, Nd, (int)C,
-                                                          n_items, chunks)))));
+    if (use_pn_t(pn_t, fb, B, Ns, Cin)) {
+        GAOT_DISPATCH_FB(fb, GAOT_DISPATCH_G(g_, GAOT_DISPATCH_N((int)Cin, CIN, (lift_aggregate_bwd_kernel<G, CIN, FB, (FB * CIN) % 4 == 0><<<(unsigned)blocks, 256, smem, st>>>(
+                                                              g, pn_t, Wl, bl, w, index, row_splits, dw, dWl, dbl, (int)B, Ns, Nd, (int)C,
+                                                              n_items, chunks)))));
+    } else {
+        GAOT_DISPATCH_FB(fb, GAOT_DISPATCH_G(g_, GAOT_DISPATCH_N((int)Cin, CIN, (lift_aggregate_bwd_kernel<G, CIN, FB, false><<<(unsigned)blocks, 256, smem, st>>>(
+                                                              g, pn, Wl, bl, w, index, row_splits, dw, dWl, dbl, (int)B, Ns, Nd, (int)C,
+                                                              n_items, chunks)))));
+    }
     GAOT_RETURN_LAST();
 }
 

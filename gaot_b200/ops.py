@@ -1119,15 +1119,18 @@ class _LiftAggregate(torch.autograd.Function):
         if Ns != plan.n_src or w.shape[0] != plan.E or w.shape[1] != C:
             raise ValueError(f"lift_aggregate: pn {tuple(pn.shape)} / w {tuple(w.shape)} do not match graph")
         out = torch.empty((B, plan.m, C), dtype=torch.float32, device=pn.device)
+        # sample-minor copy [Ns, B, Cin] (1 MB at cfg-2): the kernels read the 8 samples of a work item with two 128-bit
+        # loads per edge instead of 8 scalar gathers (used when B is a multiple of the 8-sample chunk)
+        pn_t = pn.permute(1, 0, 2).contiguous() if (B % 8 == 0 and (8 * Cin) % 4 == 0) else None
         call("gaot_lift_aggregate_fwd", ptr(pn), ptr(Wl), ptr(bl), ptr(w), ptr(plan.index), ptr(plan.splits), ptr(out), B, Ns,
-             plan.m, C, Cin)
-        ctx.save_for_backward(pn, Wl, bl, w)
+             plan.m, C, Cin, ptr(pn_t))
+        ctx.save_for_backward(pn, Wl, bl, w, pn_t)
         ctx.plan = plan
         return out
 
     @staticmethod
     def backward(ctx, g):
-        pn, Wl, bl, w = ctx.saved_tensors
+        pn, Wl, bl, w, pn_t = ctx.saved_tensors
         plan = ctx.plan
         if ctx.needs_input_grad[0]:
             raise _lib.GaotLibraryError("lift_aggregate has no gradient for its raw inputs; use the unfused lifting + "
@@ -1137,7 +1140,7 @@ class _LiftAggregate(torch.autograd.Function):
         C = Wl.shape[0]
         dw, dWl, dbl = torch.empty_like(w), torch.empty_like(Wl), torch.empty_like(bl)
         call("gaot_lift_aggregate_bwd", ptr(g), ptr(pn), ptr(Wl), ptr(bl), ptr(w), ptr(plan.index), ptr(plan.splits), ptr(dw),
-             ptr(dWl), ptr(dbl), B, Ns, plan.m, plan.E, C, Cin)
+             ptr(dWl), ptr(dbl), B, Ns, plan.m, plan.E, C, Cin, ptr(pn_t))
         return None, dWl, dbl, dw, None
 
 

@@ -133,14 +133,17 @@ int gaot_agno_weight_grad(const float* g, const float* f, const int64_t* index,
 /* Fused lifting + aggregate (encoder): out[b,r,c] = sum_{e in r} w[e,c] * (sum_i Wl[c,i] pn[b,index[e],i] + bl[c]).
  * Replaces ChannelMLP lifting (magno.py:273-274, mlp.py:274-275: a single affine map) followed by the
  * gather/multiply/segment_csr chain of agno.py:198,245-271 without materialising the lifted features.
- * pn [B,Ns,Cin], Wl [C,Cin], bl [C], w [E,C]; Cin <= 4, C % 4 == 0, C <= 128. */
+ * pn [B,Ns,Cin], Wl [C,Cin], bl [C], w [E,C]; Cin <= 4, C % 4 == 0, C <= 128.
+ * pn_t (optional, may be NULL): the same features SAMPLE-MINOR, [Ns,B,Cin]; when B is a multiple of the kernel's sample
+ * chunk (8 for B >= 8) and chunk * Cin % 4 == 0 the gather reads it instead - one 128-bit load per 4 samples. */
 int gaot_lift_aggregate_fwd(const float* pn, const float* Wl, const float* bl, const float* w, const int64_t* index,
                             const int64_t* row_splits, float* out, int64_t B, int64_t Ns, int64_t Nd, int64_t C,
-                            int64_t Cin, void* stream);
+                            int64_t Cin, const float* pn_t, void* stream);
 /* its backward: dw [E,C], dWl [C,Cin], dbl [C] (all overwritten); pn carries no gradient. */
 int gaot_lift_aggregate_bwd(const float* g, const float* pn, const float* Wl, const float* bl, const float* w,
                             const int64_t* index, const int64_t* row_splits, float* dw, float* dWl, float* dbl,
-                            int64_t B, int64_t Ns, int64_t Nd, int64_t E, int64_t C, int64_t Cin, void* stream);
+                            int64_t B, int64_t Ns, int64_t Nd, int64_t E, int64_t C, int64_t Cin, const float* pn_t,
+                            void* stream);
 
 /* Fused aggregate + affine read-out (decoder): out[b,r,o] = sum_{e in r} <u[o,e,:], f[b,index[e],:]>, with
  * u[o,e,c] = (W_proj W_rec_a)[o,c] * w[e,c] folded by the caller.  Replaces agno.py:198-271 followed by the

@@ -191,14 +191,18 @@ def gaot_agno_weight_grad(gr, f, index, row_splits, dw, B, Ns, Nd, E, C):
     _arr(dw, (E, C))[:] = (G[:, seg, :] * F[:, g["neighbors_index"], :]).sum(0).float().numpy()
 
 
-def gaot_lift_aggregate_fwd(pn, Wl, bl, w, index, row_splits, out, B, Ns, Nd, C, Cin):
+def gaot_lift_aggregate_fwd(pn, Wl, bl, w, index, row_splits, out, B, Ns, Nd, C, Cin, pn_t):
+    if pn_t:                                              # the sample-minor copy must hold the same values
+        assert torch.equal(_t(pn_t, (Ns, B, Cin)).permute(1, 0, 2), _t(pn, (B, Ns, Cin)))
     g, E = _csr(index, row_splits, Nd)
     f = _t(pn, (B, Ns, Cin)).double() @ _t(Wl, (C, Cin)).double().T + _t(bl, (C,)).double()
     msg = _t(w, (E, C)).double().unsqueeze(0) * f[:, g["neighbors_index"], :]
     _arr(out, (B, Nd, C))[:] = orc.segment_csr(msg, g["neighbors_row_splits"], "sum").float().numpy()
 
 
-def gaot_lift_aggregate_bwd(gr, pn, Wl, bl, w, index, row_splits, dw, dWl, dbl, B, Ns, Nd, E, C, Cin):
+def gaot_lift_aggregate_bwd(gr, pn, Wl, bl, w, index, row_splits, dw, dWl, dbl, B, Ns, Nd, E, C, Cin, pn_t):
+    if pn_t:
+        assert torch.equal(_t(pn_t, (Ns, B, Cin)).permute(1, 0, 2), _t(pn, (B, Ns, Cin)))
     g, _ = _csr(index, row_splits, Nd)
     with torch.enable_grad():
         wl = _t(Wl, (C, Cin)).double().requires_grad_(True)

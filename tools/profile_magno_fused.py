@@ -18,6 +18,7 @@ x = synth.uniform_points(N, 2, 0).to(dev)
 lat = synth.latent_grid((64, 64)).to(dev)
 pe, pd = ops.graph_plan(ops.radius_csr(x, lat, 0.033), N), ops.graph_plan(ops.radius_csr(lat, x, 0.033), M)
 pn = synth.normal((B, N, 1), 5).to(dev)
+pn_t = pn.permute(1, 0, 2).contiguous()
 Wl, bl = synth.normal((C, 1), 6).to(dev), synth.normal((C,), 7).to(dev)
 we, u = synth.normal((pe.E, C), 3).to(dev), synth.normal((1, pd.E, C), 8).to(dev)
 fl = synth.normal((B, M, C), 2).to(dev)
@@ -29,9 +30,9 @@ ts, tr, tp = pd.transposed()
 flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
 P = lambda t: t.data_ptr()  # noqa: E731
 calls = {
-    "lift_aggregate_fwd": lambda: _lib.call("gaot_lift_aggregate_fwd", P(pn), P(Wl), P(bl), P(we), P(pe.index), P(pe.splits), P(out_e), B, N, M, C, 1),
+    "lift_aggregate_fwd": lambda: _lib.call("gaot_lift_aggregate_fwd", P(pn), P(Wl), P(bl), P(we), P(pe.index), P(pe.splits), P(out_e), B, N, M, C, 1, P(pn_t)),
     "lift_aggregate_bwd": lambda: _lib.call("gaot_lift_aggregate_bwd", P(g_enc), P(pn), P(Wl), P(bl), P(we), P(pe.index), P(pe.splits), P(dw),
-                                            P(dWl), P(dbl), B, N, M, pe.E, C, 1),
+                                            P(dWl), P(dbl), B, N, M, pe.E, C, 1, P(pn_t)),
     "agno_dot_fwd_t": lambda: _lib.call("gaot_agno_dot_fwd_t", P(fl), P(u), P(ts), P(tr), P(tp), P(out_d), B, M, N, pd.E, C, 1),
     "agno_dot_bwd_t": lambda: _lib.call("gaot_agno_dot_bwd_t", P(g_dec), P(fl), P(u), P(pd.index), P(pd.splits), P(ts), P(tr), P(tp), P(df), P(du), B, M, N, pd.E, C, 1),
     "agno_dot_fwd": lambda: _lib.call("gaot_agno_dot_fwd", P(fl), P(u), P(pd.index), P(pd.splits), P(out_d), B, M, N, pd.E, C, 1),
