@@ -628,6 +628,91 @@ agno_dot_s_kernel(const float* __restrict__ r, const float* __restrict__ u, cons
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// (2-du) du of the decoder operator on the transposed graph with one LANE per CHANNEL: du[o, e_k, :] = sum_b g[b, row_k, o] r[b, j, :]
+// for the edges e_k leaving source j.  A warp owns a source node: for every sample it reads the latent row r[b, j, :] ONCE
+// (coalesced, lane l holds channels l, l + 32, ..) and the upstream gradients g[b, row_k, o] as warp-uniform (broadcast) loads,
+// and accumulates the KE edge gradients in registers - no reduction across lanes, no atomics, no zero fill, every latent row
+// read once per pass of KE edges (33.5 MB per pass at cfg-2) where the row walk gathers it once per edge (257 MB through the L2).
+// ---------------------------------------------------------------------------------------------
+template <int VPL, int COUT>
+__global__ void __launch_bounds__(256)
+agno_dot_du_c_kernel(const float* __restrict__ r, const float* __restrict__ g, const int64_t* __restrict__ t_rows,
+                     const int64_t* __restrict__ t_perm, const int64_t* __restrict__ ts, float* __restrict__ du, int B, int Ns,
+                     int Nd, int64_t E) {
+    constexpr int C = 32 * VPL;
+    constexpr int KE = COUT == 1 ? 8 : 4;              // edges per pass (accumulators: KE * COUT * VPL registers)
+    // upstream gradients of a pass, staged per warp as [edge][o][sample]: lane b fetches g[b, row_k, o] once (one load per
+    // lane and edge), the accumulation loop reads them back four samples at a time as warp-uniform 128-bit loads
+    __shared__ __align__(16) float gs_all[8][KE * COUT][32];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    float (*gs)[32] = gs_all[wib];
+    const int64_t j = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (j >= Ns) return;                               // whole warps leave together
+    const int64_t a = __ldg(ts + j), e = __ldg(ts + j + 1);
+    const float* rj = r + j * C + lane;
+    const int64_t rstride = (int64_t)Ns * C, gstride = (int64_t)Nd * COUT;
+    for (int64_t k0 = a; k0 < e; k0 += KE) {
+        const int ne = (int)min((int64_t)KE, e - k0);
+        int myrow = 0;
+        int64_t mype = 0;
+        if (lane < ne) { myrow = (int)__ldg(t_rows + k0 + lane); mype = __ldg(t_perm + k0 + lane); }
+        int rows[KE];
+#pragma unroll
+        for (int k = 0; k < KE; ++k) rows[k] = __shfl_sync(0xffffffffu, myrow, k < ne ? k : 0);
+        float tot[KE][COUT][VPL];
+#pragma unroll
+        for (int k = 0; k < KE; ++k)
+#pragma unroll
+            for (int o = 0; o < COUT; ++o)
+#pragma unroll
+                for (int v = 0; v < VPL; ++v) tot[k][o][v] = 0.f;
+        for (int b0 = 0; b0 < B; b0 += 32) {           // slices of 32 samples
+            const int bl = b0 + lane;
+            __syncwarp();                              // the previous slice / pass has been read
+#pragma unroll
+            for (int k = 0; k < KE; ++k)
+#pragma unroll
+                for (int o = 0; o < COUT; ++o)
+                    gs[k * COUT + o][lane] = (bl < B && k < ne) ? __ldg(g + bl * gstride + (int64_t)rows[k] * COUT + o) : 0.f;
+            __syncwarp();
+            const int nb = min(32, B - b0);
+            // (fully unrolled, with the row loads of all eight steps hoisted, the kernel needs 80 registers - three CTAs per SM
+            // instead of four - and ran 36 -> 43 us; capped at 64 registers it spills)
+#pragma unroll 1
+            for (int b4 = 0; b4 < nb; b4 += 4) {
+                float rv[4][VPL];
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+#pragma unroll
+                    for (int v = 0; v < VPL; ++v) rv[q][v] = __ldg(rj + (int64_t)min(b0 + b4 + q, B - 1) * rstride + 32 * v);   // a zero g masks the tail
+#pragma unroll
+                for (int k = 0; k < KE; ++k)
+#pragma unroll
+                    for (int o = 0; o < COUT; ++o) {
+                        const float4 g4 = *reinterpret_cast<const float4*>(&gs[k * COUT + o][b4]);
+#pragma unroll
+                        for (int v = 0; v < VPL; ++v) {
+                            float t = tot[k][o][v];
+                            t = fmaf(g4.x, rv[0][v], t); t = fmaf(g4.y, rv[1][v], t); t = fmaf(g4.z, rv[2][v], t); t = fmaf(g4.w, rv[3][v], t);
+                            tot[k][o][v] = t;
+                        }
+                    }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < KE; ++k) {
+            const int64_t pe = __shfl_sync(0xffffffffu, mype, k < ne ? k : 0);
+            if (k < ne) {
+#pragma unroll
+                for (int o = 0; o < COUT; ++o)
+#pragma unroll
+                    for (int v = 0; v < VPL; ++v) du[((int64_t)o * E + pe) * C + 32 * v + lane] = tot[k][o][v];
+            }
+        }
+    }
+}
+
 inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 inline int fb_of(int64_t B) {
     static int cap = 0;                                // GAOT_B200_FB: experiment knob, samples per work item of the encoder kernels
@@ -843,7 +928,16 @@ GAOT_API int gaot_agno_dot_bwd_t(const float* g, const float* r, const float* u,
         // formed in registers and stored once); du, the product that reduces over samples, on the row-sorted graph
         int launches = 0;
         if (dr && launch_dot_s<true>(r, u, g, t_rows, t_perm, t_splits, dr, (int)B, (int)Ns, (int)Nd, E, (int)C, (int)Cout, st)) ++launches;
-        if (du && Nd > 0 && E > 0) {
+        static const bool du_rows = getenv("GAOT_B200_DU_ROW_WALK") != nullptr;    // experiment switch: the row-walk du kernel
+        if (du && Nd > 0 && E > 0 && (C == 32 || C == 64) && !du_rows) {
+            // du with one lane per channel on the transposed graph: every edge has exactly one owner (its source), so the
+            // kernel overwrites du without atomics or a zero fill
+            const int64_t blocks = (Ns * 32 + 255) / 256;
+            if (blocks > 0x7fffffffLL) return GAOT_E_BADARG;
+            if (C == 32) { GAOT_DISPATCH_N((int)Cout, COUT, (agno_dot_du_c_kernel<1, COUT><<<(unsigned)blocks, 256, 0, st>>>(r, g, t_rows, t_perm, t_splits, du, (int)B, (int)Ns, (int)Nd, E))); }
+            else { GAOT_DISPATCH_N((int)Cout, COUT, (agno_dot_du_c_kernel<2, COUT><<<(unsigned)blocks, 256, 0, st>>>(r, g, t_rows, t_perm, t_splits, du, (int)B, (int)Ns, (int)Nd, E))); }
+            ++launches;
+        } else if (du && Nd > 0 && E > 0) {
             const int bsplit = (int)((B + 7) / 8);
             if (bsplit > 1) GAOT_CHECK(cudaMemsetAsync(du, 0, sizeof(float) * (size_t)(Cout * E * C), st));
             const int64_t n_items = Nd * bsplit;
