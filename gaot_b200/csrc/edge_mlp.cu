@@ -107,7 +107,8 @@ __device__ __forceinline__ float ex2f(float x) {
 }
 __device__ __forceinline__ void gelu_both(float x, float& y, float& dy) {
     const float u = fabsf(x) * 0.70710678118654752f;
-    const float t = __frcp_rn(fmaf(0.3275911f, u, 1.0f));
+    float t;                                                         // 1 / (1 + p u): ONE MUFU.RCP (the argument is in [1, inf); __frcp_rn
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, u, 1.0f)));   // compiles to a Newton step plus a slow-path call)
     const float ex = ex2f(x * x * -0.72134752044448170f);           // exp(-x^2 / 2)
     float p = fmaf(1.061405429f, t, -1.453152027f);
     p = fmaf(p, t, 1.421413741f);
@@ -162,14 +163,43 @@ __device__ __forceinline__ void store_row_bf16(uint32_t tile, int r, int hf, con
                pack_bf16(v[8 * c + 4], v[8 * c + 5]), pack_bf16(v[8 * c + 6], v[8 * c + 7]));
 }
 
+// explicit shared-state-space loads on 32-bit addresses (through the generic pointers derived from the aligned dynamic-smem
+// base these reads compiled to LD.E with 64-bit address arithmetic)
+__device__ __forceinline__ float lds_f32(uint32_t a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ float4 lds_f4(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+// v[o] += bias[o] for this thread's 32 columns (warp-uniform 128-bit loads)
+__device__ __forceinline__ void add_bias(uint32_t bias_s, float (&v)[EM_HW]) {
+#pragma unroll
+    for (int o = 0; o < EM_HW; o += 4) {
+        const float4 b4 = lds_f4(bias_s + (uint32_t)o * 4u);
+        v[o] += b4.x; v[o + 1] += b4.y; v[o + 2] += b4.z; v[o + 3] += b4.w;
+    }
+}
 // layer 1 on the FP32 pipe, this thread's 32 outputs: z[o] = b1[o] + sum_i W1[o, i] * z0[i]; W1 / b1 in shared memory
 template <int KIN>
 __device__ __forceinline__ void layer1(const float* sW1, const float* sb1, int hf, const float (&z0)[KIN], float (&z)[EM_HW]) {
+    const uint32_t w_s = smem_u32(sW1) + (uint32_t)(hf * EM_HW * KIN) * 4u, b_s = smem_u32(sb1) + (uint32_t)(hf * EM_HW) * 4u;
 #pragma unroll
     for (int o = 0; o < EM_HW; ++o) {
-        float acc = sb1[hf * EM_HW + o];
+        float acc = lds_f32(b_s + (uint32_t)o * 4u);
+        if constexpr (KIN % 4 == 0) {
 #pragma unroll
-        for (int i = 0; i < KIN; ++i) acc = fmaf(sW1[(hf * EM_HW + o) * KIN + i], z0[i], acc);
+            for (int i = 0; i < KIN; i += 4) {
+                const float4 w4 = lds_f4(w_s + (uint32_t)(o * KIN + i) * 4u);
+                acc = fmaf(w4.x, z0[i], acc); acc = fmaf(w4.y, z0[i + 1], acc); acc = fmaf(w4.z, z0[i + 2], acc); acc = fmaf(w4.w, z0[i + 3], acc);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < KIN; ++i) acc = fmaf(lds_f32(w_s + (uint32_t)(o * KIN + i) * 4u), z0[i], acc);
+        }
         z[o] = acc;
     }
 }
@@ -267,16 +297,16 @@ edge_mlp_fwd_tc_kernel(const EdgeMlpArgs g) {
             mbar_wait(bar, phase);
             phase ^= 1u;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const float* bl = sb + (1 + l) * EM_H + hf * EM_HW;
+            const uint32_t bl_s = smem_u32(sb) + (uint32_t)((1 + l) * EM_H + hf * EM_HW) * 4u;
             uint32_t acc[32];
             tmem_ld32(tacc, acc);
             tmem_wait_ld();
+#pragma unroll
+            for (int o = 0; o < EM_HW; ++o) v[o] = __uint_as_float(acc[o]);
+            add_bias(bl_s, v);
             if (l < nh) {
 #pragma unroll
-                for (int o = 0; o < EM_HW; ++o) v[o] = gelu_fast(__uint_as_float(acc[o]) + bl[o]);
-            } else {
-#pragma unroll
-                for (int o = 0; o < EM_HW; ++o) v[o] = __uint_as_float(acc[o]) + bl[o];
+                for (int o = 0; o < EM_HW; ++o) v[o] = gelu_fast(v[o]);
             }
         }
         if (ok) {
@@ -499,12 +529,13 @@ edge_mlp_bwd_tc_kernel(const EdgeMlpArgs g) {
                     mma_forward(tmem, s_tile, smem_u32(sWt + (l - 1) * EM_WBYTES), EM_H, bar);
                 }
                 wait_mma();
-                const float* bl = sb + l * EM_H + hf * EM_HW;
+                const uint32_t bl_s = smem_u32(sb) + (uint32_t)(l * EM_H + hf * EM_HW) * 4u;
                 uint32_t acc[32];
                 tmem_ld32(tacc, acc);
                 tmem_wait_ld();
 #pragma unroll
-                for (int o = 0; o < EM_HW; ++o) v[o] = __uint_as_float(acc[o]) + bl[o];
+                for (int o = 0; o < EM_HW; ++o) v[o] = __uint_as_float(acc[o]);
+                add_bias(bl_s, v);
             }
         }
         // ---- back-propagate: weight tile L = nh (Wo) down to 0 (Wh[0]) ----
