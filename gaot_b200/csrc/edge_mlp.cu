@@ -427,10 +427,12 @@ edge_mlp_bwd_tc_kernel(const EdgeMlpArgs g) {
     uint32_t phase = 0;
     constexpr int KC = KIN / 2;
     // dW1 | db1 on the FP32 pipe: thread-owned (output o, input i) pairs, i == KIN is the bias (ones column of sZ0)
-    constexpr int NPAIR = (EM_H * (KIN + 1) + EM_THREADS - 1) / EM_THREADS;
-    float acc1[NPAIR];
+    // first-layer gradients: thread = (output column o = t % 64, quarter t / 64 of the tile's edges); it keeps dW1[o, 0..KIN) and
+    // db1[o] of its edges: one delta read per edge serves all KIN + 1 products, the edge inputs are warp-uniform loads
+    static_assert(EM_THREADS == 4 * EM_H, "first-layer gradient mapping: 64 columns x 4 edge quarters");
+    float acc1[KIN + 1];
 #pragma unroll
-    for (int p = 0; p < NPAIR; ++p) acc1[p] = 0.f;
+    for (int p = 0; p <= KIN; ++p) acc1[p] = 0.f;
     float dbacc[EM_MAXHID + 1];                                      // column sums of delta (bias gradients of bh[.] / bo): thread t
 #pragma unroll                                                       // owns column t % 64 over the 32 rows of quarter t / 64
     for (int l = 0; l <= EM_MAXHID; ++l) dbacc[l] = 0.f;
@@ -571,18 +573,14 @@ edge_mlp_bwd_tc_kernel(const EdgeMlpArgs g) {
         }
         // ---- first layer: dW1[o, i] += sum_e delta_1[e, o] z0[e, i], db1[o] += sum_e delta_1[e, o] (FP32 pipe) ----
         __syncthreads();
+        {
+            const int o = threadIdx.x & (EM_H - 1), e_lo = (threadIdx.x >> 6) * (EM_TILE / 4);
+            const uint32_t z_s = smem_u32(sZ0), d_col = d_tile + (uint32_t)(o & 7) * 2u;
+#pragma unroll 4
+            for (int ee = e_lo; ee < e_lo + EM_TILE / 4; ++ee) {
+                const float d = lds_bf16(d_col + sw128_off(ee, o >> 3));
 #pragma unroll
-        for (int p = 0; p < NPAIR; ++p) {
-            const int pr = p * EM_THREADS + threadIdx.x;
-            if (pr < EM_H * (KIN + 1)) {
-                const int o = pr % EM_H, i = pr / EM_H;
-                float s0 = 0.f, s1 = 0.f;
-#pragma unroll 8
-                for (int ee = 0; ee < EM_TILE; ee += 2) {
-                    s0 = fmaf(lds_bf16(d_tile + sw128_off(ee, o >> 3) + (uint32_t)(o & 7) * 2u), sZ0[ee * (KIN + 1) + i], s0);
-                    s1 = fmaf(lds_bf16(d_tile + sw128_off(ee + 1, o >> 3) + (uint32_t)(o & 7) * 2u), sZ0[(ee + 1) * (KIN + 1) + i], s1);
-                }
-                acc1[p] += s0 + s1;
+                for (int i = 0; i <= KIN; ++i) acc1[i] = fmaf(d, lds_f32(z_s + (uint32_t)(ee * (KIN + 1) + i) * 4u), acc1[i]);
             }
         }
         __syncthreads();                                             // next tile overwrites sZ0 / sS / sD
@@ -607,13 +605,11 @@ edge_mlp_bwd_tc_kernel(const EdgeMlpArgs g) {
             if (c < rows) atomicAdd(db + c, dbacc[nh - L]);
         }
     }
+    {
+        const int o = threadIdx.x & (EM_H - 1);
 #pragma unroll
-    for (int p = 0; p < NPAIR; ++p) {
-        const int pr = p * EM_THREADS + threadIdx.x;
-        if (pr < EM_H * (KIN + 1)) {
-            const int o = pr % EM_H, i = pr / EM_H;
-            if (i < KIN) atomicAdd(g.dW1 + o * KIN + i, acc1[p]); else atomicAdd(g.db1 + o, acc1[p]);
-        }
+        for (int i = 0; i < KIN; ++i) atomicAdd(g.dW1 + o * KIN + i, acc1[i]);
+        atomicAdd(g.db1 + o, acc1[KIN]);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
