@@ -106,15 +106,15 @@ __device__ __forceinline__ float ex2f(float x) {
     return y;
 }
 __device__ __forceinline__ void gelu_both(float x, float& y, float& dy) {
-    const float u = fabsf(x) * 0.70710678118654752f;
+    // constants folded: p u = (p / sqrt 2) |x|; the polynomial carries the factor 1/2 of (1 - erf) / 2
     float t;                                                         // 1 / (1 + p u): ONE MUFU.RCP (the argument is in [1, inf); __frcp_rn
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, u, 1.0f)));   // compiles to a Newton step plus a slow-path call)
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.23164189f, fabsf(x), 1.0f)));   // compiles to a Newton step plus a slow-path call)
     const float ex = ex2f(x * x * -0.72134752044448170f);           // exp(-x^2 / 2)
-    float p = fmaf(1.061405429f, t, -1.453152027f);
-    p = fmaf(p, t, 1.421413741f);
-    p = fmaf(p, t, -0.284496736f);
-    p = fmaf(p, t, 0.254829592f);
-    const float tail = 0.5f * p * t * ex;                            // (1 - erf(u)) / 2
+    float p = fmaf(0.5307027145f, t, -0.7265760135f);
+    p = fmaf(p, t, 0.7107068705f);
+    p = fmaf(p, t, -0.142248368f);
+    p = fmaf(p, t, 0.127414796f);
+    const float tail = p * t * ex;                                   // (1 - erf(u)) / 2
     const float cdf = x >= 0.f ? 1.0f - tail : tail;
     y = x * cdf;
     dy = fmaf(x * 0.39894228040143268f, ex, cdf);
