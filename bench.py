@@ -587,7 +587,8 @@ def run_ours(args, w):
 
     W = max(args.warmup, 3)
     if case.vx and case.rotate:
-        W = max(W, 2 * len(case.rotate))       # every distinct mesh batch twice: the allocator has seen all edge counts
+        W = max(W, 4 * len(case.rotate))       # every distinct mesh batch four times: the caching allocator keeps growing
+                                               # (cudaMalloc inside the step) until it has seen every edge-count pattern
     for _ in range(W):
         case.dev_step()
     sampler = ClockSampler(D.local) if rank == 0 else None
