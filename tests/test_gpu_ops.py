@@ -281,7 +281,8 @@ def test_fused_lift_aggregate_and_dot_vs_oracle():
     g = orc.radius_csr(data, q, r)
     E, n, m = g["neighbors_index"].numel(), data.shape[0], q.shape[0]
     plan = ops.GraphPlan(g["neighbors_index"].to(DEV), g["neighbors_row_splits"].to(DEV), n)
-    for C, B, Cin in ((64, 11, 1), (48, 3, 3), (16, 8, 4), (64, 1, 2)):
+    # B a multiple of 8 takes the sample-minor gather (pn_t) for every Cin; the others the per-sample gather
+    for C, B, Cin in ((64, 11, 1), (48, 3, 3), (16, 8, 4), (64, 1, 2), (64, 32, 1), (64, 16, 2), (32, 24, 3)):
         pn, Wl, bl, w = cases.normal((B, n, Cin), 31), cases.normal((C, Cin), 32), cases.normal((C,), 33), cases.normal((E, C), 34)
         ref = [t.double().requires_grad_(True) for t in (Wl, bl, w)]
         f = pn.double() @ ref[0].T + ref[1]
