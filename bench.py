@@ -694,7 +694,7 @@ def run_ours(args, w):
         except Exception as e:
             out["rollout_cfg4"] = {"error": repr(e)}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        out["cpu_baseline"] = cpu_reference(w, steps=2, warmup=1, sample_B=B)
+        out["cpu_baseline"] = (cpu_reference_unmodified if reference_available(w) else cpu_reference)(w, steps=2, warmup=1, sample_B=B)
     if rank == 0:
         print(json.dumps(out), flush=True)
     case = graphed = feeder = step = None      # captured steps hold NCCL work: release them before the communicator goes
@@ -738,6 +738,52 @@ def cpu_reference(w, steps, warmup, sample_B):
             "s_per_step": dt, "batch": sample_B}
 
 
+REFERENCE_ROOT = "/root/reference"
+
+
+def reference_available(w):
+    """The unmodified reference can only be timed where its tree exists (the build container; the GPU box has none) and for
+    fx workloads (its vx path needs the graph containers of its own data pipeline)."""
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, "src", "model")) and not w.get("vx")
+
+
+def cpu_reference_unmodified(w, steps, warmup, sample_B):
+    """The UNMODIFIED reference model (`src.model.gaot.GAOT` imported from /root/reference, CPU, fp32, all host threads) in the
+    reference's own step - zero_grad, forward, MSE, backward, torch.optim.AdamW (optimizers.py:252-255, base_trainer.py:71) -
+    on the workload's mesh and batch.  torch_scatter / omegaconf / rotary_embedding_torch are absent from the image; the
+    import stand-ins of oracle/ref_shims (documented there) replace them, hence kind "reference+shims"."""
+    for pth in (os.path.join(ROOT, "oracle", "ref_shims"), REFERENCE_ROOT):
+        if pth not in sys.path:
+            sys.path.insert(0, pth)
+    from src.model.gaot import GAOT as RefGAOT                      # the reference
+    from src.model.layers.attn import AttentionConfig as RAC, TransformerConfig as RTC
+    from src.model.layers.magno import MAGNOConfig as RMC
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(42)
+    cfg = SimpleNamespace(latent_tokens_size=tuple(w["latent"]), args=SimpleNamespace(
+        magno=RMC(coord_dim=w["d"], radius=w["radius"], hidden_size=w["hidden"], mlp_layers=w["mlp_layers"], lifting_channels=w["C"],
+                  neighbor_search_method="native"),
+        transformer=RTC(patch_size=w["patch"], hidden_size=w["dh"], num_layers=w["layers"],
+                        attn_config=RAC(num_heads=w["heads"], num_kv_heads=w["heads"]))))
+    model = RefGAOT(w["cin"], w["cout"], cfg)
+    model.train()
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=1e-2)
+    lat, x, pn, tgt = synth(w, 0, sample_B)
+    times = []
+    for _ in range(warmup + steps):
+        t0 = time.perf_counter()
+        opt.zero_grad()
+        loss = torch.nn.functional.mse_loss(model(lat, x, pn), tgt)
+        loss.backward()
+        opt.step()
+        times.append(time.perf_counter() - t0)
+    dt = sum(times[warmup:]) / steps
+    return {"value": sample_B * w["n"] / dt, "unit": "points/s", "cores": torch.get_num_threads(), "kind": "reference+shims",
+            "sample": f"{steps} steps of batch {sample_B} of the unmodified reference (src.model.gaot.GAOT + torch.optim.AdamW) after "
+                      f"{warmup} warm-up (the first builds and caches the graphs); {dt:.3f} s/step",
+            "s_per_step": dt, "batch": sample_B}
+
+
 def run_reference(args, w):
     """Reference arm: the reference's own CPU implementation of the path (the oracle port: the reference is pure Python
     with no installable package), all host threads, on OUR arm's config - the same workload, the same
@@ -749,11 +795,13 @@ def run_reference(args, w):
     B = args.batch or w["B"]
     W = max(args.warmup, 3)
     steps = args.steps
-    base = cpu_reference(w, steps=1, warmup=1, sample_B=B)          # probe: seconds per step on this box
+    # the unmodified reference where its tree exists (the build container), else its pinned port (the GPU box has no /root/reference)
+    ref_fn = cpu_reference_unmodified if reference_available(w) else cpu_reference
+    base = ref_fn(w, steps=1, warmup=1, sample_B=B)                 # probe: seconds per step on this box
     budget = 150.0                                                  # seconds for the timed region + warm-up
     fit = max(1, int(budget / max(base["s_per_step"], 1e-3)) - W)
     timed_steps = min(steps, fit)
-    base = cpu_reference(w, steps=timed_steps, warmup=W, sample_B=B)
+    base = ref_fn(w, steps=timed_steps, warmup=W, sample_B=B)
     if timed_steps < steps:
         base["sample"] += f"; {timed_steps} of the requested {steps} steps timed (bounded to ~{budget:.0f} s), per-step time reported"
     out = {"impl": "reference", "metric": "mesh-points/sec fwd+bwd", "value": base["value"], "unit": "points/s",
