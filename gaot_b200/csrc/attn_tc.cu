@@ -283,8 +283,9 @@ __device__ __forceinline__ void sts_u4_(uint32_t a, uint32_t x, uint32_t y, uint
 // The running maximum is only raised when the new row maximum exceeds it by more than 2^8 (lazy rescaling): the O
 // accumulator is then rescaled in place in TMEM (tcgen05.ld / st); otherwise P is formed against the stale maximum, which
 // is exact after the final division by the row sum.  No per-tile read-back of O.
+// (hd = 64: the 144 KB tile set leaves room for one CTA per SM anyway, so the register cap of two would only cost spills)
 template <int HD, bool SPLIT>
-__global__ void __launch_bounds__(AT_THREADS, SPLIT ? 1 : 2)
+__global__ void __launch_bounds__(AT_THREADS, (SPLIT || HD > 32) ? 1 : 2)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttnArgs g) {
     constexpr int ROWB = HD * 2;                         // bytes per head row = swizzle span
     constexpr int NPL = SPLIT ? 2 : 1;                   // planes per operand tile (hi, lo)
