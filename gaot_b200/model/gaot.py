@@ -79,10 +79,9 @@ class GAOT(nn.Module):
                     raise ValueError(f"absolute positional embedding width {pe.shape[1]} != patch dim {Dp}")
                 self._pos_emb = pe.contiguous()
             add = self._pos_emb
-        elif self.positional_embedding_name == "rope":
-            raise NotImplementedError("positional_embedding='rope' is not on the accelerated path")
+        relative_positions = self.positions if self.positional_embedding_name == "rope" else None       # gaot.py:217-218
         x = ops.linear(x.view(B * T, Dp), self.patch_linear.weight, self.patch_linear.bias, add=add, tc=True).view(B, T, Dp)
-        x = self.processor(x, condition=condition, relative_positions=None)
+        x = self.processor(x, condition=condition, relative_positions=relative_positions)
         return ops.unpatchify(x, grid, P, C)
 
     def decode(self, latent_tokens_coord, rndata, query_coord, decoder_nbrs):

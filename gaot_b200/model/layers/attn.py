@@ -65,8 +65,8 @@ class GroupQueryFlashAttention(nn.Module):
         super().__init__()
         assert hidden_size % num_heads == 0, f"hidden_size {hidden_size} must be divisible by num_heads {num_heads}"
         assert num_heads % num_kv_heads == 0, f"num_heads {num_heads} must be divisible by num_kv_heads {num_kv_heads}"
-        if positional_embedding == "rope":
-            raise NotImplementedError("positional_embedding='rope' is not on the accelerated path")
+        # 'rope' (attn.py:75-76, 106-108): q and k are rotated by the token position before the attention (ops.rope_qk)
+        self.use_rope = positional_embedding == "rope"
         if atten_dropout:
             raise NotImplementedError("attention dropout is not on the accelerated path")
         self.num_heads, self.num_kv_heads = num_heads, num_kv_heads
@@ -103,6 +103,8 @@ class GroupQueryFlashAttention(nn.Module):
         self._wqkv = None
         tc_attn = ops.get_precision() == "bf16" and self.head_dim in (16, 32, 64) and D % 8 == 0
         qkv = ops.linear(x.reshape(B * T, D), wqkv, tc=True, out_bf16=tc_attn)
+        if relative_positions is not None and self.use_rope:
+            qkv = ops.rope_qk(qkv, B, T, self.num_heads, self.num_kv_heads, self.head_dim)
         o = ops.attention(qkv, B, T, self.num_heads, self.num_kv_heads, self.head_dim)
         add = residual.reshape(B * T, -1) if residual is not None else None
         return ops.linear(o, self.o_proj.weight, None, add=add, tc=True).view(B, T, -1)

@@ -766,6 +766,32 @@ class _AttentionSplit(torch.autograd.Function):
         return dqkv, None, None, None, None, None
 
 
+_ROPE_TABLES = {}
+
+
+def rope_tables(T: int, hd: int, device):
+    """cos / sin [T, hd] (fp32) of rotary-embedding-torch's default `RotaryEmbedding(dim=hd)` (reference attn.py:76, 106-108):
+    angle(t, i) = t / 10000^(2i / hd), shared by the interleaved pair (2i, 2i + 1); cached per (T, hd, device)."""
+    key = (T, hd, str(device))
+    if key not in _ROPE_TABLES:
+        inv = 1.0 / (10000 ** (torch.arange(0, hd, 2)[: hd // 2].float() / hd))
+        ang = (torch.arange(T, dtype=torch.float32)[:, None] * inv[None, :]).repeat_interleave(2, dim=-1)
+        _ROPE_TABLES[key] = (ang.cos().to(device), ang.sin().to(device))
+    return _ROPE_TABLES[key]
+
+
+def rope_qk(qkv, B, T, H, Hkv, hd):
+    """Rotates the query and key heads of the fused qkv matrix [B*T, (H + 2 Hkv) * hd] by the token position (RoPE,
+    positional_embedding='rope'); values pass through.  Plain differentiable torch ops in fp32 (an option outside the
+    benchmarked configurations); the result keeps qkv's dtype and layout for the attention kernels."""
+    cos, sin = rope_tables(T, hd, qkv.device)
+    W = (H + Hkv) * hd
+    x = qkv[:, :W].float().reshape(B, T, H + Hkv, hd)
+    rot = torch.stack((-x[..., 1::2], x[..., 0::2]), dim=-1).reshape(x.shape)       # rotate_half on interleaved pairs
+    y = x * cos[None, :, None, :] + rot * sin[None, :, None, :]
+    return torch.cat([y.reshape(B * T, W).to(qkv.dtype), qkv[:, W:]], dim=1).contiguous()
+
+
 def attention(qkv, B, T, H, Hkv, hd):
     if qkv.dtype == torch.bfloat16:
         return _AttentionTC.apply(qkv, B, T, H, Hkv, hd)

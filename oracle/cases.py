@@ -96,6 +96,12 @@ CASES = {
                                transform_type="linear_kernelonly", use_attention=False, neighbor_search_method="native"),
                     transformer=dict(patch_size=2, hidden_size=64, num_layers=1, ffn_multiplier=2),
                     attn=dict(num_heads=2, num_kv_heads=2)),
+    # rotary position embedding instead of the absolute table (attn.py:75-76, 106-108, gaot.py:217-218); GQA 4 / 2 heads
+    "rope2d": dict(latent=(8, 8), n=300, d=2, B=2, cin=2, cout=1, seed=11,
+                   magno=dict(coord_dim=2, radius=0.35, hidden_size=16, mlp_layers=2, lifting_channels=16,
+                              neighbor_search_method="native"),
+                   transformer=dict(patch_size=2, hidden_size=64, num_layers=2, ffn_multiplier=2, positional_embedding="rope"),
+                   attn=dict(num_heads=4, num_kv_heads=2)),
     # BASELINE cfg-2 geometry (Poisson-Gauss hyper-parameters, config/examples/time_indep/poisson_gauss.json)
     "cfg2": dict(latent=(64, 64), n=9216, d=2, B=2, cin=1, cout=1, seed=0, summary_only=True,
                  magno=dict(coord_dim=2, radius=0.033, hidden_size=64, mlp_layers=3, lifting_channels=64,

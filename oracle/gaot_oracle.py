@@ -355,8 +355,19 @@ def conditioned_norm(p, prefix, c, x):
     return x * scale[:, None, :] + bias[:, None, :]
 
 
-def attention(p, prefix, x, num_heads, num_kv_heads, condition=None):
-    """GroupQueryFlashAttention.forward (attn.py:78-119), non-causal, dropout 0."""
+def rotary(t):
+    """`RotaryEmbedding(dim=head_dim).rotate_queries_or_keys(t)` of the un-vendored rotary-embedding-torch wheel (attn.py:76,
+    106-108) on [b, heads, seq, hd], library defaults: angle(pos, i) = pos / 10000^(2i / hd) shared by the pair (2i, 2i + 1),
+    (x1, x2) -> (x1 cos - x2 sin, x2 cos + x1 sin)."""
+    hd, T = t.shape[-1], t.shape[-2]
+    inv = 1.0 / (10000 ** (torch.arange(0, hd, 2)[: hd // 2].float() / hd))
+    ang = (torch.arange(T, dtype=inv.dtype)[:, None] * inv[None, :]).repeat_interleave(2, dim=-1).to(t.dtype)
+    rot = torch.stack((-t[..., 1::2], t[..., 0::2]), dim=-1).reshape(t.shape)
+    return t * ang.cos() + rot * ang.sin()
+
+
+def attention(p, prefix, x, num_heads, num_kv_heads, condition=None, rope=False):
+    """GroupQueryFlashAttention.forward (attn.py:78-119), non-causal, dropout 0; rope: positional_embedding='rope'."""
     if f"{prefix}.correction.mlp_scale.layers.0.weight" in p:        # attn.py:89-90
         x = conditioned_norm(p, f"{prefix}.correction", condition, x)
     b, t, _ = x.shape
@@ -370,6 +381,8 @@ def attention(p, prefix, x, num_heads, num_kv_heads, condition=None):
     if num_kv_heads != num_heads:
         k = k.repeat_interleave(num_heads // num_kv_heads, dim=1)
         v = v.repeat_interleave(num_heads // num_kv_heads, dim=1)
+    if rope:                                              # attn.py:106-108
+        q, k = rotary(q), rotary(k)
     o = F.scaled_dot_product_attention(q, k, v)           # attn.py:114 (non-causal, scale 1/sqrt(hd), dropout 0)
     o = o.transpose(1, 2).contiguous().view(b, t, -1)
     return F.linear(o, p[f"{prefix}.o_proj.weight"])
@@ -391,7 +404,8 @@ def transformer_block(p, prefix, tc, x, skip=None, condition=None):
     if skip is not None and f"{prefix}.skip_proj.weight" in p:
         x = F.linear(torch.cat([x, skip], dim=-1), p[f"{prefix}.skip_proj.weight"], p[f"{prefix}.skip_proj.bias"])
     h = rmsnorm(x, p[f"{prefix}.attn_norm.weight"], tc.norm_eps) if tc.use_attn_norm else x
-    h = x + attention(p, f"{prefix}.attn", h, ac.num_heads, ac.num_kv_heads, condition)
+    h = x + attention(p, f"{prefix}.attn", h, ac.num_heads, ac.num_kv_heads, condition,
+                      rope=getattr(tc, "positional_embedding", "absolute") == "rope")
     h = rmsnorm(h, p[f"{prefix}.ffn_norm.weight"], tc.norm_eps) if tc.use_ffn_norm else h
     return h + ffn(p, f"{prefix}.ffn", h, condition)
 
@@ -457,7 +471,8 @@ def process(p, cfg, rndata, condition=None):
     ls = tuple(cfg.latent_tokens_size)
     x = patchify(rndata, ls, P)
     x = F.linear(x, p["patch_linear.weight"], p["patch_linear.bias"])
-    x = x + absolute_pos_emb([g // P for g in ls], x.shape[-1], x.dtype)
+    if getattr(tc, "positional_embedding", "absolute") == "absolute":    # gaot.py:212-218 ('rope' rotates q / k inside the attention)
+        x = x + absolute_pos_emb([g // P for g in ls], x.shape[-1], x.dtype)
     x = transformer(p, "processor", tc, x, condition)
     return unpatchify(x, ls, P, c)
 

@@ -56,7 +56,7 @@ def _run(name, use_golden_graphs, fuse=True):
 @pytest.mark.parametrize("fuse", [True, False])
 @pytest.mark.parametrize("name,golden_graph", [("tiny2d", False), ("tiny2d", True), ("tiny3d", False),
                                                ("plain2d", False), ("vx2d", True), ("dot2d", False), ("npe2d", False), ("pnet2d", False),
-                                               ("cond2d", False), ("vxmix", True), ("konly2d", False)])
+                                               ("cond2d", False), ("vxmix", True), ("konly2d", False), ("rope2d", False)])
 def test_forward_backward_matches_reference(name, golden_graph, fuse, parity_mode):
     c, g, model, out, loss, inter = _run(name, golden_graph, fuse)
     assert rel_l2(inter["enc_out"], g["enc_out"]) < FWD_TOL

@@ -316,7 +316,7 @@ def test_attention_split_fwd_bwd_vs_fp64(B, T, H, Hkv, hd, gscale):
 BF16_FWD_TOL, BF16_GRAD_TOL = 2e-2, 3e-2      # bf16 operands (8 mantissa bits) at every processor GEMM / attention input
 
 
-@pytest.mark.parametrize("name", ["vx2d", "dot2d", "pnet2d", "cond2d", "npe2d", "plain2d", "vxmix", "konly2d"])
+@pytest.mark.parametrize("name", ["vx2d", "dot2d", "pnet2d", "cond2d", "npe2d", "plain2d", "vxmix", "konly2d", "rope2d"])
 def test_model_bf16_mode_option_cases(name):
     from gaot_b200 import ops
     from tests.helpers import golden_graphs, graphs_to

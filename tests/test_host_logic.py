@@ -53,7 +53,7 @@ def test_nothing_in_the_product_imports_the_oracle():
 
 @pytest.mark.parametrize("precision", ["fp32", "ffma"])
 @pytest.mark.parametrize("fuse", [True, False])
-@pytest.mark.parametrize("name", ["tiny2d", "tiny3d", "plain2d", "vx2d", "dot2d", "npe2d", "pnet2d", "cond2d", "vxmix", "konly2d"])
+@pytest.mark.parametrize("name", ["tiny2d", "tiny3d", "plain2d", "vx2d", "dot2d", "npe2d", "pnet2d", "cond2d", "vxmix", "konly2d", "rope2d"])
 def test_model_wiring_matches_reference_golden(name, fuse, precision):
     """Both parity modes through the emulated ABI: 'fp32' = split-precision tensor-core entry points (the emulator forms
     the same fp16 hi / lo planes and the same three product terms as the kernels), 'ffma' = plain fp32 entry points."""

@@ -7,7 +7,7 @@ import torch
 from oracle import cases, gaot_oracle as orc
 from tests.helpers import golden_graphs, golden_params, golden_shapes, grad_rel, grad_scale, load_golden, rel_l2
 
-FULL = ["tiny2d", "tiny3d", "vx2d", "plain2d", "dot2d", "npe2d", "pnet2d", "cond2d", "vxmix", "konly2d"]
+FULL = ["tiny2d", "tiny3d", "vx2d", "plain2d", "dot2d", "npe2d", "pnet2d", "cond2d", "vxmix", "konly2d", "rope2d"]
 
 
 def _cfg(name):
